@@ -1,0 +1,209 @@
+"""Second, independent restatement of the MVRenderer arithmetic in plain torch (autograd-capable,
+dtype-generic).  TEST INFRASTRUCTURE ONLY -- same import rules as oracle/oracle.py.
+
+Purpose: (1) cross-check the C oracle (two independent restatements of an unpinned spec);
+(2) validate every hand-derived backward (C oracle and CUDA) against torch.autograd, typically in
+float64.  Follows the *python* layer of PyTorch3D v0.7 [upstream, not on disk]: renderer/cameras.py,
+renderer/mesh/shading.py, renderer/lighting.py, renderer/blending.py, renderer/points/renderer.py,
+renderer/compositing.py, structures/meshes.py -- as called from models/renderer.py:65-151.
+
+Vectorised O(P*F) -- small sizes only.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+K_EPS = 1e-8
+
+
+def pix_centers(S, dtype=torch.float32):
+    """NDC coordinate of pixel index i (0 = top row / left column): +Y up, +X left."""
+    i = torch.arange(S, dtype=dtype)
+    return -1.0 + (2.0 * (S - 1 - i) + 1.0) / S
+
+
+def look_at_view_transform(dist, elev, azim):
+    """[upstream] cameras.look_at_view_transform with at=0, up=(0,1,0), degrees=True.  -> R, T, C"""
+    e = math.pi / 180.0 * elev
+    a = math.pi / 180.0 * azim
+    C = torch.stack([dist * torch.cos(e) * torch.sin(a), dist * torch.sin(e), dist * torch.cos(e) * torch.cos(a)], dim=1)
+    up = torch.zeros_like(C); up[:, 1] = 1
+    z = F.normalize(-C, eps=1e-5)
+    x = F.normalize(torch.cross(up, z, dim=1), eps=1e-5)
+    y = F.normalize(torch.cross(z, x, dim=1), eps=1e-5)
+    close = (x.abs() <= 5e-3).all(dim=1, keepdim=True)
+    if close.any():
+        x = torch.where(close, F.normalize(torch.cross(y, z, dim=1), eps=1e-5), x)
+    R = torch.stack([x, y, z], dim=2)  # columns
+    T = -torch.bmm(R.transpose(1, 2), C[:, :, None])[:, :, 0]
+    return R, T, C
+
+
+def fov_k(fov_deg=60.0, znear=1.0, dtype=torch.float32):
+    """[upstream] FoVPerspectiveCameras.compute_projection_matrix K00 = K11 (aspect 1), as fp32 ops."""
+    fov = torch.tensor(fov_deg, dtype=dtype) * (math.pi / 180.0)
+    max_y = torch.tan(fov / 2) * znear
+    return float(2.0 * znear / (max_y - (-max_y)))
+
+
+def project_perspective(verts, R, T, k00, k11):
+    """verts (V,3), R (3,3), T (3) -> (V,3) = (x_ndc, y_ndc, z_view)."""
+    p = verts @ R + T
+    return torch.stack([p[:, 0] * k00 / p[:, 2], p[:, 1] * k11 / p[:, 2], p[:, 2]], dim=1)
+
+
+def _edge(px, py, ax, ay, bx, by):
+    return (px - ax) * (by - ay) - (py - ay) * (bx - ax)
+
+
+def bary_coords(px, py, fv, perspective_correct):
+    """px,py (...,) ; fv (...,3,3) -> bary (...,3) following geometry_utils.h."""
+    x0, y0, z0 = fv[..., 0, 0], fv[..., 0, 1], fv[..., 0, 2]
+    x1, y1, z1 = fv[..., 1, 0], fv[..., 1, 1], fv[..., 1, 2]
+    x2, y2, z2 = fv[..., 2, 0], fv[..., 2, 1], fv[..., 2, 2]
+    area = _edge(x2, y2, x0, y0, x1, y1) + K_EPS
+    w0 = _edge(px, py, x1, y1, x2, y2) / area
+    w1 = _edge(px, py, x2, y2, x0, y0) / area
+    w2 = _edge(px, py, x0, y0, x1, y1) / area
+    if perspective_correct:
+        t0, t1, t2 = w0 * z1 * z2, w1 * z0 * z2, w2 * z0 * z1
+        den = (t0 + t1 + t2).clamp_min(K_EPS)
+        w0, w1, w2 = t0 / den, t1 / den, t2 / den
+    return torch.stack([w0, w1, w2], dim=-1)
+
+
+def rasterize_meshes_naive(face_verts, H, W, K=1, perspective_correct=True, cull_backfaces=False):
+    """One view.  face_verts (F,3,3) -> pix_to_face (H,W,K) long, zbuf (H,W,K), bary (H,W,K,3)."""
+    dt = face_verts.dtype
+    yf = pix_centers(H, dt)[:, None, None]
+    xf = pix_centers(W, dt)[None, :, None]
+    fv = face_verts[None, None]
+    b = bary_coords(xf, yf, fv, perspective_correct)            # (H,W,F,3)
+    x, y, z = face_verts[..., 0], face_verts[..., 1], face_verts[..., 2]
+    area = _edge(x[:, 0], y[:, 0], x[:, 1], y[:, 1], x[:, 2], y[:, 2])
+    ok = ~((area <= K_EPS) & (area >= -K_EPS))
+    if cull_backfaces:
+        ok &= ~(area < 0)
+    ok &= ~(z.min(dim=1).values < K_EPS)
+    inbox = (xf <= x.max(1).values) & (xf >= x.min(1).values) & (yf <= y.max(1).values) & (yf >= y.min(1).values)
+    pz = (b * z[None, None]).sum(-1)
+    hit = ok[None, None] & inbox & (b > 0).all(-1) & ~(pz < 0)
+    key = torch.where(hit, pz, torch.full_like(pz, float("inf")))
+    # stable sort by z then index == lexicographic (z, idx)
+    order = torch.sort(key, dim=-1, stable=True)
+    idx = order.indices[..., :K]
+    zs = order.values[..., :K]
+    if idx.shape[-1] < K:
+        pad = K - idx.shape[-1]
+        idx = torch.cat([idx, idx.new_zeros(H, W, pad)], -1)
+        zs = torch.cat([zs, zs.new_full((H, W, pad), float("inf"))], -1)
+    valid = torch.isfinite(zs)
+    p2f = torch.where(valid, idx, torch.full_like(idx, -1))
+    bsel = torch.gather(b, 2, idx.clamp_min(0)[..., None].expand(H, W, K, 3))
+    zbuf = torch.where(valid, zs, torch.full_like(zs, -1.0))
+    bary = torch.where(valid[..., None], bsel, torch.full_like(bsel, -1.0))
+    return p2f, zbuf, bary
+
+
+def vertex_normals(verts, faces):
+    """[upstream] Meshes._compute_vertex_normals (v0.7 form)."""
+    vf = verts[faces]
+    fn = torch.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1], dim=1)
+    vn = torch.zeros_like(verts)
+    vn = vn.index_add(0, faces[:, 0], fn).index_add(0, faces[:, 1], fn).index_add(0, faces[:, 2], fn)
+    return F.normalize(vn, eps=1e-6, dim=1)
+
+
+def phong_shade(bary, p2f, verts, faces, normals, vert_rgb, light_dir, cam_center, bg,
+                ambient=0.5, diffuse=0.3, specular=0.2, shininess=64):
+    """bary (H,W,3), p2f (H,W) for k=0.  -> (3,H,W).  phong_shading + hard_rgb_blend."""
+    fg = p2f >= 0
+    f = p2f.clamp_min(0)
+    fvx = verts[faces][f]          # (H,W,3,3)
+    fnr = normals[faces][f]
+    fcl = vert_rgb[faces][f]
+    P = (bary[..., None] * fvx).sum(-2)
+    Nn = (bary[..., None] * fnr).sum(-2)
+    tex = (bary[..., None] * fcl).sum(-2)
+    n = F.normalize(Nn, p=2, dim=-1, eps=1e-6)
+    l = F.normalize(light_dir.expand_as(n), p=2, dim=-1, eps=1e-6)
+    cosang = (n * l).sum(-1)
+    diff = F.relu(cosang)
+    mask = (cosang > 0).to(bary.dtype)
+    v = F.normalize(cam_center - P, p=2, dim=-1, eps=1e-6)
+    r = -l + 2 * (cosang[..., None] * n)
+    alpha = F.relu((v * r).sum(-1)) * mask
+    col = (ambient + diffuse * diff)[..., None] * tex + (specular * torch.pow(alpha, shininess))[..., None]
+    out = torch.where(fg[..., None], col, bg.expand_as(col))
+    return out.permute(2, 0, 1)
+
+
+def render_mesh_view(verts, faces, normals, vert_rgb, R, T, Cc, light_dir, bg, k00, k11, H, W,
+                     perspective_correct=True, cull_backfaces=False, p2f=None):
+    """Differentiable single-view mesh render (K=1).  If p2f is given the raster step is skipped
+    and barycentrics are recomputed differentiably from the face ids (that is what autograd does
+    through _RasterizeFaceVerts: the index is a constant)."""
+    ndc = project_perspective(verts, R, T, k00, k11)
+    fv = ndc[faces]
+    if p2f is None:
+        with torch.no_grad():
+            p2f, _, _ = rasterize_meshes_naive(fv, H, W, 1, perspective_correct, cull_backfaces)
+        p2f = p2f[..., 0]
+    yf = pix_centers(H, verts.dtype)[:, None].expand(H, W)
+    xf = pix_centers(W, verts.dtype)[None, :].expand(H, W)
+    b = bary_coords(xf, yf, fv[p2f.clamp_min(0)], perspective_correct)
+    img = phong_shade(b, p2f, verts, faces, normals, vert_rgb, light_dir, Cc, bg)
+    return img, p2f
+
+
+def rasterize_points_naive(pts, radius, H, W, K):
+    """One view.  pts (P,3) ndc -> idx (H,W,K) long, zbuf, dists2."""
+    dt = pts.dtype
+    yf = pix_centers(H, dt)[:, None, None]
+    xf = pix_centers(W, dt)[None, :, None]
+    dx = pts[None, None, :, 0] - xf
+    dy = pts[None, None, :, 1] - yf
+    d2 = dx * dx + dy * dy
+    r2 = torch.tensor(radius, dtype=dt) * torch.tensor(radius, dtype=dt)
+    hit = (d2 < r2) & ~(pts[None, None, :, 2] < 0)
+    key = torch.where(hit, pts[None, None, :, 2].expand_as(d2), torch.full_like(d2, float("inf")))
+    order = torch.sort(key, dim=-1, stable=True)
+    idx = order.indices[..., :K]; zs = order.values[..., :K]
+    if idx.shape[-1] < K:
+        pad = K - idx.shape[-1]
+        idx = torch.cat([idx, idx.new_zeros(H, W, pad)], -1)
+        zs = torch.cat([zs, zs.new_full((H, W, pad), float("inf"))], -1)
+    valid = torch.isfinite(zs)
+    d2s = torch.gather(d2, 2, idx)
+    return (torch.where(valid, idx, torch.full_like(idx, -1)), torch.where(valid, zs, torch.full_like(zs, -1.0)),
+            torch.where(valid, d2s, torch.full_like(d2s, -1.0)))
+
+
+def composite(idx, alphas, feats, alpha_mode):
+    """idx/alphas (K,H,W), feats (3,P) -> (3,H,W).  [upstream] compositing.{norm_weighted_sum,alpha_composite}."""
+    valid = (idx >= 0).to(alphas.dtype)
+    f = feats[:, idx.clamp_min(0)]                  # (3,K,H,W)
+    a = alphas * valid
+    if alpha_mode:
+        one_minus = torch.where(idx >= 0, 1 - alphas, torch.ones_like(alphas))
+        cum = torch.cumprod(torch.cat([torch.ones_like(one_minus[:1]), one_minus[:-1]], 0), 0)
+        return (f * (a * cum)[None]).sum(1)
+    t = a.sum(0).clamp_min(1e-4)
+    return (f * a[None]).sum(1) / t[None]
+
+
+def render_points_view(pts_world, feats, R, T, inv_dist, radius, bg, H, W, K, alpha_mode, idx=None):
+    """Differentiable single-view point render: (X/d) R + T, orthographic, compositor, background."""
+    p = (pts_world * inv_dist) @ R + T
+    if idx is None:
+        with torch.no_grad():
+            idx, _, _ = rasterize_points_naive(p, radius, H, W, K)
+    yf = pix_centers(H, p.dtype)[:, None, None]
+    xf = pix_centers(W, p.dtype)[None, :, None]
+    sel = p[idx.clamp_min(0)]                       # (H,W,K,3)
+    d2 = (sel[..., 0] - xf) ** 2 + (sel[..., 1] - yf) ** 2
+    w = 1 - d2 / (radius * radius)
+    img = composite(idx.permute(2, 0, 1), w.permute(2, 0, 1), feats, alpha_mode)
+    fg = (idx[..., 0] >= 0)[None]
+    return torch.where(fg, img, bg[:, None, None].expand_as(img)), idx
