@@ -1,0 +1,134 @@
+/*
+ * mvr_b200.h -- C ABI of libmvr_b200.so: the sm_100a implementation of MVTN's MVRenderer hot path.
+ *
+ * Boundary.  The reference (ajhamdi/MVTN, Python) reaches its native code through PyTorch3D's
+ * `pytorch3d._C` extension; the entry points below are what a maintainer would bind with ctypes
+ * in place of those calls.  Each function cites the reference call site /
+ * upstream operator it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless the comment says "host";
+ *  - fp32 / int32 unless stated; row-major, innermost dimension last;
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream, does
+ *    no host synchronisation and no allocation (scratch comes from the caller's workspace);
+ *  - return value: 0 ok; <0 invalid argument (see mvr_last_error_string); >0 a cudaError_t;
+ *  - view n = b*M + m (flat order of util.py:509-534 batch_tensor / Meshes.extend(M));
+ *  - R (n,3,3), T (n,3): PyTorch3D row-vector convention X_view = X_world R + T.
+ *  - arithmetic contract for fragments: IEEE fp32, written operation order, no FMA contraction
+ *    (DESIGN.md "Parity"), so pix_to_face / idx agree bit-for-bit with oracle/mvr_oracle.c.
+ */
+#ifndef MVR_B200_H
+#define MVR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVR_ABI_VERSION 1
+
+/* flags */
+#define MVR_PERSPECTIVE_CORRECT 1  /* [upstream] RasterizationSettings.perspective_correct (FoV persp.: True) */
+#define MVR_CULL_BACKFACES 2       /* renderer.py:52,97 cull_backfaces */
+#define MVR_COMPOSITE_ALPHA 4      /* AlphaCompositor instead of NormWeightedCompositor (renderer.py:11,138) */
+#define MVR_RGB_PER_ELEMENT 8      /* per-vertex / per-point colours (object_color == "custom") */
+#define MVR_FACES_I64 16           /* faces given as int64 (F,3) -- the reference's layout, renderer.py:68 */
+
+/* Phong constants of DirectionalLights() / Materials() as constructed at renderer.py:190-191 */
+#define MVR_AMBIENT 0.5f
+#define MVR_DIFFUSE 0.3f
+#define MVR_SPECULAR 0.2f
+#define MVR_SHININESS 64
+
+/* counters[] slots written by the forward calls (device int64[MVR_NUM_COUNTERS], accumulated) */
+#define MVR_CNT_STRADDLE 0     /* faces straddling the near clip plane (rasterized unclipped) */
+#define MVR_CNT_BIN_OVERFLOW 1 /* bin chunks that took the unbinned fallback (correct, slower) */
+#define MVR_CNT_BIN_ENTRIES 2  /* total (face, tile) entries produced by the coarse pass */
+#define MVR_NUM_COUNTERS 4
+
+int mvr_abi_version(void);
+/* thread-local description of the last non-zero return value (host string) */
+const char* mvr_last_error_string(void);
+
+/* -- cameras ------------------------------------------------------------------------------ */
+/* look_at_view_transform(dist, elev, azim) + camera_position_from_spherical_angles
+ * (renderer.py:79-80,122-123,168; ops.py:160) fused with util.py:403-420
+ * check_valid_rotation_matrix: *invalid_count += number of matrices failing the check.
+ * azim/elev in degrees, n = B*M.  C (n,3) = camera centres (may be NULL). */
+int mvr_look_at_forward(const float* azim, const float* elev, const float* dist, int n, float* R,
+                        float* T, float* C, int* invalid_count, void* stream);
+/* autograd backward of the above: (gR, gT, gC) -> (g_azim, g_elev, g_dist); any g* input may be NULL */
+int mvr_look_at_backward(const float* azim, const float* elev, const float* dist, int n,
+                         const float* gR, const float* gT, const float* gC, float* g_azim,
+                         float* g_elev, float* g_dist, void* stream);
+
+/* -- meshes ------------------------------------------------------------------------------- */
+/* Device-resident packed geometry built once per batch of objects (replaces Meshes(...),
+ * Textures(verts_rgb) and verts_normals_packed(): renderer.py:67-77 + [upstream] meshes.py). */
+size_t mvr_mesh_geometry_bytes(int64_t total_verts, int64_t total_faces);
+/* verts (Vtot,3); faces (Ftot,3) int32 or int64 [MVR_FACES_I64], mesh-local vertex ids;
+ * vert_off / face_off (B+1) int32 prefix sums (device); vert_rgb (Vtot,3) or NULL. */
+int mvr_mesh_prepare(const float* verts, const void* faces, const int* vert_off, const int* face_off,
+                     int B, int64_t total_verts, int64_t total_faces, int max_faces,
+                     const float* vert_rgb, int flags, void* geometry, size_t geometry_bytes,
+                     void* stream);
+/* copy of the per-vertex unit normals (Vtot,3) out of a prepared geometry (tests / callers) */
+int mvr_mesh_get_normals(const void* geometry, int64_t total_verts, int64_t total_faces,
+                         float* normals, void* stream);
+
+size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int64_t total_faces, int max_faces);
+/* MeshRenderer(MeshRasterizer, HardPhongShader)(meshes.extend(M), cameras, lights)
+ * (renderer.py:89-113; [upstream] _C.rasterize_meshes + interp_face_attrs + phong_shading +
+ * hard_rgb_blend).  blur_radius = 0.
+ *   Cc (n,3) camera centres; light (1,3) if light_stride == 0 else (n,3) with stride 3;
+ *   obj_rgb (3) uniform colour (ignored when the geometry holds per-vertex colours); bg_rgb (3);
+ *   k00,k11: FoV projection scale (1/tan(fov/2)); z_clip < 0 disables the near-plane cull;
+ *   K = faces_per_pixel.
+ * outputs: images (n,3,H,W); pix_to_face (n,H,W,K) view-local face ids, -1 empty;
+ *          optional zbuf (n,H,W,K), bary (n,H,W,K,3), dists (n,H,W,K) (NULL to skip);
+ *          counters: device int64[MVR_NUM_COUNTERS] or NULL. */
+int mvr_mesh_forward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
+                     int64_t total_verts, int64_t total_faces, int max_faces, const float* R,
+                     const float* T, const float* Cc, const float* light, int light_stride,
+                     const float* obj_rgb, const float* bg_rgb, float k00, float k11, float z_clip,
+                     int H, int W, int K, int flags, float* images, int* pix_to_face, float* zbuf,
+                     float* bary, float* dists, int64_t* counters, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* backward of the above w.r.t. the cameras ([upstream] _C.rasterize_meshes_backward + autograd
+ * of shading/projection): grad_images (n,3,H,W) -> gR (n,3,3), gT (n,3), gC (n,3);
+ * optional grad_verts (Vtot,3) (projection + interpolated-position paths) and grad_normals
+ * (Vtot,3) (gradient w.r.t. the per-vertex unit normals), both ACCUMULATED with atomics
+ * (caller zero-fills). */
+int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
+                      int64_t total_verts, int64_t total_faces, const float* R, const float* T,
+                      const float* Cc, const float* light, int light_stride, const float* obj_rgb,
+                      float k00, float k11, int H, int W, int K, int flags, const int* pix_to_face,
+                      const float* grad_images, float* gR, float* gT, float* gC, float* grad_verts,
+                      float* grad_normals, void* workspace, size_t workspace_bytes, void* stream);
+
+/* -- point clouds --------------------------------------------------------------------------- */
+size_t mvr_points_workspace_bytes(int B, int M, int H, int W, int K);
+/* PointsRenderer(PointsRasterizer, compositor)(Pointclouds.extend(M).scale_(1/dist))
+ * (renderer.py:119-150; [upstream] _C.rasterize_points + accum_weightedsumnorm /
+ * accum_alphacomposite + background).  points (B,Np,3); rgb (3) or (B*Np,3) [MVR_RGB_PER_ELEMENT];
+ * inv_dist (n) = 1/dist; radius in NDC; K = points_per_pixel.
+ * outputs: images (n,3,H,W); idx (n,H,W,K) cloud-local point ids (-1 empty); optional zbuf,
+ * dists2 (n,H,W,K). */
+int mvr_points_forward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
+                       const float* T, const float* inv_dist, double radius, const float* bg_rgb,
+                       int H, int W, int K, int flags, float* images, int* idx, float* zbuf,
+                       float* dists2, void* workspace, size_t workspace_bytes, void* stream);
+/* backward ([upstream] accum_*_backward + _C.rasterize_points_backward + autograd of the
+ * projection): grad_images -> gR (n,3,3), gT (n,3), g_inv_dist (n); optional grad_points
+ * (B,Np,3) and grad_rgb ((3) or (B*Np,3)) ACCUMULATED with atomics (caller zero-fills). */
+int mvr_points_backward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
+                        const float* T, const float* inv_dist, double radius, int H, int W, int K,
+                        int flags, const int* idx, const float* grad_images, float* gR, float* gT,
+                        float* g_inv_dist, float* grad_points, float* grad_rgb, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVR_B200_H */

@@ -1,0 +1,70 @@
+"""ctypes binding of libmvr_b200.so (include/mvr_b200.h).  Fails loudly: there is no CPU fallback."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmvr_b200.so")
+
+ABI_VERSION = 1
+PERSPECTIVE_CORRECT = 1
+CULL_BACKFACES = 2
+COMPOSITE_ALPHA = 4
+RGB_PER_ELEMENT = 8
+FACES_I64 = 16
+CNT_STRADDLE, CNT_BIN_OVERFLOW, CNT_BIN_ENTRIES, NUM_COUNTERS = 0, 1, 2, 4
+
+_vp, _i, _f, _d, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int64, C.c_size_t
+
+# name -> (restype, argtypes): exactly the declarations of include/mvr_b200.h
+SIGNATURES = {
+    "mvr_abi_version": (_i, []),
+    "mvr_last_error_string": (C.c_char_p, []),
+    "mvr_look_at_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "mvr_look_at_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvr_mesh_geometry_bytes": (_sz, [_i64, _i64]),
+    "mvr_mesh_prepare": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _i, _vp, _sz, _vp]),
+    "mvr_mesh_get_normals": (_i, [_vp, _i64, _i64, _vp, _vp]),
+    "mvr_mesh_workspace_bytes": (_sz, [_i, _i, _i, _i, _i64, _i]),
+    "mvr_mesh_forward": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _f, _f,
+                              _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mvr_mesh_backward": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _vp, _vp, _i, _vp, _f, _f, _i, _i, _i, _i,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mvr_points_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "mvr_points_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _d, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
+                                _vp, _sz, _vp]),
+    "mvr_points_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _d, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _vp, _sz, _vp]),
+}
+
+_lib = None
+
+
+class MVRError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built: the product path never
+    falls back to a CPU or eager-PyTorch implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MVRError(
+            f"{LIB_PATH} is missing: build it with `python -m mvtn_b200.build` (or __graft_entry__.build()); "
+            "mvtn_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mvr_abi_version() != ABI_VERSION:
+        raise MVRError(f"libmvr_b200.so ABI {lib.mvr_abi_version()} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc, who):
+    if rc != 0:
+        msg = load().mvr_last_error_string()
+        raise MVRError(f"{who} failed with status {rc}: {msg.decode() if msg else ''}")

@@ -1,0 +1,111 @@
+// mvr_common.cuh -- shared device helpers for libmvr_b200 (sm_100a).
+//
+// Arithmetic contract (DESIGN.md "Parity"): everything that decides a fragment (projection,
+// edge functions, barycentrics, depth, point distances) is IEEE fp32 in the written operation
+// order.  The translation units are compiled with -fmad=false so that a*b+c is never contracted;
+// where an FMA is wanted (shading, gradients: tolerance-compared) it is written as fmaf().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mvr_b200.h"
+
+#define MVR_K_EPS 1e-8f
+#define MVR_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define MVR_THREADS 256
+
+namespace mvr {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+// [upstream] rasterization_utils PixToNonSquareNdc -- NDC coordinate of the centre of pixel i.
+__host__ __device__ __forceinline__ float pix_to_ndc(int i, int S1, int S2) {
+  float range = 2.0f;
+  if (S1 > S2) range = ((float)(S1 / S2)) * range;
+  const float offset = range / 2.0f;
+  return -offset + (range * (float)i + offset) / (float)S1;
+}
+
+// Inclusive range [lo, hi] of flipped pixel indices j (j = S-1-i) whose centre c(j) satisfies
+// vmin <= c(j) <= vmax; empty when lo > hi.  c(j) is strictly increasing in j.  The float
+// estimate is corrected with exact evaluations so the range is exact, not conservative.
+__device__ __forceinline__ void ndc_range_to_pix(float vmin, float vmax, int S1, int S2, int& lo, int& hi) {
+  float range = 2.0f;
+  if (S1 > S2) range = ((float)(S1 / S2)) * range;
+  const float offset = range / 2.0f;
+  // c(j) = -offset + (range*j + offset)/S1  =>  j = ((c + offset)*S1 - offset)/range
+  float flo = ceilf(((vmin + offset) * (float)S1 - offset) / range);
+  float fhi = floorf(((vmax + offset) * (float)S1 - offset) / range);
+  flo = fminf(fmaxf(flo, -1.0f), (float)S1);
+  fhi = fminf(fmaxf(fhi, -1.0f), (float)S1);
+  lo = (int)flo; hi = (int)fhi;
+  if (lo < 0) lo = 0;
+  if (hi > S1 - 1) hi = S1 - 1;
+  // exact fix-up (at most a step or two)
+  while (lo > 0 && pix_to_ndc(lo - 1, S1, S2) >= vmin) --lo;
+  while (lo <= S1 - 1 && pix_to_ndc(lo, S1, S2) < vmin) ++lo;
+  while (hi < S1 - 1 && pix_to_ndc(hi + 1, S1, S2) <= vmax) ++hi;
+  while (hi >= 0 && pix_to_ndc(hi, S1, S2) > vmax) --hi;
+}
+
+// X_view = X_world R + T, normative order ((x*R0j + y*R1j) + z*R2j) + Tj.
+struct Camera {
+  float r[9];
+  float t[3];
+};
+__device__ __forceinline__ Camera load_camera(const float* __restrict__ R, const float* __restrict__ T, int n) {
+  Camera c;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c.r[i] = __ldg(R + 9 * (size_t)n + i);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c.t[i] = __ldg(T + 3 * (size_t)n + i);
+  return c;
+}
+__device__ __forceinline__ void world_to_view(const Camera& c, float x, float y, float z, float& px, float& py, float& pz) {
+  px = ((x * c.r[0] + y * c.r[3]) + z * c.r[6]) + c.t[0];
+  py = ((x * c.r[1] + y * c.r[4]) + z * c.r[7]) + c.t[1];
+  pz = ((x * c.r[2] + y * c.r[5]) + z * c.r[8]) + c.t[2];
+}
+
+__device__ __forceinline__ unsigned long long make_key(float z, int idx) {
+  // z >= 0 here, so the IEEE bit pattern is monotone; +0.0f canonicalises -0.0f.
+  return ((unsigned long long)__float_as_uint(z + 0.0f) << 32) | (unsigned int)idx;
+}
+
+// 64-bit min on shared memory (lexicographic (z, idx) == the oracle's priority-queue order).
+__device__ __forceinline__ void smem_key_min(unsigned long long* addr, unsigned long long key) {
+  unsigned long long cur = *(volatile unsigned long long*)addr;
+  while (key < cur) {
+    const unsigned long long old = atomicCAS(addr, cur, key);
+    if (old == cur) break;
+    cur = old;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of NV values per thread (MVR_THREADS threads); result valid in thread 0.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* s_red /* [8][NV] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s_red[warp * NV + i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    float s = 0.f;
+    for (int w = 0; w < MVR_THREADS / 32; ++w) s += s_red[w * NV + threadIdx.x];
+    s_red[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+}  // namespace mvr

@@ -1,0 +1,345 @@
+"""Torch-facing operators over the C ABI (include/mvr_b200.h): device memory, streams and autograd
+plumbing only -- every arithmetic step of the path runs in libmvr_b200.so.
+
+Operator surface (mirrors what renderer.py reaches in PyTorch3D):
+    look_at_view_transform(dist, elev, azim)         renderer.py:79,122
+    PackedMeshes                                     renderer.py:67-77 (Meshes / Textures / normals)
+    render_meshes(...)                               renderer.py:89-107 (MeshRenderer + HardPhong)
+    render_points(...)                               renderer.py:129-145 (PointsRenderer + compositor)
+"""
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+_workspaces = {}
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise L.MVRError(f"{name} must be a CUDA tensor: mvtn_b200 has no CPU path")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def workspace(device, nbytes: int) -> torch.Tensor:
+    """Per-(device, stream) scratch reused across calls (stream order makes reuse safe)."""
+    key = (torch.device(device).index, _stream(device))
+    w = _workspaces.get(key)
+    if w is None or w.numel() < nbytes:
+        w = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = w
+    return w
+
+
+def fov_projection_scale(fov_deg: float = 60.0, znear: float = 1.0, aspect: float = 1.0):
+    """K00, K11 of [upstream] FoVPerspectiveCameras.compute_projection_matrix, evaluated with the same
+    fp32 tensor ops (fov*pi/180, tan(fov/2)*znear, 2*znear/(max-min))."""
+    fov = torch.tensor(fov_deg, dtype=torch.float32) * (math.pi / 180.0)
+    max_y = torch.tan(fov / 2) * znear
+    min_y = -max_y
+    max_x = max_y * aspect
+    min_x = -max_x
+    return float(2.0 * znear / (max_x - min_x)), float(2.0 * znear / (max_y - min_y))
+
+
+# --------------------------------------------------------------------------------------------------
+# cameras
+# --------------------------------------------------------------------------------------------------
+class _LookAt(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, azim, elev, dist):
+        _require_cuda(azim, "azim")
+        lib = L.load()
+        a, e, d = _f32c(azim).reshape(-1), _f32c(elev).reshape(-1), _f32c(dist).reshape(-1)
+        n = a.numel()
+        if e.numel() != n or d.numel() != n:
+            raise ValueError("azim, elev and dist must have the same number of elements")
+        dev = a.device
+        R = torch.empty((n, 3, 3), dtype=torch.float32, device=dev)
+        T = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        Cc = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.mvr_look_at_forward(_ptr(a), _ptr(e), _ptr(d), n, _ptr(R), _ptr(T), _ptr(Cc), _ptr(bad),
+                                            _stream(dev)), "mvr_look_at_forward")
+        ctx.save_for_backward(a, e, d)
+        ctx.shapes = (azim.shape, elev.shape, dist.shape)
+        ctx.mark_non_differentiable(bad)
+        return R, T, Cc, bad
+
+    @staticmethod
+    def backward(ctx, gR, gT, gC, _gbad):
+        lib = L.load()
+        a, e, d = ctx.saved_tensors
+        n = a.numel()
+        dev = a.device
+        gR = None if gR is None else _f32c(gR)
+        gT = None if gT is None else _f32c(gT)
+        gC = None if gC is None else _f32c(gC)
+        ga, ge, gd = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3))
+        with torch.cuda.device(dev):
+            L.check(lib.mvr_look_at_backward(_ptr(a), _ptr(e), _ptr(d), n, _ptr(gR), _ptr(gT), _ptr(gC), _ptr(ga),
+                                             _ptr(ge), _ptr(gd), _stream(dev)), "mvr_look_at_backward")
+        sa, se, sd = ctx.shapes
+        return ga.reshape(sa), ge.reshape(se), gd.reshape(sd)
+
+
+def look_at_view_transform(dist, elev, azim, return_centers=False, return_invalid=False):
+    """PyTorch3D's look_at_view_transform(dist, elev, azim) (degrees, at=0, up=+Y) on device, differentiable.
+    Returns R (n,3,3), T (n,3) [, C (n,3)] [, invalid-count int32 tensor]."""
+    R, T, Cc, bad = _LookAt.apply(azim, elev, dist)
+    out = [R, T]
+    if return_centers:
+        out.append(Cc)
+    if return_invalid:
+        out.append(bad)
+    return tuple(out)
+
+
+# --------------------------------------------------------------------------------------------------
+# packed geometry
+# --------------------------------------------------------------------------------------------------
+class PackedMeshes:
+    """Device-resident packed batch of meshes: float4 vertices / unit vertex normals / colours and
+    int4 faces, built by mvr_mesh_prepare.  Replaces Meshes(verts, faces) + Textures(verts_rgb) +
+    verts_normals_packed() (renderer.py:67-77); can be cached across iterations."""
+
+    def __init__(self, verts: Sequence[torch.Tensor], faces: Sequence[torch.Tensor], device,
+                 vert_rgb: Optional[torch.Tensor] = None):
+        lib = L.load()
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise L.MVRError("PackedMeshes needs a CUDA device: mvtn_b200 has no CPU path")
+        if len(verts) != len(faces):
+            raise ValueError("verts and faces lists differ in length")
+        self.B = len(verts)
+        nv = [int(v.shape[0]) for v in verts]
+        nf = [int(f.shape[0]) for f in faces]
+        for v, f in zip(verts, faces):
+            if v.dim() != 2 or v.shape[1] != 3 or f.dim() != 2 or f.shape[1] != 3:
+                raise ValueError("verts must be (V,3) and faces (F,3)")
+        self.num_verts, self.num_faces = nv, nf
+        self.total_verts, self.total_faces = sum(nv), sum(nf)
+        self.max_faces = max(nf) if nf else 0
+        voff = [0]
+        foff = [0]
+        for a in nv:
+            voff.append(voff[-1] + a)
+        for a in nf:
+            foff.append(foff[-1] + a)
+        self.vert_off_host, self.face_off_host = voff, foff
+        self.device = device
+        if self.B == 0:
+            return
+        # one staged host->device copy per array instead of 2B small ones (renderer.py:67-68)
+        v_all = torch.cat([v.detach().to(torch.float32) for v in verts], 0) if self.total_verts else torch.zeros(0, 3)
+        f_all = torch.cat([f.detach() for f in faces], 0) if self.total_faces else torch.zeros(0, 3, dtype=torch.int64)
+        if f_all.dtype not in (torch.int32, torch.int64):
+            f_all = f_all.to(torch.int64)
+        self.verts = v_all.to(device, non_blocking=True).contiguous()
+        self.faces = f_all.to(device, non_blocking=True).contiguous()
+        offs = torch.tensor(voff + foff, dtype=torch.int32).to(device, non_blocking=True)
+        self.vert_off, self.face_off = offs[: self.B + 1], offs[self.B + 1:]
+        flags = L.FACES_I64 if self.faces.dtype == torch.int64 else 0
+        rgb = None
+        self.per_vertex_rgb = vert_rgb is not None
+        if vert_rgb is not None:
+            rgb = _f32c(vert_rgb.to(device)).reshape(-1, 3)
+            if rgb.shape[0] != self.total_verts:
+                raise ValueError("vert_rgb must hold one colour per packed vertex")
+            flags |= L.RGB_PER_ELEMENT
+        nbytes = lib.mvr_mesh_geometry_bytes(self.total_verts, self.total_faces)
+        self.geometry = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            L.check(lib.mvr_mesh_prepare(_ptr(self.verts), _ptr(self.faces), _ptr(self.vert_off), _ptr(self.face_off),
+                                         self.B, self.total_verts, self.total_faces, self.max_faces, _ptr(rgb), flags,
+                                         _ptr(self.geometry), self.geometry.numel(), _stream(device)),
+                    "mvr_mesh_prepare")
+
+    def vertex_normals(self) -> torch.Tensor:
+        out = torch.empty((self.total_verts, 3), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.load().mvr_mesh_get_normals(_ptr(self.geometry), self.total_verts, self.total_faces, _ptr(out),
+                                                  _stream(self.device)), "mvr_mesh_get_normals")
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# mesh rendering
+# --------------------------------------------------------------------------------------------------
+class _MeshRender(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, R, T, Cc, geom: PackedMeshes, M, light, obj_rgb, bg_rgb, k00, k11, z_clip, H, W, K, flags,
+                want_fragments):
+        lib = L.load()
+        dev = geom.device
+        R, T, Cc = _f32c(R), _f32c(T), _f32c(Cc)
+        N = geom.B * M
+        if R.shape[0] != N:
+            raise ValueError(f"expected {N} cameras (B*M), got {R.shape[0]}")
+        light = _f32c(light).reshape(-1, 3)
+        if light.shape[0] not in (1, N):
+            raise ValueError("light direction must be (1,3) or (B*M,3)")
+        light_stride = 0 if light.shape[0] == 1 else 3
+        obj_rgb = None if obj_rgb is None else _f32c(obj_rgb)
+        bg_rgb = _f32c(bg_rgb)
+        if geom.per_vertex_rgb:
+            flags |= L.RGB_PER_ELEMENT
+        images = torch.empty((N, 3, H, W), dtype=torch.float32, device=dev)
+        p2f = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
+        zbuf = bary = dists = None
+        if want_fragments:
+            zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+            bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
+            dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        counters = torch.zeros(L.NUM_COUNTERS, dtype=torch.int64, device=dev)
+        ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, geom.total_faces, geom.max_faces)
+        ws = workspace(dev, ws_bytes)
+        with torch.cuda.device(dev):
+            L.check(lib.mvr_mesh_forward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
+                                         geom.total_verts, geom.total_faces, geom.max_faces, _ptr(R), _ptr(T), _ptr(Cc),
+                                         _ptr(light), light_stride, _ptr(obj_rgb), _ptr(bg_rgb), k00, k11, z_clip, H, W,
+                                         K, flags, _ptr(images), _ptr(p2f), _ptr(zbuf), _ptr(bary), _ptr(dists),
+                                         _ptr(counters), _ptr(ws), ws.numel(), _stream(dev)), "mvr_mesh_forward")
+        ctx.geom, ctx.M, ctx.light_stride = geom, M, light_stride
+        ctx.cfg = (k00, k11, H, W, K, flags)
+        ctx.save_for_backward(R, T, Cc, light, obj_rgb if obj_rgb is not None else bg_rgb, p2f)
+        extras = [p2f, counters]
+        if want_fragments:
+            extras += [zbuf, bary, dists]
+        ctx.mark_non_differentiable(*extras)
+        return (images, *extras)
+
+    @staticmethod
+    def backward(ctx, g_images, *_unused):
+        lib = L.load()
+        geom, M = ctx.geom, ctx.M
+        R, T, Cc, light, obj_rgb, p2f = ctx.saved_tensors
+        k00, k11, H, W, K, flags = ctx.cfg
+        dev = geom.device
+        N = geom.B * M
+        g_images = _f32c(g_images)
+        gR = torch.empty((N, 3, 3), dtype=torch.float32, device=dev)
+        gT = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        gC = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, geom.total_faces, geom.max_faces)
+        ws = workspace(dev, ws_bytes)
+        with torch.cuda.device(dev):
+            L.check(lib.mvr_mesh_backward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
+                                          geom.total_verts, geom.total_faces, _ptr(R), _ptr(T), _ptr(Cc), _ptr(light),
+                                          ctx.light_stride, _ptr(obj_rgb), k00, k11, H, W, K, flags, _ptr(p2f),
+                                          _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gC), None, None, _ptr(ws), ws.numel(),
+                                          _stream(dev)), "mvr_mesh_backward")
+        return (gR, gT, gC) + (None,) * 13
+
+
+def render_meshes(geom: PackedMeshes, M: int, R, T, Cc, light, obj_rgb, bg_rgb, image_size: int, faces_per_pixel=1,
+                  cull_backfaces=False, perspective_correct=True, fov=60.0, znear=1.0, z_clip: Optional[float] = None,
+                  fragments=False):
+    """images (B*M,3,H,W) [+ dict of fragments].  HardPhong + hard blend, blur_radius 0."""
+    k00, k11 = fov_projection_scale(fov, znear)
+    if z_clip is None:
+        z_clip = znear / 2 if perspective_correct else -1.0   # [upstream] MeshRasterizer.forward
+    flags = (L.PERSPECTIVE_CORRECT if perspective_correct else 0) | (L.CULL_BACKFACES if cull_backfaces else 0)
+    out = _MeshRender.apply(R, T, Cc, geom, M, light, obj_rgb, bg_rgb, k00, k11, float(z_clip), image_size, image_size,
+                            int(faces_per_pixel), flags, bool(fragments))
+    images, p2f, counters = out[0], out[1], out[2]
+    frag = {"pix_to_face": p2f, "counters": counters}
+    if fragments:
+        frag.update(zbuf=out[3], bary_coords=out[4], dists=out[5])
+    return images, frag
+
+
+# --------------------------------------------------------------------------------------------------
+# point rendering
+# --------------------------------------------------------------------------------------------------
+class _PointsRender(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, R, T, inv_dist, points, rgb, M, radius, bg_rgb, H, W, K, flags, want_fragments):
+        lib = L.load()
+        _require_cuda(points, "points")
+        dev = points.device
+        pts = _f32c(points)
+        if pts.dim() != 3 or pts.shape[2] != 3:
+            raise ValueError("points must be (B,N,3)")
+        B, Np, _ = pts.shape
+        N = B * M
+        R, T, inv_dist = _f32c(R), _f32c(T), _f32c(inv_dist).reshape(-1)
+        if R.shape[0] != N or inv_dist.numel() != N:
+            raise ValueError(f"expected {N} cameras (B*M)")
+        rgb = _f32c(rgb.to(dev))
+        if rgb.numel() != 3:
+            if rgb.numel() != pts.numel():
+                raise ValueError("rgb must be a 3-vector or one colour per point (B,N,3)")
+            flags |= L.RGB_PER_ELEMENT
+        bg_rgb = _f32c(bg_rgb)
+        images = torch.empty((N, 3, H, W), dtype=torch.float32, device=dev)
+        idx = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
+        zbuf = d2 = None
+        if want_fragments:
+            zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+            d2 = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.mvr_points_forward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), float(radius),
+                                           _ptr(bg_rgb), H, W, K, flags, _ptr(images), _ptr(idx), _ptr(zbuf), _ptr(d2),
+                                           None, 0, _stream(dev)), "mvr_points_forward")
+        ctx.cfg = (B, Np, M, float(radius), H, W, K, flags)
+        ctx.rgb_shape = rgb.shape
+        ctx.points_shape = points.shape
+        ctx.save_for_backward(R, T, inv_dist, pts, rgb, idx)
+        extras = [idx] + ([zbuf, d2] if want_fragments else [])
+        ctx.mark_non_differentiable(*extras)
+        return (images, *extras)
+
+    @staticmethod
+    def backward(ctx, g_images, *_unused):
+        lib = L.load()
+        R, T, inv_dist, pts, rgb, idx = ctx.saved_tensors
+        B, Np, M, radius, H, W, K, flags = ctx.cfg
+        dev = pts.device
+        N = B * M
+        g_images = _f32c(g_images)
+        gR = torch.empty((N, 3, 3), dtype=torch.float32, device=dev)
+        gT = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        gs = torch.empty(N, dtype=torch.float32, device=dev)
+        gP = torch.zeros_like(pts) if ctx.needs_input_grad[3] else None
+        gF = torch.zeros_like(rgb) if ctx.needs_input_grad[4] else None
+        ws_bytes = lib.mvr_points_workspace_bytes(B, M, H, W, K)
+        ws = workspace(dev, ws_bytes)
+        with torch.cuda.device(dev):
+            L.check(lib.mvr_points_backward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), radius, H,
+                                            W, K, flags, _ptr(idx), _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gs),
+                                            _ptr(gP), _ptr(gF), _ptr(ws), ws.numel(), _stream(dev)),
+                    "mvr_points_backward")
+        if gP is not None:
+            gP = gP.reshape(ctx.points_shape)
+        if gF is not None:
+            gF = gF.reshape(ctx.rgb_shape)
+        return (gR, gT, gs, gP, gF) + (None,) * 8
+
+
+def render_points(points, rgb, M: int, R, T, inv_dist, radius: float, bg_rgb, image_size: int, points_per_pixel=1,
+                  compositor="norm", fragments=False):
+    """images (B*M,3,H,W) [+ fragments].  compositor: "norm" (NormWeightedCompositor) | "alpha"."""
+    if compositor not in ("norm", "alpha"):
+        raise ValueError("compositor must be 'norm' or 'alpha'")
+    flags = L.COMPOSITE_ALPHA if compositor == "alpha" else 0
+    out = _PointsRender.apply(R, T, inv_dist, points, rgb, M, radius, bg_rgb, image_size, image_size,
+                              int(points_per_pixel), flags, bool(fragments))
+    frag = {"idx": out[1]}
+    if fragments:
+        frag.update(zbuf=out[2], dists=out[3])
+    return out[0], frag

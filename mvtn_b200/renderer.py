@@ -1,0 +1,193 @@
+"""MVRenderer -- drop-in for MVTN's models/renderer.py:MVRenderer on B200 (sm_100a).
+
+Same constructor (renderer.py:52), same forward(meshes, points, azim, elev, dist, color=None) ->
+(rendered_images (B,M,3,H,W), cameras) (renderer.py:173-198), same render_and_save (renderer.py:200-207),
+same train()/eval() behaviour for colour and light randomisation, empty state_dict().  Everything PyTorch3D
+did on this path (look_at, Meshes.extend, rasterizers, HardPhong shading, point compositing and their
+autograd) is done by libmvr_b200.so through mvtn_b200.ops; nothing here falls back to CPU or eager torch.
+"""
+import sys
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import MVRError
+from .cameras import FoVOrthographicCameras, FoVPerspectiveCameras
+from .structures import unpack_mesh_list
+from .util import torch_color
+
+ORTHOGONAL_THRESHOLD = 1e-6   # renderer.py:29
+EXAHSTION_LIMIT = 20          # renderer.py:30 (sic)
+
+
+class MVRenderer(nn.Module):
+    """The multi-view differentiable renderer (see models/renderer.py:33-50 for the argument docs).
+
+    Extra keyword-only options (defaults reproduce the reference):
+        compositor: "norm" (NormWeightedCompositor, renderer.py:138) or "alpha" (AlphaCompositor,
+            imported at renderer.py:11; BASELINE config 3).
+        perspective_correct: barycentric perspective correction (PyTorch3D >= 0.5 infers True for
+            FoV perspective cameras).
+        cache_geometry: keep the packed device geometry of the last mesh batch and reuse it when the
+            same list object is rendered again.
+    """
+
+    def __init__(self, nb_views, image_size=224, pc_rendering=True, object_color="white", background_color="white",
+                 faces_per_pixel=1, points_radius=0.006, points_per_pixel=1, light_direction="random",
+                 cull_backfaces=False, *, compositor="norm", perspective_correct=True, cache_geometry=False):
+        super().__init__()
+        self.nb_views = nb_views
+        self.image_size = image_size
+        self.pc_rendering = pc_rendering
+        self.object_color = object_color
+        self.background_color = background_color
+        self.faces_per_pixel = faces_per_pixel
+        self.points_radius = points_radius
+        self.points_per_pixel = points_per_pixel
+        self.light_direction_type = light_direction
+        self.cull_backfaces = cull_backfaces
+        self.compositor = compositor
+        self.perspective_correct = perspective_correct
+        self.cache_geometry = cache_geometry
+        self._geom_cache = (None, None)
+        self.last_fragments = None
+
+    # ---------------------------------------------------------------------------------------------
+    def _device(self, azim):
+        if isinstance(azim, torch.Tensor) and azim.is_cuda:
+            return azim.device
+        if not torch.cuda.is_available():
+            raise MVRError("MVRenderer needs a CUDA device: mvtn_b200 has no CPU path")
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def _cameras(self, azim, elev, dist, device):
+        """look_at_view_transform + check_and_correct_rotation_matrix (renderer.py:79-82, ops.py:156-165).
+        The validity test is fused into the look_at kernel; its flag is read AFTER the render has been
+        enqueued (see forward), so the reference's host sync does not stall the pipeline."""
+        azim, elev, dist = (t.to(device) if t.device != device else t for t in (azim, elev, dist))
+        if azim.shape != elev.shape or azim.shape != dist.shape or azim.dim() != 2:
+            raise ValueError("azim, elev and dist must all be (B, M)")
+        if azim.shape[1] != self.nb_views:
+            raise ValueError(f"expected {self.nb_views} views, got {azim.shape[1]}")
+        R, T, C, bad = ops.look_at_view_transform(dist.reshape(-1), elev.reshape(-1), azim.reshape(-1),
+                                                  return_centers=True, return_invalid=True)
+        return azim, elev, dist, R, T, C, bad
+
+    def _render_with_guard(self, azim, elev, dist, device, render):
+        azim, elev, dist, R, T, C, bad = self._cameras(azim, elev, dist, device)
+        out = render(R, T, C, dist)
+        exhastion = 0
+        while int(bad.item()) != 0:       # util.py:403-420: the reference syncs here on every call
+            exhastion += 1
+            e2 = elev + 90.0 * torch.rand_like(elev)
+            a2 = azim + 180.0 * torch.rand_like(azim)
+            _, _, _, R, T, C, bad = self._cameras(a2, e2, dist, device)
+            if int(bad.item()) != 0 and exhastion > EXAHSTION_LIMIT:
+                sys.exit("Remedy did not work")   # ops.py:163-164
+            if int(bad.item()) == 0:
+                out = render(R, T, C, dist)
+        return out, R, T, C
+
+    def render_meshes(self, meshes, color, azim, elev, dist, lights, background_color=(1.0, 1.0, 1.0)):
+        device = self._device(azim)
+        geom = self._packed(meshes, color, device)
+        if geom.B != azim.shape[0]:
+            raise ValueError(f"{geom.B} meshes but azim has batch {azim.shape[0]}")
+        bg = torch.as_tensor(background_color, dtype=torch.float32).to(device)
+        obj = None if geom.per_vertex_rgb else torch.as_tensor(color, dtype=torch.float32).to(device)
+
+        def render(R, T, C, dist_):
+            light = C.detach() if lights is None else torch.as_tensor(lights, dtype=torch.float32).to(device)
+            return ops.render_meshes(geom, self.nb_views, R, T, C, light, obj, bg, self.image_size,
+                                     faces_per_pixel=self.faces_per_pixel, cull_backfaces=self.cull_backfaces,
+                                     perspective_correct=self.perspective_correct)
+
+        (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
+        self.last_fragments = frag
+        B = geom.B
+        rendered_images = images.view(B, self.nb_views, 3, self.image_size, self.image_size)
+        return rendered_images, FoVPerspectiveCameras(R, T, C)
+
+    def render_points(self, points, color, azim, elev, dist, background_color=(0.0, 0.0, 0.0)):
+        device = self._device(azim)
+        if points.shape[0] != azim.shape[0]:
+            raise ValueError(f"{points.shape[0]} clouds but azim has batch {azim.shape[0]}")
+        pts = points.to(device=device, dtype=torch.float32)
+        bg = torch.as_tensor(background_color, dtype=torch.float32).to(device)
+        rgb = torch.as_tensor(color, dtype=torch.float32).to(device)
+        if rgb.numel() != 3:
+            rgb = rgb * torch.ones_like(pts)          # renderer.py:119-120 features = color * ones_like(points)
+
+        def render(R, T, C, dist_):
+            inv_dist = 1.0 / dist_.reshape(-1)        # renderer.py:142 point_cloud.scale_(1/dist)
+            return ops.render_points(pts, rgb, self.nb_views, R, T, inv_dist, self.points_radius, bg, self.image_size,
+                                     points_per_pixel=self.points_per_pixel, compositor=self.compositor)
+
+        (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
+        self.last_fragments = frag
+        rendered_images = images.view(pts.shape[0], self.nb_views, 3, self.image_size, self.image_size)
+        return rendered_images, FoVOrthographicCameras(R, T, C, znear=0.01)
+
+    def _packed(self, meshes, color, device):
+        if isinstance(meshes, ops.PackedMeshes):
+            return meshes
+        if meshes is None:
+            raise ValueError("mesh rendering (pc_rendering=False) needs `meshes`")
+        if self.cache_geometry and self._geom_cache[0] is meshes:
+            return self._geom_cache[1]
+        verts, faces = unpack_mesh_list(meshes)
+        vert_rgb = None
+        color_t = torch.as_tensor(color, dtype=torch.float32)
+        if color_t.numel() != 3:
+            # renderer.py:76-77 verts_rgb = color * ones((B, maxV, 3)): per-vertex colours (B, maxV, 3)
+            color_t = color_t.reshape(len(verts), -1, 3)
+            vert_rgb = torch.cat([color_t[b, : verts[b].shape[0]] for b in range(len(verts))], 0)
+        geom = ops.PackedMeshes(verts, faces, device, vert_rgb=vert_rgb)
+        if self.cache_geometry:
+            self._geom_cache = (meshes, geom)
+        return geom
+
+    # ---------------------------------------------------------------------------------------------
+    def rendering_color(self, custom_color=(1.0, 0, 0)):
+        """renderer.py:153-160."""
+        if self.object_color == "custom":
+            color = custom_color
+        elif self.object_color == "random" and not self.training:
+            color = torch_color("white")
+        else:
+            color = torch_color(self.object_color, max_lightness=True)
+        return color
+
+    def light_direction(self, azim, elev, dist):
+        """renderer.py:162-171.  Returns a (1,3) direction, or None for the "relative" light, in which case
+        the (detached) camera centres computed by the look_at kernel are used (Variable(...) detaches)."""
+        if self.light_direction_type == "fixed":
+            return ((0, 1.0, 0),)
+        elif self.light_direction_type == "random" and self.training:
+            return (tuple(1.0 - 2 * np.random.rand(3)),)
+        return None
+
+    def forward(self, meshes, points, azim, elev, dist, color=None):
+        """renderer.py:173-198: render meshes (pc_rendering False) or point clouds (True) from B x M views."""
+        background_color = torch_color(self.background_color, max_lightness=True)
+        color = self.rendering_color(color)
+        if not self.pc_rendering:
+            lights = self.light_direction(azim, elev, dist)
+            rendered_images, cameras = self.render_meshes(meshes=meshes, color=color, azim=azim, elev=elev, dist=dist,
+                                                          lights=lights, background_color=background_color)
+        else:
+            if points is None:
+                raise ValueError("point rendering (pc_rendering=True) needs `points`")
+            rendered_images, cameras = self.render_points(points=points, color=color, azim=azim, elev=elev, dist=dist,
+                                                          background_color=background_color)
+        return rendered_images, cameras
+
+    def render_and_save(self, meshes, points, azim, elev, dist, images_path, cameras_path, color=None):
+        """renderer.py:200-207."""
+        from .viz import save_cameras, save_grid
+        with torch.no_grad():
+            rendered_images, cameras = self.forward(meshes, points, azim, elev, dist, color)
+        save_grid(image_batch=rendered_images[0, ...], save_path=images_path, nrow=self.nb_views)
+        save_cameras(cameras, save_path=cameras_path, scale=0.22, dpi=200)
