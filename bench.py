@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- rendered views/sec (forward + backward) of the MVRenderer hot path on N B200s.
+
+Workload (config.workload): BASELINE.json configs[1] -- mesh rendering of synthetic ~10k-face meshes,
+batch 32 x 12 views per GPU, 224x224, Phong shading, forward + backward (gradients to azim/elev/dist).
+`--workload points` switches to configs[2] (2048-pt clouds, alpha compositing) for exploration.
+
+One JSON line on rank 0 (contract in the task statement):
+  value      whole-job views/s with inputs resident in HBM (device-timed, max over ranks)
+  e2e        same metric through MVRenderer.forward/backward from HOST buffers (H2D + D2H inside)
+  roofline   dominant kernel: algorithmic bytes per launch / CUDA-event time vs measured HBM peak
+  cpu_baseline  the CPU oracle timed on this box's host cores on a bounded sample (rank 0, N=1)
+`--impl reference` times the reference's CPU implementation of the path: PyTorch3D cannot be installed
+here (no network, not vendored), so this arm runs the oracle port with all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rendered_views_per_sec_fwd_bwd"
+UNIT = "views/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mesh", choices=["mesh", "points"])
+    ap.add_argument("--batch", type=int, default=32, help="objects per GPU")
+    ap.add_argument("--views", type=int, default=12)
+    ap.add_argument("--image-size", type=int, default=224)
+    ap.add_argument("--faces", type=int, default=10000)
+    ap.add_argument("--points", type=int, default=2048)
+    ap.add_argument("--points-per-pixel", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-objects", type=int, default=0, help="0 = size the sample for ~10-20 s")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    if a.workload == "mesh":
+        return (f"mesh fwd+bwd: {a.batch} objects/GPU x {a.views} views, ~{a.faces}-face synthetic meshes, "
+                f"{a.image_size}x{a.image_size}, Phong, faces_per_pixel=1 (BASELINE configs[1])")
+    return (f"points fwd+bwd: {a.batch} clouds/GPU x {a.views} learned_spherical views, {a.points} pts, "
+            f"{a.image_size}x{a.image_size}, alpha compositing K={a.points_per_pixel} (BASELINE configs[2])")
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            inside = t0 - 0.05 <= ts <= t1 + 0.15
+            try:
+                if inside:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            if inside:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+def make_inputs(a, rank):
+    from mvtn_b200 import synth
+    seed = 1236 + 1000 * rank
+    if a.workload == "mesh":
+        meshes = synth.make_meshes(a.batch, a.faces, seed)
+        azim, elev, dist = synth.circular_views(a.batch, a.views)   # config.yaml:23-24 canonical 30 deg / 2.2
+        return {"meshes": meshes, "views": (azim, elev, dist)}
+    pts = synth.make_clouds(a.batch, a.points, seed + 1)
+    return {"points": pts, "views": synth.learned_spherical_views(a.batch, a.views, seed + 2)}
+
+
+def algorithmic_bytes_per_view(a, inp, which):
+    """compulsory traffic, each tensor once, geometry counted once per view."""
+    hw = a.image_size * a.image_size
+    if a.workload == "mesh":
+        V = sum(v.shape[0] for v, _ in inp["meshes"]) / len(inp["meshes"])
+        F = sum(f.shape[0] for _, f in inp["meshes"]) / len(inp["meshes"])
+        geo = 12 * V + 12 * F
+        return geo + hw * (12 + 4)            # fwd: RGB + pix_to_face ; bwd: grad RGB + pix_to_face
+    K = a.points_per_pixel
+    return 12 * a.points + hw * (12 + 4 * K)
+
+
+def run_ours(a):
+    from mvtn_b200 import MVRenderer, Meshes, ops, parallel
+    from mvtn_b200 import _lib as L
+    rank, local_rank, world = parallel.init_distributed()
+    if world != a.gpus and world > 1:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = L.load()
+    inp = make_inputs(a, rank)
+    B, M, S = a.batch, a.views, a.image_size
+    N = B * M
+    azim_h, elev_h, dist_h = (t.contiguous().pin_memory() for t in inp["views"])
+    cot = torch.randn(N, 3, S, S, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank)) / (3 * S * S)
+    bg = torch.tensor([0.99999] * 3, device=dev)
+    obj = torch.tensor([0.99999] * 3, device=dev)
+    light = torch.tensor([[0.0, 1.0, 0.0]], device=dev)
+
+    if a.workload == "mesh":
+        nv = [v.shape[0] for v, _ in inp["meshes"]]
+        nf = [f.shape[0] for _, f in inp["meshes"]]
+        verts_d = torch.cat([v for v, _ in inp["meshes"]]).to(dev)
+        faces_d = torch.cat([f for _, f in inp["meshes"]]).to(dev)
+        mesh_list = [Meshes([v], [f]) for v, f in inp["meshes"]]          # what run_mvtn.py's loader hands over (CPU)
+        renderer = MVRenderer(M, image_size=S, pc_rendering=False, light_direction="fixed").to(dev)
+        kernels = ["mesh_bin_kernel", "mesh_fine_kernel", "mesh_backward_kernel"]
+    else:
+        pts_d = inp["points"].to(dev)
+        pts_h = inp["points"].pin_memory()
+        renderer = MVRenderer(M, image_size=S, pc_rendering=True, points_per_pixel=a.points_per_pixel,
+                              background_color="black", compositor="alpha").to(dev)
+        kernels = ["points_forward_kernel", "points_backward_kernel"]
+    renderer.train()
+    azim_d, elev_d, dist_d = (t.to(dev) for t in (azim_h, elev_h, dist_h))
+
+    def step_resident():
+        """Hot path with inputs already in HBM: prepare + look_at + forward + backward + look_at backward."""
+        az = azim_d.detach().requires_grad_(); el = elev_d.detach().requires_grad_(); di = dist_d.detach().requires_grad_()
+        R, T, C, _bad = ops._LookAt.apply(az.reshape(-1), el.reshape(-1), di.reshape(-1))
+        if a.workload == "mesh":
+            geom = ops.PackedMeshes.from_packed(verts_d, faces_d, nv, nf)
+            img, _ = ops.render_meshes(geom, M, R, T, C, light, obj, bg, S)
+        else:
+            img, _ = ops.render_points(pts_d, obj, M, R, T, 1.0 / di.reshape(-1), renderer.points_radius, bg * 0, S,
+                                       points_per_pixel=a.points_per_pixel, compositor="alpha")
+        img.backward(cot)
+        return az.grad, el.grad, di.grad
+
+    g_host = torch.empty(3, B, M, pin_memory=True)
+
+    def step_e2e():
+        """Through the public API from HOST buffers: H2D of the step's inputs, render, backward, D2H of the
+        result (gradients w.r.t. azim/elev/dist)."""
+        az = azim_h.to(dev, non_blocking=True).requires_grad_()
+        el = elev_h.to(dev, non_blocking=True).requires_grad_()
+        di = dist_h.to(dev, non_blocking=True).requires_grad_()
+        if a.workload == "mesh":
+            img, _ = renderer(mesh_list, None, az, el, di)
+        else:
+            img, _ = renderer(None, pts_h, az, el, di)
+        img.backward(cot.view_as(img))
+        g_host[0].copy_(az.grad, non_blocking=True)
+        g_host[1].copy_(el.grad, non_blocking=True)
+        g_host[2].copy_(di.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return g_host
+
+    if a.workload == "mesh":
+        h2d = sum(v.numel() * 4 + f.numel() * f.element_size() for v, f in inp["meshes"]) + 3 * B * M * 4
+    else:
+        h2d = pts_h.numel() * 4 + 3 * B * M * 4
+    d2h = 3 * B * M * 4 + 4    # gradients + the rotation-validity flag
+
+    def timed(fn, steps, profile=None):
+        parallel.barrier(); torch.cuda.synchronize()
+        if profile:
+            lib.mvr_profile_enable(profile.encode())
+        l0 = lib.mvr_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        w1 = time.time()
+        parallel.barrier()
+        ms = e0.elapsed_time(e1)
+        prof = None
+        if profile:
+            import ctypes
+            tot, n = ctypes.c_double(0), ctypes.c_int(0)
+            L.check(lib.mvr_profile_collect(ctypes.byref(tot), ctypes.byref(n)), "mvr_profile_collect")
+            prof = (tot.value, n.value)
+        return ms, lib.mvr_launch_count() - l0, prof, (w0, w1)
+
+    # warm-up (also sizes workspaces / staging buffers)
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    for _ in range(max(a.warmup, 3)):
+        step_e2e()
+    torch.cuda.synchronize()
+    # which kernel dominates?  one profiled step per candidate
+    shares = {}
+    for k in kernels:
+        _, _, prof, _ = timed(step_resident, 2, profile=k)
+        shares[k] = prof[0] / max(prof[1], 1)
+    top = max(shares, key=shares.get)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    ms, launches, prof, (w0, w1) = timed(step_resident, a.steps, profile=top)
+    ms_e2e, _, _, (w2, w3) = timed(step_e2e, a.steps)
+    clocks = sampler.stop(w0, w3)
+
+    ms_max = parallel.max_over_ranks(ms, dev)
+    ms_e2e_max = parallel.max_over_ranks(ms_e2e, dev)
+    total_views = parallel.sum_over_ranks(N * a.steps, dev)
+    value = total_views / (ms_max / 1e3)
+    e2e_value = total_views / (ms_e2e_max / 1e3)
+
+    peak, peak_src = measured_peaks()
+    per_view = algorithmic_bytes_per_view(a, inp, top)
+    k_ms = prof[0] / max(prof[1], 1)
+    achieved = (per_view * N) / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(per_view * N), "kernel_ms": round(k_ms, 4),
+                "kernel_ms_all": {k: round(v, 4) for k, v in shares.items()}}
+
+    out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+           "warmup": max(a.warmup, 3), "ms_per_step": round(ms_max / a.steps, 4), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(a), "objects_per_gpu": B, "views": M, "image_size": S,
+                      "l2": "inputs_exceed_l2 (images + cotangent + pix_to_face > 126 MB per step)"},
+           "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": round(ms_e2e_max / a.steps, 4)},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(a, inp)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+def oracle_step(a, inp, n_obj):
+    """One forward+backward of the CPU oracle on the first n_obj objects of the workload.  Returns seconds."""
+    import numpy as np
+    from oracle import oracle as orc
+    from mvtn_b200 import ops
+    M, S = a.views, a.image_size
+    az, el, di = (t[:n_obj].reshape(-1).numpy() for t in inp["views"])
+    t0 = time.time()
+    R, T, C = orc.look_at(az, el, di)
+    if a.workload == "mesh":
+        ms = inp["meshes"][:n_obj]
+        vp = np.concatenate([v.numpy() for v, _ in ms]); fp = np.concatenate([f.numpy() for _, f in ms]).astype(np.int32)
+        voff = np.cumsum([0] + [v.shape[0] for v, _ in ms]).astype(np.int32)
+        foff = np.cumsum([0] + [f.shape[0] for _, f in ms]).astype(np.int32)
+        nrm = orc.packed_vertex_normals(vp, fp, voff, foff)
+        k00, k11 = ops.fov_projection_scale()
+        rgb = np.full(3, 0.99999, np.float32); light = np.array([[0, 1.0, 0]], np.float32)
+        o = orc.mesh_forward(vp, fp, voff, foff, nrm, rgb, M, R, T, C, light, rgb, k00, k11, 0.5, S, S, 1,
+                             orc.PERSPECTIVE_CORRECT, fragments=False)
+        g = np.full((n_obj * M, 3, S, S), 1.0 / (3 * S * S), np.float32)
+        b = orc.mesh_backward(vp, fp, voff, foff, nrm, rgb, M, R, T, C, light, k00, k11, S, S, 1,
+                              orc.PERSPECTIVE_CORRECT, o["pix_to_face"], g)
+        orc.look_at_backward(az, el, di, b["gR"], b["gT"], b["gC"])
+    else:
+        pts = inp["points"][:n_obj].numpy()
+        rgb = np.full(3, 0.99999, np.float32)
+        inv = (1.0 / di).astype(np.float32)
+        K = a.points_per_pixel
+        o = orc.points_forward(pts, rgb, M, R, T, inv, 0.006, np.zeros(3, np.float32), S, S, K, orc.COMPOSITE_ALPHA,
+                               fragments=False)
+        g = np.full((n_obj * M, 3, S, S), 1.0 / (3 * S * S), np.float32)
+        b = orc.points_backward(pts, rgb, M, R, T, inv, 0.006, S, S, K, orc.COMPOSITE_ALPHA, o["idx"], g)
+        orc.look_at_backward(az, el, di, b["gR"], b["gT"], None)
+    return time.time() - t0
+
+
+def cpu_baseline(a, inp):
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    orc.set_num_threads(cores)
+    n = a.cpu_sample_objects
+    if n <= 0:
+        t1 = oracle_step(a, inp, 1)                     # probe: one object
+        n = max(1, min(a.batch, int(12.0 / max(t1, 1e-3))))
+    t = oracle_step(a, inp, n)
+    return {"value": round(n * a.views / t, 2), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+            "sample": f"{n} object(s) x {a.views} views of the same workload, fwd+bwd, {t:.2f} s of CPU work "
+                      f"(oracle/mvr_oracle.c, OpenMP over image rows)"}
+
+
+def run_reference(a):
+    """Reference arm: the reference's own CPU implementation of the path.  PyTorch3D is not vendored and
+    cannot be installed offline, so this is the oracle port with all host threads (kind "port")."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    orc.set_num_threads(cores)
+    inp = make_inputs(a, 0)
+    t1 = oracle_step(a, inp, 1)
+    n = max(1, min(a.batch, int(3.0 / max(t1, 1e-3))))      # ~3 s of CPU work per step
+    for _ in range(min(a.warmup, 1)):
+        oracle_step(a, inp, n)
+    steps = max(1, min(a.steps, 5))
+    t0 = time.time()
+    for _ in range(steps):
+        oracle_step(a, inp, n)
+    dt = time.time() - t0
+    v = round(n * a.views * steps / dt, 2)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+           "warmup": min(a.warmup, 1), "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(a), "objects_per_gpu": a.batch, "views": a.views, "image_size": a.image_size},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                            "sample": f"{n} object(s) x {a.views} views per step, fwd+bwd (PyTorch3D is not installable "
+                                      f"offline: oracle port of its CPU path)"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -34,6 +34,7 @@ extern "C" {
 #define MVR_COMPOSITE_ALPHA 4      /* AlphaCompositor instead of NormWeightedCompositor (renderer.py:11,138) */
 #define MVR_RGB_PER_ELEMENT 8      /* per-vertex / per-point colours (object_color == "custom") */
 #define MVR_FACES_I64 16           /* faces given as int64 (F,3) -- the reference's layout, renderer.py:68 */
+#define MVR_TEST_TINY_POOL 0x40000000 /* tests only: bin pool of 64 entries, forces the unbinned fallback */
 
 /* Phong constants of DirectionalLights() / Materials() as constructed at renderer.py:190-191 */
 #define MVR_AMBIENT 0.5f
@@ -50,6 +51,15 @@ extern "C" {
 int mvr_abi_version(void);
 /* thread-local description of the last non-zero return value (host string) */
 const char* mvr_last_error_string(void);
+
+/* -- measurement hooks (bench.py) ------------------------------------------------------------ */
+/* number of kernels this library has launched in this process */
+long long mvr_launch_count(void);
+/* bracket every following launch of the named kernel (e.g. "mesh_fine_kernel") with CUDA events on
+ * its launch stream; NULL disables.  mvr_profile_collect synchronises those events, returns the summed
+ * device time and the number of launches, and disables collection. */
+int mvr_profile_enable(const char* kernel_name);
+int mvr_profile_collect(double* total_ms, int* n_launches);
 
 /* -- cameras ------------------------------------------------------------------------------ */
 /* look_at_view_transform(dist, elev, azim) + camera_position_from_spherical_angles

@@ -136,11 +136,13 @@ __global__ void look_at_backward_kernel(const float* __restrict__ azim, const fl
 
 }  // namespace mvr
 
+using namespace mvr;
+
 extern "C" int mvr_look_at_forward(const float* azim, const float* elev, const float* dist, int n, float* R,
                                    float* T, float* C, int* invalid_count, void* stream) {
   if (n < 0 || (n > 0 && (!azim || !elev || !dist || !R || !T))) { mvr::set_error("mvr_look_at_forward: null pointer or negative n"); return -1; }
   if (n == 0) return 0;
-  mvr::look_at_forward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(azim, elev, dist, n, R, T, C, invalid_count);
+  MVR_LAUNCH(look_at_forward_kernel, (n + 127) / 128, 128, 0, (cudaStream_t)stream, azim, elev, dist, n, R, T, C, invalid_count);
   return mvr::check_launch("look_at_forward_kernel");
 }
 
@@ -149,6 +151,6 @@ extern "C" int mvr_look_at_backward(const float* azim, const float* elev, const 
                                     float* g_elev, float* g_dist, void* stream) {
   if (n < 0 || (n > 0 && (!azim || !elev || !dist))) { mvr::set_error("mvr_look_at_backward: null pointer or negative n"); return -1; }
   if (n == 0) return 0;
-  mvr::look_at_backward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(azim, elev, dist, n, gR, gT, gC, g_azim, g_elev, g_dist);
+  MVR_LAUNCH(look_at_backward_kernel, (n + 127) / 128, 128, 0, (cudaStream_t)stream, azim, elev, dist, n, gR, gT, gC, g_azim, g_elev, g_dist);
   return mvr::check_launch("look_at_backward_kernel");
 }

@@ -18,6 +18,17 @@ namespace mvr {
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end(const char* name, cudaStream_t st);
+
+// every kernel launch goes through this: counts it (mvr_launch_count) and, when bench.py asked for it,
+// brackets it with CUDA events on the launching stream (mvr_profile_enable / mvr_profile_collect).
+#define MVR_LAUNCH(kernel, grid, block, smem, st, ...)          \
+  do {                                                          \
+    mvr::prof_begin(#kernel, st);                               \
+    kernel<<<grid, block, smem, st>>>(__VA_ARGS__);             \
+    mvr::prof_end(#kernel, st);                                 \
+  } while (0)
 
 // [upstream] rasterization_utils PixToNonSquareNdc -- NDC coordinate of the centre of pixel i.
 __host__ __device__ __forceinline__ float pix_to_ndc(int i, int S1, int S2) {

@@ -285,8 +285,9 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_bin_kernel(const MeshParams 
   for (int f = fbeg + threadIdx.x; f < fend; f += MVR_THREADS) {
     const Face fc = load_face(p, cam, voff, __ldg(p.faces4 + f0 + f));
     int xl, xh, yl, yh; bool st;
-    if (!face_pixel_bbox(fc, p, xl, xh, yl, yh, st)) continue;
-    n_straddle += st;
+    const bool vis = face_pixel_bbox(fc, p, xl, xh, yl, yh, st);
+    n_straddle += st;          // every face crossing z_clip is counted, visible or not (as the oracle does)
+    if (!vis) continue;
     const int tx0 = xl / TILE, tx1 = xh / TILE, ty0 = yl / TILE, ty1 = yh / TILE;
     for (int ty = ty0; ty <= ty1; ++ty)
       for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&s_cnt[ty * p.tiles_x + tx], 1);
@@ -693,7 +694,15 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_backward_kernel(const MeshBw
     float dz0 = 0.f, dz1 = 0.f, dz2 = 0.f;
     if (persp) {
       const float id = 1.f / denom;
-      const float gden = -(gb0 * t0 + gb1 * t1 + gb2 * t2) * id * id;
+      // b = t / sum(t) is invariant to a common shift of d/db (its Jacobian annihilates constants), so
+      // remove k = sum(b_i gb_i) first: the d/d denom term then vanishes identically instead of cancelling
+      // O(1/area) terms in fp32.  Same gradient in exact arithmetic; not valid when denom was clamped.
+      const bool clamped = (t0 + t1 + t2) < MVR_K_EPS;
+      if (!clamped) {
+        const float k = fmaf(bb[0], gb0, fmaf(bb[1], gb1, bb[2] * gb2));
+        gb0 -= k; gb1 -= k; gb2 -= k;
+      }
+      const float gden = clamped ? -(gb0 * t0 + gb1 * t1 + gb2 * t2) * id * id : 0.f;
       const float gt0 = fmaf(gb0, id, gden), gt1 = fmaf(gb1, id, gden), gt2 = fmaf(gb2, id, gden);
       gb0 = gt0 * fc.z1 * fc.z2; gb1 = gt1 * fc.z0 * fc.z2; gb2 = gt2 * fc.z0 * fc.z1;
       dz0 = gt1 * w1 * fc.z2 + gt2 * w2 * fc.z1;
@@ -796,14 +805,13 @@ extern "C" int mvr_mesh_prepare(const float* verts, const void* faces, const int
   int4* faces4 = (int4*)(base + g.faces4);
   double* nacc = (double*)(base + g.nacc);
   const int tb = 256;
-  geom_pack_verts_kernel<<<(unsigned)((total_verts + tb - 1) / tb), tb, 0, st>>>(
-      verts, (flags & MVR_RGB_PER_ELEMENT) ? vert_rgb : nullptr, total_verts, verts4, rgb4, nacc);
+  MVR_LAUNCH(geom_pack_verts_kernel, (unsigned)((total_verts + tb - 1) / tb), tb, 0, st, verts, (flags & MVR_RGB_PER_ELEMENT) ? vert_rgb : nullptr, total_verts, verts4, rgb4, nacc);
   if (total_faces > 0 && max_faces > 0) {
     dim3 grid((max_faces + tb - 1) / tb, B);
-    if (flags & MVR_FACES_I64) geom_pack_faces_kernel<long long><<<grid, tb, 0, st>>>((const long long*)faces, vert_off, face_off, verts4, faces4, nacc);
-    else geom_pack_faces_kernel<int><<<grid, tb, 0, st>>>((const int*)faces, vert_off, face_off, verts4, faces4, nacc);
+    if (flags & MVR_FACES_I64) MVR_LAUNCH(geom_pack_faces_kernel<long long>, grid, tb, 0, st, (const long long*)faces, vert_off, face_off, verts4, faces4, nacc);
+    else MVR_LAUNCH(geom_pack_faces_kernel<int>, grid, tb, 0, st, (const int*)faces, vert_off, face_off, verts4, faces4, nacc);
   }
-  geom_finish_normals_kernel<<<(unsigned)((total_verts + tb - 1) / tb), tb, 0, st>>>(nacc, total_verts, normals4);
+  MVR_LAUNCH(geom_finish_normals_kernel, (unsigned)((total_verts + tb - 1) / tb), tb, 0, st, nacc, total_verts, normals4);
   return check_launch("mvr_mesh_prepare");
 }
 
@@ -811,8 +819,7 @@ extern "C" int mvr_mesh_get_normals(const void* geometry, int64_t total_verts, i
   if (total_verts <= 0) return 0;
   if (!geometry || !normals) { set_error("mvr_mesh_get_normals: null pointer"); return -1; }
   const GeomLayout g = geom_layout(total_verts, total_faces);
-  geom_get_normals_kernel<<<(unsigned)((total_verts + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)((const char*)geometry + g.normals4), total_verts, normals);
+  MVR_LAUNCH(geom_get_normals_kernel, (unsigned)((total_verts + 255) / 256), 256, 0, (cudaStream_t)stream, (const float4*)((const char*)geometry + g.normals4), total_verts, normals);
   return check_launch("mvr_mesh_get_normals");
 }
 
@@ -859,7 +866,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.k00 = k00; p.k11 = k11; p.z_clip = z_clip;
   p.B = B; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags;
   p.n_tiles = w.n_tiles; p.tiles_x = w.tiles_x; p.max_chunks = w.max_chunks; p.fpc = w.fpc;
-  p.pool_cap = w.pool_cap;
+  p.pool_cap = (flags & MVR_TEST_TINY_POOL) ? 64 : w.pool_cap;
   p.pool_counter = (int*)(wb + w.counter); p.seg = (int2*)(wb + w.seg); p.pool = (int*)(wb + w.pool);
   p.images = images; p.pix_to_face = pix_to_face; p.zbuf = zbuf; p.bary = bary; p.dists = dists;
   p.counters = (long long*)counters;
@@ -870,10 +877,10 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
     e = cudaFuncSetAttribute(mesh_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem);
     if (e != cudaSuccess) { set_error("mvr_mesh_forward: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   }
-  mesh_bin_kernel<<<(unsigned)(N * w.max_chunks), MVR_THREADS, bin_smem, st>>>(p);
+  MVR_LAUNCH(mesh_bin_kernel, (unsigned)(N * w.max_chunks), MVR_THREADS, bin_smem, st, p);
   rc = check_launch("mesh_bin_kernel");
   if (rc) return rc;
-  mesh_fine_kernel<<<(unsigned)(N * w.n_tiles), MVR_THREADS, 0, st>>>(p);
+  MVR_LAUNCH(mesh_fine_kernel, (unsigned)(N * w.n_tiles), MVR_THREADS, 0, st, p);
   return check_launch("mesh_fine_kernel");
 }
 
@@ -906,10 +913,10 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   p.B = B; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags; p.n_tiles = n_tiles; p.tiles_x = tiles_x;
   p.pix_to_face = pix_to_face; p.grad_images = grad_images;
   p.partials = (float*)workspace; p.grad_verts = grad_verts; p.grad_normals = grad_normals;
-  mesh_backward_kernel<<<(unsigned)(N * n_tiles), MVR_THREADS, 0, st>>>(p);
+  MVR_LAUNCH(mesh_backward_kernel, (unsigned)(N * n_tiles), MVR_THREADS, 0, st, p);
   rc = check_launch("mesh_backward_kernel");
   if (rc) return rc;
   const int wpb = 8;
-  mesh_backward_reduce_kernel<<<(unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st>>>((const float*)workspace, (int)N, n_tiles, gR, gT, gC);
+  MVR_LAUNCH(mesh_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)workspace, (int)N, n_tiles, gR, gT, gC);
   return check_launch("mesh_backward_reduce_kernel");
 }

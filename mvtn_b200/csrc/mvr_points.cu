@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
         if (pid < 0) break;
         float px, py, pz; project_point(pts, pid, s, cam, px, py, pz);
         const float dx = px - xf, dy = py - yf;
-        const float a = 1.f - (dx * dx + dy * dy) * inv_r2;
+        const float a = 1.f - (dx * dx + dy * dy) / p.r2_weight;   // exactly the forward's alpha: it is clamped at 1e-4 below
         const float* f = feat + (per_point_rgb ? 3 * (size_t)pid : 0);
         const float wgt = alpha_mode ? cum * a : a;
         tf0 = fmaf(wgt, __ldg(f), tf0); tf1 = fmaf(wgt, __ldg(f + 1), tf1); tf2 = fmaf(wgt, __ldg(f + 2), tf2);
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
       const float X0 = __ldg(pts + 3 * (size_t)pid), X1 = __ldg(pts + 3 * (size_t)pid + 1), X2 = __ldg(pts + 3 * (size_t)pid + 2);
       float px, py, pz; world_to_view(cam, X0 * s, X1 * s, X2 * s, px, py, pz);
       const float dx = px - xf, dy = py - yf;
-      const float a = 1.f - (dx * dx + dy * dy) * inv_r2;
+      const float a = 1.f - (dx * dx + dy * dy) / p.r2_weight;   // exactly the forward's alpha: it is clamped at 1e-4 below
       const float* f = feat + (per_point_rgb ? 3 * (size_t)pid : 0);
       const float f0 = __ldg(f), f1 = __ldg(f + 1), f2 = __ldg(f + 2);
       float ga, gf;   // d/d alpha_k ; d/d f_k (per unit grad_out, same for all channels)
@@ -321,7 +321,7 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
     cudaError_t e = cudaFuncSetAttribute(points_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("mvr_points_forward: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   }
-  points_forward_kernel<<<(unsigned)(N * p.n_strips), MVR_THREADS, smem, (cudaStream_t)stream>>>(p);
+  MVR_LAUNCH(points_forward_kernel, (unsigned)(N * p.n_strips), MVR_THREADS, smem, (cudaStream_t)stream, p);
   return check_launch("points_forward_kernel");
 }
 
@@ -347,10 +347,10 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
   p.idx = idx; p.grad_images = grad_images; p.partials = (float*)workspace;
   p.grad_points = grad_points; p.grad_rgb = grad_rgb;
   cudaStream_t st = (cudaStream_t)stream;
-  points_backward_kernel<<<(unsigned)(N * p.n_strips), MVR_THREADS, 0, st>>>(p);
+  MVR_LAUNCH(points_backward_kernel, (unsigned)(N * p.n_strips), MVR_THREADS, 0, st, p);
   rc = check_launch("points_backward_kernel");
   if (rc) return rc;
   const int wpb = 8;
-  points_backward_reduce_kernel<<<(unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st>>>((const float*)workspace, (int)N, p.n_strips, gR, gT, g_inv_dist);
+  MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)workspace, (int)N, p.n_strips, gR, gT, g_inv_dist);
   return check_launch("points_backward_reduce_kernel");
 }

@@ -1,6 +1,10 @@
 // mvr_util.cu -- error reporting shared by the C-ABI entry points.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "mvr_common.cuh"
 
@@ -23,7 +27,64 @@ int check_launch(const char* what) {
   return (int)e;
 }
 
+// ---- launch accounting / per-kernel device timing (bench.py's roofline leg) ---------------------
+static const int kMaxProfEvents = 8192;
+static std::atomic<long long> g_launches{0};
+static std::mutex g_prof_mu;
+static char g_prof_name[64] = "";
+static std::vector<cudaEvent_t> g_prof_events;   // start/stop pairs, created lazily and reused
+static int g_prof_used = 0;                        // number of events recorded (2 per launch)
+
+void prof_begin(const char* name, cudaStream_t st) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_name[0]) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (strcmp(name, g_prof_name) != 0 || g_prof_used + 2 > kMaxProfEvents) return;
+  while ((int)g_prof_events.size() < g_prof_used + 2) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    g_prof_events.push_back(e);
+  }
+  cudaEventRecord(g_prof_events[g_prof_used], st);
+}
+void prof_end(const char* name, cudaStream_t st) {
+  if (!g_prof_name[0]) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (strcmp(name, g_prof_name) != 0 || g_prof_used + 2 > (int)g_prof_events.size()) return;
+  cudaEventRecord(g_prof_events[g_prof_used + 1], st);
+  g_prof_used += 2;
+}
+
 }  // namespace mvr
+
+extern "C" long long mvr_launch_count(void) { return mvr::g_launches.load(); }
+
+extern "C" int mvr_profile_enable(const char* kernel_name) {
+  std::lock_guard<std::mutex> lk(mvr::g_prof_mu);
+  mvr::g_prof_used = 0;
+  if (!kernel_name) { mvr::g_prof_name[0] = 0; return 0; }
+  strncpy(mvr::g_prof_name, kernel_name, sizeof(mvr::g_prof_name) - 1);
+  mvr::g_prof_name[sizeof(mvr::g_prof_name) - 1] = 0;
+  return 0;
+}
+
+extern "C" int mvr_profile_collect(double* total_ms, int* n_launches) {
+  std::lock_guard<std::mutex> lk(mvr::g_prof_mu);
+  double tot = 0.0;
+  int n = 0;
+  for (int i = 0; i + 1 < mvr::g_prof_used; i += 2) {
+    cudaError_t e = cudaEventSynchronize(mvr::g_prof_events[i + 1]);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, mvr::g_prof_events[i], mvr::g_prof_events[i + 1]);
+    if (e != cudaSuccess) { mvr::set_error("mvr_profile_collect: %s", cudaGetErrorString(e)); return (int)e; }
+    tot += ms; ++n;
+  }
+  if (total_ms) *total_ms = tot;
+  if (n_launches) *n_launches = n;
+  mvr::g_prof_used = 0;
+  mvr::g_prof_name[0] = 0;
+  return 0;
+}
 
 extern "C" int mvr_abi_version(void) { return MVR_ABI_VERSION; }
 extern "C" const char* mvr_last_error_string(void) { return mvr::g_err; }

@@ -44,6 +44,29 @@ def workspace(device, nbytes: int) -> torch.Tensor:
     return w
 
 
+_staging_bufs = {}
+
+
+def _staging(tag, device, numel: int, dtype) -> torch.Tensor:
+    """Reusable pinned host buffer for one async H2D copy; reuse waits for the previous copy's event."""
+    key = (tag, torch.device(device).index, dtype)
+    buf, ev = _staging_bufs.get(key, (None, None))
+    if ev is not None:
+        ev.synchronize()
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(max(numel, 1), dtype=dtype, pin_memory=True)
+    _staging_bufs[key] = (buf, None)
+    return buf[:numel]
+
+
+def _staging_done(device):
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    for key, (buf, old) in list(_staging_bufs.items()):
+        if key[1] == torch.device(device).index and old is None:
+            _staging_bufs[key] = (buf, ev)
+
+
 def fov_projection_scale(fov_deg: float = 60.0, znear: float = 1.0, aspect: float = 1.0):
     """K00, K11 of [upstream] FoVPerspectiveCameras.compute_projection_matrix, evaluated with the same
     fp32 tensor ops (fov*pi/180, tan(fov/2)*znear, 2*znear/(max-min))."""
@@ -76,6 +99,7 @@ class _LookAt(torch.autograd.Function):
             L.check(lib.mvr_look_at_forward(_ptr(a), _ptr(e), _ptr(d), n, _ptr(R), _ptr(T), _ptr(Cc), _ptr(bad),
                                             _stream(dev)), "mvr_look_at_forward")
         ctx.save_for_backward(a, e, d)
+        ctx.set_materialize_grads(False)
         ctx.shapes = (azim.shape, elev.shape, dist.shape)
         ctx.mark_non_differentiable(bad)
         return R, T, Cc, bad
@@ -86,6 +110,8 @@ class _LookAt(torch.autograd.Function):
         a, e, d = ctx.saved_tensors
         n = a.numel()
         dev = a.device
+        if gR is None and gT is None and gC is None:
+            return None, None, None
         gR = None if gR is None else _f32c(gR)
         gT = None if gT is None else _f32c(gT)
         gC = None if gC is None else _f32c(gC)
@@ -119,43 +145,74 @@ class PackedMeshes:
 
     def __init__(self, verts: Sequence[torch.Tensor], faces: Sequence[torch.Tensor], device,
                  vert_rgb: Optional[torch.Tensor] = None):
-        lib = L.load()
+        """verts: list of (V_b,3) float tensors, faces: list of (F_b,3) int tensors (any device).  Host lists
+        are staged through one pinned buffer and copied with ONE async H2D per array instead of the
+        reference's 2B small copies (renderer.py:67-68)."""
         device = torch.device(device)
         if device.type != "cuda":
             raise L.MVRError("PackedMeshes needs a CUDA device: mvtn_b200 has no CPU path")
         if len(verts) != len(faces):
             raise ValueError("verts and faces lists differ in length")
-        self.B = len(verts)
-        nv = [int(v.shape[0]) for v in verts]
-        nf = [int(f.shape[0]) for f in faces]
         for v, f in zip(verts, faces):
             if v.dim() != 2 or v.shape[1] != 3 or f.dim() != 2 or f.shape[1] != 3:
                 raise ValueError("verts must be (V,3) and faces (F,3)")
+        nv = [int(v.shape[0]) for v in verts]
+        nf = [int(f.shape[0]) for f in faces]
+        tv, tf = sum(nv), sum(nf)
+        if len(verts) == 0:
+            v_dev = torch.zeros((0, 3), dtype=torch.float32, device=device)
+            f_dev = torch.zeros((0, 3), dtype=torch.int64, device=device)
+        else:
+            fdt = torch.int32 if all(f.dtype == torch.int32 for f in faces) else torch.int64
+            if all(v.is_cuda for v in verts) and all(f.is_cuda for f in faces):
+                v_dev = torch.cat([v.detach().to(torch.float32) for v in verts], 0)
+                f_dev = torch.cat([f.detach().to(fdt) for f in faces], 0)
+            else:
+                v_host = _staging("verts", device, tv * 3, torch.float32).view(tv, 3)
+                f_host = _staging("faces", device, tf * 3, fdt).view(tf, 3)
+                if tv:
+                    torch.cat([v.detach().to(device="cpu", dtype=torch.float32) for v in verts], 0, out=v_host)
+                if tf:
+                    torch.cat([f.detach().to(device="cpu", dtype=fdt) for f in faces], 0, out=f_host)
+                v_dev = v_host.to(device, non_blocking=True)
+                f_dev = f_host.to(device, non_blocking=True)
+                _staging_done(device)
+        self._init_packed(v_dev, f_dev, nv, nf, device, vert_rgb)
+
+    @classmethod
+    def from_packed(cls, verts: torch.Tensor, faces: torch.Tensor, num_verts: Sequence[int], num_faces: Sequence[int],
+                    vert_rgb: Optional[torch.Tensor] = None):
+        """Already-packed device arrays: verts (Vtot,3) f32, faces (Ftot,3) int32/int64 (mesh-local ids)."""
+        self = cls.__new__(cls)
+        _require_cuda(verts, "verts")
+        _require_cuda(faces, "faces")
+        self._init_packed(verts, faces, list(num_verts), list(num_faces), verts.device, vert_rgb)
+        return self
+
+    def _init_packed(self, v_dev, f_dev, nv, nf, device, vert_rgb):
+        lib = L.load()
+        self.B = len(nv)
         self.num_verts, self.num_faces = nv, nf
         self.total_verts, self.total_faces = sum(nv), sum(nf)
         self.max_faces = max(nf) if nf else 0
-        voff = [0]
-        foff = [0]
+        if v_dev.shape[0] != self.total_verts or f_dev.shape[0] != self.total_faces:
+            raise ValueError("packed arrays do not match the per-mesh counts")
+        voff, foff = [0], [0]
         for a in nv:
             voff.append(voff[-1] + a)
         for a in nf:
             foff.append(foff[-1] + a)
         self.vert_off_host, self.face_off_host = voff, foff
         self.device = device
-        if self.B == 0:
-            return
-        # one staged host->device copy per array instead of 2B small ones (renderer.py:67-68)
-        v_all = torch.cat([v.detach().to(torch.float32) for v in verts], 0) if self.total_verts else torch.zeros(0, 3)
-        f_all = torch.cat([f.detach() for f in faces], 0) if self.total_faces else torch.zeros(0, 3, dtype=torch.int64)
-        if f_all.dtype not in (torch.int32, torch.int64):
-            f_all = f_all.to(torch.int64)
-        self.verts = v_all.to(device, non_blocking=True).contiguous()
-        self.faces = f_all.to(device, non_blocking=True).contiguous()
+        self.per_vertex_rgb = vert_rgb is not None
+        self.verts = v_dev.detach().to(torch.float32).contiguous()
+        if f_dev.dtype not in (torch.int32, torch.int64):
+            f_dev = f_dev.to(torch.int64)
+        self.faces = f_dev.contiguous()
         offs = torch.tensor(voff + foff, dtype=torch.int32).to(device, non_blocking=True)
         self.vert_off, self.face_off = offs[: self.B + 1], offs[self.B + 1:]
         flags = L.FACES_I64 if self.faces.dtype == torch.int64 else 0
         rgb = None
-        self.per_vertex_rgb = vert_rgb is not None
         if vert_rgb is not None:
             rgb = _f32c(vert_rgb.to(device)).reshape(-1, 3)
             if rgb.shape[0] != self.total_verts:
@@ -163,6 +220,8 @@ class PackedMeshes:
             flags |= L.RGB_PER_ELEMENT
         nbytes = lib.mvr_mesh_geometry_bytes(self.total_verts, self.total_faces)
         self.geometry = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        if self.B == 0:
+            return
         with torch.cuda.device(device):
             L.check(lib.mvr_mesh_prepare(_ptr(self.verts), _ptr(self.faces), _ptr(self.vert_off), _ptr(self.face_off),
                                          self.B, self.total_verts, self.total_faces, self.max_faces, _ptr(rgb), flags,
@@ -214,6 +273,7 @@ class _MeshRender(torch.autograd.Function):
                                          _ptr(light), light_stride, _ptr(obj_rgb), _ptr(bg_rgb), k00, k11, z_clip, H, W,
                                          K, flags, _ptr(images), _ptr(p2f), _ptr(zbuf), _ptr(bary), _ptr(dists),
                                          _ptr(counters), _ptr(ws), ws.numel(), _stream(dev)), "mvr_mesh_forward")
+        ctx.set_materialize_grads(False)      # no zero-filled "gradients" for pix_to_face & co (77 MB at C2)
         ctx.geom, ctx.M, ctx.light_stride = geom, M, light_stride
         ctx.cfg = (k00, k11, H, W, K, flags)
         ctx.save_for_backward(R, T, Cc, light, obj_rgb if obj_rgb is not None else bg_rgb, p2f)
@@ -226,6 +286,8 @@ class _MeshRender(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_images, *_unused):
         lib = L.load()
+        if g_images is None:
+            return (None,) * 16
         geom, M = ctx.geom, ctx.M
         R, T, Cc, light, obj_rgb, p2f = ctx.saved_tensors
         k00, k11, H, W, K, flags = ctx.cfg
@@ -248,12 +310,12 @@ class _MeshRender(torch.autograd.Function):
 
 def render_meshes(geom: PackedMeshes, M: int, R, T, Cc, light, obj_rgb, bg_rgb, image_size: int, faces_per_pixel=1,
                   cull_backfaces=False, perspective_correct=True, fov=60.0, znear=1.0, z_clip: Optional[float] = None,
-                  fragments=False):
+                  fragments=False, _extra_flags=0):
     """images (B*M,3,H,W) [+ dict of fragments].  HardPhong + hard blend, blur_radius 0."""
     k00, k11 = fov_projection_scale(fov, znear)
     if z_clip is None:
         z_clip = znear / 2 if perspective_correct else -1.0   # [upstream] MeshRasterizer.forward
-    flags = (L.PERSPECTIVE_CORRECT if perspective_correct else 0) | (L.CULL_BACKFACES if cull_backfaces else 0)
+    flags = (L.PERSPECTIVE_CORRECT if perspective_correct else 0) | (L.CULL_BACKFACES if cull_backfaces else 0) | _extra_flags
     out = _MeshRender.apply(R, T, Cc, geom, M, light, obj_rgb, bg_rgb, k00, k11, float(z_clip), image_size, image_size,
                             int(faces_per_pixel), flags, bool(fragments))
     images, p2f, counters = out[0], out[1], out[2]
@@ -296,6 +358,7 @@ class _PointsRender(torch.autograd.Function):
             L.check(lib.mvr_points_forward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), float(radius),
                                            _ptr(bg_rgb), H, W, K, flags, _ptr(images), _ptr(idx), _ptr(zbuf), _ptr(d2),
                                            None, 0, _stream(dev)), "mvr_points_forward")
+        ctx.set_materialize_grads(False)
         ctx.cfg = (B, Np, M, float(radius), H, W, K, flags)
         ctx.rgb_shape = rgb.shape
         ctx.points_shape = points.shape
@@ -307,6 +370,8 @@ class _PointsRender(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_images, *_unused):
         lib = L.load()
+        if g_images is None:
+            return (None,) * 13
         R, T, inv_dist, pts, rgb, idx = ctx.saved_tensors
         B, Np, M, radius, H, W, K, flags = ctx.cfg
         dev = pts.device

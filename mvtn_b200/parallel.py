@@ -1,0 +1,106 @@
+"""Object-sharded data parallelism for the rendering path.
+
+Every (object, view) is independent (renderer.py:105,141 replicate per view; no cross-object term), so
+rendering needs NO collective: each rank renders a contiguous range of objects.  A collective (NCCL
+all-reduce over NVLink) is only needed for the network gradients of the training configuration.
+One process per GPU, launched with torchrun; rendezvous through RANK / WORLD_SIZE / MASTER_* env.
+"""
+import os
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def env_world() -> Tuple[int, int, int]:
+    """(rank, local_rank, world_size) from the torchrun environment (1 process => (0, 0, 1))."""
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def init_distributed(backend: str = None):
+    rank, local_rank, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        kwargs = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kwargs["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
+    return rank, local_rank, world
+
+
+def shard_range(num_objects: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous object range [lo, hi) of `rank`: sizes differ by at most one, order preserved."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, rem = divmod(num_objects, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_by_weight(weights: Sequence[float], world: int) -> List[Tuple[int, int]]:
+    """Contiguous partition of ragged objects balancing sum(weights) (e.g. faces or points per object):
+    cut i is placed where the prefix sum first reaches i/world of the total."""
+    n = len(weights)
+    total = float(sum(weights))
+    cuts = [0]
+    acc, j = 0.0, 0
+    for r in range(1, world):
+        target = total * r / world
+        while j < n and acc + weights[j] / 2.0 <= target:
+            acc += weights[j]
+            j += 1
+        cuts.append(max(j, cuts[-1]))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def barrier():
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Max of a per-rank scalar (device-timed milliseconds) over all ranks."""
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def allreduce_gradients(params, bucket_bytes: int = 32 << 20, average: bool = True):
+    """Bucketed gradient all-reduce for the training configuration (BASELINE config 4): the MVTN
+    regressor and CNN backbone gradients, ~60 MB fp32, in flat buckets sized for launch latency."""
+    if not dist.is_initialized():
+        return 0
+    world = dist.get_world_size()
+    grads = [p.grad for p in params if p.grad is not None]
+    n_buckets, i = 0, 0
+    while i < len(grads):
+        bucket, size = [], 0
+        while i < len(grads) and (not bucket or size + grads[i].numel() * grads[i].element_size() <= bucket_bytes):
+            bucket.append(grads[i])
+            size += grads[i].numel() * grads[i].element_size()
+            i += 1
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat)
+        if average:
+            flat /= world
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        n_buckets += 1
+    return n_buckets

@@ -114,7 +114,7 @@ class MVRenderer(nn.Module):
         device = self._device(azim)
         if points.shape[0] != azim.shape[0]:
             raise ValueError(f"{points.shape[0]} clouds but azim has batch {azim.shape[0]}")
-        pts = points.to(device=device, dtype=torch.float32)
+        pts = points.to(device=device, dtype=torch.float32, non_blocking=True)
         bg = torch.as_tensor(background_color, dtype=torch.float32).to(device)
         rgb = torch.as_tensor(color, dtype=torch.float32).to(device)
         if rgb.numel() != 3:

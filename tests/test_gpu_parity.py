@@ -1,0 +1,462 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI
+(mvtn_b200.ops -> libmvr_b200.so), against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * fragment indices (pix_to_face / idx): BIT-EXACT with the oracle given the same R, T (protocol stage A);
+    exact depth ties are counted (the (z, index) rule makes them reproducible, so they must match too);
+  * zbuf / barycentrics / dists2: bit-exact as well (same IEEE operation order, no FMA contraction);
+  * images: |a-b| <= 1e-5 (values in [0,1]);
+  * gradients: max|a-b| <= GRAD_RTOL * max|ref| per tensor, GRAD_RTOL = 1e-4 against the oracle's fp64-accumulated
+    result (the CUDA chain is fp32 like PyTorch3D's; 1e-5 holds for the point path, the mesh shading chain has
+    fp32 cancellation in the normalisations and is held to 1e-4);
+  * look_at itself (sinf/cosf differ between CUDA and glibc): 2e-6 absolute on R/T (protocol stage B).
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mvtn_b200 import MVRenderer, Meshes, ops, synth
+from mvtn_b200 import _lib as L
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+IMG_ATOL = 1e-5
+GRAD_RTOL = 1e-4
+POINT_GRAD_RTOL = 1e-5
+K00, K11 = ops.fov_projection_scale()
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def rel(a, b, floor=1e-6):
+    a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), floor))
+
+
+def cams(oracle, views, dev):
+    az, el, di = (t.numpy().ravel() for t in views)
+    R, T, C = oracle.look_at(az, el, di)
+    return R, T, C, tuple(torch.from_numpy(x).to(dev) for x in (R, T, C))
+
+
+def pack_np(meshes):
+    vp = torch.cat([v for v, _ in meshes]).numpy()
+    fp = torch.cat([f for _, f in meshes]).numpy().astype(np.int32)
+    voff = np.cumsum([0] + [v.shape[0] for v, _ in meshes]).astype(np.int32)
+    foff = np.cumsum([0] + [f.shape[0] for _, f in meshes]).astype(np.int32)
+    return vp, fp, voff, foff
+
+
+# ------------------------------------------------------------------------------------------------ cameras
+def test_look_at_forward_backward(oracle, cuda_device):
+    g = torch.Generator().manual_seed(0)
+    az = torch.rand(257, generator=g) * 360 - 180; el = torch.rand(257, generator=g) * 170 - 85; di = torch.rand(257, generator=g) * 2 + 1.2
+    az[:4] = torch.tensor([0., 90., -90., 180.]); el[:4] = 0; di[:4] = 2.2
+    a, e, d = (t.to(cuda_device).requires_grad_() for t in (az, el, di))
+    R, T, C, bad = ops._LookAt.apply(a, e, d)
+    Ro, To, Co = oracle.look_at(az.numpy(), el.numpy(), di.numpy())
+    assert int(bad) == 0
+    assert np.abs(R.detach().cpu().numpy() - Ro).max() < 2e-6
+    assert np.abs(T.detach().cpu().numpy() - To).max() < 2e-6
+    assert np.abs(C.detach().cpu().numpy() - Co).max() < 2e-6
+    assert torch.allclose(R[0].cpu(), torch.diag(torch.tensor([-1.0, 1.0, -1.0])), atol=1e-6)
+    gR, gT, gC = torch.randn(257, 3, 3, generator=g), torch.randn(257, 3, generator=g), torch.randn(257, 3, generator=g)
+    ((R * gR.to(cuda_device)).sum() + (T * gT.to(cuda_device)).sum() + (C * gC.to(cuda_device)).sum()).backward()
+    ga, ge, gd = oracle.look_at_backward(az.numpy(), el.numpy(), di.numpy(), gR.numpy(), gT.numpy(), gC.numpy())
+    assert rel(a.grad, ga) < 1e-5 and rel(e.grad, ge) < 1e-5 and rel(d.grad, gd) < 1e-5
+
+
+def test_rotation_guard_flag_matches_oracle(oracle, cuda_device):
+    # nan / inf angles and zero distance give invalid matrices; the fused device check must count like util.py:403-420
+    az = torch.tensor([0.0, 10.0, float("nan"), 30.0]); el = torch.tensor([0.0, 20.0, 0.0, 0.0]); di = torch.tensor([2.2, 0.0, 2.0, 2.0])
+    R, T, C, bad = ops._LookAt.apply(az.to(cuda_device), el.to(cuda_device), di.to(cuda_device))
+    Ro, _, _ = oracle.look_at(az.numpy(), el.numpy(), di.numpy())
+    assert int(bad) == oracle.count_invalid_rotations(Ro) == 2
+
+
+# ------------------------------------------------------------------------------------------------- meshes
+CUBE_V = torch.tensor([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]],
+                      dtype=torch.float32) * 0.55
+CUBE_F = torch.tensor([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [2, 3, 7], [2, 7, 6], [1, 2, 6], [1, 6, 5],
+                       [0, 4, 7], [0, 7, 3]])
+
+
+def mesh_case(name):
+    if name == "small":
+        return dict(meshes=synth.make_meshes(1, 300, 1), M=4, H=32, K=1, views=synth.circular_views(1, 4))
+    if name == "spherical":
+        return dict(meshes=synth.make_meshes(2, 2000, 2), M=4, H=64, K=1, views=synth.learned_spherical_views(2, 4, 9))
+    if name == "ragged_k3":
+        return dict(meshes=[synth.make_mesh(200, 4), synth.make_mesh(1200, 5), synth.make_mesh(60, 6)], M=2, H=50, K=3,
+                    views=synth.learned_spherical_views(3, 2, 1))
+    if name == "cube_big_faces":
+        return dict(meshes=[(CUBE_V, CUBE_F)], M=4, H=96, K=2, views=synth.learned_spherical_views(1, 4, 3))
+    if name == "cull_noperspective":
+        return dict(meshes=synth.make_meshes(1, 800, 7), M=3, H=40, K=1, views=synth.learned_spherical_views(1, 3, 4), persp=False, cull=True)
+    if name == "vertex_rgb":
+        m = synth.make_meshes(1, 600, 8)
+        return dict(meshes=m, M=3, H=48, K=1, views=synth.learned_spherical_views(1, 3, 5),
+                    vert_rgb=torch.rand(m[0][0].shape[0], 3, generator=torch.Generator().manual_seed(1)))
+    if name == "relative_light":
+        return dict(meshes=synth.make_meshes(2, 500, 9), M=3, H=40, K=1, views=synth.learned_spherical_views(2, 3, 6), light="relative")
+    if name == "close_camera_400":
+        v = synth.learned_spherical_views(1, 2, 7)
+        return dict(meshes=synth.make_meshes(1, 3000, 10), M=2, H=100, K=2, views=(v[0], v[1], v[2] * 0 + 1.25))
+    if name == "c2_slice":
+        return dict(meshes=synth.make_meshes(1, 10000, 12), M=2, H=224, K=1, views=synth.circular_views(1, 2))
+    if name == "dense_subpixel":
+        return dict(meshes=synth.make_meshes(1, 20000, 13), M=2, H=64, K=1, views=synth.learned_spherical_views(1, 2, 8))
+    raise KeyError(name)
+
+
+MESH_CASES = ["small", "spherical", "ragged_k3", "cube_big_faces", "cull_noperspective", "vertex_rgb", "relative_light",
+              "close_camera_400", "c2_slice", "dense_subpixel"]
+
+
+def run_mesh(oracle, dev, cfg, backward=True, extra_flags=0):
+    meshes, M, H, K = cfg["meshes"], cfg["M"], cfg["H"], cfg["K"]
+    persp, cull = cfg.get("persp", True), cfg.get("cull", False)
+    vert_rgb = cfg.get("vert_rgb")
+    B = len(meshes)
+    geom = ops.PackedMeshes([v for v, _ in meshes], [f for _, f in meshes], dev, vert_rgb=vert_rgb)
+    R, T, C, (Rd, Td, Cd) = cams(oracle, cfg["views"], dev)
+    light = C.copy() if cfg.get("light") == "relative" else np.array([cfg.get("light_dir", [0.3, 1.0, -0.5])], np.float32)
+    obj = np.full(3, 0.99999, np.float32); bg = np.array([0.5, 0.25, 0.75], np.float32)
+    Rg, Tg, Cg = (t.clone().requires_grad_() for t in (Rd, Td, Cd))
+    flags_note = extra_flags
+    img, frag = ops.render_meshes(geom, M, Rg, Tg, Cg, torch.from_numpy(light).to(dev), None if vert_rgb is not None else torch.from_numpy(obj).to(dev),
+                                  torch.from_numpy(bg).to(dev), H, faces_per_pixel=K, cull_backfaces=cull, perspective_correct=persp,
+                                  fragments=True, _extra_flags=flags_note)
+    vp, fp, voff, foff = pack_np(meshes)
+    nrm = oracle.packed_vertex_normals(vp, fp, voff, foff)
+    assert np.abs(geom.vertex_normals().cpu().numpy() - nrm).max() < 5e-7
+    oflags = (oracle.PERSPECTIVE_CORRECT if persp else 0) | (oracle.CULL_BACKFACES if cull else 0)
+    rgb = obj if vert_rgb is None else vert_rgb.numpy()
+    o = oracle.mesh_forward(vp, fp, voff, foff, nrm, rgb, M, R, T, C, light, bg, K00, K11, 0.5 if persp else -1.0, H, H, K, oflags)
+    p2f = frag["pix_to_face"].cpu().numpy()
+    res = dict(o=o, frag=frag, img=img, geom=geom, p2f=p2f)
+    # exact depth ties inside a pixel's K-list (counted and reported); they must still agree
+    zb = o["zbuf"]
+    res["ties"] = int(((zb[..., 1:] == zb[..., :-1]) & (o["pix_to_face"][..., 1:] >= 0)).sum()) if K > 1 else 0
+    assert (p2f == o["pix_to_face"]).all(), f"{int((p2f != o['pix_to_face']).sum())} fragment index mismatches"
+    assert (frag["zbuf"].cpu().numpy() == o["zbuf"]).all()
+    assert (frag["bary_coords"].cpu().numpy() == o["bary"]).all()
+    assert (frag["dists"].cpu().numpy() == o["dists"]).all()
+    assert np.abs(img.detach().cpu().numpy() - o["images"]).max() <= IMG_ATOL
+    assert int(frag["counters"][L.CNT_STRADDLE]) == o["straddle"]
+    if backward:
+        g = torch.randn(B * M, 3, H, H, generator=torch.Generator().manual_seed(5))
+        img.backward(g.to(dev))
+        ob = oracle.mesh_backward(vp, fp, voff, foff, nrm, rgb, M, R, T, C, light, K00, K11, H, H, K, oflags, p2f, g.numpy())
+        assert rel(Rg.grad, ob["gR"]) < GRAD_RTOL
+        assert rel(Tg.grad, ob["gT"]) < GRAD_RTOL
+        assert rel(Cg.grad, ob["gC"]) < GRAD_RTOL
+    return res
+
+
+@pytest.mark.parametrize("name", MESH_CASES)
+def test_mesh_parity(oracle, cuda_device, name):
+    res = run_mesh(oracle, cuda_device, mesh_case(name))
+    cov = (res["p2f"][..., 0] >= 0).mean()
+    assert 0.05 < cov <= 1.0
+    print(f"[{name}] coverage {cov:.3f} exact-depth ties {res['ties']}")
+
+
+def test_mesh_bin_overflow_fallback_is_exact(oracle, cuda_device):
+    # a 64-entry pool forces every chunk onto the unbinned fallback: results must not change
+    res = run_mesh(oracle, cuda_device, mesh_case("spherical"), backward=False, extra_flags=L.TEST_TINY_POOL)
+    assert int(res["frag"]["counters"][L.CNT_BIN_OVERFLOW]) > 0
+
+
+def test_mesh_duplicate_faces_tie_rule(oracle, cuda_device):
+    v, f = synth.make_mesh(400, 3)
+    f2 = torch.cat([f, f, f[:50]])                       # every face twice (some thrice): exact depth ties everywhere
+    res = run_mesh(oracle, cuda_device, dict(meshes=[(v, f2)], M=3, H=48, K=3, views=synth.learned_spherical_views(1, 3, 2)), backward=False)
+    assert res["ties"] > 100
+    p = res["p2f"]
+    hit = p[..., 1] >= 0
+    assert (p[..., 0][hit] < p[..., 1][hit]).any()
+
+
+def test_mesh_face_permutation_invariance(oracle, cuda_device):
+    v, f = synth.make_mesh(1500, 21)
+    views = synth.learned_spherical_views(1, 3, 4)
+    perm = torch.randperm(f.shape[0], generator=torch.Generator().manual_seed(0))
+    a = run_mesh(oracle, cuda_device, dict(meshes=[(v, f)], M=3, H=64, K=1, views=views), backward=False)
+    b = run_mesh(oracle, cuda_device, dict(meshes=[(v, f[perm])], M=3, H=64, K=1, views=views), backward=False)
+    pa, pb = a["p2f"][..., 0], b["p2f"][..., 0]
+    assert ((pa >= 0) == (pb >= 0)).all()
+    m = pa >= 0
+    assert (perm.numpy()[pb[m]] == pa[m]).all()          # same winning face (no exact ties in this mesh)
+    assert np.abs(a["img"].detach().cpu().numpy() - b["img"].detach().cpu().numpy()).max() <= 2e-6
+
+
+def test_mesh_edge_cases(oracle, cuda_device):
+    dev = cuda_device
+    # single triangle facing the camera; and an object entirely behind the camera / off screen
+    tri_v = torch.tensor([[-0.5, -0.5, 0.0], [0.5, -0.5, 0.0], [0.0, 0.6, 0.0]]); tri_f = torch.tensor([[0, 1, 2]])
+    run_mesh(oracle, dev, dict(meshes=[(tri_v, tri_f)], M=2, H=33, K=2, views=(torch.tensor([[0.0, 40.0]]), torch.tensor([[10.0, 30.0]]), torch.tensor([[2.2, 2.0]])),
+                           light_dir=[0.3, 0.5, 0.8]), backward=True)
+    far = tri_v + torch.tensor([0.0, 0.0, 50.0])
+    res = run_mesh(oracle, dev, dict(meshes=[(far, tri_f)], M=1, H=16, K=1, views=(torch.tensor([[0.0]]), torch.tensor([[0.0]]), torch.tensor([[2.0]]))),
+                   backward=False)
+    assert (res["p2f"] == -1).all()
+    # empty batch: a no-op, not an error
+    geom = ops.PackedMeshes([], [], dev)
+    z = torch.zeros(0, 3, device=dev)
+    img, frag = ops.render_meshes(geom, 4, torch.zeros(0, 3, 3, device=dev), z, z, torch.tensor([[0, 1.0, 0]], device=dev),
+                                  torch.ones(3, device=dev), torch.ones(3, device=dev), 32)
+    assert img.shape == (0, 3, 32, 32)
+    # camera/mesh count mismatch raises ValueError like upstream
+    geom = ops.PackedMeshes([tri_v], [tri_f], dev)
+    with pytest.raises(ValueError):
+        ops.render_meshes(geom, 2, torch.zeros(3, 3, 3, device=dev), torch.zeros(3, 3, device=dev), torch.zeros(3, 3, device=dev),
+                          torch.tensor([[0, 1.0, 0]], device=dev), torch.ones(3, device=dev), torch.ones(3, device=dev), 32)
+    with pytest.raises(L.MVRError, match="faces_per_pixel"):
+        Rd = torch.eye(3, device=dev)[None]
+        ops.render_meshes(geom, 1, Rd, torch.tensor([[0, 0, 2.0]], device=dev), torch.tensor([[0, 0, 2.0]], device=dev),
+                          torch.tensor([[0, 1.0, 0]], device=dev), torch.ones(3, device=dev), torch.ones(3, device=dev), 32, faces_per_pixel=100)
+
+
+def test_mesh_near_plane_counters(oracle, cuda_device):
+    # dist 1.1 with a unit-sphere object: faces cross z_clip = znear/2; they are culled / counted like the oracle
+    m = synth.make_meshes(1, 2000, 31)
+    v = (torch.tensor([[0.0, 90.0]]), torch.tensor([[0.0, 10.0]]), torch.tensor([[1.02, 1.05]]))
+    res = run_mesh(oracle, cuda_device, dict(meshes=m, M=2, H=64, K=1, views=v), backward=False)
+    assert res["o"]["straddle"] > 0
+
+
+def test_mesh_golden_slice(cuda_device):
+    g = np.load(os.path.join(GOLDEN, "mesh_c2_slice.npz"))
+    dev = cuda_device
+    geom = ops.PackedMeshes([torch.from_numpy(g["verts"])], [torch.from_numpy(g["faces"])], dev)
+    R, T, C = (torch.from_numpy(g[k]).to(dev) for k in ("R", "T", "C"))
+    col = torch.full((3,), 0.99999, device=dev)
+    img, frag = ops.render_meshes(geom, 12, R, T, C, torch.tensor([[0, 1.0, 0]], device=dev), col, col, 224, fragments=True)
+    assert sha(frag["pix_to_face"].cpu().numpy()) == str(g["p2f_sha256"])
+    assert sha(frag["zbuf"].cpu().numpy()) == str(g["zbuf_sha256"])
+    assert sha(frag["bary_coords"].cpu().numpy()) == str(g["bary_sha256"])
+    assert ((frag["pix_to_face"][..., 0] >= 0).sum(dim=(1, 2)).cpu().numpy() == g["covered"]).all()
+    assert np.abs(img.cpu().numpy()[:, :, ::16, ::16] - g["image_probe"]).max() <= IMG_ATOL
+    assert np.allclose(img.double().sum(dim=(1, 2, 3)).cpu().numpy(), g["image_sum"], rtol=1e-6)
+
+
+def test_mesh_full_size_c2_properties(oracle, cuda_device):
+    """BASELINE configs[1] at full size (32 x 12 views, ~10k faces, 224^2): size-independent properties +
+    the oracle on two sampled objects."""
+    dev = cuda_device
+    B, M, H = 32, 12, 224
+    meshes = synth.make_meshes(B, 10000, 1236)
+    views = synth.learned_spherical_views(B, M, 17)
+    geom = ops.PackedMeshes([v for v, _ in meshes], [f for _, f in meshes], dev)
+    R, T, C, (Rd, Td, Cd) = cams(oracle, views, dev)
+    col = torch.full((3,), 0.99999, device=dev); light = torch.tensor([[0, 1.0, 0]], device=dev)
+    img1, f1 = ops.render_meshes(geom, M, Rd, Td, Cd, light, col, col, H)
+    img2, f2 = ops.render_meshes(geom, M, Rd, Td, Cd, light, col, col, H)
+    assert torch.equal(f1["pix_to_face"], f2["pix_to_face"]) and torch.equal(img1, img2)          # run-to-run determinism
+    assert int(f1["counters"][L.CNT_BIN_OVERFLOW]) == 0
+    for b in (0, 19):                                                                              # object independence + oracle
+        gb = ops.PackedMeshes([meshes[b][0]], [meshes[b][1]], dev)
+        s = slice(b * M, (b + 1) * M)
+        imgb, fb = ops.render_meshes(gb, M, Rd[s], Td[s], Cd[s], light, col, col, H)
+        assert torch.equal(fb["pix_to_face"], f1["pix_to_face"][s]) and torch.equal(imgb, img1[s])
+        vp, fp, voff, foff = pack_np([meshes[b]])
+        o = oracle.mesh_forward(vp, fp, voff, foff, oracle.vertex_normals(vp, fp), np.full(3, 0.99999, np.float32), M, R[s], T[s], C[s],
+                                np.array([[0, 1.0, 0]], np.float32), np.full(3, 0.99999, np.float32), K00, K11, 0.5, H, H, 1,
+                                oracle.PERSPECTIVE_CORRECT, fragments=False)
+        assert (fb["pix_to_face"].cpu().numpy() == o["pix_to_face"]).all()
+        assert np.abs(imgb.cpu().numpy() - o["images"]).max() <= IMG_ATOL
+    # backward determinism (fixed-order reductions, no float atomics on this path)
+    g = torch.randn(B * M, 3, H, H, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    grads = []
+    for _ in range(2):
+        Rg, Tg, Cg = (t.clone().requires_grad_() for t in (Rd, Td, Cd))
+        im, _ = ops.render_meshes(geom, M, Rg, Tg, Cg, light, col, col, H)
+        im.backward(g)
+        grads.append((Rg.grad, Tg.grad, Cg.grad))
+    assert all(torch.equal(a, b) for a, b in zip(*grads))
+
+
+# ------------------------------------------------------------------------------------------------- points
+POINT_CASES = {
+    "c1_k1_norm": dict(B=1, Np=2048, M=3, H=224, K=1, radius=0.006, mode="norm", views=synth.circular_views(1, 3)),
+    "k4_alpha_rgb": dict(B=2, Np=500, M=3, H=64, K=4, radius=0.05, mode="alpha", views=synth.learned_spherical_views(2, 3, 2), per_point=True),
+    "k3_norm_rgb": dict(B=2, Np=300, M=2, H=50, K=3, radius=0.04, mode="norm", views=synth.learned_spherical_views(2, 2, 3), per_point=True),
+    "k1_alpha": dict(B=1, Np=1000, M=2, H=100, K=1, radius=0.02, mode="alpha", views=synth.circular_views(1, 2)),
+    "k8_big_radius": dict(B=1, Np=400, M=2, H=40, K=8, radius=0.15, mode="alpha", views=synth.learned_spherical_views(1, 2, 5), per_point=True),
+    "c5_16k_400": dict(B=1, Np=16384, M=2, H=400, K=1, radius=0.006, mode="norm", views=tuple(t[:, 4:6].contiguous() for t in synth.spherical_views(1, 20))),
+}
+
+
+def run_points(oracle, dev, cfg, backward=True, pts=None):
+    B, Np, M, H, K, radius, mode = (cfg[k] for k in ("B", "Np", "M", "H", "K", "radius", "mode"))
+    pts = synth.make_clouds(B, Np, 11) if pts is None else pts
+    R, T, C, (Rd, Td, Cd) = cams(oracle, cfg["views"], dev)
+    inv = (1.0 / cfg["views"][2].reshape(-1)).contiguous()
+    rgb = torch.rand(B, Np, 3, generator=torch.Generator().manual_seed(3)) if cfg.get("per_point") else torch.full((3,), 0.99999)
+    bg = torch.tensor([0.1, 0.2, 0.3])
+    Rg, Tg = Rd.clone().requires_grad_(), Td.clone().requires_grad_()
+    sg, pg, fg = inv.to(dev).requires_grad_(), pts.to(dev).requires_grad_(), rgb.to(dev).requires_grad_()
+    img, frag = ops.render_points(pg, fg, M, Rg, Tg, sg, radius, bg.to(dev), H, points_per_pixel=K, compositor=mode, fragments=True)
+    flags = oracle.COMPOSITE_ALPHA if mode == "alpha" else 0
+    o = oracle.points_forward(pts.numpy(), rgb.numpy(), M, R, T, inv.numpy(), radius, bg.numpy(), H, H, K, flags)
+    idx = frag["idx"].cpu().numpy()
+    assert (idx == o["idx"]).all(), f"{int((idx != o['idx']).sum())} point index mismatches"
+    assert (frag["zbuf"].cpu().numpy() == o["zbuf"]).all()
+    assert (frag["dists"].cpu().numpy() == o["dists2"]).all()
+    assert np.abs(img.detach().cpu().numpy() - o["images"]).max() <= IMG_ATOL
+    if backward:
+        g = torch.randn(B * M, 3, H, H, generator=torch.Generator().manual_seed(6))
+        img.backward(g.to(dev))
+        ob = oracle.points_backward(pts.numpy(), rgb.numpy(), M, R, T, inv.numpy(), radius, H, H, K, flags, idx, g.numpy(),
+                                    want_points=True, want_rgb=True)
+        assert rel(Rg.grad, ob["gR"]) < POINT_GRAD_RTOL
+        assert rel(Tg.grad, ob["gT"]) < POINT_GRAD_RTOL
+        assert rel(sg.grad, ob["g_inv_dist"]) < POINT_GRAD_RTOL
+        assert rel(pg.grad, ob["grad_points"]) < POINT_GRAD_RTOL
+        assert rel(fg.grad, ob["grad_rgb"]) < POINT_GRAD_RTOL
+    return dict(o=o, idx=idx, img=img)
+
+
+@pytest.mark.parametrize("name", list(POINT_CASES))
+def test_points_parity(oracle, cuda_device, name):
+    res = run_points(oracle, cuda_device, POINT_CASES[name])
+    assert (res["idx"][..., 0] >= 0).mean() > 0.005
+
+
+def test_points_duplicates_and_behind_camera(oracle, cuda_device):
+    pts = synth.make_clouds(1, 300, 4)
+    pts = torch.cat([pts, pts[:, :100]], dim=1)                 # 100 exact duplicates: (z, idx) ties
+    cfg = dict(B=1, Np=400, M=2, H=48, K=3, radius=0.06, mode="alpha", views=synth.learned_spherical_views(1, 2, 6))
+    res = run_points(oracle, cuda_device, cfg, pts=pts)
+    zb = res["o"]["zbuf"]
+    assert ((zb[..., 1:] == zb[..., :-1]) & (res["idx"][..., 1:] >= 0)).sum() > 10
+    # a cloud entirely behind the camera renders pure background
+    far = pts * 0.01 + torch.tensor([0.0, 0.0, 10.0])
+    cfg2 = dict(B=1, Np=400, M=1, H=32, K=2, radius=0.06, mode="norm", views=(torch.tensor([[0.0]]), torch.tensor([[0.0]]), torch.tensor([[2.0]])))
+    res = run_points(oracle, cuda_device, cfg2, backward=False, pts=far)
+    assert (res["idx"] == -1).all()
+    assert np.allclose(res["img"].detach().cpu().numpy()[0, :, 3, 3], [0.1, 0.2, 0.3])
+
+
+def test_points_golden(cuda_device):
+    g = np.load(os.path.join(GOLDEN, "points_c1.npz"))
+    dev = cuda_device
+    pts = torch.from_numpy(g["points"]).to(dev)
+    R, T, inv = (torch.from_numpy(g[k]).to(dev) for k in ("R", "T", "inv_dist"))
+    col = torch.full((3,), 0.99999, device=dev)
+    img, frag = ops.render_points(pts, col, 12, R, T, inv, 0.006, torch.zeros(3, device=dev), 224, fragments=True)
+    assert sha(frag["idx"].cpu().numpy()) == str(g["idx_sha256"])
+    assert sha(frag["zbuf"].cpu().numpy()) == str(g["zbuf_sha256"])
+    assert sha(frag["dists"].cpu().numpy()) == str(g["d2_sha256"])
+    assert np.allclose(img.double().sum(dim=(1, 2, 3)).cpu().numpy(), g["image_sum"], rtol=1e-6)
+    img4, frag4 = ops.render_points(pts, col, 12, R, T, inv, 0.02, torch.zeros(3, device=dev), 224, points_per_pixel=4, compositor="alpha")
+    assert sha(frag4["idx"].cpu().numpy()) == str(g["idx4_sha256"])
+    assert np.allclose(img4.double().sum(dim=(1, 2, 3)).cpu().numpy(), g["image4_sum"], rtol=1e-5)
+
+
+def test_points_full_size_c3_properties(oracle, cuda_device):
+    """BASELINE configs[2] at full size: 32 clouds x 12 learned_spherical views, alpha compositing, K=4."""
+    dev = cuda_device
+    B, M, H, K = 32, 12, 224, 4
+    pts = synth.make_clouds(B, 2048, 1237)
+    views = synth.learned_spherical_views(B, M, 23)
+    R, T, C, (Rd, Td, Cd) = cams(oracle, views, dev)
+    inv = (1.0 / views[2].reshape(-1)).to(dev)
+    col = torch.full((3,), 0.99999, device=dev); bg = torch.zeros(3, device=dev)
+    a = ops.render_points(pts.to(dev), col, M, Rd, Td, inv, 0.006, bg, H, points_per_pixel=K, compositor="alpha")
+    b = ops.render_points(pts.to(dev), col, M, Rd, Td, inv, 0.006, bg, H, points_per_pixel=K, compositor="alpha")
+    assert torch.equal(a[1]["idx"], b[1]["idx"]) and torch.equal(a[0], b[0])
+    for ob_ in (3, 30):
+        s = slice(ob_ * M, (ob_ + 1) * M)
+        im, fr = ops.render_points(pts[ob_:ob_ + 1].to(dev), col, M, Rd[s], Td[s], inv[s], 0.006, bg, H, points_per_pixel=K, compositor="alpha")
+        assert torch.equal(fr["idx"], a[1]["idx"][s]) and torch.equal(im, a[0][s])
+        o = oracle.points_forward(pts[ob_:ob_ + 1].numpy(), np.full(3, 0.99999, np.float32), M, R[s], T[s], inv[s].cpu().numpy(), 0.006,
+                                  np.zeros(3, np.float32), H, H, K, oracle.COMPOSITE_ALPHA, fragments=False)
+        assert (fr["idx"].cpu().numpy() == o["idx"]).all()
+        assert np.abs(im.cpu().numpy() - o["images"]).max() <= IMG_ATOL
+    # layers are sorted by depth and never repeat a point
+    idx = a[1]["idx"]
+    assert ((idx[..., 1:] != idx[..., :-1]) | (idx[..., 1:] < 0)).all()
+
+
+# ------------------------------------------------------------------------------------------ public API end-to-end
+def test_mvrenderer_mesh_end_to_end(oracle, cuda_device):
+    dev = cuda_device
+    B, M, S = 3, 4, 64
+    meshes = [synth.make_mesh(700, 40), synth.make_mesh(1500, 41), synth.make_mesh(300, 42)]
+    ml = [Meshes([v], [f]) for v, f in meshes]
+    az, el, di = synth.learned_spherical_views(B, M, 12)
+    r = MVRenderer(M, image_size=S, pc_rendering=False, light_direction="fixed").to(dev)
+    a, e, d = (t.to(dev).requires_grad_() for t in (az, el, di))
+    img, cams_ = r(ml, None, a, e, d)
+    assert img.shape == (B, M, 3, S, S) and img.dtype == torch.float32 and img.device.type == "cuda"
+    assert len(cams_) == B * M and cams_.R.shape == (B * M, 3, 3) and cams_.is_perspective()
+    assert torch.allclose(cams_.get_camera_center().norm(dim=1), d.detach().reshape(-1), rtol=1e-5)
+    # stage B: oracle fed with the GPU's own R, T, C reproduces the fragments; gradients flow to azim/elev/dist
+    R, T, C = (x.detach().cpu().numpy() for x in (cams_.R, cams_.T, cams_._centers))
+    vp, fp, voff, foff = pack_np(meshes)
+    nrm = oracle.packed_vertex_normals(vp, fp, voff, foff)
+    white = np.full(3, 1 / 1.00001, np.float32)
+    o = oracle.mesh_forward(vp, fp, voff, foff, nrm, white, M, R, T, C, np.array([[0, 1.0, 0]], np.float32), white, K00, K11, 0.5, S, S, 1,
+                            oracle.PERSPECTIVE_CORRECT)
+    assert (r.last_fragments["pix_to_face"].cpu().numpy() == o["pix_to_face"]).all()
+    assert np.abs(img.detach().cpu().numpy().reshape(B * M, 3, S, S) - o["images"]).max() <= IMG_ATOL
+    g = torch.randn(B, M, 3, S, S, generator=torch.Generator().manual_seed(2))
+    img.backward(g.to(dev))
+    ob = oracle.mesh_backward(vp, fp, voff, foff, nrm, white, M, R, T, C, np.array([[0, 1.0, 0]], np.float32), K00, K11, S, S, 1,
+                              oracle.PERSPECTIVE_CORRECT, o["pix_to_face"], g.numpy().reshape(B * M, 3, S, S))
+    ga, ge, gd = oracle.look_at_backward(az.numpy().ravel(), el.numpy().ravel(), di.numpy().ravel(), ob["gR"], ob["gT"], ob["gC"])
+    assert rel(a.grad.reshape(-1), ga) < GRAD_RTOL and rel(e.grad.reshape(-1), ge) < GRAD_RTOL and rel(d.grad.reshape(-1), gd) < GRAD_RTOL
+    # a batched Meshes object and eval-mode "relative" light / no_grad also work (run_mvtn.py:517-533)
+    r2 = MVRenderer(M, image_size=S, pc_rendering=False).to(dev).eval()
+    with torch.no_grad():
+        img2, _ = r2(Meshes([v for v, _ in meshes], [f for _, f in meshes]), None, az.to(dev), el.to(dev), di.to(dev))
+    assert img2.shape == img.shape and float(img2.min()) >= 0 and float(img2.max()) <= 1.0 + 1e-6
+
+
+def test_mvrenderer_points_end_to_end(oracle, cuda_device):
+    dev = cuda_device
+    B, M, S = 2, 4, 96
+    pts = synth.make_clouds(B, 1024, 8)                        # CPU tensor, as the DataLoader hands it over
+    az, el, di = synth.learned_spherical_views(B, M, 3)
+    r = MVRenderer(M, image_size=S, pc_rendering=True, points_radius=0.02, points_per_pixel=3, background_color="black",
+                   compositor="alpha").to(dev)
+    a, e, d = (t.to(dev).requires_grad_() for t in (az, el, di))
+    img, cams_ = r(None, pts, a, e, d)
+    assert img.shape == (B, M, 3, S, S) and not cams_.is_perspective()
+    R, T = cams_.R.detach().cpu().numpy(), cams_.T.detach().cpu().numpy()
+    inv = (1.0 / di.reshape(-1)).numpy()
+    white = np.full(3, 1 / 1.00001, np.float32)
+    o = oracle.points_forward(pts.numpy(), white, M, R, T, inv, 0.02, np.zeros(3, np.float32), S, S, 3, oracle.COMPOSITE_ALPHA)
+    assert (r.last_fragments["idx"].cpu().numpy() == o["idx"]).all()
+    assert np.abs(img.detach().cpu().numpy().reshape(B * M, 3, S, S) - o["images"]).max() <= IMG_ATOL
+    img.square().mean().backward()
+    gimg = (2 * img.detach() / img.numel()).cpu().numpy().reshape(B * M, 3, S, S)
+    ob = oracle.points_backward(pts.numpy(), white, M, R, T, inv, 0.02, S, S, 3, oracle.COMPOSITE_ALPHA, o["idx"], gimg)
+    ga, ge, gd = oracle.look_at_backward(az.numpy().ravel(), el.numpy().ravel(), di.numpy().ravel(), ob["gR"], ob["gT"], None)
+    gd = gd + ob["g_inv_dist"] * (-1.0 / di.numpy().ravel() ** 2)        # d(1/dist)/d dist
+    assert rel(a.grad.reshape(-1), ga) < GRAD_RTOL and rel(e.grad.reshape(-1), ge) < GRAD_RTOL and rel(d.grad.reshape(-1), gd) < GRAD_RTOL
+    assert a.grad.abs().max() > 0
+    # default MVTN configuration (NormWeighted, K=1) gives ~zero view gradients -- SURVEY 3.4
+    r1 = MVRenderer(M, image_size=S, pc_rendering=True, background_color="black").to(dev)
+    a1 = az.to(dev).requires_grad_()
+    im1, _ = r1(None, pts, a1, el.to(dev), di.to(dev))
+    im1.sum().backward()
+    assert a1.grad.abs().max() < 1e-3
+
+
+def test_mvrenderer_rotation_guard_redraws(cuda_device):
+    dev = cuda_device
+    M = 2
+    r = MVRenderer(M, image_size=32, pc_rendering=True, background_color="black").to(dev)
+    az = torch.tensor([[0.0, 45.0]]); el = torch.tensor([[float("nan"), 10.0]]); di = torch.tensor([[2.0, 2.0]])
+    with pytest.raises(SystemExit, match="Remedy did not work"):         # ops.py:163-164 semantics
+        r(None, synth.make_clouds(1, 64, 1), az.to(dev), el.to(dev), di.to(dev))

@@ -1,0 +1,182 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol (no compute calls
+without a GPU), host helpers keep the reference's semantics, and the product refuses to run without CUDA
+instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import mvtn_b200
+from mvtn_b200 import _lib, cameras, parallel, structures, synth, util
+from mvtn_b200.renderer import MVRenderer
+from conftest import ROOT
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "mvr_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(mvr_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 15 and "mvr_mesh_forward" in names and "mvr_points_backward" in names
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"libmvr_b200.so does not export {n}"
+    assert set(names) == set(_lib.SIGNATURES), "ctypes signatures and header declarations differ"
+
+
+def test_library_loads_and_answers_host_queries():
+    lib = _lib.load()
+    assert lib.mvr_abi_version() == _lib.ABI_VERSION
+    assert lib.mvr_launch_count() >= 0
+    # size queries are pure host arithmetic
+    ws = lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 32 * 10000, 10000)
+    assert 4 * 2 * 12 * 32 * 10000 <= ws < 1 << 30      # pool of 2 * M * faces int32 entries + segments
+    assert lib.mvr_mesh_geometry_bytes(5000, 10000) >= 5000 * 48 + 10000 * 16
+    assert lib.mvr_mesh_geometry_bytes(-1, 0) == 0
+    assert lib.mvr_points_workspace_bytes(32, 12, 224, 224, 1) >= 32 * 12 * 28 * 64
+
+
+def test_argument_validation_returns_status_not_crash():
+    lib = _lib.load()
+    # invalid arguments are rejected before any CUDA call: status < 0 and a message, never an exception/abort
+    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, 0.01, None, 0, 64, 1, 0, None, None, None, None, None, 0, None)
+    assert rc < 0 and b"image size" in lib.mvr_last_error_string()
+    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, 0.01, None, 64, 64, 200, 0, None, None, None, None, None, 0, None)
+    assert rc < 0 and b"points_per_pixel" in lib.mvr_last_error_string()
+    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, -1.0, None, 64, 64, 1, 0, None, None, None, None, None, 0, None)
+    assert rc < 0 and b"radius" in lib.mvr_last_error_string()
+    rc = lib.mvr_mesh_forward(None, None, None, 1, 1, 3, 1, 1, None, None, None, None, 0, None, None, 1.7, 1.7, 0.5, 64, 64, 1, 0,
+                              None, None, None, None, None, None, None, 0, None)
+    assert rc < 0 and b"null pointer" in lib.mvr_last_error_string()
+    rc = lib.mvr_mesh_prepare(None, None, None, None, 1, 10, 10, 10, None, 0, None, 16, None)
+    assert rc < 0 and b"too small" in lib.mvr_last_error_string()
+    with pytest.raises(_lib.MVRError):
+        _lib.check(rc, "mvr_mesh_prepare")
+    # empty batches are a no-op
+    assert lib.mvr_look_at_forward(None, None, None, 0, None, None, None, None, None) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    r = MVRenderer(nb_views=2, image_size=32)
+    az = torch.zeros(1, 2)
+    with pytest.raises(_lib.MVRError, match="no CPU path"):
+        r(None, torch.zeros(1, 8, 3), az, az, az + 2.0)
+    with pytest.raises(_lib.MVRError):
+        mvtn_b200.PackedMeshes([torch.zeros(3, 3)], [torch.zeros(1, 3, dtype=torch.int64)], "cpu")
+
+
+def test_constructor_matches_reference_signature():
+    import inspect
+    sig = inspect.signature(MVRenderer.__init__)
+    names = list(sig.parameters)[1:11]
+    assert names == ["nb_views", "image_size", "pc_rendering", "object_color", "background_color", "faces_per_pixel",
+                     "points_radius", "points_per_pixel", "light_direction", "cull_backfaces"]      # renderer.py:52
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["image_size"], d["pc_rendering"], d["object_color"], d["background_color"]) == (224, True, "white", "white")
+    assert (d["faces_per_pixel"], d["points_radius"], d["points_per_pixel"], d["light_direction"], d["cull_backfaces"]) == \
+        (1, 0.006, 1, "random", False)
+    r = MVRenderer(12)
+    assert len(r.state_dict()) == 0 and len(list(r.parameters())) == 0      # stateless: old checkpoints load
+    fwd = list(inspect.signature(MVRenderer.forward).parameters)
+    assert fwd == ["self", "meshes", "points", "azim", "elev", "dist", "color"]
+    assert list(inspect.signature(MVRenderer.render_and_save).parameters)[1:] == \
+        ["meshes", "points", "azim", "elev", "dist", "images_path", "cameras_path", "color"]
+
+
+def test_color_and_light_policy():
+    torch.manual_seed(0); np.random.seed(0)
+    assert torch.allclose(util.torch_color("white", max_lightness=True), torch.full((3,), 1 / 1.00001))   # util.py:314-334
+    assert torch.equal(util.torch_color("black", max_lightness=True), torch.zeros(3))
+    assert torch.allclose(util.torch_color("red", max_lightness=True), torch.tensor([1 / 1.00001, 0, 0]))
+    r = MVRenderer(4, object_color="random", light_direction="random")
+    r.train()
+    c = r.rendering_color()
+    assert c.max() == pytest.approx(1 / 1.00001, rel=1e-5) and c.min() >= 0
+    l = r.light_direction(None, None, None)
+    assert len(l) == 1 and len(l[0]) == 3 and all(-1 <= x <= 1 for x in l[0])
+    r.eval()
+    assert torch.equal(r.rendering_color(), torch.ones(3))                    # eval + "random" -> plain white
+    assert r.light_direction(None, None, None) is None                        # -> relative (camera) light
+    assert MVRenderer(4, light_direction="fixed").light_direction(None, None, None) == ((0, 1.0, 0),)
+    assert MVRenderer(4, object_color="custom").rendering_color((0.1, 0.2, 0.3)) == (0.1, 0.2, 0.3)
+
+
+def test_batch_tensor_flat_order():
+    B, M = 3, 4
+    x = torch.arange(B * M).reshape(B, M)
+    flat = util.batch_tensor(x.T, dim=1, squeeze=True)       # renderer.py:79: view n = b*M + m
+    assert torch.equal(flat, x.reshape(-1))
+    imgs = torch.arange(B * M * 2 * 2 * 3).reshape(B * M, 2, 2, 3)
+    un = util.unbatch_tensor(imgs, batch_size=M, dim=1, unsqueeze=True).transpose(0, 1)   # renderer.py:109-110
+    assert torch.equal(un, imgs.reshape(B, M, 2, 2, 3))
+
+
+def test_check_valid_rotation_matrix():
+    assert util.check_valid_rotation_matrix(torch.eye(3)[None])
+    assert not util.check_valid_rotation_matrix(torch.diag(torch.tensor([1.0, 1.0, -1.0]))[None])
+    assert not util.check_valid_rotation_matrix(torch.zeros(1, 3, 3))
+
+
+def test_meshes_container_and_unpack():
+    v, f = synth.make_mesh(100, 0)
+    ms = [structures.Meshes([v], [f]), structures.Meshes([v * 2], [f])]
+    verts, faces = structures.unpack_mesh_list(ms)
+    assert len(verts) == 2 and torch.equal(verts[1], v * 2)
+    batched = structures.Meshes([v, v * 2], [f, f])
+    verts2, _ = structures.unpack_mesh_list(batched)            # run_mvtn.py:517-533 passes a batched object
+    assert len(verts2) == 2 and len(batched) == 2 and len(batched[0:1]) == 1
+    ext = batched.extend(3)
+    assert len(ext) == 6 and torch.equal(ext.verts_list()[2], v) and torch.equal(ext.verts_list()[3], v * 2)
+
+
+def test_camera_shim_transforms():
+    from oracle import oracle as orc
+    R, T, C = orc.look_at([30.0, -70.0], [20.0, 45.0], [2.2, 1.7])
+    cam = cameras.FoVPerspectiveCameras(torch.from_numpy(R), torch.from_numpy(T))
+    assert len(cam) == 2 and cam.is_perspective()
+    assert torch.allclose(cam.get_camera_center(), torch.from_numpy(C), atol=1e-5)
+    w2v = cam.get_world_to_view_transform()
+    p = torch.randn(2, 5, 3)
+    assert torch.allclose(w2v.transform_points(p), p @ torch.from_numpy(R) + torch.from_numpy(T)[:, None], atol=1e-6)
+    assert torch.allclose(w2v.inverse().transform_points(w2v.transform_points(p)), p, atol=1e-5)
+    from mvtn_b200.viz import camera_wireframes_world
+    wires = camera_wireframes_world(cam, 0.22)
+    assert wires.shape == (2, 12, 3) and torch.allclose(wires[:, 5], torch.from_numpy(C), atol=1e-5)   # apex = centre
+
+
+def test_synthetic_inputs_follow_the_normalisation_contract():
+    v, f = synth.make_mesh(10000, 1236)
+    assert abs(f.shape[0] - 10000) < 300 and f.max() < v.shape[0] and f.min() == 0
+    assert v.norm(dim=1).max() == pytest.approx(1.0, abs=1e-5) and v.mean(0).abs().max() < 1e-5
+    e = torch.cat([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    key = e[:, 0] * v.shape[0] + e[:, 1]; rev = e[:, 1] * v.shape[0] + e[:, 0]
+    assert key.unique().numel() == key.numel() and set(key.tolist()) == set(rev.tolist())   # closed, consistently wound
+    p = synth.make_clouds(2, 2048, 5)
+    assert p.shape == (2, 2048, 3) and p[0].norm(dim=1).max() == pytest.approx(1.0, abs=1e-5)
+    assert torch.equal(synth.make_clouds(2, 64, 5), synth.make_clouds(2, 64, 5))
+    az, el, di = synth.circular_views(2, 12)
+    assert az.shape == (2, 12) and az[0, 0] == -270 and (el == 30).all() and (di == 2.2).all()   # mvtn.py:22-24
+    a, e2, _ = synth.learned_spherical_views(3, 12, 0)
+    assert a.shape == (3, 12) and e2.abs().max() <= 89.0
+
+
+def test_shard_ranges_partition_objects():
+    for n in (0, 1, 7, 32, 33, 256):
+        for w in (1, 2, 4, 8):
+            r = [parallel.shard_range(n, i, w) for i in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_range(4, 4, 4)
+    parts = parallel.shard_by_weight([10, 1, 1, 1, 1, 10, 1, 1, 1, 1], 2)
+    assert parts == [(0, 5), (5, 10)]
+    parts = parallel.shard_by_weight([1] * 3, 8)
+    assert parts[0][0] == 0 and parts[-1][1] == 3 and all(a <= b for a, b in parts)
