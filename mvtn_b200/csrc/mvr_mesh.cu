@@ -22,7 +22,6 @@ namespace mvr {
 
 constexpr int TILE = 32;              // pixels per tile side (row segment = 128 B = one line)
 constexpr int TILE_PIX = TILE * TILE;
-constexpr int SMALL_FACE_PIX = 48;    // faces covering more tile pixels go to a warp
 constexpr int MAX_CHUNKS = 256;       // face chunks per view (bin kernel CTAs per view)
 constexpr int MIN_FACES_PER_CHUNK = 2048;
 constexpr int BWD_VALS = 15;          // dR 9, dT 3, dC 3
@@ -165,16 +164,31 @@ __device__ __forceinline__ Face load_face(const MeshParams& p, const Camera& cam
 }
 
 // Face-level rejection ([upstream] clip.py near cull, CheckPointOutsideBoundingBox z_invalid,
-// RasterizeMeshesNaiveCpu zero-area / back-face tests) and the exact pixel bbox.
-// Returns false when the face can never produce a fragment.  Pixel ranges are inclusive.
-__device__ __forceinline__ bool face_pixel_bbox(const Face& f, const MeshParams& p, int& xi_lo, int& xi_hi,
-                                                int& yi_lo, int& yi_hi, bool& straddle) {
-  straddle = false;
-  if (p.z_clip >= 0.f) {
-    const int nb = (f.z0 < p.z_clip) + (f.z1 < p.z_clip) + (f.z2 < p.z_clip);
-    if (nb == 3) return false;
-    straddle = nb > 0;
-  }
+// RasterizeMeshesNaiveCpu zero-area / back-face tests) and the exact pixel bbox (inclusive ranges), clipped to the
+// rectangle [tx0,tx1] x [ty0,ty1] and made exact with pixel-centre tables (tab[i - t0], decreasing in i).
+__device__ __forceinline__ void tile_range(float vmin, float vmax, int S1, int S2, int t0, int t1, const float* tab,
+                                           int& ilo, int& ihi) {
+  float range = 2.0f;
+  if (S1 > S2) range = ((float)(S1 / S2)) * range;
+  const float offset = range / 2.0f;
+  // centre of pixel i is c(S1-1-i) with c(j) = -offset + (range*j + offset)/S1, so i decreases as the coordinate grows
+  float jhi = floorf(((vmax + offset) * (float)S1 - offset) / range);
+  float jlo = ceilf(((vmin + offset) * (float)S1 - offset) / range);
+  jhi = fminf(fmaxf(jhi, -2.0f), (float)S1 + 1.0f);
+  jlo = fminf(fmaxf(jlo, -2.0f), (float)S1 + 1.0f);
+  ilo = max(S1 - 1 - (int)jhi, t0);
+  ihi = min(S1 - 1 - (int)jlo, t1);
+  if (ilo > t1 + 1) ilo = t1 + 1;
+  if (ihi < t0 - 1) ihi = t0 - 1;
+  while (ilo > t0 && tab[ilo - 1 - t0] <= vmax) --ilo;
+  while (ilo <= t1 && tab[ilo - t0] > vmax) ++ilo;
+  while (ihi < t1 && tab[ihi + 1 - t0] >= vmin) ++ihi;
+  while (ihi >= t0 && tab[ihi - t0] < vmin) --ihi;
+}
+__device__ __forceinline__ bool face_tile_bbox(const Face& f, const MeshParams& p, int tx0, int tx1, int ty0, int ty1,
+                                               const float* s_xf, const float* s_yf, int& xi_lo, int& xi_hi,
+                                               int& yi_lo, int& yi_hi) {
+  if (p.z_clip >= 0.f && f.z0 < p.z_clip && f.z1 < p.z_clip && f.z2 < p.z_clip) return false;
   const float zmin = fminf(fminf(f.z0, f.z1), f.z2);
   if (zmin < MVR_K_EPS) return false;
   const float face_area = (f.x0 - f.x1) * (f.y2 - f.y1) - (f.y0 - f.y1) * (f.x2 - f.x1);
@@ -182,12 +196,10 @@ __device__ __forceinline__ bool face_pixel_bbox(const Face& f, const MeshParams&
   if (face_area <= MVR_K_EPS && face_area >= -1.0f * MVR_K_EPS) return false;
   const float xmin = fminf(fminf(f.x0, f.x1), f.x2), xmax = fmaxf(fmaxf(f.x0, f.x1), f.x2);
   const float ymin = fminf(fminf(f.y0, f.y1), f.y2), ymax = fmaxf(fmaxf(f.y0, f.y1), f.y2);
-  int jlo, jhi;
-  ndc_range_to_pix(xmin, xmax, p.W, p.H, jlo, jhi);
-  xi_lo = p.W - 1 - jhi; xi_hi = p.W - 1 - jlo;
-  ndc_range_to_pix(ymin, ymax, p.H, p.W, jlo, jhi);
-  yi_lo = p.H - 1 - jhi; yi_hi = p.H - 1 - jlo;
-  return xi_lo <= xi_hi && yi_lo <= yi_hi;
+  tile_range(xmin, xmax, p.W, p.H, tx0, tx1, s_xf, xi_lo, xi_hi);
+  if (xi_lo > xi_hi) return false;
+  tile_range(ymin, ymax, p.H, p.W, ty0, ty1, s_yf, yi_lo, yi_hi);
+  return yi_lo <= yi_hi;
 }
 
 struct FaceEdges {
@@ -263,11 +275,13 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_warp /* [8] */, int
 // coarse pass
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MVR_THREADS) mesh_bin_kernel(const MeshParams p) {
-  extern __shared__ int s_dyn[];       // [n_tiles] counts, [n_tiles] exclusive offsets / cursors
+  extern __shared__ int s_dyn[];       // [n_tiles] counts, [n_tiles] exclusive offsets / cursors, [W] + [H] pixel centres
   __shared__ int s_warp[8];
   __shared__ int s_base;
   int* s_cnt = s_dyn;
   int* s_off = s_dyn + p.n_tiles;
+  float* s_xf = (float*)(s_dyn + 2 * p.n_tiles);
+  float* s_yf = s_xf + p.W;
   const int n = blockIdx.x / p.max_chunks, c = blockIdx.x % p.max_chunks;
   const int b = n / p.M;
   const int f0 = p.face_off[b], F = p.face_off[b + 1] - f0;
@@ -278,16 +292,20 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_bin_kernel(const MeshParams 
     return;
   }
   for (int t = threadIdx.x; t < p.n_tiles; t += MVR_THREADS) s_cnt[t] = 0;
+  for (int i = threadIdx.x; i < p.W; i += MVR_THREADS) s_xf[i] = pix_to_ndc(p.W - 1 - i, p.W, p.H);
+  for (int i = threadIdx.x; i < p.H; i += MVR_THREADS) s_yf[i] = pix_to_ndc(p.H - 1 - i, p.H, p.W);
   __syncthreads();
   const Camera cam = load_camera(p.R, p.T, n);
   const int voff = p.vert_off[b];
   int n_straddle = 0;
   for (int f = fbeg + threadIdx.x; f < fend; f += MVR_THREADS) {
     const Face fc = load_face(p, cam, voff, __ldg(p.faces4 + f0 + f));
-    int xl, xh, yl, yh; bool st;
-    const bool vis = face_pixel_bbox(fc, p, xl, xh, yl, yh, st);
-    n_straddle += st;          // every face crossing z_clip is counted, visible or not (as the oracle does)
-    if (!vis) continue;
+    int xl, xh, yl, yh;
+    if (p.z_clip >= 0.f) {     // every face crossing z_clip is counted, visible or not (as the oracle does)
+      const int nb = (fc.z0 < p.z_clip) + (fc.z1 < p.z_clip) + (fc.z2 < p.z_clip);
+      n_straddle += (nb == 1 || nb == 2);
+    }
+    if (!face_tile_bbox(fc, p, 0, p.W - 1, 0, p.H - 1, s_xf, s_yf, xl, xh, yl, yh)) continue;
     const int tx0 = xl / TILE, tx1 = xh / TILE, ty0 = yl / TILE, ty1 = yh / TILE;
     for (int ty = ty0; ty <= ty1; ++ty)
       for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&s_cnt[ty * p.tiles_x + tx], 1);
@@ -333,8 +351,8 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_bin_kernel(const MeshParams 
   // fill: identical arithmetic => identical tile rectangles
   for (int f = fbeg + threadIdx.x; f < fend; f += MVR_THREADS) {
     const Face fc = load_face(p, cam, voff, __ldg(p.faces4 + f0 + f));
-    int xl, xh, yl, yh; bool st;
-    if (!face_pixel_bbox(fc, p, xl, xh, yl, yh, st)) continue;
+    int xl, xh, yl, yh;
+    if (!face_tile_bbox(fc, p, 0, p.W - 1, 0, p.H - 1, s_xf, s_yf, xl, xh, yl, yh)) continue;
     const int tx0 = xl / TILE, tx1 = xh / TILE, ty0 = yl / TILE, ty1 = yh / TILE;
     for (int ty = ty0; ty <= ty1; ++ty)
       for (int tx = tx0; tx <= tx1; ++tx) {
@@ -389,35 +407,126 @@ __device__ __forceinline__ void phong_pixel(const float b[3], const float4 X0, c
 // ------------------------------------------------------------------------------------------------
 // fine pass
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void scatter_face_rows(const Face& fc, const FaceEdges& fe, bool persp, int fid,
-                                                  int xl, int xh, int yl, int yh, int x0, int y0,
-                                                  const float* s_xf, const float* s_yf,
-                                                  unsigned long long* s_cur, const unsigned long long* s_prev,
-                                                  bool peel, int start, int stride) {
-  const int bw = xh - xl + 1;
-  const int npx = bw * (yh - yl + 1);
-  for (int q = start; q < npx; q += stride) {
-    const int yy = yl + q / bw, xx = xl + q % bw;
-    const int lx = xx - x0, ly = yy - y0;
-    float w[3], b[3], pz;
-    if (!raster_test(fc, fe, persp, s_xf[lx], s_yf[ly], w, b, pz)) continue;
-    const unsigned long long key = make_key(pz, fid);
-    const int pix = ly * TILE + lx;
-    if (peel && key <= s_prev[pix]) continue;
-    smem_key_min(&s_cur[pix], key);
+// Shared-memory layout of one fine CTA (dynamic): every phase of a 256-entry chunk runs DENSE --
+//   A  setup    thread per bin entry: project, cull, tile-clipped pixel bbox -> record + <= 8 sub-items
+//   B  filter   thread per sub-item (a run of bbox pixels): edge-function sign test -> candidate queue
+//   C  resolve  thread per candidate: exact barycentrics / depth -> 64-bit (z, face) min on the pixel key
+// so a 3-pixel sliver and a tile-filling triangle cost their threads the same, and the IEEE divisions
+// run only on full warps of pixels that are inside their face.
+constexpr int REC_WORDS = 11;            // x0 y0 z0 x1 y1 z1 x2 y2 z2 fid rect
+constexpr int ITEM_CAP = 2048;           // sub-items per chunk (typically 256 entries x 1-3)
+constexpr int WCAP = 320;                // candidates per warp queue
+constexpr int NWARPS = MVR_THREADS / 32;
+
+struct FineSmem {
+  unsigned long long* cur;     // [TILE_PIX]
+  unsigned long long* prev;    // [TILE_PIX] (K > 1 only)
+  float* rec;                  // [REC_WORDS][256]  SoA
+  int* items;                  // [ITEM_CAP]  slot | start << 8 | count << 18
+  int* cand;                   // [NWARPS][WCAP]  slot | pix << 8
+  int* pref;                   // [MAX_CHUNKS + 1]
+  int* segstart;               // [MAX_CHUNKS]
+  float* xf;                   // [TILE]
+  float* yf;                   // [TILE]
+  int* counters;               // [0] items
+  int* warp;                   // [8] scan scratch / per-warp candidate counts
+};
+__host__ __device__ inline size_t fine_smem_bytes(int K) {
+  return (size_t)TILE_PIX * 8 * (K > 1 ? 2 : 1) + REC_WORDS * MVR_THREADS * 4 + ITEM_CAP * 4 + NWARPS * WCAP * 4 +
+         (MAX_CHUNKS + 1 + MAX_CHUNKS) * 4 + 2 * TILE * 4 + 16 * 4;
+}
+__device__ __forceinline__ FineSmem carve_fine_smem(unsigned char* base, int K) {
+  FineSmem s;
+  s.cur = (unsigned long long*)base; base += TILE_PIX * 8;
+  s.prev = (unsigned long long*)base; if (K > 1) base += TILE_PIX * 8;
+  s.rec = (float*)base; base += REC_WORDS * MVR_THREADS * 4;
+  s.items = (int*)base; base += ITEM_CAP * 4;
+  s.cand = (int*)base; base += NWARPS * WCAP * 4;
+  s.pref = (int*)base; base += (MAX_CHUNKS + 1) * 4;
+  s.segstart = (int*)base; base += MAX_CHUNKS * 4;
+  s.xf = (float*)base; base += TILE * 4;
+  s.yf = (float*)base; base += TILE * 4;
+  s.counters = (int*)base; base += 8 * 4;
+  s.warp = (int*)base;
+  return s;
+}
+
+__device__ __forceinline__ Face load_record(const float* rec, int slot) {
+  Face f;
+  f.x0 = rec[0 * MVR_THREADS + slot]; f.y0 = rec[1 * MVR_THREADS + slot]; f.z0 = rec[2 * MVR_THREADS + slot];
+  f.x1 = rec[3 * MVR_THREADS + slot]; f.y1 = rec[4 * MVR_THREADS + slot]; f.z1 = rec[5 * MVR_THREADS + slot];
+  f.x2 = rec[6 * MVR_THREADS + slot]; f.y2 = rec[7 * MVR_THREADS + slot]; f.z2 = rec[8 * MVR_THREADS + slot];
+  return f;
+}
+
+// phase C body: exact test of one (face, pixel) candidate and the keyed min
+__device__ __forceinline__ void resolve_candidate(const FineSmem& s, int slot, int pix, bool persp, bool peel) {
+  const Face fc = load_record(s.rec, slot);
+  const FaceEdges fe = face_edges(fc);
+  float w[3], b[3], pz;
+  if (!raster_test(fc, fe, persp, s.xf[pix & (TILE - 1)], s.yf[pix / TILE], w, b, pz)) return;
+  const unsigned long long key = make_key(pz, __float_as_int(s.rec[9 * MVR_THREADS + slot]));
+  if (peel && key <= s.prev[pix]) return;
+  smem_key_min(&s.cur[pix], key);
+}
+
+__device__ __forceinline__ void fine_epilogue(const MeshParams& p, const FineSmem& s, const Camera& cam, const ShadeCtx& sc,
+                                              int n, int k, int x0, int y0, int f0, int voff, bool persp,
+                                              bool per_vertex_rgb, const float4 ucol, float bg0, float bg1, float bg2) {
+  // The barycentrics are recomputed with the SAME exact operation sequence as the scatter: for sliver faces a
+  // reciprocal-multiply shortcut moves them by far more than the 1e-5 image tolerance (error ~ ulp * |xy| / area).
+  const int tid = threadIdx.x;
+  for (int j = 0; j < TILE_PIX / MVR_THREADS; ++j) {
+    const int pix = tid + j * MVR_THREADS;
+    const int ly = pix / TILE, lx = pix % TILE;
+    const int yi = y0 + ly, xi = x0 + lx;
+    const unsigned long long key = s.cur[pix];
+    if (p.K > 1) s.prev[pix] = key;   // EMPTY stays EMPTY: later layers find nothing
+    if (yi >= p.H || xi >= p.W) continue;
+    int fid = -1;
+    float w[3] = {-1.f, -1.f, -1.f}, bb[3] = {-1.f, -1.f, -1.f}, pz = -1.f, dd = -1.f;
+    float out[3] = {bg0, bg1, bg2};
+    if (key != MVR_EMPTY_KEY) {
+      fid = (int)(unsigned int)(key & 0xffffffffull);
+      const int4 fi = __ldg(p.faces4 + f0 + fid);
+      const float4 X0 = __ldg(p.verts4 + voff + fi.x), X1 = __ldg(p.verts4 + voff + fi.y), X2 = __ldg(p.verts4 + voff + fi.z);
+      const float xf = s.xf[lx], yf = s.yf[ly];
+      Face fc;
+      project_vertex(cam, X0, p.k00, p.k11, fc.x0, fc.y0, fc.z0);
+      project_vertex(cam, X1, p.k00, p.k11, fc.x1, fc.y1, fc.z1);
+      project_vertex(cam, X2, p.k00, p.k11, fc.x2, fc.y2, fc.z2);
+      const FaceEdges fe = face_edges(fc);
+      raster_test(fc, fe, persp, xf, yf, w, bb, pz);
+      pz = __uint_as_float((unsigned int)(key >> 32));
+      if (p.dists) {
+        const float e01 = point_line_dist2(xf, yf, fc.x0, fc.y0, fc.x1, fc.y1);
+        const float e02 = point_line_dist2(xf, yf, fc.x0, fc.y0, fc.x2, fc.y2);
+        const float e12 = point_line_dist2(xf, yf, fc.x1, fc.y1, fc.x2, fc.y2);
+        dd = -fminf(fminf(e01, e02), e12);
+      }
+      if (k == 0) {
+        const float4 N0 = __ldg(p.normals4 + voff + fi.x), N1 = __ldg(p.normals4 + voff + fi.y), N2 = __ldg(p.normals4 + voff + fi.z);
+        float4 c0 = ucol, c1 = ucol, c2 = ucol;
+        if (per_vertex_rgb) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
+        phong_pixel(bb, X0, X1, X2, N0, N1, N2, c0, c1, c2, sc, out);
+      }
+    }
+    const size_t po = (((size_t)n * p.H + yi) * p.W + xi) * p.K + k;
+    p.pix_to_face[po] = fid;
+    if (p.zbuf) p.zbuf[po] = pz;
+    if (p.dists) p.dists[po] = dd;
+    if (p.bary) { p.bary[3 * po] = bb[0]; p.bary[3 * po + 1] = bb[1]; p.bary[3 * po + 2] = bb[2]; }
+    if (k == 0) {
+      const size_t io = ((size_t)n * 3 * p.H + yi) * p.W + xi;
+      const size_t plane = (size_t)p.H * p.W;
+      p.images[io] = out[0]; p.images[io + plane] = out[1]; p.images[io + 2 * plane] = out[2];
+    }
   }
 }
 
-__global__ void __launch_bounds__(MVR_THREADS) mesh_fine_kernel(const MeshParams p) {
-  __shared__ unsigned long long s_cur[TILE_PIX];
-  __shared__ unsigned long long s_prev[TILE_PIX];
-  __shared__ float s_xf[TILE], s_yf[TILE];
-  __shared__ int s_pref[MAX_CHUNKS + 1];
-  __shared__ int s_segstart[MAX_CHUNKS];
-  __shared__ int s_queue[MVR_THREADS];
-  __shared__ int s_qn[2];
-  __shared__ int s_warp[8];
-
+__global__ void __launch_bounds__(MVR_THREADS, 4) mesh_fine_kernel(const MeshParams p) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const FineSmem s = carve_fine_smem(s_raw, p.K);
   const int tid = threadIdx.x;
   const int n = blockIdx.x / p.n_tiles, tile = blockIdx.x % p.n_tiles;
   const int b = n / p.M;
@@ -430,28 +539,27 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_fine_kernel(const MeshParams
   const Camera cam = load_camera(p.R, p.T, n);
 
   if (tid < TILE) {
-    s_xf[tid] = pix_to_ndc(p.W - 1 - (x0 + tid), p.W, p.H);
-    s_yf[tid] = pix_to_ndc(p.H - 1 - (y0 + tid), p.H, p.W);
+    s.xf[tid] = pix_to_ndc(p.W - 1 - (x0 + tid), p.W, p.H);
+    s.yf[tid] = pix_to_ndc(p.H - 1 - (y0 + tid), p.H, p.W);
   }
-  if (tid < 2) s_qn[tid] = 0;
+  if (tid == 0) s.counters[0] = 0;
   // bin segments of this (view, tile): one per face chunk
   int cnt = 0;
   if (tid < n_chunks) {
     const int2 sg = p.seg[((size_t)n * p.max_chunks + tid) * p.n_tiles + tile];
-    cnt = sg.y; s_segstart[tid] = sg.x;
+    cnt = sg.y; s.segstart[tid] = sg.x;
   }
   int total;
-  const int ex = block_excl_scan(cnt, s_warp, &total);
-  if (tid < n_chunks) s_pref[tid] = ex;
-  if (tid == 0) s_pref[n_chunks] = total;
-  for (int i = tid; i < TILE_PIX; i += MVR_THREADS) s_prev[i] = 0ull;
+  const int ex = block_excl_scan(cnt, s.warp, &total);
+  if (tid < n_chunks) s.pref[tid] = ex;
+  if (tid == 0) s.pref[n_chunks] = total;
   __syncthreads();
 
   // light / camera for the epilogue
   ShadeCtx sc;
   {
-    const float* L = p.light + (size_t)p.light_stride * n;
-    const float lx = __ldg(L), ly = __ldg(L + 1), lz = __ldg(L + 2);
+    const float* Lp = p.light + (size_t)p.light_stride * n;
+    const float lx = __ldg(Lp), ly = __ldg(Lp + 1), lz = __ldg(Lp + 2);
     const float il = inv_norm_clamped(lx, ly, lz, 1e-6f);
     sc.lx = lx * il; sc.ly = ly * il; sc.lz = lz * il;
     sc.cx = __ldg(p.Cc + 3 * (size_t)n); sc.cy = __ldg(p.Cc + 3 * (size_t)n + 1); sc.cz = __ldg(p.Cc + 3 * (size_t)n + 2);
@@ -461,99 +569,128 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_fine_kernel(const MeshParams
   float4 ucol = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!per_vertex_rgb) ucol = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f);
 
-  int it = 0;
   for (int k = 0; k < p.K; ++k) {
     const bool peel = k > 0;
-    for (int i = tid; i < TILE_PIX; i += MVR_THREADS) s_cur[i] = MVR_EMPTY_KEY;
+    for (int i = tid; i < TILE_PIX; i += MVR_THREADS) s.cur[i] = MVR_EMPTY_KEY;
     __syncthreads();
-    for (int base = 0; base < total; base += MVR_THREADS, ++it) {
+    for (int base = 0; base < total; base += MVR_THREADS) {
+      // ---------------- phase A: setup ----------------
       const int i = base + tid;
       if (i < total) {
-        // chunk of entry i: largest c with s_pref[c] <= i
-        int lo = 0, hi = n_chunks - 1;
+        int lo = 0, hi = n_chunks - 1;          // chunk of entry i: largest c with pref[c] <= i
         while (lo < hi) {
           const int mid = (lo + hi + 1) >> 1;
-          if (s_pref[mid] <= i) lo = mid; else hi = mid - 1;
+          if (s.pref[mid] <= i) lo = mid; else hi = mid - 1;
         }
-        const int local = i - s_pref[lo];
-        const int start = s_segstart[lo];
+        const int local = i - s.pref[lo];
+        const int start = s.segstart[lo];
         const int fid = start < 0 ? lo * p.fpc + local : __ldg(p.pool + start + local);
         const Face fc = load_face(p, cam, voff, __ldg(p.faces4 + f0 + fid));
-        int xl, xh, yl, yh; bool st;
-        if (face_pixel_bbox(fc, p, xl, xh, yl, yh, st)) {
-          xl = max(xl, x0); xh = min(xh, x1); yl = max(yl, y0); yh = min(yh, y1);
-          if (xl <= xh && yl <= yh) {
-            const int npx = (xh - xl + 1) * (yh - yl + 1);
-            if (npx <= SMALL_FACE_PIX) {
-              const FaceEdges fe = face_edges(fc);
-              scatter_face_rows(fc, fe, persp, fid, xl, xh, yl, yh, x0, y0, s_xf, s_yf, s_cur, s_prev, peel, 0, 1);
-            } else {
-              s_queue[atomicAdd(&s_qn[it & 1], 1)] = fid;
-            }
+        int xl, xh, yl, yh;
+        if (face_tile_bbox(fc, p, x0, x1, y0, y1, s.xf, s.yf, xl, xh, yl, yh)) {
+          const int bw = xh - xl + 1, bh = yh - yl + 1, npx = bw * bh;
+          s.rec[0 * MVR_THREADS + tid] = fc.x0; s.rec[1 * MVR_THREADS + tid] = fc.y0; s.rec[2 * MVR_THREADS + tid] = fc.z0;
+          s.rec[3 * MVR_THREADS + tid] = fc.x1; s.rec[4 * MVR_THREADS + tid] = fc.y1; s.rec[5 * MVR_THREADS + tid] = fc.z1;
+          s.rec[6 * MVR_THREADS + tid] = fc.x2; s.rec[7 * MVR_THREADS + tid] = fc.y2; s.rec[8 * MVR_THREADS + tid] = fc.z2;
+          s.rec[9 * MVR_THREADS + tid] = __int_as_float(fid);
+          s.rec[10 * MVR_THREADS + tid] = __int_as_float((xl - x0) | ((yl - y0) << 5) | ((bw - 1) << 10) | ((bh - 1) << 15));
+          // runs of G pixels: 8 for ordinary faces, up to 32 for tile-sized ones (<= 32 runs per face)
+          const int G = max(8, (npx + 31) >> 5);
+          const int nsub = (npx + G - 1) / G;
+          const int at = atomicAdd(&s.counters[0], nsub);
+          if (at + nsub <= ITEM_CAP) {
+            for (int q = 0; q < nsub; ++q) s.items[at + q] = tid | ((q * G) << 8) | (min(G, npx - q * G) << 18);
+          } else {
+            // item queue exhausted (a chunk of tile-sized faces): this thread walks its own bbox
+            for (int q = at; q < ITEM_CAP; ++q) s.items[q] = 0;      // a straddling reservation leaves no garbage
+            const FaceEdges fe = face_edges(fc);
+            for (int yy = yl; yy <= yh; ++yy)
+              for (int xx = xl; xx <= xh; ++xx) {
+                float w[3], bq[3], pz;
+                if (!raster_test(fc, fe, persp, s.xf[xx - x0], s.yf[yy - y0], w, bq, pz)) continue;
+                const unsigned long long key = make_key(pz, fid);
+                const int pix = (yy - y0) * TILE + (xx - x0);
+                if (peel && key <= s.prev[pix]) continue;
+                smem_key_min(&s.cur[pix], key);
+              }
           }
         }
       }
       __syncthreads();
-      const int qn = s_qn[it & 1];
-      if (tid == 0) s_qn[(it + 1) & 1] = 0;
-      if (qn > 0) {
-        // big faces: one warp per face, lanes stride over the clipped bbox
-        for (int q = tid >> 5; q < qn; q += MVR_THREADS / 32) {
-          const int fid = s_queue[q];
-          const Face fc = load_face(p, cam, voff, __ldg(p.faces4 + f0 + fid));
-          int xl, xh, yl, yh; bool st;
-          face_pixel_bbox(fc, p, xl, xh, yl, yh, st);
-          xl = max(xl, x0); xh = min(xh, x1); yl = max(yl, y0); yh = min(yh, y1);
-          const FaceEdges fe = face_edges(fc);
-          scatter_face_rows(fc, fe, persp, fid, xl, xh, yl, yh, x0, y0, s_xf, s_yf, s_cur, s_prev, peel, tid & 31, 32);
+      // ---------------- phase B: sign filter over bbox pixels, per-warp candidate queues ----------------
+      const int n_items = min(s.counters[0], ITEM_CAP);
+      const int warp = tid >> 5, lane = tid & 31;
+      int wcnt = 0;                              // warp-uniform: candidates queued by this warp
+      int* wq = s.cand + warp * WCAP;
+      for (int j0 = warp * 32; j0 < n_items; j0 += MVR_THREADS) {      // warp-uniform trip count
+        const int j = j0 + lane;
+        int slot = 0, count = 0, row = 0, col = 0, lxl = 0, lyl = 0, bw = 1;
+        float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f, cx = 0.f, cy = 0.f;
+        unsigned int zmin_bits = 0u;
+        if (j < n_items) {
+          const int it = s.items[j];
+          slot = it & 255; count = it >> 18;
+          const int start = (it >> 8) & 1023;
+          ax = s.rec[0 * MVR_THREADS + slot]; ay = s.rec[1 * MVR_THREADS + slot];
+          bx = s.rec[3 * MVR_THREADS + slot]; by = s.rec[4 * MVR_THREADS + slot];
+          cx = s.rec[6 * MVR_THREADS + slot]; cy = s.rec[7 * MVR_THREADS + slot];
+          const int rect = __float_as_int(s.rec[10 * MVR_THREADS + slot]);
+          lxl = rect & 31; lyl = (rect >> 5) & 31; bw = ((rect >> 10) & 31) + 1;
+          row = (int)__fdividef((float)start + 0.5f, (float)bw);     // small integers: exact
+          col = start - row * bw;
+          // early depth reject: pz is a convex combination of the vertex depths up to a few ulp (perspective-
+          // corrected barycentrics sum to 1 unless their 1e-8 denominator clamp acts, which needs z ~ 1e-4;
+          // plain barycentrics sum to area/(area+1e-8), so the shortcut is not used for them), hence a face
+          // whose nearest vertex is clearly behind the pixel's current winner cannot produce a smaller key
+          const float zmin = fminf(fminf(s.rec[2 * MVR_THREADS + slot], s.rec[5 * MVR_THREADS + slot]), s.rec[8 * MVR_THREADS + slot]);
+          if (persp && zmin > 1e-3f) zmin_bits = __float_as_uint(zmin * 0.999999f);
+        }
+        const float A0 = cy - by, B0 = cx - bx, A1 = ay - cy, B1 = ax - cx, A2 = by - ay, B2 = bx - ax;
+        const float area_p = ((cx - ax) * A2 - (cy - ay) * B2) + MVR_K_EPS;
+        const int maxc = __reduce_max_sync(0xffffffffu, count);
+        for (int c = 0; c < maxc; ++c) {
+          const int lx = lxl + col, ly = lyl + row;
+          const int pix = ly * TILE + lx;
+          bool pass = c < count;
+          if (pass) {
+            const float xf = s.xf[lx], yf = s.yf[ly];
+            const float e0 = (xf - bx) * A0 - (yf - by) * B0;
+            const float e1 = (xf - cx) * A1 - (yf - cy) * B1;
+            const float e2 = (xf - ax) * A2 - (yf - ay) * B2;
+            pass = area_p > 0.f ? (e0 > 0.f && e1 > 0.f && e2 > 0.f) : (e0 < 0.f && e1 < 0.f && e2 < 0.f);
+            if (pass) pass = zmin_bits <= ((const volatile unsigned int*)s.cur)[2 * pix + 1];
+            if (++col == bw) { col = 0; ++row; }
+          }
+          const unsigned int m = __ballot_sync(0xffffffffu, pass);
+          if (pass) {
+            const int at = wcnt + __popc(m & ((1u << lane) - 1u));
+            if (at < WCAP) wq[at] = slot | (pix << 8);
+            else resolve_candidate(s, slot, pix, persp, peel);       // queue full: resolve in place
+          }
+          wcnt += __popc(m);
+        }
+      }
+      if (lane == 0) s.warp[warp] = min(wcnt, WCAP);
+      __syncthreads();
+      // ---------------- phase C: exact resolve, candidates of all warps spread over all threads ----------------
+      if (tid == 0) s.counters[0] = 0;          // every thread read the item count before the barrier above
+      {
+        int pre[NWARPS + 1];
+        pre[0] = 0;
+#pragma unroll
+        for (int wi = 0; wi < NWARPS; ++wi) pre[wi + 1] = pre[wi] + s.warp[wi];
+        for (int j = tid; j < pre[NWARPS]; j += MVR_THREADS) {
+          int wi = 0;
+#pragma unroll
+          for (int q = 1; q < NWARPS; ++q) wi += (j >= pre[q]);
+          const int cd = s.cand[wi * WCAP + (j - pre[wi])];
+          resolve_candidate(s, cd & 255, cd >> 8, persp, peel);
         }
       }
       __syncthreads();
     }
-    // ---- epilogue for layer k: fragments (+ shading / blending for k == 0) ----
-    for (int j = 0; j < TILE_PIX / MVR_THREADS; ++j) {
-      const int pix = tid + j * MVR_THREADS;
-      const int ly = pix / TILE, lx = pix % TILE;
-      const int yi = y0 + ly, xi = x0 + lx;
-      const unsigned long long key = s_cur[pix];
-      if (p.K > 1) s_prev[pix] = key;   // EMPTY stays EMPTY: later layers find nothing
-      if (yi >= p.H || xi >= p.W) continue;
-      int fid = -1;
-      float w[3] = {-1.f, -1.f, -1.f}, bb[3] = {-1.f, -1.f, -1.f}, pz = -1.f, dd = -1.f;
-      float out[3] = {bg0, bg1, bg2};
-      if (key != MVR_EMPTY_KEY) {
-        fid = (int)(unsigned int)(key & 0xffffffffull);
-        const int4 fi = __ldg(p.faces4 + f0 + fid);
-        const Face fc = load_face(p, cam, voff, fi);
-        const FaceEdges fe = face_edges(fc);
-        const float xf = s_xf[lx], yf = s_yf[ly];
-        raster_test(fc, fe, persp, xf, yf, w, bb, pz);
-        pz = __uint_as_float((unsigned int)(key >> 32));
-        if (p.dists) {
-          const float e01 = point_line_dist2(xf, yf, fc.x0, fc.y0, fc.x1, fc.y1);
-          const float e02 = point_line_dist2(xf, yf, fc.x0, fc.y0, fc.x2, fc.y2);
-          const float e12 = point_line_dist2(xf, yf, fc.x1, fc.y1, fc.x2, fc.y2);
-          dd = -fminf(fminf(e01, e02), e12);
-        }
-        if (k == 0) {
-          const float4 X0 = __ldg(p.verts4 + voff + fi.x), X1 = __ldg(p.verts4 + voff + fi.y), X2 = __ldg(p.verts4 + voff + fi.z);
-          const float4 N0 = __ldg(p.normals4 + voff + fi.x), N1 = __ldg(p.normals4 + voff + fi.y), N2 = __ldg(p.normals4 + voff + fi.z);
-          float4 c0 = ucol, c1 = ucol, c2 = ucol;
-          if (per_vertex_rgb) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
-          phong_pixel(bb, X0, X1, X2, N0, N1, N2, c0, c1, c2, sc, out);
-        }
-      }
-      const size_t po = (((size_t)n * p.H + yi) * p.W + xi) * p.K + k;
-      p.pix_to_face[po] = fid;
-      if (p.zbuf) p.zbuf[po] = pz;
-      if (p.dists) p.dists[po] = dd;
-      if (p.bary) { p.bary[3 * po] = bb[0]; p.bary[3 * po + 1] = bb[1]; p.bary[3 * po + 2] = bb[2]; }
-      if (k == 0) {
-        const size_t io = ((size_t)n * 3 * p.H + yi) * p.W + xi;
-        const size_t plane = (size_t)p.H * p.W;
-        p.images[io] = out[0]; p.images[io + plane] = out[1]; p.images[io + 2 * plane] = out[2];
-      }
-    }
+    __syncthreads();
+    fine_epilogue(p, s, cam, sc, n, k, x0, y0, f0, voff, persp, per_vertex_rgb, ucol, bg0, bg1, bg2);
     __syncthreads();
   }
 }
@@ -872,7 +1009,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.counters = (long long*)counters;
   cudaError_t e = cudaMemsetAsync(wb + w.counter, 0, 256, st);
   if (e != cudaSuccess) { set_error("mvr_mesh_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
-  const size_t bin_smem = 2 * (size_t)w.n_tiles * sizeof(int);
+  const size_t bin_smem = (2 * (size_t)w.n_tiles + W + H) * sizeof(int);
   if (bin_smem > 48 * 1024) {
     e = cudaFuncSetAttribute(mesh_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem);
     if (e != cudaSuccess) { set_error("mvr_mesh_forward: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
@@ -880,7 +1017,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   MVR_LAUNCH(mesh_bin_kernel, (unsigned)(N * w.max_chunks), MVR_THREADS, bin_smem, st, p);
   rc = check_launch("mesh_bin_kernel");
   if (rc) return rc;
-  MVR_LAUNCH(mesh_fine_kernel, (unsigned)(N * w.n_tiles), MVR_THREADS, 0, st, p);
+  MVR_LAUNCH(mesh_fine_kernel, (unsigned)(N * w.n_tiles), MVR_THREADS, fine_smem_bytes(K), st, p);
   return check_launch("mesh_fine_kernel");
 }
 
