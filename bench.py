@@ -167,7 +167,7 @@ def run_ours(a):
         faces_d = torch.cat([f for _, f in inp["meshes"]]).to(dev)
         mesh_list = [Meshes([v], [f]) for v, f in inp["meshes"]]          # what run_mvtn.py's loader hands over (CPU)
         renderer = MVRenderer(M, image_size=S, pc_rendering=False, light_direction="fixed").to(dev)
-        kernels = ["mesh_bin_kernel", "mesh_fine_kernel", "mesh_backward_kernel"]
+        kernels = ["mesh_scatter_kernel", "mesh_shade_kernel", "mesh_backward_kernel"]
     else:
         pts_d = inp["points"].to(dev)
         pts_h = inp["points"].pin_memory()

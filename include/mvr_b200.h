@@ -34,7 +34,7 @@ extern "C" {
 #define MVR_COMPOSITE_ALPHA 4      /* AlphaCompositor instead of NormWeightedCompositor (renderer.py:11,138) */
 #define MVR_RGB_PER_ELEMENT 8      /* per-vertex / per-point colours (object_color == "custom") */
 #define MVR_FACES_I64 16           /* faces given as int64 (F,3) -- the reference's layout, renderer.py:68 */
-#define MVR_TEST_TINY_POOL 0x40000000 /* tests only: bin pool of 64 entries, forces the unbinned fallback */
+#define MVR_TEST_TINY_QUEUES 0x40000000 /* tests only: shrink the scatter kernel's work queues to force their fallbacks */
 
 /* Phong constants of DirectionalLights() / Materials() as constructed at renderer.py:190-191 */
 #define MVR_AMBIENT 0.5f
@@ -44,8 +44,7 @@ extern "C" {
 
 /* counters[] slots written by the forward calls (device int64[MVR_NUM_COUNTERS], accumulated) */
 #define MVR_CNT_STRADDLE 0     /* faces straddling the near clip plane (rasterized unclipped) */
-#define MVR_CNT_BIN_OVERFLOW 1 /* bin chunks that took the unbinned fallback (correct, slower) */
-#define MVR_CNT_BIN_ENTRIES 2  /* total (face, tile) entries produced by the coarse pass */
+#define MVR_CNT_BIG_FACES 1    /* faces whose pixel bbox exceeded 1024 pixels (walked by a whole CTA) */
 #define MVR_NUM_COUNTERS 4
 
 int mvr_abi_version(void);
@@ -60,6 +59,12 @@ long long mvr_launch_count(void);
  * device time and the number of launches, and disables collection. */
 int mvr_profile_enable(const char* kernel_name);
 int mvr_profile_collect(double* total_ms, int* n_launches);
+
+/* -- host staging (renderer.py:67-68 replacement) -------------------------------- */
+/* HOST pointers: gather n arrays (counts[i] elements of elem_bytes each) back to back into dst with all
+ * host cores; narrow_i64_to_i32 converts int64 sources to int32 on the way (faces).  No CUDA calls. */
+int mvr_host_gather(const void* const* srcs, const int64_t* counts, int n, void* dst, int elem_bytes,
+                    int narrow_i64_to_i32);
 
 /* -- cameras ------------------------------------------------------------------------------ */
 /* look_at_view_transform(dist, elev, azim) + camera_position_from_spherical_angles
@@ -87,7 +92,7 @@ int mvr_mesh_prepare(const float* verts, const void* faces, const int* vert_off,
 int mvr_mesh_get_normals(const void* geometry, int64_t total_verts, int64_t total_faces,
                          float* normals, void* stream);
 
-size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int64_t total_faces, int max_faces);
+size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K);
 /* MeshRenderer(MeshRasterizer, HardPhongShader)(meshes.extend(M), cameras, lights)
  * (renderer.py:89-113; [upstream] _C.rasterize_meshes + interp_face_attrs + phong_shading +
  * hard_rgb_blend).  blur_radius = 0.

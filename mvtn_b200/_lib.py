@@ -11,8 +11,8 @@ CULL_BACKFACES = 2
 COMPOSITE_ALPHA = 4
 RGB_PER_ELEMENT = 8
 FACES_I64 = 16
-TEST_TINY_POOL = 0x40000000   # tests only: shrink the bin pool to 64 entries to force the unbinned fallback
-CNT_STRADDLE, CNT_BIN_OVERFLOW, CNT_BIN_ENTRIES, NUM_COUNTERS = 0, 1, 2, 4
+TEST_TINY_QUEUES = 0x40000000   # tests only: shrink the scatter kernel's work queues to force their fallbacks
+CNT_STRADDLE, CNT_BIG_FACES, NUM_COUNTERS = 0, 1, 4
 
 _vp, _i, _f, _d, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int64, C.c_size_t
 
@@ -23,12 +23,13 @@ SIGNATURES = {
     "mvr_launch_count": (C.c_longlong, []),
     "mvr_profile_enable": (_i, [C.c_char_p]),
     "mvr_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "mvr_host_gather": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _i, _vp, _i, _i]),
     "mvr_look_at_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mvr_look_at_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvr_mesh_geometry_bytes": (_sz, [_i64, _i64]),
     "mvr_mesh_prepare": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _i, _vp, _sz, _vp]),
     "mvr_mesh_get_normals": (_i, [_vp, _i64, _i64, _vp, _vp]),
-    "mvr_mesh_workspace_bytes": (_sz, [_i, _i, _i, _i, _i64, _i]),
+    "mvr_mesh_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "mvr_mesh_forward": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _f, _f,
                               _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mvr_mesh_backward": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _vp, _vp, _i, _vp, _f, _f, _i, _i, _i, _i,

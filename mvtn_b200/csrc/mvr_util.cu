@@ -1,4 +1,5 @@
 // mvr_util.cu -- error reporting shared by the C-ABI entry points.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -88,3 +89,38 @@ extern "C" int mvr_profile_collect(double* total_ms, int* n_launches) {
 
 extern "C" int mvr_abi_version(void) { return MVR_ABI_VERSION; }
 extern "C" const char* mvr_last_error_string(void) { return mvr::g_err; }
+
+// ---- host-side staging helper (collate -> device-resident packed geometry) -------------
+// Gathers n host arrays into one (pinned) destination with all host cores; optionally narrows int64 -> int32
+// on the way (faces), halving the bytes that cross PCIe.  Plain host code: no CUDA calls.
+extern "C" int mvr_host_gather(const void* const* srcs, const int64_t* counts, int n, void* dst, int elem_bytes,
+                               int narrow_i64_to_i32) {
+  if (n < 0 || (n > 0 && (!srcs || !counts || !dst))) { mvr::set_error("mvr_host_gather: null pointer"); return -1; }
+  if (narrow_i64_to_i32 && elem_bytes != 8) { mvr::set_error("mvr_host_gather: narrowing needs 8-byte elements"); return -2; }
+  std::vector<int64_t> off((size_t)n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    if (counts[i] < 0) { mvr::set_error("mvr_host_gather: negative count"); return -3; }
+    off[i + 1] = off[i] + counts[i];
+  }
+  const int64_t total = off[n];
+  const int64_t kChunk = 1 << 15;               // elements per work item
+  std::vector<int64_t> work;                    // (array, start) pairs flattened
+  for (int i = 0; i < n; ++i)
+    for (int64_t s = 0; s < counts[i]; s += kChunk) { work.push_back(i); work.push_back(s); }
+  const int64_t nwork = (int64_t)work.size() / 2;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t wkk = 0; wkk < nwork; ++wkk) {
+    const int i = (int)work[2 * wkk];
+    const int64_t s = work[2 * wkk + 1];
+    const int64_t cnt = std::min<int64_t>(kChunk, counts[i] - s);
+    if (narrow_i64_to_i32) {
+      const int64_t* src = (const int64_t*)srcs[i] + s;
+      int32_t* d = (int32_t*)dst + off[i] + s;
+      for (int64_t e = 0; e < cnt; ++e) d[e] = (int32_t)src[e];
+    } else {
+      memcpy((char*)dst + (off[i] + s) * elem_bytes, (const char*)srcs[i] + s * elem_bytes, (size_t)(cnt * elem_bytes));
+    }
+  }
+  (void)total;
+  return 0;
+}

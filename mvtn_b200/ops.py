@@ -67,6 +67,16 @@ def _staging_done(device):
             _staging_bufs[key] = (buf, ev)
 
 
+def _host_gather(srcs, dst: torch.Tensor, elem_bytes: int, narrow: bool):
+    import ctypes as C
+    n = len(srcs)
+    if n == 0:
+        return
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in srcs])
+    counts = (C.c_int64 * n)(*[t.numel() for t in srcs])
+    L.check(L.load().mvr_host_gather(ptrs, counts, n, dst.data_ptr(), elem_bytes, 1 if narrow else 0), "mvr_host_gather")
+
+
 def fov_projection_scale(fov_deg: float = 60.0, znear: float = 1.0, aspect: float = 1.0):
     """K00, K11 of [upstream] FoVPerspectiveCameras.compute_projection_matrix, evaluated with the same
     fp32 tensor ops (fov*pi/180, tan(fov/2)*znear, 2*znear/(max-min))."""
@@ -168,12 +178,14 @@ class PackedMeshes:
                 v_dev = torch.cat([v.detach().to(torch.float32) for v in verts], 0)
                 f_dev = torch.cat([f.detach().to(fdt) for f in faces], 0)
             else:
+                # multi-threaded gather into pinned memory (faces narrowed int64 -> int32 on the way), then
+                # ONE async H2D per array
+                v_src = [v.detach().to(device="cpu", dtype=torch.float32).contiguous() for v in verts]
+                f_src = [f.detach().to(device="cpu", dtype=fdt).contiguous() for f in faces]
                 v_host = _staging("verts", device, tv * 3, torch.float32).view(tv, 3)
-                f_host = _staging("faces", device, tf * 3, fdt).view(tf, 3)
-                if tv:
-                    torch.cat([v.detach().to(device="cpu", dtype=torch.float32) for v in verts], 0, out=v_host)
-                if tf:
-                    torch.cat([f.detach().to(device="cpu", dtype=fdt) for f in faces], 0, out=f_host)
+                f_host = _staging("faces", device, tf * 3, torch.int32).view(tf, 3)
+                _host_gather(v_src, v_host, 4, False)
+                _host_gather(f_src, f_host, 8 if fdt == torch.int64 else 4, fdt == torch.int64)
                 v_dev = v_host.to(device, non_blocking=True)
                 f_dev = f_host.to(device, non_blocking=True)
                 _staging_done(device)
@@ -265,7 +277,7 @@ class _MeshRender(torch.autograd.Function):
             bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
             dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
         counters = torch.zeros(L.NUM_COUNTERS, dtype=torch.int64, device=dev)
-        ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, geom.total_faces, geom.max_faces)
+        ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K)
         ws = workspace(dev, ws_bytes)
         with torch.cuda.device(dev):
             L.check(lib.mvr_mesh_forward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
@@ -297,7 +309,7 @@ class _MeshRender(torch.autograd.Function):
         gR = torch.empty((N, 3, 3), dtype=torch.float32, device=dev)
         gT = torch.empty((N, 3), dtype=torch.float32, device=dev)
         gC = torch.empty((N, 3), dtype=torch.float32, device=dev)
-        ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, geom.total_faces, geom.max_faces)
+        ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K)
         ws = workspace(dev, ws_bytes)
         with torch.cuda.device(dev):
             L.check(lib.mvr_mesh_backward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,

@@ -35,8 +35,9 @@ def test_library_loads_and_answers_host_queries():
     assert lib.mvr_abi_version() == _lib.ABI_VERSION
     assert lib.mvr_launch_count() >= 0
     # size queries are pure host arithmetic
-    ws = lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 32 * 10000, 10000)
-    assert 4 * 2 * 12 * 32 * 10000 <= ws < 1 << 30      # pool of 2 * M * faces int32 entries + segments
+    ws = lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 1)
+    assert 8 * 384 * 224 * 224 <= ws < 1 << 30          # one 64-bit (z, face) key per pixel and view
+    assert lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 2) >= 2 * 8 * 384 * 224 * 224   # + previous layer when peeling
     assert lib.mvr_mesh_geometry_bytes(5000, 10000) >= 5000 * 48 + 10000 * 16
     assert lib.mvr_mesh_geometry_bytes(-1, 0) == 0
     assert lib.mvr_points_workspace_bytes(32, 12, 224, 224, 1) >= 32 * 12 * 28 * 64
