@@ -210,7 +210,8 @@ def run_ours(a):
         return g_host
 
     if a.workload == "mesh":
-        h2d = sum(v.numel() * 4 + f.numel() * f.element_size() for v, f in inp["meshes"]) + 3 * B * M * 4
+        # verts fp32 + faces narrowed to int32 by the multi-threaded host gather + the three (B, M) view tensors
+        h2d = sum(v.numel() * 4 + f.numel() * 4 for v, f in inp["meshes"]) + 3 * B * M * 4
     else:
         h2d = pts_h.numel() * 4 + 3 * B * M * 4
     d2h = 3 * B * M * 4 + 4    # gradients + the rotation-validity flag

@@ -58,7 +58,7 @@ static WsLayout ws_layout(int B, int M, int H, int W, int K) {
   size_t o = 0;
   w.keys = o; o = al(o + N * HW * 8);
   w.prev = o; if (K > 1) o = al(o + N * HW * 8);
-  w.bwd_ctas_per_view = (int)((HW + MVR_THREADS * BWD_PIX_PER_THREAD - 1) / (MVR_THREADS * BWD_PIX_PER_THREAD));
+  w.bwd_ctas_per_view = ((W + 31) / 32) * ((H + 31) / 32);      // 32x32-pixel tiles
   // the backward pass reuses the front of the workspace for its per-CTA partial sums
   const size_t bwd = al(N * w.bwd_ctas_per_view * 16 * sizeof(float));
   w.total = o > bwd ? o : bwd;
@@ -479,12 +479,14 @@ __device__ __forceinline__ void phong_pixel(const float b[3], const float4 X0, c
 // ------------------------------------------------------------------------------------------------
 // shade pass: one thread per pixel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MVR_THREADS) mesh_shade_kernel(const MeshParams p, int ctas_per_view) {
-  const int n = blockIdx.x / ctas_per_view;
-  const int pix = (blockIdx.x % ctas_per_view) * MVR_THREADS + threadIdx.x;
+// grid: x = 32x8-pixel tiles of the image, y = view m, z = object b (no per-thread integer divisions)
+__global__ void __launch_bounds__(MVR_THREADS) mesh_shade_kernel(const MeshParams p, int tiles_x) {
+  const int b = blockIdx.z, n = b * p.M + blockIdx.y;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int xi = tx * 32 + (threadIdx.x & 31), yi = ty * 8 + (threadIdx.x >> 5);
   const int HW = p.H * p.W;
-  if (pix >= HW) return;
-  const int yi = pix / p.W, xi = pix - yi * p.W;
+  if (xi >= p.W || yi >= p.H) return;
+  const int pix = yi * p.W + xi;
   const int k = p.layer;
   unsigned long long* kp = p.keys + (size_t)n * HW + pix;
   const unsigned long long key = *kp;
@@ -499,7 +501,6 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_shade_kernel(const MeshParam
   if (key != MVR_EMPTY_KEY) {
     // The barycentrics are recomputed with the SAME exact operation sequence as the scatter: for sliver faces a
     // reciprocal-multiply shortcut moves them by far more than the 1e-5 image tolerance (error ~ ulp * |xy| / area).
-    const int b = n / p.M;
     const int f0 = p.face_off[b], voff = p.vert_off[b];
     const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
     const Camera cam = load_camera(p.R, p.T, n);
@@ -554,7 +555,7 @@ struct MeshBwdParams {
   const float* R; const float* T; const float* Cc; const float* light; int light_stride;
   const float* obj_rgb;
   float k00, k11;
-  int B, M, H, W, K, flags, ctas_per_view;
+  int B, M, H, W, K, flags, ctas_per_view, tiles_x;
   const int* pix_to_face; const float* grad_images;
   float* partials;       // (N, ctas_per_view, 16)
   float* grad_verts; float* grad_normals;
@@ -581,8 +582,10 @@ __global__ void __launch_bounds__(MVR_THREADS, 3) mesh_backward_kernel(const Mes
   __shared__ float s_red[NWARPS * BWD_VALS];
   __shared__ int s_any;
   const int tid = threadIdx.x;
-  const int n = blockIdx.x / p.ctas_per_view, cta = blockIdx.x % p.ctas_per_view;
-  const int b = n / p.M;
+  // grid: x = 32x32-pixel tiles, y = view m, z = object b; thread (lane, warp) owns pixels (x0+lane, y0+warp+8j)
+  const int b = blockIdx.z, n = b * p.M + blockIdx.y, cta = blockIdx.x;
+  const int tyb = cta / p.tiles_x, txb = cta - tyb * p.tiles_x;
+  const int xi = txb * 32 + (tid & 31), yi0 = tyb * 32 + (tid >> 5);
   const int HW = p.H * p.W;
   const int f0 = p.face_off[b], voff = p.vert_off[b];
   const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
@@ -592,15 +595,14 @@ __global__ void __launch_bounds__(MVR_THREADS, 3) mesh_backward_kernel(const Mes
   // issue every load of this thread's pixels first (memory-level parallelism), then do the math
   int fids[BWD_PIX_PER_THREAD];
   float gin[BWD_PIX_PER_THREAD][3];
-  const int pix0 = cta * (MVR_THREADS * BWD_PIX_PER_THREAD) + tid;
 #pragma unroll
   for (int j = 0; j < BWD_PIX_PER_THREAD; ++j) {
-    const int pix = pix0 + j * MVR_THREADS;
-    fids[j] = pix < HW ? __ldg(p.pix_to_face + ((size_t)n * HW + pix) * p.K) : -1;
+    const int yi = yi0 + 8 * j;
+    fids[j] = (xi < p.W && yi < p.H) ? __ldg(p.pix_to_face + ((size_t)n * HW + (size_t)yi * p.W + xi) * p.K) : -1;
   }
 #pragma unroll
   for (int j = 0; j < BWD_PIX_PER_THREAD; ++j) {
-    const int pix = pix0 + j * MVR_THREADS;
+    const int pix = (yi0 + 8 * j) * p.W + xi;
     if (fids[j] >= 0) {
       const size_t io = (size_t)n * 3 * HW + pix;
       gin[j][0] = __ldg(p.grad_images + io); gin[j][1] = __ldg(p.grad_images + io + HW); gin[j][2] = __ldg(p.grad_images + io + 2 * (size_t)HW);
@@ -629,8 +631,7 @@ __global__ void __launch_bounds__(MVR_THREADS, 3) mesh_backward_kernel(const Mes
     const float g0 = gin[j][0], g1 = gin[j][1], g2 = gin[j][2];
     if (fid < 0 || (g0 == 0.f && g1 == 0.f && g2 == 0.f)) continue;
     any = true;
-    const int pix = pix0 + j * MVR_THREADS;
-    const int yi = pix / p.W, xi = pix - yi * p.W;
+    const int yi = yi0 + 8 * j;
     const int4 fi = __ldg(p.faces4 + f0 + fid);
     const float4 X0 = __ldg(p.verts4 + voff + fi.x), X1 = __ldg(p.verts4 + voff + fi.y), X2 = __ldg(p.verts4 + voff + fi.z);
     const float4 N0 = __ldg(p.normals4 + voff + fi.x), N1 = __ldg(p.normals4 + voff + fi.y), N2 = __ldg(p.normals4 + voff + fi.z);
@@ -838,7 +839,7 @@ static int check_mesh_common(const char* who, int B, int M, int H, int W, int K,
   if (B < 0 || M < 0 || tv < 0 || tf < 0) { set_error("%s: negative size", who); return -1; }
   if (H <= 0 || W <= 0 || H > 4096 || W > 4096) { set_error("%s: image size %dx%d outside [1, 4096]", who, H, W); return -2; }
   if (K < 1 || K > 64) { set_error("%s: faces_per_pixel %d outside [1, 64]", who, K); return -3; }
-  if ((int64_t)B * M * (((int64_t)H * W + 255) / 256 + 1) > 0x7fffffffLL) { set_error("%s: too many views", who); return -4; }
+  if ((int64_t)B * M * (((int64_t)H * W + 255) / 256 + 1) > 0x7fffffffLL || B > 65535 || M > 65535) { set_error("%s: too many views", who); return -4; }
   return 0;
 }
 
@@ -883,7 +884,8 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   cudaError_t e = cudaMemsetAsync(p.keys, 0xFF, (size_t)N * HW * 8, st);      // every key = EMPTY
   if (e != cudaSuccess) { set_error("mvr_mesh_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
   const size_t tab_smem = ((size_t)W + H) * sizeof(float);
-  const int shade_ctas = (int)((HW + MVR_THREADS - 1) / MVR_THREADS);
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
+  const dim3 shade_grid((unsigned)(tiles_x * tiles_y), (unsigned)M, (unsigned)B);
   for (int k = 0; k < K; ++k) {
     p.layer = k;
     if (chunks_per_view > 0) {
@@ -891,7 +893,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
       rc = check_launch("mesh_scatter_kernel");
       if (rc) return rc;
     }
-    MVR_LAUNCH(mesh_shade_kernel, (unsigned)(N * shade_ctas), MVR_THREADS, 0, st, p, shade_ctas);
+    MVR_LAUNCH(mesh_shade_kernel, shade_grid, MVR_THREADS, 0, st, p, tiles_x);
     rc = check_launch("mesh_shade_kernel");
     if (rc) return rc;
   }
@@ -924,10 +926,10 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   p.vert_off = vert_off; p.face_off = face_off;
   p.R = R; p.T = T; p.Cc = Cc; p.light = light; p.light_stride = light_stride; p.obj_rgb = obj_rgb;
   p.k00 = k00; p.k11 = k11;
-  p.B = B; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags; p.ctas_per_view = w.bwd_ctas_per_view;
+  p.B = B; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags; p.ctas_per_view = w.bwd_ctas_per_view; p.tiles_x = (W + 31) / 32;
   p.pix_to_face = pix_to_face; p.grad_images = grad_images;
   p.partials = (float*)workspace; p.grad_verts = grad_verts; p.grad_normals = grad_normals;
-  MVR_LAUNCH(mesh_backward_kernel, (unsigned)(N * w.bwd_ctas_per_view), MVR_THREADS, 0, st, p);
+  MVR_LAUNCH(mesh_backward_kernel, dim3((unsigned)w.bwd_ctas_per_view, (unsigned)M, (unsigned)B), MVR_THREADS, 0, st, p);
   rc = check_launch("mesh_backward_kernel");
   if (rc) return rc;
   const int wpb = 8;

@@ -18,6 +18,25 @@ from .cameras import FoVOrthographicCameras, FoVPerspectiveCameras
 from .structures import unpack_mesh_list
 from .util import torch_color
 
+_small_cache = {}
+
+
+def _device_vec(values, device):
+    """Small constant vectors (colours, fixed light) are uploaded once per (device, value) and reused: a
+    pageable host->device copy synchronises the stream, and the reference pays one per call."""
+    t = torch.as_tensor(values, dtype=torch.float32).detach()
+    if t.is_cuda:
+        return t.to(device)
+    key = (str(device), tuple(t.reshape(-1).tolist()), tuple(t.shape))
+    hit = _small_cache.get(key)
+    if hit is None:
+        if len(_small_cache) > 256:
+            _small_cache.clear()
+        hit = t.to(device)
+        _small_cache[key] = hit
+    return hit
+
+
 ORTHOGONAL_THRESHOLD = 1e-6   # renderer.py:29
 EXAHSTION_LIMIT = 20          # renderer.py:30 (sic)
 
@@ -95,11 +114,11 @@ class MVRenderer(nn.Module):
         geom = self._packed(meshes, color, device)
         if geom.B != azim.shape[0]:
             raise ValueError(f"{geom.B} meshes but azim has batch {azim.shape[0]}")
-        bg = torch.as_tensor(background_color, dtype=torch.float32).to(device)
-        obj = None if geom.per_vertex_rgb else torch.as_tensor(color, dtype=torch.float32).to(device)
+        bg = _device_vec(background_color, device)
+        obj = None if geom.per_vertex_rgb else _device_vec(color, device)
 
         def render(R, T, C, dist_):
-            light = C.detach() if lights is None else torch.as_tensor(lights, dtype=torch.float32).to(device)
+            light = C.detach() if lights is None else _device_vec(lights, device)
             return ops.render_meshes(geom, self.nb_views, R, T, C, light, obj, bg, self.image_size,
                                      faces_per_pixel=self.faces_per_pixel, cull_backfaces=self.cull_backfaces,
                                      perspective_correct=self.perspective_correct)
@@ -115,10 +134,12 @@ class MVRenderer(nn.Module):
         if points.shape[0] != azim.shape[0]:
             raise ValueError(f"{points.shape[0]} clouds but azim has batch {azim.shape[0]}")
         pts = points.to(device=device, dtype=torch.float32, non_blocking=True)
-        bg = torch.as_tensor(background_color, dtype=torch.float32).to(device)
-        rgb = torch.as_tensor(color, dtype=torch.float32).to(device)
-        if rgb.numel() != 3:
-            rgb = rgb * torch.ones_like(pts)          # renderer.py:119-120 features = color * ones_like(points)
+        bg = _device_vec(background_color, device)
+        rgb = torch.as_tensor(color, dtype=torch.float32)
+        if rgb.numel() == 3:
+            rgb = _device_vec(rgb, device)
+        else:
+            rgb = rgb.to(device) * torch.ones_like(pts)          # renderer.py:119-120 features = color * ones_like(points)
 
         def render(R, T, C, dist_):
             inv_dist = 1.0 / dist_.reshape(-1)        # renderer.py:142 point_cloud.scale_(1/dist)
