@@ -1,13 +1,13 @@
 // mvr_points.cu -- point-cloud path of MVRenderer (renderer.py:116-151) for sm_100a.
 //
-//   forward : points_forward_kernel -- one CTA per (view, strip of image rows).  A view has only a few
-//             thousand points, so there is no global binning pass: every strip CTA streams the cloud
-//             once (coalesced, L2-resident across the M views and strips), projects
-//             p = (X / dist) R + T, rejects on the strip's y-range, and SCATTERS each surviving point into
-//             the handful of pixel centres inside its radius with a 64-bit (z, point) min on a
-//             shared-memory key per pixel.  K > 1 peels layers.  The epilogue recomputes dist2 of the
-//             winner, applies the norm-weighted or alpha compositor and the background, and writes whole
-//             image rows (fully coalesced planar stores).
+//   forward : per layer k (K = points_per_pixel passes; K = 1 in MVTN's configuration)
+//               points_scatter_kernel -- one thread per (view, point): p = (X / dist) R + T is computed ONCE per
+//                 view, the handful of pixel centres inside the point's radius are tested exactly
+//                 (dist2 < r^2, IEEE fp32) and a 64-bit (z, point) RED.MIN goes to the pixel's key in a
+//                 global, L2-resident key plane (pass k keeps keys > layer k-1);
+//               points_resolve_kernel -- one thread per pixel: key -> idx / zbuf / dists2 of layer k, key plane
+//                 handed to the next pass; the last pass recomputes dist2 of every layer, applies the
+//                 norm-weighted or alpha compositor and the background, and writes planar (n,3,H,W) rows.
 //   backward: points_backward_kernel -- per pixel recompute from idx only; compositor backward ->
 //             d dist2 -> d ndc.xy -> (dR, dT, d(1/dist)) block-reduced to one partial per (view, strip),
 //             summed in fixed order; optional per-point / colour gradients via atomics.
@@ -22,7 +22,8 @@ struct PointsParams {
   const float* points; const float* rgb;
   const float* R; const float* T; const float* inv_dist; const float* bg_rgb;
   float radius, r2_raster, r2_weight;
-  int B, Np, M, H, W, K, flags, strip_rows, n_strips;
+  int B, Np, M, H, W, K, flags, layer;
+  unsigned long long* keys; unsigned long long* prev;
   float* images; int* idx; float* zbuf; float* dists2;
 };
 
@@ -32,111 +33,118 @@ __device__ __forceinline__ void project_point(const float* __restrict__ pts, int
   world_to_view(cam, x, y, z, px, py, pz);
 }
 
-__global__ void __launch_bounds__(MVR_THREADS) points_forward_kernel(const PointsParams p) {
-  extern __shared__ unsigned long long s_keys[];   // cur [rows*W] (+ prev [rows*W] + acc float4 [rows*W] when K > 1)
-  const int tid = threadIdx.x;
-  const int n = blockIdx.x / p.n_strips, strip = blockIdx.x % p.n_strips;
-  const int b = n / p.M;
-  const int y0 = strip * p.strip_rows, y1 = min(y0 + p.strip_rows, p.H) - 1;   // inclusive
-  const int npix = (y1 - y0 + 1) * p.W;
-  const int cap = p.strip_rows * p.W;
-  unsigned long long* s_cur = s_keys;
-  unsigned long long* s_prev = s_keys + cap;
-  float4* s_acc = (float4*)(s_keys + 2 * (size_t)cap);
+// grid: x = blocks of 256 points, y = view m, z = object b
+__global__ void __launch_bounds__(MVR_THREADS) points_scatter_kernel(const PointsParams p) {
+  const int b = blockIdx.z, n = b * p.M + blockIdx.y;
+  const int pi = blockIdx.x * MVR_THREADS + threadIdx.x;
+  if (pi >= p.Np) return;
   const Camera cam = load_camera(p.R, p.T, n);
   const float s = __ldg(p.inv_dist + n);
-  const float* pts = p.points + 3 * (size_t)b * p.Np;
-  const bool per_point_rgb = p.flags & MVR_RGB_PER_ELEMENT;
-  const bool alpha_mode = p.flags & MVR_COMPOSITE_ALPHA;
-  const float* feat = per_point_rgb ? p.rgb + 3 * (size_t)b * p.Np : p.rgb;
-  const float bg0 = __ldg(p.bg_rgb), bg1 = __ldg(p.bg_rgb + 1), bg2 = __ldg(p.bg_rgb + 2);
-  // conservative search radius for candidate pixel centres (the exact test is dist2 < r2 below)
+  float px, py, pz;
+  project_point(p.points + 3 * (size_t)b * p.Np, pi, s, cam, px, py, pz);
+  if (pz < 0.f) return;
+  // conservative search window for candidate pixel centres (the exact test is dist2 < r2 below)
   const float rr = p.radius * 1.0001f + 1e-7f;
-  // y-extent of the strip in NDC (pixel centres), padded by the search radius
-  const float strip_ymax = pix_to_ndc(p.H - 1 - y0, p.H, p.W) + rr;
-  const float strip_ymin = pix_to_ndc(p.H - 1 - y1, p.H, p.W) - rr;
-
-  if (p.K > 1)
-    for (int i = tid; i < npix; i += MVR_THREADS) { s_prev[i] = 0ull; s_acc[i] = make_float4(0.f, 0.f, 0.f, alpha_mode ? 1.f : 0.f); }
-
-  for (int k = 0; k < p.K; ++k) {
-    const bool peel = k > 0;
-    for (int i = tid; i < npix; i += MVR_THREADS) s_cur[i] = MVR_EMPTY_KEY;
-    __syncthreads();
-    for (int pi = tid; pi < p.Np; pi += MVR_THREADS) {
-      float px, py, pz;
-      project_point(pts, pi, s, cam, px, py, pz);
-      if (!(py <= strip_ymax && py >= strip_ymin)) continue;
-      if (pz < 0.f) continue;
-      int jlo, jhi;
-      ndc_range_to_pix(py - rr, py + rr, p.H, p.W, jlo, jhi);
-      const int yl = max(p.H - 1 - jhi, y0), yh = min(p.H - 1 - jlo, y1);
-      if (yl > yh) continue;
-      ndc_range_to_pix(px - rr, px + rr, p.W, p.H, jlo, jhi);
-      const int xl = p.W - 1 - jhi, xh = p.W - 1 - jlo;
-      const unsigned long long key = make_key(pz, pi);
-      for (int yy = yl; yy <= yh; ++yy) {
-        const float dy = py - pix_to_ndc(p.H - 1 - yy, p.H, p.W);
-        for (int xx = xl; xx <= xh; ++xx) {
-          const float dx = px - pix_to_ndc(p.W - 1 - xx, p.W, p.H);
-          const float d2 = dx * dx + dy * dy;
-          if (!(d2 < p.r2_raster)) continue;
-          const int pix = (yy - y0) * p.W + xx;
-          if (peel && key <= s_prev[pix]) continue;
-          smem_key_min(&s_cur[pix], key);
-        }
-      }
+  int jlo, jhi;
+  ndc_range_to_pix(py - rr, py + rr, p.H, p.W, jlo, jhi);
+  const int yl = p.H - 1 - jhi, yh = p.H - 1 - jlo;
+  if (yl > yh) return;
+  ndc_range_to_pix(px - rr, px + rr, p.W, p.H, jlo, jhi);
+  const int xl = p.W - 1 - jhi, xh = p.W - 1 - jlo;
+  const unsigned long long key = make_key(pz, pi);
+  const size_t HW = (size_t)p.H * p.W;
+  unsigned long long* keys = p.keys + (size_t)n * HW;
+  const unsigned long long* prev = p.layer > 0 ? p.prev + (size_t)n * HW : nullptr;
+  for (int yy = yl; yy <= yh; ++yy) {
+    const float dy = py - pix_to_ndc(p.H - 1 - yy, p.H, p.W);
+    for (int xx = xl; xx <= xh; ++xx) {
+      const float dx = px - pix_to_ndc(p.W - 1 - xx, p.W, p.H);
+      const float d2 = dx * dx + dy * dy;
+      if (!(d2 < p.r2_raster)) continue;
+      const size_t o = (size_t)yy * p.W + xx;
+      if (prev && key <= __ldcg(prev + o)) continue;
+      if (key >= __ldcg(keys + o)) continue;
+      atomicMin(keys + o, key);      // result unused: RED.MIN.64 resolved in L2
     }
-    __syncthreads();
-    // ---- epilogue for layer k ----
-    const bool last = k == p.K - 1;
-    for (int pix = tid; pix < npix; pix += MVR_THREADS) {
-      const int yi = y0 + pix / p.W, xi = pix % p.W;
-      const unsigned long long key = s_cur[pix];
-      int pid = -1;
-      float z = -1.f, d2 = -1.f;
-      float4 acc = make_float4(0.f, 0.f, 0.f, alpha_mode ? 1.f : 0.f);
-      if (p.K > 1) { acc = s_acc[pix]; s_prev[pix] = key; }
-      if (key != MVR_EMPTY_KEY) {
-        pid = (int)(unsigned int)(key & 0xffffffffull);
-        float px, py, pz;
-        project_point(pts, pid, s, cam, px, py, pz);
-        const float dx = px - pix_to_ndc(p.W - 1 - xi, p.W, p.H);
-        const float dy = py - pix_to_ndc(p.H - 1 - yi, p.H, p.W);
-        d2 = dx * dx + dy * dy;
-        z = __uint_as_float((unsigned int)(key >> 32));
-        const float a = 1.f - d2 / p.r2_weight;
-        const float f0 = __ldg(feat + (per_point_rgb ? 3 * (size_t)pid : 0)), f1 = __ldg(feat + (per_point_rgb ? 3 * (size_t)pid : 0) + 1),
-                    f2 = __ldg(feat + (per_point_rgb ? 3 * (size_t)pid : 0) + 2);
-        if (alpha_mode) {   // out += cum * alpha * f ; cum *= (1 - alpha)
-          const float ca = acc.w * a;
-          acc.x += ca * f0; acc.y += ca * f1; acc.z += ca * f2;
-          acc.w = acc.w * (1.f - a);
-        } else {            // numerators and the alpha sum
-          acc.x += a * f0; acc.y += a * f1; acc.z += a * f2;
-          acc.w += a;
-        }
-      }
-      if (p.K > 1) s_acc[pix] = acc;
-      const size_t po = (((size_t)n * p.H + yi) * p.W + xi) * p.K + k;
-      p.idx[po] = pid;
-      if (p.zbuf) p.zbuf[po] = z;
-      if (p.dists2) p.dists2[po] = d2;
-      if (last) {
-        // background where the FIRST layer is empty ([upstream] _add_background_color_to_images)
-        const bool fg = (p.K > 1) ? (p.idx[po - k] >= 0) : (pid >= 0);
-        float o0 = bg0, o1 = bg1, o2 = bg2;
-        if (fg) {
-          if (alpha_mode) { o0 = acc.x; o1 = acc.y; o2 = acc.z; }
-          else { const float t = fmaxf(acc.w, 1e-4f); o0 = acc.x / t; o1 = acc.y / t; o2 = acc.z / t; }
-        }
-        const size_t io = ((size_t)n * 3 * p.H + yi) * p.W + xi;
-        const size_t plane = (size_t)p.H * p.W;
-        p.images[io] = o0; p.images[io + plane] = o1; p.images[io + 2 * plane] = o2;
-      }
-    }
-    __syncthreads();
   }
+}
+
+// grid: x = 32x8-pixel tiles, y = view m, z = object b
+__global__ void __launch_bounds__(MVR_THREADS) points_resolve_kernel(const PointsParams p, int tiles_x) {
+  const int b = blockIdx.z, n = b * p.M + blockIdx.y;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int xi = tx * 32 + (threadIdx.x & 31), yi = ty * 8 + (threadIdx.x >> 5);
+  if (xi >= p.W || yi >= p.H) return;
+  const size_t HW = (size_t)p.H * p.W;
+  const size_t pix = (size_t)yi * p.W + xi;
+  const int k = p.layer;
+  unsigned long long* kp = p.keys + (size_t)n * HW + pix;
+  const unsigned long long key = *kp;
+  if (k + 1 < p.K) {            // hand the layer to the next peeling pass
+    p.prev[(size_t)n * HW + pix] = key;
+    *kp = MVR_EMPTY_KEY;
+  }
+  const bool hit = key != MVR_EMPTY_KEY;
+  const int pid = hit ? (int)(unsigned int)(key & 0xffffffffull) : -1;
+  const size_t po = ((size_t)n * HW + pix) * p.K;
+  p.idx[po + k] = pid;
+  const bool want_frag = p.zbuf || p.dists2;
+  const bool last = k == p.K - 1;
+  if (!want_frag && !last) return;
+  // first-layer hit decides foreground ([upstream] _add_background_color_to_images)
+  const int first = k == 0 ? pid : p.idx[po];
+  Camera cam;
+  float s = 0.f, xf = 0.f, yf = 0.f;
+  const float* pts = p.points + 3 * (size_t)b * p.Np;
+  if (first >= 0) {
+    cam = load_camera(p.R, p.T, n);
+    s = __ldg(p.inv_dist + n);
+    xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H);
+    yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
+  }
+  if (want_frag) {
+    float z = -1.f, d2 = -1.f;
+    if (hit) {
+      float px, py, pz;
+      project_point(pts, pid, s, cam, px, py, pz);
+      const float dx = px - xf, dy = py - yf;
+      d2 = dx * dx + dy * dy;
+      z = __uint_as_float((unsigned int)(key >> 32));
+    }
+    if (p.zbuf) p.zbuf[po + k] = z;
+    if (p.dists2) p.dists2[po + k] = d2;
+  }
+  if (!last) return;
+  // ---- compositing over all layers ([upstream] norm_weighted_sum / alpha_composite) ----
+  float o0 = __ldg(p.bg_rgb), o1 = __ldg(p.bg_rgb + 1), o2 = __ldg(p.bg_rgb + 2);
+  if (first >= 0) {
+    const bool per_point_rgb = p.flags & MVR_RGB_PER_ELEMENT;
+    const bool alpha_mode = p.flags & MVR_COMPOSITE_ALPHA;
+    const float* feat = per_point_rgb ? p.rgb + 3 * (size_t)b * p.Np : p.rgb;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, aw = alpha_mode ? 1.f : 0.f;
+    for (int l = 0; l < p.K; ++l) {
+      const int q = l == k ? pid : p.idx[po + l];
+      if (q < 0) break;
+      float px, py, pz;
+      project_point(pts, q, s, cam, px, py, pz);
+      const float dx = px - xf, dy = py - yf;
+      const float a = 1.f - (dx * dx + dy * dy) / p.r2_weight;
+      const float* f = feat + (per_point_rgb ? 3 * (size_t)q : 0);
+      const float f0 = __ldg(f), f1 = __ldg(f + 1), f2 = __ldg(f + 2);
+      if (alpha_mode) {   // out += cum * alpha * f ; cum *= (1 - alpha)
+        const float ca = aw * a;
+        a0 += ca * f0; a1 += ca * f1; a2 += ca * f2;
+        aw = aw * (1.f - a);
+      } else {            // numerators and the alpha sum
+        a0 += a * f0; a1 += a * f1; a2 += a * f2;
+        aw += a;
+      }
+    }
+    if (alpha_mode) { o0 = a0; o1 = a1; o2 = a2; }
+    else { const float t = fmaxf(aw, 1e-4f); o0 = a0 / t; o1 = a1 / t; o2 = a2 / t; }
+  }
+  const size_t io = (size_t)n * 3 * HW + pix;
+  p.images[io] = o0; p.images[io + HW] = o1; p.images[io + 2 * HW] = o2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -267,17 +275,6 @@ __global__ void points_backward_reduce_kernel(const float* __restrict__ partials
   else if (lane == 12) gs[n] = s;
 }
 
-static int choose_strip_rows(int N, int H, int W, int K, size_t* smem_bytes) {
-  const size_t bpp = K == 1 ? 8 : 32;
-  int rows = (int)((64 * 1024) / ((size_t)W * bpp));
-  if (rows > 32) rows = 32;
-  if (rows < 1) rows = 1;
-  if (rows > H) rows = H;
-  while (rows > 4 && (long long)N * ((H + rows - 1) / rows) < 4 * 148) rows = (rows + 1) / 2;
-  *smem_bytes = (size_t)rows * W * bpp;
-  return rows;
-}
-
 }  // namespace mvr
 
 using namespace mvr;
@@ -287,14 +284,21 @@ static int check_points_common(const char* who, int B, int Np, int M, int H, int
   if (H <= 0 || W <= 0 || H > 4096 || W > 4096) { set_error("%s: image size %dx%d outside [1, 4096]", who, H, W); return -2; }
   if (K < 1 || K > 64) { set_error("%s: points_per_pixel %d outside [1, 64]", who, K); return -3; }
   if (!(radius > 0.0)) { set_error("%s: radius must be positive", who); return -4; }
-  if ((int64_t)B * M > 0x7fffffffLL / (H + 1)) { set_error("%s: too many views", who); return -5; }
+  if ((int64_t)B * M > 0x7fffffffLL / (H + 1) || B > 65535 || M > 65535) { set_error("%s: too many views", who); return -5; }
   return 0;
 }
 
-extern "C" size_t mvr_points_workspace_bytes(int B, int M, int H, int W, int K) {
-  if (B < 0 || M < 0 || H <= 0 || W <= 0) return 0;
+static size_t points_partials_bytes(int B, int M, int H) {
   const size_t n_strips = (H + PB_ROWS - 1) / PB_ROWS;
   return ((size_t)B * M * n_strips * 16 * sizeof(float) + 255) & ~(size_t)255;
+}
+
+extern "C" size_t mvr_points_workspace_bytes(int B, int M, int H, int W, int K) {
+  if (B < 0 || M < 0 || H <= 0 || W <= 0 || K < 1) return 0;
+  const size_t plane = (((size_t)B * M * H * W * 8) + 255) & ~(size_t)255;
+  const size_t fwd = plane * (K > 1 ? 2 : 1);
+  const size_t bwd = points_partials_bytes(B, M, H);
+  return fwd > bwd ? fwd : bwd;
 }
 
 extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
@@ -305,24 +309,36 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
   if (rc) return rc;
   const int64_t N = (int64_t)B * M;
   if (N == 0) return 0;
-  if ((Np > 0 && !points) || !rgb || !R || !T || !inv_dist || !bg_rgb || !images || !idx) { set_error("mvr_points_forward: null pointer"); return -6; }
+  if ((Np > 0 && !points) || !rgb || !R || !T || !inv_dist || !bg_rgb || !images || !idx || !workspace) { set_error("mvr_points_forward: null pointer"); return -6; }
+  const size_t HW = (size_t)H * W;
+  const size_t plane = (((size_t)N * HW * 8) + 255) & ~(size_t)255;
+  if (workspace_bytes < plane * (K > 1 ? 2 : 1)) { set_error("mvr_points_forward: workspace too small (%zu < %zu)", workspace_bytes, plane * (K > 1 ? 2 : 1)); return -7; }
   PointsParams p;
   p.points = points; p.rgb = rgb; p.R = R; p.T = T; p.inv_dist = inv_dist; p.bg_rgb = bg_rgb;
   p.radius = (float)radius;
   p.r2_raster = p.radius * p.radius;            // [upstream] rasterize_points_cpu.cpp: float radius * radius
   p.r2_weight = (float)(radius * radius);       // [upstream] points/renderer.py: python-float r * r
-  p.B = B; p.Np = Np; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags;
-  size_t smem;
-  p.strip_rows = choose_strip_rows((int)N, H, W, K, &smem);
-  p.n_strips = (H + p.strip_rows - 1) / p.strip_rows;
+  p.B = B; p.Np = Np; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags; p.layer = 0;
+  p.keys = (unsigned long long*)workspace; p.prev = (unsigned long long*)((char*)workspace + plane);
   p.images = images; p.idx = idx; p.zbuf = zbuf; p.dists2 = dists2;
-  if (smem > 200 * 1024) { set_error("mvr_points_forward: image too wide for one shared-memory row (%zu B)", smem); return -7; }
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(points_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("mvr_points_forward: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(p.keys, 0xFF, (size_t)N * HW * 8, st);      // every key = EMPTY
+  if (e != cudaSuccess) { set_error("mvr_points_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
+  const dim3 scatter_grid((unsigned)((Np + MVR_THREADS - 1) / MVR_THREADS), (unsigned)M, (unsigned)B);
+  const dim3 resolve_grid((unsigned)(tiles_x * tiles_y), (unsigned)M, (unsigned)B);
+  for (int k = 0; k < K; ++k) {
+    p.layer = k;
+    if (Np > 0) {
+      MVR_LAUNCH(points_scatter_kernel, scatter_grid, MVR_THREADS, 0, st, p);
+      rc = check_launch("points_scatter_kernel");
+      if (rc) return rc;
+    }
+    MVR_LAUNCH(points_resolve_kernel, resolve_grid, MVR_THREADS, 0, st, p, tiles_x);
+    rc = check_launch("points_resolve_kernel");
+    if (rc) return rc;
   }
-  MVR_LAUNCH(points_forward_kernel, (unsigned)(N * p.n_strips), MVR_THREADS, smem, (cudaStream_t)stream, p);
-  return check_launch("points_forward_kernel");
+  return 0;
 }
 
 extern "C" int mvr_points_backward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
@@ -337,7 +353,7 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
   if ((Np > 0 && !points) || !rgb || !R || !T || !inv_dist || !idx || !grad_images || !gR || !gT || !g_inv_dist || !workspace) {
     set_error("mvr_points_backward: null pointer"); return -6;
   }
-  const size_t need = mvr_points_workspace_bytes(B, M, H, W, K);
+  const size_t need = points_partials_bytes(B, M, H);
   if (workspace_bytes < need) { set_error("mvr_points_backward: workspace too small (%zu < %zu)", workspace_bytes, need); return -7; }
   PointsBwdParams p;
   p.points = points; p.rgb = rgb; p.R = R; p.T = T; p.inv_dist = inv_dist;

@@ -366,10 +366,11 @@ class _PointsRender(torch.autograd.Function):
         if want_fragments:
             zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
             d2 = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        ws = workspace(dev, lib.mvr_points_workspace_bytes(B, M, H, W, K))
         with torch.cuda.device(dev):
             L.check(lib.mvr_points_forward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), float(radius),
                                            _ptr(bg_rgb), H, W, K, flags, _ptr(images), _ptr(idx), _ptr(zbuf), _ptr(d2),
-                                           None, 0, _stream(dev)), "mvr_points_forward")
+                                           _ptr(ws), ws.numel(), _stream(dev)), "mvr_points_forward")
         ctx.set_materialize_grads(False)
         ctx.cfg = (B, Np, M, float(radius), H, W, K, flags)
         ctx.rgb_shape = rgb.shape
