@@ -151,6 +151,7 @@ def run_ours(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = L.load()
+    lib.mvr_host_set_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))     # ranks share the host cores
     inp = make_inputs(a, rank)
     B, M, S = a.batch, a.views, a.image_size
     N = B * M

@@ -63,6 +63,8 @@ int mvr_profile_collect(double* total_ms, int* n_launches);
 /* -- host staging (renderer.py:67-68 replacement) -------------------------------- */
 /* HOST pointers: gather n arrays (counts[i] elements of elem_bytes each) back to back into dst with all
  * host cores; narrow_i64_to_i32 converts int64 sources to int32 on the way (faces).  No CUDA calls. */
+/* number of host threads mvr_host_gather may use (0 = all); set it to cores / ranks under torchrun */
+int mvr_host_set_threads(int n);
 int mvr_host_gather(const void* const* srcs, const int64_t* counts, int n, void* dst, int elem_bytes,
                     int narrow_i64_to_i32);
 

@@ -23,6 +23,7 @@ SIGNATURES = {
     "mvr_launch_count": (C.c_longlong, []),
     "mvr_profile_enable": (_i, [C.c_char_p]),
     "mvr_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "mvr_host_set_threads": (_i, [_i]),
     "mvr_host_gather": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _i, _vp, _i, _i]),
     "mvr_look_at_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mvr_look_at_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <omp.h>
 #include <vector>
 
 #include "mvr_common.cuh"
@@ -93,6 +94,9 @@ extern "C" const char* mvr_last_error_string(void) { return mvr::g_err; }
 // ---- host-side staging helper (collate -> device-resident packed geometry) -------------
 // Gathers n host arrays into one (pinned) destination with all host cores; optionally narrows int64 -> int32
 // on the way (faces), halving the bytes that cross PCIe.  Plain host code: no CUDA calls.
+static int g_host_threads = 0;   // 0 = OpenMP default
+extern "C" int mvr_host_set_threads(int n) { g_host_threads = n > 0 ? n : 0; return 0; }
+
 extern "C" int mvr_host_gather(const void* const* srcs, const int64_t* counts, int n, void* dst, int elem_bytes,
                                int narrow_i64_to_i32) {
   if (n < 0 || (n > 0 && (!srcs || !counts || !dst))) { mvr::set_error("mvr_host_gather: null pointer"); return -1; }
@@ -108,7 +112,8 @@ extern "C" int mvr_host_gather(const void* const* srcs, const int64_t* counts, i
   for (int i = 0; i < n; ++i)
     for (int64_t s = 0; s < counts[i]; s += kChunk) { work.push_back(i); work.push_back(s); }
   const int64_t nwork = (int64_t)work.size() / 2;
-#pragma omp parallel for schedule(dynamic, 1)
+  const int nthreads = g_host_threads > 0 ? g_host_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
   for (int64_t wkk = 0; wkk < nwork; ++wkk) {
     const int i = (int)work[2 * wkk];
     const int64_t s = work[2 * wkk + 1];

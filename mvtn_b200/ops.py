@@ -67,6 +67,13 @@ def _staging_done(device):
             _staging_bufs[key] = (buf, ev)
 
 
+def _hw(image_size):
+    """int -> (S, S); (H, W) tuple as in PyTorch3D's RasterizationSettings.image_size."""
+    if isinstance(image_size, (tuple, list)):
+        return int(image_size[0]), int(image_size[1])
+    return int(image_size), int(image_size)
+
+
 def _host_gather(srcs, dst: torch.Tensor, elem_bytes: int, narrow: bool):
     import ctypes as C
     n = len(srcs)
@@ -240,6 +247,14 @@ class PackedMeshes:
                                          _ptr(self.geometry), self.geometry.numel(), _stream(device)),
                     "mvr_mesh_prepare")
 
+    def faces_global(self) -> torch.Tensor:
+        """(Ftot,3) int64 faces indexing the PACKED vertex array (mesh-local id + the mesh's vertex offset)."""
+        if getattr(self, "_faces_global", None) is None:
+            counts = torch.tensor(self.num_faces, device=self.device)
+            off = torch.repeat_interleave(self.vert_off[:-1].to(torch.int64), counts)
+            self._faces_global = self.faces.to(torch.int64) + off[:, None]
+        return self._faces_global
+
     def vertex_normals(self) -> torch.Tensor:
         out = torch.empty((self.total_verts, 3), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
@@ -248,13 +263,23 @@ class PackedMeshes:
         return out
 
 
+def vertex_normals_torch(verts: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:
+    """Differentiable area-weighted vertex normals ([upstream] Meshes._compute_vertex_normals).  Used only to chain
+    d/d normals -> d/d verts when mesh vertices require grad; the forward normals come from mvr_mesh_prepare."""
+    vf = verts[faces]
+    fn = torch.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1], dim=1)
+    vn = torch.zeros_like(verts).index_add(0, faces[:, 0], fn).index_add(0, faces[:, 1], fn).index_add(0, faces[:, 2], fn)
+    return torch.nn.functional.normalize(vn, eps=1e-6, dim=1)
+
+
 # --------------------------------------------------------------------------------------------------
 # mesh rendering
 # --------------------------------------------------------------------------------------------------
 class _MeshRender(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, R, T, Cc, geom: PackedMeshes, M, light, obj_rgb, bg_rgb, k00, k11, z_clip, H, W, K, flags,
+    def forward(ctx, R, T, Cc, verts, geom: PackedMeshes, M, light, obj_rgb, bg_rgb, k00, k11, z_clip, H, W, K, flags,
                 want_fragments):
+        # `verts` (packed (Vtot,3), same values as geom.verts) only carries autograd history for vertex gradients
         lib = L.load()
         dev = geom.device
         R, T, Cc = _f32c(R), _f32c(T), _f32c(Cc)
@@ -299,7 +324,7 @@ class _MeshRender(torch.autograd.Function):
     def backward(ctx, g_images, *_unused):
         lib = L.load()
         if g_images is None:
-            return (None,) * 16
+            return (None,) * 17
         geom, M = ctx.geom, ctx.M
         R, T, Cc, light, obj_rgb, p2f = ctx.saved_tensors
         k00, k11, H, W, K, flags = ctx.cfg
@@ -311,24 +336,38 @@ class _MeshRender(torch.autograd.Function):
         gC = torch.empty((N, 3), dtype=torch.float32, device=dev)
         ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K)
         ws = workspace(dev, ws_bytes)
+        gV = gN = None
+        if ctx.needs_input_grad[3]:
+            gV = torch.zeros((geom.total_verts, 3), dtype=torch.float32, device=dev)
+            gN = torch.zeros((geom.total_verts, 3), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             L.check(lib.mvr_mesh_backward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
                                           geom.total_verts, geom.total_faces, _ptr(R), _ptr(T), _ptr(Cc), _ptr(light),
                                           ctx.light_stride, _ptr(obj_rgb), k00, k11, H, W, K, flags, _ptr(p2f),
-                                          _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gC), None, None, _ptr(ws), ws.numel(),
-                                          _stream(dev)), "mvr_mesh_backward")
-        return (gR, gT, gC) + (None,) * 13
+                                          _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gC), _ptr(gV), _ptr(gN), _ptr(ws),
+                                          ws.numel(), _stream(dev)), "mvr_mesh_backward")
+        if gV is not None:
+            # the kernel returns d/d verts through projection + interpolated position, and d/d unit normals;
+            # the normals -> verts chain ([upstream] Meshes._compute_vertex_normals) is optional plumbing in torch
+            with torch.enable_grad():
+                v = geom.verts.detach().requires_grad_()
+                (gv2,) = torch.autograd.grad(vertex_normals_torch(v, geom.faces_global()), v, gN)
+            gV = gV + gv2
+        return (gR, gT, gC, gV) + (None,) * 13
 
 
 def render_meshes(geom: PackedMeshes, M: int, R, T, Cc, light, obj_rgb, bg_rgb, image_size: int, faces_per_pixel=1,
                   cull_backfaces=False, perspective_correct=True, fov=60.0, znear=1.0, z_clip: Optional[float] = None,
-                  fragments=False, _extra_flags=0):
-    """images (B*M,3,H,W) [+ dict of fragments].  HardPhong + hard blend, blur_radius 0."""
-    k00, k11 = fov_projection_scale(fov, znear)
+                  fragments=False, verts: Optional[torch.Tensor] = None, _extra_flags=0):
+    """images (B*M,3,H,W) [+ dict of fragments].  HardPhong + hard blend, blur_radius 0.
+    `verts`: pass the packed (Vtot,3) vertex tensor the geometry was built from to get gradients w.r.t. it."""
+    H_, W_ = _hw(image_size)
+    k00, k11 = fov_projection_scale(fov, znear, aspect=1.0)
     if z_clip is None:
         z_clip = znear / 2 if perspective_correct else -1.0   # [upstream] MeshRasterizer.forward
     flags = (L.PERSPECTIVE_CORRECT if perspective_correct else 0) | (L.CULL_BACKFACES if cull_backfaces else 0) | _extra_flags
-    out = _MeshRender.apply(R, T, Cc, geom, M, light, obj_rgb, bg_rgb, k00, k11, float(z_clip), image_size, image_size,
+    H, W = _hw(image_size)
+    out = _MeshRender.apply(R, T, Cc, verts, geom, M, light, obj_rgb, bg_rgb, k00, k11, float(z_clip), H, W,
                             int(faces_per_pixel), flags, bool(fragments))
     images, p2f, counters = out[0], out[1], out[2]
     frag = {"pix_to_face": p2f, "counters": counters}
@@ -415,7 +454,8 @@ def render_points(points, rgb, M: int, R, T, inv_dist, radius: float, bg_rgb, im
     if compositor not in ("norm", "alpha"):
         raise ValueError("compositor must be 'norm' or 'alpha'")
     flags = L.COMPOSITE_ALPHA if compositor == "alpha" else 0
-    out = _PointsRender.apply(R, T, inv_dist, points, rgb, M, radius, bg_rgb, image_size, image_size,
+    H, W = _hw(image_size)
+    out = _PointsRender.apply(R, T, inv_dist, points, rgb, M, radius, bg_rgb, H, W,
                               int(points_per_pixel), flags, bool(fragments))
     frag = {"idx": out[1]}
     if fragments:

@@ -121,7 +121,7 @@ class MVRenderer(nn.Module):
             light = C.detach() if lights is None else _device_vec(lights, device)
             return ops.render_meshes(geom, self.nb_views, R, T, C, light, obj, bg, self.image_size,
                                      faces_per_pixel=self.faces_per_pixel, cull_backfaces=self.cull_backfaces,
-                                     perspective_correct=self.perspective_correct)
+                                     perspective_correct=self.perspective_correct, verts=getattr(geom, "grad_verts", None))
 
         (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
         self.last_fragments = frag
@@ -166,6 +166,8 @@ class MVRenderer(nn.Module):
             color_t = color_t.reshape(len(verts), -1, 3)
             vert_rgb = torch.cat([color_t[b, : verts[b].shape[0]] for b in range(len(verts))], 0)
         geom = ops.PackedMeshes(verts, faces, device, vert_rgb=vert_rgb)
+        if any(v.requires_grad for v in verts):      # vertex gradients: keep the autograd history of the packing
+            geom.grad_verts = torch.cat([v.to(device=device, dtype=torch.float32) for v in verts], 0)
         if self.cache_geometry:
             self._geom_cache = (meshes, geom)
         return geom
