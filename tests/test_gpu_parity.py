@@ -537,3 +537,14 @@ def test_mesh_vertex_gradients(oracle, cuda_device):
     im2, _ = r([Meshes([v2], [f])], None, *(t.to(dev) for t in views))
     im2.sum().backward()
     assert v2.grad is not None and v2.grad.abs().max() > 0
+
+
+def test_training_step_example_runs(cuda_device):
+    """BASELINE config 4 in miniature: selector -> renderer -> MVCNN -> loss.backward() reaches the selector."""
+    import subprocess, sys as _sys
+    from conftest import ROOT
+    out = subprocess.run([_sys.executable, os.path.join(ROOT, "examples", "train_step.py"), "--batch", "2", "--views", "2",
+                          "--image-size", "64", "--faces", "500", "--steps", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "views/s end to end" in out.stdout and "|grad| into the view selector" in out.stdout
+    assert float(out.stdout.strip().split()[-1]) > 0
