@@ -48,6 +48,9 @@ def source(rep, top=22):
         print('\n## %s: %d warp-inst, %d samples' % (fn, tot, tots))
         for k, v in sorted(items, key=lambda kv: -kv[1][1])[:top]:
             print('  %5.1f%% smp %5.1f%% inst thr/inst %4.1f  %s:%d  %s' % (100 * v[1] / tots, 100 * v[0] / tot, v[2] / max(v[0], 1), k[1], k[2], k[3]))
+        print('  -- by executed instructions --')
+        for k, v in sorted(items, key=lambda kv: -kv[1][0])[:top]:
+            print('  %5.1f%% inst %5.1f%% smp thr/inst %4.1f  %s:%d  %s' % (100 * v[0] / tot, 100 * v[1] / tots, v[2] / max(v[0], 1), k[1], k[2], k[3]))
 
 
 if __name__ == '__main__':
