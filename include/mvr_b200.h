@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MVR_ABI_VERSION 1
+#define MVR_ABI_VERSION 2
 
 /* flags */
 #define MVR_PERSPECTIVE_CORRECT 1  /* [upstream] RasterizationSettings.perspective_correct (FoV persp.: True) */
@@ -94,23 +94,25 @@ int mvr_mesh_prepare(const float* verts, const void* faces, const int* vert_off,
 int mvr_mesh_get_normals(const void* geometry, int64_t total_verts, int64_t total_faces,
                          float* normals, void* stream);
 
-size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K);
+/* scratch for one forward or backward call: projected vertices of every view (16 B * M * total_verts), the
+ * pixel-centre table, and the 64-bit key plane(s) / backward partial sums */
+size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K, int64_t total_verts);
 /* MeshRenderer(MeshRasterizer, HardPhongShader)(meshes.extend(M), cameras, lights)
  * (renderer.py:89-113; [upstream] _C.rasterize_meshes + interp_face_attrs + phong_shading +
  * hard_rgb_blend).  blur_radius = 0.
  *   Cc (n,3) camera centres; light (1,3) if light_stride == 0 else (n,3) with stride 3;
  *   obj_rgb (3) uniform colour (ignored when the geometry holds per-vertex colours); bg_rgb (3);
  *   k00,k11: FoV projection scale (1/tan(fov/2)); z_clip < 0 disables the near-plane cull;
- *   K = faces_per_pixel.
+ *   K = faces_per_pixel; max_verts / max_faces = largest per-object counts (grid sizing).
  * outputs: images (n,3,H,W); pix_to_face (n,H,W,K) view-local face ids, -1 empty;
  *          optional zbuf (n,H,W,K), bary (n,H,W,K,3), dists (n,H,W,K) (NULL to skip);
  *          counters: device int64[MVR_NUM_COUNTERS] or NULL. */
 int mvr_mesh_forward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
-                     int64_t total_verts, int64_t total_faces, int max_faces, const float* R,
-                     const float* T, const float* Cc, const float* light, int light_stride,
-                     const float* obj_rgb, const float* bg_rgb, float k00, float k11, float z_clip,
-                     int H, int W, int K, int flags, float* images, int* pix_to_face, float* zbuf,
-                     float* bary, float* dists, int64_t* counters, void* workspace,
+                     int64_t total_verts, int64_t total_faces, int max_verts, int max_faces,
+                     const float* R, const float* T, const float* Cc, const float* light,
+                     int light_stride, const float* obj_rgb, const float* bg_rgb, float k00, float k11,
+                     float z_clip, int H, int W, int K, int flags, float* images, int* pix_to_face,
+                     float* zbuf, float* bary, float* dists, int64_t* counters, void* workspace,
                      size_t workspace_bytes, void* stream);
 /* backward of the above w.r.t. the cameras ([upstream] _C.rasterize_meshes_backward + autograd
  * of shading/projection): grad_images (n,3,H,W) -> gR (n,3,3), gT (n,3), gC (n,3);
@@ -118,32 +120,39 @@ int mvr_mesh_forward(const void* geometry, const int* vert_off, const int* face_
  * (Vtot,3) (gradient w.r.t. the per-vertex unit normals), both ACCUMULATED with atomics
  * (caller zero-fills). */
 int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
-                      int64_t total_verts, int64_t total_faces, const float* R, const float* T,
-                      const float* Cc, const float* light, int light_stride, const float* obj_rgb,
-                      float k00, float k11, int H, int W, int K, int flags, const int* pix_to_face,
-                      const float* grad_images, float* gR, float* gT, float* gC, float* grad_verts,
-                      float* grad_normals, void* workspace, size_t workspace_bytes, void* stream);
+                      int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
+                      const float* T, const float* Cc, const float* light, int light_stride,
+                      const float* obj_rgb, float k00, float k11, int H, int W, int K, int flags,
+                      const int* pix_to_face, const float* grad_images, float* gR, float* gT, float* gC,
+                      float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 /* -- point clouds --------------------------------------------------------------------------- */
 size_t mvr_points_workspace_bytes(int B, int M, int H, int W, int K);
+/* number of uint32 words of the optional hit mask: (n, H, ceil(W/32)), bit x%32 of word x/32 = pixel (y, x) is
+ * covered by at least one point */
+size_t mvr_points_hit_mask_words(int B, int M, int H, int W);
 /* PointsRenderer(PointsRasterizer, compositor)(Pointclouds.extend(M).scale_(1/dist))
  * (renderer.py:119-150; [upstream] _C.rasterize_points + accum_weightedsumnorm /
  * accum_alphacomposite + background).  points (B,Np,3); rgb (3) or (B*Np,3) [MVR_RGB_PER_ELEMENT];
  * inv_dist (n) = 1/dist; radius in NDC; K = points_per_pixel.
  * outputs: images (n,3,H,W); idx (n,H,W,K) cloud-local point ids (-1 empty); optional zbuf,
- * dists2 (n,H,W,K). */
+ * dists2 (n,H,W,K); optional hit_mask (mvr_points_hit_mask_words words), which lets the backward pass skip
+ * the ~90 % background pixels without reading idx. */
 int mvr_points_forward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
                        const float* T, const float* inv_dist, double radius, const float* bg_rgb,
                        int H, int W, int K, int flags, float* images, int* idx, float* zbuf,
-                       float* dists2, void* workspace, size_t workspace_bytes, void* stream);
+                       float* dists2, uint32_t* hit_mask, void* workspace, size_t workspace_bytes,
+                       void* stream);
 /* backward ([upstream] accum_*_backward + _C.rasterize_points_backward + autograd of the
  * projection): grad_images -> gR (n,3,3), gT (n,3), g_inv_dist (n); optional grad_points
- * (B,Np,3) and grad_rgb ((3) or (B*Np,3)) ACCUMULATED with atomics (caller zero-fills). */
+ * (B,Np,3) and grad_rgb ((3) or (B*Np,3)) ACCUMULATED with atomics (caller zero-fills).
+ * hit_mask: the forward's mask or NULL (then idx[..., 0] >= 0 is read for every pixel). */
 int mvr_points_backward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
                         const float* T, const float* inv_dist, double radius, int H, int W, int K,
-                        int flags, const int* idx, const float* grad_images, float* gR, float* gT,
-                        float* g_inv_dist, float* grad_points, float* grad_rgb, void* workspace,
-                        size_t workspace_bytes, void* stream);
+                        int flags, const int* idx, const uint32_t* hit_mask, const float* grad_images,
+                        float* gR, float* gT, float* g_inv_dist, float* grad_points, float* grad_rgb,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

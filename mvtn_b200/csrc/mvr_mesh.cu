@@ -2,6 +2,10 @@
 //
 //   prepare : pack verts/normals/colours to float4 and faces to int4; area-weighted vertex normals
 //             ([upstream] Meshes._compute_vertex_normals) once per OBJECT, not per view.
+//   project : mesh_project_kernel -- every vertex of every view is projected exactly ONCE (world -> view -> NDC,
+//             IEEE order) into a float4 (x_ndc, y_ndc, z_view) plane that stays L2-resident (30 MB at C2); the
+//             scatter, shade and backward kernels gather it instead of re-projecting three vertices per
+//             face / pixel.  The same launch writes the table of exact pixel-centre NDC coordinates.
 //   scatter : mesh_scatter_kernel -- each face of each view is set up exactly ONCE (project, cull, exact pixel
 //             bbox) by the CTA that owns its 1024-face chunk.  No bins: the work is flattened inside the CTA
 //             through shared-memory queues so that every phase runs on full warps --
@@ -18,6 +22,8 @@
 //   backward: mesh_backward_kernel -- per pixel recompute (no fragment traffic), chain
 //             d image -> Phong -> barycentrics -> NDC verts -> view verts -> (dR, dT, dC), block-reduced to
 //             one partial per CTA and summed in fixed order (deterministic, no float atomics).
+#include <cstdlib>
+
 #include "mvr_common.cuh"
 
 namespace mvr {
@@ -48,19 +54,24 @@ static GeomLayout geom_layout(int64_t tv, int64_t tf) {
 }
 
 struct WsLayout {
-  size_t keys, prev, total;
+  size_t pv, tab, keys, prev, partials, total;
   int bwd_ctas_per_view;
 };
-static WsLayout ws_layout(int B, int M, int H, int W, int K) {
+// [pv | tab] are shared by the forward and the backward call (each re-projects: the workspace is scratch and may
+// have been reused in between); the forward adds the key planes, the backward its per-CTA partial sums.
+static WsLayout ws_layout(int B, int M, int H, int W, int K, int64_t total_verts) {
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   WsLayout w;
   const size_t N = (size_t)B * M, HW = (size_t)H * W;
   size_t o = 0;
+  w.pv = o; o = al(o + (size_t)M * (size_t)total_verts * 16);
+  w.tab = o; o = al(o + ((size_t)W + H) * sizeof(float));
+  const size_t common = o;
   w.keys = o; o = al(o + N * HW * 8);
   w.prev = o; if (K > 1) o = al(o + N * HW * 8);
   w.bwd_ctas_per_view = ((W + 31) / 32) * ((H + 31) / 32);      // 32x32-pixel tiles
-  // the backward pass reuses the front of the workspace for its per-CTA partial sums
-  const size_t bwd = al(N * w.bwd_ctas_per_view * 16 * sizeof(float));
+  w.partials = common;
+  const size_t bwd = al(common + N * w.bwd_ctas_per_view * NWARPS * 16 * sizeof(float));
   w.total = o > bwd ? o : bwd;
   return w;
 }
@@ -119,7 +130,7 @@ __global__ void geom_get_normals_kernel(const float4* __restrict__ normals4, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared device code: face setup and the per-(face, pixel) test
+// shared device code: projection, face setup and the per-(face, pixel) test
 // ------------------------------------------------------------------------------------------------
 struct MeshParams {
   const float4* verts4; const float4* normals4; const float4* rgb4; const int4* faces4;
@@ -129,6 +140,8 @@ struct MeshParams {
   float k00, k11, z_clip;
   int B, M, H, W, K, flags;
   int chunks_per_view, layer, item_cap, wcap;
+  float4* pv;            // (x_ndc, y_ndc, z_view, 0) of vertex v of view (b, m) at M*vert_off[b] + m*V_b + v
+  float* tab;            // pixel-centre NDC coordinates: xf[W] then yf[H]
   unsigned long long* keys; unsigned long long* prev;
   float* images; int* pix_to_face; float* zbuf; float* bary; float* dists;
   long long* counters;
@@ -147,11 +160,33 @@ __device__ __forceinline__ void project_vertex(const Camera& cam, const float4 v
   zv = pz;
 }
 
-__device__ __forceinline__ Face load_face(const MeshParams& p, const Camera& cam, int voff, const int4 fi) {
+// grid: x = 256-vertex chunks of the largest object, y = view m, z = object b.  Block (0,0,0) also fills the
+// pixel-centre table ([upstream] PixToNonSquareNdc evaluated once per row / column instead of once per pixel).
+__global__ void __launch_bounds__(MVR_THREADS) mesh_project_kernel(const float4* __restrict__ verts4,
+                                                                    const int* __restrict__ vert_off,
+                                                                    const float* __restrict__ R, const float* __restrict__ T,
+                                                                    int M, int H, int W, float k00, float k11,
+                                                                    float4* __restrict__ pv, float* __restrict__ tab) {
+  const int b = blockIdx.z, m = blockIdx.y, n = b * M + m;
+  if (blockIdx.x == 0 && m == 0 && b == 0) {
+    for (int i = threadIdx.x; i < W; i += MVR_THREADS) tab[i] = pix_to_ndc(W - 1 - i, W, H);
+    for (int i = threadIdx.x; i < H; i += MVR_THREADS) tab[W + i] = pix_to_ndc(H - 1 - i, H, W);
+  }
+  const int voff = vert_off[b], V = vert_off[b + 1] - voff;
+  const int v = blockIdx.x * MVR_THREADS + threadIdx.x;
+  if (v >= V) return;
+  const Camera cam = load_camera(R, T, n);
+  float xn, yn, zv;
+  project_vertex(cam, __ldg(verts4 + voff + v), k00, k11, xn, yn, zv);
+  pv[(size_t)M * voff + (size_t)m * V + v] = make_float4(xn, yn, zv, 0.f);
+}
+
+__device__ __forceinline__ Face gather_face(const float4* __restrict__ pvn, const int4 fi) {
+  const float4 a = __ldg(pvn + fi.x), b = __ldg(pvn + fi.y), c = __ldg(pvn + fi.z);
   Face f;
-  project_vertex(cam, __ldg(p.verts4 + voff + fi.x), p.k00, p.k11, f.x0, f.y0, f.z0);
-  project_vertex(cam, __ldg(p.verts4 + voff + fi.y), p.k00, p.k11, f.x1, f.y1, f.z1);
-  project_vertex(cam, __ldg(p.verts4 + voff + fi.z), p.k00, p.k11, f.x2, f.y2, f.z2);
+  f.x0 = a.x; f.y0 = a.y; f.z0 = a.z;
+  f.x1 = b.x; f.y1 = b.y; f.z1 = b.z;
+  f.x2 = c.x; f.y2 = c.y; f.z2 = c.z;
   return f;
 }
 
@@ -248,9 +283,9 @@ __device__ __forceinline__ float point_line_dist2(float px, float py, float ax, 
 // scatter pass
 // ------------------------------------------------------------------------------------------------
 // exact test of one (face, pixel) candidate and the keyed min on the global key plane
-__device__ __forceinline__ void resolve_pixel(const MeshParams& p, const Face& fc, const FaceEdges& fe, int fid,
-                                              unsigned int zmin_bits, bool persp, float xf, float yf,
-                                              unsigned long long* key_ptr, const unsigned long long* prev_ptr) {
+__device__ __forceinline__ void resolve_pixel(const Face& fc, const FaceEdges& fe, int fid, unsigned int zmin_bits,
+                                              bool persp, float xf, float yf, unsigned long long* key_ptr,
+                                              const unsigned long long* prev_ptr) {
   const unsigned long long cur = __ldcg(key_ptr);
   // early depth reject: pz is a convex combination of the vertex depths up to a few ulp (perspective-corrected
   // barycentrics sum to 1 unless their 1e-8 denominator clamp acts, which needs z ~ 1e-4; plain barycentrics sum
@@ -265,7 +300,8 @@ __device__ __forceinline__ void resolve_pixel(const MeshParams& p, const Face& f
   atomicMin(key_ptr, key);      // result unused: RED.MIN.64 resolved in L2
 }
 
-__global__ void __launch_bounds__(MVR_THREADS, 4) mesh_scatter_kernel(const MeshParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const MeshParams p) {
   __shared__ float s_rec[REC_WORDS][MVR_THREADS];     // SoA face records of the current round
   __shared__ int s_items[ITEM_CAP];                    // slot | start << 8 | count << 18
   __shared__ int s_cand[NWARPS][WCAP];                 // slot | x << 8 | y << 20
@@ -273,23 +309,22 @@ __global__ void __launch_bounds__(MVR_THREADS, 4) mesh_scatter_kernel(const Mesh
   __shared__ int s_cnt[2];                             // [0] items, [1] big faces
   __shared__ int s_wcnt[NWARPS];
   extern __shared__ float s_tab[];                     // pixel centres: xf[W], yf[H]
-  float* s_xf = s_tab;
-  float* s_yf = s_tab + p.W;
+  const float* s_xf = s_tab;
+  const float* s_yf = s_tab + p.W;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.x / p.chunks_per_view, chunk = blockIdx.x % p.chunks_per_view;
-  const int b = n / p.M;
+  const int b = n / p.M, m = n - b * p.M;
   const int f0 = p.face_off[b], F = p.face_off[b + 1] - f0;
   const int fbeg = chunk * FACES_PER_CTA, fend = min(F, fbeg + FACES_PER_CTA);
   if (fbeg >= fend) return;
-  const int voff = p.vert_off[b];
+  const int voff = p.vert_off[b], V = p.vert_off[b + 1] - voff;
+  const float4* pvn = p.pv + (size_t)p.M * voff + (size_t)m * V;     // this view's projected vertices
   const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
-  const Camera cam = load_camera(p.R, p.T, n);
   unsigned long long* keys = p.keys + (size_t)n * p.H * p.W;
   const unsigned long long* prev = p.layer > 0 ? p.prev + (size_t)n * p.H * p.W : nullptr;
 
-  for (int i = tid; i < p.W; i += MVR_THREADS) s_xf[i] = pix_to_ndc(p.W - 1 - i, p.W, p.H);
-  for (int i = tid; i < p.H; i += MVR_THREADS) s_yf[i] = pix_to_ndc(p.H - 1 - i, p.H, p.W);
+  for (int i = tid; i < p.W + p.H; i += MVR_THREADS) s_tab[i] = __ldg(p.tab + i);
   if (tid < 2) s_cnt[tid] = 0;
   __syncthreads();
 
@@ -298,7 +333,7 @@ __global__ void __launch_bounds__(MVR_THREADS, 4) mesh_scatter_kernel(const Mesh
     // ---------------- phase A: setup, one thread per face ----------------
     const int fid = rbeg + tid;
     if (fid < fend) {
-      const Face fc = load_face(p, cam, voff, __ldg(p.faces4 + f0 + fid));
+      const Face fc = gather_face(pvn, __ldg(p.faces4 + f0 + fid));
       if (p.z_clip >= 0.f && p.layer == 0) {   // every face crossing z_clip is counted, visible or not (as the oracle does)
         const int nb = (fc.z0 < p.z_clip) + (fc.z1 < p.z_clip) + (fc.z2 < p.z_clip);
         n_straddle += (nb == 1 || nb == 2);
@@ -333,9 +368,11 @@ __global__ void __launch_bounds__(MVR_THREADS, 4) mesh_scatter_kernel(const Mesh
     const int n_items = min(s_cnt[0], p.item_cap);
     const int n_bigf = s_cnt[1];
     int wcnt = 0;                                // warp-uniform: candidates queued by this warp
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    int* const my_cand = s_cand[warp];
     for (int j0 = warp * 32; j0 < n_items; j0 += MVR_THREADS) {      // warp-uniform trip count
       const int j = j0 + lane;
-      int slot = 0, count = 0, row = 0, col = 0, xl = 0, yl = 0, bw = 1;
+      int slot = 0, count = 0, xl = 0, bw = 1, xi = 0, yi = 0;
       float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f, cx = 0.f, cy = 0.f;
       if (j < n_items) {
         const int it = s_items[j];
@@ -345,39 +382,47 @@ __global__ void __launch_bounds__(MVR_THREADS, 4) mesh_scatter_kernel(const Mesh
         bx = s_rec[3][slot]; by = s_rec[4][slot];
         cx = s_rec[6][slot]; cy = s_rec[7][slot];
         const int rxy = __float_as_int(s_rec[10][slot]);
-        xl = rxy & 0xffff; yl = rxy >> 16;
+        xl = rxy & 0xffff;
         bw = __float_as_int(s_rec[11][slot]) & 0xffff;
-        row = (int)__fdividef((float)start + 0.5f, (float)bw);     // small integers: exact
-        col = start - row * bw;
+        const int row = (int)__fdividef((float)start + 0.5f, (float)bw);     // small integers: exact
+        xi = xl + (start - row * bw);
+        yi = p.W + (rxy >> 16) + row;                                        // index of yf in s_tab
       }
-      const float A0 = cy - by, B0 = cx - bx, A1 = ay - cy, B1 = ax - cx, A2 = by - ay, B2 = bx - ax;
+      // edge coefficients with the sign of the area folded in (negation is exact and commutes with rounding), so
+      // the filter below is "all three > 0" for either winding: bit-for-bit the sign test of raster_test
+      float A0 = cy - by, B0 = cx - bx, A1 = ay - cy, B1 = ax - cx, A2 = by - ay, B2 = bx - ax;
       const float area_p = ((cx - ax) * A2 - (cy - ay) * B2) + MVR_K_EPS;
+      if (!(area_p > 0.f)) { A0 = -A0; B0 = -B0; A1 = -A1; B1 = -B1; A2 = -A2; B2 = -B2; }
+      const int x_end = xl + bw;
+      const int slot_m = slot - (p.W << 20);
       const int maxc = __reduce_max_sync(0xffffffffu, count);
       for (int c = 0; c < maxc; ++c) {
-        const int xx = xl + col, yy = yl + row;
-        bool pass = c < count;
-        if (pass) {
-          const float xf = s_xf[xx], yf = s_yf[yy];
+        const int cxi = xi, cyi = yi;
+        bool pass = false;
+        if (c < count) {
+          const float xf = s_tab[xi], yf = s_tab[yi];
           const float e0 = (xf - bx) * A0 - (yf - by) * B0;
           const float e1 = (xf - cx) * A1 - (yf - cy) * B1;
           const float e2 = (xf - ax) * A2 - (yf - ay) * B2;
-          pass = area_p > 0.f ? (e0 > 0.f && e1 > 0.f && e2 > 0.f) : (e0 < 0.f && e1 < 0.f && e2 < 0.f);
-          if (++col == bw) { col = 0; ++row; }
+          pass = e0 > 0.f && e1 > 0.f && e2 > 0.f;
+          if (++xi == x_end) { xi = xl; ++yi; }
         }
-        const unsigned int m = __ballot_sync(0xffffffffu, pass);
+        const unsigned int mk = __ballot_sync(0xffffffffu, pass);
+        if (mk == 0u) continue;
         if (pass) {
-          const int at = wcnt + __popc(m & ((1u << lane) - 1u));
+          const int at = wcnt + __popc(mk & lt_mask);
           if (at < p.wcap) {
-            s_cand[warp][at] = slot | (xx << 8) | (yy << 20);
+            my_cand[at] = slot_m + (cxi << 8) + (cyi << 20);      // slot | x << 8 | y << 20 (slot_m = slot - (W << 20))
           } else {                                                  // queue full: resolve in place
+            const int xx = cxi, yy = cyi - p.W;
             Face fc;
             fc.x0 = ax; fc.y0 = ay; fc.z0 = s_rec[2][slot]; fc.x1 = bx; fc.y1 = by; fc.z1 = s_rec[5][slot];
             fc.x2 = cx; fc.y2 = cy; fc.z2 = s_rec[8][slot];
-            resolve_pixel(p, fc, face_edges(fc), __float_as_int(s_rec[9][slot]), 0u, persp, s_xf[xx], s_yf[yy],
+            resolve_pixel(fc, face_edges(fc), __float_as_int(s_rec[9][slot]), 0u, persp, s_xf[xx], s_yf[yy],
                           keys + (size_t)yy * p.W + xx, prev ? prev + (size_t)yy * p.W + xx : nullptr);
           }
         }
-        wcnt += __popc(m);
+        wcnt += __popc(mk);
       }
     }
     if (lane == 0) s_wcnt[warp] = min(wcnt, p.wcap);
@@ -401,7 +446,7 @@ __global__ void __launch_bounds__(MVR_THREADS, 4) mesh_scatter_kernel(const Mesh
         fc.x2 = s_rec[6][slot]; fc.y2 = s_rec[7][slot]; fc.z2 = s_rec[8][slot];
         const float zmin = fminf(fminf(fc.z0, fc.z1), fc.z2);
         const unsigned int zmin_bits = (persp && zmin > 1e-3f) ? __float_as_uint(zmin * 0.999999f) : 0u;
-        resolve_pixel(p, fc, face_edges(fc), __float_as_int(s_rec[9][slot]), zmin_bits, persp, s_xf[xx], s_yf[yy],
+        resolve_pixel(fc, face_edges(fc), __float_as_int(s_rec[9][slot]), zmin_bits, persp, s_xf[xx], s_yf[yy],
                       keys + (size_t)yy * p.W + xx, prev ? prev + (size_t)yy * p.W + xx : nullptr);
       }
     }
@@ -421,7 +466,7 @@ __global__ void __launch_bounds__(MVR_THREADS, 4) mesh_scatter_kernel(const Mesh
       for (int y = warp; y < bh; y += NWARPS)
         for (int x = lane; x < bw; x += 32) {
           const int xx = xl + x, yy = yl + y;
-          resolve_pixel(p, fc, fe, bfid, zmin_bits, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
+          resolve_pixel(fc, fe, bfid, zmin_bits, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
                         prev ? prev + (size_t)yy * p.W + xx : nullptr);
         }
     }
@@ -441,10 +486,11 @@ __device__ __forceinline__ float3 interp(const float b[3], const float4 a0, cons
   return make_float3((b[0] * a0.x + b[1] * a1.x) + b[2] * a2.x, (b[0] * a0.y + b[1] * a1.y) + b[2] * a2.y,
                      (b[0] * a0.z + b[1] * a1.z) + b[2] * a2.z);
 }
+// 1 / max(|v|, eps) for F.normalize(v, eps).  Shading is tolerance-compared (1e-5 on images), so the reciprocal
+// square root comes from the SFU (<= 2 ulp) instead of an IEEE sqrt followed by an IEEE division.
 __device__ __forceinline__ float inv_norm_clamped(float x, float y, float z, float eps) {
   const float n2 = fmaf(x, x, fmaf(y, y, z * z));
-  const float n = sqrtf(n2);
-  return 1.0f / fmaxf(n, eps);
+  return n2 > eps * eps ? rsqrtf(n2) : __frcp_rn(eps);
 }
 __device__ __forceinline__ float pow64(float a) {
   a = a * a; a = a * a; a = a * a; a = a * a; a = a * a; a = a * a;
@@ -455,6 +501,17 @@ struct ShadeCtx {
   float lx, ly, lz;   // normalised light direction
   float cx, cy, cz;   // camera centre
 };
+
+__device__ __forceinline__ ShadeCtx load_shade_ctx(const float* __restrict__ light, int light_stride,
+                                                   const float* __restrict__ Cc, int n) {
+  ShadeCtx sc;
+  const float* Lp = light + (size_t)light_stride * n;
+  const float lx = __ldg(Lp), ly = __ldg(Lp + 1), lz = __ldg(Lp + 2);
+  const float il = inv_norm_clamped(lx, ly, lz, 1e-6f);
+  sc.lx = lx * il; sc.ly = ly * il; sc.lz = lz * il;
+  sc.cx = __ldg(Cc + 3 * (size_t)n); sc.cy = __ldg(Cc + 3 * (size_t)n + 1); sc.cz = __ldg(Cc + 3 * (size_t)n + 2);
+  return sc;
+}
 
 __device__ __forceinline__ void phong_pixel(const float b[3], const float4 X0, const float4 X1, const float4 X2,
                                             const float4 N0, const float4 N1, const float4 N2, const float4 c0,
@@ -479,10 +536,36 @@ __device__ __forceinline__ void phong_pixel(const float b[3], const float4 X0, c
 // ------------------------------------------------------------------------------------------------
 // shade pass: one thread per pixel
 // ------------------------------------------------------------------------------------------------
-// grid: x = 32x8-pixel tiles of the image, y = view m, z = object b (no per-thread integer divisions)
+// tile index -> (row, column) of tiles without an integer division (small integers: the float quotient is exact)
+__device__ __forceinline__ void tile_rc(int t, int tiles_x, int& ty, int& tx) {
+  ty = (int)__fdividef((float)t + 0.5f, (float)tiles_x);
+  tx = t - ty * tiles_x;
+}
+
+// Barycentrics of a pixel KNOWN to be inside its face, for shading only (images are compared at 1e-5): the edge
+// functions come from the same projected vertices as the scatter pass, so they are bit-identical to the rasterizer's;
+// only the six IEEE divisions are replaced by two SFU reciprocals (a few ulp on b, ~1e-7 on the colour).  The exact
+// sequence (raster_test) is used whenever the caller asks for the barycentrics themselves.
+__device__ __forceinline__ void shading_barycentrics(const Face& f, const FaceEdges& e, bool persp, float xf, float yf,
+                                                     float b[3]) {
+  const float e0 = (xf - f.x1) * e.A0 - (yf - f.y1) * e.B0;
+  const float e1 = (xf - f.x2) * e.A1 - (yf - f.y2) * e.B1;
+  const float e2 = (xf - f.x0) * e.A2 - (yf - f.y0) * e.B2;
+  const float ia = __fdividef(1.0f, e.area_p);
+  b[0] = e0 * ia; b[1] = e1 * ia; b[2] = e2 * ia;
+  if (persp) {
+    const float t0 = b[0] * f.z1 * f.z2, t1 = b[1] * f.z0 * f.z2, t2 = b[2] * f.z0 * f.z1;
+    const float id = __fdividef(1.0f, fmaxf(t0 + t1 + t2, MVR_K_EPS));
+    b[0] = t0 * id; b[1] = t1 * id; b[2] = t2 * id;
+  }
+}
+
+// grid: x = 32x8-pixel tiles of the image, y = view m, z = object b.  EXACT: the caller wants zbuf / bary / dists.
+template <bool EXACT>
 __global__ void __launch_bounds__(MVR_THREADS) mesh_shade_kernel(const MeshParams p, int tiles_x) {
-  const int b = blockIdx.z, n = b * p.M + blockIdx.y;
-  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int b = blockIdx.z, m = blockIdx.y, n = b * p.M + m;
+  int ty, tx;
+  tile_rc(blockIdx.x, tiles_x, ty, tx);
   const int xi = tx * 32 + (threadIdx.x & 31), yi = ty * 8 + (threadIdx.x >> 5);
   const int HW = p.H * p.W;
   if (xi >= p.W || yi >= p.H) return;
@@ -499,47 +582,47 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_shade_kernel(const MeshParam
   float out[3];
   if (k == 0) { out[0] = __ldg(p.bg_rgb); out[1] = __ldg(p.bg_rgb + 1); out[2] = __ldg(p.bg_rgb + 2); }
   if (key != MVR_EMPTY_KEY) {
-    // The barycentrics are recomputed with the SAME exact operation sequence as the scatter: for sliver faces a
-    // reciprocal-multiply shortcut moves them by far more than the 1e-5 image tolerance (error ~ ulp * |xy| / area).
-    const int f0 = p.face_off[b], voff = p.vert_off[b];
+    const int f0 = p.face_off[b], voff = p.vert_off[b], V = p.vert_off[b + 1] - voff;
     const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
-    const Camera cam = load_camera(p.R, p.T, n);
     fid = (int)(unsigned int)(key & 0xffffffffull);
     const int4 fi = __ldg(p.faces4 + f0 + fid);
-    const float4 X0 = __ldg(p.verts4 + voff + fi.x), X1 = __ldg(p.verts4 + voff + fi.y), X2 = __ldg(p.verts4 + voff + fi.z);
-    const float xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H), yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
-    Face fc;
-    project_vertex(cam, X0, p.k00, p.k11, fc.x0, fc.y0, fc.z0);
-    project_vertex(cam, X1, p.k00, p.k11, fc.x1, fc.y1, fc.z1);
-    project_vertex(cam, X2, p.k00, p.k11, fc.x2, fc.y2, fc.z2);
-    const FaceEdges fe = face_edges(fc);
-    raster_test(fc, fe, persp, xf, yf, w, bb, pz);
-    pz = __uint_as_float((unsigned int)(key >> 32));
-    if (p.dists) {
-      const float e01 = point_line_dist2(xf, yf, fc.x0, fc.y0, fc.x1, fc.y1);
-      const float e02 = point_line_dist2(xf, yf, fc.x0, fc.y0, fc.x2, fc.y2);
-      const float e12 = point_line_dist2(xf, yf, fc.x1, fc.y1, fc.x2, fc.y2);
-      dd = -fminf(fminf(e01, e02), e12);
-    }
+    // every gather of this pixel is issued before the first use (one round trip to L2 instead of three)
+    const Face fc = gather_face(p.pv + (size_t)p.M * voff + (size_t)m * V, fi);
+    float4 X0, X1, X2, N0, N1, N2, c0, c1, c2;
     if (k == 0) {
-      ShadeCtx sc;
-      const float* Lp = p.light + (size_t)p.light_stride * n;
-      const float lx = __ldg(Lp), ly = __ldg(Lp + 1), lz = __ldg(Lp + 2);
-      const float il = inv_norm_clamped(lx, ly, lz, 1e-6f);
-      sc.lx = lx * il; sc.ly = ly * il; sc.lz = lz * il;
-      sc.cx = __ldg(p.Cc + 3 * (size_t)n); sc.cy = __ldg(p.Cc + 3 * (size_t)n + 1); sc.cz = __ldg(p.Cc + 3 * (size_t)n + 2);
-      const float4 N0 = __ldg(p.normals4 + voff + fi.x), N1 = __ldg(p.normals4 + voff + fi.y), N2 = __ldg(p.normals4 + voff + fi.z);
-      float4 c0, c1, c2;
+      X0 = __ldg(p.verts4 + voff + fi.x); X1 = __ldg(p.verts4 + voff + fi.y); X2 = __ldg(p.verts4 + voff + fi.z);
+      N0 = __ldg(p.normals4 + voff + fi.x); N1 = __ldg(p.normals4 + voff + fi.y); N2 = __ldg(p.normals4 + voff + fi.z);
       if (p.flags & MVR_RGB_PER_ELEMENT) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
       else { c0 = c1 = c2 = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f); }
+    }
+    const float xf = __ldg(p.tab + xi), yf = __ldg(p.tab + p.W + yi);
+    const FaceEdges fe = face_edges(fc);
+    if (EXACT) {
+      // The barycentrics are recomputed with the SAME exact operation sequence as the scatter (from the same
+      // projected vertices), so the fragments returned to the caller are the rasterizer's, bit for bit.
+      raster_test(fc, fe, persp, xf, yf, w, bb, pz);
+      if (p.dists) {
+        const float e01 = point_line_dist2(xf, yf, fc.x0, fc.y0, fc.x1, fc.y1);
+        const float e02 = point_line_dist2(xf, yf, fc.x0, fc.y0, fc.x2, fc.y2);
+        const float e12 = point_line_dist2(xf, yf, fc.x1, fc.y1, fc.x2, fc.y2);
+        dd = -fminf(fminf(e01, e02), e12);
+      }
+    } else {
+      shading_barycentrics(fc, fe, persp, xf, yf, bb);
+    }
+    pz = __uint_as_float((unsigned int)(key >> 32));
+    if (k == 0) {
+      const ShadeCtx sc = load_shade_ctx(p.light, p.light_stride, p.Cc, n);
       phong_pixel(bb, X0, X1, X2, N0, N1, N2, c0, c1, c2, sc, out);
     }
   }
   const size_t po = ((size_t)n * HW + pix) * p.K + k;
   p.pix_to_face[po] = fid;
-  if (p.zbuf) p.zbuf[po] = pz;
-  if (p.dists) p.dists[po] = dd;
-  if (p.bary) { p.bary[3 * po] = bb[0]; p.bary[3 * po + 1] = bb[1]; p.bary[3 * po + 2] = bb[2]; }
+  if (EXACT) {
+    if (p.zbuf) p.zbuf[po] = pz;
+    if (p.dists) p.dists[po] = dd;
+    if (p.bary) { p.bary[3 * po] = bb[0]; p.bary[3 * po + 1] = bb[1]; p.bary[3 * po + 2] = bb[2]; }
+  }
   if (k == 0) {
     const size_t io = (size_t)n * 3 * HW + pix;
     p.images[io] = out[0]; p.images[io + HW] = out[1]; p.images[io + 2 * (size_t)HW] = out[2];
@@ -556,8 +639,9 @@ struct MeshBwdParams {
   const float* obj_rgb;
   float k00, k11;
   int B, M, H, W, K, flags, ctas_per_view, tiles_x;
+  const float4* pv; const float* tab;
   const int* pix_to_face; const float* grad_images;
-  float* partials;       // (N, ctas_per_view, 16)
+  float* partials;       // (N, ctas_per_view, NWARPS, 16)
   float* grad_verts; float* grad_normals;
 };
 
@@ -578,20 +662,19 @@ __device__ __forceinline__ void normalize_bwd3(float vx, float vy, float vz, flo
   }
 }
 
-__global__ void __launch_bounds__(MVR_THREADS, 3) mesh_backward_kernel(const MeshBwdParams p) {
-  __shared__ float s_red[NWARPS * BWD_VALS];
-  __shared__ int s_any;
+template <int MINB>
+__global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const MeshBwdParams p) {
   const int tid = threadIdx.x;
   // grid: x = 32x32-pixel tiles, y = view m, z = object b; thread (lane, warp) owns pixels (x0+lane, y0+warp+8j)
-  const int b = blockIdx.z, n = b * p.M + blockIdx.y, cta = blockIdx.x;
-  const int tyb = cta / p.tiles_x, txb = cta - tyb * p.tiles_x;
+  const int b = blockIdx.z, m = blockIdx.y, n = b * p.M + m, cta = blockIdx.x;
+  int tyb, txb;
+  tile_rc(cta, p.tiles_x, tyb, txb);
   const int xi = txb * 32 + (tid & 31), yi0 = tyb * 32 + (tid >> 5);
   const int HW = p.H * p.W;
-  const int f0 = p.face_off[b], voff = p.vert_off[b];
+  const int f0 = p.face_off[b], voff = p.vert_off[b], V = p.vert_off[b + 1] - voff;
+  const float4* pvn = p.pv + (size_t)p.M * voff + (size_t)m * V;
   const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
   const bool per_vertex_rgb = p.flags & MVR_RGB_PER_ELEMENT;
-  if (tid == 0) s_any = 0;
-  __syncthreads();
   // issue every load of this thread's pixels first (memory-level parallelism), then do the math
   int fids[BWD_PIX_PER_THREAD];
   float gin[BWD_PIX_PER_THREAD][3];
@@ -614,15 +697,8 @@ __global__ void __launch_bounds__(MVR_THREADS, 3) mesh_backward_kernel(const Mes
 #pragma unroll
   for (int i = 0; i < BWD_VALS; ++i) acc[i] = 0.f;
   bool any = false;
-  const Camera cam = load_camera(p.R, p.T, n);
-  ShadeCtx sc;
-  {
-    const float* Lp = p.light + (size_t)p.light_stride * n;
-    const float lx_ = __ldg(Lp), ly_ = __ldg(Lp + 1), lz_ = __ldg(Lp + 2);
-    const float il = inv_norm_clamped(lx_, ly_, lz_, 1e-6f);
-    sc.lx = lx_ * il; sc.ly = ly_ * il; sc.lz = lz_ * il;
-    sc.cx = __ldg(p.Cc + 3 * (size_t)n); sc.cy = __ldg(p.Cc + 3 * (size_t)n + 1); sc.cz = __ldg(p.Cc + 3 * (size_t)n + 2);
-  }
+  const ShadeCtx sc = load_shade_ctx(p.light, p.light_stride, p.Cc, n);
+  const float xf = xi < p.W ? __ldg(p.tab + xi) : 0.f;
   float4 ucol = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!per_vertex_rgb) ucol = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f);
 #pragma unroll 1
@@ -633,23 +709,16 @@ __global__ void __launch_bounds__(MVR_THREADS, 3) mesh_backward_kernel(const Mes
     any = true;
     const int yi = yi0 + 8 * j;
     const int4 fi = __ldg(p.faces4 + f0 + fid);
+    // ---- forward recompute from the projected vertices (exact IEEE projection, done once per view by
+    // mesh_project_kernel: for small faces the barycentrics amplify a 1-ulp change of a vertex by |xy| / area);
+    // everything downstream is well conditioned and uses fast reciprocals ----
+    const Face fc = gather_face(pvn, fi);
     const float4 X0 = __ldg(p.verts4 + voff + fi.x), X1 = __ldg(p.verts4 + voff + fi.y), X2 = __ldg(p.verts4 + voff + fi.z);
     const float4 N0 = __ldg(p.normals4 + voff + fi.x), N1 = __ldg(p.normals4 + voff + fi.y), N2 = __ldg(p.normals4 + voff + fi.z);
     float4 c0 = ucol, c1 = ucol, c2 = ucol;
     if (per_vertex_rgb) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
-    // ---- forward recompute: the projection keeps the exact (IEEE) operation sequence, because for small faces the
-    // barycentrics amplify a 1-ulp change of a vertex by |xy| / area; everything downstream is well conditioned and
-    // uses fast reciprocals ----
-    float pv[3][3];   // view-space vertices
-    world_to_view(cam, X0.x, X0.y, X0.z, pv[0][0], pv[0][1], pv[0][2]);
-    world_to_view(cam, X1.x, X1.y, X1.z, pv[1][0], pv[1][1], pv[1][2]);
-    world_to_view(cam, X2.x, X2.y, X2.z, pv[2][0], pv[2][1], pv[2][2]);
-    Face fc;
-    fc.x0 = (pv[0][0] * p.k00) / pv[0][2]; fc.y0 = (pv[0][1] * p.k11) / pv[0][2]; fc.z0 = pv[0][2];
-    fc.x1 = (pv[1][0] * p.k00) / pv[1][2]; fc.y1 = (pv[1][1] * p.k11) / pv[1][2]; fc.z1 = pv[1][2];
-    fc.x2 = (pv[2][0] * p.k00) / pv[2][2]; fc.y2 = (pv[2][1] * p.k11) / pv[2][2]; fc.z2 = pv[2][2];
     const FaceEdges fe = face_edges(fc);
-    const float xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H), yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
+    const float yf = __ldg(p.tab + p.W + yi);
     const float e0 = (xf - fc.x1) * fe.A0 - (yf - fc.y1) * fe.B0;
     const float e1 = (xf - fc.x2) * fe.A1 - (yf - fc.y2) * fe.B1;
     const float e2 = (xf - fc.x0) * fe.A2 - (yf - fc.y0) * fe.B2;
@@ -728,25 +797,27 @@ __global__ void __launch_bounds__(MVR_THREADS, 3) mesh_backward_kernel(const Mes
     gx0 += garea * (fc.y2 - fc.y1); gy0 += garea * (fc.x1 - fc.x2);
     gx1 += garea * (fc.y0 - fc.y2); gy1 += garea * (fc.x2 - fc.x0);
     gx2 += garea * (fc.y1 - fc.y0); gy2 += garea * (fc.x0 - fc.x1);
-    // ---- projection backward + X R + T backward ----
+    // ---- projection backward + X R + T backward: x_ndc = (px k00) / pz, so px k00 = x_ndc pz ----
     const float gxn[3] = {gx0, gx1, gx2}, gyn[3] = {gy0, gy1, gy2}, gzn[3] = {dz0, dz1, dz2};
+    const float xn[3] = {fc.x0, fc.x1, fc.x2}, yn[3] = {fc.y0, fc.y1, fc.y2}, zv[3] = {fc.z0, fc.z1, fc.z2};
     const float4 Xs[3] = {X0, X1, X2};
     const int vid[3] = {fi.x, fi.y, fi.z};
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const float iz = rcp_fast(pv[i][2]);
+      const float iz = rcp_fast(zv[i]);
       const float gpx = gxn[i] * p.k00 * iz;
       const float gpy = gyn[i] * p.k11 * iz;
-      const float gpz = gzn[i] - (gxn[i] * (pv[i][0] * p.k00) + gyn[i] * (pv[i][1] * p.k11)) * iz * iz;
+      const float gpz = gzn[i] - (gxn[i] * xn[i] + gyn[i] * yn[i]) * iz;
       acc[0] = fmaf(Xs[i].x, gpx, acc[0]); acc[1] = fmaf(Xs[i].x, gpy, acc[1]); acc[2] = fmaf(Xs[i].x, gpz, acc[2]);
       acc[3] = fmaf(Xs[i].y, gpx, acc[3]); acc[4] = fmaf(Xs[i].y, gpy, acc[4]); acc[5] = fmaf(Xs[i].y, gpz, acc[5]);
       acc[6] = fmaf(Xs[i].z, gpx, acc[6]); acc[7] = fmaf(Xs[i].z, gpy, acc[7]); acc[8] = fmaf(Xs[i].z, gpz, acc[8]);
       acc[9] += gpx; acc[10] += gpy; acc[11] += gpz;
       if (p.grad_verts) {
+        const float* r = p.R + 9 * (size_t)n;
         float* o = p.grad_verts + 3 * (size_t)(voff + vid[i]);
-        atomicAdd(o + 0, fmaf(cam.r[0], gpx, fmaf(cam.r[1], gpy, cam.r[2] * gpz)) - bb[i] * gvx);
-        atomicAdd(o + 1, fmaf(cam.r[3], gpx, fmaf(cam.r[4], gpy, cam.r[5] * gpz)) - bb[i] * gvy);
-        atomicAdd(o + 2, fmaf(cam.r[6], gpx, fmaf(cam.r[7], gpy, cam.r[8] * gpz)) - bb[i] * gvz);
+        atomicAdd(o + 0, fmaf(__ldg(r + 0), gpx, fmaf(__ldg(r + 1), gpy, __ldg(r + 2) * gpz)) - bb[i] * gvx);
+        atomicAdd(o + 1, fmaf(__ldg(r + 3), gpx, fmaf(__ldg(r + 4), gpy, __ldg(r + 5) * gpz)) - bb[i] * gvy);
+        atomicAdd(o + 2, fmaf(__ldg(r + 6), gpx, fmaf(__ldg(r + 7), gpy, __ldg(r + 8) * gpz)) - bb[i] * gvz);
       }
       if (p.grad_normals) {
         float* o = p.grad_normals + 3 * (size_t)(voff + vid[i]);
@@ -754,18 +825,22 @@ __global__ void __launch_bounds__(MVR_THREADS, 3) mesh_backward_kernel(const Mes
       }
     }
   }
-  if (any) s_any = 1;   // benign race: all writers store 1
-  __syncthreads();
-  float* out = p.partials + ((size_t)n * p.ctas_per_view + cta) * 16;
-  if (!s_any) {   // uniform: background-only block
-    if (tid < 16) out[tid] = 0.f;
+  // one partial per WARP, no block barrier: a warp retires as soon as its own pixels are done
+  float* out = p.partials + (((size_t)n * p.ctas_per_view + cta) * NWARPS + (tid >> 5)) * 16;
+  const int lane = tid & 31;
+  if (!__any_sync(0xffffffffu, any)) {   // background-only warp
+    if (lane < 16) out[lane] = 0.f;
     return;
   }
-  block_sum<BWD_VALS>(acc, s_red);
-  if (tid < 16) out[tid] = tid < BWD_VALS ? s_red[tid] : 0.f;
+#pragma unroll
+  for (int i = 0; i < BWD_VALS; ++i) acc[i] = warp_sum(acc[i]);
+  float mine = 0.f;
+#pragma unroll
+  for (int i = 0; i < BWD_VALS; ++i) mine = lane == i ? acc[i] : mine;
+  if (lane < 16) out[lane] = mine;
 }
 
-// fixed-order sum of the per-CTA partials: one warp per view -> gR, gT, gC
+// fixed-order sum of the per-warp partials: one warp per view -> gR, gT, gC
 __global__ void mesh_backward_reduce_kernel(const float* __restrict__ partials, int N, int n_parts,
                                             float* __restrict__ gR, float* __restrict__ gT, float* __restrict__ gC) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -830,27 +905,52 @@ extern "C" int mvr_mesh_get_normals(const void* geometry, int64_t total_verts, i
   return check_launch("mvr_mesh_get_normals");
 }
 
-extern "C" size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K) {
-  if (B < 0 || M < 0 || H <= 0 || W <= 0 || K < 1) return 0;
-  return ws_layout(B, M, H, W, K).total;
+extern "C" size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K, int64_t total_verts) {
+  if (B < 0 || M < 0 || H <= 0 || W <= 0 || K < 1 || total_verts < 0) return 0;
+  return ws_layout(B, M, H, W, K, total_verts).total;
 }
 
-static int check_mesh_common(const char* who, int B, int M, int H, int W, int K, int64_t tv, int64_t tf) {
-  if (B < 0 || M < 0 || tv < 0 || tf < 0) { set_error("%s: negative size", who); return -1; }
+static int check_mesh_common(const char* who, int B, int M, int H, int W, int K, int64_t tv, int64_t tf, int max_verts) {
+  if (B < 0 || M < 0 || tv < 0 || tf < 0 || max_verts < 0) { set_error("%s: negative size", who); return -1; }
   if (H <= 0 || W <= 0 || H > 4096 || W > 4096) { set_error("%s: image size %dx%d outside [1, 4096]", who, H, W); return -2; }
   if (K < 1 || K > 64) { set_error("%s: faces_per_pixel %d outside [1, 64]", who, K); return -3; }
   if ((int64_t)B * M * (((int64_t)H * W + 255) / 256 + 1) > 0x7fffffffLL || B > 65535 || M > 65535) { set_error("%s: too many views", who); return -4; }
   return 0;
 }
 
+// tuning knob (profiling only): MVR_SCATTER_MINB=3 trades occupancy (3 CTAs/SM, 85 registers) for fewer
+// rematerialised instructions in the scatter kernel's inner loops; default 4 CTAs/SM
+static int scatter_minb() {
+  static const int v = [] { const char* e = getenv("MVR_SCATTER_MINB"); return (e && atoi(e) == 3) ? 3 : 4; }();
+  return v;
+}
+
+static int backward_minb() {
+  static const int v = [] { const char* e = getenv("MVR_BWD_MINB"); return (e && atoi(e) == 2) ? 2 : 3; }();
+  return v;
+}
+
+// world -> NDC of every (view, vertex) + the pixel-centre table, into the front of the workspace
+static int launch_project(const char* who, const GeomLayout& g, const WsLayout& w, const void* geometry,
+                          const int* vert_off, const float* R, const float* T, int B, int M, int H, int W,
+                          int max_verts, float k00, float k11, void* workspace, cudaStream_t st) {
+  const char* gb = (const char*)geometry;
+  char* wb = (char*)workspace;
+  const dim3 grid((unsigned)((max_verts + MVR_THREADS - 1) / MVR_THREADS > 0 ? (max_verts + MVR_THREADS - 1) / MVR_THREADS : 1),
+                  (unsigned)M, (unsigned)B);
+  MVR_LAUNCH(mesh_project_kernel, grid, MVR_THREADS, 0, st, (const float4*)(gb + g.verts4), vert_off, R, T, M, H, W,
+             k00, k11, (float4*)(wb + w.pv), (float*)(wb + w.tab));
+  return check_launch(who);
+}
+
 extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
-                                int64_t total_verts, int64_t total_faces, int max_faces, const float* R,
-                                const float* T, const float* Cc, const float* light, int light_stride,
-                                const float* obj_rgb, const float* bg_rgb, float k00, float k11, float z_clip,
-                                int H, int W, int K, int flags, float* images, int* pix_to_face, float* zbuf,
-                                float* bary, float* dists, int64_t* counters, void* workspace,
+                                int64_t total_verts, int64_t total_faces, int max_verts, int max_faces,
+                                const float* R, const float* T, const float* Cc, const float* light,
+                                int light_stride, const float* obj_rgb, const float* bg_rgb, float k00, float k11,
+                                float z_clip, int H, int W, int K, int flags, float* images, int* pix_to_face,
+                                float* zbuf, float* bary, float* dists, int64_t* counters, void* workspace,
                                 size_t workspace_bytes, void* stream) {
-  int rc = check_mesh_common("mvr_mesh_forward", B, M, H, W, K, total_verts, total_faces);
+  int rc = check_mesh_common("mvr_mesh_forward", B, M, H, W, K, total_verts, total_faces, max_verts);
   if (rc) return rc;
   const int64_t N = (int64_t)B * M;
   if (N == 0) return 0;
@@ -858,7 +958,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
     set_error("mvr_mesh_forward: null pointer"); return -5;
   }
   if (!(flags & MVR_RGB_PER_ELEMENT) && !obj_rgb) { set_error("mvr_mesh_forward: obj_rgb is NULL and the geometry has no per-vertex colours"); return -6; }
-  const WsLayout w = ws_layout(B, M, H, W, K);
+  const WsLayout w = ws_layout(B, M, H, W, K, total_verts);
   if (workspace_bytes < w.total) { set_error("mvr_mesh_forward: workspace too small (%zu < %zu)", workspace_bytes, w.total); return -7; }
   const int chunks_per_view = max_faces > 0 ? (max_faces + FACES_PER_CTA - 1) / FACES_PER_CTA : 0;
   if (N * (int64_t)(chunks_per_view + 1) > 0x7fffffffLL) { set_error("mvr_mesh_forward: too many face chunks"); return -8; }
@@ -877,23 +977,28 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.chunks_per_view = chunks_per_view; p.layer = 0;
   p.item_cap = (flags & MVR_TEST_TINY_QUEUES) ? 24 : ITEM_CAP;
   p.wcap = (flags & MVR_TEST_TINY_QUEUES) ? 5 : WCAP;
+  p.pv = (float4*)(wb + w.pv); p.tab = (float*)(wb + w.tab);
   p.keys = (unsigned long long*)(wb + w.keys); p.prev = (unsigned long long*)(wb + w.prev);
   p.images = images; p.pix_to_face = pix_to_face; p.zbuf = zbuf; p.bary = bary; p.dists = dists;
   p.counters = (long long*)counters;
   const size_t HW = (size_t)H * W;
   cudaError_t e = cudaMemsetAsync(p.keys, 0xFF, (size_t)N * HW * 8, st);      // every key = EMPTY
   if (e != cudaSuccess) { set_error("mvr_mesh_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+  rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, workspace, st);
+  if (rc) return rc;
   const size_t tab_smem = ((size_t)W + H) * sizeof(float);
   const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
   const dim3 shade_grid((unsigned)(tiles_x * tiles_y), (unsigned)M, (unsigned)B);
   for (int k = 0; k < K; ++k) {
     p.layer = k;
     if (chunks_per_view > 0) {
-      MVR_LAUNCH(mesh_scatter_kernel, (unsigned)(N * chunks_per_view), MVR_THREADS, tab_smem, st, p);
+      if (scatter_minb() == 3) MVR_LAUNCH(mesh_scatter_kernel<3>, (unsigned)(N * chunks_per_view), MVR_THREADS, tab_smem, st, p);
+      else MVR_LAUNCH(mesh_scatter_kernel<4>, (unsigned)(N * chunks_per_view), MVR_THREADS, tab_smem, st, p);
       rc = check_launch("mesh_scatter_kernel");
       if (rc) return rc;
     }
-    MVR_LAUNCH(mesh_shade_kernel, shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+    if (zbuf || bary || dists) MVR_LAUNCH(mesh_shade_kernel<true>, shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+    else MVR_LAUNCH(mesh_shade_kernel<false>, shade_grid, MVR_THREADS, 0, st, p, tiles_x);
     rc = check_launch("mesh_shade_kernel");
     if (rc) return rc;
   }
@@ -901,12 +1006,13 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
 }
 
 extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
-                                 int64_t total_verts, int64_t total_faces, const float* R, const float* T,
-                                 const float* Cc, const float* light, int light_stride, const float* obj_rgb,
-                                 float k00, float k11, int H, int W, int K, int flags, const int* pix_to_face,
-                                 const float* grad_images, float* gR, float* gT, float* gC, float* grad_verts,
-                                 float* grad_normals, void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = check_mesh_common("mvr_mesh_backward", B, M, H, W, K, total_verts, total_faces);
+                                 int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
+                                 const float* T, const float* Cc, const float* light, int light_stride,
+                                 const float* obj_rgb, float k00, float k11, int H, int W, int K, int flags,
+                                 const int* pix_to_face, const float* grad_images, float* gR, float* gT, float* gC,
+                                 float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  int rc = check_mesh_common("mvr_mesh_backward", B, M, H, W, K, total_verts, total_faces, max_verts);
   if (rc) return rc;
   const int64_t N = (int64_t)B * M;
   if (N == 0) return 0;
@@ -914,12 +1020,15 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
     set_error("mvr_mesh_backward: null pointer"); return -5;
   }
   if (!(flags & MVR_RGB_PER_ELEMENT) && !obj_rgb) { set_error("mvr_mesh_backward: obj_rgb is NULL"); return -6; }
-  const WsLayout w = ws_layout(B, M, H, W, K);
-  const size_t need = (size_t)N * w.bwd_ctas_per_view * 16 * sizeof(float);
-  if (workspace_bytes < need) { set_error("mvr_mesh_backward: workspace too small (%zu < %zu)", workspace_bytes, need); return -7; }
+  const WsLayout w = ws_layout(B, M, H, W, K, total_verts);
+  if (workspace_bytes < w.total) { set_error("mvr_mesh_backward: workspace too small (%zu < %zu)", workspace_bytes, w.total); return -7; }
   const GeomLayout g = geom_layout(total_verts, total_faces);
   const char* gb = (const char*)geometry;
+  char* wb = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
+  // the workspace is scratch (it may have served another render since the forward): project again, 2% of the step
+  rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, workspace, st);
+  if (rc) return rc;
   MeshBwdParams p;
   p.verts4 = (const float4*)(gb + g.verts4); p.normals4 = (const float4*)(gb + g.normals4);
   p.rgb4 = (const float4*)(gb + g.rgb4); p.faces4 = (const int4*)(gb + g.faces4);
@@ -927,12 +1036,15 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   p.R = R; p.T = T; p.Cc = Cc; p.light = light; p.light_stride = light_stride; p.obj_rgb = obj_rgb;
   p.k00 = k00; p.k11 = k11;
   p.B = B; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags; p.ctas_per_view = w.bwd_ctas_per_view; p.tiles_x = (W + 31) / 32;
+  p.pv = (const float4*)(wb + w.pv); p.tab = (const float*)(wb + w.tab);
   p.pix_to_face = pix_to_face; p.grad_images = grad_images;
-  p.partials = (float*)workspace; p.grad_verts = grad_verts; p.grad_normals = grad_normals;
-  MVR_LAUNCH(mesh_backward_kernel, dim3((unsigned)w.bwd_ctas_per_view, (unsigned)M, (unsigned)B), MVR_THREADS, 0, st, p);
+  p.partials = (float*)(wb + w.partials); p.grad_verts = grad_verts; p.grad_normals = grad_normals;
+  const dim3 bgrid((unsigned)w.bwd_ctas_per_view, (unsigned)M, (unsigned)B);
+  if (backward_minb() == 2) MVR_LAUNCH(mesh_backward_kernel<2>, bgrid, MVR_THREADS, 0, st, p);
+  else MVR_LAUNCH(mesh_backward_kernel<3>, bgrid, MVR_THREADS, 0, st, p);
   rc = check_launch("mesh_backward_kernel");
   if (rc) return rc;
   const int wpb = 8;
-  MVR_LAUNCH(mesh_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)workspace, (int)N, w.bwd_ctas_per_view, gR, gT, gC);
+  MVR_LAUNCH(mesh_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)(wb + w.partials), (int)N, w.bwd_ctas_per_view * NWARPS, gR, gT, gC);
   return check_launch("mesh_backward_reduce_kernel");
 }

@@ -1,30 +1,35 @@
 // mvr_points.cu -- point-cloud path of MVRenderer (renderer.py:116-151) for sm_100a.
 //
-//   forward : per layer k (K = points_per_pixel passes; K = 1 in MVTN's configuration)
+//   forward : ONE pass whatever K (= points_per_pixel) is --
 //               points_scatter_kernel -- one thread per (view, point): p = (X / dist) R + T is computed ONCE per
 //                 view, the handful of pixel centres inside the point's radius are tested exactly
-//                 (dist2 < r^2, IEEE fp32) and a 64-bit (z, point) RED.MIN goes to the pixel's key in a
-//                 global, L2-resident key plane (pass k keeps keys > layer k-1);
-//               points_resolve_kernel -- one thread per pixel: key -> idx / zbuf / dists2 of layer k, key plane
-//                 handed to the next pass; the last pass recomputes dist2 of every layer, applies the
-//                 norm-weighted or alpha compositor and the background, and writes planar (n,3,H,W) rows.
-//   backward: points_backward_kernel -- per pixel recompute from idx only; compositor backward ->
-//             d dist2 -> d ndc.xy -> (dR, dT, d(1/dist)) block-reduced to one partial per (view, strip),
-//             summed in fixed order; optional per-point / colour gradients via atomics.
+//                 (dist2 < r^2, IEEE fp32) and the 64-bit (z, point) key is inserted into the pixel's K sorted
+//                 slots by a chain of 64-bit atomic mins: slot k keeps min(old, key) and the larger of the two
+//                 moves on to slot k+1.  Every key but the k smallest passes slot k exactly once, so slot k ends
+//                 up holding the (k+1)-th smallest (z, index) key whatever the order of arrival: the oracle's
+//                 priority-queue result, deterministically.  K = 1 degenerates to a fire-and-forget RED.MIN.64;
+//               points_resolve_kernel -- one thread per pixel: the pixel's K keys (one 32-byte sector for K = 4)
+//                 -> idx / zbuf / dists2 of every layer, norm-weighted or alpha compositing, background, planar
+//                 (n,3,H,W) rows, and one bit per pixel in a hit mask (the images are ~90 % background).
+//   backward: points_backward_kernel -- 32x32-pixel tiles; a warp reads the hit-mask word of its 32 pixels and only
+//             covered pixels touch idx / grad_images: compositor backward -> d dist2 -> d ndc.xy ->
+//             (dR, dT, d(1/dist)) block-reduced to one partial per (view, tile), summed in fixed order; optional
+//             per-point / colour gradients via atomics.
 #include "mvr_common.cuh"
 
 namespace mvr {
 
-constexpr int PB_ROWS = 8;     // backward strip height
-constexpr int PB_VALS = 13;    // dR 9, dT 3, d inv_dist 1
+constexpr int PB_PIX_PER_THREAD = 4;   // backward: 32x32-pixel tiles, thread (lane, warp) owns rows warp + 8j
+constexpr int PB_VALS = 13;            // dR 9, dT 3, d inv_dist 1
+constexpr int PK_MAX_REG = 8;          // layers kept in registers by the templated kernels
 
 struct PointsParams {
   const float* points; const float* rgb;
   const float* R; const float* T; const float* inv_dist; const float* bg_rgb;
   float radius, r2_raster, r2_weight;
-  int B, Np, M, H, W, K, flags, layer;
-  unsigned long long* keys; unsigned long long* prev;
-  float* images; int* idx; float* zbuf; float* dists2;
+  int B, Np, M, H, W, K, flags, mask_words;
+  unsigned long long* keys;      // (n, H*W, K): the K smallest (z, point) keys of every pixel, ascending
+  float* images; int* idx; float* zbuf; float* dists2; unsigned int* hit_mask;
 };
 
 __device__ __forceinline__ void project_point(const float* __restrict__ pts, int pi, float s, const Camera& cam,
@@ -51,95 +56,126 @@ __global__ void __launch_bounds__(MVR_THREADS) points_scatter_kernel(const Point
   if (yl > yh) return;
   ndc_range_to_pix(px - rr, px + rr, p.W, p.H, jlo, jhi);
   const int xl = p.W - 1 - jhi, xh = p.W - 1 - jlo;
-  const unsigned long long key = make_key(pz, pi);
+  const unsigned long long key0 = make_key(pz, pi);
   const size_t HW = (size_t)p.H * p.W;
-  unsigned long long* keys = p.keys + (size_t)n * HW;
-  const unsigned long long* prev = p.layer > 0 ? p.prev + (size_t)n * HW : nullptr;
+  unsigned long long* keys = p.keys + (size_t)n * HW * p.K;
   for (int yy = yl; yy <= yh; ++yy) {
     const float dy = py - pix_to_ndc(p.H - 1 - yy, p.H, p.W);
     for (int xx = xl; xx <= xh; ++xx) {
       const float dx = px - pix_to_ndc(p.W - 1 - xx, p.W, p.H);
       const float d2 = dx * dx + dy * dy;
       if (!(d2 < p.r2_raster)) continue;
-      const size_t o = (size_t)yy * p.W + xx;
-      if (prev && key <= __ldcg(prev + o)) continue;
-      if (key >= __ldcg(keys + o)) continue;
-      atomicMin(keys + o, key);      // result unused: RED.MIN.64 resolved in L2
+      unsigned long long* slot = keys + ((size_t)yy * p.W + xx) * p.K;
+      if (p.K == 1) {
+        if (key0 < __ldcg(slot)) atomicMin(slot, key0);      // result unused: RED.MIN.64 resolved in L2
+        continue;
+      }
+      unsigned long long key = key0;
+      for (int k = 0; k < p.K; ++k) {
+        // a stale (larger) snapshot only costs an atomic: keys never grow, so key >= snapshot means the slot keeps
+        // its value and `key` moves on unchanged
+        if (key >= __ldcg(slot + k)) continue;
+        const unsigned long long old = atomicMin(slot + k, key);
+        key = old > key ? old : key;                         // the displaced (or rejected) key goes one slot deeper
+        if (key == MVR_EMPTY_KEY) break;
+      }
     }
   }
 }
 
-// grid: x = 32x8-pixel tiles, y = view m, z = object b
+// grid: x = 32x8-pixel tiles, y = view m, z = object b.  KT = K when K <= PK_MAX_REG (keys in registers), 0 = generic
+template <int KT>
 __global__ void __launch_bounds__(MVR_THREADS) points_resolve_kernel(const PointsParams p, int tiles_x) {
   const int b = blockIdx.z, n = b * p.M + blockIdx.y;
   const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
   const int xi = tx * 32 + (threadIdx.x & 31), yi = ty * 8 + (threadIdx.x >> 5);
-  if (xi >= p.W || yi >= p.H) return;
+  const int K = KT > 0 ? KT : p.K;
+  const bool inside = xi < p.W && yi < p.H;
   const size_t HW = (size_t)p.H * p.W;
   const size_t pix = (size_t)yi * p.W + xi;
-  const int k = p.layer;
-  unsigned long long* kp = p.keys + (size_t)n * HW + pix;
-  const unsigned long long key = *kp;
-  if (k + 1 < p.K) {            // hand the layer to the next peeling pass
-    p.prev[(size_t)n * HW + pix] = key;
-    *kp = MVR_EMPTY_KEY;
-  }
-  const bool hit = key != MVR_EMPTY_KEY;
-  const int pid = hit ? (int)(unsigned int)(key & 0xffffffffull) : -1;
-  const size_t po = ((size_t)n * HW + pix) * p.K;
-  p.idx[po + k] = pid;
-  const bool want_frag = p.zbuf || p.dists2;
-  const bool last = k == p.K - 1;
-  if (!want_frag && !last) return;
-  // first-layer hit decides foreground ([upstream] _add_background_color_to_images)
-  const int first = k == 0 ? pid : p.idx[po];
-  Camera cam;
-  float s = 0.f, xf = 0.f, yf = 0.f;
-  const float* pts = p.points + 3 * (size_t)b * p.Np;
-  if (first >= 0) {
-    cam = load_camera(p.R, p.T, n);
-    s = __ldg(p.inv_dist + n);
-    xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H);
-    yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
-  }
-  if (want_frag) {
-    float z = -1.f, d2 = -1.f;
-    if (hit) {
-      float px, py, pz;
-      project_point(pts, pid, s, cam, px, py, pz);
-      const float dx = px - xf, dy = py - yf;
-      d2 = dx * dx + dy * dy;
-      z = __uint_as_float((unsigned int)(key >> 32));
+  const size_t po = ((size_t)n * HW + pix) * K;
+  const unsigned long long* kp = p.keys + po;
+  // ---- the pixel's keys: ascending, EMPTY-padded ----
+  unsigned long long key0 = MVR_EMPTY_KEY;
+  unsigned long long kreg[KT > 0 ? KT : 1];
+  if (inside) {
+    if (KT == 0) {
+      key0 = kp[0];
+    } else if (KT % 2 == 0) {
+#pragma unroll
+      for (int l = 0; l < KT; l += 2) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(kp + l);
+        kreg[l] = v.x; kreg[l + 1] = v.y;
+      }
+      key0 = kreg[0];
+    } else {
+#pragma unroll
+      for (int l = 0; l < KT; ++l) kreg[l] = kp[l];
+      key0 = kreg[0];
     }
-    if (p.zbuf) p.zbuf[po + k] = z;
-    if (p.dists2) p.dists2[po + k] = d2;
   }
-  if (!last) return;
-  // ---- compositing over all layers ([upstream] norm_weighted_sum / alpha_composite) ----
+  const bool hit = key0 != MVR_EMPTY_KEY;      // first-layer hit decides foreground ([upstream] _add_background_color_to_images)
+  if (p.hit_mask) {
+    const unsigned int mword = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && yi < p.H) p.hit_mask[((size_t)n * p.H + yi) * p.mask_words + tx] = mword;
+  }
+  if (!inside) return;
   float o0 = __ldg(p.bg_rgb), o1 = __ldg(p.bg_rgb + 1), o2 = __ldg(p.bg_rgb + 2);
-  if (first >= 0) {
+  const bool want_frag = p.zbuf || p.dists2;
+  if (!hit) {
+    if (KT == 4) {
+      *reinterpret_cast<int4*>(p.idx + po) = make_int4(-1, -1, -1, -1);
+    } else {
+      for (int l = 0; l < K; ++l) p.idx[po + l] = -1;
+    }
+    if (want_frag)
+      for (int l = 0; l < K; ++l) {
+        if (p.zbuf) p.zbuf[po + l] = -1.f;
+        if (p.dists2) p.dists2[po + l] = -1.f;
+      }
+  } else {
+    const Camera cam = load_camera(p.R, p.T, n);
+    const float s = __ldg(p.inv_dist + n);
+    const float xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H);
+    const float yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
+    const float* pts = p.points + 3 * (size_t)b * p.Np;
     const bool per_point_rgb = p.flags & MVR_RGB_PER_ELEMENT;
     const bool alpha_mode = p.flags & MVR_COMPOSITE_ALPHA;
     const float* feat = per_point_rgb ? p.rgb + 3 * (size_t)b * p.Np : p.rgb;
+    // ---- compositing over the layers ([upstream] norm_weighted_sum / alpha_composite) ----
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, aw = alpha_mode ? 1.f : 0.f;
-    for (int l = 0; l < p.K; ++l) {
-      const int q = l == k ? pid : p.idx[po + l];
-      if (q < 0) break;
-      float px, py, pz;
-      project_point(pts, q, s, cam, px, py, pz);
-      const float dx = px - xf, dy = py - yf;
-      const float a = 1.f - (dx * dx + dy * dy) / p.r2_weight;
-      const float* f = feat + (per_point_rgb ? 3 * (size_t)q : 0);
-      const float f0 = __ldg(f), f1 = __ldg(f + 1), f2 = __ldg(f + 2);
-      if (alpha_mode) {   // out += cum * alpha * f ; cum *= (1 - alpha)
-        const float ca = aw * a;
-        a0 += ca * f0; a1 += ca * f1; a2 += ca * f2;
-        aw = aw * (1.f - a);
-      } else {            // numerators and the alpha sum
-        a0 += a * f0; a1 += a * f1; a2 += a * f2;
-        aw += a;
+    int ids[KT > 0 ? KT : 1];
+    bool open = true;      // layers are contiguous: the first EMPTY key ends them
+#pragma unroll
+    for (int l = 0; l < K; ++l) {
+      const unsigned long long key = KT > 0 ? kreg[KT > 0 ? l : 0] : kp[l];
+      open = open && key != MVR_EMPTY_KEY;
+      int q = -1;
+      float z = -1.f, d2 = -1.f;
+      if (open) {
+        q = (int)(unsigned int)(key & 0xffffffffull);
+        float px, py, pz;
+        project_point(pts, q, s, cam, px, py, pz);
+        const float dx = px - xf, dy = py - yf;
+        d2 = dx * dx + dy * dy;
+        z = __uint_as_float((unsigned int)(key >> 32));
+        const float a = 1.f - d2 / p.r2_weight;
+        const float* f = feat + (per_point_rgb ? 3 * (size_t)q : 0);
+        const float f0 = __ldg(f), f1 = __ldg(f + 1), f2 = __ldg(f + 2);
+        if (alpha_mode) {   // out += cum * alpha * f ; cum *= (1 - alpha)
+          const float ca = aw * a;
+          a0 += ca * f0; a1 += ca * f1; a2 += ca * f2;
+          aw = aw * (1.f - a);
+        } else {            // numerators and the alpha sum
+          a0 += a * f0; a1 += a * f1; a2 += a * f2;
+          aw += a;
+        }
       }
+      if (KT == 4) ids[KT > 0 ? l : 0] = q; else p.idx[po + l] = q;
+      if (p.zbuf) p.zbuf[po + l] = z;
+      if (p.dists2) p.dists2[po + l] = d2;
     }
+    if (KT == 4) *reinterpret_cast<int4*>(p.idx + po) = make_int4(ids[0], ids[KT > 1 ? 1 : 0], ids[KT > 2 ? 2 : 0], ids[KT > 3 ? 3 : 0]);
     if (alpha_mode) { o0 = a0; o1 = a1; o2 = a2; }
     else { const float t = fmaxf(aw, 1e-4f); o0 = a0 / t; o1 = a1 / t; o2 = a2 / t; }
   }
@@ -152,43 +188,51 @@ struct PointsBwdParams {
   const float* points; const float* rgb;
   const float* R; const float* T; const float* inv_dist;
   float r2_weight;
-  int B, Np, M, H, W, K, flags, n_strips;
-  const int* idx; const float* grad_images;
-  float* partials;        // (N, n_strips, 16)
+  int B, Np, M, H, W, K, flags, tiles_x, ctas_per_view, mask_words;
+  const int* idx; const float* grad_images; const unsigned int* hit_mask;
+  float* partials;        // (N, ctas_per_view, 8 warps, 16)
   float* grad_points; float* grad_rgb;
 };
 
+// grid: x = 32x32-pixel tiles, y = view m, z = object b
 __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const PointsBwdParams p) {
-  __shared__ float s_red[8 * PB_VALS];
-  __shared__ int s_any;
-  const int tid = threadIdx.x;
-  const int n = blockIdx.x / p.n_strips, strip = blockIdx.x % p.n_strips;
-  const int b = n / p.M;
-  const int y0 = strip * PB_ROWS, y1 = min(y0 + PB_ROWS, p.H) - 1;
-  const int npix = (y1 - y0 + 1) * p.W;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b = blockIdx.z, n = b * p.M + blockIdx.y, cta = blockIdx.x;
+  const int tyb = cta / p.tiles_x, txb = cta - tyb * p.tiles_x;
+  const int xi = txb * 32 + lane, yi0 = tyb * 32 + (tid >> 5);
   const bool per_point_rgb = p.flags & MVR_RGB_PER_ELEMENT;
   const bool alpha_mode = p.flags & MVR_COMPOSITE_ALPHA;
   const float* pts = p.points + 3 * (size_t)b * p.Np;
   const float* feat = per_point_rgb ? p.rgb + 3 * (size_t)b * p.Np : p.rgb;
-  if (tid == 0) s_any = 0;
-  __syncthreads();
+  const size_t plane = (size_t)p.H * p.W;
+  // which of this thread's pixels are covered: one broadcast mask word per warp row (or idx[.., 0] without a mask)
+  bool hits[PB_PIX_PER_THREAD];
+#pragma unroll
+  for (int j = 0; j < PB_PIX_PER_THREAD; ++j) {
+    const int yi = yi0 + 8 * j;
+    hits[j] = false;
+    if (yi < p.H) {
+      if (p.hit_mask) hits[j] = (__ldg(p.hit_mask + ((size_t)n * p.H + yi) * p.mask_words + txb) >> lane) & 1u;
+      else if (xi < p.W) hits[j] = __ldg(p.idx + ((size_t)n * plane + (size_t)yi * p.W + xi) * p.K) >= 0;
+    }
+  }
   float acc[PB_VALS];
 #pragma unroll
   for (int i = 0; i < PB_VALS; ++i) acc[i] = 0.f;
   bool any = false, ctx = false;
-  Camera cam; float s = 0.f;
-  const size_t plane = (size_t)p.H * p.W;
+  Camera cam; float s = 0.f, xf = 0.f;
   const float inv_r2 = 1.f / p.r2_weight;
-  for (int pix = tid; pix < npix; pix += MVR_THREADS) {
-    const int yi = y0 + pix / p.W, xi = pix % p.W;
+#pragma unroll 1
+  for (int j = 0; j < PB_PIX_PER_THREAD; ++j) {
+    if (!hits[j]) continue;   // background pixel: masked_scatter blocks the gradient
+    const int yi = yi0 + 8 * j;
     const int* ip = p.idx + (((size_t)n * p.H + yi) * p.W + xi) * p.K;
-    if (__ldg(ip) < 0) continue;   // background pixel: masked_scatter blocks the gradient
     const size_t io = ((size_t)n * 3 * p.H + yi) * p.W + xi;
     const float g0 = __ldg(p.grad_images + io), g1 = __ldg(p.grad_images + io + plane), g2 = __ldg(p.grad_images + io + 2 * plane);
     if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
     any = true;
-    if (!ctx) { cam = load_camera(p.R, p.T, n); s = __ldg(p.inv_dist + n); ctx = true; }
-    const float xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H), yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
+    if (!ctx) { cam = load_camera(p.R, p.T, n); s = __ldg(p.inv_dist + n); xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H); ctx = true; }
+    const float yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
     // pass 1: compositor totals
     float t_alpha = 0.f, tf0 = 0.f, tf1 = 0.f, tf2 = 0.f;   // norm: sum a, sum a f ; alpha: out_c
     {
@@ -250,25 +294,28 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
       }
     }
   }
-  if (any) s_any = 1;
-  __syncthreads();
-  float* out = p.partials + ((size_t)n * p.n_strips + strip) * 16;
-  if (!s_any) {
-    if (tid < 16) out[tid] = 0.f;
+  // one partial per WARP, no block barrier
+  float* out = p.partials + (((size_t)n * p.ctas_per_view + cta) * 8 + (tid >> 5)) * 16;
+  if (!__any_sync(0xffffffffu, any)) {
+    if (lane < 16) out[lane] = 0.f;
     return;
   }
-  block_sum<PB_VALS>(acc, s_red);
-  if (tid < 16) out[tid] = tid < PB_VALS ? s_red[tid] : 0.f;
+#pragma unroll
+  for (int i = 0; i < PB_VALS; ++i) acc[i] = warp_sum(acc[i]);
+  float mine = 0.f;
+#pragma unroll
+  for (int i = 0; i < PB_VALS; ++i) mine = lane == i ? acc[i] : mine;
+  if (lane < 16) out[lane] = mine;
 }
 
-__global__ void points_backward_reduce_kernel(const float* __restrict__ partials, int N, int n_strips,
+__global__ void points_backward_reduce_kernel(const float* __restrict__ partials, int N, int n_parts,
                                               float* __restrict__ gR, float* __restrict__ gT, float* __restrict__ gs) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
   const int v = lane & 15, par = lane >> 4;
   float s = 0.f;
-  for (int t = par; t < n_strips; t += 2) s += partials[((size_t)n * n_strips + t) * 16 + v];
+  for (int t = par; t < n_parts; t += 2) s += partials[((size_t)n * n_parts + t) * 16 + v];
   s += __shfl_xor_sync(0xffffffffu, s, 16);
   if (lane < 9) gR[9 * (size_t)n + lane] = s;
   else if (lane < 12) gT[3 * (size_t)n + lane - 9] = s;
@@ -288,64 +335,83 @@ static int check_points_common(const char* who, int B, int Np, int M, int H, int
   return 0;
 }
 
-static size_t points_partials_bytes(int B, int M, int H) {
-  const size_t n_strips = (H + PB_ROWS - 1) / PB_ROWS;
-  return ((size_t)B * M * n_strips * 16 * sizeof(float) + 255) & ~(size_t)255;
+struct PointsWs {
+  size_t keys, partials, total;
+  int tiles_x, ctas_per_view, mask_words;
+};
+static PointsWs points_ws(int B, int M, int H, int W, int K) {
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  PointsWs w;
+  const size_t N = (size_t)B * M;
+  w.tiles_x = (W + 31) / 32;
+  w.ctas_per_view = w.tiles_x * ((H + 31) / 32);
+  w.mask_words = w.tiles_x;
+  w.keys = 0;
+  const size_t fwd = al(N * H * W * K * 8);
+  w.partials = 0;                                  // the backward reuses the front of the workspace
+  const size_t bwd = al(N * w.ctas_per_view * 8 * 16 * sizeof(float));
+  w.total = fwd > bwd ? fwd : bwd;
+  return w;
 }
 
 extern "C" size_t mvr_points_workspace_bytes(int B, int M, int H, int W, int K) {
   if (B < 0 || M < 0 || H <= 0 || W <= 0 || K < 1) return 0;
-  const size_t plane = (((size_t)B * M * H * W * 8) + 255) & ~(size_t)255;
-  const size_t fwd = plane * (K > 1 ? 2 : 1);
-  const size_t bwd = points_partials_bytes(B, M, H);
-  return fwd > bwd ? fwd : bwd;
+  return points_ws(B, M, H, W, K).total;
+}
+
+extern "C" size_t mvr_points_hit_mask_words(int B, int M, int H, int W) {
+  if (B < 0 || M < 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)B * M * H * ((W + 31) / 32);
 }
 
 extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
                                   const float* T, const float* inv_dist, double radius, const float* bg_rgb,
                                   int H, int W, int K, int flags, float* images, int* idx, float* zbuf,
-                                  float* dists2, void* workspace, size_t workspace_bytes, void* stream) {
+                                  float* dists2, uint32_t* hit_mask, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
   int rc = check_points_common("mvr_points_forward", B, Np, M, H, W, K, radius);
   if (rc) return rc;
   const int64_t N = (int64_t)B * M;
   if (N == 0) return 0;
   if ((Np > 0 && !points) || !rgb || !R || !T || !inv_dist || !bg_rgb || !images || !idx || !workspace) { set_error("mvr_points_forward: null pointer"); return -6; }
+  const PointsWs w = points_ws(B, M, H, W, K);
   const size_t HW = (size_t)H * W;
-  const size_t plane = (((size_t)N * HW * 8) + 255) & ~(size_t)255;
-  if (workspace_bytes < plane * (K > 1 ? 2 : 1)) { set_error("mvr_points_forward: workspace too small (%zu < %zu)", workspace_bytes, plane * (K > 1 ? 2 : 1)); return -7; }
+  const size_t need = (size_t)N * HW * K * 8;
+  if (workspace_bytes < need) { set_error("mvr_points_forward: workspace too small (%zu < %zu)", workspace_bytes, need); return -7; }
   PointsParams p;
   p.points = points; p.rgb = rgb; p.R = R; p.T = T; p.inv_dist = inv_dist; p.bg_rgb = bg_rgb;
   p.radius = (float)radius;
   p.r2_raster = p.radius * p.radius;            // [upstream] rasterize_points_cpu.cpp: float radius * radius
   p.r2_weight = (float)(radius * radius);       // [upstream] points/renderer.py: python-float r * r
-  p.B = B; p.Np = Np; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags; p.layer = 0;
-  p.keys = (unsigned long long*)workspace; p.prev = (unsigned long long*)((char*)workspace + plane);
-  p.images = images; p.idx = idx; p.zbuf = zbuf; p.dists2 = dists2;
+  p.B = B; p.Np = Np; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags; p.mask_words = w.mask_words;
+  p.keys = (unsigned long long*)((char*)workspace + w.keys);
+  p.images = images; p.idx = idx; p.zbuf = zbuf; p.dists2 = dists2; p.hit_mask = hit_mask;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(p.keys, 0xFF, (size_t)N * HW * 8, st);      // every key = EMPTY
+  cudaError_t e = cudaMemsetAsync(p.keys, 0xFF, need, st);      // every key = EMPTY
   if (e != cudaSuccess) { set_error("mvr_points_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
   const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
   const dim3 scatter_grid((unsigned)((Np + MVR_THREADS - 1) / MVR_THREADS), (unsigned)M, (unsigned)B);
   const dim3 resolve_grid((unsigned)(tiles_x * tiles_y), (unsigned)M, (unsigned)B);
-  for (int k = 0; k < K; ++k) {
-    p.layer = k;
-    if (Np > 0) {
-      MVR_LAUNCH(points_scatter_kernel, scatter_grid, MVR_THREADS, 0, st, p);
-      rc = check_launch("points_scatter_kernel");
-      if (rc) return rc;
-    }
-    MVR_LAUNCH(points_resolve_kernel, resolve_grid, MVR_THREADS, 0, st, p, tiles_x);
-    rc = check_launch("points_resolve_kernel");
+  if (Np > 0) {
+    MVR_LAUNCH(points_scatter_kernel, scatter_grid, MVR_THREADS, 0, st, p);
+    rc = check_launch("points_scatter_kernel");
     if (rc) return rc;
   }
-  return 0;
+  switch (K) {
+    case 1: MVR_LAUNCH(points_resolve_kernel<1>, resolve_grid, MVR_THREADS, 0, st, p, tiles_x); break;
+    case 2: MVR_LAUNCH(points_resolve_kernel<2>, resolve_grid, MVR_THREADS, 0, st, p, tiles_x); break;
+    case 4: MVR_LAUNCH(points_resolve_kernel<4>, resolve_grid, MVR_THREADS, 0, st, p, tiles_x); break;
+    case 8: MVR_LAUNCH(points_resolve_kernel<8>, resolve_grid, MVR_THREADS, 0, st, p, tiles_x); break;
+    default: MVR_LAUNCH(points_resolve_kernel<0>, resolve_grid, MVR_THREADS, 0, st, p, tiles_x); break;
+  }
+  return check_launch("points_resolve_kernel");
 }
 
 extern "C" int mvr_points_backward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
                                    const float* T, const float* inv_dist, double radius, int H, int W, int K,
-                                   int flags, const int* idx, const float* grad_images, float* gR, float* gT,
-                                   float* g_inv_dist, float* grad_points, float* grad_rgb, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   int flags, const int* idx, const uint32_t* hit_mask, const float* grad_images,
+                                   float* gR, float* gT, float* g_inv_dist, float* grad_points, float* grad_rgb,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_points_common("mvr_points_backward", B, Np, M, H, W, K, radius);
   if (rc) return rc;
   const int64_t N = (int64_t)B * M;
@@ -353,20 +419,22 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
   if ((Np > 0 && !points) || !rgb || !R || !T || !inv_dist || !idx || !grad_images || !gR || !gT || !g_inv_dist || !workspace) {
     set_error("mvr_points_backward: null pointer"); return -6;
   }
-  const size_t need = points_partials_bytes(B, M, H);
+  const PointsWs w = points_ws(B, M, H, W, K);
+  const size_t need = (size_t)N * w.ctas_per_view * 8 * 16 * sizeof(float);
   if (workspace_bytes < need) { set_error("mvr_points_backward: workspace too small (%zu < %zu)", workspace_bytes, need); return -7; }
   PointsBwdParams p;
   p.points = points; p.rgb = rgb; p.R = R; p.T = T; p.inv_dist = inv_dist;
   p.r2_weight = (float)(radius * radius);
   p.B = B; p.Np = Np; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags;
-  p.n_strips = (H + PB_ROWS - 1) / PB_ROWS;
-  p.idx = idx; p.grad_images = grad_images; p.partials = (float*)workspace;
+  p.tiles_x = w.tiles_x; p.ctas_per_view = w.ctas_per_view; p.mask_words = w.mask_words;
+  p.idx = idx; p.grad_images = grad_images; p.hit_mask = hit_mask;
+  p.partials = (float*)((char*)workspace + w.partials);
   p.grad_points = grad_points; p.grad_rgb = grad_rgb;
   cudaStream_t st = (cudaStream_t)stream;
-  MVR_LAUNCH(points_backward_kernel, (unsigned)(N * p.n_strips), MVR_THREADS, 0, st, p);
+  MVR_LAUNCH(points_backward_kernel, dim3((unsigned)w.ctas_per_view, (unsigned)M, (unsigned)B), MVR_THREADS, 0, st, p);
   rc = check_launch("points_backward_kernel");
   if (rc) return rc;
   const int wpb = 8;
-  MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)workspace, (int)N, p.n_strips, gR, gT, g_inv_dist);
+  MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, w.ctas_per_view * 8, gR, gT, g_inv_dist);
   return check_launch("points_backward_reduce_kernel");
 }

@@ -74,6 +74,13 @@ def _hw(image_size):
     return int(image_size), int(image_size)
 
 
+def _host_array(t: torch.Tensor, dtype) -> torch.Tensor:
+    """Contiguous CPU view of `t` in `dtype`; the common case (already so) costs three attribute reads."""
+    if t.dtype == dtype and t.device.type == "cpu" and t.is_contiguous():
+        return t
+    return t.detach().to(device="cpu", dtype=dtype).contiguous()
+
+
 def _host_gather(srcs, dst: torch.Tensor, elem_bytes: int, narrow: bool):
     import ctypes as C
     n = len(srcs)
@@ -187,8 +194,8 @@ class PackedMeshes:
             else:
                 # multi-threaded gather into pinned memory (faces narrowed int64 -> int32 on the way), then
                 # ONE async H2D per array
-                v_src = [v.detach().to(device="cpu", dtype=torch.float32).contiguous() for v in verts]
-                f_src = [f.detach().to(device="cpu", dtype=fdt).contiguous() for f in faces]
+                v_src = [_host_array(v, torch.float32) for v in verts]
+                f_src = [_host_array(f, fdt) for f in faces]
                 v_host = _staging("verts", device, tv * 3, torch.float32).view(tv, 3)
                 f_host = _staging("faces", device, tf * 3, torch.int32).view(tf, 3)
                 _host_gather(v_src, v_host, 4, False)
@@ -214,6 +221,7 @@ class PackedMeshes:
         self.num_verts, self.num_faces = nv, nf
         self.total_verts, self.total_faces = sum(nv), sum(nf)
         self.max_faces = max(nf) if nf else 0
+        self.max_verts = max(nv) if nv else 0
         if v_dev.shape[0] != self.total_verts or f_dev.shape[0] != self.total_faces:
             raise ValueError("packed arrays do not match the per-mesh counts")
         voff, foff = [0], [0]
@@ -228,7 +236,10 @@ class PackedMeshes:
         if f_dev.dtype not in (torch.int32, torch.int64):
             f_dev = f_dev.to(torch.int64)
         self.faces = f_dev.contiguous()
-        offs = torch.tensor(voff + foff, dtype=torch.int32).to(device, non_blocking=True)
+        offs_h = _staging("offs", device, 2 * self.B + 2, torch.int32)
+        offs_h.copy_(torch.tensor(voff + foff, dtype=torch.int32))
+        offs = offs_h.to(device, non_blocking=True)
+        _staging_done(device)
         self.vert_off, self.face_off = offs[: self.B + 1], offs[self.B + 1:]
         flags = L.FACES_I64 if self.faces.dtype == torch.int64 else 0
         rgb = None
@@ -302,11 +313,11 @@ class _MeshRender(torch.autograd.Function):
             bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
             dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
         counters = torch.zeros(L.NUM_COUNTERS, dtype=torch.int64, device=dev)
-        ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K)
+        ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts)
         ws = workspace(dev, ws_bytes)
         with torch.cuda.device(dev):
             L.check(lib.mvr_mesh_forward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
-                                         geom.total_verts, geom.total_faces, geom.max_faces, _ptr(R), _ptr(T), _ptr(Cc),
+                                         geom.total_verts, geom.total_faces, geom.max_verts, geom.max_faces, _ptr(R), _ptr(T), _ptr(Cc),
                                          _ptr(light), light_stride, _ptr(obj_rgb), _ptr(bg_rgb), k00, k11, z_clip, H, W,
                                          K, flags, _ptr(images), _ptr(p2f), _ptr(zbuf), _ptr(bary), _ptr(dists),
                                          _ptr(counters), _ptr(ws), ws.numel(), _stream(dev)), "mvr_mesh_forward")
@@ -334,7 +345,7 @@ class _MeshRender(torch.autograd.Function):
         gR = torch.empty((N, 3, 3), dtype=torch.float32, device=dev)
         gT = torch.empty((N, 3), dtype=torch.float32, device=dev)
         gC = torch.empty((N, 3), dtype=torch.float32, device=dev)
-        ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K)
+        ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts)
         ws = workspace(dev, ws_bytes)
         gV = gN = None
         if ctx.needs_input_grad[3]:
@@ -342,7 +353,7 @@ class _MeshRender(torch.autograd.Function):
             gN = torch.zeros((geom.total_verts, 3), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             L.check(lib.mvr_mesh_backward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
-                                          geom.total_verts, geom.total_faces, _ptr(R), _ptr(T), _ptr(Cc), _ptr(light),
+                                          geom.total_verts, geom.total_faces, geom.max_verts, _ptr(R), _ptr(T), _ptr(Cc), _ptr(light),
                                           ctx.light_stride, _ptr(obj_rgb), k00, k11, H, W, K, flags, _ptr(p2f),
                                           _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gC), _ptr(gV), _ptr(gN), _ptr(ws),
                                           ws.numel(), _stream(dev)), "mvr_mesh_backward")
@@ -406,15 +417,17 @@ class _PointsRender(torch.autograd.Function):
             zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
             d2 = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
         ws = workspace(dev, lib.mvr_points_workspace_bytes(B, M, H, W, K))
+        # one bit per pixel: the backward pass skips the (typically ~90 %) background without touching idx
+        mask = torch.empty(max(lib.mvr_points_hit_mask_words(B, M, H, W), 1), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             L.check(lib.mvr_points_forward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), float(radius),
                                            _ptr(bg_rgb), H, W, K, flags, _ptr(images), _ptr(idx), _ptr(zbuf), _ptr(d2),
-                                           _ptr(ws), ws.numel(), _stream(dev)), "mvr_points_forward")
+                                           _ptr(mask), _ptr(ws), ws.numel(), _stream(dev)), "mvr_points_forward")
         ctx.set_materialize_grads(False)
         ctx.cfg = (B, Np, M, float(radius), H, W, K, flags)
         ctx.rgb_shape = rgb.shape
         ctx.points_shape = points.shape
-        ctx.save_for_backward(R, T, inv_dist, pts, rgb, idx)
+        ctx.save_for_backward(R, T, inv_dist, pts, rgb, idx, mask)
         extras = [idx] + ([zbuf, d2] if want_fragments else [])
         ctx.mark_non_differentiable(*extras)
         return (images, *extras)
@@ -424,7 +437,7 @@ class _PointsRender(torch.autograd.Function):
         lib = L.load()
         if g_images is None:
             return (None,) * 13
-        R, T, inv_dist, pts, rgb, idx = ctx.saved_tensors
+        R, T, inv_dist, pts, rgb, idx, mask = ctx.saved_tensors
         B, Np, M, radius, H, W, K, flags = ctx.cfg
         dev = pts.device
         N = B * M
@@ -438,7 +451,7 @@ class _PointsRender(torch.autograd.Function):
         ws = workspace(dev, ws_bytes)
         with torch.cuda.device(dev):
             L.check(lib.mvr_points_backward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), radius, H,
-                                            W, K, flags, _ptr(idx), _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gs),
+                                            W, K, flags, _ptr(idx), _ptr(mask), _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gs),
                                             _ptr(gP), _ptr(gF), _ptr(ws), ws.numel(), _stream(dev)),
                     "mvr_points_backward")
         if gP is not None:

@@ -37,6 +37,30 @@ def _device_vec(values, device):
     return hit
 
 
+_flag_bufs = {}
+
+
+def _flag_reader(flag_dev):
+    """Async D2H of a device int32 flag into a pinned word + an event; the returned callable waits for that event
+    only (not for work enqueued afterwards) and returns the flag."""
+    key = flag_dev.device.index
+    pool = _flag_bufs.setdefault(key, [])
+    host = pool.pop() if pool else torch.empty(1, dtype=torch.int32, pin_memory=True)
+    host.copy_(flag_dev, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(flag_dev.device))
+    state = {}
+
+    def read():
+        if "v" not in state:
+            ev.synchronize()
+            state["v"] = int(host[0])
+            pool.append(host)
+        return state["v"]
+
+    return read
+
+
 ORTHOGONAL_THRESHOLD = 1e-6   # renderer.py:29
 EXAHSTION_LIMIT = 20          # renderer.py:30 (sic)
 
@@ -95,17 +119,22 @@ class MVRenderer(nn.Module):
         return azim, elev, dist, R, T, C, bad
 
     def _render_with_guard(self, azim, elev, dist, device, render):
+        """The validity flag travels to pinned host memory right behind the look_at kernel and is awaited through an
+        event recorded BEFORE the render is enqueued: the host check of util.py:403-420 (which the reference pays as a
+        full device sync on every call) waits only for the camera kernel, never for the rasterizer."""
         azim, elev, dist, R, T, C, bad = self._cameras(azim, elev, dist, device)
+        invalid = _flag_reader(bad)
         out = render(R, T, C, dist)
         exhastion = 0
-        while int(bad.item()) != 0:       # util.py:403-420: the reference syncs here on every call
+        while invalid() != 0:
             exhastion += 1
             e2 = elev + 90.0 * torch.rand_like(elev)
             a2 = azim + 180.0 * torch.rand_like(azim)
             _, _, _, R, T, C, bad = self._cameras(a2, e2, dist, device)
-            if int(bad.item()) != 0 and exhastion > EXAHSTION_LIMIT:
+            invalid = _flag_reader(bad)
+            if invalid() != 0 and exhastion > EXAHSTION_LIMIT:
                 sys.exit("Remedy did not work")   # ops.py:163-164
-            if int(bad.item()) == 0:
+            if invalid() == 0:
                 out = render(R, T, C, dist)
         return out, R, T, C
 

@@ -35,9 +35,10 @@ def test_library_loads_and_answers_host_queries():
     assert lib.mvr_abi_version() == _lib.ABI_VERSION
     assert lib.mvr_launch_count() >= 0
     # size queries are pure host arithmetic
-    ws = lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 1)
+    ws = lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 1, 160000)
     assert 8 * 384 * 224 * 224 <= ws < 1 << 30          # one 64-bit (z, face) key per pixel and view
-    assert lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 2) >= 2 * 8 * 384 * 224 * 224   # + previous layer when peeling
+    assert ws >= 8 * 384 * 224 * 224 + 16 * 12 * 160000    # + the projected vertices of every view
+    assert lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 2, 160000) >= 2 * 8 * 384 * 224 * 224   # + previous layer when peeling
     assert lib.mvr_mesh_geometry_bytes(5000, 10000) >= 5000 * 48 + 10000 * 16
     assert lib.mvr_mesh_geometry_bytes(-1, 0) == 0
     assert lib.mvr_points_workspace_bytes(32, 12, 224, 224, 1) >= 8 * 384 * 224 * 224
@@ -46,13 +47,13 @@ def test_library_loads_and_answers_host_queries():
 def test_argument_validation_returns_status_not_crash():
     lib = _lib.load()
     # invalid arguments are rejected before any CUDA call: status < 0 and a message, never an exception/abort
-    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, 0.01, None, 0, 64, 1, 0, None, None, None, None, None, 0, None)
+    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, 0.01, None, 0, 64, 1, 0, None, None, None, None, None, None, 0, None)
     assert rc < 0 and b"image size" in lib.mvr_last_error_string()
-    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, 0.01, None, 64, 64, 200, 0, None, None, None, None, None, 0, None)
+    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, 0.01, None, 64, 64, 200, 0, None, None, None, None, None, None, 0, None)
     assert rc < 0 and b"points_per_pixel" in lib.mvr_last_error_string()
-    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, -1.0, None, 64, 64, 1, 0, None, None, None, None, None, 0, None)
+    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, -1.0, None, 64, 64, 1, 0, None, None, None, None, None, None, 0, None)
     assert rc < 0 and b"radius" in lib.mvr_last_error_string()
-    rc = lib.mvr_mesh_forward(None, None, None, 1, 1, 3, 1, 1, None, None, None, None, 0, None, None, 1.7, 1.7, 0.5, 64, 64, 1, 0,
+    rc = lib.mvr_mesh_forward(None, None, None, 1, 1, 3, 1, 3, 1, None, None, None, None, 0, None, None, 1.7, 1.7, 0.5, 64, 64, 1, 0,
                               None, None, None, None, None, None, None, 0, None)
     assert rc < 0 and b"null pointer" in lib.mvr_last_error_string()
     rc = lib.mvr_mesh_prepare(None, None, None, None, 1, 10, 10, 10, None, 0, None, 16, None)
