@@ -68,6 +68,15 @@ int mvr_host_set_threads(int n);
 int mvr_host_gather(const void* const* srcs, const int64_t* counts, int n, void* dst, int elem_bytes,
                     int narrow_i64_to_i32);
 
+/* One-call staging of a batch of meshes: gather the n vertex arrays (vert_counts[i] FLOATS each) into pinned_verts and
+ * the n face arrays (face_counts[i] INDICES each; int64 when face_elem_bytes == 8, narrowed to int32, else int32) into
+ * pinned_faces inside one parallel region, enqueueing the H2D copy of the vertices (to dev_verts, on `stream`) while the
+ * faces are still being gathered, then the faces' copy (to dev_faces).  dev_* may be NULL (gather only: no CUDA call). */
+int mvr_host_stage_meshes(const void* const* vert_srcs, const int64_t* vert_counts,
+                          const void* const* face_srcs, const int64_t* face_counts, int n,
+                          int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
+                          float* dev_verts, int32_t* dev_faces, void* stream);
+
 /* -- cameras ------------------------------------------------------------------------------ */
 /* look_at_view_transform(dist, elev, azim) + camera_position_from_spherical_angles
  * (renderer.py:79-80,122-123,168; ops.py:160) fused with util.py:403-420

@@ -282,6 +282,25 @@ __device__ __forceinline__ float point_line_dist2(float px, float py, float ax, 
 // ------------------------------------------------------------------------------------------------
 // scatter pass
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int smem_addr_pinned(const void* ptr) {
+  unsigned int a;
+  asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(ptr));
+  return a;
+}
+__device__ __forceinline__ unsigned int lanemask_lt() {
+  unsigned int m;
+  asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ float lds_f32(unsigned int a) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(unsigned int a, unsigned int v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
 // exact test of one (face, pixel) candidate and the keyed min on the global key plane
 __device__ __forceinline__ void resolve_pixel(const Face& fc, const FaceEdges& fe, int fid, unsigned int zmin_bits,
                                               bool persp, float xf, float yf, unsigned long long* key_ptr,
@@ -327,6 +346,11 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
   for (int i = tid; i < p.W + p.H; i += MVR_THREADS) s_tab[i] = __ldg(p.tab + i);
   if (tid < 2) s_cnt[tid] = 0;
   __syncthreads();
+  // shared-memory byte addresses and the lane mask, pinned in registers (volatile asm is never rematerialised: the
+  // compiler otherwise rebuilds them from SR_TID / SR_CgaCtaId inside the phase-B inner loop)
+  const unsigned int tab_a = smem_addr_pinned(s_tab);
+  const unsigned int my_cand_a = smem_addr_pinned(&s_cand[warp][0]);
+  const unsigned int lt_mask = lanemask_lt();
 
   int n_straddle = 0, n_big = 0;
   for (int rbeg = fbeg; rbeg < fend; rbeg += MVR_THREADS) {
@@ -368,11 +392,10 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
     const int n_items = min(s_cnt[0], p.item_cap);
     const int n_bigf = s_cnt[1];
     int wcnt = 0;                                // warp-uniform: candidates queued by this warp
-    const unsigned int lt_mask = (1u << lane) - 1u;
-    int* const my_cand = s_cand[warp];
     for (int j0 = warp * 32; j0 < n_items; j0 += MVR_THREADS) {      // warp-uniform trip count
       const int j = j0 + lane;
-      int slot = 0, count = 0, xl = 0, bw = 1, xi = 0, yi = 0;
+      int slot = 0, count = 0;
+      unsigned int xl_a = tab_a, xend_a = tab_a + 4u, xa = tab_a, ya = tab_a;     // shared-memory BYTE addresses
       float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f, cx = 0.f, cy = 0.f;
       if (j < n_items) {
         const int it = s_items[j];
@@ -382,39 +405,42 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
         bx = s_rec[3][slot]; by = s_rec[4][slot];
         cx = s_rec[6][slot]; cy = s_rec[7][slot];
         const int rxy = __float_as_int(s_rec[10][slot]);
-        xl = rxy & 0xffff;
-        bw = __float_as_int(s_rec[11][slot]) & 0xffff;
+        const int xl = rxy & 0xffff;
+        const int bw = __float_as_int(s_rec[11][slot]) & 0xffff;
         const int row = (int)__fdividef((float)start + 0.5f, (float)bw);     // small integers: exact
-        xi = xl + (start - row * bw);
-        yi = p.W + (rxy >> 16) + row;                                        // index of yf in s_tab
+        xl_a = tab_a + 4u * (unsigned)xl;
+        xend_a = xl_a + 4u * (unsigned)bw;
+        xa = xl_a + 4u * (unsigned)(start - row * bw);                       // address of xf of the run's first pixel
+        ya = tab_a + 4u * (unsigned)(p.W + (rxy >> 16) + row);               // address of its yf
       }
       // edge coefficients with the sign of the area folded in (negation is exact and commutes with rounding), so
       // the filter below is "all three > 0" for either winding: bit-for-bit the sign test of raster_test
       float A0 = cy - by, B0 = cx - bx, A1 = ay - cy, B1 = ax - cx, A2 = by - ay, B2 = bx - ax;
       const float area_p = ((cx - ax) * A2 - (cy - ay) * B2) + MVR_K_EPS;
       if (!(area_p > 0.f)) { A0 = -A0; B0 = -B0; A1 = -A1; B1 = -B1; A2 = -A2; B2 = -B2; }
-      const int x_end = xl + bw;
-      const int slot_m = slot - (p.W << 20);
+      // candidate word = slot | x << 8 | y << 20 with x = (xa - tab_a) / 4, y = (ya - tab_a) / 4 - W: constants folded
+      const unsigned int cand_m = (unsigned)slot - (tab_a << 6) - ((tab_a + 4u * (unsigned)p.W) << 18);
       const int maxc = __reduce_max_sync(0xffffffffu, count);
       for (int c = 0; c < maxc; ++c) {
-        const int cxi = xi, cyi = yi;
+        const unsigned int cxa = xa, cya = ya;
         bool pass = false;
         if (c < count) {
-          const float xf = s_tab[xi], yf = s_tab[yi];
+          const float xf = lds_f32(xa), yf = lds_f32(ya);
           const float e0 = (xf - bx) * A0 - (yf - by) * B0;
           const float e1 = (xf - cx) * A1 - (yf - cy) * B1;
           const float e2 = (xf - ax) * A2 - (yf - ay) * B2;
           pass = e0 > 0.f && e1 > 0.f && e2 > 0.f;
-          if (++xi == x_end) { xi = xl; ++yi; }
+          xa += 4u;
+          if (xa == xend_a) { xa = xl_a; ya += 4u; }
         }
         const unsigned int mk = __ballot_sync(0xffffffffu, pass);
         if (mk == 0u) continue;
         if (pass) {
           const int at = wcnt + __popc(mk & lt_mask);
           if (at < p.wcap) {
-            my_cand[at] = slot_m + (cxi << 8) + (cyi << 20);      // slot | x << 8 | y << 20 (slot_m = slot - (W << 20))
+            sts_u32(my_cand_a + 4u * (unsigned)at, cand_m + (cxa << 6) + (cya << 18));
           } else {                                                  // queue full: resolve in place
-            const int xx = cxi, yy = cyi - p.W;
+            const int xx = (int)((cxa - tab_a) >> 2), yy = (int)((cya - tab_a) >> 2) - p.W;
             Face fc;
             fc.x0 = ax; fc.y0 = ay; fc.z0 = s_rec[2][slot]; fc.x1 = bx; fc.y1 = by; fc.z1 = s_rec[5][slot];
             fc.x2 = cx; fc.y2 = cy; fc.z2 = s_rec[8][slot];

@@ -11,17 +11,16 @@
 //               points_resolve_kernel -- one thread per pixel: the pixel's K keys (one 32-byte sector for K = 4)
 //                 -> idx / zbuf / dists2 of every layer, norm-weighted or alpha compositing, background, planar
 //                 (n,3,H,W) rows, and one bit per pixel in a hit mask (the images are ~90 % background).
-//   backward: points_backward_kernel -- 32x32-pixel tiles; a warp reads the hit-mask word of its 32 pixels and only
-//             covered pixels touch idx / grad_images: compositor backward -> d dist2 -> d ndc.xy ->
-//             (dR, dT, d(1/dist)) block-reduced to one partial per (view, tile), summed in fixed order; optional
+//   backward: points_backward_kernel -- one warp per 32x32-pixel tile: the hit-mask words of the tile are compacted
+//             into a dense list of covered pixels (warp scan + shared memory, no block barrier) and only those touch
+//             idx / grad_images, with all lanes busy: compositor backward -> d dist2 -> d ndc.xy ->
+//             (dR, dT, d(1/dist)) warp-reduced to one partial per (view, tile), summed in fixed order; optional
 //             per-point / colour gradients via atomics.
 #include "mvr_common.cuh"
 
 namespace mvr {
 
-constexpr int PB_PIX_PER_THREAD = 4;   // backward: 32x32-pixel tiles, thread (lane, warp) owns rows warp + 8j
 constexpr int PB_VALS = 13;            // dR 9, dT 3, d inv_dist 1
-constexpr int PK_MAX_REG = 8;          // layers kept in registers by the templated kernels
 
 struct PointsParams {
   const float* points; const float* rgb;
@@ -188,51 +187,81 @@ struct PointsBwdParams {
   const float* points; const float* rgb;
   const float* R; const float* T; const float* inv_dist;
   float r2_weight;
-  int B, Np, M, H, W, K, flags, tiles_x, ctas_per_view, mask_words;
+  int B, Np, M, H, W, K, flags, tiles_x, tiles_y, ctas_per_view, mask_words;
   const int* idx; const float* grad_images; const unsigned int* hit_mask;
-  float* partials;        // (N, ctas_per_view, 8 warps, 16)
+  float* partials;        // (N, ctas_per_view, 16): one per 32x32 tile
   float* grad_points; float* grad_rgb;
 };
 
-// grid: x = 32x32-pixel tiles, y = view m, z = object b
+// grid: x = groups of 8 vertically adjacent 32x32-pixel tiles (one per warp), y = view m, z = object b.
+// The images are sparse (~10 % of the pixels are covered), so each warp first COMPACTS the covered pixels of its tile
+// -- lane r owns row r: one hit-mask word, its set bits go to a per-warp list in shared memory at the exclusive
+// prefix of the per-row counts -- and then walks the list with all 32 lanes busy.
 __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const PointsBwdParams p) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int b = blockIdx.z, n = b * p.M + blockIdx.y, cta = blockIdx.x;
-  const int tyb = cta / p.tiles_x, txb = cta - tyb * p.tiles_x;
-  const int xi = txb * 32 + lane, yi0 = tyb * 32 + (tid >> 5);
+  __shared__ unsigned short s_list[8][1024];      // row << 5 | x of every covered pixel of the warp's tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z, n = b * p.M + blockIdx.y;
+  const int tgy = blockIdx.x / p.tiles_x, txb = blockIdx.x - tgy * p.tiles_x;
+  const int tyb = tgy * 8 + warp;                    // this warp's tile row
+  const int cta = tyb * p.tiles_x + txb;             // tile index within the view (partials slot)
+  if (tyb >= p.tiles_y) return;                      // warp-uniform; there is no block barrier in this kernel
   const bool per_point_rgb = p.flags & MVR_RGB_PER_ELEMENT;
   const bool alpha_mode = p.flags & MVR_COMPOSITE_ALPHA;
   const float* pts = p.points + 3 * (size_t)b * p.Np;
   const float* feat = per_point_rgb ? p.rgb + 3 * (size_t)b * p.Np : p.rgb;
   const size_t plane = (size_t)p.H * p.W;
-  // which of this thread's pixels are covered: one broadcast mask word per warp row (or idx[.., 0] without a mask)
-  bool hits[PB_PIX_PER_THREAD];
-#pragma unroll
-  for (int j = 0; j < PB_PIX_PER_THREAD; ++j) {
-    const int yi = yi0 + 8 * j;
-    hits[j] = false;
-    if (yi < p.H) {
-      if (p.hit_mask) hits[j] = (__ldg(p.hit_mask + ((size_t)n * p.H + yi) * p.mask_words + txb) >> lane) & 1u;
-      else if (xi < p.W) hits[j] = __ldg(p.idx + ((size_t)n * plane + (size_t)yi * p.W + xi) * p.K) >= 0;
+  // ---- covered pixels of row (tile row * 32 + lane) ----
+  unsigned int word = 0u;
+  {
+    const int yi = tyb * 32 + lane;
+    if (p.hit_mask) {
+      if (yi < p.H) word = __ldg(p.hit_mask + ((size_t)n * p.H + yi) * p.mask_words + txb);
+    } else {                                         // no mask: first-layer idx >= 0, one coalesced row per step
+      const int xi = txb * 32 + lane;
+      for (int r = 0; r < 32; ++r) {
+        const int yr = tyb * 32 + r;
+        const bool h = yr < p.H && xi < p.W && __ldg(p.idx + ((size_t)n * plane + (size_t)yr * p.W + xi) * p.K) >= 0;
+        const unsigned int wr = __ballot_sync(0xffffffffu, h);
+        if (lane == r) word = wr;
+      }
     }
   }
+  int cnt = __popc(word), pre = cnt;                 // inclusive warp scan of the per-row counts
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, pre, o);
+    if (lane >= o) pre += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, pre, 31);
+  float* out = p.partials + ((size_t)n * p.ctas_per_view + cta) * 16;
+  if (total == 0) {                                  // background-only tile
+    if (lane < 16) out[lane] = 0.f;
+    return;
+  }
+  {
+    int at = pre - cnt;
+    unsigned int wv = word;
+    while (wv) {
+      const int x = __ffs(wv) - 1;
+      wv &= wv - 1u;
+      s_list[warp][at++] = (unsigned short)((lane << 5) | x);
+    }
+  }
+  __syncwarp();
   float acc[PB_VALS];
 #pragma unroll
   for (int i = 0; i < PB_VALS; ++i) acc[i] = 0.f;
-  bool any = false, ctx = false;
-  Camera cam; float s = 0.f, xf = 0.f;
+  const Camera cam = load_camera(p.R, p.T, n);
+  const float s = __ldg(p.inv_dist + n);
   const float inv_r2 = 1.f / p.r2_weight;
-#pragma unroll 1
-  for (int j = 0; j < PB_PIX_PER_THREAD; ++j) {
-    if (!hits[j]) continue;   // background pixel: masked_scatter blocks the gradient
-    const int yi = yi0 + 8 * j;
+  for (int it = lane; it < total; it += 32) {
+    const int code = s_list[warp][it];
+    const int yi = tyb * 32 + (code >> 5), xi = txb * 32 + (code & 31);
     const int* ip = p.idx + (((size_t)n * p.H + yi) * p.W + xi) * p.K;
     const size_t io = ((size_t)n * 3 * p.H + yi) * p.W + xi;
     const float g0 = __ldg(p.grad_images + io), g1 = __ldg(p.grad_images + io + plane), g2 = __ldg(p.grad_images + io + 2 * plane);
     if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
-    any = true;
-    if (!ctx) { cam = load_camera(p.R, p.T, n); s = __ldg(p.inv_dist + n); xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H); ctx = true; }
-    const float yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
+    const float xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H), yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
     // pass 1: compositor totals
     float t_alpha = 0.f, tf0 = 0.f, tf1 = 0.f, tf2 = 0.f;   // norm: sum a, sum a f ; alpha: out_c
     {
@@ -294,12 +323,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
       }
     }
   }
-  // one partial per WARP, no block barrier
-  float* out = p.partials + (((size_t)n * p.ctas_per_view + cta) * 8 + (tid >> 5)) * 16;
-  if (!__any_sync(0xffffffffu, any)) {
-    if (lane < 16) out[lane] = 0.f;
-    return;
-  }
+  // one partial per tile (= per warp), summed in fixed order by the reduce kernel
 #pragma unroll
   for (int i = 0; i < PB_VALS; ++i) acc[i] = warp_sum(acc[i]);
   float mine = 0.f;
@@ -349,7 +373,7 @@ static PointsWs points_ws(int B, int M, int H, int W, int K) {
   w.keys = 0;
   const size_t fwd = al(N * H * W * K * 8);
   w.partials = 0;                                  // the backward reuses the front of the workspace
-  const size_t bwd = al(N * w.ctas_per_view * 8 * 16 * sizeof(float));
+  const size_t bwd = al(N * w.ctas_per_view * 16 * sizeof(float));
   w.total = fwd > bwd ? fwd : bwd;
   return w;
 }
@@ -420,21 +444,21 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
     set_error("mvr_points_backward: null pointer"); return -6;
   }
   const PointsWs w = points_ws(B, M, H, W, K);
-  const size_t need = (size_t)N * w.ctas_per_view * 8 * 16 * sizeof(float);
+  const size_t need = (size_t)N * w.ctas_per_view * 16 * sizeof(float);
   if (workspace_bytes < need) { set_error("mvr_points_backward: workspace too small (%zu < %zu)", workspace_bytes, need); return -7; }
   PointsBwdParams p;
   p.points = points; p.rgb = rgb; p.R = R; p.T = T; p.inv_dist = inv_dist;
   p.r2_weight = (float)(radius * radius);
   p.B = B; p.Np = Np; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags;
-  p.tiles_x = w.tiles_x; p.ctas_per_view = w.ctas_per_view; p.mask_words = w.mask_words;
+  p.tiles_x = w.tiles_x; p.tiles_y = (H + 31) / 32; p.ctas_per_view = w.ctas_per_view; p.mask_words = w.mask_words;
   p.idx = idx; p.grad_images = grad_images; p.hit_mask = hit_mask;
   p.partials = (float*)((char*)workspace + w.partials);
   p.grad_points = grad_points; p.grad_rgb = grad_rgb;
   cudaStream_t st = (cudaStream_t)stream;
-  MVR_LAUNCH(points_backward_kernel, dim3((unsigned)w.ctas_per_view, (unsigned)M, (unsigned)B), MVR_THREADS, 0, st, p);
+  MVR_LAUNCH(points_backward_kernel, dim3((unsigned)(w.tiles_x * ((p.tiles_y + 7) / 8)), (unsigned)M, (unsigned)B), MVR_THREADS, 0, st, p);
   rc = check_launch("points_backward_kernel");
   if (rc) return rc;
   const int wpb = 8;
-  MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, w.ctas_per_view * 8, gR, gT, g_inv_dist);
+  MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, w.ctas_per_view, gR, gT, g_inv_dist);
   return check_launch("points_backward_reduce_kernel");
 }

@@ -129,3 +129,64 @@ extern "C" int mvr_host_gather(const void* const* srcs, const int64_t* counts, i
   (void)total;
   return 0;
 }
+
+// Stage a batch of meshes for the device in ONE parallel region (renderer.py:67-68 + Meshes(...) packing): gather the
+// per-mesh vertex arrays into pinned_verts, enqueue their H2D copy from one thread while the others already gather /
+// narrow the faces into pinned_faces, then enqueue the faces' copy.  HOST pointers except dev_*; faces are int64
+// (face_elem_bytes == 8, narrowed to int32 on the way) or int32.  One fork/join and the vertex copy overlapped with the
+// face gather: the step's time-to-first-kernel is bounded by this call.
+extern "C" int mvr_host_stage_meshes(const void* const* vert_srcs, const int64_t* vert_counts,
+                                     const void* const* face_srcs, const int64_t* face_counts, int n,
+                                     int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
+                                     float* dev_verts, int32_t* dev_faces, void* stream) {
+  if (n < 0 || (n > 0 && (!vert_srcs || !vert_counts || !face_srcs || !face_counts || !pinned_verts || !pinned_faces))) {
+    mvr::set_error("mvr_host_stage_meshes: null pointer"); return -1;
+  }
+  if (face_elem_bytes != 4 && face_elem_bytes != 8) { mvr::set_error("mvr_host_stage_meshes: faces must be int32 or int64"); return -2; }
+  std::vector<int64_t> voff((size_t)n + 1, 0), foff((size_t)n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    if (vert_counts[i] < 0 || face_counts[i] < 0) { mvr::set_error("mvr_host_stage_meshes: negative count"); return -3; }
+    voff[i + 1] = voff[i] + vert_counts[i];      // counts are in ELEMENTS (floats / indices)
+    foff[i + 1] = foff[i] + face_counts[i];
+  }
+  const int64_t kChunk = 1 << 14;
+  std::vector<int64_t> vwork, fwork;              // (array, start) pairs
+  for (int i = 0; i < n; ++i) for (int64_t s = 0; s < vert_counts[i]; s += kChunk) { vwork.push_back(i); vwork.push_back(s); }
+  for (int i = 0; i < n; ++i) for (int64_t s = 0; s < face_counts[i]; s += kChunk) { fwork.push_back(i); fwork.push_back(s); }
+  const int64_t nv = (int64_t)vwork.size() / 2, nf = (int64_t)fwork.size() / 2;
+  int nthreads = g_host_threads > 0 ? g_host_threads : omp_get_max_threads();
+  if (nthreads > 8) nthreads = 8;                 // memory-bound: more threads only add wake-up latency
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t err_v = cudaSuccess;
+#pragma omp parallel num_threads(nthreads)
+  {
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t w = 0; w < nv; ++w) {
+      const int i = (int)vwork[2 * w];
+      const int64_t s = vwork[2 * w + 1], cnt = std::min<int64_t>(kChunk, vert_counts[i] - s);
+      memcpy(pinned_verts + voff[i] + s, (const float*)vert_srcs[i] + s, (size_t)cnt * sizeof(float));
+    }   // implicit barrier: every vertex is staged
+#pragma omp single nowait
+    {
+      if (dev_verts && voff[n] > 0) err_v = cudaMemcpyAsync(dev_verts, pinned_verts, (size_t)voff[n] * sizeof(float), cudaMemcpyHostToDevice, st);
+    }
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t w = 0; w < nf; ++w) {
+      const int i = (int)fwork[2 * w];
+      const int64_t s = fwork[2 * w + 1], cnt = std::min<int64_t>(kChunk, face_counts[i] - s);
+      int32_t* d = pinned_faces + foff[i] + s;
+      if (face_elem_bytes == 8) {
+        const int64_t* src = (const int64_t*)face_srcs[i] + s;
+        for (int64_t e = 0; e < cnt; ++e) d[e] = (int32_t)src[e];
+      } else {
+        memcpy(d, (const int32_t*)face_srcs[i] + s, (size_t)cnt * sizeof(int32_t));
+      }
+    }
+  }
+  if (err_v != cudaSuccess) { mvr::set_error("mvr_host_stage_meshes: cudaMemcpyAsync(verts): %s", cudaGetErrorString(err_v)); return (int)err_v; }
+  if (dev_faces && foff[n] > 0) {
+    const cudaError_t e = cudaMemcpyAsync(dev_faces, pinned_faces, (size_t)foff[n] * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { mvr::set_error("mvr_host_stage_meshes: cudaMemcpyAsync(faces): %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  return 0;
+}

@@ -7,6 +7,7 @@ Operator surface (mirrors what renderer.py reaches in PyTorch3D):
     render_meshes(...)                               renderer.py:89-107 (MeshRenderer + HardPhong)
     render_points(...)                               renderer.py:129-145 (PointsRenderer + compositor)
 """
+import functools
 import math
 from typing import List, Optional, Sequence
 
@@ -91,6 +92,21 @@ def _host_gather(srcs, dst: torch.Tensor, elem_bytes: int, narrow: bool):
     L.check(L.load().mvr_host_gather(ptrs, counts, n, dst.data_ptr(), elem_bytes, 1 if narrow else 0), "mvr_host_gather")
 
 
+def _stage_meshes(v_src, f_src, face_elem_bytes, v_host, f_host, v_dev, f_dev, device):
+    """One native call: parallel gather of every mesh into the pinned buffers with the vertices' H2D copy already in
+    flight while the faces are gathered (mvr_host_stage_meshes)."""
+    import ctypes as C
+    n = len(v_src)
+    vp = (C.c_void_p * n)(*[t.data_ptr() for t in v_src])
+    vc = (C.c_int64 * n)(*[t.numel() for t in v_src])
+    fp = (C.c_void_p * n)(*[t.data_ptr() for t in f_src])
+    fc = (C.c_int64 * n)(*[t.numel() for t in f_src])
+    with torch.cuda.device(device):
+        L.check(L.load().mvr_host_stage_meshes(vp, vc, fp, fc, n, face_elem_bytes, v_host.data_ptr(), f_host.data_ptr(),
+                                               v_dev.data_ptr(), f_dev.data_ptr(), _stream(device)), "mvr_host_stage_meshes")
+
+
+@functools.lru_cache(maxsize=16)
 def fov_projection_scale(fov_deg: float = 60.0, znear: float = 1.0, aspect: float = 1.0):
     """K00, K11 of [upstream] FoVPerspectiveCameras.compute_projection_matrix, evaluated with the same
     fp32 tensor ops (fov*pi/180, tan(fov/2)*znear, 2*znear/(max-min))."""
@@ -196,12 +212,11 @@ class PackedMeshes:
                 # ONE async H2D per array
                 v_src = [_host_array(v, torch.float32) for v in verts]
                 f_src = [_host_array(f, fdt) for f in faces]
-                v_host = _staging("verts", device, tv * 3, torch.float32).view(tv, 3)
-                f_host = _staging("faces", device, tf * 3, torch.int32).view(tf, 3)
-                _host_gather(v_src, v_host, 4, False)
-                _host_gather(f_src, f_host, 8 if fdt == torch.int64 else 4, fdt == torch.int64)
-                v_dev = v_host.to(device, non_blocking=True)
-                f_dev = f_host.to(device, non_blocking=True)
+                v_host = _staging("verts", device, tv * 3, torch.float32)
+                f_host = _staging("faces", device, tf * 3, torch.int32)
+                v_dev = torch.empty((tv, 3), dtype=torch.float32, device=device)
+                f_dev = torch.empty((tf, 3), dtype=torch.int32, device=device)
+                _stage_meshes(v_src, f_src, 8 if fdt == torch.int64 else 4, v_host, f_host, v_dev, f_dev, device)
                 _staging_done(device)
         self._init_packed(v_dev, f_dev, nv, nf, device, vert_rgb)
 

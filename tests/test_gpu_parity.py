@@ -391,6 +391,68 @@ def test_points_full_size_c3_properties(oracle, cuda_device):
     assert ((idx[..., 1:] != idx[..., :-1]) | (idx[..., 1:] < 0)).all()
 
 
+def test_points_backward_without_hit_mask_matches(oracle, cuda_device):
+    """The hit mask is an optional accelerator: mvr_points_backward(hit_mask=NULL) rebuilds the covered-pixel words
+    from idx[..., 0] and must return the same partial sums bit for bit."""
+    from mvtn_b200 import _lib as L
+    dev = cuda_device
+    B, Np, M, H, W, K = 2, 700, 3, 45, 70, 3          # W not a multiple of 32, H not a multiple of 32
+    pts = synth.make_clouds(B, Np, 21).to(dev)
+    R, T, C, (Rd, Td, Cd) = cams(oracle, synth.learned_spherical_views(B, M, 11), dev)
+    inv = torch.full((B * M,), 1 / 1.5, device=dev)
+    col = torch.full((3,), 0.9, device=dev)
+    img, frag = ops.render_points(pts, col, M, Rd, Td, inv, 0.05, torch.zeros(3, device=dev), (H, W), points_per_pixel=K, compositor="alpha")
+    idx = frag["idx"]
+    g = torch.randn(B * M, 3, H, W, device=dev)
+    lib = L.load()
+    outs = []
+    nwords = lib.mvr_points_hit_mask_words(B, M, H, W)
+    assert nwords == B * M * H * ((W + 31) // 32)
+    mask = torch.zeros(nwords, dtype=torch.int32, device=dev)
+    covered = (idx[..., 0] >= 0)
+    # rebuild the mask on the host and compare it with what the forward wrote (bit x%32 of word x/32)
+    img2 = torch.empty_like(img); idx2 = torch.empty_like(idx)
+    ws = ops.workspace(dev, lib.mvr_points_workspace_bytes(B, M, H, W, K))
+    L.check(lib.mvr_points_forward(pts.data_ptr(), col.data_ptr(), B, Np, M, Rd.data_ptr(), Td.data_ptr(), inv.data_ptr(), 0.05,
+                                   torch.zeros(3, device=dev).data_ptr(), H, W, K, L.COMPOSITE_ALPHA, img2.data_ptr(), idx2.data_ptr(),
+                                   None, None, mask.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "fwd")
+    assert torch.equal(idx2, idx) and torch.equal(img2, img)
+    words = (W + 31) // 32
+    cov = torch.zeros(B * M, H, words * 32, dtype=torch.bool, device=dev); cov[:, :, :W] = covered
+    weights = (2 ** torch.arange(32, device=dev, dtype=torch.int64))
+    expect = (cov.view(B * M, H, words, 32).to(torch.int64) * weights).sum(-1)
+    got = mask.view(B * M, H, words).to(torch.int64) & 0xFFFFFFFF
+    assert torch.equal(expect, got)
+    for m_ptr in (mask.data_ptr(), None):
+        gR = torch.empty(B * M, 3, 3, device=dev); gT = torch.empty(B * M, 3, device=dev); gs = torch.empty(B * M, device=dev)
+        L.check(lib.mvr_points_backward(pts.data_ptr(), col.data_ptr(), B, Np, M, Rd.data_ptr(), Td.data_ptr(), inv.data_ptr(), 0.05, H, W, K,
+                                        L.COMPOSITE_ALPHA, idx.data_ptr(), m_ptr, g.data_ptr(), gR.data_ptr(), gT.data_ptr(), gs.data_ptr(),
+                                        None, None, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "bwd")
+        outs.append((gR, gT, gs))
+    assert all(torch.equal(a, b) for a, b in zip(*outs))
+    assert float(outs[0][0].abs().max()) > 0
+
+
+def test_mesh_fast_shading_path_matches_exact(oracle, cuda_device):
+    """fragments=False shades with two SFU reciprocals instead of six IEEE divisions: same pix_to_face, images within
+    the 1e-5 bar of the oracle and ~1e-6 of the exact path."""
+    dev = cuda_device
+    meshes = synth.make_meshes(2, 4000, 31)
+    geom = ops.PackedMeshes([v for v, _ in meshes], [f for _, f in meshes], dev)
+    M, H = 4, 96
+    R, T, C, (Rd, Td, Cd) = cams(oracle, synth.learned_spherical_views(2, M, 12), dev)
+    light = torch.tensor([[0.3, 1.0, -0.5]], device=dev); col = torch.full((3,), 0.99999, device=dev); bg = torch.tensor([0.5, 0.25, 0.75], device=dev)
+    img_e, fr_e = ops.render_meshes(geom, M, Rd, Td, Cd, light, col, bg, H, fragments=True)
+    img_f, fr_f = ops.render_meshes(geom, M, Rd, Td, Cd, light, col, bg, H, fragments=False)
+    assert torch.equal(fr_e["pix_to_face"], fr_f["pix_to_face"])
+    assert float((img_e - img_f).abs().max()) <= 2e-6
+    vp = torch.cat([v for v, _ in meshes]).numpy(); fp = torch.cat([f for _, f in meshes]).numpy().astype(np.int32)
+    voff = np.array(geom.vert_off_host, np.int32); foff = np.array(geom.face_off_host, np.int32)
+    o = oracle.mesh_forward(vp, fp, voff, foff, oracle.packed_vertex_normals(vp, fp, voff, foff), col.cpu().numpy(), M, R, T, C,
+                            light.cpu().numpy(), bg.cpu().numpy(), K00, K11, 0.5, H, H, 1, oracle.PERSPECTIVE_CORRECT, fragments=False)
+    assert np.abs(img_f.cpu().numpy() - o["images"]).max() <= IMG_ATOL
+
+
 # ------------------------------------------------------------------------------------------ public API end-to-end
 def test_mvrenderer_mesh_end_to_end(oracle, cuda_device):
     dev = cuda_device
