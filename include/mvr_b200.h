@@ -77,6 +77,16 @@ int mvr_host_stage_meshes(const void* const* vert_srcs, const int64_t* vert_coun
                           int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
                           float* dev_verts, int32_t* dev_faces, void* stream);
 
+/* Asynchronous variant: _begin hands the same work to a persistent native worker thread (which selects CUDA device
+ * `device` before enqueueing the copies) and returns a job id > 0 at once, so the caller can build the rest of the step
+ * while the meshes are staged; _end(job) waits for it and returns its status.  Every array passed to _begin must stay
+ * alive until _end returns.  One job in flight at a time (-10 otherwise). */
+int mvr_host_stage_meshes_begin(const void* const* vert_srcs, const int64_t* vert_counts,
+                                const void* const* face_srcs, const int64_t* face_counts, int n,
+                                int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
+                                float* dev_verts, int32_t* dev_faces, int device, void* stream);
+int mvr_host_stage_meshes_end(int job);
+
 /* -- cameras ------------------------------------------------------------------------------ */
 /* look_at_view_transform(dist, elev, azim) + camera_position_from_spherical_angles
  * (renderer.py:79-80,122-123,168; ops.py:160) fused with util.py:403-420

