@@ -561,8 +561,8 @@ __device__ __forceinline__ void shading_barycentrics(const Face& f, const FaceEd
 }
 
 // grid: x = 32x8-pixel tiles of the image, y = view m, z = object b.  EXACT: the caller wants zbuf / bary / dists.
-template <bool EXACT>
-__global__ void __launch_bounds__(MVR_THREADS) mesh_shade_kernel(const MeshParams p, int tiles_x) {
+template <bool EXACT, int MINB>
+__global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_shade_kernel(const MeshParams p, int tiles_x) {
   const int b = blockIdx.z, m = blockIdx.y, n = b * p.M + m;
   int ty, tx;
   tile_rc(blockIdx.x, tiles_x, ty, tx);
@@ -925,6 +925,10 @@ static int scatter_minb() {
   return v;
 }
 
+static int shade_minb() {
+  static const int v = [] { const char* e = getenv("MVR_SHADE_MINB"); const int x = e ? atoi(e) : 4; return (x == 5 || x == 6) ? x : 4; }();
+  return v;
+}
 static int backward_minb() {
   static const int v = [] { const char* e = getenv("MVR_BWD_MINB"); return (e && atoi(e) == 2) ? 2 : 3; }();
   return v;
@@ -997,8 +1001,10 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
       rc = check_launch("mesh_scatter_kernel");
       if (rc) return rc;
     }
-    if (zbuf || bary || dists) MVR_LAUNCH(mesh_shade_kernel<true>, shade_grid, MVR_THREADS, 0, st, p, tiles_x);
-    else MVR_LAUNCH(mesh_shade_kernel<false>, shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+    if (zbuf || bary || dists) MVR_LAUNCH((mesh_shade_kernel<true, 3>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+    else if (shade_minb() == 5) MVR_LAUNCH((mesh_shade_kernel<false, 5>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+    else if (shade_minb() == 6) MVR_LAUNCH((mesh_shade_kernel<false, 6>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+    else MVR_LAUNCH((mesh_shade_kernel<false, 4>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
     rc = check_launch("mesh_shade_kernel");
     if (rc) return rc;
   }

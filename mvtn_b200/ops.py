@@ -32,6 +32,8 @@ def _require_cuda(t: torch.Tensor, name: str):
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype is torch.float32 and t.is_contiguous():
+        return t.detach()
     return t.detach().to(torch.float32).contiguous()
 
 
@@ -190,6 +192,66 @@ def look_at_view_transform(dist, elev, azim, return_centers=False, return_invali
 # --------------------------------------------------------------------------------------------------
 # packed geometry
 # --------------------------------------------------------------------------------------------------
+class HostPackedMeshes:
+    """A batch of meshes packed on the HOST into pinned memory: verts (Vtot,3) f32, faces (Ftot,3) int32 (mesh-local
+    ids), per-mesh counts.  This is what a DataLoader collate_fn should hand to MVRenderer (the
+    reference's collate keeps python lists, custom_dataset.py:149-188, and re-packs them on every forward,
+    renderer.py:67-77): the packing then runs in the loader's workers, off the training step, and the step itself only
+    pays two H2D copies.  Build with collate_meshes()."""
+
+    def __init__(self, verts: torch.Tensor, faces: torch.Tensor, num_verts: Sequence[int], num_faces: Sequence[int],
+                 vert_rgb: Optional[torch.Tensor] = None):
+        if verts.dim() != 2 or verts.shape[1] != 3 or faces.dim() != 2 or faces.shape[1] != 3:
+            raise ValueError("verts must be (Vtot,3) and faces (Ftot,3)")
+        if verts.is_cuda or faces.is_cuda:
+            raise ValueError("HostPackedMeshes holds host tensors; use PackedMeshes.from_packed for device arrays")
+        if verts.dtype != torch.float32 or faces.dtype != torch.int32:
+            raise ValueError("verts must be float32 and faces int32")
+        if sum(num_verts) != verts.shape[0] or sum(num_faces) != faces.shape[0]:
+            raise ValueError("packed arrays do not match the per-mesh counts")
+        self.verts, self.faces = verts.contiguous(), faces.contiguous()
+        self.num_verts, self.num_faces = [int(x) for x in num_verts], [int(x) for x in num_faces]
+        self.vert_rgb = vert_rgb
+
+    def __len__(self):
+        return len(self.num_verts)
+
+    def verts_list(self):
+        return list(torch.split(self.verts, self.num_verts))
+
+    def faces_list(self):
+        return list(torch.split(self.faces, self.num_faces))
+
+
+def collate_meshes(meshes, pin_memory: bool = True, vert_rgb: Optional[torch.Tensor] = None) -> HostPackedMeshes:
+    """Pack a list of meshes (objects with verts_list()/faces_list(), or (verts, faces) pairs) into one pinned
+    HostPackedMeshes with the library's multi-threaded gather (int64 faces are narrowed to int32).  Host only: usable
+    inside DataLoader workers."""
+    from .structures import unpack_mesh_list
+    verts, faces = unpack_mesh_list(meshes)
+    if len(verts) != len(faces):
+        raise ValueError("verts and faces lists differ in length")
+    for v, f in zip(verts, faces):
+        if v.dim() != 2 or v.shape[1] != 3 or f.dim() != 2 or f.shape[1] != 3:
+            raise ValueError("verts must be (V,3) and faces (F,3)")
+    nv = [int(v.shape[0]) for v in verts]
+    nf = [int(f.shape[0]) for f in faces]
+    pin = bool(pin_memory) and torch.cuda.is_available()
+    v_host = torch.empty((sum(nv), 3), dtype=torch.float32, pin_memory=pin)
+    f_host = torch.empty((sum(nf), 3), dtype=torch.int32, pin_memory=pin)
+    if len(verts):
+        import ctypes as C
+        fdt = torch.int32 if all(f.dtype == torch.int32 for f in faces) else torch.int64
+        v_src = [_host_array(v, torch.float32) for v in verts]
+        f_src = [_host_array(f, fdt) for f in faces]
+        n = len(v_src)
+        vp = (C.c_void_p * n)(*[t.data_ptr() for t in v_src]); vc = (C.c_int64 * n)(*[t.numel() for t in v_src])
+        fp = (C.c_void_p * n)(*[t.data_ptr() for t in f_src]); fc = (C.c_int64 * n)(*[t.numel() for t in f_src])
+        L.check(L.load().mvr_host_stage_meshes(vp, vc, fp, fc, n, 8 if fdt == torch.int64 else 4, v_host.data_ptr(),
+                                               f_host.data_ptr(), None, None, None), "mvr_host_stage_meshes")
+    return HostPackedMeshes(v_host, f_host, nv, nf, vert_rgb=vert_rgb)
+
+
 class PackedMeshes:
     """Device-resident packed batch of meshes: float4 vertices / unit vertex normals / colours and
     int4 faces, built by mvr_mesh_prepare.  Replaces Meshes(verts, faces) + Textures(verts_rgb) +
@@ -208,16 +270,19 @@ class PackedMeshes:
 
     @classmethod
     def begin(cls, verts: Sequence[torch.Tensor], faces: Sequence[torch.Tensor], device,
-              vert_rgb: Optional[torch.Tensor] = None):
-        """Start staging host meshes on the library's worker thread and return at once; call .finish() before the
-        geometry is used.  Lets the caller overlap the gather + H2D with its own host work (MVRenderer builds the
-        cameras and output buffers meanwhile)."""
+              vert_rgb: Optional[torch.Tensor] = None, overlap: bool = False):
+        """Deferred construction: validate now, stage + build the device geometry in .finish().  MVRenderer uses it to
+        enqueue the camera kernel and build its constants BEFORE the meshes are staged, so that the rasterizer launch
+        follows mvr_mesh_prepare with as little host work in between as possible.
+        overlap=True additionally starts the gather + H2D at once on the library's worker thread
+        (mvr_host_stage_meshes_begin); on the B200 boxes measured so far the thread hand-off costs more than it hides
+        (e2e 2.07 vs 1.85 ms at BASELINE configs[1]), so it is off by default."""
         self = cls.__new__(cls)
         self._pending = None
-        self._begin(verts, faces, device, vert_rgb, overlap=True)
+        self._begin(verts, faces, device, vert_rgb, overlap=overlap, defer=not overlap)
         return self
 
-    def _begin(self, verts, faces, device, vert_rgb, overlap):
+    def _begin(self, verts, faces, device, vert_rgb, overlap, defer=False):
         device = torch.device(device)
         if device.type != "cuda":
             raise L.MVRError("PackedMeshes needs a CUDA device: mvtn_b200 has no CPU path")
@@ -226,6 +291,16 @@ class PackedMeshes:
         for v, f in zip(verts, faces):
             if v.dim() != 2 or v.shape[1] != 3 or f.dim() != 2 or f.shape[1] != 3:
                 raise ValueError("verts must be (V,3) and faces (F,3)")
+        self.B = len(verts)                   # known before finish(): MVRenderer validates against them early
+        self.per_vertex_rgb = vert_rgb is not None
+        self.device = device
+        if defer:
+            self._pending = ("deferred", list(verts), list(faces), device, vert_rgb)
+            return
+        self._pending = self._stage(verts, faces, device, vert_rgb, overlap)
+
+    @staticmethod
+    def _stage(verts, faces, device, vert_rgb, overlap):
         nv = [int(v.shape[0]) for v in verts]
         nf = [int(f.shape[0]) for f in faces]
         tv, tf = sum(nv), sum(nf)
@@ -250,23 +325,37 @@ class PackedMeshes:
                 f_dev = torch.empty((tf, 3), dtype=torch.int32, device=device)
                 job, keep = _stage_meshes(v_src, f_src, 8 if fdt == torch.int64 else 4, v_host, f_host, v_dev, f_dev, device,
                                           overlap)
-        self.B = len(nv)                      # known before finish(): MVRenderer validates against them early
-        self.per_vertex_rgb = vert_rgb is not None
-        self.device = device
-        self._pending = (v_dev, f_dev, nv, nf, device, vert_rgb, job, keep)
+        return (v_dev, f_dev, nv, nf, device, vert_rgb, job, keep)
 
     def finish(self):
-        """Join the staging job (if any) and build the packed device geometry (mvr_mesh_prepare)."""
+        """Stage (if deferred) or join the staging job (if overlapped), then build the packed device geometry
+        (mvr_mesh_prepare).  Idempotent."""
         if self._pending is None:
             return self
-        v_dev, f_dev, nv, nf, device, vert_rgb, job, keep = self._pending
-        self._pending = None
+        pending, self._pending = self._pending, None
+        if pending[0] == "deferred":
+            _, verts, faces, device, vert_rgb = pending
+            pending = self._stage(verts, faces, device, vert_rgb, overlap=False)
+        v_dev, f_dev, nv, nf, device, vert_rgb, job, keep = pending
         if job is not None:
             L.check(L.load().mvr_host_stage_meshes_end(job), "mvr_host_stage_meshes_end")
         if keep is not None:
             _staging_done(device)
         del keep
         self._init_packed(v_dev, f_dev, nv, nf, device, vert_rgb)
+        return self
+
+    @classmethod
+    def from_host_packed(cls, hp: "HostPackedMeshes", device, vert_rgb: Optional[torch.Tensor] = None):
+        """Two async H2D copies of an already packed (ideally pinned) host batch + mvr_mesh_prepare."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise L.MVRError("PackedMeshes needs a CUDA device: mvtn_b200 has no CPU path")
+        self = cls.__new__(cls)
+        v_dev = hp.verts.to(device, non_blocking=True)
+        f_dev = hp.faces.to(device, non_blocking=True)
+        self._init_packed(v_dev, f_dev, list(hp.num_verts), list(hp.num_faces), device,
+                          vert_rgb if vert_rgb is not None else hp.vert_rgb)
         return self
 
     @classmethod

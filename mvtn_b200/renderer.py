@@ -140,8 +140,9 @@ class MVRenderer(nn.Module):
 
     def render_meshes(self, meshes, color, azim, elev, dist, lights, background_color=(1.0, 1.0, 1.0)):
         device = self._device(azim)
-        # host meshes start staging on the library's worker thread now; the cameras and constants below are built while
-        # the gather + H2D run, and finish() joins right before the geometry is needed
+        # deferred: the meshes are staged (gather + H2D + mvr_mesh_prepare) inside render(), AFTER the camera kernel and
+        # the constants below have been enqueued, so that the rasterizer launch follows the geometry with as little host
+        # work in between as possible (the GPU would idle through it)
         geom = self._packed(meshes, color, device)
         if geom.B != azim.shape[0]:
             raise ValueError(f"{geom.B} meshes but azim has batch {azim.shape[0]}")
@@ -159,7 +160,7 @@ class MVRenderer(nn.Module):
         try:
             (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
         finally:
-            geom.finish()      # never leave a staging job in flight (e.g. when the camera arguments were rejected)
+            geom.finish()      # never leave a deferred / in-flight staging behind (e.g. when the cameras were rejected)
         self.last_fragments = frag
         B = geom.B
         H, W = ops._hw(self.image_size)
@@ -191,6 +192,13 @@ class MVRenderer(nn.Module):
     def _packed(self, meshes, color, device):
         if isinstance(meshes, ops.PackedMeshes):
             return meshes
+        if isinstance(meshes, ops.HostPackedMeshes):     # collated by the data loader: two H2D copies, no gather
+            color_t = torch.as_tensor(color, dtype=torch.float32)
+            vert_rgb = None
+            if color_t.numel() != 3:
+                color_t = color_t.reshape(len(meshes), -1, 3)
+                vert_rgb = torch.cat([color_t[b, :n] for b, n in enumerate(meshes.num_verts)], 0)
+            return ops.PackedMeshes.from_host_packed(meshes, device, vert_rgb=vert_rgb)
         if meshes is None:
             raise ValueError("mesh rendering (pc_rendering=False) needs `meshes`")
         if self.cache_geometry and self._geom_cache[0] is meshes:

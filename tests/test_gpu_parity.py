@@ -488,6 +488,23 @@ def test_mvrenderer_mesh_end_to_end(oracle, cuda_device):
     assert img2.shape == img.shape and float(img2.min()) >= 0 and float(img2.max()) <= 1.0 + 1e-6
 
 
+def test_mvrenderer_accepts_collated_host_batch(cuda_device):
+    """The loader-side collate (HostPackedMeshes) and the reference's python list render identically."""
+    from mvtn_b200 import collate_meshes
+    dev = cuda_device
+    meshes = [synth.make_mesh(nf, 50 + i) for i, nf in enumerate((700, 90, 2500))]
+    ml = [Meshes([v], [f]) for v, f in meshes]
+    r = MVRenderer(3, image_size=48, pc_rendering=False, light_direction="fixed").to(dev).eval()
+    az, el, di = (t.to(dev) for t in synth.learned_spherical_views(3, 3, 14))
+    img_a, _ = r(ml, None, az, el, di)
+    img_b, _ = r(collate_meshes(ml), None, az, el, di)
+    assert torch.equal(img_a, img_b)
+    a2 = az.clone().requires_grad_()
+    img_c, _ = r(collate_meshes(ml), None, a2, el, di)
+    img_c.square().mean().backward()
+    assert a2.grad is not None and torch.isfinite(a2.grad).all()
+
+
 def test_mvrenderer_points_end_to_end(oracle, cuda_device):
     dev = cuda_device
     B, M, S = 2, 4, 96

@@ -213,3 +213,20 @@ def test_async_mesh_staging_worker_matches_torch_cat():
     assert lib.mvr_host_stage_meshes(vp, vc, fp32, fc, n, 4, vd.data_ptr(), fd.data_ptr(), None, None, None) == 0
     assert torch.equal(torch.cat(f32).reshape(-1), fd)
     assert lib.mvr_host_stage_meshes(vp, vc, fp32, fc, n, 2, vd.data_ptr(), fd.data_ptr(), None, None, None) == -2
+
+
+def test_collate_meshes_packs_like_torch_cat():
+    from mvtn_b200 import HostPackedMeshes, Meshes, collate_meshes, synth
+    meshes = [synth.make_mesh(nf, 7 + i) for i, nf in enumerate((500, 80, 3000))]
+    hp = collate_meshes([Meshes([v], [f]) for v, f in meshes], pin_memory=False)
+    assert isinstance(hp, HostPackedMeshes) and len(hp) == 3
+    assert hp.num_verts == [v.shape[0] for v, _ in meshes] and hp.num_faces == [f.shape[0] for _, f in meshes]
+    assert torch.equal(hp.verts, torch.cat([v for v, _ in meshes])) and hp.faces.dtype == torch.int32
+    assert torch.equal(hp.faces, torch.cat([f for _, f in meshes]).to(torch.int32))
+    assert all(torch.equal(a, b) for a, (b, _) in zip(hp.verts_list(), meshes))
+    with pytest.raises(ValueError):
+        HostPackedMeshes(hp.verts, hp.faces, [1, 2, 3], hp.num_faces)
+    with pytest.raises(ValueError):
+        HostPackedMeshes(hp.verts, hp.faces.to(torch.int64), hp.num_verts, hp.num_faces)
+    empty = collate_meshes([], pin_memory=False)
+    assert len(empty) == 0 and empty.verts.shape == (0, 3)
