@@ -403,13 +403,20 @@ class PackedMeshes:
             flags |= L.RGB_PER_ELEMENT
         nbytes = lib.mvr_mesh_geometry_bytes(self.total_verts, self.total_faces)
         self.geometry = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        self._rgb, self._prep_flags = rgb, flags
+        self.refresh()
+
+    def refresh(self):
+        """(Re)build the packed float4 / int4 geometry and the vertex normals from self.verts / self.faces
+        (mvr_mesh_prepare): call it after updating self.verts in place.  Pure device work on the current stream."""
         if self.B == 0:
-            return
-        with torch.cuda.device(device):
-            L.check(lib.mvr_mesh_prepare(_ptr(self.verts), _ptr(self.faces), _ptr(self.vert_off), _ptr(self.face_off),
-                                         self.B, self.total_verts, self.total_faces, self.max_faces, _ptr(rgb), flags,
-                                         _ptr(self.geometry), self.geometry.numel(), _stream(device)),
-                    "mvr_mesh_prepare")
+            return self
+        with torch.cuda.device(self.device):
+            L.check(L.load().mvr_mesh_prepare(_ptr(self.verts), _ptr(self.faces), _ptr(self.vert_off), _ptr(self.face_off),
+                                              self.B, self.total_verts, self.total_faces, self.max_faces, _ptr(self._rgb),
+                                              self._prep_flags, _ptr(self.geometry), self.geometry.numel(),
+                                              _stream(self.device)), "mvr_mesh_prepare")
+        return self
 
     def faces_global(self) -> torch.Tensor:
         """(Ftot,3) int64 faces indexing the PACKED vertex array (mesh-local id + the mesh's vertex offset)."""

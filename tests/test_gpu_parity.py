@@ -505,6 +505,56 @@ def test_mvrenderer_accepts_collated_host_batch(cuda_device):
     assert a2.grad is not None and torch.isfinite(a2.grad).all()
 
 
+def test_cuda_graph_replay_matches_eager(cuda_device):
+    """mvtn_b200.graphs: the captured forward / backward graphs reproduce the eager path bit for bit, and pick up
+    in-place updates of the captured buffers (new points, moved vertices, new views)."""
+    from mvtn_b200 import graphs
+    dev = cuda_device
+    B, M, S = 3, 4, 64
+    views = [t.to(dev) for t in synth.learned_spherical_views(B, M, 17)]
+    views2 = [t.to(dev) for t in synth.learned_spherical_views(B, M, 18)]
+    cot = torch.randn(B * M, 3, S, S, device=dev)
+    col = torch.full((3,), 0.9, device=dev); bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+
+    def run(fn, vs):
+        a, e, d = (t.detach().clone().requires_grad_() for t in vs)
+        img = fn(a, e, d)
+        img.backward(cot)
+        return img.detach().clone(), a.grad.clone(), e.grad.clone(), d.grad.clone()
+
+    # ---- points
+    pts = synth.make_clouds(B, 800, 3).to(dev)
+    pts2 = synth.make_clouds(B, 800, 4).to(dev)
+
+    def eager_points(a, e, d):
+        R, T, _, _ = ops._LookAt.apply(a.reshape(-1), e.reshape(-1), d.reshape(-1))
+        return ops.render_points(pts, col, M, R, T, 1.0 / d.reshape(-1), 0.03, bg, S, points_per_pixel=4, compositor="alpha")[0]
+
+    step = graphs.graphed_points_render(pts, col, M, 0.03, bg, S, views, points_per_pixel=4, compositor="alpha")
+    for vs, newp in ((views, None), (views2, None), (views, pts2)):
+        if newp is not None:
+            pts.copy_(newp)
+        got, want = run(step, vs), run(eager_points, vs)
+        assert all(torch.equal(x, y) for x, y in zip(got, want))
+    # ---- meshes (vertex positions updated in place: prepare is part of the graph)
+    meshes = synth.make_meshes(B, 1500, 61)
+    geom = ops.PackedMeshes([v for v, _ in meshes], [f for _, f in meshes], dev)
+    light = torch.tensor([[0.2, 1.0, -0.3]], device=dev)
+
+    def eager_mesh(a, e, d):
+        geom.refresh()
+        R, T, C, _ = ops._LookAt.apply(a.reshape(-1), e.reshape(-1), d.reshape(-1))
+        return ops.render_meshes(geom, M, R, T, C, light, col, bg, S)[0]
+
+    mstep = graphs.graphed_mesh_render(geom, M, light, col, bg, S, views)
+    for vs, scale in ((views, None), (views2, None), (views, 0.8)):
+        if scale is not None:
+            geom.verts.mul_(scale)
+        got, want = run(mstep, vs), run(eager_mesh, vs)
+        assert all(torch.equal(x, y) for x, y in zip(got, want))
+    assert float(got[0].std()) > 0
+
+
 def test_mvrenderer_points_end_to_end(oracle, cuda_device):
     dev = cuda_device
     B, M, S = 2, 4, 96
