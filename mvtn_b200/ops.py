@@ -145,9 +145,8 @@ class _LookAt(torch.autograd.Function):
         if e.numel() != n or d.numel() != n:
             raise ValueError("azim, elev and dist must have the same number of elements")
         dev = a.device
-        R = torch.empty((n, 3, 3), dtype=torch.float32, device=dev)
-        T = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        Cc = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        buf = torch.empty(15 * n, dtype=torch.float32, device=dev)      # one allocation: R | T | C
+        R, T, Cc = buf[: 9 * n].view(n, 3, 3), buf[9 * n: 12 * n].view(n, 3), buf[12 * n:].view(n, 3)
         bad = torch.zeros(1, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             L.check(lib.mvr_look_at_forward(_ptr(a), _ptr(e), _ptr(d), n, _ptr(R), _ptr(T), _ptr(Cc), _ptr(bad),

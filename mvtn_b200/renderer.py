@@ -16,14 +16,21 @@ from . import ops
 from ._lib import MVRError
 from .cameras import FoVOrthographicCameras, FoVPerspectiveCameras
 from .structures import unpack_mesh_list
-from .util import torch_color
+from .util import is_cached_constant, torch_color
 
 _small_cache = {}
+_small_cache_by_id = {}
 
 
 def _device_vec(values, device):
     """Small constant vectors (colours, fixed light) are uploaded once per (device, value) and reused: a
     pageable host->device copy synchronises the stream, and the reference pays one per call."""
+    # identity fast path: the cached named colours (util.torch_color) and constant tuples come back as the same object
+    ident = (id(values), device.index) if isinstance(values, torch.Tensor) and is_cached_constant(values) else None
+    if ident is not None:
+        hit = _small_cache_by_id.get(ident)
+        if hit is not None and hit[0] is values:
+            return hit[1]
     t = torch.as_tensor(values, dtype=torch.float32).detach()
     if t.is_cuda:
         return t.to(device)
@@ -34,6 +41,10 @@ def _device_vec(values, device):
             _small_cache.clear()
         hit = t.to(device)
         _small_cache[key] = hit
+    if ident is not None and not values.requires_grad:
+        if len(_small_cache_by_id) > 256:
+            _small_cache_by_id.clear()
+        _small_cache_by_id[ident] = (values, hit)      # keeps `values` alive, so the id cannot be reused
     return hit
 
 

@@ -2,6 +2,10 @@
 import torch
 
 
+_named_color_cache = {}
+_constant_ids = set()
+
+
 def torch_color(color_type, custom_color=(1.0, 0, 0), max_lightness=False, epsilon=0.00001):
     """util.py:314-334: name -> RGB 3-vector; max_lightness divides by (max + 1e-5) ("white" = 0.99999).
     The reference's `elif color == "custom"` branch can never match a string name (it compares the
@@ -9,6 +13,9 @@ def torch_color(color_type, custom_color=(1.0, 0, 0), max_lightness=False, epsil
     names = {"white": (1.0, 1.0, 1.0), "red": (1.0, 0.0, 0.0), "green": (0.0, 1.0, 0.0),
              "blue": (0.0, 0.0, 1.0), "black": (0.0, 0.0, 0.0)}
     if color_type in names:
+        hit = _named_color_cache.get((color_type, max_lightness, epsilon))
+        if hit is not None:          # named colours are constants: built once (callers never mutate them)
+            return hit
         color = torch.tensor(names[color_type])
     elif color_type == "random":
         color = torch.rand(3)
@@ -18,7 +25,15 @@ def torch_color(color_type, custom_color=(1.0, 0, 0), max_lightness=False, epsil
         raise ValueError(f"unknown color '{color_type}'")
     if max_lightness and color_type != "black":
         color = color / (torch.max(color) + epsilon)
+    if color_type in names:
+        _named_color_cache[(color_type, max_lightness, epsilon)] = color
+        _constant_ids.add(id(color))
     return color
+
+
+def is_cached_constant(t) -> bool:
+    """True for the tensors handed out by torch_color's named-colour cache (never mutated, never freed)."""
+    return id(t) in _constant_ids
 
 
 def batch_tensor(tensor, dim=1, squeeze=False):
