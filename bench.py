@@ -178,7 +178,9 @@ def run_ours(a):
         pts_h = inp["points"].pin_memory()
         renderer = MVRenderer(M, image_size=S, pc_rendering=True, points_per_pixel=a.points_per_pixel,
                               background_color="black", compositor="alpha").to(dev)
-        kernels = ["points_scatter_kernel", "points_resolve_kernel", "points_backward_kernel"]
+        tiled = a.points_per_pixel in (1, 2, 4, 8) and os.environ.get("MVR_POINTS_TILED", "1") != "0"
+        kernels = (["points_bin_kernel", "points_tile_kernel", "points_backward_kernel"] if tiled
+                   else ["points_scatter_kernel", "points_resolve_kernel", "points_backward_kernel"])
     renderer.train()
     azim_d, elev_d, dist_d = (t.to(dev) for t in (azim_h, elev_h, dist_h))
 

@@ -147,7 +147,9 @@ int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face
                       void* stream);
 
 /* -- point clouds --------------------------------------------------------------------------- */
-size_t mvr_points_workspace_bytes(int B, int M, int H, int W, int K);
+/* scratch for one forward or backward call (forward: pixel table + per-view projected points, tile lists, or for K not
+ * in {1,2,4,8} a K-slot key plane; backward: per-tile partial sums) */
+size_t mvr_points_workspace_bytes(int B, int Np, int M, int H, int W, int K, double radius);
 /* number of uint32 words of the optional hit mask: (n, H, ceil(W/32)), bit x%32 of word x/32 = pixel (y, x) is
  * covered by at least one point */
 size_t mvr_points_hit_mask_words(int B, int M, int H, int W);

@@ -16,6 +16,8 @@
 //             idx / grad_images, with all lanes busy: compositor backward -> d dist2 -> d ndc.xy ->
 //             (dR, dT, d(1/dist)) warp-reduced to one partial per (view, tile), summed in fixed order; optional
 //             per-point / colour gradients via atomics.
+#include <cstdlib>
+
 #include "mvr_common.cuh"
 
 namespace mvr {
@@ -29,6 +31,9 @@ struct PointsParams {
   int B, Np, M, H, W, K, flags, mask_words;
   unsigned long long* keys;      // (n, H*W, K): the K smallest (z, point) keys of every pixel, ascending
   const float* tab;              // pixel-centre NDC coordinates: xf[W] then yf[H]
+  // tiled path (K in {1,2,4,8}): per-(view, point) projection + pixel window, per-(view, tile) point lists
+  float4* pp; int2* pw; int* tile_cnt; int* tile_off; int* tile_cur; int* list;
+  int tiles_x, tiles_y, ntiles, list_cap;
   float* images; int* idx; float* zbuf; float* dists2; unsigned int* hit_mask;
 };
 
@@ -112,41 +117,22 @@ __global__ void __launch_bounds__(MVR_THREADS) points_scatter_kernel(const Point
   }
 }
 
-// grid: x = 32x8-pixel tiles, y = view m, z = object b.  KT = K when K <= PK_MAX_REG (keys in registers), 0 = generic
+// Everything that happens to ONE pixel once its K ascending keys are known: hit-mask bit (warp ballot: call with all
+// 32 lanes, lane = x within a 32-pixel row word `mask_word`), idx / zbuf / dists2 of every layer, norm-weighted or alpha
+// compositing, background, planar image stores.  kreg: the keys in registers (KT > 0) or kp: their address (KT == 0).
 template <int KT>
-__global__ void __launch_bounds__(MVR_THREADS) points_resolve_kernel(const PointsParams p, int tiles_x) {
-  const int b = blockIdx.z, n = b * p.M + blockIdx.y;
-  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-  const int xi = tx * 32 + (threadIdx.x & 31), yi = ty * 8 + (threadIdx.x >> 5);
+__device__ __forceinline__ void composite_and_store(const PointsParams& p, const unsigned long long* kreg,
+                                                    const unsigned long long* kp, int b, int n, int xi, int yi,
+                                                    int mask_word, bool inside) {
   const int K = KT > 0 ? KT : p.K;
-  const bool inside = xi < p.W && yi < p.H;
   const size_t HW = (size_t)p.H * p.W;
   const size_t pix = (size_t)yi * p.W + xi;
   const size_t po = ((size_t)n * HW + pix) * K;
-  const unsigned long long* kp = p.keys + po;
-  // ---- the pixel's keys: ascending, EMPTY-padded ----
-  unsigned long long key0 = MVR_EMPTY_KEY;
-  unsigned long long kreg[KT > 0 ? KT : 1];
-  if (inside) {
-    if (KT == 0) {
-      key0 = kp[0];
-    } else if (KT % 2 == 0) {
-#pragma unroll
-      for (int l = 0; l < KT; l += 2) {
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(kp + l);
-        kreg[l] = v.x; kreg[l + 1] = v.y;
-      }
-      key0 = kreg[0];
-    } else {
-#pragma unroll
-      for (int l = 0; l < KT; ++l) kreg[l] = kp[l];
-      key0 = kreg[0];
-    }
-  }
+  const unsigned long long key0 = inside ? (KT > 0 ? kreg[0] : kp[0]) : MVR_EMPTY_KEY;
   const bool hit = key0 != MVR_EMPTY_KEY;      // first-layer hit decides foreground ([upstream] _add_background_color_to_images)
   if (p.hit_mask) {
     const unsigned int mword = __ballot_sync(0xffffffffu, hit);
-    if ((threadIdx.x & 31) == 0 && yi < p.H) p.hit_mask[((size_t)n * p.H + yi) * p.mask_words + tx] = mword;
+    if ((threadIdx.x & 31) == 0 && yi < p.H) p.hit_mask[((size_t)n * p.H + yi) * p.mask_words + mask_word] = mword;
   }
   if (!inside) return;
   float o0 = __ldg(p.bg_rgb), o1 = __ldg(p.bg_rgb + 1), o2 = __ldg(p.bg_rgb + 2);
@@ -210,6 +196,188 @@ __global__ void __launch_bounds__(MVR_THREADS) points_resolve_kernel(const Point
   }
   const size_t io = (size_t)n * 3 * HW + pix;
   p.images[io] = o0; p.images[io + HW] = o1; p.images[io + 2 * HW] = o2;
+}
+
+// grid: x = 32x8-pixel tiles, y = view m, z = object b.  KT = K when K <= PK_MAX_REG (keys in registers), 0 = generic
+template <int KT>
+__global__ void __launch_bounds__(MVR_THREADS) points_resolve_kernel(const PointsParams p, int tiles_x) {
+  const int b = blockIdx.z, n = b * p.M + blockIdx.y;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int xi = tx * 32 + (threadIdx.x & 31), yi = ty * 8 + (threadIdx.x >> 5);
+  const int K = KT > 0 ? KT : p.K;
+  const bool inside = xi < p.W && yi < p.H;
+  const size_t HW = (size_t)p.H * p.W;
+  const size_t pix = (size_t)yi * p.W + xi;
+  const size_t po = ((size_t)n * HW + pix) * K;
+  const unsigned long long* kp = p.keys + po;
+  // ---- the pixel's keys: ascending, EMPTY-padded ----
+  unsigned long long kreg[KT > 0 ? KT : 1];
+  kreg[0] = MVR_EMPTY_KEY;
+  if (inside) {
+    if (KT == 0) {
+    } else if (KT % 2 == 0) {
+#pragma unroll
+      for (int l = 0; l < KT; l += 2) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(kp + l);
+        kreg[l] = v.x; kreg[l + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int l = 0; l < KT; ++l) kreg[l] = kp[l];
+    }
+  }
+  composite_and_store<KT>(p, kreg, kp, b, n, xi, yi, tx, inside);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiled forward (K in {1, 2, 4, 8}): bin the points of every view into 32x32-pixel tiles, then ONE CTA per
+// (view, tile) keeps the tile's K-slot key planes in shared memory, inserts its points with shared-memory atomics and
+// writes idx / zbuf / dists2 / image / hit mask directly -- no global key plane, no memset, no global atomics.
+// ------------------------------------------------------------------------------------------------
+constexpr int PT_QCAP = 2048;      // (point, pixel) candidates queued per round
+
+// grid: x = blocks of 256 points, y = view m, z = object b.  FILL = false: project, window, count per tile;
+// FILL = true: append the point to the lists of the tiles its window touches.
+template <bool FILL>
+__global__ void __launch_bounds__(MVR_THREADS) points_bin_kernel(const PointsParams p) {
+  const int b = blockIdx.z, n = b * p.M + blockIdx.y;
+  const int pi = blockIdx.x * MVR_THREADS + threadIdx.x;
+  if (pi >= p.Np) return;
+  const size_t o = (size_t)n * p.Np + pi;
+  int xl, xh, yl, yh;
+  if (!FILL) {
+    const Camera cam = load_camera(p.R, p.T, n);
+    const float s = __ldg(p.inv_dist + n);
+    float px, py, pz;
+    project_point(p.points + 3 * (size_t)b * p.Np, pi, s, cam, px, py, pz);
+    xl = 1; xh = 0; yl = 1; yh = 0;                       // empty window
+    if (!(pz < 0.f)) {
+      // conservative search window for candidate pixel centres (the exact test is dist2 < r2 in the tile kernel)
+      const float rr = p.radius * 1.0001f + 1e-7f;
+      pixel_range(py - rr, py + rr, p.H, p.W, 0, p.H - 1, p.tab + p.W, yl, yh);
+      if (yl <= yh) pixel_range(px - rr, px + rr, p.W, p.H, 0, p.W - 1, p.tab, xl, xh);
+      if (yl > yh || xl > xh) { xl = 1; xh = 0; yl = 1; yh = 0; }
+    }
+    p.pp[o] = make_float4(px, py, pz, 0.f);
+    p.pw[o] = make_int2(xl | (xh << 16), yl | (yh << 16));
+  } else {
+    const int2 w = p.pw[o];
+    xl = w.x & 0xffff; xh = w.x >> 16; yl = w.y & 0xffff; yh = w.y >> 16;
+  }
+  if (xl > xh) return;
+  int* cnt = (FILL ? p.tile_cur : p.tile_cnt) + (size_t)n * p.ntiles;
+  for (int ty = yl >> 5; ty <= (yh >> 5); ++ty)
+    for (int tx = xl >> 5; tx <= (xh >> 5); ++tx) {
+      const int at = atomicAdd(cnt + ty * p.tiles_x + tx, 1);
+      if (FILL && at < p.list_cap) p.list[(size_t)n * p.list_cap + at] = pi;      // at < list_cap by construction
+    }
+}
+
+// one CTA per view: exclusive scan of the per-tile counts -> list offsets (tile_off) and fill cursors (tile_cur)
+__global__ void __launch_bounds__(MVR_THREADS) points_bin_scan_kernel(const PointsParams p) {
+  __shared__ int s_part[MVR_THREADS];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const int per = (p.ntiles + MVR_THREADS - 1) / MVR_THREADS;
+  const int beg = min(tid * per, p.ntiles), end = min(beg + per, p.ntiles);
+  const int* cnt = p.tile_cnt + (size_t)n * p.ntiles;
+  int sum = 0;
+  for (int t = beg; t < end; ++t) sum += cnt[t];
+  s_part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int i = 0; i < MVR_THREADS; ++i) { const int v = s_part[i]; s_part[i] = acc; acc += v; }
+  }
+  __syncthreads();
+  int acc = s_part[tid];
+  for (int t = beg; t < end; ++t) {
+    p.tile_off[(size_t)n * p.ntiles + t] = acc;
+    p.tile_cur[(size_t)n * p.ntiles + t] = acc;
+    acc += cnt[t];
+  }
+}
+
+// slot-major shared key planes: slot k of local pixel q at s_keys[k * 1024 + q]
+template <int KT>
+__device__ __forceinline__ void insert_key_smem(unsigned long long* s_keys, int q, unsigned long long key) {
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    unsigned long long* slot = s_keys + k * 1024 + q;
+    if (key >= *(volatile unsigned long long*)slot) continue;      // keys never grow: a stale snapshot is conservative
+    const unsigned long long old = atomicMin(slot, key);
+    key = old > key ? old : key;
+    if (key == MVR_EMPTY_KEY) break;
+  }
+}
+
+// grid: x = tile (ty * tiles_x + tx), y = view m, z = object b; dynamic shared memory: KT * 1024 keys
+template <int KT>
+__global__ void __launch_bounds__(MVR_THREADS) points_tile_kernel(const PointsParams p) {
+  extern __shared__ unsigned long long s_keys[];              // [KT][1024]
+  __shared__ unsigned int s_cand[PT_QCAP];                    // local point << 10 | local pixel
+  __shared__ unsigned long long s_key[MVR_THREADS];
+  __shared__ int s_n;
+  const int b = blockIdx.z, n = b * p.M + blockIdx.y, t = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int ty, tx;
+  { ty = (int)__fdividef((float)t + 0.5f, (float)p.tiles_x); tx = t - ty * p.tiles_x; }
+  const int x0 = tx * 32, y0 = ty * 32;
+  const int beg = p.Np > 0 ? p.tile_off[(size_t)n * p.ntiles + t] : 0;
+  const int end = p.Np > 0 ? min(p.tile_cur[(size_t)n * p.ntiles + t], p.list_cap) : 0;
+  if (beg < end) {                                            // block-uniform
+    for (int i = tid; i < KT * 1024; i += MVR_THREADS) s_keys[i] = MVR_EMPTY_KEY;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const float* tabx = p.tab;
+    const float* taby = p.tab + p.W;
+    for (int base = beg; base < end; base += MVR_THREADS) {
+      // phase 1: thread per point -- pixel centres of the window (clipped to this tile) inside the radius
+      const int i = base + tid;
+      if (i < end) {
+        const int pi = p.list[(size_t)n * p.list_cap + i];
+        const size_t o = (size_t)n * p.Np + pi;
+        const float4 P = p.pp[o];
+        const int2 w = p.pw[o];
+        const int xl = max(w.x & 0xffff, x0), xh = min(w.x >> 16, x0 + 31);
+        const int yl = max(w.y & 0xffff, y0), yh = min(w.y >> 16, y0 + 31);
+        const unsigned long long key = make_key(P.z, pi);
+        s_key[tid] = key;
+        for (int yy = yl; yy <= yh; ++yy) {
+          const float dy = P.y - __ldg(taby + yy);
+          for (int xx = xl; xx <= xh; ++xx) {
+            const float dx = P.x - __ldg(tabx + xx);
+            const float d2 = dx * dx + dy * dy;
+            if (!(d2 < p.r2_raster)) continue;
+            const int q = ((yy - y0) << 5) | (xx - x0);
+            const int at = atomicAdd(&s_n, 1);
+            if (at < PT_QCAP) s_cand[at] = ((unsigned int)tid << 10) | (unsigned int)q;
+            else insert_key_smem<KT>(s_keys, q, key);          // queue full: insert in place
+          }
+        }
+      }
+      __syncthreads();
+      // phase 2: thread per queued fragment -- all lanes busy in the atomic chain
+      const int nc = min(s_n, PT_QCAP);
+      for (int c = tid; c < nc; c += MVR_THREADS) {
+        const unsigned int cd = s_cand[c];
+        insert_key_smem<KT>(s_keys, cd & 1023, s_key[cd >> 10]);
+      }
+      __syncthreads();
+      if (tid == 0) s_n = 0;
+      __syncthreads();
+    }
+  }
+  // resolve: thread (lane, warp) owns pixels (x0 + lane, y0 + warp + 8 j)
+#pragma unroll 1
+  for (int j = 0; j < 4; ++j) {
+    const int row = warp + 8 * j;
+    const int xi = x0 + lane, yi = y0 + row;
+    const bool inside = xi < p.W && yi < p.H;
+    unsigned long long kreg[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) kreg[k] = (beg < end) ? s_keys[k * 1024 + (row << 5) + lane] : MVR_EMPTY_KEY;
+    composite_and_store<KT>(p, kreg, nullptr, b, n, xi, yi, tx, inside);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -390,28 +558,56 @@ static int check_points_common(const char* who, int B, int Np, int M, int H, int
 }
 
 struct PointsWs {
-  size_t keys, tab, partials, total;
-  int tiles_x, ctas_per_view, mask_words;
+  size_t keys, tab, pp, pw, tile_cnt, tile_off, tile_cur, list, partials, total;
+  int tiles_x, tiles_y, ntiles, list_cap, ctas_per_view, mask_words;
+  bool tiled;
 };
-static PointsWs points_ws(int B, int M, int H, int W, int K) {
+static bool points_use_tiles(int K) {
+  static const bool off = [] { const char* e = getenv("MVR_POINTS_TILED"); return e && atoi(e) == 0; }();   // profiling knob
+  return !off && (K == 1 || K == 2 || K == 4 || K == 8);
+}
+static PointsWs points_ws(int B, int Np, int M, int H, int W, int K, double radius) {
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   PointsWs w;
   const size_t N = (size_t)B * M;
   w.tiles_x = (W + 31) / 32;
-  w.ctas_per_view = w.tiles_x * ((H + 31) / 32);
+  w.tiles_y = (H + 31) / 32;
+  w.ntiles = w.tiles_x * w.tiles_y;
+  w.ctas_per_view = w.ntiles;
   w.mask_words = w.tiles_x;
-  w.keys = 0;
-  w.tab = al(N * H * W * K * 8);
-  const size_t fwd = al(w.tab + ((size_t)W + H) * sizeof(float));
+  w.tiled = points_use_tiles(K);
+  // a window of wpx consecutive pixels touches at most (wpx - 1) / 32 + 2 tiles per axis; the window holds the pixel
+  // centres within +-rr of the point, at most floor(2 rr / pitch) + 1 with pitch >= 2 / max(H, W)
+  const double rr = radius * 1.0001 + 1e-7;
+  const long long wpx = (long long)(rr * (H > W ? H : W)) + 2;
+  long long span = (wpx - 1) / 32 + 2;
+  if (span > w.tiles_x && span > w.tiles_y) span = w.tiles_x > w.tiles_y ? w.tiles_x : w.tiles_y;
+  const long long sx = span < w.tiles_x ? span : w.tiles_x, sy = span < w.tiles_y ? span : w.tiles_y;
+  const long long cap = (long long)Np * sx * sy;
+  w.list_cap = cap > 0x7fffffffLL ? 0x7fffffff : (int)cap;
+  size_t o = 0;
+  w.tab = o; o = al(o + ((size_t)W + H) * sizeof(float));
+  w.keys = w.pp = w.pw = w.tile_cnt = w.tile_off = w.tile_cur = w.list = o;
+  if (w.tiled) {
+    w.pp = o; o = al(o + N * Np * sizeof(float4));
+    w.pw = o; o = al(o + N * Np * sizeof(int2));
+    w.tile_cnt = o; o = al(o + N * w.ntiles * sizeof(int));
+    w.tile_off = o; o = al(o + N * w.ntiles * sizeof(int));
+    w.tile_cur = o; o = al(o + N * w.ntiles * sizeof(int));
+    w.list = o; o = al(o + N * (size_t)w.list_cap * sizeof(int));
+  } else {
+    w.keys = o; o = al(o + N * H * W * K * 8);
+  }
+  const size_t fwd = o;
   w.partials = 0;                                  // the backward reuses the front of the workspace
   const size_t bwd = al(N * w.ctas_per_view * 16 * sizeof(float));
   w.total = fwd > bwd ? fwd : bwd;
   return w;
 }
 
-extern "C" size_t mvr_points_workspace_bytes(int B, int M, int H, int W, int K) {
-  if (B < 0 || M < 0 || H <= 0 || W <= 0 || K < 1) return 0;
-  return points_ws(B, M, H, W, K).total;
+extern "C" size_t mvr_points_workspace_bytes(int B, int Np, int M, int H, int W, int K, double radius) {
+  if (B < 0 || Np < 0 || M < 0 || H <= 0 || W <= 0 || K < 1 || !(radius > 0.0)) return 0;
+  return points_ws(B, Np, M, H, W, K, radius).total;
 }
 
 extern "C" size_t mvr_points_hit_mask_words(int B, int M, int H, int W) {
@@ -429,28 +625,61 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
   const int64_t N = (int64_t)B * M;
   if (N == 0) return 0;
   if ((Np > 0 && !points) || !rgb || !R || !T || !inv_dist || !bg_rgb || !images || !idx || !workspace) { set_error("mvr_points_forward: null pointer"); return -6; }
-  const PointsWs w = points_ws(B, M, H, W, K);
+  const PointsWs w = points_ws(B, Np, M, H, W, K, radius);
   const size_t HW = (size_t)H * W;
-  const size_t need = (size_t)N * HW * K * 8;
   if (workspace_bytes < w.total) { set_error("mvr_points_forward: workspace too small (%zu < %zu)", workspace_bytes, w.total); return -7; }
+  if (w.tiled && (long long)Np * 1 > 0 && (long long)w.list_cap >= 0x7fffffffLL) { set_error("mvr_points_forward: point lists too large"); return -8; }
+  char* wb = (char*)workspace;
   PointsParams p;
   p.points = points; p.rgb = rgb; p.R = R; p.T = T; p.inv_dist = inv_dist; p.bg_rgb = bg_rgb;
   p.radius = (float)radius;
   p.r2_raster = p.radius * p.radius;            // [upstream] rasterize_points_cpu.cpp: float radius * radius
   p.r2_weight = (float)(radius * radius);       // [upstream] points/renderer.py: python-float r * r
   p.B = B; p.Np = Np; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags; p.mask_words = w.mask_words;
-  p.keys = (unsigned long long*)((char*)workspace + w.keys);
-  p.tab = (const float*)((char*)workspace + w.tab);
+  p.keys = (unsigned long long*)(wb + w.keys);
+  p.tab = (const float*)(wb + w.tab);
+  p.pp = (float4*)(wb + w.pp); p.pw = (int2*)(wb + w.pw);
+  p.tile_cnt = (int*)(wb + w.tile_cnt); p.tile_off = (int*)(wb + w.tile_off); p.tile_cur = (int*)(wb + w.tile_cur);
+  p.list = (int*)(wb + w.list);
+  p.tiles_x = w.tiles_x; p.tiles_y = w.tiles_y; p.ntiles = w.ntiles; p.list_cap = w.list_cap;
   p.images = images; p.idx = idx; p.zbuf = zbuf; p.dists2 = dists2; p.hit_mask = hit_mask;
   cudaStream_t st = (cudaStream_t)stream;
+  const dim3 point_grid((unsigned)((Np + MVR_THREADS - 1) / MVR_THREADS), (unsigned)M, (unsigned)B);
+  if (Np > 0) MVR_LAUNCH(pixel_table_kernel, 1, MVR_THREADS, 0, st, (float*)(wb + w.tab), H, W);
+  if (w.tiled) {
+    if (Np > 0) {
+      cudaError_t e = cudaMemsetAsync(p.tile_cnt, 0, (size_t)N * w.ntiles * sizeof(int), st);
+      if (e != cudaSuccess) { set_error("mvr_points_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+      MVR_LAUNCH(points_bin_kernel<false>, point_grid, MVR_THREADS, 0, st, p);
+      MVR_LAUNCH(points_bin_scan_kernel, (unsigned)N, MVR_THREADS, 0, st, p);
+      MVR_LAUNCH(points_bin_kernel<true>, point_grid, MVR_THREADS, 0, st, p);
+      rc = check_launch("points_bin_kernel");
+      if (rc) return rc;
+    }
+    const dim3 tile_grid((unsigned)w.ntiles, (unsigned)M, (unsigned)B);
+    const size_t smem = (size_t)K * 1024 * sizeof(unsigned long long);
+    cudaError_t e = cudaSuccess;
+    switch (K) {
+      case 1: MVR_LAUNCH(points_tile_kernel<1>, tile_grid, MVR_THREADS, smem, st, p); break;
+      case 2: MVR_LAUNCH(points_tile_kernel<2>, tile_grid, MVR_THREADS, smem, st, p); break;
+      case 4: MVR_LAUNCH(points_tile_kernel<4>, tile_grid, MVR_THREADS, smem, st, p); break;
+      default: {
+        // 64 KB of dynamic shared memory needs the opt-in (per device; the call is a few hundred nanoseconds)
+        e = cudaFuncSetAttribute(points_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("mvr_points_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        MVR_LAUNCH(points_tile_kernel<8>, tile_grid, MVR_THREADS, smem, st, p);
+      }
+    }
+    return check_launch("points_tile_kernel");
+  }
+  // ---- generic K: global key plane (memset + scatter with global atomics + resolve) ----
+  const size_t need = (size_t)N * HW * K * 8;
   cudaError_t e = cudaMemsetAsync(p.keys, 0xFF, need, st);      // every key = EMPTY
   if (e != cudaSuccess) { set_error("mvr_points_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
   const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
-  const dim3 scatter_grid((unsigned)((Np + MVR_THREADS - 1) / MVR_THREADS), (unsigned)M, (unsigned)B);
   const dim3 resolve_grid((unsigned)(tiles_x * tiles_y), (unsigned)M, (unsigned)B);
   if (Np > 0) {
-    MVR_LAUNCH(pixel_table_kernel, 1, MVR_THREADS, 0, st, (float*)((char*)workspace + w.tab), H, W);
-    MVR_LAUNCH(points_scatter_kernel, scatter_grid, MVR_THREADS, 0, st, p);
+    MVR_LAUNCH(points_scatter_kernel, point_grid, MVR_THREADS, 0, st, p);
     rc = check_launch("points_scatter_kernel");
     if (rc) return rc;
   }
@@ -476,7 +705,7 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
   if ((Np > 0 && !points) || !rgb || !R || !T || !inv_dist || !idx || !grad_images || !gR || !gT || !g_inv_dist || !workspace) {
     set_error("mvr_points_backward: null pointer"); return -6;
   }
-  const PointsWs w = points_ws(B, M, H, W, K);
+  const PointsWs w = points_ws(B, Np, M, H, W, K, radius);
   const size_t need = (size_t)N * w.ctas_per_view * 16 * sizeof(float);
   if (workspace_bytes < need) { set_error("mvr_points_backward: workspace too small (%zu < %zu)", workspace_bytes, need); return -7; }
   PointsBwdParams p;

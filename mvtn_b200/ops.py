@@ -575,7 +575,7 @@ class _PointsRender(torch.autograd.Function):
         if want_fragments:
             zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
             d2 = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
-        ws = workspace(dev, lib.mvr_points_workspace_bytes(B, M, H, W, K))
+        ws = workspace(dev, lib.mvr_points_workspace_bytes(B, Np, M, H, W, K, float(radius)))
         # one bit per pixel: the backward pass skips the (typically ~90 %) background without touching idx
         mask = torch.empty(max(lib.mvr_points_hit_mask_words(B, M, H, W), 1), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
@@ -606,7 +606,7 @@ class _PointsRender(torch.autograd.Function):
         gs = torch.empty(N, dtype=torch.float32, device=dev)
         gP = torch.zeros_like(pts) if ctx.needs_input_grad[3] else None
         gF = torch.zeros_like(rgb) if ctx.needs_input_grad[4] else None
-        ws_bytes = lib.mvr_points_workspace_bytes(B, M, H, W, K)
+        ws_bytes = lib.mvr_points_workspace_bytes(B, Np, M, H, W, K, float(radius))
         ws = workspace(dev, ws_bytes)
         with torch.cuda.device(dev):
             L.check(lib.mvr_points_backward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), radius, H,

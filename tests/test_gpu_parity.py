@@ -391,6 +391,25 @@ def test_points_full_size_c3_properties(oracle, cuda_device):
     assert ((idx[..., 1:] != idx[..., :-1]) | (idx[..., 1:] < 0)).all()
 
 
+def test_points_empty_cloud_and_tile_edges(oracle, cuda_device):
+    """Zero points render pure background (tiled path with empty lists); a cloud concentrated on tile borders
+    (x, y = multiples of 32 pixels) exercises points whose window straddles 2 or 4 tiles."""
+    dev = cuda_device
+    bg = torch.tensor([0.3, 0.6, 0.9], device=dev); col = torch.full((3,), 0.8, device=dev)
+    R, T, C, (Rd, Td, Cd) = cams(oracle, (torch.tensor([[0.0, 40.0]]), torch.tensor([[0.0, 10.0]]), torch.tensor([[2.0, 2.0]])), dev)
+    inv = torch.full((2,), 0.5, device=dev)
+    img, fr = ops.render_points(torch.zeros(1, 0, 3, device=dev), col, 2, Rd, Td, inv, 0.02, bg, 70, points_per_pixel=4, compositor="alpha")
+    assert (fr["idx"] == -1).all() and torch.allclose(img[0, :, 5, 5], bg)
+    # points on a lattice whose projections fall near tile borders of a 96x96 image (3x3 tiles), large radius
+    g = torch.linspace(-0.9, 0.9, 19)
+    pts = torch.stack(torch.meshgrid(g, g, indexing="ij"), -1).reshape(1, -1, 2)
+    pts = torch.cat([pts, 0.05 * torch.randn(1, pts.shape[1], 1, generator=torch.Generator().manual_seed(2))], -1)
+    cfg = dict(B=1, Np=pts.shape[1], M=2, H=96, K=4, radius=0.09, mode="alpha",
+               views=(torch.tensor([[0.0, 3.0]]), torch.tensor([[0.0, 2.0]]), torch.tensor([[2.0, 2.0]])))
+    res = run_points(oracle, dev, cfg, pts=pts)
+    assert (res["idx"][..., 3] >= 0).sum() > 100          # deep layers are populated across tile borders
+
+
 def test_points_backward_without_hit_mask_matches(oracle, cuda_device):
     """The hit mask is an optional accelerator: mvr_points_backward(hit_mask=NULL) rebuilds the covered-pixel words
     from idx[..., 0] and must return the same partial sums bit for bit."""
@@ -412,7 +431,7 @@ def test_points_backward_without_hit_mask_matches(oracle, cuda_device):
     covered = (idx[..., 0] >= 0)
     # rebuild the mask on the host and compare it with what the forward wrote (bit x%32 of word x/32)
     img2 = torch.empty_like(img); idx2 = torch.empty_like(idx)
-    ws = ops.workspace(dev, lib.mvr_points_workspace_bytes(B, M, H, W, K))
+    ws = ops.workspace(dev, lib.mvr_points_workspace_bytes(B, Np, M, H, W, K, 0.05))
     L.check(lib.mvr_points_forward(pts.data_ptr(), col.data_ptr(), B, Np, M, Rd.data_ptr(), Td.data_ptr(), inv.data_ptr(), 0.05,
                                    torch.zeros(3, device=dev).data_ptr(), H, W, K, L.COMPOSITE_ALPHA, img2.data_ptr(), idx2.data_ptr(),
                                    None, None, mask.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "fwd")

@@ -41,7 +41,7 @@ def test_library_loads_and_answers_host_queries():
     assert lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 2, 160000) >= 2 * 8 * 384 * 224 * 224   # + previous layer when peeling
     assert lib.mvr_mesh_geometry_bytes(5000, 10000) >= 5000 * 48 + 10000 * 16
     assert lib.mvr_mesh_geometry_bytes(-1, 0) == 0
-    assert lib.mvr_points_workspace_bytes(32, 12, 224, 224, 1) >= 8 * 384 * 224 * 224
+    assert lib.mvr_points_workspace_bytes(32, 2048, 12, 224, 224, 3, 0.006) >= 3 * 8 * 384 * 224 * 224   # generic K: key plane
 
 
 def test_argument_validation_returns_status_not_crash():
