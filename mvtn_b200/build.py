@@ -12,12 +12,14 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmvr_b200.so")
-SOURCES = ["mvr_util.cu", "mvr_camera.cu", "mvr_mesh.cu", "mvr_points.cu"]
+# source -> allow FMA contraction?  The forward units decide fragments and keep the written IEEE operation order
+# (-fmad=false); mvr_mesh_bwd.cu only produces tolerance-compared gradients from inputs that are exact by construction
+# (intrinsics in mvr_common.cuh / mvr_mesh.cuh) and is compiled with contraction.
+SOURCES = {"mvr_util.cu": False, "mvr_camera.cu": False, "mvr_mesh.cu": False, "mvr_mesh_bwd.cu": True, "mvr_points.cu": False}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-fmad=false",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp",
 ]
 
 
@@ -39,18 +41,35 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS
+    base = [_nvcc()] + NVCC_FLAGS
     if os.path.exists("/usr/bin/g++"):
-        cmd += ["-ccbin", "/usr/bin/g++"]
+        base += ["-ccbin", "/usr/bin/g++"]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        base += ["-Xptxas", "-v"]
+    objdir = os.path.join(HERE, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(item):
+        src, fmad = item
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = base + ["-fmad=true" if fmad else "-fmad=false", "-c", os.path.join(CSRC, src), "-o", obj]
+        return obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES.items()))
+    objs = []
+    for obj, res in results:
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed building libmvr_b200.so")
+        if verbose:
+            sys.stderr.write(res.stderr)
+        objs.append(obj)
+    res = subprocess.run(base + ["-shared", "-o", LIB] + objs, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libmvr_b200.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("nvcc failed linking libmvr_b200.so")
     return LIB
 
 

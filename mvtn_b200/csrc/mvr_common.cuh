@@ -104,10 +104,12 @@ __device__ __forceinline__ Camera load_camera(const float* __restrict__ R, const
   for (int i = 0; i < 3; ++i) c.t[i] = __ldg(T + 3 * (size_t)n + i);
   return c;
 }
+// Written with round-to-nearest intrinsics, which the compiler never contracts into FMAs: the result is the oracle's
+// IEEE sequence whatever -fmad says for the translation unit (the backward units are compiled with contraction).
 __device__ __forceinline__ void world_to_view(const Camera& c, float x, float y, float z, float& px, float& py, float& pz) {
-  px = ((x * c.r[0] + y * c.r[3]) + z * c.r[6]) + c.t[0];
-  py = ((x * c.r[1] + y * c.r[4]) + z * c.r[7]) + c.t[1];
-  pz = ((x * c.r[2] + y * c.r[5]) + z * c.r[8]) + c.t[2];
+  px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, c.r[0]), __fmul_rn(y, c.r[3])), __fmul_rn(z, c.r[6])), c.t[0]);
+  py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, c.r[1]), __fmul_rn(y, c.r[4])), __fmul_rn(z, c.r[7])), c.t[1]);
+  pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, c.r[2]), __fmul_rn(y, c.r[5])), __fmul_rn(z, c.r[8])), c.t[2]);
 }
 
 __device__ __forceinline__ unsigned long long make_key(float z, int idx) {

@@ -1,0 +1,289 @@
+// mvr_mesh_bwd.cu -- backward of the mesh path (see mvr_mesh.cu for the forward).  Compiled WITH FMA contraction
+// (build.py: no -fmad=false for this file): everything here is compared with the oracle at a tolerance, and the exact
+// part it depends on -- the projected vertices -- comes from mesh_project_kernel, whose arithmetic is written with
+// non-contractable intrinsics.  Contraction removes ~120 of the ~480 floating-point instructions per covered pixel.
+//
+//   mesh_backward_kernel -- per pixel recompute (no fragment traffic), chain
+//             d image -> Phong -> barycentrics -> NDC verts -> view verts -> (dR, dT, dC), warp-reduced to one partial
+//             per warp and summed in fixed order (deterministic, no float atomics on the camera gradients).
+#include "mvr_mesh.cuh"
+
+namespace mvr {
+
+struct MeshBwdParams {
+  const float4* verts4; const float4* normals4; const float4* rgb4; const int4* faces4;
+  const int* vert_off; const int* face_off;
+  const float* R; const float* T; const float* Cc; const float* light; int light_stride;
+  const float* obj_rgb;
+  float k00, k11;
+  int B, M, H, W, K, flags, ctas_per_view, tiles_x;
+  const float4* pv; const float* tab;
+  const int* pix_to_face; const float* grad_images;
+  float* partials;       // (N, ctas_per_view, NWARPS, 16)
+  float* grad_verts; float* grad_normals;
+};
+
+__device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
+
+// d/dv of v / max(|v|, eps)
+__device__ __forceinline__ void normalize_bwd3(float vx, float vy, float vz, float eps, float gx, float gy, float gz,
+                                               float& ox, float& oy, float& oz) {
+  const float n2 = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
+  if (n2 > eps * eps) {
+    const float inv = rsqrtf(n2);
+    const float ux = vx * inv, uy = vy * inv, uz = vz * inv;
+    const float d = fmaf(ux, gx, fmaf(uy, gy, uz * gz));
+    ox = fmaf(-ux, d, gx) * inv; oy = fmaf(-uy, d, gy) * inv; oz = fmaf(-uz, d, gz) * inv;
+  } else {
+    const float inv = 1.f / eps;
+    ox = gx * inv; oy = gy * inv; oz = gz * inv;
+  }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const MeshBwdParams p) {
+  const int tid = threadIdx.x;
+  // grid: x = 32x32-pixel tiles, y = view m, z = object b; thread (lane, warp) owns pixels (x0+lane, y0+warp+8j)
+  const int b = blockIdx.z, m = blockIdx.y, n = b * p.M + m, cta = blockIdx.x;
+  int tyb, txb;
+  tile_rc(cta, p.tiles_x, tyb, txb);
+  const int xi = txb * 32 + (tid & 31), yi0 = tyb * 32 + (tid >> 5);
+  const int HW = p.H * p.W;
+  const int f0 = p.face_off[b], voff = p.vert_off[b], V = p.vert_off[b + 1] - voff;
+  const float4* pvn = p.pv + (size_t)p.M * voff + (size_t)m * V;
+  const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
+  const bool per_vertex_rgb = p.flags & MVR_RGB_PER_ELEMENT;
+  // issue every load of this thread's pixels first (memory-level parallelism), then do the math
+  int fids[BWD_PIX_PER_THREAD];
+  float gin[BWD_PIX_PER_THREAD][3];
+#pragma unroll
+  for (int j = 0; j < BWD_PIX_PER_THREAD; ++j) {
+    const int yi = yi0 + 8 * j;
+    fids[j] = (xi < p.W && yi < p.H) ? __ldg(p.pix_to_face + ((size_t)n * HW + (size_t)yi * p.W + xi) * p.K) : -1;
+  }
+#pragma unroll
+  for (int j = 0; j < BWD_PIX_PER_THREAD; ++j) {
+    const int pix = (yi0 + 8 * j) * p.W + xi;
+    if (fids[j] >= 0) {
+      const size_t io = (size_t)n * 3 * HW + pix;
+      gin[j][0] = __ldg(p.grad_images + io); gin[j][1] = __ldg(p.grad_images + io + HW); gin[j][2] = __ldg(p.grad_images + io + 2 * (size_t)HW);
+    } else {
+      gin[j][0] = gin[j][1] = gin[j][2] = 0.f;
+    }
+  }
+  float acc[BWD_VALS];
+#pragma unroll
+  for (int i = 0; i < BWD_VALS; ++i) acc[i] = 0.f;
+  bool any = false;
+  const ShadeCtx sc = load_shade_ctx(p.light, p.light_stride, p.Cc, n);
+  const float xf = xi < p.W ? __ldg(p.tab + xi) : 0.f;
+  float4 ucol = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!per_vertex_rgb) ucol = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f);
+#pragma unroll 1
+  for (int j = 0; j < BWD_PIX_PER_THREAD; ++j) {
+    const int fid = fids[j];
+    const float g0 = gin[j][0], g1 = gin[j][1], g2 = gin[j][2];
+    if (fid < 0 || (g0 == 0.f && g1 == 0.f && g2 == 0.f)) continue;
+    any = true;
+    const int yi = yi0 + 8 * j;
+    const int4 fi = __ldg(p.faces4 + f0 + fid);
+    // ---- forward recompute from the projected vertices (exact IEEE projection, done once per view by
+    // mesh_project_kernel: for small faces the barycentrics amplify a 1-ulp change of a vertex by |xy| / area);
+    // everything downstream is well conditioned and uses fast reciprocals ----
+    const Face fc = gather_face(pvn, fi);
+    const float4 X0 = __ldg(p.verts4 + voff + fi.x), X1 = __ldg(p.verts4 + voff + fi.y), X2 = __ldg(p.verts4 + voff + fi.z);
+    const float4 N0 = __ldg(p.normals4 + voff + fi.x), N1 = __ldg(p.normals4 + voff + fi.y), N2 = __ldg(p.normals4 + voff + fi.z);
+    float4 c0 = ucol, c1 = ucol, c2 = ucol;
+    if (per_vertex_rgb) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
+    const FaceEdges fe = face_edges(fc);
+    const float yf = __ldg(p.tab + p.W + yi);
+    const float e0 = (xf - fc.x1) * fe.A0 - (yf - fc.y1) * fe.B0;
+    const float e1 = (xf - fc.x2) * fe.A1 - (yf - fc.y2) * fe.B1;
+    const float e2 = (xf - fc.x0) * fe.A2 - (yf - fc.y0) * fe.B2;
+    const float inv_area = rcp_fast(fe.area_p);
+    const float w0 = e0 * inv_area, w1 = e1 * inv_area, w2 = e2 * inv_area;
+    float bb[3] = {w0, w1, w2};
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, id = 1.f;
+    bool clamped = false;
+    if (persp) {
+      t0 = w0 * fc.z1 * fc.z2; t1 = w1 * fc.z0 * fc.z2; t2 = w2 * fc.z0 * fc.z1;
+      const float st = t0 + t1 + t2;
+      clamped = st < MVR_K_EPS;
+      id = rcp_fast(fmaxf(st, MVR_K_EPS));
+      bb[0] = t0 * id; bb[1] = t1 * id; bb[2] = t2 * id;
+    }
+    // ---- Phong backward ----
+    const float3 P = interp(bb, X0, X1, X2);
+    const float3 Nn = interp(bb, N0, N1, N2);
+    const float3 tex = interp(bb, c0, c1, c2);
+    const float in = inv_norm_clamped(Nn.x, Nn.y, Nn.z, 1e-6f);
+    const float nx = Nn.x * in, ny = Nn.y * in, nz = Nn.z * in;
+    const float cosang = fmaf(nx, sc.lx, fmaf(ny, sc.ly, nz * sc.lz));
+    const float diff = fmaxf(cosang, 0.f);
+    const float vx = sc.cx - P.x, vy = sc.cy - P.y, vz = sc.cz - P.z;
+    const float iv = inv_norm_clamped(vx, vy, vz, 1e-6f);
+    const float vhx = vx * iv, vhy = vy * iv, vhz = vz * iv;
+    const float rx = fmaf(2.f * cosang, nx, -sc.lx), ry = fmaf(2.f * cosang, ny, -sc.ly), rz = fmaf(2.f * cosang, nz, -sc.lz);
+    const float dt = fmaf(vhx, rx, fmaf(vhy, ry, vhz * rz));
+    const bool lit = cosang > 0.f;
+    const float alpha = (dt > 0.f && lit) ? dt : 0.f;
+    const float kd = fmaf(MVR_DIFFUSE, diff, MVR_AMBIENT);
+    const float gtx = g0 * kd, gty = g1 * kd, gtz = g2 * kd;
+    const float gdiff = MVR_DIFFUSE * fmaf(g0, tex.x, fmaf(g1, tex.y, g2 * tex.z));
+    const float gs = MVR_SPECULAR * (g0 + g1 + g2);
+    const float a2 = alpha * alpha, a4 = a2 * a2, a8 = a4 * a4, a16 = a8 * a8, a32 = a16 * a16;
+    const float a63 = a32 * a16 * a8 * a4 * a2 * alpha;
+    const float gdt = (dt > 0.f && lit) ? gs * 64.f * a63 : 0.f;
+    const float gvhx = gdt * rx, gvhy = gdt * ry, gvhz = gdt * rz;
+    const float grx = gdt * vhx, gry = gdt * vhy, grz = gdt * vhz;
+    const float gcos = (lit ? gdiff : 0.f) + 2.f * fmaf(grx, nx, fmaf(gry, ny, grz * nz));
+    const float gnx = fmaf(2.f * cosang, grx, gcos * sc.lx), gny = fmaf(2.f * cosang, gry, gcos * sc.ly), gnz = fmaf(2.f * cosang, grz, gcos * sc.lz);
+    float gNx, gNy, gNz, gvx, gvy, gvz;
+    normalize_bwd3(Nn.x, Nn.y, Nn.z, 1e-6f, gnx, gny, gnz, gNx, gNy, gNz);
+    normalize_bwd3(vx, vy, vz, 1e-6f, gvhx, gvhy, gvhz, gvx, gvy, gvz);
+    acc[12] += gvx; acc[13] += gvy; acc[14] += gvz;   // dC
+    // d bary_i = gtex.col_i + gN.n_i + gP.X_i  with gP = -gv
+    float gb0 = fmaf(gtx, c0.x, fmaf(gty, c0.y, gtz * c0.z)) + fmaf(gNx, N0.x, fmaf(gNy, N0.y, gNz * N0.z)) - fmaf(gvx, X0.x, fmaf(gvy, X0.y, gvz * X0.z));
+    float gb1 = fmaf(gtx, c1.x, fmaf(gty, c1.y, gtz * c1.z)) + fmaf(gNx, N1.x, fmaf(gNy, N1.y, gNz * N1.z)) - fmaf(gvx, X1.x, fmaf(gvy, X1.y, gvz * X1.z));
+    float gb2 = fmaf(gtx, c2.x, fmaf(gty, c2.y, gtz * c2.z)) + fmaf(gNx, N2.x, fmaf(gNy, N2.y, gNz * N2.z)) - fmaf(gvx, X2.x, fmaf(gvy, X2.y, gvz * X2.z));
+    // ---- [upstream] BarycentricPerspectiveCorrectionBackward ----
+    float dz0 = 0.f, dz1 = 0.f, dz2 = 0.f;
+    if (persp) {
+      // b = t / sum(t) is invariant to a common shift of d/db (its Jacobian annihilates constants), so
+      // remove k = sum(b_i gb_i) first: the d/d denom term then vanishes identically instead of cancelling
+      // O(1/area) terms in fp32.  Same gradient in exact arithmetic; not valid when denom was clamped.
+      if (!clamped) {
+        const float kk = fmaf(bb[0], gb0, fmaf(bb[1], gb1, bb[2] * gb2));
+        gb0 -= kk; gb1 -= kk; gb2 -= kk;
+      }
+      const float gden = clamped ? -(gb0 * t0 + gb1 * t1 + gb2 * t2) * id * id : 0.f;
+      const float gt0 = fmaf(gb0, id, gden), gt1 = fmaf(gb1, id, gden), gt2 = fmaf(gb2, id, gden);
+      gb0 = gt0 * fc.z1 * fc.z2; gb1 = gt1 * fc.z0 * fc.z2; gb2 = gt2 * fc.z0 * fc.z1;
+      dz0 = gt1 * w1 * fc.z2 + gt2 * w2 * fc.z1;
+      dz1 = gt0 * w0 * fc.z2 + gt2 * w2 * fc.z0;
+      dz2 = gt0 * w0 * fc.z1 + gt1 * w1 * fc.z0;
+    }
+    // ---- [upstream] BarycentricCoordsBackward / EdgeFunctionBackward ----
+    const float ge0 = gb0 * inv_area, ge1 = gb1 * inv_area, ge2 = gb2 * inv_area;
+    const float garea = -(gb0 * e0 + gb1 * e1 + gb2 * e2) * inv_area * inv_area;
+    float gx0, gy0, gx1, gy1, gx2, gy2;
+    // E(p,a,b): dE/da = (py-by, bx-px), dE/db = (ay-py, px-ax)
+    gx1 = ge0 * (yf - fc.y2); gy1 = ge0 * (fc.x2 - xf); gx2 = ge0 * (fc.y1 - yf); gy2 = ge0 * (xf - fc.x1);          // e0 = E(p,v1,v2)
+    gx2 += ge1 * (yf - fc.y0); gy2 += ge1 * (fc.x0 - xf); gx0 = ge1 * (fc.y2 - yf); gy0 = ge1 * (xf - fc.x2);        // e1 = E(p,v2,v0)
+    gx0 += ge2 * (yf - fc.y1); gy0 += ge2 * (fc.x1 - xf); gx1 += ge2 * (fc.y0 - yf); gy1 += ge2 * (xf - fc.x0);      // e2 = E(p,v0,v1)
+    // area = E(v2, v0, v1)
+    gx0 += garea * (fc.y2 - fc.y1); gy0 += garea * (fc.x1 - fc.x2);
+    gx1 += garea * (fc.y0 - fc.y2); gy1 += garea * (fc.x2 - fc.x0);
+    gx2 += garea * (fc.y1 - fc.y0); gy2 += garea * (fc.x0 - fc.x1);
+    // ---- projection backward + X R + T backward: x_ndc = (px k00) / pz, so px k00 = x_ndc pz ----
+    const float gxn[3] = {gx0, gx1, gx2}, gyn[3] = {gy0, gy1, gy2}, gzn[3] = {dz0, dz1, dz2};
+    const float xn[3] = {fc.x0, fc.x1, fc.x2}, yn[3] = {fc.y0, fc.y1, fc.y2}, zv[3] = {fc.z0, fc.z1, fc.z2};
+    const float4 Xs[3] = {X0, X1, X2};
+    const int vid[3] = {fi.x, fi.y, fi.z};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float iz = rcp_fast(zv[i]);
+      const float gpx = gxn[i] * p.k00 * iz;
+      const float gpy = gyn[i] * p.k11 * iz;
+      const float gpz = gzn[i] - (gxn[i] * xn[i] + gyn[i] * yn[i]) * iz;
+      acc[0] = fmaf(Xs[i].x, gpx, acc[0]); acc[1] = fmaf(Xs[i].x, gpy, acc[1]); acc[2] = fmaf(Xs[i].x, gpz, acc[2]);
+      acc[3] = fmaf(Xs[i].y, gpx, acc[3]); acc[4] = fmaf(Xs[i].y, gpy, acc[4]); acc[5] = fmaf(Xs[i].y, gpz, acc[5]);
+      acc[6] = fmaf(Xs[i].z, gpx, acc[6]); acc[7] = fmaf(Xs[i].z, gpy, acc[7]); acc[8] = fmaf(Xs[i].z, gpz, acc[8]);
+      acc[9] += gpx; acc[10] += gpy; acc[11] += gpz;
+      if (p.grad_verts) {
+        const float* r = p.R + 9 * (size_t)n;
+        float* o = p.grad_verts + 3 * (size_t)(voff + vid[i]);
+        atomicAdd(o + 0, fmaf(__ldg(r + 0), gpx, fmaf(__ldg(r + 1), gpy, __ldg(r + 2) * gpz)) - bb[i] * gvx);
+        atomicAdd(o + 1, fmaf(__ldg(r + 3), gpx, fmaf(__ldg(r + 4), gpy, __ldg(r + 5) * gpz)) - bb[i] * gvy);
+        atomicAdd(o + 2, fmaf(__ldg(r + 6), gpx, fmaf(__ldg(r + 7), gpy, __ldg(r + 8) * gpz)) - bb[i] * gvz);
+      }
+      if (p.grad_normals) {
+        float* o = p.grad_normals + 3 * (size_t)(voff + vid[i]);
+        atomicAdd(o + 0, bb[i] * gNx); atomicAdd(o + 1, bb[i] * gNy); atomicAdd(o + 2, bb[i] * gNz);
+      }
+    }
+  }
+  // one partial per WARP, no block barrier: a warp retires as soon as its own pixels are done
+  float* out = p.partials + (((size_t)n * p.ctas_per_view + cta) * NWARPS + (tid >> 5)) * 16;
+  const int lane = tid & 31;
+  if (!__any_sync(0xffffffffu, any)) {   // background-only warp
+    if (lane < 16) out[lane] = 0.f;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < BWD_VALS; ++i) acc[i] = warp_sum(acc[i]);
+  float mine = 0.f;
+#pragma unroll
+  for (int i = 0; i < BWD_VALS; ++i) mine = lane == i ? acc[i] : mine;
+  if (lane < 16) out[lane] = mine;
+}
+
+// fixed-order sum of the per-warp partials: one warp per view -> gR, gT, gC
+__global__ void mesh_backward_reduce_kernel(const float* __restrict__ partials, int N, int n_parts,
+                                            float* __restrict__ gR, float* __restrict__ gT, float* __restrict__ gC) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  // lane l < 16 owns value l of even parts, lane l >= 16 value l-16 of odd parts
+  const int v = lane & 15, par = lane >> 4;
+  float s = 0.f;
+  for (int t = par; t < n_parts; t += 2) s += partials[((size_t)n * n_parts + t) * 16 + v];
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  if (lane < 9) gR[9 * (size_t)n + lane] = s;
+  else if (lane < 12) gT[3 * (size_t)n + lane - 9] = s;
+  else if (lane < 15) gC[3 * (size_t)n + lane - 12] = s;
+}
+
+}  // namespace mvr
+
+using namespace mvr;
+
+static int backward_minb() {
+  static const int v = [] { const char* e = getenv("MVR_BWD_MINB"); const int x = e ? atoi(e) : 3; return (x == 2 || x == 4) ? x : 3; }();
+  return v;
+}
+
+extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
+                                 int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
+                                 const float* T, const float* Cc, const float* light, int light_stride,
+                                 const float* obj_rgb, float k00, float k11, int H, int W, int K, int flags,
+                                 const int* pix_to_face, const float* grad_images, float* gR, float* gT, float* gC,
+                                 float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  int rc = check_mesh_common("mvr_mesh_backward", B, M, H, W, K, total_verts, total_faces, max_verts);
+  if (rc) return rc;
+  const int64_t N = (int64_t)B * M;
+  if (N == 0) return 0;
+  if (!geometry || !vert_off || !face_off || !R || !T || !Cc || !light || !pix_to_face || !grad_images || !gR || !gT || !gC || !workspace) {
+    set_error("mvr_mesh_backward: null pointer"); return -5;
+  }
+  if (!(flags & MVR_RGB_PER_ELEMENT) && !obj_rgb) { set_error("mvr_mesh_backward: obj_rgb is NULL"); return -6; }
+  const WsLayout w = ws_layout(B, M, H, W, K, total_verts);
+  if (workspace_bytes < w.total) { set_error("mvr_mesh_backward: workspace too small (%zu < %zu)", workspace_bytes, w.total); return -7; }
+  const GeomLayout g = geom_layout(total_verts, total_faces);
+  const char* gb = (const char*)geometry;
+  char* wb = (char*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  // the workspace is scratch (it may have served another render since the forward): project again, 2% of the step
+  rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, workspace, st);
+  if (rc) return rc;
+  MeshBwdParams p;
+  p.verts4 = (const float4*)(gb + g.verts4); p.normals4 = (const float4*)(gb + g.normals4);
+  p.rgb4 = (const float4*)(gb + g.rgb4); p.faces4 = (const int4*)(gb + g.faces4);
+  p.vert_off = vert_off; p.face_off = face_off;
+  p.R = R; p.T = T; p.Cc = Cc; p.light = light; p.light_stride = light_stride; p.obj_rgb = obj_rgb;
+  p.k00 = k00; p.k11 = k11;
+  p.B = B; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags; p.ctas_per_view = w.bwd_ctas_per_view; p.tiles_x = (W + 31) / 32;
+  p.pv = (const float4*)(wb + w.pv); p.tab = (const float*)(wb + w.tab);
+  p.pix_to_face = pix_to_face; p.grad_images = grad_images;
+  p.partials = (float*)(wb + w.partials); p.grad_verts = grad_verts; p.grad_normals = grad_normals;
+  const dim3 bgrid((unsigned)w.bwd_ctas_per_view, (unsigned)M, (unsigned)B);
+  if (backward_minb() == 2) MVR_LAUNCH(mesh_backward_kernel<2>, bgrid, MVR_THREADS, 0, st, p);
+  else if (backward_minb() == 4) MVR_LAUNCH(mesh_backward_kernel<4>, bgrid, MVR_THREADS, 0, st, p);
+  else MVR_LAUNCH(mesh_backward_kernel<3>, bgrid, MVR_THREADS, 0, st, p);
+  rc = check_launch("mesh_backward_kernel");
+  if (rc) return rc;
+  const int wpb = 8;
+  MVR_LAUNCH(mesh_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)(wb + w.partials), (int)N, w.bwd_ctas_per_view * NWARPS, gR, gT, gC);
+  return check_launch("mesh_backward_reduce_kernel");
+}

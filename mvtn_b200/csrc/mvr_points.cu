@@ -62,6 +62,30 @@ __device__ __forceinline__ void insert_key(unsigned long long* slot, unsigned lo
   }
 }
 
+// exclusive prefix sum of one int per thread over the CTA (MVR_THREADS threads); total returned to every thread.
+// s_w: shared int[MVR_THREADS / 32 + 1].  Contains two block barriers.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_w, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < MVR_THREADS / 32; ++w) {
+    const int x = s_w[w];
+    base += w < warp ? x : 0;
+    tot += x;
+  }
+  __syncthreads();
+  total = tot;
+  return base + inc - v;
+}
+
 constexpr int PS_CAP = 4096;      // (point, pixel) candidates queued per CTA; beyond that they are inserted in place
 
 // grid: x = blocks of 256 points, y = view m, z = object b.
@@ -72,44 +96,55 @@ constexpr int PS_CAP = 4096;      // (point, pixel) candidates queued per CTA; b
 __global__ void __launch_bounds__(MVR_THREADS) points_scatter_kernel(const PointsParams p) {
   __shared__ unsigned int s_cand[PS_CAP];       // local point << 24 | y << 12 | x
   __shared__ unsigned long long s_key[MVR_THREADS];
-  __shared__ int s_n;
+  __shared__ int s_w[MVR_THREADS / 32 + 1];
   const int b = blockIdx.z, n = b * p.M + blockIdx.y;
   const int tid = threadIdx.x;
   const int pi = blockIdx.x * MVR_THREADS + tid;
   const size_t HW = (size_t)p.H * p.W;
   unsigned long long* keys = p.keys + (size_t)n * HW * p.K;
-  if (tid == 0) s_n = 0;
-  __syncthreads();
+  const float* tx = p.tab;
+  const float* ty = p.tab + p.W;
+  float px = 0.f, py = 0.f;
+  int xl = 1, xh = 0, yl = 1, yh = 0, cnt = 0;
+  unsigned long long key = MVR_EMPTY_KEY;
   if (pi < p.Np) {
     const Camera cam = load_camera(p.R, p.T, n);
     const float s = __ldg(p.inv_dist + n);
-    float px, py, pz;
+    float pz;
     project_point(p.points + 3 * (size_t)b * p.Np, pi, s, cam, px, py, pz);
     if (!(pz < 0.f)) {
-      const unsigned long long key = make_key(pz, pi);
-      s_key[tid] = key;
+      key = make_key(pz, pi);
       // conservative search window for candidate pixel centres (the exact test is dist2 < r2 below)
       const float rr = p.radius * 1.0001f + 1e-7f;
-      const float* tx = p.tab;
-      const float* ty = p.tab + p.W;
-      int xl, xh, yl, yh;
       pixel_range(py - rr, py + rr, p.H, p.W, 0, p.H - 1, ty, yl, yh);
       pixel_range(px - rr, px + rr, p.W, p.H, 0, p.W - 1, tx, xl, xh);
-      for (int yy = yl; yy <= yh; ++yy) {
+      if (yl > yh || xl > xh) { xl = 1; xh = 0; yl = 1; yh = 0; }
+      for (int yy = yl; yy <= yh; ++yy) {          // pass 1: count the pixel centres inside the radius
         const float dy = py - __ldg(ty + yy);
         for (int xx = xl; xx <= xh; ++xx) {
           const float dx = px - __ldg(tx + xx);
-          const float d2 = dx * dx + dy * dy;
-          if (!(d2 < p.r2_raster)) continue;
-          const int at = atomicAdd(&s_n, 1);
-          if (at < PS_CAP) s_cand[at] = ((unsigned int)tid << 24) | ((unsigned int)yy << 12) | (unsigned int)xx;
-          else insert_key(keys + ((size_t)yy * p.W + xx) * p.K, key, p.K);
+          cnt += (dx * dx + dy * dy < p.r2_raster) ? 1 : 0;
         }
       }
     }
   }
+  s_key[tid] = key;
+  int total;
+  int at = block_exclusive_scan(cnt, s_w, total);      // queue slots without atomics (and in a deterministic order)
+  if (cnt > 0) {
+    for (int yy = yl; yy <= yh; ++yy) {            // pass 2: same tests, write the queue
+      const float dy = py - __ldg(ty + yy);
+      for (int xx = xl; xx <= xh; ++xx) {
+        const float dx = px - __ldg(tx + xx);
+        if (!(dx * dx + dy * dy < p.r2_raster)) continue;
+        if (at < PS_CAP) s_cand[at] = ((unsigned int)tid << 24) | ((unsigned int)yy << 12) | (unsigned int)xx;
+        else insert_key(keys + ((size_t)yy * p.W + xx) * p.K, key, p.K);
+        ++at;
+      }
+    }
+  }
   __syncthreads();
-  const int nc = min(s_n, PS_CAP);
+  const int nc = min(total, PS_CAP);
   for (int c = tid; c < nc; c += MVR_THREADS) {
     const unsigned int cd = s_cand[c];
     const int xx = cd & 4095, yy = (cd >> 12) & 4095;
@@ -331,7 +366,8 @@ __global__ void __launch_bounds__(MVR_THREADS) points_tile_kernel(const PointsPa
     const float* tabx = p.tab;
     const float* taby = p.tab + p.W;
     for (int base = beg; base < end; base += MVR_THREADS) {
-      // phase 1: thread per point -- pixel centres of the window (clipped to this tile) inside the radius
+      // phase 1: thread per point -- pixel centres of the window (clipped to this tile) inside the radius go to the
+      // queue (one shared atomic per hit: measured faster here than count + block scan + second pass)
       const int i = base + tid;
       if (i < end) {
         const int pi = p.list[(size_t)n * p.list_cap + i];
