@@ -133,6 +133,44 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Warp-wide sums of 16 values per lane in 16 shuffles instead of 80: at each butterfly step a lane keeps the half of
+// its values selected by the corresponding bit of its lane id and hands the other half to its partner.  On return
+// lanes 2i and 2i+1 both hold the warp total of v[i] (i = 0..15); the summation order is fixed, so the result is
+// run-to-run identical.
+__device__ __forceinline__ float warp_sum16_transposed(float (&v)[16]) {
+  const int lane = threadIdx.x & 31;
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 // Block-wide sum of NV values per thread (MVR_THREADS threads); result valid in thread 0.
 template <int NV>
 __device__ __forceinline__ void block_sum(float (&v)[NV], float* s_red /* [8][NV] */) {

@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
       gin[j][0] = gin[j][1] = gin[j][2] = 0.f;
     }
   }
-  float acc[BWD_VALS];
+  float acc[16];                                      // BWD_VALS used, [15] stays 0
 #pragma unroll
-  for (int i = 0; i < BWD_VALS; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   bool any = false;
   const ShadeCtx sc = load_shade_ctx(p.light, p.light_stride, p.Cc, n);
   const float xf = xi < p.W ? __ldg(p.tab + xi) : 0.f;
@@ -210,28 +210,30 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
     if (lane < 16) out[lane] = 0.f;
     return;
   }
-#pragma unroll
-  for (int i = 0; i < BWD_VALS; ++i) acc[i] = warp_sum(acc[i]);
-  float mine = 0.f;
-#pragma unroll
-  for (int i = 0; i < BWD_VALS; ++i) mine = lane == i ? acc[i] : mine;
-  if (lane < 16) out[lane] = mine;
+  const float mine = warp_sum16_transposed(acc);      // lanes 2i, 2i+1: total of value i
+  if (!(lane & 1)) out[lane >> 1] = mine;
 }
 
-// fixed-order sum of the per-warp partials: one warp per view -> gR, gT, gC
-__global__ void mesh_backward_reduce_kernel(const float* __restrict__ partials, int N, int n_parts,
-                                            float* __restrict__ gR, float* __restrict__ gT, float* __restrict__ gC) {
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (n >= N) return;
-  // lane l < 16 owns value l of even parts, lane l >= 16 value l-16 of odd parts
-  const int v = lane & 15, par = lane >> 4;
+// fixed-order sum of the per-warp partials: one CTA per view -> gR, gT, gC.  Thread t owns value t & 15 of the parts
+// congruent to t >> 4 modulo 16 (coalesced 64-byte rows), then 16 threads add the 16 group sums in a fixed order.
+__global__ void __launch_bounds__(MVR_THREADS) mesh_backward_reduce_kernel(const float* __restrict__ partials, int n_parts,
+                                                                           float* __restrict__ gR, float* __restrict__ gT,
+                                                                           float* __restrict__ gC) {
+  __shared__ float s_sum[MVR_THREADS];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const int v = tid & 15, grp = tid >> 4;
   float s = 0.f;
-  for (int t = par; t < n_parts; t += 2) s += partials[((size_t)n * n_parts + t) * 16 + v];
-  s += __shfl_xor_sync(0xffffffffu, s, 16);
-  if (lane < 9) gR[9 * (size_t)n + lane] = s;
-  else if (lane < 12) gT[3 * (size_t)n + lane - 9] = s;
-  else if (lane < 15) gC[3 * (size_t)n + lane - 12] = s;
+  for (int t = grp; t < n_parts; t += MVR_THREADS / 16) s += partials[((size_t)n * n_parts + t) * 16 + v];
+  s_sum[tid] = s;
+  __syncthreads();
+  if (tid < 16) {
+    float tot = 0.f;
+#pragma unroll
+    for (int g = 0; g < MVR_THREADS / 16; ++g) tot += s_sum[g * 16 + tid];
+    if (tid < 9) gR[9 * (size_t)n + tid] = tot;
+    else if (tid < 12) gT[3 * (size_t)n + tid - 9] = tot;
+    else if (tid < 15) gC[3 * (size_t)n + tid - 12] = tot;
+  }
 }
 
 }  // namespace mvr
@@ -283,7 +285,6 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   else MVR_LAUNCH(mesh_backward_kernel<3>, bgrid, MVR_THREADS, 0, st, p);
   rc = check_launch("mesh_backward_kernel");
   if (rc) return rc;
-  const int wpb = 8;
-  MVR_LAUNCH(mesh_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)(wb + w.partials), (int)N, w.bwd_ctas_per_view * NWARPS, gR, gT, gC);
+  MVR_LAUNCH(mesh_backward_reduce_kernel, (unsigned)N, MVR_THREADS, 0, st, (const float*)(wb + w.partials), w.bwd_ctas_per_view * NWARPS, gR, gT, gC);
   return check_launch("mesh_backward_reduce_kernel");
 }

@@ -482,9 +482,9 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
     }
   }
   __syncwarp();
-  float acc[PB_VALS];
+  float acc[16];                                      // PB_VALS used, the rest stay 0
 #pragma unroll
-  for (int i = 0; i < PB_VALS; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   const Camera cam = load_camera(p.R, p.T, n);
   const float s = __ldg(p.inv_dist + n);
   const float inv_r2 = 1.f / p.r2_weight;
@@ -558,12 +558,8 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
     }
   }
   // one partial per tile (= per warp), summed in fixed order by the reduce kernel
-#pragma unroll
-  for (int i = 0; i < PB_VALS; ++i) acc[i] = warp_sum(acc[i]);
-  float mine = 0.f;
-#pragma unroll
-  for (int i = 0; i < PB_VALS; ++i) mine = lane == i ? acc[i] : mine;
-  if (lane < 16) out[lane] = mine;
+  const float mine = warp_sum16_transposed(acc);      // lanes 2i, 2i+1: total of value i
+  if (!(lane & 1)) out[lane >> 1] = mine;
 }
 
 __global__ void points_backward_reduce_kernel(const float* __restrict__ partials, int N, int n_parts,
