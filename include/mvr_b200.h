@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MVR_ABI_VERSION 2
+#define MVR_ABI_VERSION 3
 
 /* flags */
 #define MVR_PERSPECTIVE_CORRECT 1  /* [upstream] RasterizationSettings.perspective_correct (FoV persp.: True) */
@@ -42,7 +42,7 @@ extern "C" {
 #define MVR_SPECULAR 0.2f
 #define MVR_SHININESS 64
 
-/* counters[] slots written by the forward calls (device int64[MVR_NUM_COUNTERS], accumulated) */
+/* counters[] slots written by mvr_mesh_forward (device int64[MVR_NUM_COUNTERS]; the call zeroes them first) */
 #define MVR_CNT_STRADDLE 0     /* faces straddling the near clip plane (rasterized unclipped) */
 #define MVR_CNT_BIG_FACES 1    /* faces whose pixel bbox exceeded 1024 pixels (walked by a whole CTA) */
 #define MVR_NUM_COUNTERS 4
@@ -90,7 +90,7 @@ int mvr_host_stage_meshes_end(int job);
 /* -- cameras ------------------------------------------------------------------------------ */
 /* look_at_view_transform(dist, elev, azim) + camera_position_from_spherical_angles
  * (renderer.py:79-80,122-123,168; ops.py:160) fused with util.py:403-420
- * check_valid_rotation_matrix: *invalid_count += number of matrices failing the check.
+ * check_valid_rotation_matrix: *invalid_count = number of matrices failing the check (the call zeroes it first).
  * azim/elev in degrees, n = B*M.  C (n,3) = camera centres (may be NULL). */
 int mvr_look_at_forward(const float* azim, const float* elev, const float* dist, int n, float* R,
                         float* T, float* C, int* invalid_count, void* stream);
@@ -125,7 +125,7 @@ size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K, int64_t total
  *   K = faces_per_pixel; max_verts / max_faces = largest per-object counts (grid sizing).
  * outputs: images (n,3,H,W); pix_to_face (n,H,W,K) view-local face ids, -1 empty;
  *          optional zbuf (n,H,W,K), bary (n,H,W,K,3), dists (n,H,W,K) (NULL to skip);
- *          counters: device int64[MVR_NUM_COUNTERS] or NULL. */
+ *          counters: device int64[MVR_NUM_COUNTERS] or NULL (zeroed by the call, then counted into). */
 int mvr_mesh_forward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
                      int64_t total_verts, int64_t total_faces, int max_verts, int max_faces,
                      const float* R, const float* T, const float* Cc, const float* light,

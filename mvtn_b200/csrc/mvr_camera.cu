@@ -141,6 +141,10 @@ using namespace mvr;
 extern "C" int mvr_look_at_forward(const float* azim, const float* elev, const float* dist, int n, float* R,
                                    float* T, float* C, int* invalid_count, void* stream) {
   if (n < 0 || (n > 0 && (!azim || !elev || !dist || !R || !T))) { mvr::set_error("mvr_look_at_forward: null pointer or negative n"); return -1; }
+  if (invalid_count) {      // the call owns the flag: zeroed here, so that the caller does not pay a fill launch for it
+    cudaError_t e = cudaMemsetAsync(invalid_count, 0, sizeof(int), (cudaStream_t)stream);
+    if (e != cudaSuccess) { mvr::set_error("mvr_look_at_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+  }
   if (n == 0) return 0;
   MVR_LAUNCH(look_at_forward_kernel, (n + 127) / 128, 128, 0, (cudaStream_t)stream, azim, elev, dist, n, R, T, C, invalid_count);
   return mvr::check_launch("look_at_forward_kernel");

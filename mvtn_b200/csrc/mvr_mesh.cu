@@ -563,6 +563,10 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   int rc = check_mesh_common("mvr_mesh_forward", B, M, H, W, K, total_verts, total_faces, max_verts);
   if (rc) return rc;
   const int64_t N = (int64_t)B * M;
+  if (counters) {           // the call owns the counters: zeroed here, so that the caller does not pay a fill launch for them
+    cudaError_t ce = cudaMemsetAsync(counters, 0, MVR_NUM_COUNTERS * sizeof(int64_t), (cudaStream_t)stream);
+    if (ce != cudaSuccess) { set_error("mvr_mesh_forward: cudaMemsetAsync: %s", cudaGetErrorString(ce)); return (int)ce; }
+  }
   if (N == 0) return 0;
   if (!geometry || !vert_off || !face_off || !R || !T || !Cc || !light || !bg_rgb || !images || !pix_to_face || !workspace) {
     set_error("mvr_mesh_forward: null pointer"); return -5;

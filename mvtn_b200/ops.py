@@ -18,8 +18,35 @@ from . import _lib as L
 _workspaces = {}
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(device):
+    """Raw cudaStream_t of torch's current stream on `device` (the C-level accessor when this torch has it: the python
+    Stream object costs several microseconds per call, and the hot path asks a dozen times per step)."""
+    if _raw_stream is not None:
+        idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+        return _raw_stream(torch.cuda.current_device() if idx is None else idx)
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class _NoCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOCTX = _NoCtx()
+
+
+def _on(device):
+    """Context making `device` current for a C-ABI call; free when it already is (the usual case)."""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NOCTX
+    return torch.cuda.device(device)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -114,7 +141,7 @@ def _stage_meshes(v_src, f_src, face_elem_bytes, v_host, f_host, v_dev, f_dev, d
             return job, keep
         if job != -10:          # -10: the worker is busy with another batch -> stage synchronously
             L.check(job, "mvr_host_stage_meshes_begin")
-    with torch.cuda.device(device):
+    with _on(torch.device(device)):
         L.check(lib.mvr_host_stage_meshes(vp, vc, fp, fc, n, face_elem_bytes, v_host.data_ptr(), f_host.data_ptr(),
                                           v_dev.data_ptr(), f_dev.data_ptr(), _stream(device)), "mvr_host_stage_meshes")
     return None, keep
@@ -147,8 +174,8 @@ class _LookAt(torch.autograd.Function):
         dev = a.device
         buf = torch.empty(15 * n, dtype=torch.float32, device=dev)      # one allocation: R | T | C
         R, T, Cc = buf[: 9 * n].view(n, 3, 3), buf[9 * n: 12 * n].view(n, 3), buf[12 * n:].view(n, 3)
-        bad = torch.zeros(1, dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
+        bad = torch.empty(1, dtype=torch.int32, device=dev)      # zeroed by mvr_look_at_forward
+        with _on(dev):
             L.check(lib.mvr_look_at_forward(_ptr(a), _ptr(e), _ptr(d), n, _ptr(R), _ptr(T), _ptr(Cc), _ptr(bad),
                                             _stream(dev)), "mvr_look_at_forward")
         ctx.save_for_backward(a, e, d)
@@ -169,7 +196,7 @@ class _LookAt(torch.autograd.Function):
         gT = None if gT is None else _f32c(gT)
         gC = None if gC is None else _f32c(gC)
         ga, ge, gd = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3))
-        with torch.cuda.device(dev):
+        with _on(dev):
             L.check(lib.mvr_look_at_backward(_ptr(a), _ptr(e), _ptr(d), n, _ptr(gR), _ptr(gT), _ptr(gC), _ptr(ga),
                                              _ptr(ge), _ptr(gd), _stream(dev)), "mvr_look_at_backward")
         sa, se, sd = ctx.shapes
@@ -211,6 +238,15 @@ class HostPackedMeshes:
         self.verts, self.faces = verts.contiguous(), faces.contiguous()
         self.num_verts, self.num_faces = [int(x) for x in num_verts], [int(x) for x in num_faces]
         self.vert_rgb = vert_rgb
+        # per-batch metadata the step would otherwise rebuild on every forward: prefix offsets (one small pinned tensor,
+        # [vert_off | face_off]) and the totals / maxima that size the grids
+        self.vert_off_host, self.face_off_host = [0], [0]
+        for a in self.num_verts:
+            self.vert_off_host.append(self.vert_off_host[-1] + a)
+        for a in self.num_faces:
+            self.face_off_host.append(self.face_off_host[-1] + a)
+        offs = torch.tensor(self.vert_off_host + self.face_off_host, dtype=torch.int32)
+        self.offs = offs.pin_memory() if verts.is_pinned() else offs
 
     def __len__(self):
         return len(self.num_verts)
@@ -353,8 +389,10 @@ class PackedMeshes:
         self = cls.__new__(cls)
         v_dev = hp.verts.to(device, non_blocking=True)
         f_dev = hp.faces.to(device, non_blocking=True)
-        self._init_packed(v_dev, f_dev, list(hp.num_verts), list(hp.num_faces), device,
-                          vert_rgb if vert_rgb is not None else hp.vert_rgb)
+        offs = hp.offs.to(device, non_blocking=True)
+        self._init_packed(v_dev, f_dev, hp.num_verts, hp.num_faces, device,
+                          vert_rgb if vert_rgb is not None else hp.vert_rgb,
+                          offsets=(hp.vert_off_host, hp.face_off_host, offs))
         return self
 
     @classmethod
@@ -367,31 +405,34 @@ class PackedMeshes:
         self._init_packed(verts, faces, list(num_verts), list(num_faces), verts.device, vert_rgb)
         return self
 
-    def _init_packed(self, v_dev, f_dev, nv, nf, device, vert_rgb):
+    def _init_packed(self, v_dev, f_dev, nv, nf, device, vert_rgb, offsets=None):
         lib = L.load()
         self.B = len(nv)
         self.num_verts, self.num_faces = nv, nf
-        self.total_verts, self.total_faces = sum(nv), sum(nf)
+        if offsets is not None:          # precomputed at collate time (HostPackedMeshes), already on their way to the device
+            voff, foff, offs = offsets
+        else:
+            voff, foff = [0], [0]
+            for a in nv:
+                voff.append(voff[-1] + a)
+            for a in nf:
+                foff.append(foff[-1] + a)
+            offs_h = _staging("offs", device, 2 * self.B + 2, torch.int32)
+            offs_h.copy_(torch.tensor(voff + foff, dtype=torch.int32))
+            offs = offs_h.to(device, non_blocking=True)
+            _staging_done(device)
+        self.total_verts, self.total_faces = voff[-1], foff[-1]
         self.max_faces = max(nf) if nf else 0
         self.max_verts = max(nv) if nv else 0
         if v_dev.shape[0] != self.total_verts or f_dev.shape[0] != self.total_faces:
             raise ValueError("packed arrays do not match the per-mesh counts")
-        voff, foff = [0], [0]
-        for a in nv:
-            voff.append(voff[-1] + a)
-        for a in nf:
-            foff.append(foff[-1] + a)
         self.vert_off_host, self.face_off_host = voff, foff
         self.device = device
         self.per_vertex_rgb = vert_rgb is not None
-        self.verts = v_dev.detach().to(torch.float32).contiguous()
+        self.verts = _f32c(v_dev)
         if f_dev.dtype not in (torch.int32, torch.int64):
             f_dev = f_dev.to(torch.int64)
-        self.faces = f_dev.contiguous()
-        offs_h = _staging("offs", device, 2 * self.B + 2, torch.int32)
-        offs_h.copy_(torch.tensor(voff + foff, dtype=torch.int32))
-        offs = offs_h.to(device, non_blocking=True)
-        _staging_done(device)
+        self.faces = f_dev if f_dev.is_contiguous() else f_dev.contiguous()
         self.vert_off, self.face_off = offs[: self.B + 1], offs[self.B + 1:]
         flags = L.FACES_I64 if self.faces.dtype == torch.int64 else 0
         rgb = None
@@ -410,7 +451,7 @@ class PackedMeshes:
         (mvr_mesh_prepare): call it after updating self.verts in place.  Pure device work on the current stream."""
         if self.B == 0:
             return self
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             L.check(L.load().mvr_mesh_prepare(_ptr(self.verts), _ptr(self.faces), _ptr(self.vert_off), _ptr(self.face_off),
                                               self.B, self.total_verts, self.total_faces, self.max_faces, _ptr(self._rgb),
                                               self._prep_flags, _ptr(self.geometry), self.geometry.numel(),
@@ -427,7 +468,7 @@ class PackedMeshes:
 
     def vertex_normals(self) -> torch.Tensor:
         out = torch.empty((self.total_verts, 3), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             L.check(L.load().mvr_mesh_get_normals(_ptr(self.geometry), self.total_verts, self.total_faces, _ptr(out),
                                                   _stream(self.device)), "mvr_mesh_get_normals")
         return out
@@ -471,10 +512,10 @@ class _MeshRender(torch.autograd.Function):
             zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
             bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
             dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
-        counters = torch.zeros(L.NUM_COUNTERS, dtype=torch.int64, device=dev)
+        counters = torch.empty(L.NUM_COUNTERS, dtype=torch.int64, device=dev)      # zeroed by mvr_mesh_forward
         ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts)
         ws = workspace(dev, ws_bytes)
-        with torch.cuda.device(dev):
+        with _on(dev):
             L.check(lib.mvr_mesh_forward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
                                          geom.total_verts, geom.total_faces, geom.max_verts, geom.max_faces, _ptr(R), _ptr(T), _ptr(Cc),
                                          _ptr(light), light_stride, _ptr(obj_rgb), _ptr(bg_rgb), k00, k11, z_clip, H, W,
@@ -510,7 +551,7 @@ class _MeshRender(torch.autograd.Function):
         if ctx.needs_input_grad[3]:
             gV = torch.zeros((geom.total_verts, 3), dtype=torch.float32, device=dev)
             gN = torch.zeros((geom.total_verts, 3), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             L.check(lib.mvr_mesh_backward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
                                           geom.total_verts, geom.total_faces, geom.max_verts, _ptr(R), _ptr(T), _ptr(Cc), _ptr(light),
                                           ctx.light_stride, _ptr(obj_rgb), k00, k11, H, W, K, flags, _ptr(p2f),
@@ -578,7 +619,7 @@ class _PointsRender(torch.autograd.Function):
         ws = workspace(dev, lib.mvr_points_workspace_bytes(B, Np, M, H, W, K, float(radius)))
         # one bit per pixel: the backward pass skips the (typically ~90 %) background without touching idx
         mask = torch.empty(max(lib.mvr_points_hit_mask_words(B, M, H, W), 1), dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             L.check(lib.mvr_points_forward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), float(radius),
                                            _ptr(bg_rgb), H, W, K, flags, _ptr(images), _ptr(idx), _ptr(zbuf), _ptr(d2),
                                            _ptr(mask), _ptr(ws), ws.numel(), _stream(dev)), "mvr_points_forward")
@@ -608,7 +649,7 @@ class _PointsRender(torch.autograd.Function):
         gF = torch.zeros_like(rgb) if ctx.needs_input_grad[4] else None
         ws_bytes = lib.mvr_points_workspace_bytes(B, Np, M, H, W, K, float(radius))
         ws = workspace(dev, ws_bytes)
-        with torch.cuda.device(dev):
+        with _on(dev):
             L.check(lib.mvr_points_backward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), radius, H,
                                             W, K, flags, _ptr(idx), _ptr(mask), _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gs),
                                             _ptr(gP), _ptr(gF), _ptr(ws), ws.numel(), _stream(dev)),

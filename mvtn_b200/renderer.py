@@ -25,6 +25,16 @@ _small_cache_by_id = {}
 def _device_vec(values, device):
     """Small constant vectors (colours, fixed light) are uploaded once per (device, value) and reused: a
     pageable host->device copy synchronises the stream, and the reference pays one per call."""
+    if isinstance(values, tuple):       # constant tuples (fixed light, default colours): hashable, no tensor round trip
+        try:
+            tkey = ("tuple", device.index, values)
+            hit = _small_cache.get(tkey)
+            if hit is None:
+                hit = torch.as_tensor(values, dtype=torch.float32).to(device)
+                _small_cache[tkey] = hit
+            return hit
+        except TypeError:               # unhashable content (tensors inside): fall through to the generic path
+            pass
     # identity fast path: the cached named colours (util.torch_color) and constant tuples come back as the same object
     ident = (id(values), device.index) if isinstance(values, torch.Tensor) and is_cached_constant(values) else None
     if ident is not None:
@@ -125,8 +135,7 @@ class MVRenderer(nn.Module):
             raise ValueError("azim, elev and dist must all be (B, M)")
         if azim.shape[1] != self.nb_views:
             raise ValueError(f"expected {self.nb_views} views, got {azim.shape[1]}")
-        R, T, C, bad = ops.look_at_view_transform(dist.reshape(-1), elev.reshape(-1), azim.reshape(-1),
-                                                  return_centers=True, return_invalid=True)
+        R, T, C, bad = ops._LookAt.apply(azim, elev, dist)      # flattens (B, M) -> B*M itself, flat order b*M + m
         return azim, elev, dist, R, T, C, bad
 
     def _render_with_guard(self, azim, elev, dist, device, render):
