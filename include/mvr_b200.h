@@ -34,6 +34,7 @@ extern "C" {
 #define MVR_COMPOSITE_ALPHA 4      /* AlphaCompositor instead of NormWeightedCompositor (renderer.py:11,138) */
 #define MVR_RGB_PER_ELEMENT 8      /* per-vertex / per-point colours (object_color == "custom") */
 #define MVR_FACES_I64 16           /* faces given as int64 (F,3) -- the reference's layout, renderer.py:68 */
+#define MVR_IMAGES_BF16 32         /* images (forward) / grad_images (backward) are bfloat16 instead of float32 */
 #define MVR_TEST_TINY_QUEUES 0x40000000 /* tests only: shrink the scatter kernel's work queues to force their fallbacks */
 
 /* Phong constants of DirectionalLights() / Materials() as constructed at renderer.py:190-191 */
@@ -123,6 +124,9 @@ size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K, int64_t total
  *   obj_rgb (3) uniform colour (ignored when the geometry holds per-vertex colours); bg_rgb (3);
  *   k00,k11: FoV projection scale (1/tan(fov/2)); z_clip < 0 disables the near-plane cull;
  *   K = faces_per_pixel; max_verts / max_faces = largest per-object counts (grid sizing).
+ *   out_mean_std: HOST float[6] = per-channel mean[3], std[3], or NULL.  Consumer-side fusion:
+ *   the images are written as (x - mean_c) / std_c -- viewGCN/tools/Trainer_mvt.py:41-49 Normalize -- and, with
+ *   MVR_IMAGES_BF16, rounded to bfloat16, i.e. in the layout and dtype the CNN consumes; NULL + fp32 = the reference.
  * outputs: images (n,3,H,W); pix_to_face (n,H,W,K) view-local face ids, -1 empty;
  *          optional zbuf (n,H,W,K), bary (n,H,W,K,3), dists (n,H,W,K) (NULL to skip);
  *          counters: device int64[MVR_NUM_COUNTERS] or NULL (zeroed by the call, then counted into). */
@@ -130,19 +134,21 @@ int mvr_mesh_forward(const void* geometry, const int* vert_off, const int* face_
                      int64_t total_verts, int64_t total_faces, int max_verts, int max_faces,
                      const float* R, const float* T, const float* Cc, const float* light,
                      int light_stride, const float* obj_rgb, const float* bg_rgb, float k00, float k11,
-                     float z_clip, int H, int W, int K, int flags, float* images, int* pix_to_face,
-                     float* zbuf, float* bary, float* dists, int64_t* counters, void* workspace,
-                     size_t workspace_bytes, void* stream);
+                     float z_clip, int H, int W, int K, int flags, const float* out_mean_std, void* images,
+                     int* pix_to_face, float* zbuf, float* bary, float* dists, int64_t* counters,
+                     void* workspace, size_t workspace_bytes, void* stream);
 /* backward of the above w.r.t. the cameras ([upstream] _C.rasterize_meshes_backward + autograd
  * of shading/projection): grad_images (n,3,H,W) -> gR (n,3,3), gT (n,3), gC (n,3);
  * optional grad_verts (Vtot,3) (projection + interpolated-position paths) and grad_normals
  * (Vtot,3) (gradient w.r.t. the per-vertex unit normals), both ACCUMULATED with atomics
- * (caller zero-fills). */
+ * (caller zero-fills).  out_mean_std / MVR_IMAGES_BF16 as in the forward: grad_images is then the cotangent of
+ * the normalised (bfloat16) tensor. */
 int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
                       int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
                       const float* T, const float* Cc, const float* light, int light_stride,
                       const float* obj_rgb, float k00, float k11, int H, int W, int K, int flags,
-                      const int* pix_to_face, const float* grad_images, float* gR, float* gT, float* gC,
+                      const float* out_mean_std, const int* pix_to_face, const void* grad_images, float* gR,
+                      float* gT, float* gC,
                       float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,
                       void* stream);
 
@@ -156,14 +162,14 @@ size_t mvr_points_hit_mask_words(int B, int M, int H, int W);
 /* PointsRenderer(PointsRasterizer, compositor)(Pointclouds.extend(M).scale_(1/dist))
  * (renderer.py:119-150; [upstream] _C.rasterize_points + accum_weightedsumnorm /
  * accum_alphacomposite + background).  points (B,Np,3); rgb (3) or (B*Np,3) [MVR_RGB_PER_ELEMENT];
- * inv_dist (n) = 1/dist; radius in NDC; K = points_per_pixel.
+ * inv_dist (n) = 1/dist; radius in NDC; K = points_per_pixel; out_mean_std / MVR_IMAGES_BF16 as in mvr_mesh_forward.
  * outputs: images (n,3,H,W); idx (n,H,W,K) cloud-local point ids (-1 empty); optional zbuf,
  * dists2 (n,H,W,K); optional hit_mask (mvr_points_hit_mask_words words), which lets the backward pass skip
  * the ~90 % background pixels without reading idx. */
 int mvr_points_forward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
                        const float* T, const float* inv_dist, double radius, const float* bg_rgb,
-                       int H, int W, int K, int flags, float* images, int* idx, float* zbuf,
-                       float* dists2, uint32_t* hit_mask, void* workspace, size_t workspace_bytes,
+                       int H, int W, int K, int flags, const float* out_mean_std, void* images, int* idx,
+                       float* zbuf, float* dists2, uint32_t* hit_mask, void* workspace, size_t workspace_bytes,
                        void* stream);
 /* backward ([upstream] accum_*_backward + _C.rasterize_points_backward + autograd of the
  * projection): grad_images -> gR (n,3,3), gT (n,3), g_inv_dist (n); optional grad_points
@@ -171,8 +177,8 @@ int mvr_points_forward(const float* points, const float* rgb, int B, int Np, int
  * hit_mask: the forward's mask or NULL (then idx[..., 0] >= 0 is read for every pixel). */
 int mvr_points_backward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
                         const float* T, const float* inv_dist, double radius, int H, int W, int K,
-                        int flags, const int* idx, const uint32_t* hit_mask, const float* grad_images,
-                        float* gR, float* gT, float* g_inv_dist, float* grad_points, float* grad_rgb,
+                        int flags, const float* out_mean_std, const int* idx, const uint32_t* hit_mask,
+                        const void* grad_images, float* gR, float* gT, float* g_inv_dist, float* grad_points, float* grad_rgb,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

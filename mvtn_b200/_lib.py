@@ -11,6 +11,7 @@ CULL_BACKFACES = 2
 COMPOSITE_ALPHA = 4
 RGB_PER_ELEMENT = 8
 FACES_I64 = 16
+IMAGES_BF16 = 32
 TEST_TINY_QUEUES = 0x40000000   # tests only: shrink the scatter kernel's work queues to force their fallbacks
 CNT_STRADDLE, CNT_BIG_FACES, NUM_COUNTERS = 0, 1, 4
 
@@ -37,14 +38,14 @@ SIGNATURES = {
     "mvr_mesh_get_normals": (_i, [_vp, _i64, _i64, _vp, _vp]),
     "mvr_mesh_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i64]),
     "mvr_mesh_forward": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _f, _f,
-                              _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+                              _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mvr_mesh_backward": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _f, _f, _i, _i, _i, _i,
-                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mvr_points_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _d]),
     "mvr_points_hit_mask_words": (_sz, [_i, _i, _i, _i]),
-    "mvr_points_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _d, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
+    "mvr_points_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _d, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _vp, _sz, _vp]),
-    "mvr_points_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _d, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
+    "mvr_points_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _d, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 

@@ -5,6 +5,7 @@
 // order.  The translation units are compiled with -fmad=false so that a*b+c is never contracted;
 // where an FMA is wanted (shading, gradients: tolerance-compared) it is written as fmaf().
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -110,6 +111,52 @@ __device__ __forceinline__ void world_to_view(const Camera& c, float x, float y,
   px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, c.r[0]), __fmul_rn(y, c.r[3])), __fmul_rn(z, c.r[6])), c.t[0]);
   py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, c.r[1]), __fmul_rn(y, c.r[4])), __fmul_rn(z, c.r[7])), c.t[1]);
   pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, c.r[2]), __fmul_rn(y, c.r[5])), __fmul_rn(z, c.r[8])), c.t[2]);
+}
+
+// Consumer-side output transform (Trainer_mvt.py:41-49 Normalize, run before the CNN): the image
+// is written as (x - mean_c) * (1 / std_c), optionally rounded to bfloat16 [MVR_IMAGES_BF16]; the backward reads the
+// cotangent of THAT tensor and scales it by 1 / std_c.  on == false leaves the arithmetic of the default path untouched.
+struct OutNorm {
+  float m0, m1, m2, s0, s1, s2;
+  bool on;
+};
+static inline OutNorm make_out_norm(const float* host_mean_std) {
+  OutNorm q = {0.f, 0.f, 0.f, 1.f, 1.f, 1.f, false};
+  if (host_mean_std) {
+    q.m0 = host_mean_std[0]; q.m1 = host_mean_std[1]; q.m2 = host_mean_std[2];
+    q.s0 = 1.0f / host_mean_std[3]; q.s1 = 1.0f / host_mean_std[4]; q.s2 = 1.0f / host_mean_std[5];
+    q.on = true;
+  }
+  return q;
+}
+static inline bool out_norm_valid(const float* host_mean_std) {
+  if (!host_mean_std) return true;
+  for (int i = 3; i < 6; ++i)
+    if (!(host_mean_std[i] > 0.f)) return false;
+  return true;
+}
+// planar (n,3,H,W) pixel store / cotangent load; io = offset of channel 0, plane = H*W
+__device__ __forceinline__ void store_rgb(void* images, bool bf16, size_t io, size_t plane, float r, float g, float b,
+                                          const OutNorm& q) {
+  if (q.on) { r = (r - q.m0) * q.s0; g = (g - q.m1) * q.s1; b = (b - q.m2) * q.s2; }
+  if (bf16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(images);
+    o[io] = __float2bfloat16_rn(r); o[io + plane] = __float2bfloat16_rn(g); o[io + 2 * plane] = __float2bfloat16_rn(b);
+  } else {
+    float* o = reinterpret_cast<float*>(images);
+    o[io] = r; o[io + plane] = g; o[io + 2 * plane] = b;
+  }
+}
+__device__ __forceinline__ void load_grad_rgb(const void* grad, bool bf16, size_t io, size_t plane, const OutNorm& q,
+                                              float& g0, float& g1, float& g2) {
+  if (bf16) {
+    const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(grad);
+    g0 = __bfloat162float(g[io]); g1 = __bfloat162float(g[io + plane]); g2 = __bfloat162float(g[io + 2 * plane]);
+  } else {
+    const float* g = reinterpret_cast<const float*>(grad);
+    g0 = __ldg(g + io); g1 = __ldg(g + io + plane); g2 = __ldg(g + io + 2 * plane);
+  }
+  if (q.on) { g0 *= q.s0; g1 *= q.s1; g2 *= q.s2; }
 }
 
 __device__ __forceinline__ unsigned long long make_key(float z, int idx) {

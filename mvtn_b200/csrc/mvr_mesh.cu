@@ -93,8 +93,9 @@ struct MeshParams {
   float4* pv;            // (x_ndc, y_ndc, z_view, 0) of vertex v of view (b, m) at M*vert_off[b] + m*V_b + v
   float* tab;            // pixel-centre NDC coordinates: xf[W] then yf[H]
   unsigned long long* keys; unsigned long long* prev;
-  float* images; int* pix_to_face; float* zbuf; float* bary; float* dists;
+  void* images; int* pix_to_face; float* zbuf; float* bary; float* dists;
   long long* counters;
+  OutNorm onorm;
 };
 
 // Face-level rejection ([upstream] clip.py near cull, CheckPointOutsideBoundingBox z_invalid,
@@ -482,10 +483,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_shade_kernel(const Mes
     if (p.dists) p.dists[po] = dd;
     if (p.bary) { p.bary[3 * po] = bb[0]; p.bary[3 * po + 1] = bb[1]; p.bary[3 * po + 2] = bb[2]; }
   }
-  if (k == 0) {
-    const size_t io = (size_t)n * 3 * HW + pix;
-    p.images[io] = out[0]; p.images[io + HW] = out[1]; p.images[io + 2 * (size_t)HW] = out[2];
-  }
+  if (k == 0) store_rgb(p.images, p.flags & MVR_IMAGES_BF16, (size_t)n * 3 * HW + pix, (size_t)HW, out[0], out[1], out[2], p.onorm);
 }
 
 }  // namespace mvr
@@ -557,9 +555,9 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
                                 int64_t total_verts, int64_t total_faces, int max_verts, int max_faces,
                                 const float* R, const float* T, const float* Cc, const float* light,
                                 int light_stride, const float* obj_rgb, const float* bg_rgb, float k00, float k11,
-                                float z_clip, int H, int W, int K, int flags, float* images, int* pix_to_face,
-                                float* zbuf, float* bary, float* dists, int64_t* counters, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                float z_clip, int H, int W, int K, int flags, const float* out_mean_std, void* images,
+                                int* pix_to_face, float* zbuf, float* bary, float* dists, int64_t* counters,
+                                void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_mesh_common("mvr_mesh_forward", B, M, H, W, K, total_verts, total_faces, max_verts);
   if (rc) return rc;
   const int64_t N = (int64_t)B * M;
@@ -572,6 +570,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
     set_error("mvr_mesh_forward: null pointer"); return -5;
   }
   if (!(flags & MVR_RGB_PER_ELEMENT) && !obj_rgb) { set_error("mvr_mesh_forward: obj_rgb is NULL and the geometry has no per-vertex colours"); return -6; }
+  if (!out_norm_valid(out_mean_std)) { set_error("mvr_mesh_forward: out_mean_std needs std > 0"); return -9; }
   const WsLayout w = ws_layout(B, M, H, W, K, total_verts);
   if (workspace_bytes < w.total) { set_error("mvr_mesh_forward: workspace too small (%zu < %zu)", workspace_bytes, w.total); return -7; }
   const int chunks_per_view = max_faces > 0 ? (max_faces + FACES_PER_CTA - 1) / FACES_PER_CTA : 0;
@@ -595,6 +594,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.keys = (unsigned long long*)(wb + w.keys); p.prev = (unsigned long long*)(wb + w.prev);
   p.images = images; p.pix_to_face = pix_to_face; p.zbuf = zbuf; p.bary = bary; p.dists = dists;
   p.counters = (long long*)counters;
+  p.onorm = make_out_norm(out_mean_std);
   const size_t HW = (size_t)H * W;
   cudaError_t e = cudaMemsetAsync(p.keys, 0xFF, (size_t)N * HW * 8, st);      // every key = EMPTY
   if (e != cudaSuccess) { set_error("mvr_mesh_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }

@@ -18,9 +18,10 @@ struct MeshBwdParams {
   float k00, k11;
   int B, M, H, W, K, flags, ctas_per_view, tiles_x;
   const float4* pv; const float* tab;
-  const int* pix_to_face; const float* grad_images;
+  const int* pix_to_face; const void* grad_images;
   float* partials;       // (N, ctas_per_view, NWARPS, 16)
   float* grad_verts; float* grad_normals;
+  OutNorm onorm;
 };
 
 __device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
@@ -65,8 +66,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
   for (int j = 0; j < BWD_PIX_PER_THREAD; ++j) {
     const int pix = (yi0 + 8 * j) * p.W + xi;
     if (fids[j] >= 0) {
-      const size_t io = (size_t)n * 3 * HW + pix;
-      gin[j][0] = __ldg(p.grad_images + io); gin[j][1] = __ldg(p.grad_images + io + HW); gin[j][2] = __ldg(p.grad_images + io + 2 * (size_t)HW);
+      load_grad_rgb(p.grad_images, p.flags & MVR_IMAGES_BF16, (size_t)n * 3 * HW + pix, (size_t)HW, p.onorm, gin[j][0], gin[j][1], gin[j][2]);
     } else {
       gin[j][0] = gin[j][1] = gin[j][2] = 0.f;
     }
@@ -249,7 +249,7 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
                                  int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
                                  const float* T, const float* Cc, const float* light, int light_stride,
                                  const float* obj_rgb, float k00, float k11, int H, int W, int K, int flags,
-                                 const int* pix_to_face, const float* grad_images, float* gR, float* gT, float* gC,
+                                 const float* out_mean_std, const int* pix_to_face, const void* grad_images, float* gR, float* gT, float* gC,
                                  float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,
                                  void* stream) {
   int rc = check_mesh_common("mvr_mesh_backward", B, M, H, W, K, total_verts, total_faces, max_verts);
@@ -260,6 +260,7 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
     set_error("mvr_mesh_backward: null pointer"); return -5;
   }
   if (!(flags & MVR_RGB_PER_ELEMENT) && !obj_rgb) { set_error("mvr_mesh_backward: obj_rgb is NULL"); return -6; }
+  if (!out_norm_valid(out_mean_std)) { set_error("mvr_mesh_backward: out_mean_std needs std > 0"); return -9; }
   const WsLayout w = ws_layout(B, M, H, W, K, total_verts);
   if (workspace_bytes < w.total) { set_error("mvr_mesh_backward: workspace too small (%zu < %zu)", workspace_bytes, w.total); return -7; }
   const GeomLayout g = geom_layout(total_verts, total_faces);
@@ -279,6 +280,7 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   p.pv = (const float4*)(wb + w.pv); p.tab = (const float*)(wb + w.tab);
   p.pix_to_face = pix_to_face; p.grad_images = grad_images;
   p.partials = (float*)(wb + w.partials); p.grad_verts = grad_verts; p.grad_normals = grad_normals;
+  p.onorm = make_out_norm(out_mean_std);
   const dim3 bgrid((unsigned)w.bwd_ctas_per_view, (unsigned)M, (unsigned)B);
   if (backward_minb() == 2) MVR_LAUNCH(mesh_backward_kernel<2>, bgrid, MVR_THREADS, 0, st, p);
   else if (backward_minb() == 4) MVR_LAUNCH(mesh_backward_kernel<4>, bgrid, MVR_THREADS, 0, st, p);

@@ -34,7 +34,8 @@ struct PointsParams {
   // tiled path (K in {1,2,4,8}): per-(view, point) projection + pixel window, per-(view, tile) point lists
   float4* pp; int2* pw; int* tile_cnt; int* tile_off; int* tile_cur; int* list;
   int tiles_x, tiles_y, ntiles, list_cap;
-  float* images; int* idx; float* zbuf; float* dists2; unsigned int* hit_mask;
+  void* images; int* idx; float* zbuf; float* dists2; unsigned int* hit_mask;
+  OutNorm onorm;
 };
 
 __device__ __forceinline__ void project_point(const float* __restrict__ pts, int pi, float s, const Camera& cam,
@@ -229,8 +230,7 @@ __device__ __forceinline__ void composite_and_store(const PointsParams& p, const
     if (alpha_mode) { o0 = a0; o1 = a1; o2 = a2; }
     else { const float t = fmaxf(aw, 1e-4f); o0 = a0 / t; o1 = a1 / t; o2 = a2 / t; }
   }
-  const size_t io = (size_t)n * 3 * HW + pix;
-  p.images[io] = o0; p.images[io + HW] = o1; p.images[io + 2 * HW] = o2;
+  store_rgb(p.images, p.flags & MVR_IMAGES_BF16, (size_t)n * 3 * HW + pix, HW, o0, o1, o2, p.onorm);
 }
 
 // grid: x = 32x8-pixel tiles, y = view m, z = object b.  KT = K when K <= PK_MAX_REG (keys in registers), 0 = generic
@@ -422,9 +422,10 @@ struct PointsBwdParams {
   const float* R; const float* T; const float* inv_dist;
   float r2_weight;
   int B, Np, M, H, W, K, flags, tiles_x, tiles_y, ctas_per_view, mask_words;
-  const int* idx; const float* grad_images; const unsigned int* hit_mask;
+  const int* idx; const void* grad_images; const unsigned int* hit_mask;
   float* partials;        // (N, ctas_per_view, 16): one per 32x32 tile
   float* grad_points; float* grad_rgb;
+  OutNorm onorm;
 };
 
 // grid: x = groups of 8 vertically adjacent 32x32-pixel tiles (one per warp), y = view m, z = object b.
@@ -493,7 +494,8 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
     const int yi = tyb * 32 + (code >> 5), xi = txb * 32 + (code & 31);
     const int* ip = p.idx + (((size_t)n * p.H + yi) * p.W + xi) * p.K;
     const size_t io = ((size_t)n * 3 * p.H + yi) * p.W + xi;
-    const float g0 = __ldg(p.grad_images + io), g1 = __ldg(p.grad_images + io + plane), g2 = __ldg(p.grad_images + io + 2 * plane);
+    float g0, g1, g2;
+    load_grad_rgb(p.grad_images, p.flags & MVR_IMAGES_BF16, io, plane, p.onorm, g0, g1, g2);
     if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
     const float xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H), yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
     // pass 1: compositor totals
@@ -649,14 +651,15 @@ extern "C" size_t mvr_points_hit_mask_words(int B, int M, int H, int W) {
 
 extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
                                   const float* T, const float* inv_dist, double radius, const float* bg_rgb,
-                                  int H, int W, int K, int flags, float* images, int* idx, float* zbuf,
-                                  float* dists2, uint32_t* hit_mask, void* workspace, size_t workspace_bytes,
-                                  void* stream) {
+                                  int H, int W, int K, int flags, const float* out_mean_std, void* images, int* idx,
+                                  float* zbuf, float* dists2, uint32_t* hit_mask, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
   int rc = check_points_common("mvr_points_forward", B, Np, M, H, W, K, radius);
   if (rc) return rc;
   const int64_t N = (int64_t)B * M;
   if (N == 0) return 0;
   if ((Np > 0 && !points) || !rgb || !R || !T || !inv_dist || !bg_rgb || !images || !idx || !workspace) { set_error("mvr_points_forward: null pointer"); return -6; }
+  if (!out_norm_valid(out_mean_std)) { set_error("mvr_points_forward: out_mean_std needs std > 0"); return -9; }
   const PointsWs w = points_ws(B, Np, M, H, W, K, radius);
   const size_t HW = (size_t)H * W;
   if (workspace_bytes < w.total) { set_error("mvr_points_forward: workspace too small (%zu < %zu)", workspace_bytes, w.total); return -7; }
@@ -675,6 +678,7 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
   p.list = (int*)(wb + w.list);
   p.tiles_x = w.tiles_x; p.tiles_y = w.tiles_y; p.ntiles = w.ntiles; p.list_cap = w.list_cap;
   p.images = images; p.idx = idx; p.zbuf = zbuf; p.dists2 = dists2; p.hit_mask = hit_mask;
+  p.onorm = make_out_norm(out_mean_std);
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 point_grid((unsigned)((Np + MVR_THREADS - 1) / MVR_THREADS), (unsigned)M, (unsigned)B);
   if (Np > 0) MVR_LAUNCH(pixel_table_kernel, 1, MVR_THREADS, 0, st, (float*)(wb + w.tab), H, W);
@@ -727,7 +731,8 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
 
 extern "C" int mvr_points_backward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
                                    const float* T, const float* inv_dist, double radius, int H, int W, int K,
-                                   int flags, const int* idx, const uint32_t* hit_mask, const float* grad_images,
+                                   int flags, const float* out_mean_std, const int* idx, const uint32_t* hit_mask,
+                                   const void* grad_images,
                                    float* gR, float* gT, float* g_inv_dist, float* grad_points, float* grad_rgb,
                                    void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_points_common("mvr_points_backward", B, Np, M, H, W, K, radius);
@@ -737,6 +742,7 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
   if ((Np > 0 && !points) || !rgb || !R || !T || !inv_dist || !idx || !grad_images || !gR || !gT || !g_inv_dist || !workspace) {
     set_error("mvr_points_backward: null pointer"); return -6;
   }
+  if (!out_norm_valid(out_mean_std)) { set_error("mvr_points_backward: out_mean_std needs std > 0"); return -9; }
   const PointsWs w = points_ws(B, Np, M, H, W, K, radius);
   const size_t need = (size_t)N * w.ctas_per_view * 16 * sizeof(float);
   if (workspace_bytes < need) { set_error("mvr_points_backward: workspace too small (%zu < %zu)", workspace_bytes, need); return -7; }
@@ -748,6 +754,7 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
   p.idx = idx; p.grad_images = grad_images; p.hit_mask = hit_mask;
   p.partials = (float*)((char*)workspace + w.partials);
   p.grad_points = grad_points; p.grad_rgb = grad_rgb;
+  p.onorm = make_out_norm(out_mean_std);
   cudaStream_t st = (cudaStream_t)stream;
   MVR_LAUNCH(points_backward_kernel, dim3((unsigned)(w.tiles_x * ((p.tiles_y + 7) / 8)), (unsigned)M, (unsigned)B), MVR_THREADS, 0, st, p);
   rc = check_launch("points_backward_kernel");

@@ -97,6 +97,38 @@ def _staging_done(device):
             _staging_bufs[key] = (buf, ev)
 
 
+def _out_norm(normalize):
+    """(mean, std) -> ctypes float[6] for the C ABI's HOST out_mean_std argument (None = identity)."""
+    if normalize is None:
+        return None
+    import ctypes as C
+    mean, std = normalize
+    mean = [float(x) for x in (mean if hasattr(mean, "__len__") else (mean,) * 3)]
+    std = [float(x) for x in (std if hasattr(std, "__len__") else (std,) * 3)]
+    if len(mean) != 3 or len(std) != 3:
+        raise ValueError("normalize must be (mean, std) with 3 channels each")
+    if not all(x > 0 for x in std):
+        raise ValueError("normalize: std must be positive")
+    return (C.c_float * 6)(*mean, *std)
+
+
+def _image_dtype(out_dtype):
+    if out_dtype in (None, torch.float32):
+        return torch.float32, 0
+    if out_dtype is torch.bfloat16:
+        return torch.bfloat16, L.IMAGES_BF16
+    raise ValueError("out_dtype must be torch.float32 or torch.bfloat16")
+
+
+def _grad_like_images(g, flags):
+    """Cotangent of the images in the dtype the forward wrote (fp32, or bf16 under IMAGES_BF16), contiguous."""
+    want = torch.bfloat16 if flags & L.IMAGES_BF16 else torch.float32
+    g = g.detach()
+    if g.dtype is not want:
+        g = g.to(want)
+    return g if g.is_contiguous() else g.contiguous()
+
+
 def _hw(image_size):
     """int -> (S, S); (H, W) tuple as in PyTorch3D's RasterizationSettings.image_size."""
     if isinstance(image_size, (tuple, list)):
@@ -489,7 +521,7 @@ def vertex_normals_torch(verts: torch.Tensor, faces: torch.Tensor) -> torch.Tens
 class _MeshRender(torch.autograd.Function):
     @staticmethod
     def forward(ctx, R, T, Cc, verts, geom: PackedMeshes, M, light, obj_rgb, bg_rgb, k00, k11, z_clip, H, W, K, flags,
-                want_fragments):
+                want_fragments, out_norm=None, out_dtype=None):
         # `verts` (packed (Vtot,3), same values as geom.verts) only carries autograd history for vertex gradients
         lib = L.load()
         dev = geom.device
@@ -505,7 +537,9 @@ class _MeshRender(torch.autograd.Function):
         bg_rgb = _f32c(bg_rgb)
         if geom.per_vertex_rgb:
             flags |= L.RGB_PER_ELEMENT
-        images = torch.empty((N, 3, H, W), dtype=torch.float32, device=dev)
+        img_dtype, dt_flag = _image_dtype(out_dtype)
+        flags |= dt_flag
+        images = torch.empty((N, 3, H, W), dtype=img_dtype, device=dev)
         p2f = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
         zbuf = bary = dists = None
         if want_fragments:
@@ -519,11 +553,11 @@ class _MeshRender(torch.autograd.Function):
             L.check(lib.mvr_mesh_forward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
                                          geom.total_verts, geom.total_faces, geom.max_verts, geom.max_faces, _ptr(R), _ptr(T), _ptr(Cc),
                                          _ptr(light), light_stride, _ptr(obj_rgb), _ptr(bg_rgb), k00, k11, z_clip, H, W,
-                                         K, flags, _ptr(images), _ptr(p2f), _ptr(zbuf), _ptr(bary), _ptr(dists),
+                                         K, flags, out_norm, _ptr(images), _ptr(p2f), _ptr(zbuf), _ptr(bary), _ptr(dists),
                                          _ptr(counters), _ptr(ws), ws.numel(), _stream(dev)), "mvr_mesh_forward")
         ctx.set_materialize_grads(False)      # no zero-filled "gradients" for pix_to_face & co (77 MB at C2)
         ctx.geom, ctx.M, ctx.light_stride = geom, M, light_stride
-        ctx.cfg = (k00, k11, H, W, K, flags)
+        ctx.cfg = (k00, k11, H, W, K, flags, out_norm)
         ctx.save_for_backward(R, T, Cc, light, obj_rgb if obj_rgb is not None else bg_rgb, p2f)
         extras = [p2f, counters]
         if want_fragments:
@@ -535,13 +569,13 @@ class _MeshRender(torch.autograd.Function):
     def backward(ctx, g_images, *_unused):
         lib = L.load()
         if g_images is None:
-            return (None,) * 17
+            return (None,) * 19
         geom, M = ctx.geom, ctx.M
         R, T, Cc, light, obj_rgb, p2f = ctx.saved_tensors
-        k00, k11, H, W, K, flags = ctx.cfg
+        k00, k11, H, W, K, flags, out_norm = ctx.cfg
         dev = geom.device
         N = geom.B * M
-        g_images = _f32c(g_images)
+        g_images = _grad_like_images(g_images, flags)
         gR = torch.empty((N, 3, 3), dtype=torch.float32, device=dev)
         gT = torch.empty((N, 3), dtype=torch.float32, device=dev)
         gC = torch.empty((N, 3), dtype=torch.float32, device=dev)
@@ -554,7 +588,7 @@ class _MeshRender(torch.autograd.Function):
         with _on(dev):
             L.check(lib.mvr_mesh_backward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
                                           geom.total_verts, geom.total_faces, geom.max_verts, _ptr(R), _ptr(T), _ptr(Cc), _ptr(light),
-                                          ctx.light_stride, _ptr(obj_rgb), k00, k11, H, W, K, flags, _ptr(p2f),
+                                          ctx.light_stride, _ptr(obj_rgb), k00, k11, H, W, K, flags, out_norm, _ptr(p2f),
                                           _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gC), _ptr(gV), _ptr(gN), _ptr(ws),
                                           ws.numel(), _stream(dev)), "mvr_mesh_backward")
         if gV is not None:
@@ -564,14 +598,16 @@ class _MeshRender(torch.autograd.Function):
                 v = geom.verts.detach().requires_grad_()
                 (gv2,) = torch.autograd.grad(vertex_normals_torch(v, geom.faces_global()), v, gN)
             gV = gV + gv2
-        return (gR, gT, gC, gV) + (None,) * 13
+        return (gR, gT, gC, gV) + (None,) * 15
 
 
 def render_meshes(geom: PackedMeshes, M: int, R, T, Cc, light, obj_rgb, bg_rgb, image_size: int, faces_per_pixel=1,
                   cull_backfaces=False, perspective_correct=True, fov=60.0, znear=1.0, z_clip: Optional[float] = None,
-                  fragments=False, verts: Optional[torch.Tensor] = None, _extra_flags=0):
+                  fragments=False, verts: Optional[torch.Tensor] = None, _extra_flags=0, normalize=None, out_dtype=None):
     """images (B*M,3,H,W) [+ dict of fragments].  HardPhong + hard blend, blur_radius 0.
-    `verts`: pass the packed (Vtot,3) vertex tensor the geometry was built from to get gradients w.r.t. it."""
+    `verts`: pass the packed (Vtot,3) vertex tensor the geometry was built from to get gradients w.r.t. it.
+    `normalize=(mean, std)` / `out_dtype=torch.bfloat16`: consumer-side fusion -- the kernel writes
+    (x - mean) / std (Trainer_mvt.py:41-49) in the dtype the CNN consumes; gradients flow through both."""
     H_, W_ = _hw(image_size)
     k00, k11 = fov_projection_scale(fov, znear, aspect=1.0)
     if z_clip is None:
@@ -579,7 +615,7 @@ def render_meshes(geom: PackedMeshes, M: int, R, T, Cc, light, obj_rgb, bg_rgb, 
     flags = (L.PERSPECTIVE_CORRECT if perspective_correct else 0) | (L.CULL_BACKFACES if cull_backfaces else 0) | _extra_flags
     H, W = _hw(image_size)
     out = _MeshRender.apply(R, T, Cc, verts, geom, M, light, obj_rgb, bg_rgb, k00, k11, float(z_clip), H, W,
-                            int(faces_per_pixel), flags, bool(fragments))
+                            int(faces_per_pixel), flags, bool(fragments), _out_norm(normalize), out_dtype)
     images, p2f, counters = out[0], out[1], out[2]
     frag = {"pix_to_face": p2f, "counters": counters}
     if fragments:
@@ -592,7 +628,8 @@ def render_meshes(geom: PackedMeshes, M: int, R, T, Cc, light, obj_rgb, bg_rgb, 
 # --------------------------------------------------------------------------------------------------
 class _PointsRender(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, R, T, inv_dist, points, rgb, M, radius, bg_rgb, H, W, K, flags, want_fragments):
+    def forward(ctx, R, T, inv_dist, points, rgb, M, radius, bg_rgb, H, W, K, flags, want_fragments, out_norm=None,
+                out_dtype=None):
         lib = L.load()
         _require_cuda(points, "points")
         dev = points.device
@@ -610,7 +647,9 @@ class _PointsRender(torch.autograd.Function):
                 raise ValueError("rgb must be a 3-vector or one colour per point (B,N,3)")
             flags |= L.RGB_PER_ELEMENT
         bg_rgb = _f32c(bg_rgb)
-        images = torch.empty((N, 3, H, W), dtype=torch.float32, device=dev)
+        img_dtype, dt_flag = _image_dtype(out_dtype)
+        flags |= dt_flag
+        images = torch.empty((N, 3, H, W), dtype=img_dtype, device=dev)
         idx = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
         zbuf = d2 = None
         if want_fragments:
@@ -621,10 +660,10 @@ class _PointsRender(torch.autograd.Function):
         mask = torch.empty(max(lib.mvr_points_hit_mask_words(B, M, H, W), 1), dtype=torch.int32, device=dev)
         with _on(dev):
             L.check(lib.mvr_points_forward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), float(radius),
-                                           _ptr(bg_rgb), H, W, K, flags, _ptr(images), _ptr(idx), _ptr(zbuf), _ptr(d2),
+                                           _ptr(bg_rgb), H, W, K, flags, out_norm, _ptr(images), _ptr(idx), _ptr(zbuf), _ptr(d2),
                                            _ptr(mask), _ptr(ws), ws.numel(), _stream(dev)), "mvr_points_forward")
         ctx.set_materialize_grads(False)
-        ctx.cfg = (B, Np, M, float(radius), H, W, K, flags)
+        ctx.cfg = (B, Np, M, float(radius), H, W, K, flags, out_norm)
         ctx.rgb_shape = rgb.shape
         ctx.points_shape = points.shape
         ctx.save_for_backward(R, T, inv_dist, pts, rgb, idx, mask)
@@ -636,12 +675,12 @@ class _PointsRender(torch.autograd.Function):
     def backward(ctx, g_images, *_unused):
         lib = L.load()
         if g_images is None:
-            return (None,) * 13
+            return (None,) * 15
         R, T, inv_dist, pts, rgb, idx, mask = ctx.saved_tensors
-        B, Np, M, radius, H, W, K, flags = ctx.cfg
+        B, Np, M, radius, H, W, K, flags, out_norm = ctx.cfg
         dev = pts.device
         N = B * M
-        g_images = _f32c(g_images)
+        g_images = _grad_like_images(g_images, flags)
         gR = torch.empty((N, 3, 3), dtype=torch.float32, device=dev)
         gT = torch.empty((N, 3), dtype=torch.float32, device=dev)
         gs = torch.empty(N, dtype=torch.float32, device=dev)
@@ -651,25 +690,26 @@ class _PointsRender(torch.autograd.Function):
         ws = workspace(dev, ws_bytes)
         with _on(dev):
             L.check(lib.mvr_points_backward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), radius, H,
-                                            W, K, flags, _ptr(idx), _ptr(mask), _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gs),
+                                            W, K, flags, out_norm, _ptr(idx), _ptr(mask), _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gs),
                                             _ptr(gP), _ptr(gF), _ptr(ws), ws.numel(), _stream(dev)),
                     "mvr_points_backward")
         if gP is not None:
             gP = gP.reshape(ctx.points_shape)
         if gF is not None:
             gF = gF.reshape(ctx.rgb_shape)
-        return (gR, gT, gs, gP, gF) + (None,) * 8
+        return (gR, gT, gs, gP, gF) + (None,) * 10
 
 
 def render_points(points, rgb, M: int, R, T, inv_dist, radius: float, bg_rgb, image_size: int, points_per_pixel=1,
-                  compositor="norm", fragments=False):
-    """images (B*M,3,H,W) [+ fragments].  compositor: "norm" (NormWeightedCompositor) | "alpha"."""
+                  compositor="norm", fragments=False, normalize=None, out_dtype=None):
+    """images (B*M,3,H,W) [+ fragments].  compositor: "norm" (NormWeightedCompositor) | "alpha".
+    normalize / out_dtype: as in render_meshes (consumer-side fusion)."""
     if compositor not in ("norm", "alpha"):
         raise ValueError("compositor must be 'norm' or 'alpha'")
     flags = L.COMPOSITE_ALPHA if compositor == "alpha" else 0
     H, W = _hw(image_size)
     out = _PointsRender.apply(R, T, inv_dist, points, rgb, M, radius, bg_rgb, H, W,
-                              int(points_per_pixel), flags, bool(fragments))
+                              int(points_per_pixel), flags, bool(fragments), _out_norm(normalize), out_dtype)
     frag = {"idx": out[1]}
     if fragments:
         frag.update(zbuf=out[2], dists=out[3])

@@ -96,11 +96,16 @@ class MVRenderer(nn.Module):
             FoV perspective cameras).
         cache_geometry: keep the packed device geometry of the last mesh batch and reuse it when the
             same list object is rendered again.
+        normalize: None or (mean, std) (3-vectors or scalars): the kernels write (image - mean) / std, the
+            normalisation viewGCN/tools/Trainer_mvt.py:41-49 applies before the CNN.
+        out_dtype: torch.float32 (default) or torch.bfloat16 -- the dtype the images are written in (a bf16 backbone
+            then reads them without a conversion pass); gradients flow through either.
     """
 
     def __init__(self, nb_views, image_size=224, pc_rendering=True, object_color="white", background_color="white",
                  faces_per_pixel=1, points_radius=0.006, points_per_pixel=1, light_direction="random",
-                 cull_backfaces=False, *, compositor="norm", perspective_correct=True, cache_geometry=False):
+                 cull_backfaces=False, *, compositor="norm", perspective_correct=True, cache_geometry=False,
+                 normalize=None, out_dtype=None):
         super().__init__()
         self.nb_views = nb_views
         self.image_size = image_size
@@ -115,6 +120,8 @@ class MVRenderer(nn.Module):
         self.compositor = compositor
         self.perspective_correct = perspective_correct
         self.cache_geometry = cache_geometry
+        self.normalize = normalize
+        self.out_dtype = out_dtype
         self._geom_cache = (None, None)
         self.last_fragments = None
 
@@ -175,7 +182,8 @@ class MVRenderer(nn.Module):
             light = C.detach() if fixed_light is None else fixed_light
             return ops.render_meshes(geom, self.nb_views, R, T, C, light, obj, bg, self.image_size,
                                      faces_per_pixel=self.faces_per_pixel, cull_backfaces=self.cull_backfaces,
-                                     perspective_correct=self.perspective_correct, verts=getattr(geom, "grad_verts", None))
+                                     perspective_correct=self.perspective_correct, verts=getattr(geom, "grad_verts", None),
+                                     normalize=self.normalize, out_dtype=self.out_dtype)
 
         try:
             (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
@@ -202,7 +210,8 @@ class MVRenderer(nn.Module):
         def render(R, T, C, dist_):
             inv_dist = 1.0 / dist_.reshape(-1)        # renderer.py:142 point_cloud.scale_(1/dist)
             return ops.render_points(pts, rgb, self.nb_views, R, T, inv_dist, self.points_radius, bg, self.image_size,
-                                     points_per_pixel=self.points_per_pixel, compositor=self.compositor)
+                                     points_per_pixel=self.points_per_pixel, compositor=self.compositor,
+                                     normalize=self.normalize, out_dtype=self.out_dtype)
 
         (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
         self.last_fragments = frag

@@ -433,7 +433,7 @@ def test_points_backward_without_hit_mask_matches(oracle, cuda_device):
     img2 = torch.empty_like(img); idx2 = torch.empty_like(idx)
     ws = ops.workspace(dev, lib.mvr_points_workspace_bytes(B, Np, M, H, W, K, 0.05))
     L.check(lib.mvr_points_forward(pts.data_ptr(), col.data_ptr(), B, Np, M, Rd.data_ptr(), Td.data_ptr(), inv.data_ptr(), 0.05,
-                                   torch.zeros(3, device=dev).data_ptr(), H, W, K, L.COMPOSITE_ALPHA, img2.data_ptr(), idx2.data_ptr(),
+                                   torch.zeros(3, device=dev).data_ptr(), H, W, K, L.COMPOSITE_ALPHA, None, img2.data_ptr(), idx2.data_ptr(),
                                    None, None, mask.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "fwd")
     assert torch.equal(idx2, idx) and torch.equal(img2, img)
     words = (W + 31) // 32
@@ -445,7 +445,7 @@ def test_points_backward_without_hit_mask_matches(oracle, cuda_device):
     for m_ptr in (mask.data_ptr(), None):
         gR = torch.empty(B * M, 3, 3, device=dev); gT = torch.empty(B * M, 3, device=dev); gs = torch.empty(B * M, device=dev)
         L.check(lib.mvr_points_backward(pts.data_ptr(), col.data_ptr(), B, Np, M, Rd.data_ptr(), Td.data_ptr(), inv.data_ptr(), 0.05, H, W, K,
-                                        L.COMPOSITE_ALPHA, idx.data_ptr(), m_ptr, g.data_ptr(), gR.data_ptr(), gT.data_ptr(), gs.data_ptr(),
+                                        L.COMPOSITE_ALPHA, None, idx.data_ptr(), m_ptr, g.data_ptr(), gR.data_ptr(), gT.data_ptr(), gs.data_ptr(),
                                         None, None, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "bwd")
         outs.append((gR, gT, gs))
     assert all(torch.equal(a, b) for a, b in zip(*outs))
@@ -696,3 +696,88 @@ def test_training_step_example_runs(cuda_device):
     assert out.returncode == 0, out.stderr[-2000:]
     assert "views/s end to end" in out.stdout and "|grad| into the view selector" in out.stdout
     assert float(out.stdout.strip().split()[-1]) > 0
+
+
+# ------------------------------------------------------------------------------------------ consumer-side fusion (8f N2)
+NORM = ((0.456, 0.456, 0.456), (0.225, 0.225, 0.225))      # viewGCN/tools/Trainer_mvt.py:41-49
+
+
+def _bf16_ulp_close(got_bf16, want_f32):
+    """bf16 keeps 8 significant bits: round-to-nearest is within 2^-9 relative, and a value known only to ~1e-5 may
+    land on the other neighbour -- allow one bf16 ulp (2^-8 relative) plus the fp32 tolerance."""
+    got = got_bf16.to(torch.float32)
+    return bool(((got - want_f32).abs() <= want_f32.abs() * 2.0 ** -8 + 1e-4).all())
+
+
+def test_mesh_normalized_and_bf16_output_matches_oracle(oracle, cuda_device):
+    """The shade kernel writes (image - mean) / std (and rounds to bf16 on request) instead of leaving a Normalize +
+    cast pass to the consumer; the backward takes the cotangent of THAT tensor.  Checked against the oracle's fp32
+    image pushed through the reference's own Normalize, and its gradients fed with g / std."""
+    dev = cuda_device
+    B, M, S = 2, 3, 80
+    meshes = synth.make_meshes(B, 1500, 52)
+    ml = [Meshes([v], [f]) for v, f in meshes]
+    az, el, di = synth.learned_spherical_views(B, M, 5)
+    mean = torch.tensor(NORM[0]).view(1, 3, 1, 1); std = torch.tensor(NORM[1]).view(1, 3, 1, 1)
+    g = torch.randn(B, M, 3, S, S, generator=torch.Generator().manual_seed(4))
+    grads = {}
+    for dt in (torch.float32, torch.bfloat16):
+        r = MVRenderer(M, image_size=S, pc_rendering=False, light_direction="fixed", normalize=NORM, out_dtype=dt).to(dev)
+        a, e, d = (t.to(dev).requires_grad_() for t in (az, el, di))
+        img, cams_ = r(ml, None, a, e, d)
+        assert img.dtype == dt and img.shape == (B, M, 3, S, S)
+        R, T, C = (x.detach().cpu().numpy() for x in (cams_.R, cams_.T, cams_._centers))
+        vp, fp, voff, foff = pack_np(meshes)
+        nrm = oracle.packed_vertex_normals(vp, fp, voff, foff)
+        white = np.full(3, 1 / 1.00001, np.float32)
+        o = oracle.mesh_forward(vp, fp, voff, foff, nrm, white, M, R, T, C, np.array([[0, 1.0, 0]], np.float32), white, K00, K11, 0.5,
+                                S, S, 1, oracle.PERSPECTIVE_CORRECT)
+        assert (r.last_fragments["pix_to_face"].cpu().numpy() == o["pix_to_face"]).all()
+        want = (torch.from_numpy(o["images"]) - mean) / std                     # Trainer_mvt.py:41-49 on the oracle image
+        got = img.detach().cpu().reshape(B * M, 3, S, S)
+        if dt is torch.float32:
+            assert float((got - want).abs().max()) <= IMG_ATOL / min(NORM[1])
+        else:
+            assert _bf16_ulp_close(got, want)
+        gd_ = g.to(dev).to(dt)
+        img.backward(gd_)
+        g_raw = (gd_.to(torch.float32).cpu().reshape(B * M, 3, S, S) / std).numpy()      # chain rule through Normalize
+        ob = oracle.mesh_backward(vp, fp, voff, foff, nrm, white, M, R, T, C, np.array([[0, 1.0, 0]], np.float32), K00, K11, S, S, 1,
+                                  oracle.PERSPECTIVE_CORRECT, o["pix_to_face"], g_raw)
+        ga, ge, gdd = oracle.look_at_backward(az.numpy().ravel(), el.numpy().ravel(), di.numpy().ravel(), ob["gR"], ob["gT"], ob["gC"])
+        assert rel(a.grad.reshape(-1), ga) < GRAD_RTOL and rel(e.grad.reshape(-1), ge) < GRAD_RTOL and rel(d.grad.reshape(-1), gdd) < GRAD_RTOL
+        grads[dt] = a.grad.clone()
+    assert float(grads[torch.float32].abs().max()) > 0
+
+
+def test_points_normalized_and_bf16_output_matches_oracle(oracle, cuda_device):
+    dev = cuda_device
+    B, M, S, K = 2, 3, 96, 4
+    pts = synth.make_clouds(B, 1024, 18)
+    az, el, di = synth.learned_spherical_views(B, M, 6)
+    mean = torch.tensor(NORM[0]).view(1, 3, 1, 1); std = torch.tensor(NORM[1]).view(1, 3, 1, 1)
+    g = torch.randn(B, M, 3, S, S, generator=torch.Generator().manual_seed(5))
+    for dt in (torch.float32, torch.bfloat16):
+        r = MVRenderer(M, image_size=S, pc_rendering=True, points_radius=0.02, points_per_pixel=K, background_color="black",
+                       compositor="alpha", normalize=NORM, out_dtype=dt).to(dev)
+        a, e, d = (t.to(dev).requires_grad_() for t in (az, el, di))
+        img, cams_ = r(None, pts, a, e, d)
+        assert img.dtype == dt
+        R, T = cams_.R.detach().cpu().numpy(), cams_.T.detach().cpu().numpy()
+        inv = (1.0 / di.reshape(-1)).numpy()
+        white = np.full(3, 1 / 1.00001, np.float32)
+        o = oracle.points_forward(pts.numpy(), white, M, R, T, inv, 0.02, np.zeros(3, np.float32), S, S, K, oracle.COMPOSITE_ALPHA)
+        assert (r.last_fragments["idx"].cpu().numpy() == o["idx"]).all()
+        want = (torch.from_numpy(o["images"]) - mean) / std
+        got = img.detach().cpu().reshape(B * M, 3, S, S)
+        if dt is torch.float32:
+            assert float((got - want).abs().max()) <= IMG_ATOL / min(NORM[1])
+        else:
+            assert _bf16_ulp_close(got, want)
+        gd_ = g.to(dev).to(dt)
+        img.backward(gd_)
+        g_raw = (gd_.to(torch.float32).cpu().reshape(B * M, 3, S, S) / std).numpy()
+        ob = oracle.points_backward(pts.numpy(), white, M, R, T, inv, 0.02, S, S, K, oracle.COMPOSITE_ALPHA, o["idx"], g_raw)
+        ga, ge, gdd = oracle.look_at_backward(az.numpy().ravel(), el.numpy().ravel(), di.numpy().ravel(), ob["gR"], ob["gT"], None)
+        gdd = gdd + ob["g_inv_dist"] * (-1.0 / di.numpy().ravel() ** 2)
+        assert rel(a.grad.reshape(-1), ga) < GRAD_RTOL and rel(e.grad.reshape(-1), ge) < GRAD_RTOL and rel(d.grad.reshape(-1), gdd) < GRAD_RTOL

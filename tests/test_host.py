@@ -47,14 +47,14 @@ def test_library_loads_and_answers_host_queries():
 def test_argument_validation_returns_status_not_crash():
     lib = _lib.load()
     # invalid arguments are rejected before any CUDA call: status < 0 and a message, never an exception/abort
-    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, 0.01, None, 0, 64, 1, 0, None, None, None, None, None, None, 0, None)
+    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, 0.01, None, 0, 64, 1, 0, None, None, None, None, None, None, None, 0, None)
     assert rc < 0 and b"image size" in lib.mvr_last_error_string()
-    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, 0.01, None, 64, 64, 200, 0, None, None, None, None, None, None, 0, None)
+    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, 0.01, None, 64, 64, 200, 0, None, None, None, None, None, None, None, 0, None)
     assert rc < 0 and b"points_per_pixel" in lib.mvr_last_error_string()
-    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, -1.0, None, 64, 64, 1, 0, None, None, None, None, None, None, 0, None)
+    rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, -1.0, None, 64, 64, 1, 0, None, None, None, None, None, None, None, 0, None)
     assert rc < 0 and b"radius" in lib.mvr_last_error_string()
     rc = lib.mvr_mesh_forward(None, None, None, 1, 1, 3, 1, 3, 1, None, None, None, None, 0, None, None, 1.7, 1.7, 0.5, 64, 64, 1, 0,
-                              None, None, None, None, None, None, None, 0, None)
+                              None, None, None, None, None, None, None, None, 0, None)
     assert rc < 0 and b"null pointer" in lib.mvr_last_error_string()
     rc = lib.mvr_mesh_prepare(None, None, None, None, 1, 10, 10, 10, None, 0, None, 16, None)
     assert rc < 0 and b"too small" in lib.mvr_last_error_string()
