@@ -7,8 +7,8 @@ Python host side that mirrors the reference's interface.  There is no CPU fallba
 """
 from .renderer import MVRenderer  # noqa: F401
 from .structures import Meshes  # noqa: F401
-from .ops import (HostPackedMeshes, PackedMeshes, collate_meshes, look_at_view_transform, render_meshes,  # noqa: F401
-                  render_points)
+from .ops import (HostPackedMeshes, PackedMeshes, camera_position_from_spherical_angles, collate_meshes,  # noqa: F401
+                  look_at_view_transform, render_meshes, render_points)
 from .cameras import (FoVOrthographicCameras, FoVPerspectiveCameras, OpenGLOrthographicCameras,  # noqa: F401
                       OpenGLPerspectiveCameras)
 

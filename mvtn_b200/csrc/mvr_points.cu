@@ -153,17 +153,88 @@ __global__ void __launch_bounds__(MVR_THREADS) points_scatter_kernel(const Point
   }
 }
 
-// Everything that happens to ONE pixel once its K ascending keys are known: hit-mask bit (warp ballot: call with all
-// 32 lanes, lane = x within a 32-pixel row word `mask_word`), idx / zbuf / dists2 of every layer, norm-weighted or alpha
-// compositing, background, planar image stores.  kreg: the keys in registers (KT > 0) or kp: their address (KT == 0).
+// A pixel no point covers: empty fragment slots and the background colour.
 template <int KT>
-__device__ __forceinline__ void composite_and_store(const PointsParams& p, const unsigned long long* kreg,
-                                                    const unsigned long long* kp, int b, int n, int xi, int yi,
-                                                    int mask_word, bool inside) {
+__device__ __forceinline__ void store_background_pixel(const PointsParams& p, int n, int xi, int yi) {
   const int K = KT > 0 ? KT : p.K;
   const size_t HW = (size_t)p.H * p.W;
   const size_t pix = (size_t)yi * p.W + xi;
   const size_t po = ((size_t)n * HW + pix) * K;
+  if (KT == 4) {
+    *reinterpret_cast<int4*>(p.idx + po) = make_int4(-1, -1, -1, -1);
+  } else {
+    for (int l = 0; l < K; ++l) p.idx[po + l] = -1;
+  }
+  if (p.zbuf || p.dists2)
+    for (int l = 0; l < K; ++l) {
+      if (p.zbuf) p.zbuf[po + l] = -1.f;
+      if (p.dists2) p.dists2[po + l] = -1.f;
+    }
+  store_rgb(p.images, p.flags & MVR_IMAGES_BF16, (size_t)n * 3 * HW + pix, HW, __ldg(p.bg_rgb), __ldg(p.bg_rgb + 1),
+            __ldg(p.bg_rgb + 2), p.onorm);
+}
+
+// A covered pixel, its K ascending keys known (kreg: in registers, KT > 0; kp: their address, KT == 0): idx / zbuf /
+// dists2 of every layer, norm-weighted or alpha compositing ([upstream] norm_weighted_sum / alpha_composite), planar
+// image stores.
+template <int KT>
+__device__ __forceinline__ void composite_hit_pixel(const PointsParams& p, const unsigned long long* kreg,
+                                                    const unsigned long long* kp, const Camera& cam, float s, int b, int n,
+                                                    int xi, int yi) {
+  const int K = KT > 0 ? KT : p.K;
+  const size_t HW = (size_t)p.H * p.W;
+  const size_t pix = (size_t)yi * p.W + xi;
+  const size_t po = ((size_t)n * HW + pix) * K;
+  const float xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H);
+  const float yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
+  const float* pts = p.points + 3 * (size_t)b * p.Np;
+  const bool per_point_rgb = p.flags & MVR_RGB_PER_ELEMENT;
+  const bool alpha_mode = p.flags & MVR_COMPOSITE_ALPHA;
+  const float* feat = per_point_rgb ? p.rgb + 3 * (size_t)b * p.Np : p.rgb;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, aw = alpha_mode ? 1.f : 0.f;
+  int ids[KT > 0 ? KT : 1];
+  bool open = true;      // layers are contiguous: the first EMPTY key ends them
+#pragma unroll
+  for (int l = 0; l < K; ++l) {
+    const unsigned long long key = KT > 0 ? kreg[KT > 0 ? l : 0] : kp[l];
+    open = open && key != MVR_EMPTY_KEY;
+    int q = -1;
+    float z = -1.f, d2 = -1.f;
+    if (open) {
+      q = (int)(unsigned int)(key & 0xffffffffull);
+      float px, py, pz;
+      project_point(pts, q, s, cam, px, py, pz);
+      const float dx = px - xf, dy = py - yf;
+      d2 = dx * dx + dy * dy;
+      z = __uint_as_float((unsigned int)(key >> 32));
+      const float a = 1.f - d2 / p.r2_weight;
+      const float* f = feat + (per_point_rgb ? 3 * (size_t)q : 0);
+      const float f0 = __ldg(f), f1 = __ldg(f + 1), f2 = __ldg(f + 2);
+      if (alpha_mode) {   // out += cum * alpha * f ; cum *= (1 - alpha)
+        const float ca = aw * a;
+        a0 += ca * f0; a1 += ca * f1; a2 += ca * f2;
+        aw = aw * (1.f - a);
+      } else {            // numerators and the alpha sum
+        a0 += a * f0; a1 += a * f1; a2 += a * f2;
+        aw += a;
+      }
+    }
+    if (KT == 4) ids[KT > 0 ? l : 0] = q; else p.idx[po + l] = q;
+    if (p.zbuf) p.zbuf[po + l] = z;
+    if (p.dists2) p.dists2[po + l] = d2;
+  }
+  if (KT == 4) *reinterpret_cast<int4*>(p.idx + po) = make_int4(ids[0], ids[KT > 1 ? 1 : 0], ids[KT > 2 ? 2 : 0], ids[KT > 3 ? 3 : 0]);
+  float o0 = a0, o1 = a1, o2 = a2;
+  if (!alpha_mode) { const float t = fmaxf(aw, 1e-4f); o0 = a0 / t; o1 = a1 / t; o2 = a2 / t; }
+  store_rgb(p.images, p.flags & MVR_IMAGES_BF16, (size_t)n * 3 * HW + pix, HW, o0, o1, o2, p.onorm);
+}
+
+// Everything that happens to ONE pixel once its K ascending keys are known: hit-mask bit (warp ballot: call with all
+// 32 lanes, lane = x within a 32-pixel row word `mask_word`), then the background or the composited pixel.
+template <int KT>
+__device__ __forceinline__ void composite_and_store(const PointsParams& p, const unsigned long long* kreg,
+                                                    const unsigned long long* kp, int b, int n, int xi, int yi,
+                                                    int mask_word, bool inside) {
   const unsigned long long key0 = inside ? (KT > 0 ? kreg[0] : kp[0]) : MVR_EMPTY_KEY;
   const bool hit = key0 != MVR_EMPTY_KEY;      // first-layer hit decides foreground ([upstream] _add_background_color_to_images)
   if (p.hit_mask) {
@@ -171,66 +242,9 @@ __device__ __forceinline__ void composite_and_store(const PointsParams& p, const
     if ((threadIdx.x & 31) == 0 && yi < p.H) p.hit_mask[((size_t)n * p.H + yi) * p.mask_words + mask_word] = mword;
   }
   if (!inside) return;
-  float o0 = __ldg(p.bg_rgb), o1 = __ldg(p.bg_rgb + 1), o2 = __ldg(p.bg_rgb + 2);
-  const bool want_frag = p.zbuf || p.dists2;
-  if (!hit) {
-    if (KT == 4) {
-      *reinterpret_cast<int4*>(p.idx + po) = make_int4(-1, -1, -1, -1);
-    } else {
-      for (int l = 0; l < K; ++l) p.idx[po + l] = -1;
-    }
-    if (want_frag)
-      for (int l = 0; l < K; ++l) {
-        if (p.zbuf) p.zbuf[po + l] = -1.f;
-        if (p.dists2) p.dists2[po + l] = -1.f;
-      }
-  } else {
-    const Camera cam = load_camera(p.R, p.T, n);
-    const float s = __ldg(p.inv_dist + n);
-    const float xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H);
-    const float yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
-    const float* pts = p.points + 3 * (size_t)b * p.Np;
-    const bool per_point_rgb = p.flags & MVR_RGB_PER_ELEMENT;
-    const bool alpha_mode = p.flags & MVR_COMPOSITE_ALPHA;
-    const float* feat = per_point_rgb ? p.rgb + 3 * (size_t)b * p.Np : p.rgb;
-    // ---- compositing over the layers ([upstream] norm_weighted_sum / alpha_composite) ----
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, aw = alpha_mode ? 1.f : 0.f;
-    int ids[KT > 0 ? KT : 1];
-    bool open = true;      // layers are contiguous: the first EMPTY key ends them
-#pragma unroll
-    for (int l = 0; l < K; ++l) {
-      const unsigned long long key = KT > 0 ? kreg[KT > 0 ? l : 0] : kp[l];
-      open = open && key != MVR_EMPTY_KEY;
-      int q = -1;
-      float z = -1.f, d2 = -1.f;
-      if (open) {
-        q = (int)(unsigned int)(key & 0xffffffffull);
-        float px, py, pz;
-        project_point(pts, q, s, cam, px, py, pz);
-        const float dx = px - xf, dy = py - yf;
-        d2 = dx * dx + dy * dy;
-        z = __uint_as_float((unsigned int)(key >> 32));
-        const float a = 1.f - d2 / p.r2_weight;
-        const float* f = feat + (per_point_rgb ? 3 * (size_t)q : 0);
-        const float f0 = __ldg(f), f1 = __ldg(f + 1), f2 = __ldg(f + 2);
-        if (alpha_mode) {   // out += cum * alpha * f ; cum *= (1 - alpha)
-          const float ca = aw * a;
-          a0 += ca * f0; a1 += ca * f1; a2 += ca * f2;
-          aw = aw * (1.f - a);
-        } else {            // numerators and the alpha sum
-          a0 += a * f0; a1 += a * f1; a2 += a * f2;
-          aw += a;
-        }
-      }
-      if (KT == 4) ids[KT > 0 ? l : 0] = q; else p.idx[po + l] = q;
-      if (p.zbuf) p.zbuf[po + l] = z;
-      if (p.dists2) p.dists2[po + l] = d2;
-    }
-    if (KT == 4) *reinterpret_cast<int4*>(p.idx + po) = make_int4(ids[0], ids[KT > 1 ? 1 : 0], ids[KT > 2 ? 2 : 0], ids[KT > 3 ? 3 : 0]);
-    if (alpha_mode) { o0 = a0; o1 = a1; o2 = a2; }
-    else { const float t = fmaxf(aw, 1e-4f); o0 = a0 / t; o1 = a1 / t; o2 = a2 / t; }
-  }
-  store_rgb(p.images, p.flags & MVR_IMAGES_BF16, (size_t)n * 3 * HW + pix, HW, o0, o1, o2, p.onorm);
+  if (!hit) { store_background_pixel<KT>(p, n, xi, yi); return; }
+  const Camera cam = load_camera(p.R, p.T, n);
+  composite_hit_pixel<KT>(p, kreg, kp, cam, __ldg(p.inv_dist + n), b, n, xi, yi);
 }
 
 // grid: x = 32x8-pixel tiles, y = view m, z = object b.  KT = K when K <= PK_MAX_REG (keys in registers), 0 = generic
@@ -403,16 +417,77 @@ __global__ void __launch_bounds__(MVR_THREADS) points_tile_kernel(const PointsPa
       __syncthreads();
     }
   }
-  // resolve: thread (lane, warp) owns pixels (x0 + lane, y0 + warp + 8 j)
+  // resolve.  The images are sparse (~10 % of the pixels are covered) and a covered pixel costs ~10x a background one,
+  // so the two are separated: pass 1 -- thread (lane, warp) owns pixels (x0 + lane, y0 + warp + 8 j) -- writes the hit
+  // mask and the background pixels (full coalesced rows) and compacts the covered pixels into a list in shared memory;
+  // pass 2 walks that list with every lane busy.
+  unsigned short* s_hits = reinterpret_cast<unsigned short*>(s_cand);      // the candidate queue is free by now
+  const bool have = beg < end;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  {
+    // per-view bases and the (normalised) background colour once per thread: the loop body is then 32-bit index
+    // arithmetic and stores
+    const size_t HW = (size_t)p.H * p.W;
+    int* idx_v = p.idx + (size_t)n * HW * KT;
+    float* zb_v = p.zbuf ? p.zbuf + (size_t)n * HW * KT : nullptr;
+    float* d2_v = p.dists2 ? p.dists2 + (size_t)n * HW * KT : nullptr;
+    unsigned int* mask_v = p.hit_mask ? p.hit_mask + (size_t)n * p.H * p.mask_words + tx : nullptr;
+    const bool bf16 = p.flags & MVR_IMAGES_BF16;
+    float* img_f = reinterpret_cast<float*>(p.images) + (size_t)n * 3 * HW;
+    __nv_bfloat16* img_h = reinterpret_cast<__nv_bfloat16*>(p.images) + (size_t)n * 3 * HW;
+    float g0 = __ldg(p.bg_rgb), g1 = __ldg(p.bg_rgb + 1), g2 = __ldg(p.bg_rgb + 2);
+    if (p.onorm.on) { g0 = (g0 - p.onorm.m0) * p.onorm.s0; g1 = (g1 - p.onorm.m1) * p.onorm.s1; g2 = (g2 - p.onorm.m2) * p.onorm.s2; }
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(g0), h1 = __float2bfloat16_rn(g1), h2 = __float2bfloat16_rn(g2);
+    const int hw = (int)HW, xi = x0 + lane;
 #pragma unroll 1
-  for (int j = 0; j < 4; ++j) {
-    const int row = warp + 8 * j;
-    const int xi = x0 + lane, yi = y0 + row;
-    const bool inside = xi < p.W && yi < p.H;
-    unsigned long long kreg[KT];
+    for (int j = 0; j < 4; ++j) {
+      const int row = warp + 8 * j, yi = y0 + row;
+      const bool inside = xi < p.W && yi < p.H;
+      const bool hit = inside && have && s_keys[(row << 5) + lane] != MVR_EMPTY_KEY;      // slot 0 decides foreground
+      const unsigned int mword = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0 && mask_v && yi < p.H) mask_v[yi * p.mask_words] = mword;
+      if (mword) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_n, __popc(mword));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) s_hits[base + __popc(mword & ((1u << lane) - 1u))] = (unsigned short)((row << 5) | lane);
+      }
+      if (inside && !hit) {                              // background pixel: empty fragment slots + background colour
+        const int pix = yi * p.W + xi;
+        if (KT == 4) {
+          *reinterpret_cast<int4*>(idx_v + 4 * pix) = make_int4(-1, -1, -1, -1);
+        } else if (KT == 2) {
+          *reinterpret_cast<int2*>(idx_v + 2 * pix) = make_int2(-1, -1);
+        } else {
 #pragma unroll
-    for (int k = 0; k < KT; ++k) kreg[k] = (beg < end) ? s_keys[k * 1024 + (row << 5) + lane] : MVR_EMPTY_KEY;
-    composite_and_store<KT>(p, kreg, nullptr, b, n, xi, yi, tx, inside);
+          for (int l = 0; l < KT; ++l) idx_v[KT * pix + l] = -1;
+        }
+        if (zb_v) {
+#pragma unroll
+          for (int l = 0; l < KT; ++l) zb_v[KT * pix + l] = -1.f;
+        }
+        if (d2_v) {
+#pragma unroll
+          for (int l = 0; l < KT; ++l) d2_v[KT * pix + l] = -1.f;
+        }
+        if (bf16) { img_h[pix] = h0; img_h[pix + hw] = h1; img_h[pix + 2 * hw] = h2; }
+        else { img_f[pix] = g0; img_f[pix + hw] = g1; img_f[pix + 2 * hw] = g2; }
+      }
+    }
+  }
+  __syncthreads();
+  const int nhit = s_n;
+  if (nhit > 0) {
+    const Camera cam = load_camera(p.R, p.T, n);
+    const float s = __ldg(p.inv_dist + n);
+    for (int i = tid; i < nhit; i += MVR_THREADS) {
+      const int q = s_hits[i];
+      unsigned long long kreg[KT];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) kreg[k] = s_keys[k * 1024 + q];
+      composite_hit_pixel<KT>(p, kreg, nullptr, cam, s, b, n, x0 + (q & 31), y0 + (q >> 5));
+    }
   }
 }
 

@@ -247,6 +247,17 @@ def look_at_view_transform(dist, elev, azim, return_centers=False, return_invali
     return tuple(out)
 
 
+def camera_position_from_spherical_angles(distance, elevation, azimuth, degrees: bool = True):
+    """[upstream] cameras.py camera_position_from_spherical_angles(distance, elevation, azimuth) -> (n,3) camera
+    centres, as used for the "relative" light (renderer.py:168) and for ViewGCN's graph vertices
+    (viewGCN/tools/Trainer_mvt.py:131-133).  Same kernel as look_at_view_transform (one launch yields
+    R, T and C), differentiable w.r.t. all three inputs.  Inputs may be (B, M): the result is in flat order b*M + m."""
+    if not degrees:
+        k = 180.0 / math.pi
+        elevation, azimuth = elevation * k, azimuth * k
+    return _LookAt.apply(azimuth, elevation, distance)[2]
+
+
 # --------------------------------------------------------------------------------------------------
 # packed geometry
 # --------------------------------------------------------------------------------------------------

@@ -73,6 +73,20 @@ def test_look_at_forward_backward(oracle, cuda_device):
     assert rel(a.grad, ga) < 1e-5 and rel(e.grad, ge) < 1e-5 and rel(d.grad, gd) < 1e-5
 
 
+def test_camera_position_from_spherical_angles(oracle, cuda_device):
+    """ViewGCN's graph vertices (Trainer_mvt.py:131-133) come from the same kernel as R and T."""
+    az = torch.linspace(-180, 180, 13)[:-1].repeat(3, 1) - 90; el = torch.full((3, 12), 35.0); di = torch.full((3, 12), 2.2)
+    d = di.to(cuda_device).requires_grad_()
+    C = ops.camera_position_from_spherical_angles(d, el.to(cuda_device), az.to(cuda_device))
+    _, _, Co = oracle.look_at(az.numpy().ravel(), el.numpy().ravel(), di.numpy().ravel())
+    assert C.shape == (36, 3) and np.abs(C.detach().cpu().numpy() - Co).max() < 2e-6
+    C.sum().backward()      # dC/d dist = C / dist
+    assert torch.allclose(d.grad.reshape(-1).cpu(), torch.from_numpy(Co).sum(1) / 2.2, atol=1e-5)
+    Cr = ops.camera_position_from_spherical_angles(di.to(cuda_device), torch.deg2rad(el).to(cuda_device),
+                                                   torch.deg2rad(az).to(cuda_device), degrees=False)
+    assert torch.allclose(Cr, C.detach(), atol=1e-5)
+
+
 def test_rotation_guard_flag_matches_oracle(oracle, cuda_device):
     # nan / inf angles and zero distance give invalid matrices; the fused device check must count like util.py:403-420
     az = torch.tensor([0.0, 10.0, float("nan"), 30.0]); el = torch.tensor([0.0, 20.0, 0.0, 0.0]); di = torch.tensor([2.2, 0.0, 2.0, 2.0])
