@@ -301,7 +301,9 @@ def run_ours(a):
     achieved = (per_view * N) / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
     try:   # DRAM bytes per launch of this kernel from the committed ncu capture (only valid for the default workload)
-        if a.workload == "mesh" and (B, M, S, a.faces) == (32, 12, 224, 10000):
+        default_mesh = a.workload == "mesh" and (B, M, S, a.faces) == (32, 12, 224, 10000)
+        default_points = a.workload == "points" and (B, M, S, a.points, a.points_per_pixel) == (32, 12, 224, 2048, 4)
+        if default_mesh or default_points:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[top]["bytes"]
     except Exception:
         traffic = None
