@@ -160,6 +160,7 @@ def run_ours(a):
     azim_h, elev_h, dist_h = (t.contiguous().pin_memory() for t in inp["views"])
     cot = torch.randn(N, 3, S, S, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank)) / (3 * S * S)
     bg = torch.tensor([0.99999] * 3, device=dev)
+    bg_black = torch.zeros(3, device=dev)
     obj = torch.tensor([0.99999] * 3, device=dev)
     light = torch.tensor([[0.0, 1.0, 0.0]], device=dev)
 
@@ -207,8 +208,8 @@ def run_ours(a):
             geom = ops.PackedMeshes.from_packed(verts_d, faces_d, nv, nf)
             img, _ = ops.render_meshes(geom, M, R, T, C, light, obj, bg, S)
         else:
-            img, _ = ops.render_points(pts_d, obj, M, R, T, 1.0 / di.reshape(-1), renderer.points_radius, bg * 0, S,
-                                       points_per_pixel=a.points_per_pixel, compositor="alpha")
+            img, _ = ops.render_points(pts_d, obj, M, R, T, None, renderer.points_radius, bg_black, S,
+                                       points_per_pixel=a.points_per_pixel, compositor="alpha", dist=di)
         img.backward(cot)
         return az.grad, el.grad, di.grad
 

@@ -35,6 +35,7 @@ extern "C" {
 #define MVR_RGB_PER_ELEMENT 8      /* per-vertex / per-point colours (object_color == "custom") */
 #define MVR_FACES_I64 16           /* faces given as int64 (F,3) -- the reference's layout, renderer.py:68 */
 #define MVR_IMAGES_BF16 32         /* images (forward) / grad_images (backward) are bfloat16 instead of float32 */
+#define MVR_SCALE_IS_DIST 64       /* points: the per-view scale array holds dist, not 1/dist (see mvr_points_forward) */
 #define MVR_TEST_TINY_QUEUES 0x40000000 /* tests only: shrink the scatter kernel's work queues to force their fallbacks */
 
 /* Phong constants of DirectionalLights() / Materials() as constructed at renderer.py:190-191 */
@@ -162,7 +163,8 @@ size_t mvr_points_hit_mask_words(int B, int M, int H, int W);
 /* PointsRenderer(PointsRasterizer, compositor)(Pointclouds.extend(M).scale_(1/dist))
  * (renderer.py:119-150; [upstream] _C.rasterize_points + accum_weightedsumnorm /
  * accum_alphacomposite + background).  points (B,Np,3); rgb (3) or (B*Np,3) [MVR_RGB_PER_ELEMENT];
- * inv_dist (n) = 1/dist; radius in NDC; K = points_per_pixel; out_mean_std / MVR_IMAGES_BF16 as in mvr_mesh_forward.
+ * inv_dist (n) = 1/dist, the scale of renderer.py:142 -- or dist itself with MVR_SCALE_IS_DIST (the kernels then take
+ * the IEEE reciprocal torch's `1.0 / dist` takes, and the backward returns d/d dist in g_inv_dist); radius in NDC; K = points_per_pixel; out_mean_std / MVR_IMAGES_BF16 as in mvr_mesh_forward.
  * outputs: images (n,3,H,W); idx (n,H,W,K) cloud-local point ids (-1 empty); optional zbuf,
  * dists2 (n,H,W,K); optional hit_mask (mvr_points_hit_mask_words words), which lets the backward pass skip
  * the ~90 % background pixels without reading idx. */

@@ -12,6 +12,7 @@ COMPOSITE_ALPHA = 4
 RGB_PER_ELEMENT = 8
 FACES_I64 = 16
 IMAGES_BF16 = 32
+SCALE_IS_DIST = 64
 TEST_TINY_QUEUES = 0x40000000   # tests only: shrink the scatter kernel's work queues to force their fallbacks
 CNT_STRADDLE, CNT_BIG_FACES, NUM_COUNTERS = 0, 1, 4
 

@@ -44,6 +44,14 @@ __device__ __forceinline__ void project_point(const float* __restrict__ pts, int
   world_to_view(cam, x, y, z, px, py, pz);
 }
 
+// per-view scale of the cloud (renderer.py:142 point_cloud.scale_(1 / dist)): the caller passes 1/dist, or dist itself
+// with MVR_SCALE_IS_DIST -- then the reciprocal is the IEEE division torch's `1.0 / dist` performs, bit for bit, and the
+// backward returns d/d dist instead of d/d (1/dist) (two elementwise launches and their autograd nodes less per step)
+__device__ __forceinline__ float view_scale(const float* __restrict__ scale, int flags, int n) {
+  const float v = __ldg(scale + n);
+  return (flags & MVR_SCALE_IS_DIST) ? __fdiv_rn(1.0f, v) : v;
+}
+
 __global__ void pixel_table_kernel(float* __restrict__ tab, int H, int W) { fill_pixel_table(tab, H, W, threadIdx.x, blockDim.x); }
 
 // insertion of one (z, point) key into the K ascending slots of a pixel (see the file header)
@@ -110,7 +118,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_scatter_kernel(const Point
   unsigned long long key = MVR_EMPTY_KEY;
   if (pi < p.Np) {
     const Camera cam = load_camera(p.R, p.T, n);
-    const float s = __ldg(p.inv_dist + n);
+    const float s = view_scale(p.inv_dist, p.flags, n);
     float pz;
     project_point(p.points + 3 * (size_t)b * p.Np, pi, s, cam, px, py, pz);
     if (!(pz < 0.f)) {
@@ -244,7 +252,7 @@ __device__ __forceinline__ void composite_and_store(const PointsParams& p, const
   if (!inside) return;
   if (!hit) { store_background_pixel<KT>(p, n, xi, yi); return; }
   const Camera cam = load_camera(p.R, p.T, n);
-  composite_hit_pixel<KT>(p, kreg, kp, cam, __ldg(p.inv_dist + n), b, n, xi, yi);
+  composite_hit_pixel<KT>(p, kreg, kp, cam, view_scale(p.inv_dist, p.flags, n), b, n, xi, yi);
 }
 
 // grid: x = 32x8-pixel tiles, y = view m, z = object b.  KT = K when K <= PK_MAX_REG (keys in registers), 0 = generic
@@ -296,7 +304,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_bin_kernel(const PointsPar
   int xl, xh, yl, yh;
   if (!FILL) {
     const Camera cam = load_camera(p.R, p.T, n);
-    const float s = __ldg(p.inv_dist + n);
+    const float s = view_scale(p.inv_dist, p.flags, n);
     float px, py, pz;
     project_point(p.points + 3 * (size_t)b * p.Np, pi, s, cam, px, py, pz);
     xl = 1; xh = 0; yl = 1; yh = 0;                       // empty window
@@ -480,7 +488,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_tile_kernel(const PointsPa
   const int nhit = s_n;
   if (nhit > 0) {
     const Camera cam = load_camera(p.R, p.T, n);
-    const float s = __ldg(p.inv_dist + n);
+    const float s = view_scale(p.inv_dist, p.flags, n);
     for (int i = tid; i < nhit; i += MVR_THREADS) {
       const int q = s_hits[i];
       unsigned long long kreg[KT];
@@ -562,7 +570,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   const Camera cam = load_camera(p.R, p.T, n);
-  const float s = __ldg(p.inv_dist + n);
+  const float s = view_scale(p.inv_dist, p.flags, n);
   const float inv_r2 = 1.f / p.r2_weight;
   for (int it = lane; it < total; it += 32) {
     const int code = s_list[warp][it];
@@ -640,7 +648,8 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
 }
 
 __global__ void points_backward_reduce_kernel(const float* __restrict__ partials, int N, int n_parts,
-                                              float* __restrict__ gR, float* __restrict__ gT, float* __restrict__ gs) {
+                                              float* __restrict__ gR, float* __restrict__ gT, float* __restrict__ gs,
+                                              const float* __restrict__ scale, int flags) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -650,7 +659,13 @@ __global__ void points_backward_reduce_kernel(const float* __restrict__ partials
   s += __shfl_xor_sync(0xffffffffu, s, 16);
   if (lane < 9) gR[9 * (size_t)n + lane] = s;
   else if (lane < 12) gT[3 * (size_t)n + lane - 9] = s;
-  else if (lane == 12) gs[n] = s;
+  else if (lane == 12) {
+    if (flags & MVR_SCALE_IS_DIST) {      // d(1/dist)/d dist = -(1/dist)^2
+      const float inv = __fdiv_rn(1.0f, __ldg(scale + n));
+      s = -s * (inv * inv);
+    }
+    gs[n] = s;
+  }
 }
 
 }  // namespace mvr
@@ -835,6 +850,6 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
   rc = check_launch("points_backward_kernel");
   if (rc) return rc;
   const int wpb = 8;
-  MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, w.ctas_per_view, gR, gT, g_inv_dist);
+  MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, w.ctas_per_view, gR, gT, g_inv_dist, inv_dist, flags);
   return check_launch("points_backward_reduce_kernel");
 }

@@ -41,7 +41,7 @@ def graphed_points_render(points: torch.Tensor, rgb: torch.Tensor, M: int, radiu
 
     def fn(az, el, di):
         R, T, _C, _bad = ops._LookAt.apply(az.reshape(-1), el.reshape(-1), di.reshape(-1))
-        img, _ = ops.render_points(points, rgb, M, R, T, 1.0 / di.reshape(-1), radius, bg, image_size,
+        img, _ = ops.render_points(points, rgb, M, R, T, None, radius, bg, image_size, dist=di,
                                    points_per_pixel=points_per_pixel, compositor=compositor)
         return img
 

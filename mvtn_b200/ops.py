@@ -194,22 +194,41 @@ def fov_projection_scale(fov_deg: float = 60.0, znear: float = 1.0, aspect: floa
 # --------------------------------------------------------------------------------------------------
 # cameras
 # --------------------------------------------------------------------------------------------------
+def _look_at_launch(azim, elev, dist):
+    """Flat fp32 copies of the angles + one mvr_look_at_forward launch -> (a, e, d, R, T, C, invalid flag)."""
+    _require_cuda(azim, "azim")
+    a, e, d = _f32c(azim).reshape(-1), _f32c(elev).reshape(-1), _f32c(dist).reshape(-1)
+    n = a.numel()
+    if e.numel() != n or d.numel() != n:
+        raise ValueError("azim, elev and dist must have the same number of elements")
+    dev = a.device
+    buf = torch.empty(15 * n, dtype=torch.float32, device=dev)      # one allocation: R | T | C
+    R, T, Cc = buf[: 9 * n].view(n, 3, 3), buf[9 * n: 12 * n].view(n, 3), buf[12 * n:].view(n, 3)
+    bad = torch.empty(1, dtype=torch.int32, device=dev)      # zeroed by mvr_look_at_forward
+    with _on(dev):
+        L.check(L.load().mvr_look_at_forward(_ptr(a), _ptr(e), _ptr(d), n, _ptr(R), _ptr(T), _ptr(Cc), _ptr(bad),
+                                             _stream(dev)), "mvr_look_at_forward")
+    return a, e, d, R, T, Cc, bad
+
+
+def _look_at_backward_launch(a, e, d, gR, gT, gC):
+    n = a.numel()
+    dev = a.device
+    gR = None if gR is None else _f32c(gR)
+    gT = None if gT is None else _f32c(gT)
+    gC = None if gC is None else _f32c(gC)
+    g = torch.empty(3 * n, dtype=torch.float32, device=dev)
+    ga, ge, gd = g[:n], g[n: 2 * n], g[2 * n:]
+    with _on(dev):
+        L.check(L.load().mvr_look_at_backward(_ptr(a), _ptr(e), _ptr(d), n, _ptr(gR), _ptr(gT), _ptr(gC), _ptr(ga),
+                                              _ptr(ge), _ptr(gd), _stream(dev)), "mvr_look_at_backward")
+    return ga, ge, gd
+
+
 class _LookAt(torch.autograd.Function):
     @staticmethod
     def forward(ctx, azim, elev, dist):
-        _require_cuda(azim, "azim")
-        lib = L.load()
-        a, e, d = _f32c(azim).reshape(-1), _f32c(elev).reshape(-1), _f32c(dist).reshape(-1)
-        n = a.numel()
-        if e.numel() != n or d.numel() != n:
-            raise ValueError("azim, elev and dist must have the same number of elements")
-        dev = a.device
-        buf = torch.empty(15 * n, dtype=torch.float32, device=dev)      # one allocation: R | T | C
-        R, T, Cc = buf[: 9 * n].view(n, 3, 3), buf[9 * n: 12 * n].view(n, 3), buf[12 * n:].view(n, 3)
-        bad = torch.empty(1, dtype=torch.int32, device=dev)      # zeroed by mvr_look_at_forward
-        with _on(dev):
-            L.check(lib.mvr_look_at_forward(_ptr(a), _ptr(e), _ptr(d), n, _ptr(R), _ptr(T), _ptr(Cc), _ptr(bad),
-                                            _stream(dev)), "mvr_look_at_forward")
+        a, e, d, R, T, Cc, bad = _look_at_launch(azim, elev, dist)
         ctx.save_for_backward(a, e, d)
         ctx.set_materialize_grads(False)
         ctx.shapes = (azim.shape, elev.shape, dist.shape)
@@ -218,19 +237,10 @@ class _LookAt(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gR, gT, gC, _gbad):
-        lib = L.load()
         a, e, d = ctx.saved_tensors
-        n = a.numel()
-        dev = a.device
         if gR is None and gT is None and gC is None:
             return None, None, None
-        gR = None if gR is None else _f32c(gR)
-        gT = None if gT is None else _f32c(gT)
-        gC = None if gC is None else _f32c(gC)
-        ga, ge, gd = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3))
-        with _on(dev):
-            L.check(lib.mvr_look_at_backward(_ptr(a), _ptr(e), _ptr(d), n, _ptr(gR), _ptr(gT), _ptr(gC), _ptr(ga),
-                                             _ptr(ge), _ptr(gd), _stream(dev)), "mvr_look_at_backward")
+        ga, ge, gd = _look_at_backward_launch(a, e, d, gR, gT, gC)
         sa, se, sd = ctx.shapes
         return ga.reshape(sa), ge.reshape(se), gd.reshape(sd)
 
@@ -529,87 +539,161 @@ def vertex_normals_torch(verts: torch.Tensor, faces: torch.Tensor) -> torch.Tens
 # --------------------------------------------------------------------------------------------------
 # mesh rendering
 # --------------------------------------------------------------------------------------------------
+def _mesh_forward_launch(geom: "PackedMeshes", M, R, T, Cc, light, obj_rgb, bg_rgb, k00, k11, z_clip, H, W, K, flags,
+                         want_fragments, out_norm, out_dtype):
+    """Argument normalisation, output allocation and ONE mvr_mesh_forward call.  Returns (saved, images, extras): `saved` is
+    what the matching backward launch needs."""
+    lib = L.load()
+    dev = geom.device
+    R, T, Cc = _f32c(R), _f32c(T), _f32c(Cc)
+    N = geom.B * M
+    if R.shape[0] != N:
+        raise ValueError(f"expected {N} cameras (B*M), got {R.shape[0]}")
+    light = _f32c(light).reshape(-1, 3)
+    if light.shape[0] not in (1, N):
+        raise ValueError("light direction must be (1,3) or (B*M,3)")
+    light_stride = 0 if light.shape[0] == 1 else 3
+    obj_rgb = None if obj_rgb is None else _f32c(obj_rgb)
+    bg_rgb = _f32c(bg_rgb)
+    if geom.per_vertex_rgb:
+        flags |= L.RGB_PER_ELEMENT
+    img_dtype, dt_flag = _image_dtype(out_dtype)
+    flags |= dt_flag
+    images = torch.empty((N, 3, H, W), dtype=img_dtype, device=dev)
+    p2f = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
+    zbuf = bary = dists = None
+    if want_fragments:
+        zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
+        dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+    counters = torch.empty(L.NUM_COUNTERS, dtype=torch.int64, device=dev)      # zeroed by mvr_mesh_forward
+    ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts)
+    ws = workspace(dev, ws_bytes)
+    with _on(dev):
+        L.check(lib.mvr_mesh_forward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
+                                     geom.total_verts, geom.total_faces, geom.max_verts, geom.max_faces, _ptr(R), _ptr(T), _ptr(Cc),
+                                     _ptr(light), light_stride, _ptr(obj_rgb), _ptr(bg_rgb), k00, k11, z_clip, H, W,
+                                     K, flags, out_norm, _ptr(images), _ptr(p2f), _ptr(zbuf), _ptr(bary), _ptr(dists),
+                                     _ptr(counters), _ptr(ws), ws.numel(), _stream(dev)), "mvr_mesh_forward")
+    cfg = (k00, k11, H, W, K, flags, out_norm, light_stride)
+    saved = (R, T, Cc, light, obj_rgb if obj_rgb is not None else bg_rgb, p2f)
+    extras = [p2f, counters]
+    if want_fragments:
+        extras += [zbuf, bary, dists]
+    return cfg, saved, images, extras
+
+
+def _mesh_backward_launch(geom: "PackedMeshes", M, cfg, saved, g_images, want_verts):
+    """ONE mvr_mesh_backward call -> (gR, gT, gC, gV | None) (gV includes the torch chain through the vertex normals)."""
+    lib = L.load()
+    R, T, Cc, light, obj_rgb, p2f = saved
+    k00, k11, H, W, K, flags, out_norm, light_stride = cfg
+    dev = geom.device
+    N = geom.B * M
+    g_images = _grad_like_images(g_images, flags)
+    g = torch.empty(15 * N, dtype=torch.float32, device=dev)
+    gR, gT, gC = g[: 9 * N].view(N, 3, 3), g[9 * N: 12 * N].view(N, 3), g[12 * N:].view(N, 3)
+    ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts)
+    ws = workspace(dev, ws_bytes)
+    gV = gN = None
+    if want_verts:
+        gV = torch.zeros((geom.total_verts, 3), dtype=torch.float32, device=dev)
+        gN = torch.zeros((geom.total_verts, 3), dtype=torch.float32, device=dev)
+    with _on(dev):
+        L.check(lib.mvr_mesh_backward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
+                                      geom.total_verts, geom.total_faces, geom.max_verts, _ptr(R), _ptr(T), _ptr(Cc), _ptr(light),
+                                      light_stride, _ptr(obj_rgb), k00, k11, H, W, K, flags, out_norm, _ptr(p2f),
+                                      _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gC), _ptr(gV), _ptr(gN), _ptr(ws),
+                                      ws.numel(), _stream(dev)), "mvr_mesh_backward")
+    if gV is not None:
+        # the kernel returns d/d verts through projection + interpolated position, and d/d unit normals;
+        # the normals -> verts chain ([upstream] Meshes._compute_vertex_normals) is optional plumbing in torch
+        with torch.enable_grad():
+            v = geom.verts.detach().requires_grad_()
+            (gv2,) = torch.autograd.grad(vertex_normals_torch(v, geom.faces_global()), v, gN)
+        gV = gV + gv2
+    return gR, gT, gC, gV
+
+
 class _MeshRender(torch.autograd.Function):
     @staticmethod
     def forward(ctx, R, T, Cc, verts, geom: PackedMeshes, M, light, obj_rgb, bg_rgb, k00, k11, z_clip, H, W, K, flags,
                 want_fragments, out_norm=None, out_dtype=None):
         # `verts` (packed (Vtot,3), same values as geom.verts) only carries autograd history for vertex gradients
-        lib = L.load()
-        dev = geom.device
-        R, T, Cc = _f32c(R), _f32c(T), _f32c(Cc)
-        N = geom.B * M
-        if R.shape[0] != N:
-            raise ValueError(f"expected {N} cameras (B*M), got {R.shape[0]}")
-        light = _f32c(light).reshape(-1, 3)
-        if light.shape[0] not in (1, N):
-            raise ValueError("light direction must be (1,3) or (B*M,3)")
-        light_stride = 0 if light.shape[0] == 1 else 3
-        obj_rgb = None if obj_rgb is None else _f32c(obj_rgb)
-        bg_rgb = _f32c(bg_rgb)
-        if geom.per_vertex_rgb:
-            flags |= L.RGB_PER_ELEMENT
-        img_dtype, dt_flag = _image_dtype(out_dtype)
-        flags |= dt_flag
-        images = torch.empty((N, 3, H, W), dtype=img_dtype, device=dev)
-        p2f = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
-        zbuf = bary = dists = None
-        if want_fragments:
-            zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
-            bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
-            dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
-        counters = torch.empty(L.NUM_COUNTERS, dtype=torch.int64, device=dev)      # zeroed by mvr_mesh_forward
-        ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts)
-        ws = workspace(dev, ws_bytes)
-        with _on(dev):
-            L.check(lib.mvr_mesh_forward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
-                                         geom.total_verts, geom.total_faces, geom.max_verts, geom.max_faces, _ptr(R), _ptr(T), _ptr(Cc),
-                                         _ptr(light), light_stride, _ptr(obj_rgb), _ptr(bg_rgb), k00, k11, z_clip, H, W,
-                                         K, flags, out_norm, _ptr(images), _ptr(p2f), _ptr(zbuf), _ptr(bary), _ptr(dists),
-                                         _ptr(counters), _ptr(ws), ws.numel(), _stream(dev)), "mvr_mesh_forward")
+        cfg, saved, images, extras = _mesh_forward_launch(geom, M, R, T, Cc, light, obj_rgb, bg_rgb, k00, k11, z_clip, H, W, K,
+                                                          flags, want_fragments, out_norm, out_dtype)
         ctx.set_materialize_grads(False)      # no zero-filled "gradients" for pix_to_face & co (77 MB at C2)
-        ctx.geom, ctx.M, ctx.light_stride = geom, M, light_stride
-        ctx.cfg = (k00, k11, H, W, K, flags, out_norm)
-        ctx.save_for_backward(R, T, Cc, light, obj_rgb if obj_rgb is not None else bg_rgb, p2f)
-        extras = [p2f, counters]
-        if want_fragments:
-            extras += [zbuf, bary, dists]
+        ctx.geom, ctx.M, ctx.cfg = geom, M, cfg
+        ctx.save_for_backward(*saved)
         ctx.mark_non_differentiable(*extras)
         return (images, *extras)
 
     @staticmethod
     def backward(ctx, g_images, *_unused):
-        lib = L.load()
         if g_images is None:
             return (None,) * 19
-        geom, M = ctx.geom, ctx.M
-        R, T, Cc, light, obj_rgb, p2f = ctx.saved_tensors
-        k00, k11, H, W, K, flags, out_norm = ctx.cfg
-        dev = geom.device
-        N = geom.B * M
-        g_images = _grad_like_images(g_images, flags)
-        gR = torch.empty((N, 3, 3), dtype=torch.float32, device=dev)
-        gT = torch.empty((N, 3), dtype=torch.float32, device=dev)
-        gC = torch.empty((N, 3), dtype=torch.float32, device=dev)
-        ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts)
-        ws = workspace(dev, ws_bytes)
-        gV = gN = None
-        if ctx.needs_input_grad[3]:
-            gV = torch.zeros((geom.total_verts, 3), dtype=torch.float32, device=dev)
-            gN = torch.zeros((geom.total_verts, 3), dtype=torch.float32, device=dev)
-        with _on(dev):
-            L.check(lib.mvr_mesh_backward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
-                                          geom.total_verts, geom.total_faces, geom.max_verts, _ptr(R), _ptr(T), _ptr(Cc), _ptr(light),
-                                          ctx.light_stride, _ptr(obj_rgb), k00, k11, H, W, K, flags, out_norm, _ptr(p2f),
-                                          _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gC), _ptr(gV), _ptr(gN), _ptr(ws),
-                                          ws.numel(), _stream(dev)), "mvr_mesh_backward")
-        if gV is not None:
-            # the kernel returns d/d verts through projection + interpolated position, and d/d unit normals;
-            # the normals -> verts chain ([upstream] Meshes._compute_vertex_normals) is optional plumbing in torch
-            with torch.enable_grad():
-                v = geom.verts.detach().requires_grad_()
-                (gv2,) = torch.autograd.grad(vertex_normals_torch(v, geom.faces_global()), v, gN)
-            gV = gV + gv2
+        gR, gT, gC, gV = _mesh_backward_launch(ctx.geom, ctx.M, ctx.cfg, ctx.saved_tensors, g_images, ctx.needs_input_grad[3])
         return (gR, gT, gC, gV) + (None,) * 15
+
+
+class _MeshRenderFromAngles(torch.autograd.Function):
+    """look_at + mesh render as ONE autograd node: (azim, elev, dist) -> images (+ R, T, C, pix_to_face, counters).
+    Same two C-ABI launches as _LookAt followed by _MeshRender, without the second Function.apply and the tensor
+    plumbing between them -- on the end-to-end step the GPU has the geometry before the host has reached
+    mvr_mesh_forward, so host microseconds in front of that call are step time.
+    light=None: the "relative" light, i.e. the (detached) camera centres (renderer.py:168).
+    after_cameras: called with the invalid-rotation flag tensor right after the camera kernel has been enqueued (the
+    renderer records its event there, in front of the rasterizer)."""
+
+    @staticmethod
+    def forward(ctx, azim, elev, dist, geom: PackedMeshes, M, light, obj_rgb, bg_rgb, k00, k11, z_clip, H, W, K, flags,
+                out_norm, out_dtype, after_cameras):
+        a, e, d, R, T, Cc, bad = _look_at_launch(azim, elev, dist)
+        if after_cameras is not None:
+            after_cameras(bad)
+        cfg, saved, images, extras = _mesh_forward_launch(geom, M, R, T, Cc, Cc if light is None else light, obj_rgb, bg_rgb,
+                                                          k00, k11, z_clip, H, W, K, flags, False, out_norm, out_dtype)
+        ctx.set_materialize_grads(False)
+        ctx.geom, ctx.M, ctx.cfg = geom, M, cfg
+        ctx.shapes = (azim.shape, elev.shape, dist.shape)
+        ctx.save_for_backward(a, e, d, *saved)
+        ctx.mark_non_differentiable(bad, *extras)
+        return (images, R, T, Cc, bad, *extras)
+
+    @staticmethod
+    def backward(ctx, g_images, gR_ext, gT_ext, gC_ext, *_unused):
+        if g_images is None and gR_ext is None and gT_ext is None and gC_ext is None:
+            return (None,) * 18
+        a, e, d = ctx.saved_tensors[:3]
+        gR = gT = gC = None
+        if g_images is not None:
+            gR, gT, gC, _ = _mesh_backward_launch(ctx.geom, ctx.M, ctx.cfg, ctx.saved_tensors[3:], g_images, False)
+        # R, T, C are outputs too (the cameras object): gradients a caller sends through them join the renderer's
+        if gR_ext is not None:
+            gR = gR_ext if gR is None else gR + gR_ext
+        if gT_ext is not None:
+            gT = gT_ext if gT is None else gT + gT_ext
+        if gC_ext is not None:
+            gC = gC_ext if gC is None else gC + gC_ext
+        ga, ge, gd = _look_at_backward_launch(a, e, d, gR, gT, gC)
+        sa, se, sd = ctx.shapes
+        return (ga.reshape(sa), ge.reshape(se), gd.reshape(sd)) + (None,) * 15
+
+
+def render_meshes_from_angles(geom: PackedMeshes, M: int, azim, elev, dist, light, obj_rgb, bg_rgb, image_size,
+                              faces_per_pixel=1, cull_backfaces=False, perspective_correct=True, fov=60.0, znear=1.0,
+                              z_clip: Optional[float] = None, normalize=None, out_dtype=None, after_cameras=None):
+    """look_at_view_transform + render_meshes in one autograd node (see _MeshRenderFromAngles).
+    Returns images (B*M,3,H,W), (R, T, C, invalid flag), fragments dict."""
+    k00, k11 = fov_projection_scale(fov, znear, aspect=1.0)
+    if z_clip is None:
+        z_clip = znear / 2 if perspective_correct else -1.0
+    flags = (L.PERSPECTIVE_CORRECT if perspective_correct else 0) | (L.CULL_BACKFACES if cull_backfaces else 0)
+    H, W = _hw(image_size)
+    images, R, T, Cc, bad, p2f, counters = _MeshRenderFromAngles.apply(
+        azim, elev, dist, geom, M, light, obj_rgb, bg_rgb, k00, k11, float(z_clip), H, W, int(faces_per_pixel), flags,
+        _out_norm(normalize), out_dtype, after_cameras)
+    return images, (R, T, Cc, bad), {"pix_to_face": p2f, "counters": counters}
 
 
 def render_meshes(geom: PackedMeshes, M: int, R, T, Cc, light, obj_rgb, bg_rgb, image_size: int, faces_per_pixel=1,
@@ -649,6 +733,7 @@ class _PointsRender(torch.autograd.Function):
             raise ValueError("points must be (B,N,3)")
         B, Np, _ = pts.shape
         N = B * M
+        scale_shape = inv_dist.shape
         R, T, inv_dist = _f32c(R), _f32c(T), _f32c(inv_dist).reshape(-1)
         if R.shape[0] != N or inv_dist.numel() != N:
             raise ValueError(f"expected {N} cameras (B*M)")
@@ -677,6 +762,7 @@ class _PointsRender(torch.autograd.Function):
         ctx.cfg = (B, Np, M, float(radius), H, W, K, flags, out_norm)
         ctx.rgb_shape = rgb.shape
         ctx.points_shape = points.shape
+        ctx.scale_shape = scale_shape
         ctx.save_for_backward(R, T, inv_dist, pts, rgb, idx, mask)
         extras = [idx] + ([zbuf, d2] if want_fragments else [])
         ctx.mark_non_differentiable(*extras)
@@ -708,16 +794,24 @@ class _PointsRender(torch.autograd.Function):
             gP = gP.reshape(ctx.points_shape)
         if gF is not None:
             gF = gF.reshape(ctx.rgb_shape)
-        return (gR, gT, gs, gP, gF) + (None,) * 10
+        return (gR, gT, gs.reshape(ctx.scale_shape), gP, gF) + (None,) * 10
 
 
 def render_points(points, rgb, M: int, R, T, inv_dist, radius: float, bg_rgb, image_size: int, points_per_pixel=1,
-                  compositor="norm", fragments=False, normalize=None, out_dtype=None):
+                  compositor="norm", fragments=False, normalize=None, out_dtype=None, dist=None):
     """images (B*M,3,H,W) [+ fragments].  compositor: "norm" (NormWeightedCompositor) | "alpha".
+    The clouds are scaled by inv_dist (renderer.py:142 scale_(1 / dist)); pass inv_dist=None and dist=(B*M,) or (B, M)
+    to have the kernels take the reciprocal themselves (same IEEE division as torch's 1.0 / dist) and return the gradient
+    w.r.t. dist directly -- no elementwise launches or autograd nodes around the renderer.
     normalize / out_dtype: as in render_meshes (consumer-side fusion)."""
     if compositor not in ("norm", "alpha"):
         raise ValueError("compositor must be 'norm' or 'alpha'")
     flags = L.COMPOSITE_ALPHA if compositor == "alpha" else 0
+    if (inv_dist is None) == (dist is None):
+        raise ValueError("pass exactly one of inv_dist and dist")
+    if dist is not None:
+        inv_dist = dist
+        flags |= L.SCALE_IS_DIST
     H, W = _hw(image_size)
     out = _PointsRender.apply(R, T, inv_dist, points, rgb, M, radius, bg_rgb, H, W,
                               int(points_per_pixel), flags, bool(fragments), _out_norm(normalize), out_dtype)

@@ -133,15 +133,19 @@ class MVRenderer(nn.Module):
             raise MVRError("MVRenderer needs a CUDA device: mvtn_b200 has no CPU path")
         return torch.device("cuda", torch.cuda.current_device())
 
-    def _cameras(self, azim, elev, dist, device):
-        """look_at_view_transform + check_and_correct_rotation_matrix (renderer.py:79-82, ops.py:156-165).
-        The validity test is fused into the look_at kernel; its flag is read AFTER the render has been
-        enqueued (see forward), so the reference's host sync does not stall the pipeline."""
+    def _views(self, azim, elev, dist, device):
         azim, elev, dist = (t.to(device) if t.device != device else t for t in (azim, elev, dist))
         if azim.shape != elev.shape or azim.shape != dist.shape or azim.dim() != 2:
             raise ValueError("azim, elev and dist must all be (B, M)")
         if azim.shape[1] != self.nb_views:
             raise ValueError(f"expected {self.nb_views} views, got {azim.shape[1]}")
+        return azim, elev, dist
+
+    def _cameras(self, azim, elev, dist, device):
+        """look_at_view_transform + check_and_correct_rotation_matrix (renderer.py:79-82, ops.py:156-165).
+        The validity test is fused into the look_at kernel; its flag is read AFTER the render has been
+        enqueued (see forward), so the reference's host sync does not stall the pipeline."""
+        azim, elev, dist = self._views(azim, elev, dist, device)
         R, T, C, bad = ops._LookAt.apply(azim, elev, dist)      # flattens (B, M) -> B*M itself, flat order b*M + m
         return azim, elev, dist, R, T, C, bad
 
@@ -186,7 +190,23 @@ class MVRenderer(nn.Module):
                                      normalize=self.normalize, out_dtype=self.out_dtype)
 
         try:
-            (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
+            out = None
+            if getattr(geom, "grad_verts", None) is None:
+                # fast path: cameras + rasterizer as ONE autograd node (ops.render_meshes_from_angles); the validity flag
+                # is still awaited through an event recorded between the camera kernel and the rasterizer
+                az, el, di = self._views(azim, elev, dist, device)
+                geom.finish()
+                reader = []
+                images, (R, T, C, _bad), frag = ops.render_meshes_from_angles(
+                    geom, self.nb_views, az, el, di, fixed_light, obj, bg, self.image_size,
+                    faces_per_pixel=self.faces_per_pixel, cull_backfaces=self.cull_backfaces,
+                    perspective_correct=self.perspective_correct, normalize=self.normalize, out_dtype=self.out_dtype,
+                    after_cameras=lambda bad: reader.append(_flag_reader(bad)))
+                if reader[0]() == 0:
+                    out = (images, frag)
+            if out is None:      # vertex gradients wanted, or invalid rotations: the general path with the redraw loop
+                out, R, T, C = self._render_with_guard(azim, elev, dist, device, render)
+            images, frag = out
         finally:
             geom.finish()      # never leave a deferred / in-flight staging behind (e.g. when the cameras were rejected)
         self.last_fragments = frag
@@ -208,10 +228,10 @@ class MVRenderer(nn.Module):
             rgb = rgb.to(device) * torch.ones_like(pts)          # renderer.py:119-120 features = color * ones_like(points)
 
         def render(R, T, C, dist_):
-            inv_dist = 1.0 / dist_.reshape(-1)        # renderer.py:142 point_cloud.scale_(1/dist)
-            return ops.render_points(pts, rgb, self.nb_views, R, T, inv_dist, self.points_radius, bg, self.image_size,
+            # renderer.py:142 point_cloud.scale_(1/dist): the reciprocal is taken inside the kernels (dist=)
+            return ops.render_points(pts, rgb, self.nb_views, R, T, None, self.points_radius, bg, self.image_size,
                                      points_per_pixel=self.points_per_pixel, compositor=self.compositor,
-                                     normalize=self.normalize, out_dtype=self.out_dtype)
+                                     normalize=self.normalize, out_dtype=self.out_dtype, dist=dist_)
 
         (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
         self.last_fragments = frag
