@@ -276,6 +276,62 @@ static inline void bary_persp_forward(const float w[3], float z0, float z1, floa
   b[0] = t0 / denom; b[1] = t1 / denom; b[2] = t2 / denom;
 }
 
+/* [upstream] renderer/mesh/clip.py clip_faces / _find_verts_intersecting_clipping_plane (z plane only: MeshRasterizer
+ * passes cull_to_frustum=False).  A face with one or two vertices behind z = c is replaced by one (case 3: two
+ * behind) or two (case 4: one behind) triangles:
+ *     p1 = the lone vertex (in front for case 3, behind for case 4), p2, p3 = the next two in cyclic order,
+ *     w2 = (p1.z - c) / (p1.z - p2.z), w3 = (p1.z - c) / (p1.z - p3.z),
+ *     p4 = p1 (1 - w2) + p2 w2, p5 = p1 (1 - w3) + p3 w3 -- with perspective_correct the xy are interpolated
+ *     un-projected: ((p1.xy p1.z)(1 - w) + (p2.xy p2.z) w) / c,
+ *     case 3 -> (p4, p5, p1);  case 4 -> (p4, p2, p5), (p5, p2, p3)  (consecutive in the clipped face list).
+ * conv[s][3 j + k] = barycentric weight of ORIGINAL vertex j in clipped vertex k of sub-triangle s
+ * (convert_clipped_rasterization_to_original_faces: bary_unclipped = conv . bary_clipped).
+ * Returns the number of sub-triangles (1 or 2), or 0 when the face does not straddle the plane.
+ * info: i1 | case4 << 2 (for the backward). */
+static int clip_face(const float* v, float c, int persp, float sub[2][9], float conv[2][9], int* info) {
+  const int b0 = v[2] < c, b1 = v[5] < c, b2 = v[8] < c;
+  const int nb = b0 + b1 + b2;
+  if (nb == 0 || nb == 3) return 0;
+  const int case4 = nb == 1;
+  int i1;
+  if (case4) i1 = b0 ? 0 : (b1 ? 1 : 2);       /* the vertex behind */
+  else i1 = !b0 ? 0 : (!b1 ? 1 : 2);           /* the vertex in front */
+  const int i2 = (i1 + 1) % 3, i3 = (i1 + 2) % 3;
+  const float* p1 = v + 3 * i1; const float* p2 = v + 3 * i2; const float* p3 = v + 3 * i3;
+  const float w2 = (p1[2] - c) / (p1[2] - p2[2]);
+  const float w3 = (p1[2] - c) / (p1[2] - p3[2]);
+  const float om2 = 1.0f - w2, om3 = 1.0f - w3;
+  float p4[3], p5[3];
+  for (int d = 0; d < 3; ++d) { p4[d] = p1[d] * om2 + p2[d] * w2; p5[d] = p1[d] * om3 + p3[d] * w3; }
+  if (persp) {
+    for (int d = 0; d < 2; ++d) {
+      const float a1 = p1[d] * p1[2], a2 = p2[d] * p2[2], a3 = p3[d] * p3[2];
+      p4[d] = (a1 * om2 + a2 * w2) / c;
+      p5[d] = (a1 * om3 + a3 * w3) / c;
+    }
+  }
+  float bc[5][3];                                /* barycentrics of p1..p5 in the original triangle */
+  memset(bc, 0, sizeof(bc));
+  bc[0][i1] = 1.f; bc[1][i2] = 1.f; bc[2][i3] = 1.f;
+  bc[3][i1] = om2; bc[3][i2] = w2;
+  bc[4][i1] = om3; bc[4][i3] = w3;
+  const float* P[5] = {p1, p2, p3, p4, p5};
+  int pick[2][3];
+  int ns;
+  if (!case4) { ns = 1; pick[0][0] = 3; pick[0][1] = 4; pick[0][2] = 0; }
+  else { ns = 2; pick[0][0] = 3; pick[0][1] = 1; pick[0][2] = 4; pick[1][0] = 4; pick[1][1] = 1; pick[1][2] = 2; }
+  for (int s2 = 0; s2 < ns; ++s2)
+    for (int k = 0; k < 3; ++k) {
+      memcpy(sub[s2] + 3 * k, P[pick[s2][k]], 12);
+      for (int j = 0; j < 3; ++j) conv[s2][3 * j + k] = bc[pick[s2][k]][j];
+    }
+  if (info) *info = i1 | (case4 << 2);
+  return ns;
+}
+static inline void conv_bary(const float* conv, const float bc[3], float bo[3]) {
+  for (int j = 0; j < 3; ++j) bo[j] = (conv[3 * j] * bc[0] + conv[3 * j + 1] * bc[1]) + conv[3 * j + 2] * bc[2];
+}
+
 typedef struct { float z; int idx; float d; float b0, b1, b2; } frag_t;
 static inline int frag_less(const frag_t* a, const frag_t* b) {
   /* std::tuple<float,int,...> operator< : lexicographic; idx is unique so (z, idx) decides */
@@ -424,6 +480,79 @@ static void raster_bwd_one(float xf, float yf, const float* v, int persp, const 
   }
 }
 
+/* Backward of clip_face + conv_bary for one pixel of sub-triangle s2 (autograd of [upstream] clip.py, whose tensor
+ * ops are all differentiable): gq (3,3) = gradient w.r.t. the clipped triangle's (x, y, z) from raster_bwd_one,
+ * gb (3) = gradient w.r.t. the UNCLIPPED barycentrics, bcl = the clipped barycentrics.  Accumulates into gfv (3,3),
+ * the gradient w.r.t. the original face's (x_ndc, y_ndc, z_view). */
+static void clip_face_bwd(const float* v, float c, int persp, int info, int s2, const double gq[9],
+                          const double gb[3], const float bcl[3], double gfv[9]) {
+  const int i1 = info & 3, case4 = (info >> 2) & 1;
+  const int i2 = (i1 + 1) % 3, i3 = (i1 + 2) % 3;
+  const double p1[3] = {v[3 * i1], v[3 * i1 + 1], v[3 * i1 + 2]};
+  const double p2[3] = {v[3 * i2], v[3 * i2 + 1], v[3 * i2 + 2]};
+  const double p3[3] = {v[3 * i3], v[3 * i3 + 1], v[3 * i3 + 2]};
+  const double w2 = (p1[2] - c) / (p1[2] - p2[2]), w3 = (p1[2] - c) / (p1[2] - p3[2]);
+  int pick[3];
+  if (!case4) { pick[0] = 3; pick[1] = 4; pick[2] = 0; }
+  else if (s2 == 0) { pick[0] = 3; pick[1] = 1; pick[2] = 4; }
+  else { pick[0] = 4; pick[1] = 1; pick[2] = 2; }
+  double gP[5][3];
+  memset(gP, 0, sizeof(gP));
+  double gw2 = 0, gw3 = 0;
+  for (int k = 0; k < 3; ++k) {
+    for (int d = 0; d < 3; ++d) gP[pick[k]][d] += gq[3 * k + d];
+    /* conv[:, k] = barycentrics of clipped vertex k: p4 -> (1 - w2) e_i1 + w2 e_i2, p5 -> (1 - w3) e_i1 + w3 e_i3 */
+    if (pick[k] == 3) gw2 += (double)bcl[k] * (gb[i2] - gb[i1]);
+    if (pick[k] == 4) gw3 += (double)bcl[k] * (gb[i3] - gb[i1]);
+  }
+  double g1[3] = {gP[0][0], gP[0][1], gP[0][2]}, g2[3] = {gP[1][0], gP[1][1], gP[1][2]}, g3[3] = {gP[2][0], gP[2][1], gP[2][2]};
+  /* p4 = f(p1, p2, w2), p5 = f(p1, p3, w3) */
+  for (int q = 0; q < 2; ++q) {
+    const double* gp = q == 0 ? gP[3] : gP[4];
+    const double* po = q == 0 ? p2 : p3;
+    double* go = q == 0 ? g2 : g3;
+    const double w = q == 0 ? w2 : w3;
+    double* gw = q == 0 ? &gw2 : &gw3;
+    for (int d = 0; d < 2; ++d) {
+      if (persp) {     /* p.xy = ((p1.xy p1.z)(1 - w) + (po.xy po.z) w) / c */
+        const double A = p1[d] * p1[2], Bq = po[d] * po[2];
+        const double gA = gp[d] * (1 - w) / c, gB = gp[d] * w / c;
+        *gw += gp[d] * (Bq - A) / c;
+        g1[d] += gA * p1[2]; g1[2] += gA * p1[d];
+        go[d] += gB * po[2]; go[2] += gB * po[d];
+      } else {
+        g1[d] += gp[d] * (1 - w); go[d] += gp[d] * w; *gw += gp[d] * (po[d] - p1[d]);
+      }
+    }
+    g1[2] += gp[2] * (1 - w); go[2] += gp[2] * w; *gw += gp[2] * (po[2] - p1[2]);
+  }
+  /* w2 = (z1 - c) / (z1 - z2) */
+  {
+    const double d2 = p1[2] - p2[2], d3 = p1[2] - p3[2];
+    g1[2] += gw2 * (c - p2[2]) / (d2 * d2); g2[2] += gw2 * (p1[2] - c) / (d2 * d2);
+    g1[2] += gw3 * (c - p3[2]) / (d3 * d3); g3[2] += gw3 * (p1[2] - c) / (d3 * d3);
+  }
+  for (int d = 0; d < 3; ++d) { gfv[3 * i1 + d] += g1[d]; gfv[3 * i2 + d] += g2[d]; gfv[3 * i3 + d] += g3[d]; }
+}
+
+/* Which sub-triangle of a clipped face owns pixel (xf, yf): the one the rasterizer keeps, i.e. the inside one with the
+ * smallest (pz, index).  Returns -1 if none (cannot happen for a pixel whose pix_to_face is this face). */
+static int clip_pick_sub(float xf, float yf, float sub[2][9], int ns, int persp, float bcl[3]) {
+  int best = -1; float bz = 0.f;
+  for (int s2 = 0; s2 < ns; ++s2) {
+    const float* tv = sub[s2];
+    const float fa = edge_fn(tv[0], tv[1], tv[3], tv[4], tv[6], tv[7]);
+    if (fa <= K_EPS && fa >= -1.0f * K_EPS) continue;
+    float w[3], b[3];
+    bary_forward(xf, yf, tv, w);
+    if (persp) bary_persp_forward(w, tv[2], tv[5], tv[8], b); else { b[0] = w[0]; b[1] = w[1]; b[2] = w[2]; }
+    const float pz = b[0] * tv[2] + b[1] * tv[5] + b[2] * tv[8];
+    if (pz < 0 || !(b[0] > 0.0f && b[1] > 0.0f && b[2] > 0.0f)) continue;
+    if (best < 0 || pz < bz) { best = s2; bz = pz; memcpy(bcl, b, 12); }
+  }
+  return best;
+}
+
 void orc_rasterize_meshes_backward(const float* face_verts, const int* pix_to_face,
                                    const float* grad_zbuf, const float* grad_bary, int N, int H,
                                    int W, int K, int Ftot, int flags, float* grad_face_verts) {
@@ -556,7 +685,8 @@ static void phong_pixel_bwd(const float bf[3], const float* X[3], const float* N
 /*  normals (Vtot,3) from orc_vertex_normals, rgb: (3) or (Vtot,3) [ORC_RGB_PER_ELEMENT],      */
 /*  R (B*M,3,3), T, C (B*M,3); light (1,3) if light_stride==0 else (B*M,3); bg (3).            */
 /*  out images (B*M,3,H,W); pix_to_face (B*M,H,W,K) VIEW-LOCAL face ids (-1 pad);               */
-/*  optional zbuf (..K), bary (..K,3), dists (..K).  counters[0] += faces straddling z_clip.    */
+/*  optional zbuf (..K), bary (..K,3), dists (..K).  counters[0] += faces straddling z_clip     */
+/*  (they are clipped against it as [upstream] clip.py does; z_clip < 0 disables cull and clip). */
 /* ------------------------------------------------------------------------------------------ */
 void orc_mesh_forward(const float* verts, const int* faces, const int* vert_off, const int* face_off,
                       const float* normals, const float* rgb, int B, int M, const float* R,
@@ -565,46 +695,65 @@ void orc_mesh_forward(const float* verts, const int* faces, const int* vert_off,
                       int flags, float* images, int* pix_to_face, float* zbuf, float* bary,
                       float* dists, long long* counters) {
   long long straddle = 0;
+  const int persp = flags & ORC_PERSPECTIVE_CORRECT;
   for (int n = 0; n < B * M; ++n) {
     const int b = n / M;
     const int V = vert_off[b + 1] - vert_off[b], F = face_off[b + 1] - face_off[b];
     const float* vw = verts + 3 * (size_t)vert_off[b];
     const int* fc = faces + 3 * (size_t)face_off[b];
+    const size_t Fa = (size_t)(F > 0 ? F : 1);
     float* ndc = (float*)malloc(sizeof(float) * 3 * (size_t)(V > 0 ? V : 1));
-    float* fv = (float*)malloc(sizeof(float) * 9 * (size_t)(F > 0 ? F : 1));
-    unsigned char* skip = (unsigned char*)calloc((size_t)(F > 0 ? F : 1), 1);
+    /* the CLIPPED face list ([upstream] clip.py ClippedFaces): unclipped faces in their original order, culled faces
+     * removed, clipped faces replaced in place by their one or two sub-triangles */
+    float* fvc = (float*)malloc(sizeof(float) * 9 * 2 * Fa);
+    float* cnv = (float*)malloc(sizeof(float) * 9 * 2 * Fa);
+    int* c2u = (int*)malloc(sizeof(int) * 2 * Fa);
+    unsigned char* has_conv = (unsigned char*)calloc(2 * Fa, 1);
+    int Fc = 0;
     orc_project_perspective(vw, V, R + 9 * n, T + 3 * n, k00, k11, ndc);
     for (int f = 0; f < F; ++f) {
+      float fv[9];
       int nb = 0;
       for (int i = 0; i < 3; ++i) {
-        memcpy(fv + 9 * (size_t)f + 3 * i, ndc + 3 * (size_t)fc[3 * f + i], 12);
-        nb += (z_clip >= 0.f && fv[9 * (size_t)f + 3 * i + 2] < z_clip);
+        memcpy(fv + 3 * i, ndc + 3 * (size_t)fc[3 * f + i], 12);
+        nb += (z_clip >= 0.f && fv[3 * i + 2] < z_clip);
       }
-      /* [upstream] renderer/mesh/clip.py: faces fully behind z_clip are culled; faces that
-       * straddle it are clipped upstream -- here they are counted and rasterized unclipped. */
-      if (nb == 3) skip[f] = 1; else if (nb > 0) straddle++;
+      if (nb == 3) continue;                     /* entirely behind the plane: culled */
+      if (nb == 0) { memcpy(fvc + 9 * (size_t)Fc, fv, 36); c2u[Fc++] = f; continue; }
+      straddle++;
+      float sub[2][9], conv[2][9];
+      const int ns = clip_face(fv, z_clip, persp, sub, conv, NULL);
+      for (int s2 = 0; s2 < ns; ++s2) {
+        memcpy(fvc + 9 * (size_t)Fc, sub[s2], 36);
+        memcpy(cnv + 9 * (size_t)Fc, conv[s2], 36);
+        has_conv[Fc] = 1; c2u[Fc++] = f;
+      }
     }
     const int first = 0;
     const size_t po = (size_t)n * H * W * K;
-    orc_rasterize_meshes(fv, &first, &F, skip, 1, H, W, K, flags, pix_to_face + po,
-                         zbuf ? zbuf + po : NULL, bary ? bary + 3 * po : NULL, dists ? dists + po : NULL);
+    const size_t npk = (size_t)H * W * K;
+    int* p2c = (int*)malloc(sizeof(int) * npk);            /* clipped-list ids */
+    float* bc = (float*)malloc(sizeof(float) * 3 * npk);   /* barycentrics w.r.t. the clipped faces */
+    orc_rasterize_meshes(fvc, &first, &Fc, NULL, 1, H, W, K, flags, p2c, zbuf ? zbuf + po : NULL, bc,
+                         dists ? dists + po : NULL);
+    /* [upstream] convert_clipped_rasterization_to_original_faces: ids and barycentrics back to the unclipped faces
+     * (zbuf and dists stay those of the clipped triangle) */
+    for (size_t i = 0; i < npk; ++i) {
+      const int c = p2c[i];
+      pix_to_face[po + i] = c < 0 ? -1 : c2u[c];
+      if (c >= 0 && has_conv[c]) { float bo[3]; conv_bary(cnv + 9 * (size_t)c, bc + 3 * i, bo); memcpy(bc + 3 * i, bo, 12); }
+      if (bary) memcpy(bary + 3 * (po + i), bc + 3 * i, 12);
+    }
     /* shade k = 0 (hard_rgb_blend uses colors[..., 0, :]) */
     const float* Ln = light + (size_t)light_stride * n;
     float* img = images + (size_t)n * 3 * H * W;
 #pragma omp parallel for schedule(static)
     for (int yi = 0; yi < H; ++yi) {
-      const float yf = pix_to_ndc(H - 1 - yi, H, W);
       for (int xi = 0; xi < W; ++xi) {
-        const size_t o = po + ((size_t)yi * W + xi) * K;
-        const int f = pix_to_face[o];
+        const size_t o = ((size_t)yi * W + xi) * K;
+        const int f = pix_to_face[po + o];
         float out[3] = {bg[0], bg[1], bg[2]};
         if (f >= 0) {
-          const float xf = pix_to_ndc(W - 1 - xi, W, H);
-          const float* v = fv + 9 * (size_t)f;
-          float w[3], bb[3];
-          bary_forward(xf, yf, v, w);
-          if (flags & ORC_PERSPECTIVE_CORRECT) bary_persp_forward(w, v[2], v[5], v[8], bb);
-          else { bb[0] = w[0]; bb[1] = w[1]; bb[2] = w[2]; }
           const float *X[3], *Nv[3], *col[3];
           for (int i = 0; i < 3; ++i) {
             const int vi = fc[3 * f + i];
@@ -612,12 +761,12 @@ void orc_mesh_forward(const float* verts, const int* faces, const int* vert_off,
             Nv[i] = normals + 3 * ((size_t)vert_off[b] + vi);
             col[i] = (flags & ORC_RGB_PER_ELEMENT) ? rgb + 3 * ((size_t)vert_off[b] + vi) : rgb;
           }
-          phong_pixel(bb, X, Nv, col, Ln, C + 3 * n, out);
+          phong_pixel(bc + 3 * o, X, Nv, col, Ln, C + 3 * n, out);
         }
         for (int c = 0; c < 3; ++c) img[((size_t)c * H + yi) * W + xi] = out[c];
       }
     }
-    free(ndc); free(fv); free(skip);
+    free(ndc); free(fvc); free(cnv); free(c2u); free(has_conv); free(p2c); free(bc);
   }
   if (counters) counters[0] += straddle;
 }
@@ -630,7 +779,7 @@ void orc_mesh_forward(const float* verts, const int* faces, const int* vert_off,
 void orc_mesh_backward(const float* verts, const int* faces, const int* vert_off, const int* face_off,
                        const float* normals, const float* rgb, int B, int M, const float* R,
                        const float* T, const float* C, const float* light, int light_stride,
-                       float k00, float k11, int H, int W, int K, int flags, const int* pix_to_face,
+                       float k00, float k11, float z_clip, int H, int W, int K, int flags, const int* pix_to_face,
                        const float* grad_images, float* gR, float* gT, float* gC, float* grad_verts,
                        float* grad_normals) {
   int Vtot = vert_off[B];
@@ -645,6 +794,7 @@ void orc_mesh_backward(const float* verts, const int* faces, const int* vert_off
     float* ndc = (float*)malloc(sizeof(float) * 3 * (size_t)(V > 0 ? V : 1));
     orc_project_perspective(vw, V, Rn, Tn, k00, k11, ndc);
     double aR[9] = {0}, aT[3] = {0}, aC[3] = {0};
+    const int persp = flags & ORC_PERSPECTIVE_CORRECT;
     const float* gimg = grad_images + (size_t)n * 3 * H * W;
     for (int yi = 0; yi < H; ++yi) {
       const float yf = pix_to_ndc(H - 1 - yi, H, W);
@@ -661,15 +811,33 @@ void orc_mesh_backward(const float* verts, const int* faces, const int* vert_off
           col[i] = (flags & ORC_RGB_PER_ELEMENT) ? rgb + 3 * ((size_t)vert_off[b] + vi[i]) : rgb;
         }
         float w[3], bb[3];
-        bary_forward(xf, yf, v, w);
-        if (flags & ORC_PERSPECTIVE_CORRECT) bary_persp_forward(w, v[2], v[5], v[8], bb);
-        else { bb[0] = w[0]; bb[1] = w[1]; bb[2] = w[2]; }
+        /* a face straddling z_clip was rasterized as its clipped sub-triangle(s) (orc_mesh_forward) */
+        float sub[2][9], conv[2][9], bcl[3];
+        int info = 0, s2 = -1;
+        const int ns = z_clip >= 0.f ? clip_face(v, z_clip, persp, sub, conv, &info) : 0;
+        if (ns > 0) {
+          s2 = clip_pick_sub(xf, yf, sub, ns, persp, bcl);
+          if (s2 < 0) continue;
+          conv_bary(conv[s2], bcl, bb);
+        } else {
+          bary_forward(xf, yf, v, w);
+          if (persp) bary_persp_forward(w, v[2], v[5], v[8], bb);
+          else { bb[0] = w[0]; bb[1] = w[1]; bb[2] = w[2]; }
+        }
         double g[3], gb[3], gCp[3], gX[9] = {0}, gN[9] = {0};
         for (int c = 0; c < 3; ++c) g[c] = gimg[((size_t)c * H + yi) * W + xi];
         phong_pixel_bwd(bb, X, Nv, col, Ln, C + 3 * n, g, gb, gCp, gv_acc ? gX : NULL, gn_acc ? gN : NULL, NULL);
         for (int d = 0; d < 3; ++d) aC[d] += gCp[d];
         double gfv[9] = {0};
-        raster_bwd_one(xf, yf, v, flags & ORC_PERSPECTIVE_CORRECT, gb, 0.0, gfv);
+        if (ns > 0) {
+          double gbeta[3], gq[9] = {0};
+          for (int k = 0; k < 3; ++k)
+            gbeta[k] = (double)conv[s2][k] * gb[0] + (double)conv[s2][3 + k] * gb[1] + (double)conv[s2][6 + k] * gb[2];
+          raster_bwd_one(xf, yf, sub[s2], persp, gbeta, 0.0, gq);
+          clip_face_bwd(v, z_clip, persp, info, s2, gq, gb, bcl, gfv);
+        } else {
+          raster_bwd_one(xf, yf, v, persp, gb, 0.0, gfv);
+        }
         for (int i = 0; i < 3; ++i) {
           /* projection backward: xn = xv*k00/zv, yn = yv*k11/zv, z = zv */
           float pv[3]; world_to_view(X[i], Rn, Tn, pv);

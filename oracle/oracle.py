@@ -173,7 +173,11 @@ def mesh_forward(verts, faces, vert_off, face_off, normals, rgb, M, R, T, Cc, li
 
 
 def mesh_backward(verts, faces, vert_off, face_off, normals, rgb, M, R, T, Cc, light, k00, k11, H, W,
-                  K, flags, pix_to_face, grad_images, want_verts=False):
+                  K, flags, pix_to_face, grad_images, want_verts=False, z_clip=None):
+    """z_clip: the forward's near clip plane; None = [upstream] MeshRasterizer's default (znear / 2 = 0.5 with
+    perspective_correct, no clipping otherwise)."""
+    if z_clip is None:
+        z_clip = 0.5 if (flags & PERSPECTIVE_CORRECT) else -1.0
     verts = _f(verts).reshape(-1, 3); faces = _i(faces).reshape(-1, 3)
     vert_off, face_off = _i(vert_off), _i(face_off)
     B = vert_off.size - 1
@@ -188,7 +192,7 @@ def mesh_backward(verts, faces, vert_off, face_off, normals, rgb, M, R, T, Cc, l
     gN = np.empty_like(verts) if want_verts else None
     lib().orc_mesh_backward(_p(verts), _p(faces), _p(vert_off), _p(face_off), _p(normals), _p(rgb),
                             C.c_int(B), C.c_int(M), _p(R), _p(T), _p(Cc), _p(light), C.c_int(light_stride),
-                            C.c_float(k00), C.c_float(k11), C.c_int(H), C.c_int(W), C.c_int(K),
+                            C.c_float(k00), C.c_float(k11), C.c_float(z_clip), C.c_int(H), C.c_int(W), C.c_int(K),
                             C.c_int(flags), _p(_i(pix_to_face)), _p(_f(grad_images)), _p(gR), _p(gT),
                             _p(gC), _p(gV), _p(gN))
     return dict(gR=gR, gT=gT, gC=gC, grad_verts=gV, grad_normals=gN)

@@ -139,19 +139,72 @@ def phong_shade(bary, p2f, verts, faces, normals, vert_rgb, light_dir, cam_cente
     return out.permute(2, 0, 1)
 
 
+def clip_faces(fv, z_clip, perspective_correct):
+    """[upstream] renderer/mesh/clip.py clip_faces against the plane z = z_clip only (MeshRasterizer: cull_to_frustum
+    False), written per face with differentiable tensor ops.  fv (F,3,3) = (x_ndc, y_ndc, z_view).
+    -> fvc (Fc,3,3) clipped face list, c2u (Fc,) index of the unclipped face, conv (Fc,3,3) with conv[c][j][k] = barycentric
+    weight of original vertex j in clipped vertex k (identity for untouched faces)."""
+    out_v, out_u, out_c = [], [], []
+    eye = torch.eye(3, dtype=fv.dtype)
+    for f in range(fv.shape[0]):
+        v = fv[f]
+        behind = v[:, 2] < z_clip
+        nb = int(behind.sum())
+        if nb == 3:
+            continue
+        if nb == 0:
+            out_v.append(v); out_u.append(f); out_c.append(eye); continue
+        case4 = nb == 1
+        i1 = int(torch.nonzero(behind if case4 else ~behind)[0])
+        i2, i3 = (i1 + 1) % 3, (i1 + 2) % 3
+        p1, p2, p3 = v[i1], v[i2], v[i3]
+        w2 = (p1[2] - z_clip) / (p1[2] - p2[2])
+        w3 = (p1[2] - z_clip) / (p1[2] - p3[2])
+        p4 = p1 * (1 - w2) + p2 * w2
+        p5 = p1 * (1 - w3) + p3 * w3
+        if perspective_correct:      # interpolate the un-projected xy, re-project at the plane
+            a1, a2, a3 = p1[:2] * p1[2], p2[:2] * p2[2], p3[:2] * p3[2]
+            p4 = torch.cat([(a1 * (1 - w2) + a2 * w2) / z_clip, p4[2:]])
+            p5 = torch.cat([(a1 * (1 - w3) + a3 * w3) / z_clip, p5[2:]])
+        e = [eye[i1], eye[i2], eye[i3]]
+        bc = [e[0], e[1], e[2], e[0] * (1 - w2) + e[1] * w2, e[0] * (1 - w3) + e[2] * w3]
+        P = [p1, p2, p3, p4, p5]
+        picks = [(3, 1, 4), (4, 1, 2)] if case4 else [(3, 4, 0)]
+        for pk in picks:
+            out_v.append(torch.stack([P[k] for k in pk]))
+            out_u.append(f)
+            out_c.append(torch.stack([bc[k] for k in pk], dim=1))
+    if not out_v:
+        return fv.new_zeros((0, 3, 3)), torch.zeros(0, dtype=torch.long), fv.new_zeros((0, 3, 3))
+    return torch.stack(out_v), torch.tensor(out_u, dtype=torch.long), torch.stack(out_c)
+
+
 def render_mesh_view(verts, faces, normals, vert_rgb, R, T, Cc, light_dir, bg, k00, k11, H, W,
-                     perspective_correct=True, cull_backfaces=False, p2f=None):
+                     perspective_correct=True, cull_backfaces=False, p2f=None, z_clip=None):
     """Differentiable single-view mesh render (K=1).  If p2f is given the raster step is skipped
     and barycentrics are recomputed differentiably from the face ids (that is what autograd does
-    through _RasterizeFaceVerts: the index is a constant)."""
+    through _RasterizeFaceVerts: the index is a constant).  z_clip: near-plane cull + clip ([upstream] clip.py);
+    with it the rasterizer always runs (on the clipped face list) and p2f must be None."""
     ndc = project_perspective(verts, R, T, k00, k11)
     fv = ndc[faces]
+    yf = pix_centers(H, verts.dtype)[:, None].expand(H, W)
+    xf = pix_centers(W, verts.dtype)[None, :].expand(H, W)
+    if z_clip is not None:
+        assert p2f is None
+        fvc, c2u, conv = clip_faces(fv, z_clip, perspective_correct)
+        with torch.no_grad():
+            p2c, _, _ = rasterize_meshes_naive(fvc, H, W, 1, perspective_correct, cull_backfaces)
+        p2c = p2c[..., 0]
+        sel = p2c.clamp_min(0)
+        bc = bary_coords(xf, yf, fvc[sel], perspective_correct)
+        b = (conv[sel] * bc[..., None, :]).sum(-1)          # convert_clipped_rasterization_to_original_faces
+        p2f = torch.where(p2c >= 0, c2u[sel], torch.full_like(p2c, -1))
+        img = phong_shade(b, p2f, verts, faces, normals, vert_rgb, light_dir, Cc, bg)
+        return img, p2f
     if p2f is None:
         with torch.no_grad():
             p2f, _, _ = rasterize_meshes_naive(fv, H, W, 1, perspective_correct, cull_backfaces)
         p2f = p2f[..., 0]
-    yf = pix_centers(H, verts.dtype)[:, None].expand(H, W)
-    xf = pix_centers(W, verts.dtype)[None, :].expand(H, W)
     b = bary_coords(xf, yf, fv[p2f.clamp_min(0)], perspective_correct)
     img = phong_shade(b, p2f, verts, faces, normals, vert_rgb, light_dir, Cc, bg)
     return img, p2f

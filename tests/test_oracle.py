@@ -395,3 +395,107 @@ def test_golden_points(oracle):
     o4 = oracle.points_forward(g["points"], col, 12, g["R"], g["T"], g["inv_dist"], 0.02, np.zeros(3, np.float32), 224, 224, 4,
                                oracle.COMPOSITE_ALPHA)
     assert sha(o4["idx"]) == str(g["idx4_sha256"])
+
+
+# --------------------------------------------------------------------- near-plane clipping ([upstream] clip.py)
+def test_clip_faces_known_answers():
+    """Hand-derived clipping of one triangle against z = 0.5 (no perspective correction: plain lerps)."""
+    # case 3: vertex 0 in front (z = 1.5), vertices 1, 2 behind (z = 0.25) -> one triangle (p4, p5, p1), w = 1/1.25 = 0.8
+    fv = torch.tensor([[[0.0, 0.0, 1.5], [1.0, 0.0, 0.25], [0.0, 1.0, 0.25]]], dtype=torch.float64)
+    fvc, c2u, conv = tr.clip_faces(fv, 0.5, False)
+    assert fvc.shape == (1, 3, 3) and c2u.tolist() == [0]
+    assert torch.allclose(fvc[0], torch.tensor([[0.8, 0.0, 0.5], [0.0, 0.8, 0.5], [0.0, 0.0, 1.5]], dtype=torch.float64))
+    # columns = barycentrics of (p4, p5, p1) in the original triangle
+    assert torch.allclose(conv[0], torch.tensor([[0.2, 0.2, 1.0], [0.8, 0.0, 0.0], [0.0, 0.8, 0.0]], dtype=torch.float64))
+    # case 4: vertex 1 behind -> quad split into (p4, p2, p5), (p5, p2, p3) with p1 = v1, p2 = v2, p3 = v0
+    fv = torch.tensor([[[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 1.0]]], dtype=torch.float64)
+    fvc, c2u, conv = tr.clip_faces(fv, 0.5, False)
+    assert fvc.shape == (2, 3, 3) and c2u.tolist() == [0, 0]
+    p4 = torch.tensor([0.5, 0.5, 0.5], dtype=torch.float64); p5 = torch.tensor([0.5, 0.0, 0.5], dtype=torch.float64)
+    assert torch.allclose(fvc[0], torch.stack([p4, fv[0, 2], p5])) and torch.allclose(fvc[1], torch.stack([p5, fv[0, 2], fv[0, 0]]))
+    # every clipped vertex is the conv-weighted combination of the original ones (z exactly, xy because persp is off)
+    for c in range(2):
+        assert torch.allclose(conv[c].T @ fv[0], fvc[c])
+    # perspective-correct: xy are interpolated un-projected and re-projected at the plane
+    fv = torch.tensor([[[0.2, -0.4, 2.0], [1.0, 0.6, 0.25], [-0.8, 1.0, 0.25]]], dtype=torch.float64)
+    fvc, _, conv = tr.clip_faces(fv, 0.5, True)
+    world = fv[0, :, :2] * fv[0, :, 2:3]
+    assert torch.allclose(fvc[0, :, :2] * fvc[0, :, 2:3], conv[0].T @ world) and torch.allclose(fvc[0, :2, 2], torch.tensor([0.5, 0.5], dtype=torch.float64))
+    # untouched and fully-behind faces
+    fv = torch.tensor([[[0, 0, 1.0], [1, 0, 1.0], [0, 1, 1.0]], [[0, 0, 0.1], [1, 0, 0.2], [0, 1, 0.3]]], dtype=torch.float64)
+    fvc, c2u, conv = tr.clip_faces(fv, 0.5, True)
+    assert c2u.tolist() == [0] and torch.equal(conv[0], torch.eye(3, dtype=torch.float64))
+
+
+def _close_up(seed, faces=260, M=3):
+    """A camera 1.15 - 1.3 away from a unit-sphere object: faces straddle z = 0.5 (mvtn.py:33 transform_distance)."""
+    v, f = synth.make_mesh(faces, seed)
+    az = torch.tensor([15., 140., -80.])[:M]; el = torch.tensor([10., -35., 50.])[:M]; di = torch.tensor([1.15, 1.22, 1.3])[:M]
+    return v, f, az, el, di
+
+
+def test_mesh_forward_with_clipping_matches_torch_restatement(oracle):
+    v, f, az, el, di = _close_up(5)
+    M, H = 3, 48
+    R, T, C = oracle.look_at(az.numpy(), el.numpy(), di.numpy())
+    nrm = oracle.vertex_normals(v.numpy(), f.numpy())
+    voff = np.array([0, v.shape[0]], np.int32); foff = np.array([0, f.shape[0]], np.int32)
+    rgb = np.random.RandomState(5).rand(v.shape[0], 3).astype(np.float32)
+    light = np.array([[0.3, 1.0, -0.5]], np.float32); bg = np.array([0.2, 0.4, 0.6], np.float32)
+    o = oracle.mesh_forward(v.numpy(), f.numpy(), voff, foff, nrm, rgb, M, R, T, C, light, bg, K00, K11, 0.5, H, H, 1,
+                            oracle.PERSPECTIVE_CORRECT)
+    assert o["straddle"] > 0
+    unclipped = oracle.mesh_forward(v.numpy(), f.numpy(), voff, foff, nrm, rgb, M, R, T, C, light, bg, K00, K11, -1.0, H, H, 1,
+                                    oracle.PERSPECTIVE_CORRECT)
+    assert (unclipped["pix_to_face"] != o["pix_to_face"]).sum() > 0      # the clip removes what is nearer than the plane
+    assert float(o["zbuf"][o["pix_to_face"] >= 0].min()) >= 0.5 - 1e-5
+    mism = 0
+    for n in range(M):
+        Rn, Tn, Cn = (torch.from_numpy(x[n]).double() for x in (R, T, C))
+        img, p2f = tr.render_mesh_view(v.double(), f, torch.from_numpy(nrm).double(), torch.from_numpy(rgb).double(), Rn, Tn, Cn,
+                                       torch.from_numpy(light[0]).double(), torch.from_numpy(bg).double(), K00, K11, H, H, z_clip=0.5)
+        bad = p2f.numpy() != o["pix_to_face"][n, ..., 0]
+        mism += int(bad.sum())
+        assert np.abs(img.numpy() - o["images"][n])[:, ~bad].max() < 1e-5
+    assert mism <= 4          # fp64 restatement vs fp32 oracle: pixels a rounding error away from an edge
+
+
+def test_mesh_backward_with_clipping_matches_autograd(oracle):
+    for persp in (True, False):
+        v, f, az, el, di = _close_up(6)
+        M, H = 3, 40
+        R, T, C = oracle.look_at(az.numpy(), el.numpy(), di.numpy())
+        nrm = oracle.vertex_normals(v.numpy(), f.numpy())
+        voff = np.array([0, v.shape[0]], np.int32); foff = np.array([0, f.shape[0]], np.int32)
+        rgb = np.random.RandomState(6).rand(v.shape[0], 3).astype(np.float32)
+        light = np.array([[0.3, 1.0, -0.5]], np.float32); bg = np.full(3, 0.99999, np.float32)
+        flags = oracle.PERSPECTIVE_CORRECT if persp else 0
+        o = oracle.mesh_forward(v.numpy(), f.numpy(), voff, foff, nrm, rgb, M, R, T, C, light, bg, K00, K11, 0.5, H, H, 1, flags)
+        assert o["straddle"] > 0
+        gimg = np.random.RandomState(7).randn(M, 3, H, H).astype(np.float32)
+        bw = oracle.mesh_backward(v.numpy(), f.numpy(), voff, foff, nrm, rgb, M, R, T, C, light, K00, K11, H, H, 1, flags,
+                                  o["pix_to_face"], gimg, want_verts=True, z_clip=0.5)
+        D = torch.float64
+        Rd, Td, Cd = (torch.from_numpy(x).to(D).requires_grad_() for x in (R, T, C))
+        vd = v.to(D).requires_grad_(); nd = torch.from_numpy(nrm).to(D).requires_grad_()
+        loss = 0
+        n_clipped_px = 0
+        for n in range(M):
+            img, p2f = tr.render_mesh_view(vd, f, nd, torch.from_numpy(rgb).to(D), Rd[n], Td[n], Cd[n], torch.from_numpy(light[0]).to(D),
+                                           torch.from_numpy(bg).to(D), K00, K11, H, H, perspective_correct=persp, z_clip=0.5)
+            same = torch.from_numpy(o["pix_to_face"][n, ..., 0]).long() == p2f       # drop the rare edge-rounding pixels from both sides
+            gm = torch.from_numpy(gimg[n]).to(D) * same[None]
+            gimg[n] *= same.numpy()[None]
+            loss = loss + (img * gm).sum()
+            fv = tr.project_perspective(v.double(), Rd[n].detach(), Td[n].detach(), K00, K11)[f]
+            strad = ((fv[:, :, 2] < 0.5).sum(1) % 3 != 0)
+            n_clipped_px += int(strad[p2f.clamp_min(0)][p2f >= 0].sum())
+        assert n_clipped_px > 20      # the test exercises the clipped-triangle chain, not just the ordinary one
+        bw = oracle.mesh_backward(v.numpy(), f.numpy(), voff, foff, nrm, rgb, M, R, T, C, light, K00, K11, H, H, 1, flags,
+                                  o["pix_to_face"], gimg, want_verts=True, z_clip=0.5)
+        loss.backward()
+        assert rel(bw["gR"], Rd.grad.numpy()) < 5e-5
+        assert rel(bw["gT"], Td.grad.numpy()) < 5e-5
+        assert rel(bw["gC"], Cd.grad.numpy()) < 5e-5
+        assert rel(bw["grad_verts"], vd.grad.numpy()) < 1e-4
+        assert rel(bw["grad_normals"], nd.grad.numpy()) < 5e-5
