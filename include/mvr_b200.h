@@ -45,7 +45,7 @@ extern "C" {
 #define MVR_SHININESS 64
 
 /* counters[] slots written by mvr_mesh_forward (device int64[MVR_NUM_COUNTERS]; the call zeroes them first) */
-#define MVR_CNT_STRADDLE 0     /* faces straddling the near clip plane (rasterized unclipped) */
+#define MVR_CNT_STRADDLE 0     /* faces straddling the near clip plane (clipped against it, [upstream] clip.py) */
 #define MVR_CNT_BIG_FACES 1    /* faces whose pixel bbox exceeded 1024 pixels (walked by a whole CTA) */
 #define MVR_NUM_COUNTERS 4
 
@@ -123,7 +123,9 @@ size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K, int64_t total
  * hard_rgb_blend).  blur_radius = 0.
  *   Cc (n,3) camera centres; light (1,3) if light_stride == 0 else (n,3) with stride 3;
  *   obj_rgb (3) uniform colour (ignored when the geometry holds per-vertex colours); bg_rgb (3);
- *   k00,k11: FoV projection scale (1/tan(fov/2)); z_clip < 0 disables the near-plane cull;
+ *   k00,k11: FoV projection scale (1/tan(fov/2)); z_clip: near clip plane in view space ([upstream] MeshRasterizer:
+ *   znear / 2) -- faces entirely behind it are culled, faces crossing it are clipped into one or two triangles and their
+ *   fragments mapped back to the original face ([upstream] clip.py); z_clip < 0 disables both;
  *   K = faces_per_pixel; max_verts / max_faces = largest per-object counts (grid sizing).
  *   out_mean_std: HOST float[6] = per-channel mean[3], std[3], or NULL.  Consumer-side fusion:
  *   the images are written as (x - mean_c) / std_c -- viewGCN/tools/Trainer_mvt.py:41-49 Normalize -- and, with
@@ -142,12 +144,12 @@ int mvr_mesh_forward(const void* geometry, const int* vert_off, const int* face_
  * of shading/projection): grad_images (n,3,H,W) -> gR (n,3,3), gT (n,3), gC (n,3);
  * optional grad_verts (Vtot,3) (projection + interpolated-position paths) and grad_normals
  * (Vtot,3) (gradient w.r.t. the per-vertex unit normals), both ACCUMULATED with atomics
- * (caller zero-fills).  out_mean_std / MVR_IMAGES_BF16 as in the forward: grad_images is then the cotangent of
+ * (caller zero-fills).  z_clip: the forward's value.  out_mean_std / MVR_IMAGES_BF16 as in the forward: grad_images is then the cotangent of
  * the normalised (bfloat16) tensor. */
 int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
                       int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
                       const float* T, const float* Cc, const float* light, int light_stride,
-                      const float* obj_rgb, float k00, float k11, int H, int W, int K, int flags,
+                      const float* obj_rgb, float k00, float k11, float z_clip, int H, int W, int K, int flags,
                       const float* out_mean_std, const int* pix_to_face, const void* grad_images, float* gR,
                       float* gT, float* gC,
                       float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,

@@ -40,7 +40,7 @@ SIGNATURES = {
     "mvr_mesh_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i64]),
     "mvr_mesh_forward": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _f, _f,
                               _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "mvr_mesh_backward": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _f, _f, _i, _i, _i, _i,
+    "mvr_mesh_backward": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _f, _f, _f, _i, _i, _i, _i,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mvr_points_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _d]),
     "mvr_points_hit_mask_words": (_sz, [_i, _i, _i, _i]),

@@ -82,22 +82,6 @@ __global__ void geom_get_normals_kernel(const float4* __restrict__ normals4, int
 // ------------------------------------------------------------------------------------------------
 // shared device code: projection, face setup and the per-(face, pixel) test
 // ------------------------------------------------------------------------------------------------
-struct MeshParams {
-  const float4* verts4; const float4* normals4; const float4* rgb4; const int4* faces4;
-  const int* vert_off; const int* face_off;
-  const float* R; const float* T; const float* Cc; const float* light; int light_stride;
-  const float* obj_rgb; const float* bg_rgb;
-  float k00, k11, z_clip;
-  int B, M, H, W, K, flags;
-  int chunks_per_view, layer, item_cap, wcap;
-  float4* pv;            // (x_ndc, y_ndc, z_view, 0) of vertex v of view (b, m) at M*vert_off[b] + m*V_b + v
-  float* tab;            // pixel-centre NDC coordinates: xf[W] then yf[H]
-  unsigned long long* keys; unsigned long long* prev;
-  void* images; int* pix_to_face; float* zbuf; float* bary; float* dists;
-  long long* counters;
-  OutNorm onorm;
-};
-
 // Face-level rejection ([upstream] clip.py near cull, CheckPointOutsideBoundingBox z_invalid,
 // RasterizeMeshesNaiveCpu zero-area / back-face tests) and the exact pixel bbox (inclusive ranges).
 __device__ __forceinline__ bool face_pixel_bbox(const Face& f, const MeshParams& p, const float* s_xf, const float* s_yf,
@@ -114,40 +98,6 @@ __device__ __forceinline__ bool face_pixel_bbox(const Face& f, const MeshParams&
   if (xi_lo > xi_hi) return false;
   pixel_range(ymin, ymax, p.H, p.W, 0, p.H - 1, s_yf, yi_lo, yi_hi);
   return yi_lo <= yi_hi;
-}
-
-// [upstream] BarycentricCoordinatesForward (+ BarycentricPerspectiveCorrectionForward), pz, inside.
-// w = plain barycentrics, b = (corrected) barycentrics.  A cheap sign filter comes first: a pixel can
-// only be inside if every edge function has the sign of the area (DESIGN.md "Parity" proves the
-// filter never rejects a pixel the oracle accepts).
-__device__ __forceinline__ bool raster_test(const Face& f, const FaceEdges& e, bool persp, float xf, float yf,
-                                            float w[3], float b[3], float& pz) {
-  const float e0 = (xf - f.x1) * e.A0 - (yf - f.y1) * e.B0;
-  const float e1 = (xf - f.x2) * e.A1 - (yf - f.y2) * e.B1;
-  const float e2 = (xf - f.x0) * e.A2 - (yf - f.y0) * e.B2;
-  if (e.area_p > 0.f) { if (!(e0 > 0.f && e1 > 0.f && e2 > 0.f)) return false; }
-  else { if (!(e0 < 0.f && e1 < 0.f && e2 < 0.f)) return false; }
-  w[0] = e0 / e.area_p; w[1] = e1 / e.area_p; w[2] = e2 / e.area_p;
-  if (persp) {
-    const float t0 = w[0] * f.z1 * f.z2, t1 = w[1] * f.z0 * f.z2, t2 = w[2] * f.z0 * f.z1;
-    const float denom = fmaxf(t0 + t1 + t2, MVR_K_EPS);
-    b[0] = t0 / denom; b[1] = t1 / denom; b[2] = t2 / denom;
-  } else {
-    b[0] = w[0]; b[1] = w[1]; b[2] = w[2];
-  }
-  pz = b[0] * f.z0 + b[1] * f.z1 + b[2] * f.z2;
-  if (pz < 0.f) return false;
-  return b[0] > 0.0f && b[1] > 0.0f && b[2] > 0.0f;
-}
-
-__device__ __forceinline__ float point_line_dist2(float px, float py, float ax, float ay, float bx, float by) {
-  const float dx = bx - ax, dy = by - ay;
-  const float l2 = dx * dx + dy * dy;
-  if (l2 <= MVR_K_EPS) return (px - bx) * (px - bx) + (py - by) * (py - by);
-  const float t = (dx * (px - ax) + dy * (py - ay)) / l2;
-  const float tt = fminf(fmaxf(t, 0.00f), 1.00f);
-  const float qx = ax + tt * dx, qy = ay + tt * dy;
-  return (px - qx) * (px - qx) + (py - qy) * (py - qy);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -237,12 +187,17 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
     const int fid = rbeg + tid;
     if (fid < fend) {
       const Face fc = gather_face(pvn, __ldg(p.faces4 + f0 + fid));
-      if (p.z_clip >= 0.f && p.layer == 0) {   // every face crossing z_clip is counted, visible or not (as the oracle does)
-        const int nb = (fc.z0 < p.z_clip) + (fc.z1 < p.z_clip) + (fc.z2 < p.z_clip);
-        n_straddle += (nb == 1 || nb == 2);
-      }
       int xl, xh, yl, yh;
-      if (face_pixel_bbox(fc, p, s_xf, s_yf, xl, xh, yl, yh)) {
+      if (face_straddles(fc, p.z_clip)) {
+        // crosses the near clip plane ([upstream] clip.py): counted, visible or not (as the oracle does), and handed to
+        // the whole CTA below, which rasterizes its one or two clipped sub-triangles
+        n_straddle += p.layer == 0;
+        s_rec[0][tid] = fc.x0; s_rec[1][tid] = fc.y0; s_rec[2][tid] = fc.z0;
+        s_rec[3][tid] = fc.x1; s_rec[4][tid] = fc.y1; s_rec[5][tid] = fc.z1;
+        s_rec[6][tid] = fc.x2; s_rec[7][tid] = fc.y2; s_rec[8][tid] = fc.z2;
+        s_rec[9][tid] = __int_as_float(fid);
+        s_big[atomicAdd(&s_cnt[1], 1)] = tid | 0x100;
+      } else if (face_pixel_bbox(fc, p, s_xf, s_yf, xl, xh, yl, yh)) {
         const int bw = xh - xl + 1, bh = yh - yl + 1, npx = bw * bh;
         s_rec[0][tid] = fc.x0; s_rec[1][tid] = fc.y0; s_rec[2][tid] = fc.z0;
         s_rec[3][tid] = fc.x1; s_rec[4][tid] = fc.y1; s_rec[5][tid] = fc.z1;
@@ -373,14 +328,31 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
       }
     }
     // ---------------- large faces: the whole CTA walks the bbox ----------------
+    int n_clipf = 0;
     for (int q = 0; q < n_bigf; ++q) {
-      const int slot = s_big[q];
+      const int ent = s_big[q], slot = ent & 255;
       Face fc;
       fc.x0 = s_rec[0][slot]; fc.y0 = s_rec[1][slot]; fc.z0 = s_rec[2][slot];
       fc.x1 = s_rec[3][slot]; fc.y1 = s_rec[4][slot]; fc.z1 = s_rec[5][slot];
       fc.x2 = s_rec[6][slot]; fc.y2 = s_rec[7][slot]; fc.z2 = s_rec[8][slot];
-      const FaceEdges fe = face_edges(fc);
       const int bfid = __float_as_int(s_rec[9][slot]);
+      if (ent & 0x100) {      // near-plane clipping: the sub-triangles compete under the ORIGINAL face id
+        ++n_clipf;
+        ClipSub cs;
+        clip_face(fc, p.z_clip, persp, cs);
+        for (int s = 0; s < cs.ns; ++s) {
+          const Face sf = cs.f[s];
+          int cxl, cxh, cyl, cyh;
+          if (!face_pixel_bbox(sf, p, s_xf, s_yf, cxl, cxh, cyl, cyh)) continue;
+          const FaceEdges sfe = face_edges(sf);
+          for (int yy = cyl + warp; yy <= cyh; yy += NWARPS)
+            for (int xx = cxl + lane; xx <= cxh; xx += 32)
+              resolve_pixel(sf, sfe, bfid, 0u, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
+                            prev ? prev + (size_t)yy * p.W + xx : nullptr);
+        }
+        continue;
+      }
+      const FaceEdges fe = face_edges(fc);
       const int rxy = __float_as_int(s_rec[10][slot]), rwh = __float_as_int(s_rec[11][slot]);
       const int xl = rxy & 0xffff, yl = rxy >> 16, bw = rwh & 0xffff, bh = rwh >> 16;
       const float zmin = fminf(fminf(fc.z0, fc.z1), fc.z2);
@@ -392,7 +364,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
                         prev ? prev + (size_t)yy * p.W + xx : nullptr);
         }
     }
-    n_big += (tid == 0) ? n_bigf : 0;
+    n_big += (tid == 0) ? n_bigf - n_clipf : 0;
     __syncthreads();
   }
   if (p.counters) {
@@ -404,26 +376,6 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
 // ------------------------------------------------------------------------------------------------
 // shading ([upstream] shading.py phong_shading, lighting.py diffuse/specular, blending.py hard_rgb_blend)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void phong_pixel(const float b[3], const float4 X0, const float4 X1, const float4 X2,
-                                            const float4 N0, const float4 N1, const float4 N2, const float4 c0,
-                                            const float4 c1, const float4 c2, const ShadeCtx& s, float out[3]) {
-  const float3 P = interp(b, X0, X1, X2);
-  const float3 Nn = interp(b, N0, N1, N2);
-  const float3 tex = interp(b, c0, c1, c2);
-  const float in = inv_norm_clamped(Nn.x, Nn.y, Nn.z, 1e-6f);
-  const float nx = Nn.x * in, ny = Nn.y * in, nz = Nn.z * in;
-  const float cosang = fmaf(nx, s.lx, fmaf(ny, s.ly, nz * s.lz));
-  const float diff = fmaxf(cosang, 0.f);
-  const float vx = s.cx - P.x, vy = s.cy - P.y, vz = s.cz - P.z;
-  const float iv = inv_norm_clamped(vx, vy, vz, 1e-6f);
-  const float rx = fmaf(2.f * cosang, nx, -s.lx), ry = fmaf(2.f * cosang, ny, -s.ly), rz = fmaf(2.f * cosang, nz, -s.lz);
-  const float dt = fmaf(vx * iv, rx, fmaf(vy * iv, ry, (vz * iv) * rz));
-  const float alpha = (dt > 0.f && cosang > 0.f) ? dt : 0.f;
-  const float spec = MVR_SPECULAR * pow64(alpha);
-  const float kd = fmaf(MVR_DIFFUSE, diff, MVR_AMBIENT);
-  out[0] = fmaf(kd, tex.x, spec); out[1] = fmaf(kd, tex.y, spec); out[2] = fmaf(kd, tex.z, spec);
-}
-
 // ------------------------------------------------------------------------------------------------
 // shade pass: one thread per pixel
 // ------------------------------------------------------------------------------------------------
@@ -473,6 +425,8 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_shade_kernel(const Mes
     const int4 fi = __ldg(p.faces4 + f0 + fid);
     // every gather of this pixel is issued before the first use (one round trip to L2 instead of three)
     const Face fc = gather_face(p.pv + (size_t)p.M * voff + (size_t)m * V, fi);
+    // rasterized as clipped sub-triangles: mesh_shade_clipped_kernel owns this pixel (flag: see WSF_CLIP)
+    if (may_clip(p.wsflags) && face_straddles(fc, p.z_clip)) return;
     float4 X0, X1, X2, N0, N1, N2, c0, c1, c2;
     if (k == 0) {
       X0 = __ldg(p.verts4 + voff + fi.x); X1 = __ldg(p.verts4 + voff + fi.y); X2 = __ldg(p.verts4 + voff + fi.z);
@@ -620,10 +574,12 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.images = images; p.pix_to_face = pix_to_face; p.zbuf = zbuf; p.bary = bary; p.dists = dists;
   p.counters = (long long*)counters;
   p.onorm = make_out_norm(out_mean_std);
+  p.wsflags = (int*)(wb + w.flags);
   const size_t HW = (size_t)H * W;
-  cudaError_t e = cudaMemsetAsync(p.keys, 0xFF, (size_t)N * HW * 8, st);      // every key = EMPTY
+  // every key = EMPTY, and the workspace flags right in front of the plane armed (WSF_CLIP)
+  cudaError_t e = cudaMemsetAsync(wb + w.flags, 0xFF, (w.keys - w.flags) + (size_t)N * HW * 8, st);
   if (e != cudaSuccess) { set_error("mvr_mesh_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
-  rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, workspace, st);
+  rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, z_clip, false, workspace, st);
   if (rc) return rc;
   const size_t tab_smem = ((size_t)W + H) * sizeof(float);
   const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
@@ -642,6 +598,10 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
     else MVR_LAUNCH((mesh_shade_kernel<false, 4>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
     rc = check_launch("mesh_shade_kernel");
     if (rc) return rc;
+    if (z_clip >= 0.f) {      // pixels won by a face crossing the near plane (none in MVTN's default configurations: the kernel exits at once)
+      rc = launch_mesh_shade_clipped(p, (int)N, st);
+      if (rc) return rc;
+    }
   }
   return 0;
 }

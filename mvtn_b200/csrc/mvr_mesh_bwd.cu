@@ -5,41 +5,11 @@
 //
 //   mesh_backward_kernel -- per pixel recompute (no fragment traffic), chain
 //             d image -> Phong -> barycentrics -> NDC verts -> view verts -> (dR, dT, dC), warp-reduced to one partial
-//             per warp and summed in fixed order (deterministic, no float atomics on the camera gradients).
+//             per warp; mesh_backward_finish_kernel (mvr_mesh_clip.cu) sums them in fixed order (deterministic, no
+//             float atomics on the camera gradients).
 #include "mvr_mesh.cuh"
 
 namespace mvr {
-
-struct MeshBwdParams {
-  const float4* verts4; const float4* normals4; const float4* rgb4; const int4* faces4;
-  const int* vert_off; const int* face_off;
-  const float* R; const float* T; const float* Cc; const float* light; int light_stride;
-  const float* obj_rgb;
-  float k00, k11;
-  int B, M, H, W, K, flags, ctas_per_view, tiles_x;
-  const float4* pv; const float* tab;
-  const int* pix_to_face; const void* grad_images;
-  float* partials;       // (N, ctas_per_view, NWARPS, 16)
-  float* grad_verts; float* grad_normals;
-  OutNorm onorm;
-};
-
-__device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
-
-// d/dv of v / max(|v|, eps)
-__device__ __forceinline__ void normalize_bwd3(float vx, float vy, float vz, float eps, float gx, float gy, float gz,
-                                               float& ox, float& oy, float& oz) {
-  const float n2 = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
-  if (n2 > eps * eps) {
-    const float inv = rsqrtf(n2);
-    const float ux = vx * inv, uy = vy * inv, uz = vz * inv;
-    const float d = fmaf(ux, gx, fmaf(uy, gy, uz * gz));
-    ox = fmaf(-ux, d, gx) * inv; oy = fmaf(-uy, d, gy) * inv; oz = fmaf(-uz, d, gz) * inv;
-  } else {
-    const float inv = 1.f / eps;
-    ox = gx * inv; oy = gy * inv; oz = gz * inv;
-  }
-}
 
 template <int MINB>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const MeshBwdParams p) {
@@ -95,6 +65,10 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
     const float4 N0 = __ldg(p.normals4 + voff + fi.x), N1 = __ldg(p.normals4 + voff + fi.y), N2 = __ldg(p.normals4 + voff + fi.z);
     float4 c0 = ucol, c1 = ucol, c2 = ucol;
     if (per_vertex_rgb) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
+    // (after every load of the pixel has been issued) a face crossing the near plane: mesh_backward_clipped_kernel owns the pixel
+    // (the flag -- some vertex lies behind the plane, never in MVTN's default setups -- is re-read per pixel: an L1 hit
+    // is cheaper than a register kept live across this loop)
+    if (may_clip(p.wsflags) && face_straddles(fc, p.z_clip)) continue;
     const FaceEdges fe = face_edges(fc);
     const float yf = __ldg(p.tab + p.W + yi);
     const float e0 = (xf - fc.x1) * fe.A0 - (yf - fc.y1) * fe.B0;
@@ -204,7 +178,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
     }
   }
   // one partial per WARP, no block barrier: a warp retires as soon as its own pixels are done
-  float* out = p.partials + (((size_t)n * p.ctas_per_view + cta) * NWARPS + (tid >> 5)) * 16;
+  float* out = p.partials + ((size_t)n * p.parts_per_view + (size_t)cta * NWARPS + (tid >> 5)) * 16;
   const int lane = tid & 31;
   if (!__any_sync(0xffffffffu, any)) {   // background-only warp
     if (lane < 16) out[lane] = 0.f;
@@ -212,28 +186,6 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
   }
   const float mine = warp_sum16_transposed(acc);      // lanes 2i, 2i+1: total of value i
   if (!(lane & 1)) out[lane >> 1] = mine;
-}
-
-// fixed-order sum of the per-warp partials: one CTA per view -> gR, gT, gC.  Thread t owns value t & 15 of the parts
-// congruent to t >> 4 modulo 16 (coalesced 64-byte rows), then 16 threads add the 16 group sums in a fixed order.
-__global__ void __launch_bounds__(MVR_THREADS) mesh_backward_reduce_kernel(const float* __restrict__ partials, int n_parts,
-                                                                           float* __restrict__ gR, float* __restrict__ gT,
-                                                                           float* __restrict__ gC) {
-  __shared__ float s_sum[MVR_THREADS];
-  const int n = blockIdx.x, tid = threadIdx.x;
-  const int v = tid & 15, grp = tid >> 4;
-  float s = 0.f;
-  for (int t = grp; t < n_parts; t += MVR_THREADS / 16) s += partials[((size_t)n * n_parts + t) * 16 + v];
-  s_sum[tid] = s;
-  __syncthreads();
-  if (tid < 16) {
-    float tot = 0.f;
-#pragma unroll
-    for (int g = 0; g < MVR_THREADS / 16; ++g) tot += s_sum[g * 16 + tid];
-    if (tid < 9) gR[9 * (size_t)n + tid] = tot;
-    else if (tid < 12) gT[3 * (size_t)n + tid - 9] = tot;
-    else if (tid < 15) gC[3 * (size_t)n + tid - 12] = tot;
-  }
 }
 
 }  // namespace mvr
@@ -248,7 +200,7 @@ static int backward_minb() {
 extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
                                  int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
                                  const float* T, const float* Cc, const float* light, int light_stride,
-                                 const float* obj_rgb, float k00, float k11, int H, int W, int K, int flags,
+                                 const float* obj_rgb, float k00, float k11, float z_clip, int H, int W, int K, int flags,
                                  const float* out_mean_std, const int* pix_to_face, const void* grad_images, float* gR, float* gT, float* gC,
                                  float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,
                                  void* stream) {
@@ -268,7 +220,7 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   char* wb = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   // the workspace is scratch (it may have served another render since the forward): project again, 2% of the step
-  rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, workspace, st);
+  rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, z_clip, true, workspace, st);
   if (rc) return rc;
   MeshBwdParams p;
   p.verts4 = (const float4*)(gb + g.verts4); p.normals4 = (const float4*)(gb + g.normals4);
@@ -281,12 +233,13 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   p.pix_to_face = pix_to_face; p.grad_images = grad_images;
   p.partials = (float*)(wb + w.partials); p.grad_verts = grad_verts; p.grad_normals = grad_normals;
   p.onorm = make_out_norm(out_mean_std);
+  p.z_clip = z_clip; p.wsflags = (int*)(wb + w.flags); p.parts_per_view = w.bwd_parts_per_view;
   const dim3 bgrid((unsigned)w.bwd_ctas_per_view, (unsigned)M, (unsigned)B);
   if (backward_minb() == 2) MVR_LAUNCH(mesh_backward_kernel<2>, bgrid, MVR_THREADS, 0, st, p);
   else if (backward_minb() == 4) MVR_LAUNCH(mesh_backward_kernel<4>, bgrid, MVR_THREADS, 0, st, p);
   else MVR_LAUNCH(mesh_backward_kernel<3>, bgrid, MVR_THREADS, 0, st, p);
   rc = check_launch("mesh_backward_kernel");
   if (rc) return rc;
-  MVR_LAUNCH(mesh_backward_reduce_kernel, (unsigned)N, MVR_THREADS, 0, st, (const float*)(wb + w.partials), w.bwd_ctas_per_view * NWARPS, gR, gT, gC);
-  return check_launch("mesh_backward_reduce_kernel");
+  // clipped-face pixels (if any) + the fixed-order sum of the per-warp partials -> gR, gT, gC
+  return launch_mesh_backward_finish(p, (int)N, gR, gT, gC, st);
 }

@@ -575,7 +575,7 @@ def _mesh_forward_launch(geom: "PackedMeshes", M, R, T, Cc, light, obj_rgb, bg_r
                                      _ptr(light), light_stride, _ptr(obj_rgb), _ptr(bg_rgb), k00, k11, z_clip, H, W,
                                      K, flags, out_norm, _ptr(images), _ptr(p2f), _ptr(zbuf), _ptr(bary), _ptr(dists),
                                      _ptr(counters), _ptr(ws), ws.numel(), _stream(dev)), "mvr_mesh_forward")
-    cfg = (k00, k11, H, W, K, flags, out_norm, light_stride)
+    cfg = (k00, k11, H, W, K, flags, out_norm, light_stride, z_clip)
     saved = (R, T, Cc, light, obj_rgb if obj_rgb is not None else bg_rgb, p2f)
     extras = [p2f, counters]
     if want_fragments:
@@ -587,7 +587,7 @@ def _mesh_backward_launch(geom: "PackedMeshes", M, cfg, saved, g_images, want_ve
     """ONE mvr_mesh_backward call -> (gR, gT, gC, gV | None) (gV includes the torch chain through the vertex normals)."""
     lib = L.load()
     R, T, Cc, light, obj_rgb, p2f = saved
-    k00, k11, H, W, K, flags, out_norm, light_stride = cfg
+    k00, k11, H, W, K, flags, out_norm, light_stride, z_clip = cfg
     dev = geom.device
     N = geom.B * M
     g_images = _grad_like_images(g_images, flags)
@@ -602,7 +602,7 @@ def _mesh_backward_launch(geom: "PackedMeshes", M, cfg, saved, g_images, want_ve
     with _on(dev):
         L.check(lib.mvr_mesh_backward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
                                       geom.total_verts, geom.total_faces, geom.max_verts, _ptr(R), _ptr(T), _ptr(Cc), _ptr(light),
-                                      light_stride, _ptr(obj_rgb), k00, k11, H, W, K, flags, out_norm, _ptr(p2f),
+                                      light_stride, _ptr(obj_rgb), k00, k11, z_clip, H, W, K, flags, out_norm, _ptr(p2f),
                                       _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gC), _ptr(gV), _ptr(gN), _ptr(ws),
                                       ws.numel(), _stream(dev)), "mvr_mesh_backward")
     if gV is not None:

@@ -147,13 +147,14 @@ def run_mesh(oracle, dev, cfg, backward=True, extra_flags=0):
     flags_note = extra_flags
     img, frag = ops.render_meshes(geom, M, Rg, Tg, Cg, torch.from_numpy(light).to(dev), None if vert_rgb is not None else torch.from_numpy(obj).to(dev),
                                   torch.from_numpy(bg).to(dev), H, faces_per_pixel=K, cull_backfaces=cull, perspective_correct=persp,
-                                  fragments=True, _extra_flags=flags_note)
+                                  fragments=True, _extra_flags=flags_note, z_clip=cfg.get("z_clip"))
     vp, fp, voff, foff = pack_np(meshes)
     nrm = oracle.packed_vertex_normals(vp, fp, voff, foff)
     assert np.abs(geom.vertex_normals().cpu().numpy() - nrm).max() < 5e-7
     oflags = (oracle.PERSPECTIVE_CORRECT if persp else 0) | (oracle.CULL_BACKFACES if cull else 0)
     rgb = obj if vert_rgb is None else vert_rgb.numpy()
-    o = oracle.mesh_forward(vp, fp, voff, foff, nrm, rgb, M, R, T, C, light, bg, K00, K11, 0.5 if persp else -1.0, H, H, K, oflags)
+    z_clip = cfg.get("z_clip", 0.5 if persp else -1.0)
+    o = oracle.mesh_forward(vp, fp, voff, foff, nrm, rgb, M, R, T, C, light, bg, K00, K11, z_clip, H, H, K, oflags)
     p2f = frag["pix_to_face"].cpu().numpy()
     res = dict(o=o, frag=frag, img=img, geom=geom, p2f=p2f)
     # exact depth ties inside a pixel's K-list (counted and reported); they must still agree
@@ -168,7 +169,7 @@ def run_mesh(oracle, dev, cfg, backward=True, extra_flags=0):
     if backward:
         g = torch.randn(B * M, 3, H, H, generator=torch.Generator().manual_seed(5))
         img.backward(g.to(dev))
-        ob = oracle.mesh_backward(vp, fp, voff, foff, nrm, rgb, M, R, T, C, light, K00, K11, H, H, K, oflags, p2f, g.numpy())
+        ob = oracle.mesh_backward(vp, fp, voff, foff, nrm, rgb, M, R, T, C, light, K00, K11, H, H, K, oflags, p2f, g.numpy(), z_clip=z_clip)
         assert rel(Rg.grad, ob["gR"]) < GRAD_RTOL
         assert rel(Tg.grad, ob["gT"]) < GRAD_RTOL
         assert rel(Cg.grad, ob["gC"]) < GRAD_RTOL
@@ -250,6 +251,76 @@ def test_mesh_near_plane_counters(oracle, cuda_device):
     v = (torch.tensor([[0.0, 90.0]]), torch.tensor([[0.0, 10.0]]), torch.tensor([[1.02, 1.05]]))
     res = run_mesh(oracle, cuda_device, dict(meshes=m, M=2, H=64, K=1, views=v), backward=False)
     assert res["o"]["straddle"] > 0
+
+
+def _clipped_pixels(oracle, res, cfg, z_clip=0.5):
+    """Pixels whose winning face crosses the near plane (recomputed from the oracle's projection)."""
+    meshes, M = cfg["meshes"], cfg["M"]
+    az, el, di = cfg["views"]
+    R, T, _ = oracle.look_at(az.numpy().ravel(), el.numpy().ravel(), di.numpy().ravel())
+    n_px = 0
+    for b, (v, f) in enumerate(meshes):
+        for m in range(M):
+            n = b * M + m
+            z = (v.numpy() @ R[n] + T[n])[:, 2][f.numpy()]              # (F,3) view depths
+            strad = ((z < z_clip).sum(1) % 3) != 0
+            p = res["p2f"][n, ..., 0]
+            n_px += int(strad[p[p >= 0]].sum())
+    return n_px
+
+
+@pytest.mark.parametrize("variant", ["persp_k1", "persp_k2", "noperspective", "vertex_rgb_relative_light"])
+def test_mesh_near_plane_clipping(oracle, cuda_device, variant):
+    """Cameras 1.12 - 1.3 away from a unit-sphere object (mvtn.py:33 transform_distance reaches 1.1): faces crossing
+    z = znear / 2 are clipped into one or two triangles ([upstream] clip.py) -- fragments bit-exact, images and camera
+    gradients within the usual bars, for the pixels the clipped kernels own as for all the others."""
+    m = synth.make_meshes(2, 1500, 61)
+    views = (torch.tensor([[15.0, 140.0, -80.0], [200.0, 33.0, 77.0]]), torch.tensor([[10.0, -35.0, 50.0], [0.0, 20.0, -15.0]]),
+             torch.tensor([[1.12, 1.2, 1.3], [1.15, 1.25, 1.18]]))
+    cfg = dict(meshes=m, M=3, H=72, K=1, views=views)
+    if variant == "persp_k2":
+        cfg["K"] = 2
+    if variant == "noperspective":
+        cfg.update(persp=False, z_clip=0.5)
+    if variant == "vertex_rgb_relative_light":
+        cfg.update(meshes=m[:1], views=tuple(t[:1] for t in views), light="relative",
+                   vert_rgb=torch.rand(m[0][0].shape[0], 3, generator=torch.Generator().manual_seed(3)))
+    res = run_mesh(oracle, cuda_device, cfg)
+    assert res["o"]["straddle"] > 0
+    assert _clipped_pixels(oracle, res, cfg) > 200
+    zb = res["o"]["zbuf"][res["o"]["pix_to_face"] >= 0]
+    assert float(zb.min()) >= 0.5 - 1e-5      # nothing nearer than the plane survives
+
+
+def test_mesh_clipping_vertex_gradients(oracle, cuda_device):
+    from oracle import torch_ref as tr
+    dev = cuda_device
+    v, f = synth.make_mesh(400, 15)
+    M, H = 3, 48
+    views = (torch.tensor([[15.0, 140.0, -80.0]]), torch.tensor([[10.0, -35.0, 50.0]]), torch.tensor([[1.15, 1.22, 1.3]]))
+    R, T, C, (Rd, Td, Cd) = cams(oracle, views, dev)
+    vg = v.to(dev).requires_grad_()
+    geom = ops.PackedMeshes.from_packed(vg.detach(), f.to(dev), [v.shape[0]], [f.shape[0]])
+    col = torch.full((3,), 0.99999, device=dev); light = torch.tensor([[0.3, 1.0, -0.5]], device=dev)
+    img, frag = ops.render_meshes(geom, M, Rd, Td, Cd, light, col, col, H, verts=vg)
+    assert int(frag["counters"][L.CNT_STRADDLE]) > 0
+    g = torch.randn(M, 3, H, H, generator=torch.Generator().manual_seed(4))
+    p2f = frag["pix_to_face"].cpu().numpy()
+    D = torch.float64
+    vd = v.to(D).requires_grad_()
+    nd = tr.vertex_normals(vd, f)
+    loss = 0
+    for n in range(M):
+        im, p2 = tr.render_mesh_view(vd, f, nd, torch.full((v.shape[0], 3), 0.99999, dtype=D), torch.from_numpy(R[n]).to(D), torch.from_numpy(T[n]).to(D),
+                                     torch.from_numpy(C[n]).to(D), torch.tensor([0.3, 1.0, -0.5], dtype=D), torch.full((3,), 0.99999, dtype=D), K00, K11, H, H,
+                                     z_clip=0.5)
+        same = torch.from_numpy(p2f[n, ..., 0]).long() == p2       # fp64 restatement: drop pixels a rounding error away from an edge
+        assert int((~same).sum()) <= 2
+        g[n] *= same[None]
+        loss = loss + (im * g[n].to(D)).sum()
+    img.backward(g.to(dev))
+    loss.backward()
+    assert rel(vg.grad, vd.grad.numpy()) < 5e-4
 
 
 def test_mesh_golden_slice(cuda_device):
