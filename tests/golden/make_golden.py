@@ -64,6 +64,32 @@ def points_c1():
     print("points: covered", (o["idx"] >= 0).mean(), (o4["idx"][..., 0] >= 0).mean())
 
 
+def mesh_clip():
+    """Close-up (dist 1.12 - 1.3, the range mvtn.py:33 transform_distance reaches): faces cross z_clip = 0.5 and are clipped
+    ([upstream] clip.py).  One ~1.5k-face mesh x 3 views, 96x96, K = 2.  Only mesh_clip.npz is (re)written."""
+    v, f = synth.make_mesh(1500, 61)
+    az = np.array([15.0, 140.0, -80.0], np.float32); el = np.array([10.0, -35.0, 50.0], np.float32)
+    di = np.array([1.12, 1.2, 1.3], np.float32)
+    R, T, C = orc.look_at(az, el, di)
+    vp = v.numpy(); fp = f.numpy().astype(np.int32)
+    voff = np.array([0, vp.shape[0]], np.int32); foff = np.array([0, fp.shape[0]], np.int32)
+    nrm = orc.vertex_normals(vp, fp)
+    k00, k11 = ops.fov_projection_scale()
+    col = np.full(3, 0.99999, np.float32); light = np.array([[0, 1.0, 0]], np.float32)
+    o = orc.mesh_forward(vp, fp, voff, foff, nrm, col, 3, R, T, C, light, col, k00, k11, 0.5, 96, 96, 2, orc.PERSPECTIVE_CORRECT)
+    assert o["straddle"] > 0
+    np.savez_compressed(os.path.join(HERE, "mesh_clip.npz"), verts=vp, faces=fp, R=R, T=T, C=C,
+                        k00=np.float32(k00), k11=np.float32(k11), straddle=np.int64(o["straddle"]),
+                        p2f_sha256=sha(o["pix_to_face"]), zbuf_sha256=sha(o["zbuf"]), bary_sha256=sha(o["bary"]),
+                        dists_sha256=sha(o["dists"]),
+                        covered=(o["pix_to_face"][..., 0] >= 0).sum(axis=(1, 2)).astype(np.int64),
+                        image_sum=o["images"].astype(np.float64).sum(axis=(1, 2, 3)),
+                        image_probe=o["images"][:, :, ::8, ::8].copy())
+    print("mesh clip: straddling faces", o["straddle"], "covered", (o["pix_to_face"][..., 0] >= 0).mean())
+
+
 if __name__ == "__main__":
-    mesh_slice()
-    points_c1()
+    if "--only-clip" not in sys.argv:
+        mesh_slice()
+        points_c1()
+    mesh_clip()

@@ -338,6 +338,22 @@ def test_mesh_golden_slice(cuda_device):
     assert np.allclose(img.double().sum(dim=(1, 2, 3)).cpu().numpy(), g["image_sum"], rtol=1e-6)
 
 
+def test_mesh_golden_clip(cuda_device):
+    """Committed golden of a close-up scene with 238 faces crossing the near plane (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, "mesh_clip.npz"))
+    dev = cuda_device
+    geom = ops.PackedMeshes([torch.from_numpy(g["verts"])], [torch.from_numpy(g["faces"])], dev)
+    R, T, C = (torch.from_numpy(g[k]).to(dev) for k in ("R", "T", "C"))
+    col = torch.full((3,), 0.99999, device=dev)
+    img, frag = ops.render_meshes(geom, 3, R, T, C, torch.tensor([[0, 1.0, 0]], device=dev), col, col, 96, faces_per_pixel=2, fragments=True)
+    assert int(frag["counters"][L.CNT_STRADDLE]) == int(g["straddle"])
+    assert sha(frag["pix_to_face"].cpu().numpy()) == str(g["p2f_sha256"])
+    assert sha(frag["zbuf"].cpu().numpy()) == str(g["zbuf_sha256"])
+    assert sha(frag["bary_coords"].cpu().numpy()) == str(g["bary_sha256"])
+    assert sha(frag["dists"].cpu().numpy()) == str(g["dists_sha256"])
+    assert np.abs(img.cpu().numpy()[:, :, ::8, ::8] - g["image_probe"]).max() <= IMG_ATOL
+
+
 def test_mesh_full_size_c2_properties(oracle, cuda_device):
     """BASELINE configs[1] at full size (32 x 12 views, ~10k faces, 224^2): size-independent properties +
     the oracle on two sampled objects."""

@@ -386,6 +386,19 @@ def test_golden_mesh_slice(oracle):
     assert np.abs(o["images"][:, :, ::16, ::16] - g["image_probe"]).max() < 1e-6
 
 
+def test_golden_mesh_clip(oracle):
+    g = np.load(os.path.join(GOLDEN, "mesh_clip.npz"))
+    vp, fp = g["verts"], g["faces"]
+    nrm = oracle.vertex_normals(vp, fp)
+    col = np.full(3, 0.99999, np.float32); light = np.array([[0, 1.0, 0]], np.float32)
+    o = oracle.mesh_forward(vp, fp, [0, vp.shape[0]], [0, fp.shape[0]], nrm, col, 3, g["R"], g["T"], g["C"], light, col,
+                            float(g["k00"]), float(g["k11"]), 0.5, 96, 96, 2, oracle.PERSPECTIVE_CORRECT)
+    assert o["straddle"] == int(g["straddle"]) > 0
+    assert sha(o["pix_to_face"]) == str(g["p2f_sha256"]) and sha(o["zbuf"]) == str(g["zbuf_sha256"])
+    assert sha(o["bary"]) == str(g["bary_sha256"]) and sha(o["dists"]) == str(g["dists_sha256"])
+    assert np.abs(o["images"][:, :, ::8, ::8] - g["image_probe"]).max() < 1e-6
+
+
 def test_golden_points(oracle):
     g = np.load(os.path.join(GOLDEN, "points_c1.npz"))
     col = np.full(3, 0.99999, np.float32)
