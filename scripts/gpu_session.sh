@@ -1,26 +1,27 @@
 #!/bin/bash
-# One GPU-box session: parity tests, bench (mesh + points + C5 shapes), e2e host breakdown, ncu launch list + captures.
-# usage: scripts/gpu_session.sh <tag> [quick]
-TAG=${1:-rX}
-OUT=gpurun_out
-mkdir -p $OUT
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $OUT/${TAG}_smi.txt 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1
-tail -2 $OUT/${TAG}_smoke.log
-timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
-tail -3 $OUT/${TAG}_pytest.log
-B="python bench.py --steps 30 --warmup 5"
-$B > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
-MVR_BWD_MINB=2 $B --no-cpu-baseline > $OUT/${TAG}_bench_bwd2.json 2>> $OUT/${TAG}_bench.err
-$B --workload points --no-cpu-baseline > $OUT/${TAG}_bench_points.json 2>> $OUT/${TAG}_bench.err
-$B --workload points --points-per-pixel 1 --no-cpu-baseline > $OUT/${TAG}_bench_points_k1.json 2>> $OUT/${TAG}_bench.err
-$B --batch 8 --views 20 --image-size 400 --faces 100000 --no-cpu-baseline > $OUT/${TAG}_bench_c5_mesh.json 2>> $OUT/${TAG}_bench.err
-$B --workload points --batch 8 --views 20 --image-size 400 --points 16384 --no-cpu-baseline > $OUT/${TAG}_bench_c5_points.json 2>> $OUT/${TAG}_bench.err
-python scripts/e2e_breakdown.py > $OUT/${TAG}_e2e_breakdown.txt 2>&1
-if [ "$2" != "quick" ]; then
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_b.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:mesh_ -s 30 -c 5 -o $OUT/${TAG}_mesh -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_m.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:points_ -s 20 -c 4 -o $OUT/${TAG}_points -f python bench.py --workload points --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_p.log 2>&1
-fi
-for f in bench bench_bwd2 bench_points bench_points_k1 bench_c5_mesh bench_c5_points; do echo "== $f"; cut -c1-1500 $OUT/${TAG}_$f.json; done
-tail -5 $OUT/${TAG}_bench.err
+# Quick GPU-box session: parity tests + the bench lines quoted in README / DESIGN (no CPU baseline, no ncu).
+#   gpurun --timeout 900 -- 'bash scripts/gpu_session.sh <tag>'        (scripts/gpu_session_full.sh adds the CPU
+#   baseline, the reference arm, the ncu launch list and the --set full captures summarised under profiles/)
+TAG=${1:-rX}; OUT=gpurun_out; mkdir -p $OUT
+python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; tail -1 $OUT/${TAG}_smoke.log
+timeout 1500 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest.log 2>&1; tail -2 $OUT/${TAG}_pytest.log | cut -c1-200
+B="python bench.py --steps 30 --warmup 5 --no-cpu-baseline"
+run() { name=$1; shift; $B "$@" > $OUT/${TAG}_$name.json 2>> $OUT/${TAG}_bench.err; python - <<PY
+import json
+try:
+    d = json.load(open("$OUT/${TAG}_$name.json"))
+    print("$name", d["value"], d["ms_per_step"], "fwd", d.get("forward_only", {}).get("value"), "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"],
+          d["e2e"].get("list_api", {}).get("value"), d["roofline"]["kernel_ms_all"], d["roofline"]["frac"], d["gpu_launches"])
+except Exception as e:
+    print("$name", "FAILED", e)
+PY
+}
+run mesh
+run points --workload points
+run points_graph --workload points --cuda-graph
+run points_k1 --workload points --points-per-pixel 1
+run c1 --workload points --batch 1 --points-per-pixel 1
+run c1_graph --workload points --batch 1 --points-per-pixel 1 --cuda-graph
+run c5_mesh --batch 8 --views 20 --image-size 400 --faces 100000
+run c5_points --workload points --batch 8 --views 20 --image-size 400 --points 16384
+grep -v "UserWarning\|run_backward" $OUT/${TAG}_bench.err | tail -5

@@ -230,3 +230,19 @@ def test_collate_meshes_packs_like_torch_cat():
         HostPackedMeshes(hp.verts, hp.faces.to(torch.int64), hp.num_verts, hp.num_faces)
     empty = collate_meshes([], pin_memory=False)
     assert len(empty) == 0 and empty.verts.shape == (0, 3)
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the oracle port on the host cores) needs no GPU: one tiny step, one JSON line."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--batch", "1", "--views", "2",
+                          "--image-size", "32", "--faces", "200", "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "views/s" and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
