@@ -247,6 +247,32 @@ def run_ours(a):
         torch.cuda.current_stream().synchronize()
         return g_host
 
+    g_ring = [torch.empty(3, B, M, pin_memory=True) for _ in range(2)]
+    ev_ring = [torch.cuda.Event() for _ in range(2)]
+    ring = {"i": 0}
+
+    def step_e2e_pipelined():
+        """step_e2e without the per-step device sync: the gradients of step i travel to a pinned ring buffer behind an
+        event and are read on the host while step i+1 is in flight (what a training loop that logs with one step of lag
+        does).  Every step still pays its own H2D and D2H inside the timed region; only the wait moves."""
+        i = ring["i"]; ring["i"] = i + 1
+        az = azim_h.to(dev, non_blocking=True).requires_grad_()
+        el = elev_h.to(dev, non_blocking=True).requires_grad_()
+        di = dist_h.to(dev, non_blocking=True).requires_grad_()
+        if a.workload == "mesh":
+            img, _ = renderer(mesh_host, None, az, el, di)
+        else:
+            img, _ = renderer(None, pts_h, az, el, di)
+        img.backward(cot.view_as(img))
+        g = g_ring[i & 1]
+        g[0].copy_(az.grad, non_blocking=True)
+        g[1].copy_(el.grad, non_blocking=True)
+        g[2].copy_(di.grad, non_blocking=True)
+        ev_ring[i & 1].record()
+        if i > 0:
+            ev_ring[(i - 1) & 1].synchronize()
+        return g_ring[(i - 1) & 1]
+
     if a.workload == "mesh":
         # verts fp32 + faces narrowed to int32 by the multi-threaded host gather + the three (B, M) view tensors
         h2d = sum(v.numel() * 4 + f.numel() * 4 for v, f in inp["meshes"]) + 3 * B * M * 4
@@ -283,6 +309,7 @@ def run_ours(a):
         step_forward_only()
     for _ in range(max(a.warmup, 3)):
         step_e2e()
+        step_e2e_pipelined()
         if a.workload == "mesh":
             step_e2e(list_api=True)
     torch.cuda.synchronize()
@@ -299,6 +326,7 @@ def run_ours(a):
     ms, launches, prof, (w0, w1) = timed(step_resident, a.steps, profile=top)
     ms_fwd, _, _, _ = timed(step_forward_only, a.steps)
     ms_e2e, _, _, (w2, w3) = timed(step_e2e, a.steps)
+    ms_e2e_pipe, _, _, (_, w3) = timed(step_e2e_pipelined, a.steps)
     ms_e2e_list = None
     if a.workload == "mesh":
         ms_e2e_list, _, _, (_, w3) = timed(lambda: step_e2e(list_api=True), a.steps)
@@ -307,6 +335,7 @@ def run_ours(a):
     ms_max = parallel.max_over_ranks(ms, dev)
     ms_fwd_max = parallel.max_over_ranks(ms_fwd, dev)
     ms_e2e_max = parallel.max_over_ranks(ms_e2e, dev)
+    ms_e2e_pipe_max = parallel.max_over_ranks(ms_e2e_pipe, dev)
     ms_e2e_list_max = parallel.max_over_ranks(ms_e2e_list, dev) if ms_e2e_list is not None else None
     total_views = parallel.sum_over_ranks(N * a.steps, dev)
     value = total_views / (ms_max / 1e3)
@@ -342,6 +371,8 @@ def run_ours(a):
            "forward_only": {"value": round(total_views / (ms_fwd_max / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms_fwd_max / a.steps, 4)},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
 
+    out["e2e"]["pipelined"] = {"value": round(total_views / (ms_e2e_pipe_max / 1e3), 1), "ms_per_step": round(ms_e2e_pipe_max / a.steps, 4),
+                               "note": "same per-step H2D / D2H, but the result of step i is awaited on the host during step i+1 (no per-step device sync)"}
     if ms_e2e_list_max is not None:
         out["e2e"]["list_api"] = {"value": round(total_views / (ms_e2e_list_max / 1e3), 1), "ms_per_step": round(ms_e2e_list_max / a.steps, 4),
                                   "input": "python list of per-object CPU meshes (the reference's loader output); gather into pinned memory inside the timed region"}

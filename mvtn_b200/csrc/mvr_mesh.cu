@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
   const int n = blockIdx.x / p.chunks_per_view, chunk = blockIdx.x % p.chunks_per_view;
   const int b = n / p.M, m = n - b * p.M;
   const int f0 = p.face_off[b], F = p.face_off[b + 1] - f0;
-  const int fbeg = chunk * FACES_PER_CTA, fend = min(F, fbeg + FACES_PER_CTA);
+  const int fbeg = chunk * p.faces_per_cta, fend = min(F, fbeg + p.faces_per_cta);
   if (fbeg >= fend) return;
   const int voff = p.vert_off[b], V = p.vert_off[b + 1] - voff;
   const float4* pvn = p.pv + (size_t)p.M * voff + (size_t)m * V;     // this view's projected vertices
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
         bool queued = false;
         if (npx <= BIG_FACE_PIX) {
           // runs of G pixels: 8 for ordinary faces, up to 32 for large ones (<= 32 runs per face)
-          const int G = max(8, (npx + 31) >> 5);
+          const int G = max(p.run_len, (npx + 31) >> 5);
           const int nsub = (npx + G - 1) / G;
           const int at = atomicAdd(&s_cnt[0], nsub);
           if (at + nsub <= p.item_cap) {
@@ -397,72 +397,86 @@ __device__ __forceinline__ void shading_barycentrics(const Face& f, const FaceEd
   }
 }
 
-// grid: x = 32x8-pixel tiles of the image, y = view m, z = object b.  EXACT: the caller wants zbuf / bary / dists.
-template <bool EXACT, int MINB>
+// grid: x = 32 x (8 PPT)-pixel tiles of the image, y = view m, z = object b.  EXACT: the caller wants zbuf / bary / dists.
+// PPT pixels per thread (rows yi0 + 8 j): the keys -- the one operand that comes from DRAM -- of all of them are
+// loaded before the first is shaded, so a thread pays the DRAM trip once instead of once per pixel; the dependent L2
+// trips (face -> vertex records) of pixel j then overlap with those of the other warps only.
+template <bool EXACT, int MINB, int PPT>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_shade_kernel(const MeshParams p, int tiles_x) {
   const int b = blockIdx.z, m = blockIdx.y, n = b * p.M + m;
   int ty, tx;
   tile_rc(blockIdx.x, tiles_x, ty, tx);
-  const int xi = tx * 32 + (threadIdx.x & 31), yi = ty * 8 + (threadIdx.x >> 5);
+  const int xi = tx * 32 + (threadIdx.x & 31), yi0 = ty * (8 * PPT) + (threadIdx.x >> 5);
   const int HW = p.H * p.W;
-  if (xi >= p.W || yi >= p.H) return;
-  const int pix = yi * p.W + xi;
+  if (xi >= p.W || yi0 >= p.H) return;
   const int k = p.layer;
-  unsigned long long* kp = p.keys + (size_t)n * HW + pix;
-  const unsigned long long key = *kp;
-  if (k + 1 < p.K) {            // hand the layer to the next peeling pass
-    p.prev[(size_t)n * HW + pix] = key;
-    *kp = MVR_EMPTY_KEY;
-  }
-  int fid = -1;
-  float w[3] = {-1.f, -1.f, -1.f}, bb[3] = {-1.f, -1.f, -1.f}, pz = -1.f, dd = -1.f;
-  float out[3];
-  if (k == 0) { out[0] = __ldg(p.bg_rgb); out[1] = __ldg(p.bg_rgb + 1); out[2] = __ldg(p.bg_rgb + 2); }
-  if (key != MVR_EMPTY_KEY) {
-    const int f0 = p.face_off[b], voff = p.vert_off[b], V = p.vert_off[b + 1] - voff;
-    const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
-    fid = (int)(unsigned int)(key & 0xffffffffull);
-    const int4 fi = __ldg(p.faces4 + f0 + fid);
-    // every gather of this pixel is issued before the first use (one round trip to L2 instead of three)
-    const Face fc = gather_face(p.pv + (size_t)p.M * voff + (size_t)m * V, fi);
-    // rasterized as clipped sub-triangles: mesh_shade_clipped_kernel owns this pixel (flag: see WSF_CLIP)
-    if (may_clip(p.wsflags) && face_straddles(fc, p.z_clip)) return;
-    float4 X0, X1, X2, N0, N1, N2, c0, c1, c2;
-    if (k == 0) {
-      X0 = __ldg(p.verts4 + voff + fi.x); X1 = __ldg(p.verts4 + voff + fi.y); X2 = __ldg(p.verts4 + voff + fi.z);
-      N0 = __ldg(p.normals4 + voff + fi.x); N1 = __ldg(p.normals4 + voff + fi.y); N2 = __ldg(p.normals4 + voff + fi.z);
-      if (p.flags & MVR_RGB_PER_ELEMENT) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
-      else { c0 = c1 = c2 = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f); }
+  unsigned long long* const kp0 = p.keys + (size_t)n * HW + (size_t)yi0 * p.W + xi;
+  unsigned long long keys[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) keys[j] = (j == 0 || yi0 + 8 * j < p.H) ? __ldcs(kp0 + (size_t)(8 * j) * p.W) : MVR_EMPTY_KEY;
+  const float xf = __ldg(p.tab + xi);
+  const int f0 = p.face_off[b], voff = p.vert_off[b], V = p.vert_off[b + 1] - voff;
+  const float4* pvn = p.pv + (size_t)p.M * voff + (size_t)m * V;
+  const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
+  float bg[3] = {0.f, 0.f, 0.f};
+  if (k == 0) { bg[0] = __ldg(p.bg_rgb); bg[1] = __ldg(p.bg_rgb + 1); bg[2] = __ldg(p.bg_rgb + 2); }
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int yi = yi0 + 8 * j;
+    if (j > 0 && yi >= p.H) break;
+    const int pix = yi * p.W + xi;
+    const unsigned long long key = keys[j];
+    if (k + 1 < p.K) {            // hand the layer to the next peeling pass
+      p.prev[(size_t)n * HW + pix] = key;
+      p.keys[(size_t)n * HW + pix] = MVR_EMPTY_KEY;
     }
-    const float xf = __ldg(p.tab + xi), yf = __ldg(p.tab + p.W + yi);
-    const FaceEdges fe = face_edges(fc);
-    if (EXACT) {
-      // The barycentrics are recomputed with the SAME exact operation sequence as the scatter (from the same
-      // projected vertices), so the fragments returned to the caller are the rasterizer's, bit for bit.
-      raster_test(fc, fe, persp, xf, yf, w, bb, pz);
-      if (p.dists) {
-        const float e01 = point_line_dist2(xf, yf, fc.x0, fc.y0, fc.x1, fc.y1);
-        const float e02 = point_line_dist2(xf, yf, fc.x0, fc.y0, fc.x2, fc.y2);
-        const float e12 = point_line_dist2(xf, yf, fc.x1, fc.y1, fc.x2, fc.y2);
-        dd = -fminf(fminf(e01, e02), e12);
+    int fid = -1;
+    float w[3] = {-1.f, -1.f, -1.f}, bb[3] = {-1.f, -1.f, -1.f}, pz = -1.f, dd = -1.f;
+    float out[3] = {bg[0], bg[1], bg[2]};
+    if (key != MVR_EMPTY_KEY) {
+      fid = (int)(unsigned int)(key & 0xffffffffull);
+      const int4 fi = __ldg(p.faces4 + f0 + fid);
+      // every gather of this pixel is issued before the first use (one round trip to L2 instead of three)
+      const Face fc = gather_face(pvn, fi);
+      // rasterized as clipped sub-triangles: mesh_shade_clipped_kernel owns this pixel (flag: see WSF_CLIP)
+      if (may_clip(p.wsflags) && face_straddles(fc, p.z_clip)) continue;
+      float4 X0, X1, X2, N0, N1, N2, c0, c1, c2;
+      if (k == 0) {
+        X0 = __ldg(p.verts4 + voff + fi.x); X1 = __ldg(p.verts4 + voff + fi.y); X2 = __ldg(p.verts4 + voff + fi.z);
+        N0 = __ldg(p.normals4 + voff + fi.x); N1 = __ldg(p.normals4 + voff + fi.y); N2 = __ldg(p.normals4 + voff + fi.z);
+        if (p.flags & MVR_RGB_PER_ELEMENT) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
+        else { c0 = c1 = c2 = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f); }
       }
-    } else {
-      shading_barycentrics(fc, fe, persp, xf, yf, bb);
+      const float yf = __ldg(p.tab + p.W + yi);
+      const FaceEdges fe = face_edges(fc);
+      if (EXACT) {
+        // The barycentrics are recomputed with the SAME exact operation sequence as the scatter (from the same
+        // projected vertices), so the fragments returned to the caller are the rasterizer's, bit for bit.
+        raster_test(fc, fe, persp, xf, yf, w, bb, pz);
+        if (p.dists) {
+          const float e01 = point_line_dist2(xf, yf, fc.x0, fc.y0, fc.x1, fc.y1);
+          const float e02 = point_line_dist2(xf, yf, fc.x0, fc.y0, fc.x2, fc.y2);
+          const float e12 = point_line_dist2(xf, yf, fc.x1, fc.y1, fc.x2, fc.y2);
+          dd = -fminf(fminf(e01, e02), e12);
+        }
+      } else {
+        shading_barycentrics(fc, fe, persp, xf, yf, bb);
+      }
+      pz = __uint_as_float((unsigned int)(key >> 32));
+      if (k == 0) {
+        const ShadeCtx sc = load_shade_ctx(p.light, p.light_stride, p.Cc, n);
+        phong_pixel(bb, X0, X1, X2, N0, N1, N2, c0, c1, c2, sc, out);
+      }
     }
-    pz = __uint_as_float((unsigned int)(key >> 32));
-    if (k == 0) {
-      const ShadeCtx sc = load_shade_ctx(p.light, p.light_stride, p.Cc, n);
-      phong_pixel(bb, X0, X1, X2, N0, N1, N2, c0, c1, c2, sc, out);
+    const size_t po = ((size_t)n * HW + pix) * p.K + k;
+    p.pix_to_face[po] = fid;
+    if (EXACT) {
+      if (p.zbuf) p.zbuf[po] = pz;
+      if (p.dists) p.dists[po] = dd;
+      if (p.bary) { p.bary[3 * po] = bb[0]; p.bary[3 * po + 1] = bb[1]; p.bary[3 * po + 2] = bb[2]; }
     }
+    if (k == 0) store_rgb(p.images, p.flags & MVR_IMAGES_BF16, (size_t)n * 3 * HW + pix, (size_t)HW, out[0], out[1], out[2], p.onorm);
   }
-  const size_t po = ((size_t)n * HW + pix) * p.K + k;
-  p.pix_to_face[po] = fid;
-  if (EXACT) {
-    if (p.zbuf) p.zbuf[po] = pz;
-    if (p.dists) p.dists[po] = dd;
-    if (p.bary) { p.bary[3 * po] = bb[0]; p.bary[3 * po + 1] = bb[1]; p.bary[3 * po + 2] = bb[2]; }
-  }
-  if (k == 0) store_rgb(p.images, p.flags & MVR_IMAGES_BF16, (size_t)n * 3 * HW + pix, (size_t)HW, out[0], out[1], out[2], p.onorm);
 }
 
 }  // namespace mvr
@@ -527,8 +541,36 @@ static int scatter_minb() {
 }
 
 static int shade_minb() {
-  static const int v = [] { const char* e = getenv("MVR_SHADE_MINB"); const int x = e ? atoi(e) : 4; return (x == 5 || x == 6) ? x : 4; }();
+  static const int v = [] { const char* e = getenv("MVR_SHADE_MINB"); const int x = e ? atoi(e) : 4; return (x == 3 || x == 5 || x == 6) ? x : 4; }();
   return v;
+}
+// pixels per thread of the image-only shade kernel (profiling knob; default MVR_SHADE_PPT_DEFAULT)
+#ifndef MVR_SHADE_PPT_DEFAULT
+#define MVR_SHADE_PPT_DEFAULT 4
+#endif
+static int shade_ppt() {
+  static const int v = [] { const char* e = getenv("MVR_SHADE_PPT"); const int x = e ? atoi(e) : MVR_SHADE_PPT_DEFAULT; return (x == 1 || x == 2 || x == 4) ? x : MVR_SHADE_PPT_DEFAULT; }();
+  return v;
+}
+// scatter: faces per CTA (profiling knob: 256 / 512 / 1024 / 2048)
+static int scatter_fpc() {
+  static const int v = [] { const char* e = getenv("MVR_SCATTER_FPC"); const int x = e ? atoi(e) : FACES_PER_CTA; return (x == 256 || x == 512 || x == 2048) ? x : FACES_PER_CTA; }();
+  return v;
+}
+// scatter: pixels per filter run (profiling knob: 4 / 8 / 16)
+static int scatter_run() {
+  static const int v = [] { const char* e = getenv("MVR_SCATTER_RUN"); const int x = e ? atoi(e) : 8; return (x == 4 || x == 16) ? x : 8; }();
+  return v;
+}
+template <int PPT>
+static void launch_shade_fast(const MeshParams& p, int B, int M, int H, int W, cudaStream_t st) {
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + 8 * PPT - 1) / (8 * PPT);
+  const dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)M, (unsigned)B);
+  const int mb = shade_minb();
+  if (mb == 3) MVR_LAUNCH((mesh_shade_kernel<false, 3, PPT>), grid, MVR_THREADS, 0, st, p, tiles_x);
+  else if (mb == 5) MVR_LAUNCH((mesh_shade_kernel<false, 5, PPT>), grid, MVR_THREADS, 0, st, p, tiles_x);
+  else if (mb == 6) MVR_LAUNCH((mesh_shade_kernel<false, 6, PPT>), grid, MVR_THREADS, 0, st, p, tiles_x);
+  else MVR_LAUNCH((mesh_shade_kernel<false, 4, PPT>), grid, MVR_THREADS, 0, st, p, tiles_x);
 }
 extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
                                 int64_t total_verts, int64_t total_faces, int max_verts, int max_faces,
@@ -552,7 +594,8 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   if (!out_norm_valid(out_mean_std)) { set_error("mvr_mesh_forward: out_mean_std needs std > 0"); return -9; }
   const WsLayout w = ws_layout(B, M, H, W, K, total_verts);
   if (workspace_bytes < w.total) { set_error("mvr_mesh_forward: workspace too small (%zu < %zu)", workspace_bytes, w.total); return -7; }
-  const int chunks_per_view = max_faces > 0 ? (max_faces + FACES_PER_CTA - 1) / FACES_PER_CTA : 0;
+  const int fpc = scatter_fpc();
+  const int chunks_per_view = max_faces > 0 ? (max_faces + fpc - 1) / fpc : 0;
   if (N * (int64_t)(chunks_per_view + 1) > 0x7fffffffLL) { set_error("mvr_mesh_forward: too many face chunks"); return -8; }
   const GeomLayout g = geom_layout(total_verts, total_faces);
   const char* gb = (const char*)geometry;
@@ -566,7 +609,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.obj_rgb = obj_rgb; p.bg_rgb = bg_rgb;
   p.k00 = k00; p.k11 = k11; p.z_clip = z_clip;
   p.B = B; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags;
-  p.chunks_per_view = chunks_per_view; p.layer = 0;
+  p.chunks_per_view = chunks_per_view; p.layer = 0; p.faces_per_cta = fpc; p.run_len = scatter_run();
   p.item_cap = (flags & MVR_TEST_TINY_QUEUES) ? 24 : ITEM_CAP;
   p.wcap = (flags & MVR_TEST_TINY_QUEUES) ? 5 : WCAP;
   p.pv = (float4*)(wb + w.pv); p.tab = (float*)(wb + w.tab);
@@ -592,10 +635,10 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
       rc = check_launch("mesh_scatter_kernel");
       if (rc) return rc;
     }
-    if (zbuf || bary || dists) MVR_LAUNCH((mesh_shade_kernel<true, 3>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
-    else if (shade_minb() == 5) MVR_LAUNCH((mesh_shade_kernel<false, 5>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
-    else if (shade_minb() == 6) MVR_LAUNCH((mesh_shade_kernel<false, 6>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
-    else MVR_LAUNCH((mesh_shade_kernel<false, 4>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+    if (zbuf || bary || dists) MVR_LAUNCH((mesh_shade_kernel<true, 3, 1>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+    else if (shade_ppt() == 4) launch_shade_fast<4>(p, B, M, H, W, st);
+    else if (shade_ppt() == 2) launch_shade_fast<2>(p, B, M, H, W, st);
+    else launch_shade_fast<1>(p, B, M, H, W, st);
     rc = check_launch("mesh_shade_kernel");
     if (rc) return rc;
     if (z_clip >= 0.f) {      // pixels won by a face crossing the near plane (none in MVTN's default configurations: the kernel exits at once)

@@ -11,7 +11,9 @@
 
 namespace mvr {
 
-template <int MINB>
+// UNCOND: the cotangent of every pixel is loaded without waiting for its face id (background pixels included: ~40 % more
+// DRAM reads, one dependent DRAM trip less on every thread's critical path)
+template <int MINB, bool UNCOND>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const MeshBwdParams p) {
   const int tid = threadIdx.x;
   // grid: x = 32x32-pixel tiles, y = view m, z = object b; thread (lane, warp) owns pixels (x0+lane, y0+warp+8j)
@@ -35,7 +37,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
 #pragma unroll
   for (int j = 0; j < BWD_PIX_PER_THREAD; ++j) {
     const int pix = (yi0 + 8 * j) * p.W + xi;
-    if (fids[j] >= 0) {
+    if (UNCOND ? (xi < p.W && yi0 + 8 * j < p.H) : fids[j] >= 0) {
       load_grad_rgb(p.grad_images, p.flags & MVR_IMAGES_BF16, (size_t)n * 3 * HW + pix, (size_t)HW, p.onorm, gin[j][0], gin[j][1], gin[j][2]);
     } else {
       gin[j][0] = gin[j][1] = gin[j][2] = 0.f;
@@ -197,6 +199,11 @@ static int backward_minb() {
   return v;
 }
 
+static bool backward_uncond() {
+  static const bool v = [] { const char* e = getenv("MVR_BWD_UNCOND"); return e && atoi(e) == 1; }();
+  return v;
+}
+
 extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
                                  int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
                                  const float* T, const float* Cc, const float* light, int light_stride,
@@ -235,9 +242,10 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   p.onorm = make_out_norm(out_mean_std);
   p.z_clip = z_clip; p.wsflags = (int*)(wb + w.flags); p.parts_per_view = w.bwd_parts_per_view;
   const dim3 bgrid((unsigned)w.bwd_ctas_per_view, (unsigned)M, (unsigned)B);
-  if (backward_minb() == 2) MVR_LAUNCH(mesh_backward_kernel<2>, bgrid, MVR_THREADS, 0, st, p);
-  else if (backward_minb() == 4) MVR_LAUNCH(mesh_backward_kernel<4>, bgrid, MVR_THREADS, 0, st, p);
-  else MVR_LAUNCH(mesh_backward_kernel<3>, bgrid, MVR_THREADS, 0, st, p);
+  if (backward_minb() == 2) MVR_LAUNCH((mesh_backward_kernel<2, false>), bgrid, MVR_THREADS, 0, st, p);
+  else if (backward_minb() == 4) MVR_LAUNCH((mesh_backward_kernel<4, false>), bgrid, MVR_THREADS, 0, st, p);
+  else if (backward_uncond()) MVR_LAUNCH((mesh_backward_kernel<3, true>), bgrid, MVR_THREADS, 0, st, p);
+  else MVR_LAUNCH((mesh_backward_kernel<3, false>), bgrid, MVR_THREADS, 0, st, p);
   rc = check_launch("mesh_backward_kernel");
   if (rc) return rc;
   // clipped-face pixels (if any) + the fixed-order sum of the per-warp partials -> gR, gT, gC
