@@ -36,6 +36,13 @@ extern "C" {
 #define MVR_FACES_I64 16           /* faces given as int64 (F,3) -- the reference's layout, renderer.py:68 */
 #define MVR_IMAGES_BF16 32         /* images (forward) / grad_images (backward) are bfloat16 instead of float32 */
 #define MVR_SCALE_IS_DIST 64       /* points: the per-view scale array holds dist, not 1/dist (see mvr_points_forward) */
+/* workspace reuse hints of the mesh path (the caller vouches for them; all optional, off = always safe):             */
+#define MVR_WS_KEYS_ARMED 128      /* mvr_mesh_forward: the key plane of this workspace was left re-armed by a previous
+                                      mvr_mesh_forward with the SAME (B, M, H, W, K, total_verts) and MVR_WS_REARM_KEYS, and
+                                      nothing but mvr_mesh_backward has touched the workspace since: skip the plane memset */
+#define MVR_WS_REARM_KEYS 256      /* mvr_mesh_forward: the shade pass writes EMPTY back over every key it consumed */
+#define MVR_WS_PROJECTED 512       /* mvr_mesh_backward: projected vertices / pixel table / clip flag in the workspace are
+                                      those of the matching mvr_mesh_forward (same geometry, R, T): skip the re-projection */
 #define MVR_TEST_TINY_QUEUES 0x40000000 /* tests only: shrink the scatter kernel's work queues to force their fallbacks */
 
 /* Phong constants of DirectionalLights() / Materials() as constructed at renderer.py:190-191 */

@@ -63,13 +63,16 @@ __global__ void geom_pack_faces_kernel(const IdxT* __restrict__ faces, const int
   atomicAdd(nacc + 3 * (size_t)(voff + i2), nx); atomicAdd(nacc + 3 * (size_t)(voff + i2) + 1, ny); atomicAdd(nacc + 3 * (size_t)(voff + i2) + 2, nz);
 }
 
-__global__ void geom_finish_normals_kernel(const double* __restrict__ nacc, int64_t tv, float4* __restrict__ normals4) {
+__global__ void geom_finish_normals_kernel(const double* __restrict__ nacc, int64_t tv, const float4* __restrict__ verts4,
+                                           float4* __restrict__ normals4, float4* __restrict__ xn8) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= tv) return;
   const float x = (float)nacc[3 * v], y = (float)nacc[3 * v + 1], z = (float)nacc[3 * v + 2];
   const float n = sqrtf((x * x + y * y) + z * z);
   const float d = n > 1e-6f ? n : 1e-6f;
-  normals4[v] = make_float4(x / d, y / d, z / d, 0.f);
+  const float4 nn = make_float4(x / d, y / d, z / d, 0.f);
+  normals4[v] = nn;
+  xn8[2 * v] = verts4[v]; xn8[2 * v + 1] = nn;      // the interleaved copy the per-pixel kernels gather
 }
 
 __global__ void geom_get_normals_kernel(const float4* __restrict__ normals4, int64_t tv, float* __restrict__ out) {
@@ -440,10 +443,12 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_shade_kernel(const Mes
       const Face fc = gather_face(pvn, fi);
       // rasterized as clipped sub-triangles: mesh_shade_clipped_kernel owns this pixel (flag: see WSF_CLIP)
       if (may_clip(p.wsflags) && face_straddles(fc, p.z_clip)) continue;
+      // last layer: leave the plane armed for the next forward (background keys are EMPTY already; clipped pixels are
+      // re-armed by mesh_shade_clipped_kernel, which still needs their keys)
+      if ((p.flags & MVR_WS_REARM_KEYS) && k + 1 == p.K) p.keys[(size_t)n * HW + pix] = MVR_EMPTY_KEY;
       float4 X0, X1, X2, N0, N1, N2, c0, c1, c2;
       if (k == 0) {
-        X0 = __ldg(p.verts4 + voff + fi.x); X1 = __ldg(p.verts4 + voff + fi.y); X2 = __ldg(p.verts4 + voff + fi.z);
-        N0 = __ldg(p.normals4 + voff + fi.x); N1 = __ldg(p.normals4 + voff + fi.y); N2 = __ldg(p.normals4 + voff + fi.z);
+        gather_xn(p.xn8, voff + fi.x, X0, N0); gather_xn(p.xn8, voff + fi.y, X1, N1); gather_xn(p.xn8, voff + fi.z, X2, N2);
         if (p.flags & MVR_RGB_PER_ELEMENT) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
         else { c0 = c1 = c2 = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f); }
       }
@@ -516,7 +521,7 @@ extern "C" int mvr_mesh_prepare(const float* verts, const void* faces, const int
     if (flags & MVR_FACES_I64) MVR_LAUNCH(geom_pack_faces_kernel<long long>, grid, tb, 0, st, (const long long*)faces, vert_off, face_off, verts4, faces4, nacc);
     else MVR_LAUNCH(geom_pack_faces_kernel<int>, grid, tb, 0, st, (const int*)faces, vert_off, face_off, verts4, faces4, nacc);
   }
-  MVR_LAUNCH(geom_finish_normals_kernel, (unsigned)((total_verts + tb - 1) / tb), tb, 0, st, nacc, total_verts, normals4);
+  MVR_LAUNCH(geom_finish_normals_kernel, (unsigned)((total_verts + tb - 1) / tb), tb, 0, st, nacc, total_verts, verts4, normals4, (float4*)(base + g.xn8));
   return check_launch("mvr_mesh_prepare");
 }
 
@@ -552,9 +557,9 @@ static int shade_ppt() {
   static const int v = [] { const char* e = getenv("MVR_SHADE_PPT"); const int x = e ? atoi(e) : MVR_SHADE_PPT_DEFAULT; return (x == 1 || x == 2 || x == 4) ? x : MVR_SHADE_PPT_DEFAULT; }();
   return v;
 }
-// scatter: faces per CTA (profiling knob: 256 / 512 / 1024 / 2048)
+// scatter: faces per CTA (profiling knob: 256 / 512 / 1024 / 2048; 512 = 13 waves of CTAs at C2 instead of 6.5 -> shorter tail)
 static int scatter_fpc() {
-  static const int v = [] { const char* e = getenv("MVR_SCATTER_FPC"); const int x = e ? atoi(e) : FACES_PER_CTA; return (x == 256 || x == 512 || x == 2048) ? x : FACES_PER_CTA; }();
+  static const int v = [] { const char* e = getenv("MVR_SCATTER_FPC"); const int x = e ? atoi(e) : FACES_PER_CTA; return (x == 256 || x == 512 || x == 1024 || x == 2048) ? x : FACES_PER_CTA; }();
   return v;
 }
 // scatter: pixels per filter run (profiling knob: 4 / 8 / 16)
@@ -603,7 +608,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   cudaStream_t st = (cudaStream_t)stream;
   MeshParams p;
   p.verts4 = (const float4*)(gb + g.verts4); p.normals4 = (const float4*)(gb + g.normals4);
-  p.rgb4 = (const float4*)(gb + g.rgb4); p.faces4 = (const int4*)(gb + g.faces4);
+  p.rgb4 = (const float4*)(gb + g.rgb4); p.faces4 = (const int4*)(gb + g.faces4); p.xn8 = (const float4*)(gb + g.xn8);
   p.vert_off = vert_off; p.face_off = face_off;
   p.R = R; p.T = T; p.Cc = Cc; p.light = light; p.light_stride = light_stride;
   p.obj_rgb = obj_rgb; p.bg_rgb = bg_rgb;
@@ -620,7 +625,8 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.wsflags = (int*)(wb + w.flags);
   const size_t HW = (size_t)H * W;
   // every key = EMPTY, and the workspace flags right in front of the plane armed (WSF_CLIP)
-  cudaError_t e = cudaMemsetAsync(wb + w.flags, 0xFF, (w.keys - w.flags) + (size_t)N * HW * 8, st);
+  const size_t plane_bytes = (flags & MVR_WS_KEYS_ARMED) ? 0 : (size_t)N * HW * 8;
+  cudaError_t e = cudaMemsetAsync(wb + w.flags, 0xFF, (w.keys - w.flags) + plane_bytes, st);
   if (e != cudaSuccess) { set_error("mvr_mesh_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
   rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, z_clip, false, workspace, st);
   if (rc) return rc;

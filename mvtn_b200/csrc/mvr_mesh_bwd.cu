@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
     // mesh_project_kernel: for small faces the barycentrics amplify a 1-ulp change of a vertex by |xy| / area);
     // everything downstream is well conditioned and uses fast reciprocals ----
     const Face fc = gather_face(pvn, fi);
-    const float4 X0 = __ldg(p.verts4 + voff + fi.x), X1 = __ldg(p.verts4 + voff + fi.y), X2 = __ldg(p.verts4 + voff + fi.z);
-    const float4 N0 = __ldg(p.normals4 + voff + fi.x), N1 = __ldg(p.normals4 + voff + fi.y), N2 = __ldg(p.normals4 + voff + fi.z);
+    float4 X0, X1, X2, N0, N1, N2;
+    gather_xn(p.xn8, voff + fi.x, X0, N0); gather_xn(p.xn8, voff + fi.y, X1, N1); gather_xn(p.xn8, voff + fi.z, X2, N2);
     float4 c0 = ucol, c1 = ucol, c2 = ucol;
     if (per_vertex_rgb) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
     // (after every load of the pixel has been issued) a face crossing the near plane: mesh_backward_clipped_kernel owns the pixel
@@ -226,12 +226,13 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   const char* gb = (const char*)geometry;
   char* wb = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
-  // the workspace is scratch (it may have served another render since the forward): project again, 2% of the step
-  rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, z_clip, true, workspace, st);
+  // the workspace is scratch (it may have served another render since the forward): project again, 1% of the step,
+  // unless the caller vouches that it has not (MVR_WS_PROJECTED)
+  if (!(flags & MVR_WS_PROJECTED)) rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, z_clip, true, workspace, st);
   if (rc) return rc;
   MeshBwdParams p;
   p.verts4 = (const float4*)(gb + g.verts4); p.normals4 = (const float4*)(gb + g.normals4);
-  p.rgb4 = (const float4*)(gb + g.rgb4); p.faces4 = (const int4*)(gb + g.faces4);
+  p.rgb4 = (const float4*)(gb + g.rgb4); p.faces4 = (const int4*)(gb + g.faces4); p.xn8 = (const float4*)(gb + g.xn8);
   p.vert_off = vert_off; p.face_off = face_off;
   p.R = R; p.T = T; p.Cc = Cc; p.light = light; p.light_stride = light_stride; p.obj_rgb = obj_rgb;
   p.k00 = k00; p.k11 = k11;

@@ -47,6 +47,8 @@ __device__ __forceinline__ void shade_clipped_pixel(const MeshParams& p, int b, 
   // the shade pass has already handed this layer's keys to `prev` when another layer follows
   const unsigned long long key = (k + 1 < p.K) ? p.prev[(size_t)n * HW + pix] : p.keys[(size_t)n * HW + pix];
   if (key == MVR_EMPTY_KEY) return;
+  // the shade pass re-armed every key it consumed (MVR_WS_REARM_KEYS) except those of the pixels handled here
+  if ((p.flags & MVR_WS_REARM_KEYS) && k + 1 == p.K) p.keys[(size_t)n * HW + pix] = MVR_EMPTY_KEY;
   const int f0 = p.face_off[b], voff = p.vert_off[b], V = p.vert_off[b + 1] - voff;
   const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
   const int fid = (int)(unsigned int)(key & 0xffffffffull);

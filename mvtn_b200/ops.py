@@ -64,14 +64,63 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
-def workspace(device, nbytes: int) -> torch.Tensor:
-    """Per-(device, stream) scratch reused across calls (stream order makes reuse safe)."""
+def workspace(device, nbytes: int, _mesh_owner: bool = False) -> torch.Tensor:
+    """Per-(device, stream) scratch reused across calls (stream order makes reuse safe).  Any user other than the mesh
+    path invalidates what the mesh path remembers about the buffer's contents (see _ws_mesh_state)."""
     key = (torch.device(device).index, _stream(device))
     w = _workspaces.get(key)
     if w is None or w.numel() < nbytes:
         w = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = w
+        if _ws_mesh.get(key) is not _WS_POISON:
+            _ws_mesh.pop(key, None)
+    if not _mesh_owner and _ws_mesh.get(key) is not _WS_POISON:
+        _ws_mesh.pop(key, None)
     return w
+
+
+# What the mesh path knows about a workspace between its own calls (SURVEY 8f N1/N4: no redundant passes per step):
+#   "armed": (data_ptr, layout) -- the key plane was left all-EMPTY by the last forward (MVR_WS_REARM_KEYS), so the next
+#            forward with the same layout skips its 154 MB memset (C2);
+#   "proj":  token of the forward whose projected vertices / pixel table / clip flag still sit in the buffer, so its
+#            backward skips the re-projection.
+# Cleared by any other user of the buffer (workspace()), by reallocation, and never used on a stream that has been
+# captured into a CUDA graph (replays touch the buffer behind python's back).
+_ws_mesh = {}
+_WS_POISON = object()
+_ws_token = [0]
+
+
+def _ws_mesh_flags_forward(dev, ws, layout):
+    """-> (extra flags for mvr_mesh_forward, commit(): call after a successful launch, returns the projection token)."""
+    key = (torch.device(dev).index, _stream(dev))
+    if torch.cuda.is_current_stream_capturing():
+        _ws_mesh[key] = _WS_POISON
+    st = _ws_mesh.get(key)
+    if st is _WS_POISON:
+        return 0, lambda: None
+    flags = L.WS_REARM_KEYS
+    if st is not None and st.get("armed") == (ws.data_ptr(), layout):
+        flags |= L.WS_KEYS_ARMED
+    _ws_mesh.pop(key, None)          # nothing is known while the call is being made (it may raise)
+
+    def commit():
+        _ws_token[0] += 1
+        _ws_mesh[key] = {"armed": (ws.data_ptr(), layout), "proj": (ws.data_ptr(), _ws_token[0])}
+        return _ws_token[0]
+
+    return flags, commit
+
+
+def _ws_mesh_flags_backward(dev, ws, token):
+    key = (torch.device(dev).index, _stream(dev))
+    st = _ws_mesh.get(key)
+    if token is None or st is None or st is _WS_POISON or torch.cuda.is_current_stream_capturing():
+        return 0
+    if st.get("proj") == (ws.data_ptr(), token):
+        return L.WS_PROJECTED
+    st["proj"] = None      # this backward re-projects ITS views over whatever a later forward left there
+    return 0
 
 
 _staging_bufs = {}
@@ -568,14 +617,15 @@ def _mesh_forward_launch(geom: "PackedMeshes", M, R, T, Cc, light, obj_rgb, bg_r
         dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
     counters = torch.empty(L.NUM_COUNTERS, dtype=torch.int64, device=dev)      # zeroed by mvr_mesh_forward
     ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts)
-    ws = workspace(dev, ws_bytes)
+    ws = workspace(dev, ws_bytes, _mesh_owner=True)
+    ws_flags, ws_commit = _ws_mesh_flags_forward(dev, ws, (geom.B, M, H, W, K, geom.total_verts))
     with _on(dev):
         L.check(lib.mvr_mesh_forward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
                                      geom.total_verts, geom.total_faces, geom.max_verts, geom.max_faces, _ptr(R), _ptr(T), _ptr(Cc),
                                      _ptr(light), light_stride, _ptr(obj_rgb), _ptr(bg_rgb), k00, k11, z_clip, H, W,
-                                     K, flags, out_norm, _ptr(images), _ptr(p2f), _ptr(zbuf), _ptr(bary), _ptr(dists),
+                                     K, flags | ws_flags, out_norm, _ptr(images), _ptr(p2f), _ptr(zbuf), _ptr(bary), _ptr(dists),
                                      _ptr(counters), _ptr(ws), ws.numel(), _stream(dev)), "mvr_mesh_forward")
-    cfg = (k00, k11, H, W, K, flags, out_norm, light_stride, z_clip)
+    cfg = (k00, k11, H, W, K, flags, out_norm, light_stride, z_clip, ws_commit())
     saved = (R, T, Cc, light, obj_rgb if obj_rgb is not None else bg_rgb, p2f)
     extras = [p2f, counters]
     if want_fragments:
@@ -587,14 +637,15 @@ def _mesh_backward_launch(geom: "PackedMeshes", M, cfg, saved, g_images, want_ve
     """ONE mvr_mesh_backward call -> (gR, gT, gC, gV | None) (gV includes the torch chain through the vertex normals)."""
     lib = L.load()
     R, T, Cc, light, obj_rgb, p2f = saved
-    k00, k11, H, W, K, flags, out_norm, light_stride, z_clip = cfg
+    k00, k11, H, W, K, flags, out_norm, light_stride, z_clip, ws_token = cfg
     dev = geom.device
     N = geom.B * M
     g_images = _grad_like_images(g_images, flags)
     g = torch.empty(15 * N, dtype=torch.float32, device=dev)
     gR, gT, gC = g[: 9 * N].view(N, 3, 3), g[9 * N: 12 * N].view(N, 3), g[12 * N:].view(N, 3)
     ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts)
-    ws = workspace(dev, ws_bytes)
+    ws = workspace(dev, ws_bytes, _mesh_owner=True)
+    flags = flags | _ws_mesh_flags_backward(dev, ws, ws_token)
     gV = gN = None
     if want_verts:
         gV = torch.zeros((geom.total_verts, 3), dtype=torch.float32, device=dev)

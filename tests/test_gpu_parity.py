@@ -323,6 +323,79 @@ def test_mesh_clipping_vertex_gradients(oracle, cuda_device):
     assert rel(vg.grad, vd.grad.numpy()) < 5e-4
 
 
+def test_mesh_workspace_reuse_hints_are_exact(oracle, cuda_device):
+    """The mesh path remembers what it left in its workspace (ops._ws_mesh): a forward after a same-layout forward skips
+    the key-plane memset (the shade pass re-armed the plane, clipped pixels included), and a backward right after its
+    forward skips the re-projection.  Results must be those of a cold workspace, bit for bit -- across changing views,
+    layer peeling, near-plane clipping, out-of-order backwards and another renderer using the buffer."""
+    dev = cuda_device
+    col = torch.full((3,), 0.99999, device=dev); light = torch.tensor([[0, 1.0, 0]], device=dev)
+    key = (dev.index, ops._stream(dev))
+
+    def render(geom, M, views, H, K, fragments):
+        az, el, di = (t.to(dev).reshape(-1).requires_grad_() for t in views)
+        R, T, C, _ = ops._LookAt.apply(az, el, di)
+        img, fr = ops.render_meshes(geom, M, R, T, C, light, col, col, H, faces_per_pixel=K, fragments=fragments)
+        return img, fr, (az, el, di)
+
+    m = synth.make_meshes(2, 1500, 61)
+    geom = ops.PackedMeshes([v for v, _ in m], [f for _, f in m], dev)
+    far = (torch.tensor([[15.0, 140.0, -80.0], [200.0, 33.0, 77.0]]), torch.tensor([[10.0, -35.0, 50.0], [0.0, 20.0, -15.0]]),
+           torch.tensor([[2.2, 2.0, 2.5], [1.9, 2.25, 3.0]]))
+    near = (far[0] + 30.0, far[1], torch.tensor([[1.12, 1.2, 1.3], [1.15, 1.25, 1.18]]))      # faces cross the near plane
+    armed_hits = 0
+    for K in (1, 2):
+        for H in (72, 40):
+            for fragments in (True, False):
+                ref = {}
+                for name, views in (("far", far), ("near", near)):
+                    ops._ws_mesh.pop(key, None)
+                    img, fr, _ = render(geom, 3, views, H, K, fragments)
+                    ref[name] = (img.clone(), {k: v.clone() for k, v in fr.items() if k != "counters"})
+                if fragments:
+                    assert int(fr["counters"][L.CNT_STRADDLE]) > 0
+                ops._ws_mesh.pop(key, None)
+                for i, name in enumerate(["far", "near", "near", "far", "far", "near"]):
+                    st = ops._ws_mesh.get(key)
+                    armed_hits += st is not None and st["armed"] is not None
+                    img, fr, _ = render(geom, 3, far if name == "far" else near, H, K, fragments)
+                    assert torch.equal(img, ref[name][0]), (K, H, i, name)
+                    for k, v in ref[name][1].items():
+                        assert torch.equal(fr[k], v), (K, H, i, name, k)
+                    if i == 2:      # another user of the buffer: the hints must be dropped, not trusted
+                        pts = torch.rand(2, 256, 3, device=dev) - 0.5
+                        R, T, C, _ = ops._LookAt.apply(*(t.to(dev).reshape(-1) for t in far))
+                        ops.render_points(pts, col, 3, R, T, None, 0.02, col * 0, H, dist=far[2].to(dev).reshape(-1))
+                        assert ops._ws_mesh.get(key) is None
+    assert armed_hits >= 8 * 4
+    # gradients: warm (projection reused) == cold (re-projected), also when the backwards run out of order
+    cot = torch.randn(6, 3, 72, 72, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+
+    def grads(views, warm):
+        if not warm:
+            ops._ws_mesh.pop(key, None)
+        img, _, leaves = render(geom, 3, views, 72, 1, False)
+        if not warm:
+            ops._ws_mesh.pop(key, None)
+        else:
+            assert ops._ws_mesh[key]["proj"] is not None
+        img.backward(cot)
+        return [t.grad.clone() for t in leaves]
+
+    for views in (far, near):
+        for a, b in zip(grads(views, False), grads(views, True)):
+            assert torch.equal(a, b)
+    img_a, _, la = render(geom, 3, far, 72, 1, False)
+    img_b, _, lb = render(geom, 3, near, 72, 1, False)
+    img_a.backward(cot)      # a's projection was overwritten by b's forward: a re-projects, which in turn invalidates b's
+    assert ops._ws_mesh[key]["proj"] is None
+    img_b.backward(cot)
+    for a, b in zip(grads(far, False), [t.grad for t in la]):
+        assert torch.equal(a, b)
+    for a, b in zip(grads(near, False), [t.grad for t in lb]):
+        assert torch.equal(a, b)
+
+
 def test_mesh_golden_slice(cuda_device):
     g = np.load(os.path.join(GOLDEN, "mesh_c2_slice.npz"))
     dev = cuda_device
