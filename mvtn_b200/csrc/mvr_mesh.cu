@@ -151,6 +151,31 @@ __device__ __forceinline__ void resolve_pixel_with(const Face& fc, const FaceEdg
   atomicMin(key_ptr, key);      // result unused: RED.MIN.64 resolved in L2
 }
 
+// Phase B's pixel filter in FMA form.  Edge function i of the oracle, e_i = (px - xa) A - (py - ya) B (five IEEE
+// operations), is evaluated as fma(px, A, fma(-py, B, C)) with C = ya B - xa A: two instructions.  The two differ by
+// rounding only: with u = 2^-24, |px|, |py| <= pmax (1, or the aspect ratio of a non-square image) and
+// S = (pmax + |xa|) |A| + (pmax + |ya|) |B|, the IEEE sequence is within
+// 3 u S of the real value and the FMA form within 4 u S, so adding 16 u S to C makes "fma form > 0" a NECESSARY condition
+// for "IEEE form > 0": the filter never drops a pixel the exact test of phase C would accept, it only lets a few pixels
+// within 2^-20 S of an edge through to be rejected there.  The sign of the area is folded into (A, B, C) first (negation
+// is exact).  Record words 12..20 of the face: (A0, B0, C0', A1, B1, C1', A2, B2, C2').
+__device__ __forceinline__ void store_filter_edges(const Face& f, float pmax, float* rec) {
+  float A[3] = {f.y2 - f.y1, f.y0 - f.y2, f.y1 - f.y0};
+  float B[3] = {f.x2 - f.x1, f.x0 - f.x2, f.x1 - f.x0};
+  const float xa[3] = {f.x1, f.x2, f.x0}, ya[3] = {f.y1, f.y2, f.y0};
+  const float area_p = ((f.x2 - f.x0) * A[2] - (f.y2 - f.y0) * B[2]) + MVR_K_EPS;
+  const bool flip = !(area_p > 0.f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (flip) { A[i] = -A[i]; B[i] = -B[i]; }
+    const float C = ya[i] * B[i] - xa[i] * A[i];
+    const float S = (pmax + fabsf(xa[i])) * fabsf(A[i]) + (pmax + fabsf(ya[i])) * fabsf(B[i]);
+    rec[(3 * i + 0) * MVR_THREADS] = A[i];
+    rec[(3 * i + 1) * MVR_THREADS] = B[i];
+    rec[(3 * i + 2) * MVR_THREADS] = C + 9.5367431640625e-07f * S;      // 2^-20
+  }
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const MeshParams p) {
   __shared__ float s_rec[REC_WORDS][MVR_THREADS];     // SoA face records of the current round
@@ -208,6 +233,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
         s_rec[9][tid] = __int_as_float(fid);
         s_rec[10][tid] = __int_as_float(xl | (yl << 16));
         s_rec[11][tid] = __int_as_float(bw | (bh << 16));
+        store_filter_edges(fc, p.ndc_max, &s_rec[12][tid]);
         bool queued = false;
         if (npx <= BIG_FACE_PIX) {
           // runs of G pixels: 8 for ordinary faces, up to 32 for large ones (<= 32 runs per face)
@@ -233,14 +259,14 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
       const int j = j0 + lane;
       int slot = 0, count = 0;
       unsigned int xl_a = tab_a, xend_a = tab_a + 4u, xa = tab_a, ya = tab_a;     // shared-memory BYTE addresses
-      float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f, cx = 0.f, cy = 0.f;
+      float A0 = 0.f, B0 = 0.f, C0 = 0.f, A1 = 0.f, B1 = 0.f, C1 = 0.f, A2 = 0.f, B2 = 0.f, C2 = 0.f;
       if (j < n_items) {
         const int it = s_items[j];
         slot = it & 255; count = it >> 18;
         const int start = (it >> 8) & 1023;
-        ax = s_rec[0][slot]; ay = s_rec[1][slot];
-        bx = s_rec[3][slot]; by = s_rec[4][slot];
-        cx = s_rec[6][slot]; cy = s_rec[7][slot];
+        A0 = s_rec[12][slot]; B0 = s_rec[13][slot]; C0 = s_rec[14][slot];
+        A1 = s_rec[15][slot]; B1 = s_rec[16][slot]; C1 = s_rec[17][slot];
+        A2 = s_rec[18][slot]; B2 = s_rec[19][slot]; C2 = s_rec[20][slot];
         const int rxy = __float_as_int(s_rec[10][slot]);
         const int xl = rxy & 0xffff;
         const int bw = __float_as_int(s_rec[11][slot]) & 0xffff;
@@ -250,11 +276,6 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
         xa = xl_a + 4u * (unsigned)(start - row * bw);                       // address of xf of the run's first pixel
         ya = tab_a + 4u * (unsigned)(p.W + (rxy >> 16) + row);               // address of its yf
       }
-      // edge coefficients with the sign of the area folded in (negation is exact and commutes with rounding), so
-      // the filter below is "all three > 0" for either winding: bit-for-bit the sign test of raster_test
-      float A0 = cy - by, B0 = cx - bx, A1 = ay - cy, B1 = ax - cx, A2 = by - ay, B2 = bx - ax;
-      const float area_p = ((cx - ax) * A2 - (cy - ay) * B2) + MVR_K_EPS;
-      if (!(area_p > 0.f)) { A0 = -A0; B0 = -B0; A1 = -A1; B1 = -B1; A2 = -A2; B2 = -B2; }
       // candidate word = slot | x << 8 | y << 20 with x = (xa - tab_a) / 4, y = (ya - tab_a) / 4 - W: constants folded
       const unsigned int cand_m = (unsigned)slot - (tab_a << 6) - ((tab_a + 4u * (unsigned)p.W) << 18);
       const int maxc = __reduce_max_sync(0xffffffffu, count);
@@ -263,9 +284,10 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
         bool pass = false;
         if (c < count) {
           const float xf = lds_f32(xa), yf = lds_f32(ya);
-          const float e0 = (xf - bx) * A0 - (yf - by) * B0;
-          const float e1 = (xf - cx) * A1 - (yf - cy) * B1;
-          const float e2 = (xf - ax) * A2 - (yf - ay) * B2;
+          // conservative FMA form of the three edge functions (store_filter_edges): necessary for the exact test
+          const float e0 = fmaf(xf, A0, fmaf(-yf, B0, C0));
+          const float e1 = fmaf(xf, A1, fmaf(-yf, B1, C1));
+          const float e2 = fmaf(xf, A2, fmaf(-yf, B2, C2));
           pass = e0 > 0.f && e1 > 0.f && e2 > 0.f;
           xa += 4u;
           if (xa == xend_a) { xa = xl_a; ya += 4u; }
@@ -279,8 +301,9 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
           } else {                                                  // queue full: resolve in place
             const int xx = (int)((cxa - tab_a) >> 2), yy = (int)((cya - tab_a) >> 2) - p.W;
             Face fc;
-            fc.x0 = ax; fc.y0 = ay; fc.z0 = s_rec[2][slot]; fc.x1 = bx; fc.y1 = by; fc.z1 = s_rec[5][slot];
-            fc.x2 = cx; fc.y2 = cy; fc.z2 = s_rec[8][slot];
+            fc.x0 = s_rec[0][slot]; fc.y0 = s_rec[1][slot]; fc.z0 = s_rec[2][slot];
+            fc.x1 = s_rec[3][slot]; fc.y1 = s_rec[4][slot]; fc.z1 = s_rec[5][slot];
+            fc.x2 = s_rec[6][slot]; fc.y2 = s_rec[7][slot]; fc.z2 = s_rec[8][slot];
             resolve_pixel(fc, face_edges(fc), __float_as_int(s_rec[9][slot]), 0u, persp, s_xf[xx], s_yf[yy],
                           keys + (size_t)yy * p.W + xx, prev ? prev + (size_t)yy * p.W + xx : nullptr);
           }
@@ -391,11 +414,11 @@ __device__ __forceinline__ void shading_barycentrics(const Face& f, const FaceEd
   const float e0 = (xf - f.x1) * e.A0 - (yf - f.y1) * e.B0;
   const float e1 = (xf - f.x2) * e.A1 - (yf - f.y2) * e.B1;
   const float e2 = (xf - f.x0) * e.A2 - (yf - f.y0) * e.B2;
-  const float ia = __fdividef(1.0f, e.area_p);
+  const float ia = rcp_fast(e.area_p);
   b[0] = e0 * ia; b[1] = e1 * ia; b[2] = e2 * ia;
   if (persp) {
     const float t0 = b[0] * f.z1 * f.z2, t1 = b[1] * f.z0 * f.z2, t2 = b[2] * f.z0 * f.z1;
-    const float id = __fdividef(1.0f, fmaxf(t0 + t1 + t2, MVR_K_EPS));
+    const float id = rcp_fast(fmaxf(t0 + t1 + t2, MVR_K_EPS));
     b[0] = t0 * id; b[1] = t1 * id; b[2] = t2 * id;
   }
 }
@@ -404,7 +427,7 @@ __device__ __forceinline__ void shading_barycentrics(const Face& f, const FaceEd
 // PPT pixels per thread (rows yi0 + 8 j): the keys -- the one operand that comes from DRAM -- of all of them are
 // loaded before the first is shaded, so a thread pays the DRAM trip once instead of once per pixel; the dependent L2
 // trips (face -> vertex records) of pixel j then overlap with those of the other warps only.
-template <bool EXACT, int MINB, int PPT>
+template <bool EXACT, int MINB, int PPT, bool VRGB>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_shade_kernel(const MeshParams p, int tiles_x) {
   const int b = blockIdx.z, m = blockIdx.y, n = b * p.M + m;
   int ty, tx;
@@ -449,7 +472,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_shade_kernel(const Mes
       float4 X0, X1, X2, N0, N1, N2, c0, c1, c2;
       if (k == 0) {
         gather_xn(p.xn8, voff + fi.x, X0, N0); gather_xn(p.xn8, voff + fi.y, X1, N1); gather_xn(p.xn8, voff + fi.z, X2, N2);
-        if (p.flags & MVR_RGB_PER_ELEMENT) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
+        if (VRGB) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
         else { c0 = c1 = c2 = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f); }
       }
       const float yf = __ldg(p.tab + p.W + yi);
@@ -470,7 +493,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_shade_kernel(const Mes
       pz = __uint_as_float((unsigned int)(key >> 32));
       if (k == 0) {
         const ShadeCtx sc = load_shade_ctx(p.light, p.light_stride, p.Cc, n);
-        phong_pixel(bb, X0, X1, X2, N0, N1, N2, c0, c1, c2, sc, out);
+        phong_pixel<VRGB>(bb, X0, X1, X2, N0, N1, N2, c0, c1, c2, sc, out);
       }
     }
     const size_t po = ((size_t)n * HW + pix) * p.K + k;
@@ -546,7 +569,7 @@ static int scatter_minb() {
 }
 
 static int shade_minb() {
-  static const int v = [] { const char* e = getenv("MVR_SHADE_MINB"); const int x = e ? atoi(e) : 4; return (x == 3 || x == 5 || x == 6) ? x : 4; }();
+  static const int v = [] { const char* e = getenv("MVR_SHADE_MINB"); const int x = e ? atoi(e) : 4; return x == 3 ? 3 : 4; }();
   return v;
 }
 // pixels per thread of the image-only shade kernel (profiling knob; default MVR_SHADE_PPT_DEFAULT)
@@ -567,15 +590,13 @@ static int scatter_run() {
   static const int v = [] { const char* e = getenv("MVR_SCATTER_RUN"); const int x = e ? atoi(e) : 8; return (x == 4 || x == 16) ? x : 8; }();
   return v;
 }
-template <int PPT>
+template <int PPT, bool VRGB>
 static void launch_shade_fast(const MeshParams& p, int B, int M, int H, int W, cudaStream_t st) {
   const int tiles_x = (W + 31) / 32, tiles_y = (H + 8 * PPT - 1) / (8 * PPT);
   const dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)M, (unsigned)B);
   const int mb = shade_minb();
-  if (mb == 3) MVR_LAUNCH((mesh_shade_kernel<false, 3, PPT>), grid, MVR_THREADS, 0, st, p, tiles_x);
-  else if (mb == 5) MVR_LAUNCH((mesh_shade_kernel<false, 5, PPT>), grid, MVR_THREADS, 0, st, p, tiles_x);
-  else if (mb == 6) MVR_LAUNCH((mesh_shade_kernel<false, 6, PPT>), grid, MVR_THREADS, 0, st, p, tiles_x);
-  else MVR_LAUNCH((mesh_shade_kernel<false, 4, PPT>), grid, MVR_THREADS, 0, st, p, tiles_x);
+  if (mb == 3) MVR_LAUNCH((mesh_shade_kernel<false, 3, PPT, VRGB>), grid, MVR_THREADS, 0, st, p, tiles_x);
+  else MVR_LAUNCH((mesh_shade_kernel<false, 4, PPT, VRGB>), grid, MVR_THREADS, 0, st, p, tiles_x);
 }
 extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
                                 int64_t total_verts, int64_t total_faces, int max_verts, int max_faces,
@@ -615,6 +636,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.k00 = k00; p.k11 = k11; p.z_clip = z_clip;
   p.B = B; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags;
   p.chunks_per_view = chunks_per_view; p.layer = 0; p.faces_per_cta = fpc; p.run_len = scatter_run();
+  p.ndc_max = W > H ? (float)((W + H - 1) / H) : (float)((H + W - 1) / W);      // bound on |pixel-centre NDC| (>= aspect ratio)
   p.item_cap = (flags & MVR_TEST_TINY_QUEUES) ? 24 : ITEM_CAP;
   p.wcap = (flags & MVR_TEST_TINY_QUEUES) ? 5 : WCAP;
   p.pv = (float4*)(wb + w.pv); p.tab = (float*)(wb + w.tab);
@@ -641,10 +663,12 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
       rc = check_launch("mesh_scatter_kernel");
       if (rc) return rc;
     }
-    if (zbuf || bary || dists) MVR_LAUNCH((mesh_shade_kernel<true, 3, 1>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
-    else if (shade_ppt() == 4) launch_shade_fast<4>(p, B, M, H, W, st);
-    else if (shade_ppt() == 2) launch_shade_fast<2>(p, B, M, H, W, st);
-    else launch_shade_fast<1>(p, B, M, H, W, st);
+    const bool vrgb = flags & MVR_RGB_PER_ELEMENT;
+    if (zbuf || bary || dists) MVR_LAUNCH((mesh_shade_kernel<true, 3, 1, true>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+    else if (vrgb) launch_shade_fast<4, true>(p, B, M, H, W, st);
+    else if (shade_ppt() == 4) launch_shade_fast<4, false>(p, B, M, H, W, st);
+    else if (shade_ppt() == 2) launch_shade_fast<2, false>(p, B, M, H, W, st);
+    else launch_shade_fast<1, false>(p, B, M, H, W, st);
     rc = check_launch("mesh_shade_kernel");
     if (rc) return rc;
     if (z_clip >= 0.f) {      // pixels won by a face crossing the near plane (none in MVTN's default configurations: the kernel exits at once)

@@ -11,9 +11,9 @@
 
 namespace mvr {
 
-// UNCOND: the cotangent of every pixel is loaded without waiting for its face id (background pixels included: ~40 % more
-// DRAM reads, one dependent DRAM trip less on every thread's critical path)
-template <int MINB, bool UNCOND>
+// VRGB: per-vertex colours (object_color == "custom"); otherwise ONE object colour: the texel is c * sum(b) and its
+// cotangent one dot product -- six registers and ~13 floating-point instructions less per covered pixel.
+template <int MINB, bool VRGB>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const MeshBwdParams p) {
   const int tid = threadIdx.x;
   // grid: x = 32x32-pixel tiles, y = view m, z = object b; thread (lane, warp) owns pixels (x0+lane, y0+warp+8j)
@@ -25,7 +25,6 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
   const int f0 = p.face_off[b], voff = p.vert_off[b], V = p.vert_off[b + 1] - voff;
   const float4* pvn = p.pv + (size_t)p.M * voff + (size_t)m * V;
   const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
-  const bool per_vertex_rgb = p.flags & MVR_RGB_PER_ELEMENT;
   // issue every load of this thread's pixels first (memory-level parallelism), then do the math
   int fids[BWD_PIX_PER_THREAD];
   float gin[BWD_PIX_PER_THREAD][3];
@@ -37,7 +36,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
 #pragma unroll
   for (int j = 0; j < BWD_PIX_PER_THREAD; ++j) {
     const int pix = (yi0 + 8 * j) * p.W + xi;
-    if (UNCOND ? (xi < p.W && yi0 + 8 * j < p.H) : fids[j] >= 0) {
+    if (fids[j] >= 0) {
       load_grad_rgb(p.grad_images, p.flags & MVR_IMAGES_BF16, (size_t)n * 3 * HW + pix, (size_t)HW, p.onorm, gin[j][0], gin[j][1], gin[j][2]);
     } else {
       gin[j][0] = gin[j][1] = gin[j][2] = 0.f;
@@ -50,7 +49,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
   const ShadeCtx sc = load_shade_ctx(p.light, p.light_stride, p.Cc, n);
   const float xf = xi < p.W ? __ldg(p.tab + xi) : 0.f;
   float4 ucol = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!per_vertex_rgb) ucol = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f);
+  if (!VRGB) ucol = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f);
 #pragma unroll 1
   for (int j = 0; j < BWD_PIX_PER_THREAD; ++j) {
     const int fid = fids[j];
@@ -63,10 +62,12 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
     // mesh_project_kernel: for small faces the barycentrics amplify a 1-ulp change of a vertex by |xy| / area);
     // everything downstream is well conditioned and uses fast reciprocals ----
     const Face fc = gather_face(pvn, fi);
-    float4 X0, X1, X2, N0, N1, N2;
-    gather_xn(p.xn8, voff + fi.x, X0, N0); gather_xn(p.xn8, voff + fi.y, X1, N1); gather_xn(p.xn8, voff + fi.z, X2, N2);
+    // (two 16-byte gathers per vertex here: the 32-byte record of the shade kernel needs 8 aligned registers per load,
+    // which this register-bound kernel pays for in spills -- measured 369 vs 362 us)
+    const float4 X0 = __ldg(p.verts4 + voff + fi.x), X1 = __ldg(p.verts4 + voff + fi.y), X2 = __ldg(p.verts4 + voff + fi.z);
+    const float4 N0 = __ldg(p.normals4 + voff + fi.x), N1 = __ldg(p.normals4 + voff + fi.y), N2 = __ldg(p.normals4 + voff + fi.z);
     float4 c0 = ucol, c1 = ucol, c2 = ucol;
-    if (per_vertex_rgb) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
+    if (VRGB) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
     // (after every load of the pixel has been issued) a face crossing the near plane: mesh_backward_clipped_kernel owns the pixel
     // (the flag -- some vertex lies behind the plane, never in MVTN's default setups -- is re-read per pixel: an L1 hit
     // is cheaper than a register kept live across this loop)
@@ -91,7 +92,9 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
     // ---- Phong backward ----
     const float3 P = interp(bb, X0, X1, X2);
     const float3 Nn = interp(bb, N0, N1, N2);
-    const float3 tex = interp(bb, c0, c1, c2);
+    float3 tex;
+    if (VRGB) tex = interp(bb, c0, c1, c2);
+    else { const float sb = bb[0] + bb[1] + bb[2]; tex = make_float3(ucol.x * sb, ucol.y * sb, ucol.z * sb); }
     const float in = inv_norm_clamped(Nn.x, Nn.y, Nn.z, 1e-6f);
     const float nx = Nn.x * in, ny = Nn.y * in, nz = Nn.z * in;
     const float cosang = fmaf(nx, sc.lx, fmaf(ny, sc.ly, nz * sc.lz));
@@ -119,9 +122,12 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
     normalize_bwd3(vx, vy, vz, 1e-6f, gvhx, gvhy, gvhz, gvx, gvy, gvz);
     acc[12] += gvx; acc[13] += gvy; acc[14] += gvz;   // dC
     // d bary_i = gtex.col_i + gN.n_i + gP.X_i  with gP = -gv
-    float gb0 = fmaf(gtx, c0.x, fmaf(gty, c0.y, gtz * c0.z)) + fmaf(gNx, N0.x, fmaf(gNy, N0.y, gNz * N0.z)) - fmaf(gvx, X0.x, fmaf(gvy, X0.y, gvz * X0.z));
-    float gb1 = fmaf(gtx, c1.x, fmaf(gty, c1.y, gtz * c1.z)) + fmaf(gNx, N1.x, fmaf(gNy, N1.y, gNz * N1.z)) - fmaf(gvx, X1.x, fmaf(gvy, X1.y, gvz * X1.z));
-    float gb2 = fmaf(gtx, c2.x, fmaf(gty, c2.y, gtz * c2.z)) + fmaf(gNx, N2.x, fmaf(gNy, N2.y, gNz * N2.z)) - fmaf(gvx, X2.x, fmaf(gvy, X2.y, gvz * X2.z));
+    const float gc0 = fmaf(gtx, c0.x, fmaf(gty, c0.y, gtz * c0.z));
+    const float gc1 = VRGB ? fmaf(gtx, c1.x, fmaf(gty, c1.y, gtz * c1.z)) : gc0;
+    const float gc2 = VRGB ? fmaf(gtx, c2.x, fmaf(gty, c2.y, gtz * c2.z)) : gc0;
+    float gb0 = gc0 + fmaf(gNx, N0.x, fmaf(gNy, N0.y, gNz * N0.z)) - fmaf(gvx, X0.x, fmaf(gvy, X0.y, gvz * X0.z));
+    float gb1 = gc1 + fmaf(gNx, N1.x, fmaf(gNy, N1.y, gNz * N1.z)) - fmaf(gvx, X1.x, fmaf(gvy, X1.y, gvz * X1.z));
+    float gb2 = gc2 + fmaf(gNx, N2.x, fmaf(gNy, N2.y, gNz * N2.z)) - fmaf(gvx, X2.x, fmaf(gvy, X2.y, gvz * X2.z));
     // ---- [upstream] BarycentricPerspectiveCorrectionBackward ----
     float dz0 = 0.f, dz1 = 0.f, dz2 = 0.f;
     if (persp) {
@@ -199,11 +205,6 @@ static int backward_minb() {
   return v;
 }
 
-static bool backward_uncond() {
-  static const bool v = [] { const char* e = getenv("MVR_BWD_UNCOND"); return e && atoi(e) == 1; }();
-  return v;
-}
-
 extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
                                  int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
                                  const float* T, const float* Cc, const float* light, int light_stride,
@@ -243,9 +244,10 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   p.onorm = make_out_norm(out_mean_std);
   p.z_clip = z_clip; p.wsflags = (int*)(wb + w.flags); p.parts_per_view = w.bwd_parts_per_view;
   const dim3 bgrid((unsigned)w.bwd_ctas_per_view, (unsigned)M, (unsigned)B);
-  if (backward_minb() == 2) MVR_LAUNCH((mesh_backward_kernel<2, false>), bgrid, MVR_THREADS, 0, st, p);
-  else if (backward_minb() == 4) MVR_LAUNCH((mesh_backward_kernel<4, false>), bgrid, MVR_THREADS, 0, st, p);
-  else if (backward_uncond()) MVR_LAUNCH((mesh_backward_kernel<3, true>), bgrid, MVR_THREADS, 0, st, p);
+  const bool vrgb = flags & MVR_RGB_PER_ELEMENT;
+  if (backward_minb() == 2) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<2, true>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<2, false>), bgrid, MVR_THREADS, 0, st, p); }
+  else if (backward_minb() == 4) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<4, true>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<4, false>), bgrid, MVR_THREADS, 0, st, p); }
+  else if (vrgb) MVR_LAUNCH((mesh_backward_kernel<3, true>), bgrid, MVR_THREADS, 0, st, p);
   else MVR_LAUNCH((mesh_backward_kernel<3, false>), bgrid, MVR_THREADS, 0, st, p);
   rc = check_launch("mesh_backward_kernel");
   if (rc) return rc;
