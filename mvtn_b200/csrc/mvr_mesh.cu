@@ -664,8 +664,10 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
       if (rc) return rc;
     }
     const bool vrgb = flags & MVR_RGB_PER_ELEMENT;
-    if (zbuf || bary || dists) MVR_LAUNCH((mesh_shade_kernel<true, 3, 1, true>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
-    else if (vrgb) launch_shade_fast<4, true>(p, B, M, H, W, st);
+    if (zbuf || bary || dists) {
+      if (vrgb) MVR_LAUNCH((mesh_shade_kernel<true, 3, 1, true>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+      else MVR_LAUNCH((mesh_shade_kernel<true, 3, 1, false>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+    } else if (vrgb) launch_shade_fast<4, true>(p, B, M, H, W, st);
     else if (shade_ppt() == 4) launch_shade_fast<4, false>(p, B, M, H, W, st);
     else if (shade_ppt() == 2) launch_shade_fast<2, false>(p, B, M, H, W, st);
     else launch_shade_fast<1, false>(p, B, M, H, W, st);

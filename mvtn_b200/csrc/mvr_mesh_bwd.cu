@@ -7,9 +7,146 @@
 //             d image -> Phong -> barycentrics -> NDC verts -> view verts -> (dR, dT, dC), warp-reduced to one partial
 //             per warp; mesh_backward_finish_kernel (mvr_mesh_clip.cu) sums them in fixed order (deterministic, no
 //             float atomics on the camera gradients).
+#include <cstdint>
+
 #include "mvr_mesh.cuh"
 
 namespace mvr {
+
+// One covered pixel: forward recompute from the projected vertices, then the chain
+// d image -> Phong -> barycentrics -> NDC vertices -> view-space vertices -> acc = (dR 9, dT 3, dC 3).
+template <bool VRGB>
+__device__ __forceinline__ void mesh_backward_pixel(const MeshBwdParams& p, int n, int f0, int voff, const float4* __restrict__ pvn,
+                                                    bool persp, const ShadeCtx& sc, const float4 ucol, int fid, float g0, float g1,
+                                                    float g2, float xf, int yi, float acc[16]) {
+  const int4 fi = __ldg(p.faces4 + f0 + fid);
+  // ---- forward recompute from the projected vertices (exact IEEE projection, done once per view by
+  // mesh_project_kernel: for small faces the barycentrics amplify a 1-ulp change of a vertex by |xy| / area);
+  // everything downstream is well conditioned and uses fast reciprocals ----
+  const Face fc = gather_face(pvn, fi);
+  // (two 16-byte gathers per vertex here: the 32-byte record of the shade kernel needs 8 aligned registers per load,
+  // which this register-bound kernel pays for in spills -- measured 369 vs 362 us)
+  const float4 X0 = __ldg(p.verts4 + voff + fi.x), X1 = __ldg(p.verts4 + voff + fi.y), X2 = __ldg(p.verts4 + voff + fi.z);
+  const float4 N0 = __ldg(p.normals4 + voff + fi.x), N1 = __ldg(p.normals4 + voff + fi.y), N2 = __ldg(p.normals4 + voff + fi.z);
+  float4 c0 = ucol, c1 = ucol, c2 = ucol;
+  if (VRGB) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
+  // (after every load of the pixel has been issued) a face crossing the near plane: mesh_backward_clipped_kernel owns the pixel
+  // (the flag -- some vertex lies behind the plane, never in MVTN's default setups -- is re-read per pixel: an L1 hit
+  // is cheaper than a register kept live across this loop)
+  if (may_clip(p.wsflags) && face_straddles(fc, p.z_clip)) return;
+  const FaceEdges fe = face_edges(fc);
+  const float yf = __ldg(p.tab + p.W + yi);
+  const float e0 = (xf - fc.x1) * fe.A0 - (yf - fc.y1) * fe.B0;
+  const float e1 = (xf - fc.x2) * fe.A1 - (yf - fc.y2) * fe.B1;
+  const float e2 = (xf - fc.x0) * fe.A2 - (yf - fc.y0) * fe.B2;
+  const float inv_area = rcp_fast(fe.area_p);
+  const float w0 = e0 * inv_area, w1 = e1 * inv_area, w2 = e2 * inv_area;
+  float bb[3] = {w0, w1, w2};
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, id = 1.f;
+  bool clamped = false;
+  if (persp) {
+    t0 = w0 * fc.z1 * fc.z2; t1 = w1 * fc.z0 * fc.z2; t2 = w2 * fc.z0 * fc.z1;
+    const float st = t0 + t1 + t2;
+    clamped = st < MVR_K_EPS;
+    id = rcp_fast(fmaxf(st, MVR_K_EPS));
+    bb[0] = t0 * id; bb[1] = t1 * id; bb[2] = t2 * id;
+  }
+  // ---- Phong backward ----
+  const float3 P = interp(bb, X0, X1, X2);
+  const float3 Nn = interp(bb, N0, N1, N2);
+  float3 tex;
+  if (VRGB) tex = interp(bb, c0, c1, c2);
+  else { const float sb = bb[0] + bb[1] + bb[2]; tex = make_float3(ucol.x * sb, ucol.y * sb, ucol.z * sb); }
+  const float in = inv_norm_clamped(Nn.x, Nn.y, Nn.z, 1e-6f);
+  const float nx = Nn.x * in, ny = Nn.y * in, nz = Nn.z * in;
+  const float cosang = fmaf(nx, sc.lx, fmaf(ny, sc.ly, nz * sc.lz));
+  const float diff = fmaxf(cosang, 0.f);
+  const float vx = sc.cx - P.x, vy = sc.cy - P.y, vz = sc.cz - P.z;
+  const float iv = inv_norm_clamped(vx, vy, vz, 1e-6f);
+  const float vhx = vx * iv, vhy = vy * iv, vhz = vz * iv;
+  const float rx = fmaf(2.f * cosang, nx, -sc.lx), ry = fmaf(2.f * cosang, ny, -sc.ly), rz = fmaf(2.f * cosang, nz, -sc.lz);
+  const float dt = fmaf(vhx, rx, fmaf(vhy, ry, vhz * rz));
+  const bool lit = cosang > 0.f;
+  const float alpha = (dt > 0.f && lit) ? dt : 0.f;
+  const float kd = fmaf(MVR_DIFFUSE, diff, MVR_AMBIENT);
+  const float gtx = g0 * kd, gty = g1 * kd, gtz = g2 * kd;
+  const float gdiff = MVR_DIFFUSE * fmaf(g0, tex.x, fmaf(g1, tex.y, g2 * tex.z));
+  const float gs = MVR_SPECULAR * (g0 + g1 + g2);
+  const float a2 = alpha * alpha, a4 = a2 * a2, a8 = a4 * a4, a16 = a8 * a8, a32 = a16 * a16;
+  const float a63 = a32 * a16 * a8 * a4 * a2 * alpha;
+  const float gdt = (dt > 0.f && lit) ? gs * 64.f * a63 : 0.f;
+  const float gvhx = gdt * rx, gvhy = gdt * ry, gvhz = gdt * rz;
+  const float grx = gdt * vhx, gry = gdt * vhy, grz = gdt * vhz;
+  const float gcos = (lit ? gdiff : 0.f) + 2.f * fmaf(grx, nx, fmaf(gry, ny, grz * nz));
+  const float gnx = fmaf(2.f * cosang, grx, gcos * sc.lx), gny = fmaf(2.f * cosang, gry, gcos * sc.ly), gnz = fmaf(2.f * cosang, grz, gcos * sc.lz);
+  float gNx, gNy, gNz, gvx, gvy, gvz;
+  normalize_bwd3(Nn.x, Nn.y, Nn.z, 1e-6f, gnx, gny, gnz, gNx, gNy, gNz);
+  normalize_bwd3(vx, vy, vz, 1e-6f, gvhx, gvhy, gvhz, gvx, gvy, gvz);
+  acc[12] += gvx; acc[13] += gvy; acc[14] += gvz;   // dC
+  // d bary_i = gtex.col_i + gN.n_i + gP.X_i  with gP = -gv
+  const float gc0 = fmaf(gtx, c0.x, fmaf(gty, c0.y, gtz * c0.z));
+  const float gc1 = VRGB ? fmaf(gtx, c1.x, fmaf(gty, c1.y, gtz * c1.z)) : gc0;
+  const float gc2 = VRGB ? fmaf(gtx, c2.x, fmaf(gty, c2.y, gtz * c2.z)) : gc0;
+  float gb0 = gc0 + fmaf(gNx, N0.x, fmaf(gNy, N0.y, gNz * N0.z)) - fmaf(gvx, X0.x, fmaf(gvy, X0.y, gvz * X0.z));
+  float gb1 = gc1 + fmaf(gNx, N1.x, fmaf(gNy, N1.y, gNz * N1.z)) - fmaf(gvx, X1.x, fmaf(gvy, X1.y, gvz * X1.z));
+  float gb2 = gc2 + fmaf(gNx, N2.x, fmaf(gNy, N2.y, gNz * N2.z)) - fmaf(gvx, X2.x, fmaf(gvy, X2.y, gvz * X2.z));
+  // ---- [upstream] BarycentricPerspectiveCorrectionBackward ----
+  float dz0 = 0.f, dz1 = 0.f, dz2 = 0.f;
+  if (persp) {
+    // b = t / sum(t) is invariant to a common shift of d/db (its Jacobian annihilates constants), so
+    // remove k = sum(b_i gb_i) first: the d/d denom term then vanishes identically instead of cancelling
+    // O(1/area) terms in fp32.  Same gradient in exact arithmetic; not valid when denom was clamped.
+    if (!clamped) {
+      const float kk = fmaf(bb[0], gb0, fmaf(bb[1], gb1, bb[2] * gb2));
+      gb0 -= kk; gb1 -= kk; gb2 -= kk;
+    }
+    const float gden = clamped ? -(gb0 * t0 + gb1 * t1 + gb2 * t2) * id * id : 0.f;
+    const float gt0 = fmaf(gb0, id, gden), gt1 = fmaf(gb1, id, gden), gt2 = fmaf(gb2, id, gden);
+    gb0 = gt0 * fc.z1 * fc.z2; gb1 = gt1 * fc.z0 * fc.z2; gb2 = gt2 * fc.z0 * fc.z1;
+    dz0 = gt1 * w1 * fc.z2 + gt2 * w2 * fc.z1;
+    dz1 = gt0 * w0 * fc.z2 + gt2 * w2 * fc.z0;
+    dz2 = gt0 * w0 * fc.z1 + gt1 * w1 * fc.z0;
+  }
+  // ---- [upstream] BarycentricCoordsBackward / EdgeFunctionBackward ----
+  const float ge0 = gb0 * inv_area, ge1 = gb1 * inv_area, ge2 = gb2 * inv_area;
+  const float garea = -(gb0 * e0 + gb1 * e1 + gb2 * e2) * inv_area * inv_area;
+  float gx0, gy0, gx1, gy1, gx2, gy2;
+  // E(p,a,b): dE/da = (py-by, bx-px), dE/db = (ay-py, px-ax)
+  gx1 = ge0 * (yf - fc.y2); gy1 = ge0 * (fc.x2 - xf); gx2 = ge0 * (fc.y1 - yf); gy2 = ge0 * (xf - fc.x1);          // e0 = E(p,v1,v2)
+  gx2 += ge1 * (yf - fc.y0); gy2 += ge1 * (fc.x0 - xf); gx0 = ge1 * (fc.y2 - yf); gy0 = ge1 * (xf - fc.x2);        // e1 = E(p,v2,v0)
+  gx0 += ge2 * (yf - fc.y1); gy0 += ge2 * (fc.x1 - xf); gx1 += ge2 * (fc.y0 - yf); gy1 += ge2 * (xf - fc.x0);      // e2 = E(p,v0,v1)
+  // area = E(v2, v0, v1)
+  gx0 += garea * (fc.y2 - fc.y1); gy0 += garea * (fc.x1 - fc.x2);
+  gx1 += garea * (fc.y0 - fc.y2); gy1 += garea * (fc.x2 - fc.x0);
+  gx2 += garea * (fc.y1 - fc.y0); gy2 += garea * (fc.x0 - fc.x1);
+  // ---- projection backward + X R + T backward: x_ndc = (px k00) / pz, so px k00 = x_ndc pz ----
+  const float gxn[3] = {gx0, gx1, gx2}, gyn[3] = {gy0, gy1, gy2}, gzn[3] = {dz0, dz1, dz2};
+  const float xn[3] = {fc.x0, fc.x1, fc.x2}, yn[3] = {fc.y0, fc.y1, fc.y2}, zv[3] = {fc.z0, fc.z1, fc.z2};
+  const float4 Xs[3] = {X0, X1, X2};
+  const int vid[3] = {fi.x, fi.y, fi.z};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float iz = rcp_fast(zv[i]);
+    const float gpx = gxn[i] * p.k00 * iz;
+    const float gpy = gyn[i] * p.k11 * iz;
+    const float gpz = gzn[i] - (gxn[i] * xn[i] + gyn[i] * yn[i]) * iz;
+    acc[0] = fmaf(Xs[i].x, gpx, acc[0]); acc[1] = fmaf(Xs[i].x, gpy, acc[1]); acc[2] = fmaf(Xs[i].x, gpz, acc[2]);
+    acc[3] = fmaf(Xs[i].y, gpx, acc[3]); acc[4] = fmaf(Xs[i].y, gpy, acc[4]); acc[5] = fmaf(Xs[i].y, gpz, acc[5]);
+    acc[6] = fmaf(Xs[i].z, gpx, acc[6]); acc[7] = fmaf(Xs[i].z, gpy, acc[7]); acc[8] = fmaf(Xs[i].z, gpz, acc[8]);
+    acc[9] += gpx; acc[10] += gpy; acc[11] += gpz;
+    if (p.grad_verts) {
+      const float* r = p.R + 9 * (size_t)n;
+      float* o = p.grad_verts + 3 * (size_t)(voff + vid[i]);
+      atomicAdd(o + 0, fmaf(__ldg(r + 0), gpx, fmaf(__ldg(r + 1), gpy, __ldg(r + 2) * gpz)) - bb[i] * gvx);
+      atomicAdd(o + 1, fmaf(__ldg(r + 3), gpx, fmaf(__ldg(r + 4), gpy, __ldg(r + 5) * gpz)) - bb[i] * gvy);
+      atomicAdd(o + 2, fmaf(__ldg(r + 6), gpx, fmaf(__ldg(r + 7), gpy, __ldg(r + 8) * gpz)) - bb[i] * gvz);
+    }
+    if (p.grad_normals) {
+      float* o = p.grad_normals + 3 * (size_t)(voff + vid[i]);
+      atomicAdd(o + 0, bb[i] * gNx); atomicAdd(o + 1, bb[i] * gNy); atomicAdd(o + 2, bb[i] * gNz);
+    }
+  }
+}
 
 // VRGB: per-vertex colours (object_color == "custom"); otherwise ONE object colour: the texel is c * sum(b) and its
 // cotangent one dot product -- six registers and ~13 floating-point instructions less per covered pixel.
@@ -57,133 +194,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
     if (fid < 0 || (g0 == 0.f && g1 == 0.f && g2 == 0.f)) continue;
     any = true;
     const int yi = yi0 + 8 * j;
-    const int4 fi = __ldg(p.faces4 + f0 + fid);
-    // ---- forward recompute from the projected vertices (exact IEEE projection, done once per view by
-    // mesh_project_kernel: for small faces the barycentrics amplify a 1-ulp change of a vertex by |xy| / area);
-    // everything downstream is well conditioned and uses fast reciprocals ----
-    const Face fc = gather_face(pvn, fi);
-    // (two 16-byte gathers per vertex here: the 32-byte record of the shade kernel needs 8 aligned registers per load,
-    // which this register-bound kernel pays for in spills -- measured 369 vs 362 us)
-    const float4 X0 = __ldg(p.verts4 + voff + fi.x), X1 = __ldg(p.verts4 + voff + fi.y), X2 = __ldg(p.verts4 + voff + fi.z);
-    const float4 N0 = __ldg(p.normals4 + voff + fi.x), N1 = __ldg(p.normals4 + voff + fi.y), N2 = __ldg(p.normals4 + voff + fi.z);
-    float4 c0 = ucol, c1 = ucol, c2 = ucol;
-    if (VRGB) { c0 = __ldg(p.rgb4 + voff + fi.x); c1 = __ldg(p.rgb4 + voff + fi.y); c2 = __ldg(p.rgb4 + voff + fi.z); }
-    // (after every load of the pixel has been issued) a face crossing the near plane: mesh_backward_clipped_kernel owns the pixel
-    // (the flag -- some vertex lies behind the plane, never in MVTN's default setups -- is re-read per pixel: an L1 hit
-    // is cheaper than a register kept live across this loop)
-    if (may_clip(p.wsflags) && face_straddles(fc, p.z_clip)) continue;
-    const FaceEdges fe = face_edges(fc);
-    const float yf = __ldg(p.tab + p.W + yi);
-    const float e0 = (xf - fc.x1) * fe.A0 - (yf - fc.y1) * fe.B0;
-    const float e1 = (xf - fc.x2) * fe.A1 - (yf - fc.y2) * fe.B1;
-    const float e2 = (xf - fc.x0) * fe.A2 - (yf - fc.y0) * fe.B2;
-    const float inv_area = rcp_fast(fe.area_p);
-    const float w0 = e0 * inv_area, w1 = e1 * inv_area, w2 = e2 * inv_area;
-    float bb[3] = {w0, w1, w2};
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f, id = 1.f;
-    bool clamped = false;
-    if (persp) {
-      t0 = w0 * fc.z1 * fc.z2; t1 = w1 * fc.z0 * fc.z2; t2 = w2 * fc.z0 * fc.z1;
-      const float st = t0 + t1 + t2;
-      clamped = st < MVR_K_EPS;
-      id = rcp_fast(fmaxf(st, MVR_K_EPS));
-      bb[0] = t0 * id; bb[1] = t1 * id; bb[2] = t2 * id;
-    }
-    // ---- Phong backward ----
-    const float3 P = interp(bb, X0, X1, X2);
-    const float3 Nn = interp(bb, N0, N1, N2);
-    float3 tex;
-    if (VRGB) tex = interp(bb, c0, c1, c2);
-    else { const float sb = bb[0] + bb[1] + bb[2]; tex = make_float3(ucol.x * sb, ucol.y * sb, ucol.z * sb); }
-    const float in = inv_norm_clamped(Nn.x, Nn.y, Nn.z, 1e-6f);
-    const float nx = Nn.x * in, ny = Nn.y * in, nz = Nn.z * in;
-    const float cosang = fmaf(nx, sc.lx, fmaf(ny, sc.ly, nz * sc.lz));
-    const float diff = fmaxf(cosang, 0.f);
-    const float vx = sc.cx - P.x, vy = sc.cy - P.y, vz = sc.cz - P.z;
-    const float iv = inv_norm_clamped(vx, vy, vz, 1e-6f);
-    const float vhx = vx * iv, vhy = vy * iv, vhz = vz * iv;
-    const float rx = fmaf(2.f * cosang, nx, -sc.lx), ry = fmaf(2.f * cosang, ny, -sc.ly), rz = fmaf(2.f * cosang, nz, -sc.lz);
-    const float dt = fmaf(vhx, rx, fmaf(vhy, ry, vhz * rz));
-    const bool lit = cosang > 0.f;
-    const float alpha = (dt > 0.f && lit) ? dt : 0.f;
-    const float kd = fmaf(MVR_DIFFUSE, diff, MVR_AMBIENT);
-    const float gtx = g0 * kd, gty = g1 * kd, gtz = g2 * kd;
-    const float gdiff = MVR_DIFFUSE * fmaf(g0, tex.x, fmaf(g1, tex.y, g2 * tex.z));
-    const float gs = MVR_SPECULAR * (g0 + g1 + g2);
-    const float a2 = alpha * alpha, a4 = a2 * a2, a8 = a4 * a4, a16 = a8 * a8, a32 = a16 * a16;
-    const float a63 = a32 * a16 * a8 * a4 * a2 * alpha;
-    const float gdt = (dt > 0.f && lit) ? gs * 64.f * a63 : 0.f;
-    const float gvhx = gdt * rx, gvhy = gdt * ry, gvhz = gdt * rz;
-    const float grx = gdt * vhx, gry = gdt * vhy, grz = gdt * vhz;
-    const float gcos = (lit ? gdiff : 0.f) + 2.f * fmaf(grx, nx, fmaf(gry, ny, grz * nz));
-    const float gnx = fmaf(2.f * cosang, grx, gcos * sc.lx), gny = fmaf(2.f * cosang, gry, gcos * sc.ly), gnz = fmaf(2.f * cosang, grz, gcos * sc.lz);
-    float gNx, gNy, gNz, gvx, gvy, gvz;
-    normalize_bwd3(Nn.x, Nn.y, Nn.z, 1e-6f, gnx, gny, gnz, gNx, gNy, gNz);
-    normalize_bwd3(vx, vy, vz, 1e-6f, gvhx, gvhy, gvhz, gvx, gvy, gvz);
-    acc[12] += gvx; acc[13] += gvy; acc[14] += gvz;   // dC
-    // d bary_i = gtex.col_i + gN.n_i + gP.X_i  with gP = -gv
-    const float gc0 = fmaf(gtx, c0.x, fmaf(gty, c0.y, gtz * c0.z));
-    const float gc1 = VRGB ? fmaf(gtx, c1.x, fmaf(gty, c1.y, gtz * c1.z)) : gc0;
-    const float gc2 = VRGB ? fmaf(gtx, c2.x, fmaf(gty, c2.y, gtz * c2.z)) : gc0;
-    float gb0 = gc0 + fmaf(gNx, N0.x, fmaf(gNy, N0.y, gNz * N0.z)) - fmaf(gvx, X0.x, fmaf(gvy, X0.y, gvz * X0.z));
-    float gb1 = gc1 + fmaf(gNx, N1.x, fmaf(gNy, N1.y, gNz * N1.z)) - fmaf(gvx, X1.x, fmaf(gvy, X1.y, gvz * X1.z));
-    float gb2 = gc2 + fmaf(gNx, N2.x, fmaf(gNy, N2.y, gNz * N2.z)) - fmaf(gvx, X2.x, fmaf(gvy, X2.y, gvz * X2.z));
-    // ---- [upstream] BarycentricPerspectiveCorrectionBackward ----
-    float dz0 = 0.f, dz1 = 0.f, dz2 = 0.f;
-    if (persp) {
-      // b = t / sum(t) is invariant to a common shift of d/db (its Jacobian annihilates constants), so
-      // remove k = sum(b_i gb_i) first: the d/d denom term then vanishes identically instead of cancelling
-      // O(1/area) terms in fp32.  Same gradient in exact arithmetic; not valid when denom was clamped.
-      if (!clamped) {
-        const float kk = fmaf(bb[0], gb0, fmaf(bb[1], gb1, bb[2] * gb2));
-        gb0 -= kk; gb1 -= kk; gb2 -= kk;
-      }
-      const float gden = clamped ? -(gb0 * t0 + gb1 * t1 + gb2 * t2) * id * id : 0.f;
-      const float gt0 = fmaf(gb0, id, gden), gt1 = fmaf(gb1, id, gden), gt2 = fmaf(gb2, id, gden);
-      gb0 = gt0 * fc.z1 * fc.z2; gb1 = gt1 * fc.z0 * fc.z2; gb2 = gt2 * fc.z0 * fc.z1;
-      dz0 = gt1 * w1 * fc.z2 + gt2 * w2 * fc.z1;
-      dz1 = gt0 * w0 * fc.z2 + gt2 * w2 * fc.z0;
-      dz2 = gt0 * w0 * fc.z1 + gt1 * w1 * fc.z0;
-    }
-    // ---- [upstream] BarycentricCoordsBackward / EdgeFunctionBackward ----
-    const float ge0 = gb0 * inv_area, ge1 = gb1 * inv_area, ge2 = gb2 * inv_area;
-    const float garea = -(gb0 * e0 + gb1 * e1 + gb2 * e2) * inv_area * inv_area;
-    float gx0, gy0, gx1, gy1, gx2, gy2;
-    // E(p,a,b): dE/da = (py-by, bx-px), dE/db = (ay-py, px-ax)
-    gx1 = ge0 * (yf - fc.y2); gy1 = ge0 * (fc.x2 - xf); gx2 = ge0 * (fc.y1 - yf); gy2 = ge0 * (xf - fc.x1);          // e0 = E(p,v1,v2)
-    gx2 += ge1 * (yf - fc.y0); gy2 += ge1 * (fc.x0 - xf); gx0 = ge1 * (fc.y2 - yf); gy0 = ge1 * (xf - fc.x2);        // e1 = E(p,v2,v0)
-    gx0 += ge2 * (yf - fc.y1); gy0 += ge2 * (fc.x1 - xf); gx1 += ge2 * (fc.y0 - yf); gy1 += ge2 * (xf - fc.x0);      // e2 = E(p,v0,v1)
-    // area = E(v2, v0, v1)
-    gx0 += garea * (fc.y2 - fc.y1); gy0 += garea * (fc.x1 - fc.x2);
-    gx1 += garea * (fc.y0 - fc.y2); gy1 += garea * (fc.x2 - fc.x0);
-    gx2 += garea * (fc.y1 - fc.y0); gy2 += garea * (fc.x0 - fc.x1);
-    // ---- projection backward + X R + T backward: x_ndc = (px k00) / pz, so px k00 = x_ndc pz ----
-    const float gxn[3] = {gx0, gx1, gx2}, gyn[3] = {gy0, gy1, gy2}, gzn[3] = {dz0, dz1, dz2};
-    const float xn[3] = {fc.x0, fc.x1, fc.x2}, yn[3] = {fc.y0, fc.y1, fc.y2}, zv[3] = {fc.z0, fc.z1, fc.z2};
-    const float4 Xs[3] = {X0, X1, X2};
-    const int vid[3] = {fi.x, fi.y, fi.z};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const float iz = rcp_fast(zv[i]);
-      const float gpx = gxn[i] * p.k00 * iz;
-      const float gpy = gyn[i] * p.k11 * iz;
-      const float gpz = gzn[i] - (gxn[i] * xn[i] + gyn[i] * yn[i]) * iz;
-      acc[0] = fmaf(Xs[i].x, gpx, acc[0]); acc[1] = fmaf(Xs[i].x, gpy, acc[1]); acc[2] = fmaf(Xs[i].x, gpz, acc[2]);
-      acc[3] = fmaf(Xs[i].y, gpx, acc[3]); acc[4] = fmaf(Xs[i].y, gpy, acc[4]); acc[5] = fmaf(Xs[i].y, gpz, acc[5]);
-      acc[6] = fmaf(Xs[i].z, gpx, acc[6]); acc[7] = fmaf(Xs[i].z, gpy, acc[7]); acc[8] = fmaf(Xs[i].z, gpz, acc[8]);
-      acc[9] += gpx; acc[10] += gpy; acc[11] += gpz;
-      if (p.grad_verts) {
-        const float* r = p.R + 9 * (size_t)n;
-        float* o = p.grad_verts + 3 * (size_t)(voff + vid[i]);
-        atomicAdd(o + 0, fmaf(__ldg(r + 0), gpx, fmaf(__ldg(r + 1), gpy, __ldg(r + 2) * gpz)) - bb[i] * gvx);
-        atomicAdd(o + 1, fmaf(__ldg(r + 3), gpx, fmaf(__ldg(r + 4), gpy, __ldg(r + 5) * gpz)) - bb[i] * gvy);
-        atomicAdd(o + 2, fmaf(__ldg(r + 6), gpx, fmaf(__ldg(r + 7), gpy, __ldg(r + 8) * gpz)) - bb[i] * gvz);
-      }
-      if (p.grad_normals) {
-        float* o = p.grad_normals + 3 * (size_t)(voff + vid[i]);
-        atomicAdd(o + 0, bb[i] * gNx); atomicAdd(o + 1, bb[i] * gNy); atomicAdd(o + 2, bb[i] * gNz);
-      }
-    }
+    mesh_backward_pixel<VRGB>(p, n, f0, voff, pvn, persp, sc, ucol, fid, g0, g1, g2, xf, yi, acc);
   }
   // one partial per WARP, no block barrier: a warp retires as soon as its own pixels are done
   float* out = p.partials + ((size_t)n * p.parts_per_view + (size_t)cta * NWARPS + (tid >> 5)) * 16;
@@ -196,12 +207,102 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
   if (!(lane & 1)) out[lane >> 1] = mine;
 }
 
+// ---- strip variant: one CTA walks a ROW of 32x32-pixel tiles with a two-stage cp.async pipeline ----
+// The face ids and the cotangent of tile t + 1 (16 KB) travel to shared memory while tile t is being processed, so the
+// two dependent DRAM trips every thread of mesh_backward_kernel starts with (pix_to_face, then the cotangent of its
+// covered pixels) leave the critical path, the per-thread staging arrays (local memory) disappear, and a warp reduces
+// and writes ONE partial per strip instead of one per tile.  Requirements (else mesh_backward_kernel runs):
+// K == 1, fp32 cotangent, W % 4 == 0 (16-byte chunks never straddle the image edge).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned int a = (unsigned int)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MINB, bool VRGB>
+__global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(const MeshBwdParams p) {
+  __shared__ __align__(16) int s_fid[2][32 * 32];
+  __shared__ __align__(16) float s_g[2][3][32 * 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // grid: x = tile row, y = view m, z = object b
+  const int b = blockIdx.z, m = blockIdx.y, n = b * p.M + m, tyb = blockIdx.x;
+  const int HW = p.H * p.W;
+  const int f0 = p.face_off[b], voff = p.vert_off[b], V = p.vert_off[b + 1] - voff;
+  const float4* pvn = p.pv + (size_t)p.M * voff + (size_t)m * V;
+  const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
+  const int* fid_base = p.pix_to_face + (size_t)n * HW;
+  const float* g_base = reinterpret_cast<const float*>(p.grad_images) + (size_t)n * 3 * HW;
+  // this thread's 16-byte chunk of every plane of a tile: row cr, pixels cc .. cc + 3
+  const int cr = tid >> 3, cc = (tid & 7) * 4;
+  const int cy = tyb * 32 + cr;
+  auto issue = [&](int txb, int buf) {
+    const int x0 = txb * 32 + cc;
+    int* df = &s_fid[buf][cr * 32 + cc];
+    if (cy < p.H && x0 < p.W) {
+      const size_t pix = (size_t)cy * p.W + x0;
+      cp_async16(df, fid_base + pix);
+      cp_async16(&s_g[buf][0][cr * 32 + cc], g_base + pix);
+      cp_async16(&s_g[buf][1][cr * 32 + cc], g_base + (size_t)HW + pix);
+      cp_async16(&s_g[buf][2][cr * 32 + cc], g_base + 2 * (size_t)HW + pix);
+    } else {
+      *reinterpret_cast<int4*>(df) = make_int4(-1, -1, -1, -1);      // outside the image: background
+    }
+    cp_async_commit();
+  };
+  issue(0, 0);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  bool any = false;
+  const ShadeCtx sc = load_shade_ctx(p.light, p.light_stride, p.Cc, n);
+  float4 ucol = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!VRGB) ucol = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f);
+  const int yi0 = tyb * 32 + warp;
+#pragma unroll 1
+  for (int t = 0; t < p.tiles_x; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < p.tiles_x) { issue(t + 1, buf ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();                                   // tile t has landed for every thread
+    const int xi = t * 32 + lane;
+    const float xf = xi < p.W ? __ldg(p.tab + xi) : 0.f;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int o = (warp + 8 * j) * 32 + lane;
+      const int fid = s_fid[buf][o];
+      if (fid < 0) continue;
+      float g0 = s_g[buf][0][o], g1 = s_g[buf][1][o], g2 = s_g[buf][2][o];
+      if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
+      if (p.onorm.on) { g0 *= p.onorm.s0; g1 *= p.onorm.s1; g2 *= p.onorm.s2; }
+      any = true;
+      mesh_backward_pixel<VRGB>(p, n, f0, voff, pvn, persp, sc, ucol, fid, g0, g1, g2, xf, yi0 + 8 * j, acc);
+    }
+    __syncthreads();                                   // everyone is done with `buf` before tile t + 2 overwrites it
+  }
+  float* out = p.partials + ((size_t)n * p.parts_per_view + (size_t)tyb * NWARPS + warp) * 16;
+  if (!__any_sync(0xffffffffu, any)) {
+    if (lane < 16) out[lane] = 0.f;
+    return;
+  }
+  const float mine = warp_sum16_transposed(acc);
+  if (!(lane & 1)) out[lane >> 1] = mine;
+}
+
+
 }  // namespace mvr
 
 using namespace mvr;
 
 static int backward_minb() {
   static const int v = [] { const char* e = getenv("MVR_BWD_MINB"); const int x = e ? atoi(e) : 3; return (x == 2 || x == 4) ? x : 3; }();
+  return v;
+}
+
+// profiling knob: MVR_BWD_STRIP=0 falls back to the tile-per-CTA kernel everywhere
+static bool backward_strip() {
+  static const bool v = [] { const char* e = getenv("MVR_BWD_STRIP"); return !(e && atoi(e) == 0); }();
   return v;
 }
 
@@ -245,7 +346,15 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   p.z_clip = z_clip; p.wsflags = (int*)(wb + w.flags); p.parts_per_view = w.bwd_parts_per_view;
   const dim3 bgrid((unsigned)w.bwd_ctas_per_view, (unsigned)M, (unsigned)B);
   const bool vrgb = flags & MVR_RGB_PER_ELEMENT;
-  if (backward_minb() == 2) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<2, true>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<2, false>), bgrid, MVR_THREADS, 0, st, p); }
+  const bool strip = backward_strip() && K == 1 && !(flags & MVR_IMAGES_BF16) && W % 4 == 0 &&
+                     ((uintptr_t)pix_to_face % 16 == 0) && ((uintptr_t)grad_images % 16 == 0);
+  if (strip) {
+    p.parts_per_view = ((H + 31) / 32) * NWARPS;      // one partial per warp of every tile ROW
+    const dim3 sgrid((unsigned)((H + 31) / 32), (unsigned)M, (unsigned)B);
+    if (vrgb) MVR_LAUNCH((mesh_backward_kernel_strip<3, true>), sgrid, MVR_THREADS, 0, st, p);
+    else MVR_LAUNCH((mesh_backward_kernel_strip<3, false>), sgrid, MVR_THREADS, 0, st, p);
+  }
+  else if (backward_minb() == 2) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<2, true>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<2, false>), bgrid, MVR_THREADS, 0, st, p); }
   else if (backward_minb() == 4) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<4, true>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<4, false>), bgrid, MVR_THREADS, 0, st, p); }
   else if (vrgb) MVR_LAUNCH((mesh_backward_kernel<3, true>), bgrid, MVR_THREADS, 0, st, p);
   else MVR_LAUNCH((mesh_backward_kernel<3, false>), bgrid, MVR_THREADS, 0, st, p);

@@ -125,13 +125,15 @@ def mesh_case(name):
         return dict(meshes=synth.make_meshes(1, 3000, 10), M=2, H=100, K=2, views=(v[0], v[1], v[2] * 0 + 1.25))
     if name == "c2_slice":
         return dict(meshes=synth.make_meshes(1, 10000, 12), M=2, H=224, K=1, views=synth.circular_views(1, 2))
+    if name == "odd_width_k1":      # W % 4 != 0: the tile-per-CTA backward instead of the cp.async strip kernel; 97 px: partial tiles
+        return dict(meshes=synth.make_meshes(2, 900, 14), M=3, H=97, K=1, views=synth.learned_spherical_views(2, 3, 11))
     if name == "dense_subpixel":
         return dict(meshes=synth.make_meshes(1, 20000, 13), M=2, H=64, K=1, views=synth.learned_spherical_views(1, 2, 8))
     raise KeyError(name)
 
 
 MESH_CASES = ["small", "spherical", "ragged_k3", "cube_big_faces", "cull_noperspective", "vertex_rgb", "relative_light",
-              "close_camera_400", "c2_slice", "dense_subpixel"]
+              "close_camera_400", "c2_slice", "dense_subpixel", "odd_width_k1"]
 
 
 def run_mesh(oracle, dev, cfg, backward=True, extra_flags=0):
