@@ -43,6 +43,9 @@ extern "C" {
 #define MVR_WS_REARM_KEYS 256      /* mvr_mesh_forward: the shade pass writes EMPTY back over every key it consumed */
 #define MVR_WS_PROJECTED 512       /* mvr_mesh_backward: projected vertices / pixel table / clip flag in the workspace are
                                       those of the matching mvr_mesh_forward (same geometry, R, T): skip the re-projection */
+#define MVR_IDX_SPARSE 1024        /* mvr_points_forward (K in {1,2,4,8}, hit_mask given, no zbuf / dists2 wanted): idx is written
+                                      only where the pixel's hit_mask bit is set -- 4 K bytes per background pixel (~90 % of a
+                                      point image) are not stored; mvr_points_backward never reads them */
 #define MVR_TEST_TINY_QUEUES 0x40000000 /* tests only: shrink the scatter kernel's work queues to force their fallbacks */
 
 /* Phong constants of DirectionalLights() / Materials() as constructed at renderer.py:190-191 */

@@ -16,6 +16,7 @@ SCALE_IS_DIST = 64
 WS_KEYS_ARMED = 128    # workspace reuse hints of the mesh path (include/mvr_b200.h)
 WS_REARM_KEYS = 256
 WS_PROJECTED = 512
+IDX_SPARSE = 1024
 TEST_TINY_QUEUES = 0x40000000   # tests only: shrink the scatter kernel's work queues to force their fallbacks
 CNT_STRADDLE, CNT_BIG_FACES, NUM_COUNTERS = 0, 1, 4
 

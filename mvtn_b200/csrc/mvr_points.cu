@@ -442,6 +442,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_tile_kernel(const PointsPa
     float* d2_v = p.dists2 ? p.dists2 + (size_t)n * HW * KT : nullptr;
     unsigned int* mask_v = p.hit_mask ? p.hit_mask + (size_t)n * p.H * p.mask_words + tx : nullptr;
     const bool bf16 = p.flags & MVR_IMAGES_BF16;
+    const bool sparse_idx = (p.flags & MVR_IDX_SPARSE) && mask_v;
     float* img_f = reinterpret_cast<float*>(p.images) + (size_t)n * 3 * HW;
     __nv_bfloat16* img_h = reinterpret_cast<__nv_bfloat16*>(p.images) + (size_t)n * 3 * HW;
     float g0 = __ldg(p.bg_rgb), g1 = __ldg(p.bg_rgb + 1), g2 = __ldg(p.bg_rgb + 2);
@@ -463,7 +464,9 @@ __global__ void __launch_bounds__(MVR_THREADS) points_tile_kernel(const PointsPa
       }
       if (inside && !hit) {                              // background pixel: empty fragment slots + background colour
         const int pix = yi * p.W + xi;
-        if (KT == 4) {
+        if (sparse_idx) {
+          // MVR_IDX_SPARSE: the hit mask already says "empty"; 4 K bytes per background pixel (~90 % of the image) stay unwritten
+        } else if (KT == 4) {
           *reinterpret_cast<int4*>(idx_v + 4 * pix) = make_int4(-1, -1, -1, -1);
         } else if (KT == 2) {
           *reinterpret_cast<int2*>(idx_v + 2 * pix) = make_int2(-1, -1);

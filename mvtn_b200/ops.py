@@ -805,17 +805,20 @@ class _PointsRender(torch.autograd.Function):
         ws = workspace(dev, lib.mvr_points_workspace_bytes(B, Np, M, H, W, K, float(radius)))
         # one bit per pixel: the backward pass skips the (typically ~90 %) background without touching idx
         mask = torch.empty(max(lib.mvr_points_hit_mask_words(B, M, H, W), 1), dtype=torch.int32, device=dev)
+        if not want_fragments:
+            flags |= L.IDX_SPARSE      # idx stays unwritten where the hit mask says "background" (see _PointFragments)
         with _on(dev):
             L.check(lib.mvr_points_forward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), float(radius),
                                            _ptr(bg_rgb), H, W, K, flags, out_norm, _ptr(images), _ptr(idx), _ptr(zbuf), _ptr(d2),
                                            _ptr(mask), _ptr(ws), ws.numel(), _stream(dev)), "mvr_points_forward")
         ctx.set_materialize_grads(False)
+        flags &= ~L.IDX_SPARSE
         ctx.cfg = (B, Np, M, float(radius), H, W, K, flags, out_norm)
         ctx.rgb_shape = rgb.shape
         ctx.points_shape = points.shape
         ctx.scale_shape = scale_shape
         ctx.save_for_backward(R, T, inv_dist, pts, rgb, idx, mask)
-        extras = [idx] + ([zbuf, d2] if want_fragments else [])
+        extras = [idx] + ([zbuf, d2] if want_fragments else [mask])
         ctx.mark_non_differentiable(*extras)
         return (images, *extras)
 
@@ -866,7 +869,44 @@ def render_points(points, rgb, M: int, R, T, inv_dist, radius: float, bg_rgb, im
     H, W = _hw(image_size)
     out = _PointsRender.apply(R, T, inv_dist, points, rgb, M, radius, bg_rgb, H, W,
                               int(points_per_pixel), flags, bool(fragments), _out_norm(normalize), out_dtype)
-    frag = {"idx": out[1]}
     if fragments:
-        frag.update(zbuf=out[2], dists=out[3])
+        frag = {"idx": out[1], "zbuf": out[2], "dists": out[3]}
+    else:
+        frag = _PointFragments(out[1], out[2], H, W)
     return out[0], frag
+
+
+class _PointFragments(dict):
+    """{"idx": (N,H,W,K) int32} of a render that did not ask for fragments.  The kernels then skip the `-1` stores of the
+    background pixels (MVR_IDX_SPARSE: 277 of the 308 MB of idx at C3) -- the backward pass goes by the 1-bit hit mask --
+    so the dense tensor the caller may still look at is completed here, on first access, outside the hot path."""
+
+    def __init__(self, idx, mask, H, W):
+        super().__init__(idx=None)
+        self._raw = (idx, mask, H, W)
+
+    def _dense(self):
+        if self._raw is not None:
+            idx, mask, H, W = self._raw
+            N, mw = idx.shape[0], (W + 31) // 32
+            words = mask[: N * H * mw].view(N, H, mw, 1)
+            bits = (words >> torch.arange(32, device=idx.device, dtype=torch.int32)) & 1
+            hit = bits.view(N, H, mw * 32)[:, :, :W].bool()
+            dict.__setitem__(self, "idx", idx.masked_fill(~hit.unsqueeze(-1), -1))
+            self._raw = None
+
+    def __getitem__(self, k):
+        self._dense()
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        self._dense()
+        return dict.get(self, k, default)
+
+    def items(self):
+        self._dense()
+        return dict.items(self)
+
+    def values(self):
+        self._dense()
+        return dict.values(self)
