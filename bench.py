@@ -204,13 +204,13 @@ def run_ours(a):
             img = graphed(az, el, di)
             img.backward(cot)
             return az.grad, el.grad, di.grad
-        R, T, C, _bad = ops._LookAt.apply(az.reshape(-1), el.reshape(-1), di.reshape(-1))
         if a.workload == "mesh":
+            R, T, C, _bad = ops._LookAt.apply(az.reshape(-1), el.reshape(-1), di.reshape(-1))
             geom = ops.PackedMeshes.from_packed(verts_d, faces_d, nv, nf)
             img, _ = ops.render_meshes(geom, M, R, T, C, light, obj, bg, S)
         else:
-            img, _ = ops.render_points(pts_d, obj, M, R, T, None, renderer.points_radius, bg_black, S,
-                                       points_per_pixel=a.points_per_pixel, compositor="alpha", dist=di)
+            img, _cams, _ = ops.render_points_from_angles(pts_d, obj, M, az, el, di, renderer.points_radius, bg_black, S,
+                                                          points_per_pixel=a.points_per_pixel, compositor="alpha")
         img.backward(cot)
         return az.grad, el.grad, di.grad
 

@@ -772,83 +772,150 @@ def render_meshes(geom: PackedMeshes, M: int, R, T, Cc, light, obj_rgb, bg_rgb, 
 # --------------------------------------------------------------------------------------------------
 # point rendering
 # --------------------------------------------------------------------------------------------------
+def _points_forward_launch(R, T, inv_dist, points, rgb, M, radius, bg_rgb, H, W, K, flags, want_fragments, out_norm, out_dtype):
+    """Argument normalisation, output allocation and ONE mvr_points_forward call.
+    Returns (cfg, saved, images, extras): cfg / saved are what the matching backward launch needs."""
+    lib = L.load()
+    _require_cuda(points, "points")
+    dev = points.device
+    pts = _f32c(points)
+    if pts.dim() != 3 or pts.shape[2] != 3:
+        raise ValueError("points must be (B,N,3)")
+    B, Np, _ = pts.shape
+    N = B * M
+    R, T, inv_dist = _f32c(R), _f32c(T), _f32c(inv_dist).reshape(-1)
+    if R.shape[0] != N or inv_dist.numel() != N:
+        raise ValueError(f"expected {N} cameras (B*M)")
+    rgb = _f32c(rgb.to(dev))
+    if rgb.numel() != 3:
+        if rgb.numel() != pts.numel():
+            raise ValueError("rgb must be a 3-vector or one colour per point (B,N,3)")
+        flags |= L.RGB_PER_ELEMENT
+    bg_rgb = _f32c(bg_rgb)
+    img_dtype, dt_flag = _image_dtype(out_dtype)
+    flags |= dt_flag
+    images = torch.empty((N, 3, H, W), dtype=img_dtype, device=dev)
+    idx = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
+    zbuf = d2 = None
+    if want_fragments:
+        zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        d2 = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+    ws = workspace(dev, lib.mvr_points_workspace_bytes(B, Np, M, H, W, K, float(radius)))
+    # one bit per pixel: the backward pass skips the (typically ~90 %) background without touching idx
+    mask = torch.empty(max(lib.mvr_points_hit_mask_words(B, M, H, W), 1), dtype=torch.int32, device=dev)
+    call_flags = flags if want_fragments else flags | L.IDX_SPARSE      # idx unwritten where the mask says "background" (_PointFragments)
+    with _on(dev):
+        L.check(lib.mvr_points_forward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), float(radius),
+                                       _ptr(bg_rgb), H, W, K, call_flags, out_norm, _ptr(images), _ptr(idx), _ptr(zbuf), _ptr(d2),
+                                       _ptr(mask), _ptr(ws), ws.numel(), _stream(dev)), "mvr_points_forward")
+    cfg = (B, Np, M, float(radius), H, W, K, flags, out_norm, rgb.shape, points.shape)
+    saved = (R, T, inv_dist, pts, rgb, idx, mask)
+    extras = [idx] + ([zbuf, d2] if want_fragments else [mask])
+    return cfg, saved, images, extras
+
+
+def _points_backward_launch(cfg, saved, g_images, want_points, want_rgb):
+    """ONE mvr_points_backward call -> (gR, gT, g_scale (flat), g_points | None, g_rgb | None)."""
+    lib = L.load()
+    R, T, inv_dist, pts, rgb, idx, mask = saved
+    B, Np, M, radius, H, W, K, flags, out_norm, rgb_shape, points_shape = cfg
+    dev = pts.device
+    N = B * M
+    g_images = _grad_like_images(g_images, flags)
+    g = torch.empty(13 * N, dtype=torch.float32, device=dev)      # one allocation: gR | gT | g_scale
+    gR, gT, gs = g[: 9 * N].view(N, 3, 3), g[9 * N: 12 * N].view(N, 3), g[12 * N:]
+    gP = torch.zeros_like(pts) if want_points else None
+    gF = torch.zeros_like(rgb) if want_rgb else None
+    ws_bytes = lib.mvr_points_workspace_bytes(B, Np, M, H, W, K, float(radius))
+    ws = workspace(dev, ws_bytes)
+    with _on(dev):
+        L.check(lib.mvr_points_backward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), radius, H,
+                                        W, K, flags, out_norm, _ptr(idx), _ptr(mask), _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gs),
+                                        _ptr(gP), _ptr(gF), _ptr(ws), ws.numel(), _stream(dev)),
+                "mvr_points_backward")
+    if gP is not None:
+        gP = gP.reshape(points_shape)
+    if gF is not None:
+        gF = gF.reshape(rgb_shape)
+    return gR, gT, gs, gP, gF
+
+
 class _PointsRender(torch.autograd.Function):
     @staticmethod
     def forward(ctx, R, T, inv_dist, points, rgb, M, radius, bg_rgb, H, W, K, flags, want_fragments, out_norm=None,
                 out_dtype=None):
-        lib = L.load()
-        _require_cuda(points, "points")
-        dev = points.device
-        pts = _f32c(points)
-        if pts.dim() != 3 or pts.shape[2] != 3:
-            raise ValueError("points must be (B,N,3)")
-        B, Np, _ = pts.shape
-        N = B * M
-        scale_shape = inv_dist.shape
-        R, T, inv_dist = _f32c(R), _f32c(T), _f32c(inv_dist).reshape(-1)
-        if R.shape[0] != N or inv_dist.numel() != N:
-            raise ValueError(f"expected {N} cameras (B*M)")
-        rgb = _f32c(rgb.to(dev))
-        if rgb.numel() != 3:
-            if rgb.numel() != pts.numel():
-                raise ValueError("rgb must be a 3-vector or one colour per point (B,N,3)")
-            flags |= L.RGB_PER_ELEMENT
-        bg_rgb = _f32c(bg_rgb)
-        img_dtype, dt_flag = _image_dtype(out_dtype)
-        flags |= dt_flag
-        images = torch.empty((N, 3, H, W), dtype=img_dtype, device=dev)
-        idx = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
-        zbuf = d2 = None
-        if want_fragments:
-            zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
-            d2 = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
-        ws = workspace(dev, lib.mvr_points_workspace_bytes(B, Np, M, H, W, K, float(radius)))
-        # one bit per pixel: the backward pass skips the (typically ~90 %) background without touching idx
-        mask = torch.empty(max(lib.mvr_points_hit_mask_words(B, M, H, W), 1), dtype=torch.int32, device=dev)
-        if not want_fragments:
-            flags |= L.IDX_SPARSE      # idx stays unwritten where the hit mask says "background" (see _PointFragments)
-        with _on(dev):
-            L.check(lib.mvr_points_forward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), float(radius),
-                                           _ptr(bg_rgb), H, W, K, flags, out_norm, _ptr(images), _ptr(idx), _ptr(zbuf), _ptr(d2),
-                                           _ptr(mask), _ptr(ws), ws.numel(), _stream(dev)), "mvr_points_forward")
+        cfg, saved, images, extras = _points_forward_launch(R, T, inv_dist, points, rgb, M, radius, bg_rgb, H, W, K, flags,
+                                                            want_fragments, out_norm, out_dtype)
         ctx.set_materialize_grads(False)
-        flags &= ~L.IDX_SPARSE
-        ctx.cfg = (B, Np, M, float(radius), H, W, K, flags, out_norm)
-        ctx.rgb_shape = rgb.shape
-        ctx.points_shape = points.shape
-        ctx.scale_shape = scale_shape
-        ctx.save_for_backward(R, T, inv_dist, pts, rgb, idx, mask)
-        extras = [idx] + ([zbuf, d2] if want_fragments else [mask])
+        ctx.cfg = cfg
+        ctx.scale_shape = inv_dist.shape
+        ctx.save_for_backward(*saved)
         ctx.mark_non_differentiable(*extras)
         return (images, *extras)
 
     @staticmethod
     def backward(ctx, g_images, *_unused):
-        lib = L.load()
         if g_images is None:
             return (None,) * 15
-        R, T, inv_dist, pts, rgb, idx, mask = ctx.saved_tensors
-        B, Np, M, radius, H, W, K, flags, out_norm = ctx.cfg
-        dev = pts.device
-        N = B * M
-        g_images = _grad_like_images(g_images, flags)
-        gR = torch.empty((N, 3, 3), dtype=torch.float32, device=dev)
-        gT = torch.empty((N, 3), dtype=torch.float32, device=dev)
-        gs = torch.empty(N, dtype=torch.float32, device=dev)
-        gP = torch.zeros_like(pts) if ctx.needs_input_grad[3] else None
-        gF = torch.zeros_like(rgb) if ctx.needs_input_grad[4] else None
-        ws_bytes = lib.mvr_points_workspace_bytes(B, Np, M, H, W, K, float(radius))
-        ws = workspace(dev, ws_bytes)
-        with _on(dev):
-            L.check(lib.mvr_points_backward(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(inv_dist), radius, H,
-                                            W, K, flags, out_norm, _ptr(idx), _ptr(mask), _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gs),
-                                            _ptr(gP), _ptr(gF), _ptr(ws), ws.numel(), _stream(dev)),
-                    "mvr_points_backward")
-        if gP is not None:
-            gP = gP.reshape(ctx.points_shape)
-        if gF is not None:
-            gF = gF.reshape(ctx.rgb_shape)
+        gR, gT, gs, gP, gF = _points_backward_launch(ctx.cfg, ctx.saved_tensors, g_images, ctx.needs_input_grad[3],
+                                                     ctx.needs_input_grad[4])
         return (gR, gT, gs.reshape(ctx.scale_shape), gP, gF) + (None,) * 10
+
+
+class _PointsRenderFromAngles(torch.autograd.Function):
+    """look_at + point render as ONE autograd node: (azim, elev, dist, points, rgb) -> images (+ R, T, C, flag, idx, mask).
+    The clouds are scaled by 1 / dist inside the kernels (MVR_SCALE_IS_DIST), so `dist` reaches the images twice -- through
+    the cameras and through the scale -- and its two gradients are summed here instead of by an AccumulateGrad node.
+    The point path at MVTN's sizes is launch- and host-bound: one Function.apply and one backward
+    node less per step is measurable.  after_cameras: as in _MeshRenderFromAngles."""
+
+    @staticmethod
+    def forward(ctx, azim, elev, dist, points, rgb, M, radius, bg_rgb, H, W, K, flags, out_norm, out_dtype, after_cameras):
+        a, e, d, R, T, Cc, bad = _look_at_launch(azim, elev, dist)
+        if after_cameras is not None:
+            after_cameras(bad)
+        cfg, saved, images, extras = _points_forward_launch(R, T, d, points, rgb, M, radius, bg_rgb, H, W, K,
+                                                            flags | L.SCALE_IS_DIST, False, out_norm, out_dtype)
+        ctx.set_materialize_grads(False)
+        ctx.cfg = cfg
+        ctx.shapes = (azim.shape, elev.shape, dist.shape)
+        ctx.save_for_backward(a, e, *saved)
+        ctx.mark_non_differentiable(bad, *extras)
+        return (images, R, T, Cc, bad, *extras)
+
+    @staticmethod
+    def backward(ctx, g_images, gR_ext, gT_ext, gC_ext, *_unused):
+        if g_images is None and gR_ext is None and gT_ext is None and gC_ext is None:
+            return (None,) * 15
+        a, e = ctx.saved_tensors[:2]
+        saved = ctx.saved_tensors[2:]
+        d = saved[2]
+        gR = gT = gs = gP = gF = None
+        if g_images is not None:
+            gR, gT, gs, gP, gF = _points_backward_launch(ctx.cfg, saved, g_images, ctx.needs_input_grad[3], ctx.needs_input_grad[4])
+        if gR_ext is not None:
+            gR = gR_ext if gR is None else gR + gR_ext
+        if gT_ext is not None:
+            gT = gT_ext if gT is None else gT + gT_ext
+        ga, ge, gd = _look_at_backward_launch(a, e, d, gR, gT, gC_ext)
+        if gs is not None:
+            gd = gd + gs
+        sa, se, sd = ctx.shapes
+        return (ga.reshape(sa), ge.reshape(se), gd.reshape(sd), gP, gF) + (None,) * 10
+
+
+def render_points_from_angles(points, rgb, M: int, azim, elev, dist, radius: float, bg_rgb, image_size, points_per_pixel=1,
+                              compositor="norm", normalize=None, out_dtype=None, after_cameras=None):
+    """look_at_view_transform + render_points(dist=...) in one autograd node (see _PointsRenderFromAngles).
+    Returns images (B*M,3,H,W), (R, T, C, invalid flag), fragments dict."""
+    if compositor not in ("norm", "alpha"):
+        raise ValueError("compositor must be 'norm' or 'alpha'")
+    flags = L.COMPOSITE_ALPHA if compositor == "alpha" else 0
+    H, W = _hw(image_size)
+    images, R, T, Cc, bad, idx, mask = _PointsRenderFromAngles.apply(
+        azim, elev, dist, points, rgb, M, radius, bg_rgb, H, W, int(points_per_pixel), flags, _out_norm(normalize), out_dtype,
+        after_cameras)
+    return images, (R, T, Cc, bad), _PointFragments(idx, mask, H, W)
 
 
 def render_points(points, rgb, M: int, R, T, inv_dist, radius: float, bg_rgb, image_size: int, points_per_pixel=1,

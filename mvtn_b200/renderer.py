@@ -233,7 +233,16 @@ class MVRenderer(nn.Module):
                                      points_per_pixel=self.points_per_pixel, compositor=self.compositor,
                                      normalize=self.normalize, out_dtype=self.out_dtype, dist=dist_)
 
-        (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
+        # fast path: cameras + rasterizer + compositor as ONE autograd node (ops.render_points_from_angles); the validity
+        # flag is awaited through an event recorded between the camera kernel and the rasterizer
+        az, el, di = self._views(azim, elev, dist, device)
+        reader = []
+        images, (R, T, C, _bad), frag = ops.render_points_from_angles(
+            pts, rgb, self.nb_views, az, el, di, self.points_radius, bg, self.image_size,
+            points_per_pixel=self.points_per_pixel, compositor=self.compositor, normalize=self.normalize,
+            out_dtype=self.out_dtype, after_cameras=lambda bad: reader.append(_flag_reader(bad)))
+        if reader[0]() != 0:      # invalid rotations: the general path with the redraw loop
+            (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
         self.last_fragments = frag
         rendered_images = images.view(pts.shape[0], self.nb_views, 3, self.image_size, self.image_size)
         return rendered_images, FoVOrthographicCameras(R, T, C, znear=0.01)
