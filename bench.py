@@ -377,7 +377,7 @@ def run_ours(a):
         out["e2e"]["list_api"] = {"value": round(total_views / (ms_e2e_list_max / 1e3), 1), "ms_per_step": round(ms_e2e_list_max / a.steps, 4),
                                   "input": "python list of per-object CPU meshes (the reference's loader output); gather into pinned memory inside the timed region"}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(a, inp)
+        out["cpu_baseline"], out["parity"] = cpu_baseline(a, inp)
     if rank == 0:
         emit(out)
     if world > 1:
@@ -385,8 +385,9 @@ def run_ours(a):
 
 
 # ---------------------------------------------------------------------------------------------------
-def oracle_step(a, inp, n_obj):
-    """One forward+backward of the CPU oracle on the first n_obj objects of the workload.  Returns seconds."""
+def oracle_step(a, inp, n_obj, keep=None):
+    """One forward+backward of the CPU oracle on the first n_obj objects of the workload.  Returns seconds; `keep` (a dict)
+    receives the cameras, fragment indices, images and gradients for the parity report."""
     import numpy as np
     from oracle import oracle as orc
     from mvtn_b200 import ops
@@ -407,7 +408,9 @@ def oracle_step(a, inp, n_obj):
         g = np.full((n_obj * M, 3, S, S), 1.0 / (3 * S * S), np.float32)
         b = orc.mesh_backward(vp, fp, voff, foff, nrm, rgb, M, R, T, C, light, k00, k11, S, S, 1,
                               orc.PERSPECTIVE_CORRECT, o["pix_to_face"], g)
-        orc.look_at_backward(az, el, di, b["gR"], b["gT"], b["gC"])
+        gv = orc.look_at_backward(az, el, di, b["gR"], b["gT"], b["gC"])
+        if keep is not None:
+            keep.update(R=R, T=T, C=C, index=o["pix_to_face"], images=o["images"], gR=b["gR"], gT=b["gT"], gC=b["gC"], g_views=gv)
     else:
         pts = inp["points"][:n_obj].numpy()
         rgb = np.full(3, 0.99999, np.float32)
@@ -417,7 +420,9 @@ def oracle_step(a, inp, n_obj):
                                fragments=False)
         g = np.full((n_obj * M, 3, S, S), 1.0 / (3 * S * S), np.float32)
         b = orc.points_backward(pts, rgb, M, R, T, inv, 0.006, S, S, K, orc.COMPOSITE_ALPHA, o["idx"], g)
-        orc.look_at_backward(az, el, di, b["gR"], b["gT"], None)
+        gv = orc.look_at_backward(az, el, di, b["gR"], b["gT"], np.zeros_like(b["gT"]))      # the orthographic path does not use C
+        if keep is not None:
+            keep.update(R=R, T=T, C=C, index=o["idx"], images=o["images"], gR=b["gR"], gT=b["gT"], g_scale=b.get("g_inv_dist"), g_views=gv)
     return time.time() - t0
 
 
@@ -429,10 +434,79 @@ def cpu_baseline(a, inp):
     if n <= 0:
         t1 = oracle_step(a, inp, 1)                     # probe: one object
         n = max(1, min(a.batch, int(12.0 / max(t1, 1e-3))))
-    t = oracle_step(a, inp, n)
-    return {"value": round(n * a.views / t, 2), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+    keep = {}
+    t = oracle_step(a, inp, n, keep)
+    base = {"value": round(n * a.views / t, 2), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
             "sample": f"{n} object(s) x {a.views} views of the same workload, fwd+bwd, {t:.2f} s of CPU work "
                       f"(oracle/mvr_oracle.c, OpenMP over image rows)"}
+    return base, parity_report(a, inp, n, keep)
+
+
+def parity_report(a, inp, n_obj, ref):
+    """the parity gates that go with every throughput number.  The CUDA path renders the objects the CPU
+    baseline has just rendered (same constant cotangent) and is compared with the oracle's outputs in the two stages of
+    the test protocol: (A) rasterizer / shader / compositor and their backward from the SAME cameras -- fragment indices
+    bit-exact, images and camera gradients within tolerance; (B) the camera kernels on their own -- look_at forward
+    against the oracle's R, T, C and look_at backward fed with the oracle's camera gradients.  (An end-to-end comparison
+    through DIFFERENT cameras would measure how many edge pixels a 1e-7 change of R flips, not the kernels.)
+    Exact depth ties are counted from the K-list (meshes: a K = 2 render)."""
+    import numpy as np
+    import torch
+    from mvtn_b200 import ops
+    dev = torch.device("cuda", torch.cuda.current_device())
+    M, S = a.views, a.image_size
+    N = n_obj * M
+    cot = torch.full((N, 3, S, S), 1.0 / (3 * S * S), device=dev)
+    col = torch.tensor([0.99999] * 3, device=dev)
+    Rd, Td, Cd = (torch.from_numpy(ref[k]).to(dev).requires_grad_() for k in ("R", "T", "C"))
+    views = [t[:n_obj].reshape(-1).to(dev).requires_grad_() for t in inp["views"]]
+
+    def rel(x, y):
+        x = x.detach().cpu().numpy().reshape(-1); y = np.asarray(y).reshape(-1)
+        return float(np.abs(x - y).max() / max(np.abs(y).max(), 1e-30))
+
+    out = {"sample": f"the cpu_baseline sample ({n_obj} object(s) x {M} views)", "pixels": int(N * S * S)}
+    if a.workload == "mesh":
+        ms = inp["meshes"][:n_obj]
+        geom = ops.PackedMeshes([v for v, _ in ms], [f for _, f in ms], dev)
+        light = torch.tensor([[0.0, 1.0, 0.0]], device=dev)
+        img, fr = ops.render_meshes(geom, M, Rd, Td, Cd, light, col, col, S)
+        img.backward(cot)
+        index = fr["pix_to_face"]
+        _, fr2 = ops.render_meshes(geom, M, Rd.detach(), Td.detach(), Cd.detach(), light, col, col, S, faces_per_pixel=2, fragments=True)
+        zb = fr2["zbuf"]
+        ties = int(((zb[..., 0] == zb[..., 1]) & (fr2["pix_to_face"][..., 1] >= 0)).sum())
+        g_cam = max(rel(Rd.grad, ref["gR"]), rel(Td.grad, ref["gT"]), rel(Cd.grad, ref["gC"]))
+        tol = {"index": "bit-exact", "images_abs": 1e-5, "gradients_rel": 1e-4, "look_at_abs": 2e-6}
+    else:
+        pts = inp["points"][:n_obj].to(dev)
+        inv = (1.0 / views[2].detach()).requires_grad_()
+        img, fr = ops.render_points(pts, col, M, Rd, Td, inv, 0.006, col * 0, S, points_per_pixel=a.points_per_pixel,
+                                    compositor="alpha", fragments=True)
+        img.backward(cot)
+        index = fr["idx"]
+        zb = fr["zbuf"]
+        ties = int(((zb[..., 1:] == zb[..., :-1]) & (index[..., 1:] >= 0)).sum()) if zb.shape[-1] > 1 else 0
+        g_cam = max(rel(Rd.grad, ref["gR"]), rel(Td.grad, ref["gT"]), rel(inv.grad, ref["g_scale"]))
+        tol = {"index": "bit-exact", "images_abs": 1e-5, "gradients_rel": 1e-5, "look_at_abs": 2e-6}
+    out["index_mismatches"] = int((index.cpu().numpy() != ref["index"]).sum())
+    out["exact_depth_ties"] = ties
+    out["image_max_abs_err"] = round(float(np.abs(img.detach().cpu().numpy() - ref["images"]).max()), 9)
+    out["grad_camera_max_rel_err"] = round(g_cam, 9)
+    # stage B: the camera kernels
+    R2, T2, C2, _ = ops._LookAt.apply(*views)
+    out["look_at_max_abs_err"] = round(max(float((R2.detach().cpu() - torch.from_numpy(ref["R"])).abs().max()),
+                                           float((T2.detach().cpu() - torch.from_numpy(ref["T"])).abs().max()),
+                                           float((C2.detach().cpu() - torch.from_numpy(ref["C"])).abs().max())), 9)
+    gC_ref = ref.get("gC")
+    loss = (R2 * torch.from_numpy(ref["gR"]).to(dev)).sum() + (T2 * torch.from_numpy(ref["gT"]).to(dev)).sum()
+    if gC_ref is not None:
+        loss = loss + (C2 * torch.from_numpy(gC_ref).to(dev)).sum()
+    loss.backward()
+    # one scale for the three view gradients: with orthographic cameras d/d dist through the cameras is identically ~0
+    out["look_at_backward_max_rel_err"] = round(rel(torch.cat([v.grad for v in views]), np.concatenate([np.asarray(g) for g in ref["g_views"]])), 9)
+    out["tolerance"] = tol
+    return out
 
 
 def run_reference(a):
