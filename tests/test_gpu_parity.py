@@ -957,3 +957,31 @@ def test_points_normalized_and_bf16_output_matches_oracle(oracle, cuda_device):
         ga, ge, gdd = oracle.look_at_backward(az.numpy().ravel(), el.numpy().ravel(), di.numpy().ravel(), ob["gR"], ob["gT"], None)
         gdd = gdd + ob["g_inv_dist"] * (-1.0 / di.numpy().ravel() ** 2)
         assert rel(a.grad.reshape(-1), ga) < GRAD_RTOL and rel(e.grad.reshape(-1), ge) < GRAD_RTOL and rel(d.grad.reshape(-1), gdd) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("workload", ["mesh", "points"])
+def test_bench_line_carries_the_contract_keys_and_parity(cuda_device, workload):
+    """One tiny `bench.py` run per workload: ONE JSON line with the contract's keys, and the parity object
+    says what the parity tests say -- bit-exact fragment indices, images / gradients within the stated tolerances."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--workload", workload, "--batch", "2", "--views", "3", "--image-size", "64",
+           "--faces", "600", "--points", "512", "--steps", "2", "--warmup", "1", "--cpu-sample-objects", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "parity"):
+        assert k in d, k
+    assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1.5
+    par = d["parity"]
+    assert par["index_mismatches"] == 0
+    assert par["image_max_abs_err"] <= par["tolerance"]["images_abs"]
+    assert par["grad_camera_max_rel_err"] <= par["tolerance"]["gradients_rel"]
+    assert par["look_at_max_abs_err"] <= par["tolerance"]["look_at_abs"]
+    assert par["look_at_backward_max_rel_err"] <= 1e-4
