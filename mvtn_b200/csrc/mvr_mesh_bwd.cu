@@ -223,6 +223,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <int MINB, bool VRGB>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(const MeshBwdParams p) {
+  // rows of 32 words whose eight 16-byte chunks are XOR-swizzled by 2 (row & 3): the 8x4-pixel warp blocks below read
+  // 32 distinct banks (chunk pair 2 bx, 2 bx + 1 of row r lands on pair bx ^ r), with no padding
   __shared__ __align__(16) int s_fid[2][32 * 32];
   __shared__ __align__(16) float s_g[2][3][32 * 32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -239,13 +241,14 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(
   const int cy = tyb * 32 + cr;
   auto issue = [&](int txb, int buf) {
     const int x0 = txb * 32 + cc;
-    int* df = &s_fid[buf][cr * 32 + cc];
+    const int so = cr * 32 + (((cc >> 2) ^ ((cr & 3) << 1)) << 2);      // swizzled word offset of the chunk
+    int* df = &s_fid[buf][so];
     if (cy < p.H && x0 < p.W) {
       const size_t pix = (size_t)cy * p.W + x0;
       cp_async16(df, fid_base + pix);
-      cp_async16(&s_g[buf][0][cr * 32 + cc], g_base + pix);
-      cp_async16(&s_g[buf][1][cr * 32 + cc], g_base + (size_t)HW + pix);
-      cp_async16(&s_g[buf][2][cr * 32 + cc], g_base + 2 * (size_t)HW + pix);
+      cp_async16(&s_g[buf][0][so], g_base + pix);
+      cp_async16(&s_g[buf][1][so], g_base + (size_t)HW + pix);
+      cp_async16(&s_g[buf][2][so], g_base + 2 * (size_t)HW + pix);
     } else {
       *reinterpret_cast<int4*>(df) = make_int4(-1, -1, -1, -1);      // outside the image: background
     }
@@ -259,25 +262,29 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(
   const ShadeCtx sc = load_shade_ctx(p.light, p.light_stride, p.Cc, n);
   float4 ucol = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!VRGB) ucol = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f);
-  const int yi0 = tyb * 32 + warp;
+  // Pixels -> lanes: shared memory has no coalescing rules, so a warp takes 8x4-pixel BLOCKS (lane = 8 r + c) instead of
+  // 32x1 rows.  A face covers ~2.5 x 2.5 pixels at C2: a block touches ~5 faces where a row touches ~13, and every
+  // gather instruction of the warp (face record, 3 + 6 vertex records) splits into that many fewer L1 wavefronts.
+  const int lc = lane & 7, lr = lane >> 3;
 #pragma unroll 1
   for (int t = 0; t < p.tiles_x; ++t) {
     const int buf = t & 1;
     if (t + 1 < p.tiles_x) { issue(t + 1, buf ^ 1); cp_async_wait<1>(); }
     else cp_async_wait<0>();
     __syncthreads();                                   // tile t has landed for every thread
-    const int xi = t * 32 + lane;
-    const float xf = xi < p.W ? __ldg(p.tab + xi) : 0.f;
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
-      const int o = (warp + 8 * j) * 32 + lane;
+      const int q = warp + 8 * j;                      // block q of the tile: 4 across, 8 down
+      const int x = ((q & 3) << 3) + lc, y = ((q >> 2) << 2) + lr;
+      const int o = y * 32 + ((((x >> 2) ^ ((y & 3) << 1)) << 2) | (x & 3));
       const int fid = s_fid[buf][o];
       if (fid < 0) continue;
       float g0 = s_g[buf][0][o], g1 = s_g[buf][1][o], g2 = s_g[buf][2][o];
       if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
       if (p.onorm.on) { g0 *= p.onorm.s0; g1 *= p.onorm.s1; g2 *= p.onorm.s2; }
       any = true;
-      mesh_backward_pixel<VRGB>(p, n, f0, voff, pvn, persp, sc, ucol, fid, g0, g1, g2, xf, yi0 + 8 * j, acc);
+      const float xf = __ldg(p.tab + t * 32 + x);      // covered => inside the image
+      mesh_backward_pixel<VRGB>(p, n, f0, voff, pvn, persp, sc, ucol, fid, g0, g1, g2, xf, tyb * 32 + y, acc);
     }
     __syncthreads();                                   // everyone is done with `buf` before tile t + 2 overwrites it
   }
