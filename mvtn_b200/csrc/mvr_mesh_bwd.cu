@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(
   // 32 distinct banks (chunk pair 2 bx, 2 bx + 1 of row r lands on pair bx ^ r), with no padding
   __shared__ __align__(16) int s_fid[2][32 * 32];
   __shared__ __align__(16) float s_g[2][3][32 * 32];
+  __shared__ unsigned char s_list[NWARPS][128];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // grid: x = tile row, y = view m, z = object b
   const int b = blockIdx.z, m = blockIdx.y, n = b * p.M + m, tyb = blockIdx.x;
@@ -272,13 +273,27 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(
     if (t + 1 < p.tiles_x) { issue(t + 1, buf ^ 1); cp_async_wait<1>(); }
     else cp_async_wait<0>();
     __syncthreads();                                   // tile t has landed for every thread
-#pragma unroll 1
+    // the warp's covered pixels (of its four blocks) compacted into a list: the chain below then runs in
+    // ceil(covered / 32) rounds with every lane busy instead of four rounds with the background lanes idle
+    int cnt = 0;
+#pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int q = warp + 8 * j;                      // block q of the tile: 4 across, 8 down
       const int x = ((q & 3) << 3) + lc, y = ((q >> 2) << 2) + lr;
+      const bool cov = s_fid[buf][y * 32 + ((((x >> 2) ^ ((y & 3) << 1)) << 2) | (x & 3))] >= 0;
+      const unsigned int mk = __ballot_sync(0xffffffffu, cov);
+      if (cov) s_list[warp][cnt + __popc(mk & ((1u << lane) - 1u))] = (unsigned char)((j << 5) | lane);
+      cnt += __popc(mk);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int base = 0; base < cnt; base += 32) {
+      if (base + lane >= cnt) continue;
+      const int e = s_list[warp][base + lane];
+      const int q = warp + 8 * (e >> 5);
+      const int x = ((q & 3) << 3) + (e & 7), y = ((q >> 2) << 2) + ((e >> 3) & 3);
       const int o = y * 32 + ((((x >> 2) ^ ((y & 3) << 1)) << 2) | (x & 3));
       const int fid = s_fid[buf][o];
-      if (fid < 0) continue;
       float g0 = s_g[buf][0][o], g1 = s_g[buf][1][o], g2 = s_g[buf][2][o];
       if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
       if (p.onorm.on) { g0 *= p.onorm.s0; g1 *= p.onorm.s1; g2 *= p.onorm.s2; }
@@ -286,6 +301,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(
       const float xf = __ldg(p.tab + t * 32 + x);      // covered => inside the image
       mesh_backward_pixel<VRGB>(p, n, f0, voff, pvn, persp, sc, ucol, fid, g0, g1, g2, xf, tyb * 32 + y, acc);
     }
+    __syncwarp();                                      // the list is rebuilt for the next tile
     __syncthreads();                                   // everyone is done with `buf` before tile t + 2 overwrites it
   }
   float* out = p.partials + ((size_t)n * p.parts_per_view + (size_t)tyb * NWARPS + warp) * 16;
