@@ -124,6 +124,7 @@ def _ws_mesh_flags_backward(dev, ws, token):
 
 
 _staging_bufs = {}
+_copy_streams = {}
 
 
 def _staging(tag, device, numel: int, dtype) -> torch.Tensor:
@@ -483,15 +484,31 @@ class PackedMeshes:
         return self
 
     @classmethod
-    def from_host_packed(cls, hp: "HostPackedMeshes", device, vert_rgb: Optional[torch.Tensor] = None):
-        """Two async H2D copies of an already packed (ideally pinned) host batch + mvr_mesh_prepare."""
+    def from_host_packed(cls, hp: "HostPackedMeshes", device, vert_rgb: Optional[torch.Tensor] = None, copy_stream: bool = False):
+        """Two async H2D copies of an already packed (ideally pinned) host batch + mvr_mesh_prepare.
+        copy_stream=True: the copies go through a dedicated stream (the compute stream waits on an event), so that in a
+        loop that does not synchronise every step they overlap with the previous step's kernels instead of queueing
+        behind them (5.8 MB = 0.11 ms per step at C2)."""
         device = torch.device(device)
         if device.type != "cuda":
             raise L.MVRError("PackedMeshes needs a CUDA device: mvtn_b200 has no CPU path")
         self = cls.__new__(cls)
-        v_dev = hp.verts.to(device, non_blocking=True)
-        f_dev = hp.faces.to(device, non_blocking=True)
-        offs = hp.offs.to(device, non_blocking=True)
+        if copy_stream:
+            cur = torch.cuda.current_stream(device)
+            cs = _copy_streams.get(device.index)
+            if cs is None:
+                cs = _copy_streams[device.index] = torch.cuda.Stream(device)
+            with torch.cuda.stream(cs):
+                v_dev = hp.verts.to(device, non_blocking=True)
+                f_dev = hp.faces.to(device, non_blocking=True)
+                offs = hp.offs.to(device, non_blocking=True)
+            cur.wait_stream(cs)
+            for t in (v_dev, f_dev, offs):
+                t.record_stream(cur)
+        else:
+            v_dev = hp.verts.to(device, non_blocking=True)
+            f_dev = hp.faces.to(device, non_blocking=True)
+            offs = hp.offs.to(device, non_blocking=True)
         self._init_packed(v_dev, f_dev, hp.num_verts, hp.num_faces, device,
                           vert_rgb if vert_rgb is not None else hp.vert_rgb,
                           offsets=(hp.vert_off_host, hp.face_off_host, offs))

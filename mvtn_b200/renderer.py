@@ -94,6 +94,8 @@ class MVRenderer(nn.Module):
             imported at renderer.py:11; BASELINE config 3).
         perspective_correct: barycentric perspective correction (PyTorch3D >= 0.5 infers True for
             FoV perspective cameras).
+        copy_stream: H2D of a collated host batch on a side stream (overlaps with the previous step's kernels when the
+            loop does not synchronise every step; see ops.PackedMeshes.from_host_packed)
         cache_geometry: keep the packed device geometry of the last mesh batch and reuse it when the
             same list object is rendered again.
         normalize: None or (mean, std) (3-vectors or scalars): the kernels write (image - mean) / std, the
@@ -105,8 +107,9 @@ class MVRenderer(nn.Module):
     def __init__(self, nb_views, image_size=224, pc_rendering=True, object_color="white", background_color="white",
                  faces_per_pixel=1, points_radius=0.006, points_per_pixel=1, light_direction="random",
                  cull_backfaces=False, *, compositor="norm", perspective_correct=True, cache_geometry=False,
-                 normalize=None, out_dtype=None):
+                 normalize=None, out_dtype=None, copy_stream=False):
         super().__init__()
+        self.copy_stream = copy_stream
         self.nb_views = nb_views
         self.image_size = image_size
         self.pc_rendering = pc_rendering
@@ -256,7 +259,7 @@ class MVRenderer(nn.Module):
             if color_t.numel() != 3:
                 color_t = color_t.reshape(len(meshes), -1, 3)
                 vert_rgb = torch.cat([color_t[b, :n] for b, n in enumerate(meshes.num_verts)], 0)
-            return ops.PackedMeshes.from_host_packed(meshes, device, vert_rgb=vert_rgb)
+            return ops.PackedMeshes.from_host_packed(meshes, device, vert_rgb=vert_rgb, copy_stream=self.copy_stream)
         if meshes is None:
             raise ValueError("mesh rendering (pc_rendering=False) needs `meshes`")
         if self.cache_geometry and self._geom_cache[0] is meshes:
