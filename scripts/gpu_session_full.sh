@@ -11,10 +11,11 @@ $B --workload points --batch 8 --views 20 --image-size 400 --points 16384 > $OUT
 for f in bench_mesh bench_points bench_c5_mesh bench_c5_points; do python - <<PY
 import json
 d=json.load(open("$OUT/${TAG}_$f.json"))
-print("$f", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"].get("list_api",{}).get("value"), d["roofline"]["kernel_ms_all"], d["roofline"]["frac"], d["gpu_launches"], d.get("cpu_baseline",{}).get("value"))
+print("$f", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "pipe", d["e2e"].get("pipelined",{}).get("value"), d["e2e"].get("list_api",{}).get("value"), d["roofline"]["kernel_ms_all"], d["roofline"]["frac"], d["gpu_launches"], d.get("cpu_baseline",{}).get("value"))
 PY
 done
 cut -c1-400 $OUT/${TAG}_bench_reference.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_b.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:mesh_ -s 40 -c 7 -o $OUT/${TAG}_mesh -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_m.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:points_ -s 40 -c 7 -o $OUT/${TAG}_points -f python bench.py --workload points --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_p.log 2>&1
 grep -v "UserWarning\|run_backward" $OUT/${TAG}_bench.err | tail -5
