@@ -246,3 +246,26 @@ def test_bench_reference_arm_runs_on_cpu():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "views/s" and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_point_fragments_complete_the_sparse_idx_lazily():
+    """ops._PointFragments: with MVR_IDX_SPARSE the kernels leave idx unwritten at background pixels; the dict handed to the
+    caller fills those with -1 from the 1-bit hit mask (bit x & 31 of word x >> 5 of row y) on first access."""
+    import torch
+    from mvtn_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    N, H, W, K = 2, 5, 70, 2                                   # 3 mask words per row, the last one partial
+    hit = torch.rand(N, H, W, generator=g) < 0.3
+    idx = torch.randint(0, 1000, (N, H, W, K), dtype=torch.int32, generator=g)      # "uninitialised" background included
+    mw = (W + 31) // 32
+    bits = torch.zeros(N, H, mw * 32, dtype=torch.int64)
+    bits[:, :, :W] = hit.long()
+    words = (bits.view(N, H, mw, 32) << torch.arange(32)).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)   # bit 31 set = negative int32
+    mask = torch.cat([words.reshape(-1), torch.full((7,), -1, dtype=torch.int32)])  # the buffer may be longer than needed
+    fr = ops._PointFragments(idx, mask, H, W)
+    assert list(fr.keys()) == ["idx"]
+    dense = fr["idx"]
+    assert torch.equal(dense[hit], idx[hit])
+    assert (dense[~hit] == -1).all()
+    assert fr.get("idx") is dense and dict(fr.items())["idx"] is dense
