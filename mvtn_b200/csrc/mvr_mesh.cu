@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
   const float* s_yf = s_tab + p.W;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = blockIdx.x / p.chunks_per_view, chunk = blockIdx.x % p.chunks_per_view;
-  const int b = n / p.M, m = n - b * p.M;
+  // grid: x = chunk of faces, y = view m, z = object b (no integer divisions in the prologue)
+  const int chunk = blockIdx.x, m = blockIdx.y, b = blockIdx.z, n = b * p.M + m;
   const int f0 = p.face_off[b], F = p.face_off[b + 1] - f0;
   const int fbeg = chunk * p.faces_per_cta, fend = min(F, fbeg + p.faces_per_cta);
   if (fbeg >= fend) return;
@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
         bool queued = false;
         if (npx <= BIG_FACE_PIX) {
           // runs of G pixels: 8 for ordinary faces, up to 32 for large ones (<= 32 runs per face)
-          const int G = max(p.run_len, (npx + 31) >> 5);
-          const int nsub = (npx + G - 1) / G;
+          int G = 8, nsub = (npx + 7) >> 3;
+          if (npx > 256) { G = (npx + 31) >> 5; nsub = (npx + G - 1) / G; }      // the division only for the rare large face
           const int at = atomicAdd(&s_cnt[0], nsub);
           if (at + nsub <= p.item_cap) {
             for (int q = 0; q < nsub; ++q) s_items[at + q] = tid | ((q * G) << 8) | (min(G, npx - q * G) << 18);
@@ -585,11 +585,6 @@ static int scatter_fpc() {
   static const int v = [] { const char* e = getenv("MVR_SCATTER_FPC"); const int x = e ? atoi(e) : FACES_PER_CTA; return (x == 256 || x == 512 || x == 1024 || x == 2048) ? x : FACES_PER_CTA; }();
   return v;
 }
-// scatter: pixels per filter run (profiling knob: 4 / 8 / 16)
-static int scatter_run() {
-  static const int v = [] { const char* e = getenv("MVR_SCATTER_RUN"); const int x = e ? atoi(e) : 8; return (x == 4 || x == 16) ? x : 8; }();
-  return v;
-}
 template <int PPT, bool VRGB>
 static void launch_shade_fast(const MeshParams& p, int B, int M, int H, int W, cudaStream_t st) {
   const int tiles_x = (W + 31) / 32, tiles_y = (H + 8 * PPT - 1) / (8 * PPT);
@@ -635,7 +630,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.obj_rgb = obj_rgb; p.bg_rgb = bg_rgb;
   p.k00 = k00; p.k11 = k11; p.z_clip = z_clip;
   p.B = B; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags;
-  p.chunks_per_view = chunks_per_view; p.layer = 0; p.faces_per_cta = fpc; p.run_len = scatter_run();
+  p.chunks_per_view = chunks_per_view; p.layer = 0; p.faces_per_cta = fpc;
   p.ndc_max = W > H ? (float)((W + H - 1) / H) : (float)((H + W - 1) / W);      // bound on |pixel-centre NDC| (>= aspect ratio)
   p.item_cap = (flags & MVR_TEST_TINY_QUEUES) ? 24 : ITEM_CAP;
   p.wcap = (flags & MVR_TEST_TINY_QUEUES) ? 5 : WCAP;
@@ -658,8 +653,9 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   for (int k = 0; k < K; ++k) {
     p.layer = k;
     if (chunks_per_view > 0) {
-      if (scatter_minb() == 3) MVR_LAUNCH(mesh_scatter_kernel<3>, (unsigned)(N * chunks_per_view), MVR_THREADS, tab_smem, st, p);
-      else MVR_LAUNCH(mesh_scatter_kernel<4>, (unsigned)(N * chunks_per_view), MVR_THREADS, tab_smem, st, p);
+      const dim3 scatter_grid((unsigned)chunks_per_view, (unsigned)M, (unsigned)B);
+      if (scatter_minb() == 3) MVR_LAUNCH(mesh_scatter_kernel<3>, scatter_grid, MVR_THREADS, tab_smem, st, p);
+      else MVR_LAUNCH(mesh_scatter_kernel<4>, scatter_grid, MVR_THREADS, tab_smem, st, p);
       rc = check_launch("mesh_scatter_kernel");
       if (rc) return rc;
     }
