@@ -180,7 +180,7 @@ def run_ours(a):
         pts_d = inp["points"].to(dev)
         pts_h = inp["points"].pin_memory()
         renderer = MVRenderer(M, image_size=S, pc_rendering=True, points_per_pixel=a.points_per_pixel,
-                              background_color="black", compositor="alpha").to(dev)
+                              background_color="black", compositor="alpha", cuda_graph=a.cuda_graph).to(dev)
         tiled = a.points_per_pixel in (1, 2, 4, 8) and os.environ.get("MVR_POINTS_TILED", "1") != "0"
         kernels = (["points_bin_kernel", "points_tile_kernel", "points_backward_kernel"] if tiled
                    else ["points_scatter_kernel", "points_resolve_kernel", "points_backward_kernel"])

@@ -32,17 +32,23 @@ def _views_like(sample_views: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, ...
 
 
 def graphed_points_render(points: torch.Tensor, rgb: torch.Tensor, M: int, radius: float, bg: torch.Tensor, image_size,
-                          sample_views: Sequence[torch.Tensor], points_per_pixel: int = 1, compositor: str = "norm"):
+                          sample_views: Sequence[torch.Tensor], points_per_pixel: int = 1, compositor: str = "norm",
+                          normalize=None, out_dtype=None, return_cameras: bool = False):
     """Capture look_at + point rasterization + compositing (and their backward) for a FIXED (B, N, 3) device tensor
-    `points` (update it in place between replays).  Returns step(azim, elev, dist) -> images (B*M, 3, H, W)."""
+    `points` (update it -- and `rgb` / `bg` -- in place between replays).
+    Returns step(azim, elev, dist) -> images (B*M, 3, H, W); with return_cameras=True -> (images, cams, invalid) where
+    cams is the flat R | T | C buffer (9n + 3n + 3n floats, n = B*M) and invalid the rotation-validity flag of look_at
+    (both live in captured buffers: copy what must outlive the next replay)."""
     ops._require_cuda(points, "points")
     rgb = rgb.to(points.device)
     bg = bg.to(points.device)
 
     def fn(az, el, di):
-        R, T, _C, _bad = ops._LookAt.apply(az.reshape(-1), el.reshape(-1), di.reshape(-1))
-        img, _ = ops.render_points(points, rgb, M, R, T, None, radius, bg, image_size, dist=di,
-                                   points_per_pixel=points_per_pixel, compositor=compositor)
+        img, (R, T, C, bad), _ = ops.render_points_from_angles(points, rgb, M, az, el, di, radius, bg, image_size,
+                                                               points_per_pixel=points_per_pixel, compositor=compositor,
+                                                               normalize=normalize, out_dtype=out_dtype)
+        if return_cameras:
+            return img, torch.cat([R.reshape(-1), T.reshape(-1), C.reshape(-1)]), bad
         return img
 
     return torch.cuda.make_graphed_callables(fn, _views_like(sample_views))

@@ -96,6 +96,12 @@ class MVRenderer(nn.Module):
             FoV perspective cameras).
         copy_stream: H2D of a collated host batch on a side stream (overlaps with the previous step's kernels when the
             loop does not synchronise every step; see ops.PackedMeshes.from_host_packed)
+        cuda_graph: point path only -- the device part of a step (look_at, binning, tile rasterizer + compositor, and their
+            backward) is captured once per (B, N, views-require-grad) and replayed with ONE launch per direction: the
+            point path at small batches is launch-bound (BASELINE configs[0], one cloud x 12 views: 0.470 -> 0.356 ms per
+            end-to-end step, r2m); at 32 clouds the eager step is already GPU-bound and the copies into the captured buffers
+            make this mode slower (0.516 -> 0.590 ms): leave it off there.  Needs one object colour and fixed shapes; anything else (per-point colours, invalid rotations, new shapes being captured) takes the eager
+            path.  In this mode `cameras` holds detached copies and `last_fragments` is None.
         cache_geometry: keep the packed device geometry of the last mesh batch and reuse it when the
             same list object is rendered again.
         normalize: None or (mean, std) (3-vectors or scalars): the kernels write (image - mean) / std, the
@@ -107,9 +113,11 @@ class MVRenderer(nn.Module):
     def __init__(self, nb_views, image_size=224, pc_rendering=True, object_color="white", background_color="white",
                  faces_per_pixel=1, points_radius=0.006, points_per_pixel=1, light_direction="random",
                  cull_backfaces=False, *, compositor="norm", perspective_correct=True, cache_geometry=False,
-                 normalize=None, out_dtype=None, copy_stream=False):
+                 normalize=None, out_dtype=None, copy_stream=False, cuda_graph=False):
         super().__init__()
         self.copy_stream = copy_stream
+        self.cuda_graph = cuda_graph
+        self._point_graphs = {}
         self.nb_views = nb_views
         self.image_size = image_size
         self.pc_rendering = pc_rendering
@@ -222,9 +230,14 @@ class MVRenderer(nn.Module):
         device = self._device(azim)
         if points.shape[0] != azim.shape[0]:
             raise ValueError(f"{points.shape[0]} clouds but azim has batch {azim.shape[0]}")
-        pts = points.to(device=device, dtype=torch.float32, non_blocking=True)
         bg = _device_vec(background_color, device)
         rgb = torch.as_tensor(color, dtype=torch.float32)
+        if self.cuda_graph and rgb.numel() == 3:
+            az, el, di = self._views(azim, elev, dist, device)
+            out = self._render_points_graphed(points, _device_vec(rgb, device), az, el, di, bg, device)
+            if out is not None:
+                return out
+        pts = points.to(device=device, dtype=torch.float32, non_blocking=True)
         if rgb.numel() == 3:
             rgb = _device_vec(rgb, device)
         else:
@@ -236,9 +249,9 @@ class MVRenderer(nn.Module):
                                      points_per_pixel=self.points_per_pixel, compositor=self.compositor,
                                      normalize=self.normalize, out_dtype=self.out_dtype, dist=dist_)
 
+        az, el, di = self._views(azim, elev, dist, device)
         # fast path: cameras + rasterizer + compositor as ONE autograd node (ops.render_points_from_angles); the validity
         # flag is awaited through an event recorded between the camera kernel and the rasterizer
-        az, el, di = self._views(azim, elev, dist, device)
         reader = []
         images, (R, T, C, _bad), frag = ops.render_points_from_angles(
             pts, rgb, self.nb_views, az, el, di, self.points_radius, bg, self.image_size,
@@ -248,6 +261,40 @@ class MVRenderer(nn.Module):
             (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
         self.last_fragments = frag
         rendered_images = images.view(pts.shape[0], self.nb_views, 3, self.image_size, self.image_size)
+        return rendered_images, FoVOrthographicCameras(R, T, C, znear=0.01)
+
+    def _render_points_graphed(self, points, rgb, az, el, di, bg, device):
+        """CUDA-graph replay of the point step (see `cuda_graph` in the class docstring): `points` (host or device) is
+        copied straight into the captured buffer.  Returns None when the eager path must take over (invalid rotations)."""
+        from . import graphs
+        grads = (az.requires_grad, el.requires_grad, di.requires_grad)
+        key = (tuple(points.shape), device.index, grads, torch.is_grad_enabled())
+        st = self._point_graphs.get(key)
+        if st is None:
+            static_pts = points.to(device=device, dtype=torch.float32).clone()
+            static_rgb, static_bg = rgb.clone(), bg.clone()
+            sample = tuple(t.detach().clone().requires_grad_(g) for t, g in zip((az, el, di), grads))
+            step = graphs.graphed_points_render(static_pts, static_rgb, self.nb_views, self.points_radius, static_bg,
+                                                self.image_size, sample, points_per_pixel=self.points_per_pixel,
+                                                compositor=self.compositor, normalize=self.normalize,
+                                                out_dtype=self.out_dtype, return_cameras=True)
+            st = self._point_graphs[key] = {"pts": static_pts, "rgb": static_rgb, "bg": static_bg, "step": step,
+                                            "rgb_src": rgb, "bg_src": bg}
+        else:
+            st["pts"].copy_(points, non_blocking=True)
+            if st["rgb_src"] is not rgb:          # named colours are cached constants: nothing to copy in the steady state
+                st["rgb"].copy_(rgb); st["rgb_src"] = rgb
+            if st["bg_src"] is not bg:
+                st["bg"].copy_(bg); st["bg_src"] = bg
+        images, cams, bad = st["step"](az, el, di)
+        invalid = _flag_reader(bad)
+        n = az.numel()
+        cams = cams.detach().clone()              # the captured buffer is overwritten by the next replay
+        if invalid() != 0:
+            return None
+        self.last_fragments = None
+        R, T, C = cams[: 9 * n].view(n, 3, 3), cams[9 * n: 12 * n].view(n, 3), cams[12 * n:].view(n, 3)
+        rendered_images = images.view(points.shape[0], self.nb_views, 3, self.image_size, self.image_size)
         return rendered_images, FoVOrthographicCameras(R, T, C, znear=0.01)
 
     def _packed(self, meshes, color, device):

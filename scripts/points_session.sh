@@ -18,3 +18,5 @@ run points_k1 --points-per-pixel 1
 run c1 --batch 1 --points-per-pixel 1
 run c5_points --batch 8 --views 20 --image-size 400 --points 16384
 grep -v "UserWarning\|run_backward" $OUT/${TAG}_bench.err | tail -5
+run points_graph --cuda-graph
+run c1_graph --batch 1 --points-per-pixel 1 --cuda-graph
