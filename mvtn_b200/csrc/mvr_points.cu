@@ -437,9 +437,8 @@ __global__ void __launch_bounds__(MVR_THREADS) points_tile_kernel(const PointsPa
     // per-view bases and the (normalised) background colour once per thread: the loop body is then 32-bit index
     // arithmetic and stores
     const size_t HW = (size_t)p.H * p.W;
-    int* idx_v = p.idx + (size_t)n * HW * KT;
-    float* zb_v = p.zbuf ? p.zbuf + (size_t)n * HW * KT : nullptr;
-    float* d2_v = p.dists2 ? p.dists2 + (size_t)n * HW * KT : nullptr;
+    const size_t frag_o = (size_t)n * HW * KT;      // (the zbuf / dists2 pointers are formed only where a caller asked for them)
+    int* idx_v = p.idx + frag_o;
     unsigned int* mask_v = p.hit_mask ? p.hit_mask + (size_t)n * p.H * p.mask_words + tx : nullptr;
     const bool bf16 = p.flags & MVR_IMAGES_BF16;
     const bool sparse_idx = (p.flags & MVR_IDX_SPARSE) && mask_v;
@@ -449,7 +448,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_tile_kernel(const PointsPa
     if (p.onorm.on) { g0 = (g0 - p.onorm.m0) * p.onorm.s0; g1 = (g1 - p.onorm.m1) * p.onorm.s1; g2 = (g2 - p.onorm.m2) * p.onorm.s2; }
     const __nv_bfloat16 h0 = __float2bfloat16_rn(g0), h1 = __float2bfloat16_rn(g1), h2 = __float2bfloat16_rn(g2);
     const int hw = (int)HW, xi = x0 + lane;
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int row = warp + 8 * j, yi = y0 + row;
       const bool inside = xi < p.W && yi < p.H;
@@ -474,13 +473,13 @@ __global__ void __launch_bounds__(MVR_THREADS) points_tile_kernel(const PointsPa
 #pragma unroll
           for (int l = 0; l < KT; ++l) idx_v[KT * pix + l] = -1;
         }
-        if (zb_v) {
+        if (p.zbuf) {
 #pragma unroll
-          for (int l = 0; l < KT; ++l) zb_v[KT * pix + l] = -1.f;
+          for (int l = 0; l < KT; ++l) p.zbuf[frag_o + KT * pix + l] = -1.f;
         }
-        if (d2_v) {
+        if (p.dists2) {
 #pragma unroll
-          for (int l = 0; l < KT; ++l) d2_v[KT * pix + l] = -1.f;
+          for (int l = 0; l < KT; ++l) p.dists2[frag_o + KT * pix + l] = -1.f;
         }
         if (bf16) { img_h[pix] = h0; img_h[pix + hw] = h1; img_h[pix + 2 * hw] = h2; }
         else { img_f[pix] = g0; img_f[pix + hw] = g1; img_f[pix + 2 * hw] = g2; }
