@@ -1,0 +1,28 @@
+"""Tiny forward + backward of both paths (mesh: strip and tile backward, K = 1 and 2, a clipped view; points: tiled and generic K)
+for compute-sanitizer:   compute-sanitizer --tool memcheck|racecheck python scripts/sanitize_small.py"""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mvtn_b200 import ops, synth
+
+dev = torch.device("cuda:0")
+col = torch.full((3,), 0.9, device=dev); bg = torch.tensor([0.1, 0.2, 0.3], device=dev); light = torch.tensor([[0.2, 1.0, -0.3]], device=dev)
+meshes = synth.make_meshes(2, 700, 5)
+geom = ops.PackedMeshes([v for v, _ in meshes], [f for _, f in meshes], dev)
+views = synth.learned_spherical_views(2, 3, 7)
+near = (views[0], views[1], views[2] * 0 + 1.15)
+for H, K, vs in ((64, 1, views), (50, 1, views), (40, 2, views), (64, 1, near), (64, 1, views)):
+    a, e, d = (t.to(dev).reshape(-1).requires_grad_() for t in vs)
+    R, T, C, _ = ops._LookAt.apply(a, e, d)
+    img, fr = ops.render_meshes(geom, 3, R, T, C, light, col, bg, H, faces_per_pixel=K)
+    img.backward(torch.ones_like(img))
+    torch.cuda.synchronize()
+    print("mesh", H, K, float(img.sum()), float(a.grad.abs().sum()))
+pts = synth.make_clouds(2, 600, 3).to(dev)
+for K in (1, 4, 3):
+    a, e, d = (t.to(dev).requires_grad_() for t in views)
+    img, _, fr = ops.render_points_from_angles(pts, col, 3, a, e, d, 0.03, bg, 64, points_per_pixel=K, compositor="alpha")
+    img.backward(torch.ones_like(img))
+    torch.cuda.synchronize()
+    print("points", K, float(img.sum()), float(d.grad.abs().sum()), int((fr["idx"] >= 0).sum()))
