@@ -354,6 +354,69 @@ __global__ void __launch_bounds__(MVR_THREADS) points_bin_scan_kernel(const Poin
   }
 }
 
+// The three binning launches (+ the pixel-table launch and the counter memset) as ONE kernel for clouds of up to
+// BIN_FUSED_MAX_POINTS points and images of up to BIN_FUSED_MAX_TILES tiles: one CTA per view counts into shared
+// memory, scans, and fills its lists.  At MVTN's sizes (2048 points, 49 tiles) the point path is launch-bound: five
+// launches of 5-18 us of work each become one.  grid: x = view m, y = object b; dynamic smem: (W + H) floats.
+constexpr int BIN_FUSED_MAX_TILES = 1024;
+constexpr int BIN_FUSED_MAX_POINTS = 16384;
+__global__ void __launch_bounds__(MVR_THREADS) points_bin_kernel_fused(const PointsParams p, float* __restrict__ tab_out) {
+  __shared__ int s_cnt[BIN_FUSED_MAX_TILES];
+  __shared__ int s_cur[BIN_FUSED_MAX_TILES];
+  __shared__ int s_w[MVR_THREADS / 32 + 1];
+  extern __shared__ float s_ptab[];                          // xf[W], yf[H]
+  const int b = blockIdx.y, n = b * p.M + blockIdx.x, tid = threadIdx.x;
+  fill_pixel_table(s_ptab, p.H, p.W, tid, MVR_THREADS);
+  for (int t = tid; t < p.ntiles; t += MVR_THREADS) s_cnt[t] = 0;
+  __syncthreads();
+  if (n == 0) for (int i = tid; i < p.W + p.H; i += MVR_THREADS) tab_out[i] = s_ptab[i];      // the tile / backward kernels read it
+  const Camera cam = load_camera(p.R, p.T, n);
+  const float s = view_scale(p.inv_dist, p.flags, n);
+  const float rr = p.radius * 1.0001f + 1e-7f;               // conservative window (the exact test is dist2 < r2 in the tile kernel)
+  for (int pi = tid; pi < p.Np; pi += MVR_THREADS) {
+    const size_t o = (size_t)n * p.Np + pi;
+    float px, py, pz;
+    project_point(p.points + 3 * (size_t)b * p.Np, pi, s, cam, px, py, pz);
+    int xl = 1, xh = 0, yl = 1, yh = 0;                      // empty window
+    if (!(pz < 0.f)) {
+      pixel_range(py - rr, py + rr, p.H, p.W, 0, p.H - 1, s_ptab + p.W, yl, yh);
+      if (yl <= yh) pixel_range(px - rr, px + rr, p.W, p.H, 0, p.W - 1, s_ptab, xl, xh);
+      if (yl > yh || xl > xh) { xl = 1; xh = 0; yl = 1; yh = 0; }
+    }
+    p.pp[o] = make_float4(px, py, pz, 0.f);
+    p.pw[o] = make_int2(xl | (xh << 16), yl | (yh << 16));
+    if (xl > xh) continue;
+    for (int ty = yl >> 5; ty <= (yh >> 5); ++ty)
+      for (int tx = xl >> 5; tx <= (xh >> 5); ++tx) atomicAdd(&s_cnt[ty * p.tiles_x + tx], 1);
+  }
+  __syncthreads();
+  // exclusive scan of the per-tile counts: `per` consecutive tiles per thread
+  const int per = (p.ntiles + MVR_THREADS - 1) / MVR_THREADS;
+  const int beg = min(tid * per, p.ntiles), end = min(beg + per, p.ntiles);
+  int sum = 0;
+  for (int t = beg; t < end; ++t) sum += s_cnt[t];
+  int total;
+  int acc = block_exclusive_scan(sum, s_w, total);
+  for (int t = beg; t < end; ++t) {
+    const int c = s_cnt[t];
+    s_cur[t] = acc;
+    p.tile_off[(size_t)n * p.ntiles + t] = acc;
+    p.tile_cur[(size_t)n * p.ntiles + t] = acc + c;          // where the fill below ends
+    acc += c;
+  }
+  __syncthreads();
+  for (int pi = tid; pi < p.Np; pi += MVR_THREADS) {
+    const int2 w = p.pw[(size_t)n * p.Np + pi];              // this thread's own store
+    const int xl = w.x & 0xffff, xh = w.x >> 16, yl = w.y & 0xffff, yh = w.y >> 16;
+    if (xl > xh) continue;
+    for (int ty = yl >> 5; ty <= (yh >> 5); ++ty)
+      for (int tx = xl >> 5; tx <= (xh >> 5); ++tx) {
+        const int at = atomicAdd(&s_cur[ty * p.tiles_x + tx], 1);
+        if (at < p.list_cap) p.list[(size_t)n * p.list_cap + at] = pi;
+      }
+  }
+}
+
 // slot-major shared key planes: slot k of local pixel q at s_keys[k * 1024 + q]
 template <int KT>
 __device__ __forceinline__ void insert_key_smem(unsigned long long* s_keys, int q, unsigned long long key) {
@@ -741,6 +804,12 @@ extern "C" size_t mvr_points_hit_mask_words(int B, int M, int H, int W) {
   return (size_t)B * M * H * ((W + 31) / 32);
 }
 
+// profiling knob: MVR_POINTS_BIN_FUSED=0 keeps the three-launch binning everywhere
+static bool points_bin_fused() {
+  static const bool v = [] { const char* e = getenv("MVR_POINTS_BIN_FUSED"); return !(e && atoi(e) == 0); }();
+  return v;
+}
+
 extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
                                   const float* T, const float* inv_dist, double radius, const float* bg_rgb,
                                   int H, int W, int K, int flags, const float* out_mean_std, void* images, int* idx,
@@ -773,9 +842,14 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
   p.onorm = make_out_norm(out_mean_std);
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 point_grid((unsigned)((Np + MVR_THREADS - 1) / MVR_THREADS), (unsigned)M, (unsigned)B);
-  if (Np > 0) MVR_LAUNCH(pixel_table_kernel, 1, MVR_THREADS, 0, st, (float*)(wb + w.tab), H, W);
+  const bool bin_fused = w.tiled && Np > 0 && Np <= BIN_FUSED_MAX_POINTS && w.ntiles <= BIN_FUSED_MAX_TILES && points_bin_fused();
+  if (Np > 0 && !bin_fused) MVR_LAUNCH(pixel_table_kernel, 1, MVR_THREADS, 0, st, (float*)(wb + w.tab), H, W);
   if (w.tiled) {
-    if (Np > 0) {
+    if (bin_fused) {
+      MVR_LAUNCH(points_bin_kernel_fused, dim3((unsigned)M, (unsigned)B), MVR_THREADS, ((size_t)W + H) * sizeof(float), st, p, (float*)(wb + w.tab));
+      rc = check_launch("points_bin_kernel_fused");
+      if (rc) return rc;
+    } else if (Np > 0) {
       cudaError_t e = cudaMemsetAsync(p.tile_cnt, 0, (size_t)N * w.ntiles * sizeof(int), st);
       if (e != cudaSuccess) { set_error("mvr_points_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
       MVR_LAUNCH(points_bin_kernel<false>, point_grid, MVR_THREADS, 0, st, p);
