@@ -287,6 +287,45 @@ def test_mesh_backward_matches_autograd(oracle):
     assert rel(bw["grad_normals"], nd.grad.numpy()) < 2e-5
 
 
+def test_mesh_backward_matches_finite_differences(oracle):
+    """The whole hand-derived chain of the C oracle -- d image -> Phong -> barycentrics -> projection -> (dR, dT, dC) ->
+    look_at backward -> d azim / elev / dist -- against central differences of its OWN forward: no torch_ref, no autograd.
+    The image is one large triangle that fills every view (no silhouette, so the loss is smooth in the camera) with
+    per-vertex colours and normals that are not the face normal (so interpolation, diffuse and specular terms all move)."""
+    H, M = 24, 3
+    v = np.array([[-9.0, -7.0, 0.3], [9.0, -7.0, -0.2], [0.0, 11.0, 0.1]], np.float32)
+    f = np.array([[0, 1, 2]], np.int32)
+    nrm = np.array([[0.3, 0.1, 1.0], [-0.2, 0.2, 1.0], [0.1, -0.3, 1.0]], np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    rgb = np.array([[0.9, 0.2, 0.3], [0.1, 0.8, 0.4], [0.3, 0.3, 0.9]], np.float32)
+    light = np.array([[0.3, 0.2, 1.0]], np.float32); bg = np.zeros(3, np.float32)
+    az0 = np.array([8.0, -12.0, 3.0]); el0 = np.array([5.0, 10.0, -7.0]); di0 = np.array([2.2, 2.6, 3.1])
+    g = np.random.RandomState(3).randn(M, 3, H, H).astype(np.float32)
+
+    def loss(az, el, di, want_grad=False):
+        R, T, C = oracle.look_at(az, el, di)
+        o = oracle.mesh_forward(v, f, [0, 3], [0, 1], nrm, rgb, M, R, T, C, light, bg, K00, K11, 0.5, H, H, 1, oracle.PERSPECTIVE_CORRECT)
+        assert (o["pix_to_face"] == 0).all()                  # the triangle fills every view: coverage never changes
+        val = float((o["images"].astype(np.float64) * g).sum())
+        if not want_grad:
+            return val
+        b = oracle.mesh_backward(v, f, [0, 3], [0, 1], nrm, rgb, M, R, T, C, light, K00, K11, H, H, 1, oracle.PERSPECTIVE_CORRECT,
+                                 o["pix_to_face"], g)
+        return val, oracle.look_at_backward(az, el, di, b["gR"], b["gT"], b["gC"])
+
+    _, (ga, ge, gd) = loss(az0, el0, di0, want_grad=True)
+    for name, grad, h in (("azim", ga, 0.25), ("elev", ge, 0.25), ("dist", gd, 0.02)):
+        for i in range(M):
+            args = {"azim": az0.copy(), "elev": el0.copy(), "dist": di0.copy()}
+            args[name][i] += h
+            up = loss(args["azim"], args["elev"], args["dist"])
+            args[name][i] -= 2 * h
+            dn = loss(args["azim"], args["elev"], args["dist"])
+            fd = (up - dn) / (2 * h)
+            scale = max(abs(fd), float(np.abs(grad).max()), 1e-6)
+            assert abs(grad[i] - fd) <= 2e-3 * scale, (name, i, float(grad[i]), fd)
+
+
 def test_rasterize_meshes_backward_operator(oracle):
     # operator-level backward ([upstream] RasterizeMeshesBackwardCpu): grad_bary and grad_zbuf -> grad_face_verts
     g = torch.Generator().manual_seed(3)
@@ -357,6 +396,55 @@ def test_perspective_projection_kat(oracle):
     p = oracle.project_perspective(np.array([[0.5, 0.5, 0.0], [0.0, 0.0, 1.0]], np.float32), R[0], T[0], K00, K11)
     assert np.allclose(p[0], [-0.5 * K00 / 2.0, 0.5 * K00 / 2.0, 2.0], atol=1e-6)
     assert np.allclose(p[1], [0.0, 0.0, 1.0], atol=1e-6)
+
+
+def test_phong_shading_closed_form_kat(oracle):
+    """A large triangle in the world plane z = 0 facing the camera at (0, 0, 2.2), light direction (0.3, 0.2, 1): every
+    covered pixel has a closed-form colour -- ambient 0.5 + diffuse 0.3 (n.l) + specular 0.2 (v.r)^64 with
+    r = -l + 2 (n.l) n ([upstream] lighting.py / shading.py, constants of renderer.py:190-191), evaluated at the world
+    point the pixel centre back-projects to (which is what perspective-correct interpolation must reproduce).  Pins the
+    pixel grid (x left, y up), the FoV constants, the interpolation and the Phong constants independently of
+    torch_ref.py; float64 here, 1e-5 against the fp32 oracle."""
+    H = W = 32
+    v = np.array([[-3.0, -2.0, 0.0], [3.0, -2.0, 0.0], [0.0, 4.0, 0.0]], np.float32)
+    f = np.array([[0, 1, 2]], np.int32)
+    nrm = oracle.vertex_normals(v, f)
+    sign = float(np.sign(nrm[0, 2]))
+    assert np.allclose(nrm, [[0, 0, sign]] * 3, atol=1e-7) and sign != 0
+    if sign < 0:                                     # face the camera (+z): flip the winding
+        f = f[:, ::-1].copy(); nrm = oracle.vertex_normals(v, f)
+        assert np.allclose(nrm, [[0, 0, 1.0]] * 3, atol=1e-7)
+    d = 2.2
+    R, T, C = oracle.look_at([0.0], [0.0], [d])
+    light = np.array([[0.3, 0.2, 1.0]], np.float32)
+    rgb = np.array([0.9, 0.6, 0.3], np.float32); bg = np.array([0.1, 0.2, 0.7], np.float32)
+    o = oracle.mesh_forward(v, f, [0, 3], [0, 1], nrm, rgb, 1, R, T, C, light, bg, K00, K11, 0.5, H, W, 1, oracle.PERSPECTIVE_CORRECT)
+    img, p2f = o["images"][0], o["pix_to_face"][0, ..., 0]
+    assert (p2f >= 0).mean() > 0.5
+    l = light[0].astype(np.float64); l /= np.linalg.norm(l)
+    n = np.array([0.0, 0.0, 1.0])
+    k = float(K00)
+    worst = 0.0
+    for yi in range(H):
+        for xi in range(W):
+            xf = 1.0 - (2 * xi + 1) / W; yf = 1.0 - (2 * yi + 1) / H          # pixel centre in NDC: +x left, +y up
+            xv, yv = xf * d / k, yf * d / k                                    # view-space point on the plane z_v = d
+            P = np.array([-xv, yv, 0.0])                                       # R = diag(-1, 1, -1): world x = -view x
+            inside = (P[1] > -2.0) and (P[1] < 4.0 - 2.0 * abs(P[0]))          # the triangle's three edges
+            if not inside:
+                if p2f[yi, xi] < 0:
+                    assert np.allclose(img[:, yi, xi], bg, atol=1e-7)
+                continue
+            if p2f[yi, xi] < 0:
+                continue                                                       # a centre within rounding of an edge
+            cosang = float(n @ l)
+            vdir = np.array([0.0, 0.0, d]) - P; vdir /= np.linalg.norm(vdir)
+            r = -l + 2.0 * cosang * n
+            spec = 0.2 * max(float(vdir @ r), 0.0) ** 64
+            want = (0.5 + 0.3 * max(cosang, 0.0)) * rgb.astype(np.float64) + spec
+            worst = max(worst, float(np.abs(img[:, yi, xi] - want).max()))
+    assert worst <= 1e-5, worst
+    assert abs(o["zbuf"][0][p2f >= 0] - d).max() <= 1e-5                        # the whole plane lies at view depth d
 
 
 def test_near_plane_cull_counts_straddlers(oracle):
