@@ -382,6 +382,49 @@ def test_points_forward_backward_match_torch(oracle, mode, K):
     assert rel(pb["grad_rgb"][0], fd.grad.numpy()) < 2e-5
 
 
+def test_points_backward_matches_finite_differences(oracle):
+    """The point path's hand-derived chain -- d image -> alpha compositor -> dists2 -> projection (R, T, 1 / dist scale) ->
+    look_at backward -> d azim / elev / dist -- against central differences of the oracle's OWN forward (no torch_ref).
+    The scene is chosen so that the rendered loss is continuous in the camera: alpha compositing over a black background
+    (a covered pixel whose weights vanish meets the background continuously), K >= the depth complexity (front / back
+    pairs: no point is ever dropped from a pixel's K-list), well separated pairs.  Pixel centres entering or leaving a disc
+    leave kinks, hence the loose tolerance; a wrong factor (degrees, -1 / dist^2, a sign) is off by far more."""
+    rs = np.random.RandomState(5)
+    gx, gy = np.meshgrid(np.linspace(-0.75, 0.75, 4), np.linspace(-0.5, 0.5, 3))
+    front = np.stack([gx.ravel(), gy.ravel(), 0.15 + 0.1 * rs.rand(12)], 1)
+    back = front.copy(); back[:, 2] -= 0.35; back[:, :2] += 0.03 * rs.randn(12, 2)
+    pts = np.concatenate([front, back])[None].astype(np.float32)
+    M, H, rad, K = 3, 48, 0.08, 2
+    feat = rs.rand(1, pts.shape[1], 3).astype(np.float32)
+    bg = np.zeros(3, np.float32)
+    g = rs.randn(M, 3, H, H).astype(np.float32)
+    az0 = np.array([4.0, -9.0, 12.0]); el0 = np.array([3.0, 8.0, -6.0]); di0 = np.array([2.2, 2.4, 2.0])
+
+    def loss(az, el, di, want_grad=False):
+        R, T, _ = oracle.look_at(az, el, di)
+        inv = (1.0 / di).astype(np.float32)
+        o = oracle.points_forward(pts, feat, M, R, T, inv, rad, bg, H, H, K, oracle.COMPOSITE_ALPHA)
+        val = float((o["images"].astype(np.float64) * g).sum())
+        if not want_grad:
+            return val
+        assert (o["idx"][..., 1] >= 0).mean() > 0.02            # second layers are populated
+        b = oracle.points_backward(pts, feat, M, R, T, inv, rad, H, H, K, oracle.COMPOSITE_ALPHA, o["idx"], g)
+        ga, ge, gd = oracle.look_at_backward(az, el, di, b["gR"], b["gT"], np.zeros_like(b["gT"]))
+        return val, (ga, ge, gd + b["g_inv_dist"] * (-1.0 / di ** 2))      # dist also scales the cloud (renderer.py:142)
+
+    _, (ga, ge, gd) = loss(az0, el0, di0, want_grad=True)
+    for name, grad, h in (("azim", ga, 0.02), ("elev", ge, 0.02), ("dist", gd, 0.002)):
+        for i in range(M):
+            args = {"azim": az0.copy(), "elev": el0.copy(), "dist": di0.copy()}
+            args[name][i] += h
+            up = loss(args["azim"], args["elev"], args["dist"])
+            args[name][i] -= 2 * h
+            dn = loss(args["azim"], args["elev"], args["dist"])
+            fd = (up - dn) / (2 * h)
+            scale = max(abs(fd), float(np.abs(grad).max()), 1e-6)
+            assert abs(grad[i] - fd) <= 0.1 * scale, (name, i, float(grad[i]), fd)
+
+
 def test_point_projection_scales_by_inverse_distance(oracle):
     # renderer.py:141-143: the ONLY place dist enters an orthographic image is the 1/dist cloud scaling
     R, T, _ = oracle.look_at([0.0], [0.0], [2.0])
