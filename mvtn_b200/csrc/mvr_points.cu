@@ -431,8 +431,8 @@ __device__ __forceinline__ void insert_key_smem(unsigned long long* s_keys, int 
 }
 
 // grid: x = tile (ty * tiles_x + tx), y = view m, z = object b; dynamic shared memory: KT * 1024 keys
-template <int KT>
-__global__ void __launch_bounds__(MVR_THREADS) points_tile_kernel(const PointsParams p) {
+template <int KT, int MINB>
+__global__ void __launch_bounds__(MVR_THREADS, MINB) points_tile_kernel(const PointsParams p) {
   extern __shared__ unsigned long long s_keys[];              // [KT][1024]
   __shared__ unsigned int s_cand[PT_QCAP];                    // local point << 10 | local pixel
   __shared__ unsigned long long s_key[MVR_THREADS];
@@ -804,6 +804,11 @@ extern "C" size_t mvr_points_hit_mask_words(int B, int M, int H, int W) {
   return (size_t)B * M * H * ((W + 31) / 32);
 }
 
+// profiling knob: MVR_TILE_MINB=4 asks for four instead of five tile CTAs per SM at K = 4
+static int points_tile_minb() {
+  static const int v = [] { const char* e = getenv("MVR_TILE_MINB"); return (e && atoi(e) == 4) ? 4 : 5; }();
+  return v;
+}
 // profiling knob: MVR_POINTS_BIN_FUSED=0 keeps the three-launch binning everywhere
 static bool points_bin_fused() {
   static const bool v = [] { const char* e = getenv("MVR_POINTS_BIN_FUSED"); return !(e && atoi(e) == 0); }();
@@ -862,14 +867,18 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
     const size_t smem = (size_t)K * 1024 * sizeof(unsigned long long);
     cudaError_t e = cudaSuccess;
     switch (K) {
-      case 1: MVR_LAUNCH(points_tile_kernel<1>, tile_grid, MVR_THREADS, smem, st, p); break;
-      case 2: MVR_LAUNCH(points_tile_kernel<2>, tile_grid, MVR_THREADS, smem, st, p); break;
-      case 4: MVR_LAUNCH(points_tile_kernel<4>, tile_grid, MVR_THREADS, smem, st, p); break;
+      // five tile CTAs per SM (48-51 registers): the CTAs are short and latency-bound, occupancy is what hides their start-up
+      case 1: MVR_LAUNCH((points_tile_kernel<1, 5>), tile_grid, MVR_THREADS, smem, st, p); break;
+      case 2: MVR_LAUNCH((points_tile_kernel<2, 5>), tile_grid, MVR_THREADS, smem, st, p); break;
+      case 4:
+        if (points_tile_minb() == 4) MVR_LAUNCH((points_tile_kernel<4, 4>), tile_grid, MVR_THREADS, smem, st, p);
+        else MVR_LAUNCH((points_tile_kernel<4, 5>), tile_grid, MVR_THREADS, smem, st, p);
+        break;
       default: {
         // 64 KB of dynamic shared memory needs the opt-in (per device; the call is a few hundred nanoseconds)
-        e = cudaFuncSetAttribute(points_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(points_tile_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("mvr_points_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        MVR_LAUNCH(points_tile_kernel<8>, tile_grid, MVR_THREADS, smem, st, p);
+        MVR_LAUNCH((points_tile_kernel<8, 3>), tile_grid, MVR_THREADS, smem, st, p);
       }
     }
     return check_launch("points_tile_kernel");
