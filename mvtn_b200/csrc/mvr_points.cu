@@ -431,6 +431,7 @@ __device__ __forceinline__ void insert_key_smem(unsigned long long* s_keys, int 
 }
 
 // grid: x = tile (ty * tiles_x + tx), y = view m, z = object b; dynamic shared memory: KT * 1024 keys
+// MINB: minimum CTAs per SM for the register allocator; 0 = unconstrained
 template <int KT, int MINB>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) points_tile_kernel(const PointsParams p) {
   extern __shared__ unsigned long long s_keys[];              // [KT][1024]
@@ -804,6 +805,10 @@ extern "C" size_t mvr_points_hit_mask_words(int B, int M, int H, int W) {
   return (size_t)B * M * H * ((W + 31) / 32);
 }
 
+static int points_tile_minb_k1() {
+  static const int v = [] { const char* e = getenv("MVR_TILE_MINB_K1"); return (e && atoi(e) == 5) ? 5 : 4; }();
+  return v;
+}
 // profiling knob: MVR_TILE_MINB=4 asks for four instead of five tile CTAs per SM at K = 4
 static int points_tile_minb() {
   static const int v = [] { const char* e = getenv("MVR_TILE_MINB"); return (e && atoi(e) == 4) ? 4 : 5; }();
@@ -867,11 +872,17 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
     const size_t smem = (size_t)K * 1024 * sizeof(unsigned long long);
     cudaError_t e = cudaSuccess;
     switch (K) {
-      // five tile CTAs per SM (48-51 registers): the CTAs are short and latency-bound, occupancy is what hides their start-up
-      case 1: MVR_LAUNCH((points_tile_kernel<1, 5>), tile_grid, MVR_THREADS, smem, st, p); break;
-      case 2: MVR_LAUNCH((points_tile_kernel<2, 5>), tile_grid, MVR_THREADS, smem, st, p); break;
+      // Occupancy is what hides the start-up latency of these short CTAs (r2t, same box, K = 1: 40 registers / unconstrained
+      // 0.094 ms, 47 registers / 5 CTAs 0.102 ms, 55 registers / 4 CTAs 0.110 ms): K = 1 / 2 compile to 40 / 46 registers when
+      // left alone (MINB = 0), K = 4 is held to five CTAs per SM (48 registers instead of 56, no spills: 0.131 vs 0.133 ms),
+      // K = 8 to three (74 KB of shared memory per CTA).
+      case 1:
+        if (points_tile_minb_k1() == 5) MVR_LAUNCH((points_tile_kernel<1, 5>), tile_grid, MVR_THREADS, smem, st, p);
+        else MVR_LAUNCH((points_tile_kernel<1, 0>), tile_grid, MVR_THREADS, smem, st, p);
+        break;
+      case 2: MVR_LAUNCH((points_tile_kernel<2, 0>), tile_grid, MVR_THREADS, smem, st, p); break;
       case 4:
-        if (points_tile_minb() == 4) MVR_LAUNCH((points_tile_kernel<4, 4>), tile_grid, MVR_THREADS, smem, st, p);
+        if (points_tile_minb() == 4) MVR_LAUNCH((points_tile_kernel<4, 0>), tile_grid, MVR_THREADS, smem, st, p);
         else MVR_LAUNCH((points_tile_kernel<4, 5>), tile_grid, MVR_THREADS, smem, st, p);
         break;
       default: {
