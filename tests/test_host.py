@@ -269,3 +269,52 @@ def test_point_fragments_complete_the_sparse_idx_lazily():
     assert torch.equal(dense[hit], idx[hit])
     assert (dense[~hit] == -1).all()
     assert fr.get("idx") is dense and dict(fr.items())["idx"] is dense
+
+
+def test_mesh_workspace_hint_bookkeeping(monkeypatch):
+    """ops._ws_mesh: what the mesh path may assume about its workspace between calls (MVR_WS_* flags).  Pure host logic:
+    the stream accessor and the capture query are stubbed, the "workspace" is a CPU tensor."""
+    import torch
+    from mvtn_b200 import ops
+    L = _lib
+    monkeypatch.setattr(ops, "_stream", lambda device: 1234)
+    capturing = {"on": False}
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: capturing["on"])
+    dev = torch.device("cuda", 0)
+    key = (0, 1234)
+    ws = torch.empty(1 << 12, dtype=torch.uint8)
+    monkeypatch.setitem(ops._workspaces, key, ws)
+    ops._ws_mesh.pop(key, None)
+    layout = (2, 3, 64, 64, 1, 1000)
+    # cold: re-arm only; nothing is known while the call is in flight (it may raise before commit)
+    flags, commit = ops._ws_mesh_flags_forward(dev, ws, layout)
+    assert flags == L.WS_REARM_KEYS and key not in ops._ws_mesh
+    t1 = commit()
+    assert ops._ws_mesh_flags_backward(dev, ws, t1) == L.WS_PROJECTED
+    # warm, same layout: the memset is skipped
+    flags, commit = ops._ws_mesh_flags_forward(dev, ws, layout)
+    assert flags == L.WS_REARM_KEYS | L.WS_KEYS_ARMED
+    t2 = commit()
+    assert t2 != t1
+    # the backward of the OLDER forward re-projects and thereby invalidates the newer projection
+    assert ops._ws_mesh_flags_backward(dev, ws, t1) == 0
+    assert ops._ws_mesh_flags_backward(dev, ws, t2) == 0
+    # another layout, another buffer, a failed call, another user of the buffer: all cold again
+    flags, commit = ops._ws_mesh_flags_forward(dev, ws, (2, 3, 64, 64, 2, 1000)); commit()
+    assert flags == L.WS_REARM_KEYS
+    flags, commit = ops._ws_mesh_flags_forward(dev, torch.empty(1 << 12, dtype=torch.uint8), (2, 3, 64, 64, 2, 1000)); commit()
+    assert flags == L.WS_REARM_KEYS
+    flags, _no_commit = ops._ws_mesh_flags_forward(dev, ws, layout)            # the C call raised: commit never ran
+    flags, commit = ops._ws_mesh_flags_forward(dev, ws, layout); commit()
+    assert flags == L.WS_REARM_KEYS
+    assert ops.workspace(dev, 16, _mesh_owner=True) is ws and key in ops._ws_mesh
+    assert ops.workspace(dev, 16) is ws and key not in ops._ws_mesh             # e.g. the point path
+    # a stream that has been captured into a CUDA graph is never trusted again (replays bypass this bookkeeping)
+    flags, commit = ops._ws_mesh_flags_forward(dev, ws, layout); commit()
+    capturing["on"] = True
+    flags, commit = ops._ws_mesh_flags_forward(dev, ws, layout)
+    assert flags == 0 and commit() is None
+    capturing["on"] = False
+    flags, commit = ops._ws_mesh_flags_forward(dev, ws, layout)
+    assert flags == 0 and commit() is None and ops._ws_mesh_flags_backward(dev, ws, 7) == 0
+    ops._ws_mesh.pop(key, None)
