@@ -318,3 +318,19 @@ def test_mesh_workspace_hint_bookkeeping(monkeypatch):
     flags, commit = ops._ws_mesh_flags_forward(dev, ws, layout)
     assert flags == 0 and commit() is None and ops._ws_mesh_flags_backward(dev, ws, 7) == 0
     ops._ws_mesh.pop(key, None)
+
+
+def test_flag_constants_match_the_header():
+    """Every `#define MVR_<NAME> <int>` flag / counter slot of include/mvr_b200.h that the ctypes layer mirrors carries the
+    same value there (mvtn_b200/_lib.py), and the flag bits are pairwise disjoint."""
+    hdr = open(os.path.join(ROOT, "include", "mvr_b200.h")).read()
+    defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+MVR_([A-Z0-9_]+)\s+(0x[0-9a-fA-F]+|\d+)\b", hdr)}
+    assert defs["ABI_VERSION"] == _lib.ABI_VERSION
+    mirrored = [n for n in defs if hasattr(_lib, n) and n != "ABI_VERSION"]
+    assert {"PERSPECTIVE_CORRECT", "CULL_BACKFACES", "COMPOSITE_ALPHA", "RGB_PER_ELEMENT", "FACES_I64", "IMAGES_BF16", "SCALE_IS_DIST",
+            "WS_KEYS_ARMED", "WS_REARM_KEYS", "WS_PROJECTED", "IDX_SPARSE", "TEST_TINY_QUEUES", "NUM_COUNTERS"} <= set(mirrored)
+    for n in mirrored:
+        assert getattr(_lib, n) == defs[n], n
+    flags = [defs[n] for n in mirrored if n not in ("NUM_COUNTERS", "CNT_STRADDLE", "CNT_BIG_FACES")]
+    assert all(f & (f - 1) == 0 for f in flags)                   # single bits
+    assert len(set(flags)) == len(flags)                          # no two flags share a bit
