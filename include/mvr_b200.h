@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MVR_ABI_VERSION 4
+#define MVR_ABI_VERSION 5
 
 /* flags */
 #define MVR_PERSPECTIVE_CORRECT 1  /* [upstream] RasterizationSettings.perspective_correct (FoV persp.: True) */
@@ -124,6 +124,14 @@ int mvr_mesh_prepare(const float* verts, const void* faces, const int* vert_off,
 /* copy of the per-vertex unit normals (Vtot,3) out of a prepared geometry (tests / callers) */
 int mvr_mesh_get_normals(const void* geometry, int64_t total_verts, int64_t total_faces,
                          float* normals, void* stream);
+
+/* backward of the vertex normals ([upstream] meshes.py Meshes._compute_vertex_normals: per-corner area-weighted cross
+ * products, index_add, F.normalize(eps 1e-6)) for callers that want gradients w.r.t. mesh vertices: grad_normals (Vtot,3)
+ * = d loss / d unit normals (as accumulated by mvr_mesh_backward; CONSUMED -- overwritten with the gradient w.r.t. the
+ * un-normalised sums), grad_verts (Vtot,3) ACCUMULATED with atomics.  `geometry` as left by mvr_mesh_prepare. */
+int mvr_mesh_normals_backward(const void* geometry, const int* vert_off, const int* face_off, int B,
+                              int64_t total_verts, int64_t total_faces, int max_faces, float* grad_normals,
+                              float* grad_verts, void* stream);
 
 /* scratch for one forward or backward call: projected vertices of every view (16 B * M * total_verts), the
  * pixel-centre table, and the 64-bit key plane(s) / backward partial sums */

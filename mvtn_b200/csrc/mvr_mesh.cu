@@ -53,14 +53,73 @@ __global__ void geom_pack_faces_kernel(const IdxT* __restrict__ faces, const int
   i0 = min(max(i0, 0), V - 1); i1 = min(max(i1, 0), V - 1); i2 = min(max(i2, 0), V - 1);
   faces4[f0 + f] = make_int4(i0, i1, i2, 0);
   const float4 v0 = verts4[voff + i0], v1 = verts4[voff + i1], v2 = verts4[voff + i2];
-  // fn = cross(v2 - v1, v0 - v1), area-weighted
-  const float ax = v2.x - v1.x, ay = v2.y - v1.y, az = v2.z - v1.z;
-  const float bx = v0.x - v1.x, by = v0.y - v1.y, bz = v0.z - v1.z;
-  const double nx = (double)(ay * bz - az * by), ny = (double)(az * bx - ax * bz), nz = (double)(ax * by - ay * bx);
+  // [upstream] Meshes._compute_vertex_normals: one area-weighted cross product PER CORNER -- corner c adds
+  // (v_next - v_c) x (v_prev - v_c) to its vertex (the three are equal in exact arithmetic, ~1 ulp apart in fp32).
   // double accumulation: order-independent to ~1e-16, i.e. run-to-run identical after rounding to fp32
-  atomicAdd(nacc + 3 * (size_t)(voff + i0), nx); atomicAdd(nacc + 3 * (size_t)(voff + i0) + 1, ny); atomicAdd(nacc + 3 * (size_t)(voff + i0) + 2, nz);
-  atomicAdd(nacc + 3 * (size_t)(voff + i1), nx); atomicAdd(nacc + 3 * (size_t)(voff + i1) + 1, ny); atomicAdd(nacc + 3 * (size_t)(voff + i1) + 2, nz);
-  atomicAdd(nacc + 3 * (size_t)(voff + i2), nx); atomicAdd(nacc + 3 * (size_t)(voff + i2) + 1, ny); atomicAdd(nacc + 3 * (size_t)(voff + i2) + 2, nz);
+  const float4 vc[3] = {v0, v1, v2};
+  const int id[3] = {i0, i1, i2};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float4 o = vc[c], a = vc[(c + 1) % 3], b = vc[(c + 2) % 3];
+    const float ax = a.x - o.x, ay = a.y - o.y, az = a.z - o.z;
+    const float bx = b.x - o.x, by = b.y - o.y, bz = b.z - o.z;
+    double* dst = nacc + 3 * (size_t)(voff + id[c]);
+    atomicAdd(dst, (double)(ay * bz - az * by)); atomicAdd(dst + 1, (double)(az * bx - ax * bz)); atomicAdd(dst + 2, (double)(ax * by - ay * bx));
+  }
+}
+
+// ---- backward of the vertex normals (only when mesh vertices require grad): d/d unit normals -> d/d verts ----
+// n_v = s_v / max(|s_v|, 1e-6), s_v = sum over the corners at v of (v_next - v_c) x (v_prev - v_c).
+// pass 1 (thread / vertex): g_s = normalize_bwd(s, g_n), in place over grad_normals;
+// pass 2 (thread / face):   per corner with a = v_next - v_c, b = v_prev - v_c: g_a = b x g_s, g_b = g_s x a,
+//                           v_next += g_a, v_prev += g_b, v_c -= g_a + g_b  (float atomics: tolerance-compared).
+__global__ void geom_normals_bwd_vertex_kernel(const double* __restrict__ nacc, int64_t tv, float* __restrict__ gn) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= tv) return;
+  const float x = (float)nacc[3 * v], y = (float)nacc[3 * v + 1], z = (float)nacc[3 * v + 2];
+  const float gx = gn[3 * v], gy = gn[3 * v + 1], gz = gn[3 * v + 2];
+  const float n = sqrtf((x * x + y * y) + z * z);
+  float ox, oy, oz;
+  if (n > 1e-6f) {
+    const float inv = 1.0f / n, ux = x * inv, uy = y * inv, uz = z * inv;
+    const float d = ux * gx + uy * gy + uz * gz;
+    ox = (gx - ux * d) * inv; oy = (gy - uy * d) * inv; oz = (gz - uz * d) * inv;
+  } else {
+    ox = gx * 1e6f; oy = gy * 1e6f; oz = gz * 1e6f;
+  }
+  gn[3 * v] = ox; gn[3 * v + 1] = oy; gn[3 * v + 2] = oz;
+}
+
+__global__ void geom_normals_bwd_face_kernel(const int4* __restrict__ faces4, const int* __restrict__ vert_off,
+                                             const int* __restrict__ face_off, const float4* __restrict__ verts4,
+                                             const float* __restrict__ gs, float* __restrict__ grad_verts) {
+  const int b = blockIdx.y;
+  const int f0 = face_off[b], F = face_off[b + 1] - f0;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const int voff = vert_off[b];
+  const int4 fi = faces4[f0 + f];
+  const int id[3] = {fi.x, fi.y, fi.z};
+  const float4 vc[3] = {verts4[voff + fi.x], verts4[voff + fi.y], verts4[voff + fi.z]};
+  float acc[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int nx = (c + 1) % 3, pr = (c + 2) % 3;
+    const float* g = gs + 3 * (size_t)(voff + id[c]);
+    const float gx = g[0], gy = g[1], gz = g[2];
+    const float ax = vc[nx].x - vc[c].x, ay = vc[nx].y - vc[c].y, az = vc[nx].z - vc[c].z;
+    const float bx = vc[pr].x - vc[c].x, by = vc[pr].y - vc[c].y, bz = vc[pr].z - vc[c].z;
+    const float gax = by * gz - bz * gy, gay = bz * gx - bx * gz, gaz = bx * gy - by * gx;      // b x g
+    const float gbx = gy * az - gz * ay, gby = gz * ax - gx * az, gbz = gx * ay - gy * ax;      // g x a
+    acc[nx][0] += gax; acc[nx][1] += gay; acc[nx][2] += gaz;
+    acc[pr][0] += gbx; acc[pr][1] += gby; acc[pr][2] += gbz;
+    acc[c][0] -= gax + gbx; acc[c][1] -= gay + gby; acc[c][2] -= gaz + gbz;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float* o = grad_verts + 3 * (size_t)(voff + id[c]);
+    atomicAdd(o, acc[c][0]); atomicAdd(o + 1, acc[c][1]); atomicAdd(o + 2, acc[c][2]);
+  }
 }
 
 __global__ void geom_finish_normals_kernel(const double* __restrict__ nacc, int64_t tv, const float4* __restrict__ verts4,
@@ -554,6 +613,24 @@ extern "C" int mvr_mesh_get_normals(const void* geometry, int64_t total_verts, i
   const GeomLayout g = geom_layout(total_verts, total_faces);
   MVR_LAUNCH(geom_get_normals_kernel, (unsigned)((total_verts + 255) / 256), 256, 0, (cudaStream_t)stream, (const float4*)((const char*)geometry + g.normals4), total_verts, normals);
   return check_launch("mvr_mesh_get_normals");
+}
+
+extern "C" int mvr_mesh_normals_backward(const void* geometry, const int* vert_off, const int* face_off, int B,
+                                         int64_t total_verts, int64_t total_faces, int max_faces, float* grad_normals,
+                                         float* grad_verts, void* stream) {
+  if (B < 0 || total_verts < 0 || total_faces < 0 || max_faces < 0) { set_error("mvr_mesh_normals_backward: negative size"); return -1; }
+  if (B == 0 || total_verts == 0) return 0;
+  if (!geometry || !vert_off || !face_off || !grad_normals || !grad_verts) { set_error("mvr_mesh_normals_backward: null pointer"); return -2; }
+  const GeomLayout g = geom_layout(total_verts, total_faces);
+  const char* gb = (const char*)geometry;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tb = 256;
+  MVR_LAUNCH(geom_normals_bwd_vertex_kernel, (unsigned)((total_verts + tb - 1) / tb), tb, 0, st, (const double*)(gb + g.nacc), total_verts, grad_normals);
+  if (total_faces > 0 && max_faces > 0) {
+    dim3 grid((max_faces + tb - 1) / tb, B);
+    MVR_LAUNCH(geom_normals_bwd_face_kernel, grid, tb, 0, st, (const int4*)(gb + g.faces4), vert_off, face_off, (const float4*)(gb + g.verts4), (const float*)grad_normals, grad_verts);
+  }
+  return check_launch("mvr_mesh_normals_backward");
 }
 
 extern "C" size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K, int64_t total_verts) {

@@ -306,7 +306,7 @@ __device__ __forceinline__ void backward_clipped_view(const MeshBwdParams& p, in
 // (coalesced 64-byte rows), then 16 threads add the 16 group sums (and the clipped part) in a fixed order.
 __global__ void __launch_bounds__(MVR_THREADS) mesh_backward_finish_kernel(const MeshBwdParams p, float* __restrict__ gR,
                                                                            float* __restrict__ gT, float* __restrict__ gC) {
-  __shared__ float s_sum[MVR_THREADS];
+  __shared__ double s_sum[MVR_THREADS];
   __shared__ float s_red[(MVR_THREADS / 32) * 16];
   const int n = blockIdx.x, tid = threadIdx.x;
   const bool clip = may_clip(p.wsflags);      // block-uniform
@@ -317,18 +317,21 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_backward_finish_kernel(const
     backward_clipped_view(p, n, acc);
     block_sum<16>(acc, s_red);                // s_red[0..15] = the clipped pixels' totals
   }
+  // the per-warp partials (tens to hundreds per view, of mixed sign) are summed in fp64: free here, and it removes the
+  // one accumulation level whose operands are large next to the result
   const int v = tid & 15, grp = tid >> 4;
-  float s = 0.f;
-  for (int t = grp; t < p.parts_per_view; t += MVR_THREADS / 16) s += p.partials[((size_t)n * p.parts_per_view + t) * 16 + v];
+  double s = 0.0;
+  for (int t = grp; t < p.parts_per_view; t += MVR_THREADS / 16) s += (double)p.partials[((size_t)n * p.parts_per_view + t) * 16 + v];
   s_sum[tid] = s;
   __syncthreads();
   if (tid < 16) {
-    float tot = clip ? s_red[tid] : 0.f;
+    double tot = clip ? (double)s_red[tid] : 0.0;
 #pragma unroll
     for (int g = 0; g < MVR_THREADS / 16; ++g) tot += s_sum[g * 16 + tid];
-    if (tid < 9) gR[9 * (size_t)n + tid] = tot;
-    else if (tid < 12) gT[3 * (size_t)n + tid - 9] = tot;
-    else if (tid < 15) gC[3 * (size_t)n + tid - 12] = tot;
+    const float out = (float)tot;
+    if (tid < 9) gR[9 * (size_t)n + tid] = out;
+    else if (tid < 12) gT[3 * (size_t)n + tid - 9] = out;
+    else if (tid < 15) gC[3 * (size_t)n + tid - 12] = out;
   }
 }
 

@@ -354,6 +354,20 @@ class HostPackedMeshes:
     def __len__(self):
         return len(self.num_verts)
 
+    def is_pinned(self):
+        return self.verts.is_pinned() and self.faces.is_pinned() and self.offs.is_pinned()
+
+    def pin_memory(self):
+        """Pinned copy (or self when already pinned).  torch's DataLoader(pin_memory=True) calls this on the batch in its
+        pin thread of the MAIN process: batches collated in forked workers come back through shared memory, un-pinned
+        (workers must not touch CUDA), and are pinned here, off the training step."""
+        if self.is_pinned():
+            return self
+        hp = HostPackedMeshes.__new__(HostPackedMeshes)
+        hp.__dict__.update(self.__dict__)
+        hp.verts, hp.faces, hp.offs = self.verts.pin_memory(), self.faces.pin_memory(), self.offs.pin_memory()
+        return hp
+
     def verts_list(self):
         return list(torch.split(self.verts, self.num_verts))
 
@@ -361,10 +375,22 @@ class HostPackedMeshes:
         return list(torch.split(self.faces, self.num_faces))
 
 
-def collate_meshes(meshes, pin_memory: bool = True, vert_rgb: Optional[torch.Tensor] = None) -> HostPackedMeshes:
-    """Pack a list of meshes (objects with verts_list()/faces_list(), or (verts, faces) pairs) into one pinned
+def _in_loader_worker() -> bool:
+    try:
+        from torch.utils.data import get_worker_info
+        return get_worker_info() is not None
+    except Exception:
+        return False
+
+
+def collate_meshes(meshes, pin_memory: Optional[bool] = None, vert_rgb: Optional[torch.Tensor] = None) -> HostPackedMeshes:
+    """Pack a list of meshes (objects with verts_list()/faces_list(), or (verts, faces) pairs) into one
     HostPackedMeshes with the library's multi-threaded gather (int64 faces are narrowed to int32).  Host only: usable
-    inside DataLoader workers."""
+    as a DataLoader collate_fn.
+    pin_memory=None (default): pinned when called in the main process with CUDA available, pageable inside a DataLoader
+    worker -- a forked worker must not initialise CUDA (run_mvtn.py:110 uses num_workers=6), and its batch travels back
+    through shared memory anyway; DataLoader(pin_memory=True) then pins it via HostPackedMeshes.pin_memory() in the main
+    process, and PackedMeshes.from_host_packed stages whatever is still pageable through a reusable pinned buffer."""
     from .structures import unpack_mesh_list
     verts, faces = unpack_mesh_list(meshes)
     if len(verts) != len(faces):
@@ -374,7 +400,9 @@ def collate_meshes(meshes, pin_memory: bool = True, vert_rgb: Optional[torch.Ten
             raise ValueError("verts must be (V,3) and faces (F,3)")
     nv = [int(v.shape[0]) for v in verts]
     nf = [int(f.shape[0]) for f in faces]
-    pin = bool(pin_memory) and torch.cuda.is_available()
+    if pin_memory is None:
+        pin_memory = not _in_loader_worker()
+    pin = bool(pin_memory) and not _in_loader_worker() and torch.cuda.is_available()
     v_host = torch.empty((sum(nv), 3), dtype=torch.float32, pin_memory=pin)
     f_host = torch.empty((sum(nf), 3), dtype=torch.int32, pin_memory=pin)
     if len(verts):
@@ -493,6 +521,20 @@ class PackedMeshes:
         if device.type != "cuda":
             raise L.MVRError("PackedMeshes needs a CUDA device: mvtn_b200 has no CPU path")
         self = cls.__new__(cls)
+        if not hp.is_pinned():
+            # a batch that came out of a DataLoader worker without DataLoader(pin_memory=True): copy it into reusable pinned
+            # staging buffers first, so that the H2D below is still asynchronous (a pageable source would block the host)
+            src = hp
+            hp = HostPackedMeshes.__new__(HostPackedMeshes)
+            hp.__dict__.update(src.__dict__)
+            v_st = _staging("hp_verts", device, src.verts.numel(), torch.float32).view(-1, 3)
+            f_st = _staging("hp_faces", device, src.faces.numel(), torch.int32).view(-1, 3)
+            o_st = _staging("hp_offs", device, src.offs.numel(), torch.int32)
+            v_st.copy_(src.verts); f_st.copy_(src.faces); o_st.copy_(src.offs)
+            hp.verts, hp.faces, hp.offs = v_st, f_st, o_st
+            staged = True
+        else:
+            staged = False
         if copy_stream:
             cur = torch.cuda.current_stream(device)
             cs = _copy_streams.get(device.index)
@@ -509,6 +551,8 @@ class PackedMeshes:
             v_dev = hp.verts.to(device, non_blocking=True)
             f_dev = hp.faces.to(device, non_blocking=True)
             offs = hp.offs.to(device, non_blocking=True)
+        if staged:
+            _staging_done(device)
         self._init_packed(v_dev, f_dev, hp.num_verts, hp.num_faces, device,
                           vert_rgb if vert_rgb is not None else hp.vert_rgb,
                           offsets=(hp.vert_off_host, hp.face_off_host, offs))
@@ -593,15 +637,6 @@ class PackedMeshes:
         return out
 
 
-def vertex_normals_torch(verts: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:
-    """Differentiable area-weighted vertex normals ([upstream] Meshes._compute_vertex_normals).  Used only to chain
-    d/d normals -> d/d verts when mesh vertices require grad; the forward normals come from mvr_mesh_prepare."""
-    vf = verts[faces]
-    fn = torch.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1], dim=1)
-    vn = torch.zeros_like(verts).index_add(0, faces[:, 0], fn).index_add(0, faces[:, 1], fn).index_add(0, faces[:, 2], fn)
-    return torch.nn.functional.normalize(vn, eps=1e-6, dim=1)
-
-
 # --------------------------------------------------------------------------------------------------
 # mesh rendering
 # --------------------------------------------------------------------------------------------------
@@ -674,12 +709,12 @@ def _mesh_backward_launch(geom: "PackedMeshes", M, cfg, saved, g_images, want_ve
                                       _ptr(g_images), _ptr(gR), _ptr(gT), _ptr(gC), _ptr(gV), _ptr(gN), _ptr(ws),
                                       ws.numel(), _stream(dev)), "mvr_mesh_backward")
     if gV is not None:
-        # the kernel returns d/d verts through projection + interpolated position, and d/d unit normals;
-        # the normals -> verts chain ([upstream] Meshes._compute_vertex_normals) is optional plumbing in torch
-        with torch.enable_grad():
-            v = geom.verts.detach().requires_grad_()
-            (gv2,) = torch.autograd.grad(vertex_normals_torch(v, geom.faces_global()), v, gN)
-        gV = gV + gv2
+        # the kernel returned d/d verts through projection + interpolated position, and d/d unit normals; the
+        # normals -> verts chain ([upstream] Meshes._compute_vertex_normals) is mvr_mesh_normals_backward
+        with _on(dev):
+            L.check(lib.mvr_mesh_normals_backward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B,
+                                                  geom.total_verts, geom.total_faces, geom.max_faces, _ptr(gN), _ptr(gV),
+                                                  _stream(dev)), "mvr_mesh_normals_backward")
     return gR, gT, gC, gV
 
 

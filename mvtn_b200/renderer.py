@@ -30,6 +30,8 @@ def _device_vec(values, device):
             tkey = ("tuple", device.index, values)
             hit = _small_cache.get(tkey)
             if hit is None:
+                if len(_small_cache) > 256:      # a fresh random light per training step lands here: bounded
+                    _small_cache.clear()
                 hit = torch.as_tensor(values, dtype=torch.float32).to(device)
                 _small_cache[tkey] = hit
             return hit
@@ -100,8 +102,10 @@ class MVRenderer(nn.Module):
             backward) is captured once per (B, N, views-require-grad) and replayed with ONE launch per direction: the
             point path at small batches is launch-bound (BASELINE configs[0], one cloud x 12 views: 0.470 -> 0.356 ms per
             end-to-end step, r2m); at 32 clouds the eager step is already GPU-bound and the copies into the captured buffers
-            make this mode slower (0.516 -> 0.590 ms): leave it off there.  Needs one object colour and fixed shapes; anything else (per-point colours, invalid rotations, new shapes being captured) takes the eager
-            path.  In this mode `cameras` holds detached copies and `last_fragments` is None.
+            make this mode slower (0.516 -> 0.590 ms): leave it off there.  Needs one object colour and fixed shapes; anything else (per-point colours, invalid rotations, torch.no_grad()) takes the eager
+            path.  In this mode `cameras` holds detached copies, `last_fragments` is None and the images are a copy of the
+            captured buffer; the tensors the captured backward reads are static, so at most ONE forward may be outstanding
+            per backward (two forwards of the same shapes before a backward would overwrite the first one's saved state).
         cache_geometry: keep the packed device geometry of the last mesh batch and reuse it when the
             same list object is rendered again.
         normalize: None or (mean, std) (3-vectors or scalars): the kernels write (image - mean) / std, the
@@ -160,13 +164,24 @@ class MVRenderer(nn.Module):
         R, T, C, bad = ops._LookAt.apply(azim, elev, dist)      # flattens (B, M) -> B*M itself, flat order b*M + m
         return azim, elev, dist, R, T, C, bad
 
-    def _render_with_guard(self, azim, elev, dist, device, render):
+    def _render_with_guard(self, azim, elev, dist, device, render, known_invalid=False):
         """The validity flag travels to pinned host memory right behind the look_at kernel and is awaited through an
         event recorded BEFORE the render is enqueued: the host check of util.py:403-420 (which the reference pays as a
-        full device sync on every call) waits only for the camera kernel, never for the rasterizer."""
+        full device sync on every call) waits only for the camera kernel, never for the rasterizer.
+        known_invalid: the caller's fast path has already seen the flag raised for these angles -- go straight to the
+        redraw loop instead of rasterizing the rejected cameras once more.  `render` receives the camera centres of the
+        ORIGINAL angles as its last argument: the reference evaluates the "relative" light once, before any redraw
+        (renderer.py:168,190)."""
         azim, elev, dist, R, T, C, bad = self._cameras(azim, elev, dist, device)
-        invalid = _flag_reader(bad)
-        out = render(R, T, C, dist)
+        C_light = C.detach()
+        render_ = render
+        render = lambda R_, T_, C_, d_: render_(R_, T_, C_, d_, C_light)
+        if known_invalid:
+            invalid = lambda: 1
+            out = None
+        else:
+            invalid = _flag_reader(bad)
+            out = render(R, T, C, dist)
         exhastion = 0
         while invalid() != 0:
             exhastion += 1
@@ -192,9 +207,9 @@ class MVRenderer(nn.Module):
         obj = None if geom.per_vertex_rgb else _device_vec(color, device)
         fixed_light = None if lights is None else _device_vec(lights, device)
 
-        def render(R, T, C, dist_):
+        def render(R, T, C, dist_, C_light):
             geom.finish()
-            light = C.detach() if fixed_light is None else fixed_light
+            light = C_light if fixed_light is None else fixed_light
             return ops.render_meshes(geom, self.nb_views, R, T, C, light, obj, bg, self.image_size,
                                      faces_per_pixel=self.faces_per_pixel, cull_backfaces=self.cull_backfaces,
                                      perspective_correct=self.perspective_correct, verts=getattr(geom, "grad_verts", None),
@@ -202,12 +217,12 @@ class MVRenderer(nn.Module):
 
         try:
             out = None
+            reader = []
             if getattr(geom, "grad_verts", None) is None:
                 # fast path: cameras + rasterizer as ONE autograd node (ops.render_meshes_from_angles); the validity flag
                 # is still awaited through an event recorded between the camera kernel and the rasterizer
                 az, el, di = self._views(azim, elev, dist, device)
                 geom.finish()
-                reader = []
                 images, (R, T, C, _bad), frag = ops.render_meshes_from_angles(
                     geom, self.nb_views, az, el, di, fixed_light, obj, bg, self.image_size,
                     faces_per_pixel=self.faces_per_pixel, cull_backfaces=self.cull_backfaces,
@@ -216,7 +231,7 @@ class MVRenderer(nn.Module):
                 if reader[0]() == 0:
                     out = (images, frag)
             if out is None:      # vertex gradients wanted, or invalid rotations: the general path with the redraw loop
-                out, R, T, C = self._render_with_guard(azim, elev, dist, device, render)
+                out, R, T, C = self._render_with_guard(azim, elev, dist, device, render, known_invalid=bool(reader))
             images, frag = out
         finally:
             geom.finish()      # never leave a deferred / in-flight staging behind (e.g. when the cameras were rejected)
@@ -232,7 +247,7 @@ class MVRenderer(nn.Module):
             raise ValueError(f"{points.shape[0]} clouds but azim has batch {azim.shape[0]}")
         bg = _device_vec(background_color, device)
         rgb = torch.as_tensor(color, dtype=torch.float32)
-        if self.cuda_graph and rgb.numel() == 3:
+        if self.cuda_graph and rgb.numel() == 3 and torch.is_grad_enabled():      # under no_grad the eager path runs
             az, el, di = self._views(azim, elev, dist, device)
             out = self._render_points_graphed(points, _device_vec(rgb, device), az, el, di, bg, device)
             if out is not None:
@@ -243,7 +258,7 @@ class MVRenderer(nn.Module):
         else:
             rgb = rgb.to(device) * torch.ones_like(pts)          # renderer.py:119-120 features = color * ones_like(points)
 
-        def render(R, T, C, dist_):
+        def render(R, T, C, dist_, _C_light=None):
             # renderer.py:142 point_cloud.scale_(1/dist): the reciprocal is taken inside the kernels (dist=)
             return ops.render_points(pts, rgb, self.nb_views, R, T, None, self.points_radius, bg, self.image_size,
                                      points_per_pixel=self.points_per_pixel, compositor=self.compositor,
@@ -258,7 +273,7 @@ class MVRenderer(nn.Module):
             points_per_pixel=self.points_per_pixel, compositor=self.compositor, normalize=self.normalize,
             out_dtype=self.out_dtype, after_cameras=lambda bad: reader.append(_flag_reader(bad)))
         if reader[0]() != 0:      # invalid rotations: the general path with the redraw loop
-            (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render)
+            (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render, known_invalid=True)
         self.last_fragments = frag
         rendered_images = images.view(pts.shape[0], self.nb_views, 3, self.image_size, self.image_size)
         return rendered_images, FoVOrthographicCameras(R, T, C, znear=0.01)
@@ -294,7 +309,10 @@ class MVRenderer(nn.Module):
             return None
         self.last_fragments = None
         R, T, C = cams[: 9 * n].view(n, 3, 3), cams[9 * n: 12 * n].view(n, 3), cams[12 * n:].view(n, 3)
-        rendered_images = images.view(points.shape[0], self.nb_views, 3, self.image_size, self.image_size)
+        # a copy, not a view of the captured output buffer: images kept by the caller (logging, two renders per loss)
+        # survive the next replay.  What the captured BACKWARD reads (idx, hit mask, cameras) stays static: one
+        # outstanding forward per backward -- call backward() before the next forward() of the same shapes.
+        rendered_images = images.clone().view(points.shape[0], self.nb_views, 3, self.image_size, self.image_size)
         return rendered_images, FoVOrthographicCameras(R, T, C, znear=0.01)
 
     def _packed(self, meshes, color, device):

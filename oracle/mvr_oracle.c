@@ -583,16 +583,23 @@ void orc_rasterize_meshes_backward(const float* face_verts, const int* pix_to_fa
 /* ------------------------------------------------------------------------------------------ */
 void orc_vertex_normals(const float* verts, const int* faces, int V, int F, float* normals) {
   memset(normals, 0, sizeof(float) * 3 * (size_t)V);
-  for (int i = 0; i < 3; ++i)         /* three successive index_add passes, face order */
+  /* upstream runs three successive index_add passes in face order, one per CORNER, each with that corner's own
+   * cross product (equal in exact arithmetic, ~1 ulp apart in fp32):
+   *   faces[:,1] += (v2 - v1) x (v0 - v1);  faces[:,2] += (v0 - v2) x (v1 - v2);  faces[:,0] += (v1 - v0) x (v2 - v0) */
+  static const int corner[3] = {1, 2, 0};
+  for (int pass = 0; pass < 3; ++pass) {
+    const int c = corner[pass], n = (c + 1) % 3, pr = (c + 2) % 3;
     for (int f = 0; f < F; ++f) {
-      const float* v0 = verts + 3 * (size_t)faces[3 * f], *v1 = verts + 3 * (size_t)faces[3 * f + 1],
-                 *v2 = verts + 3 * (size_t)faces[3 * f + 2];
-      const float a[3] = {v2[0] - v1[0], v2[1] - v1[1], v2[2] - v1[2]};
-      const float b[3] = {v0[0] - v1[0], v0[1] - v1[1], v0[2] - v1[2]};
+      const float* vc = verts + 3 * (size_t)faces[3 * f + c];
+      const float* vn = verts + 3 * (size_t)faces[3 * f + n];
+      const float* vp = verts + 3 * (size_t)faces[3 * f + pr];
+      const float a[3] = {vn[0] - vc[0], vn[1] - vc[1], vn[2] - vc[2]};
+      const float b[3] = {vp[0] - vc[0], vp[1] - vc[1], vp[2] - vc[2]};
       float fn[3]; cross3(a, b, fn);
-      float* o = normals + 3 * (size_t)faces[3 * f + i];
+      float* o = normals + 3 * (size_t)faces[3 * f + c];
       o[0] += fn[0]; o[1] += fn[1]; o[2] += fn[2];
     }
+  }
   for (int v = 0; v < V; ++v) { float t[3]; normalize3(normals + 3 * v, 1e-6f, t); memcpy(normals + 3 * v, t, 12); }
 }
 

@@ -109,9 +109,11 @@ def rasterize_meshes_naive(face_verts, H, W, K=1, perspective_correct=True, cull
 def vertex_normals(verts, faces):
     """[upstream] Meshes._compute_vertex_normals (v0.7 form)."""
     vf = verts[faces]
-    fn = torch.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1], dim=1)
     vn = torch.zeros_like(verts)
-    vn = vn.index_add(0, faces[:, 0], fn).index_add(0, faces[:, 1], fn).index_add(0, faces[:, 2], fn)
+    # one cross product per corner, three index_add passes in upstream's order (corner 1, 2, 0)
+    vn = vn.index_add(0, faces[:, 1], torch.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1], dim=1))
+    vn = vn.index_add(0, faces[:, 2], torch.cross(vf[:, 0] - vf[:, 2], vf[:, 1] - vf[:, 2], dim=1))
+    vn = vn.index_add(0, faces[:, 0], torch.cross(vf[:, 1] - vf[:, 0], vf[:, 2] - vf[:, 0], dim=1))
     return F.normalize(vn, eps=1e-6, dim=1)
 
 
