@@ -1,15 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- rendered views/sec (forward + backward) of the MVRenderer hot path on N B200s.
 
-Workload (config.workload): BASELINE.json configs[1] -- mesh rendering of synthetic ~10k-face meshes,
-batch 32 x 12 views per GPU, 224x224, Phong shading, forward + backward (gradients to azim/elev/dist).
-`--workload points` switches to configs[2] (2048-pt clouds, alpha compositing) for exploration.
+Main record (the contract's `value`): BASELINE.json configs[1] -- mesh rendering of synthetic ~10k-face meshes, batch 32 x 12
+views per GPU, 224x224, Phong shading, forward + backward (gradients to azim / elev / dist).
+
+`extra` (same JSON line): one sub-record per remaining BASELINE configuration, each with its own throughput, `roofline`,
+and -- on rank 0 at N = 1 -- `cpu_baseline` (stated sub-sample) and `parity` gates:
+  c1_points   configs[0]  1 cloud x 12 circular views, 2048 pts, 224^2, K = 1, norm-weighted (launch-bound: L2 flushed between steps)
+  c3_points   configs[2]  32 clouds x 12 learned_spherical views, 2048 pts, alpha compositing K = 4
+  c5_mesh     configs[4]  8 meshes x 20 views, 400^2, ~100k faces
+  c5_points   configs[4]  8 clouds x 20 views, 400^2, 16384 pts
+  c2_strong   SURVEY 8e   configs[1] with 32 objects IN TOTAL split over the N ranks (strong scaling row; N > 1 only)
+  c4_train    configs[3]  MVTN view selector + MVCNN (ResNet-18) training step around the renderer, 32 objects x 12 views per
+                          GPU, NCCL gradient all-reduce overlapped with backward (examples/train_step.py)
 
 One JSON line on rank 0 (contract in the task statement):
   value      whole-job views/s (forward + backward) with inputs resident in HBM (device-timed, max over ranks)
-  forward_only  the same for the forward pass alone
   e2e        same metric through MVRenderer.forward/backward from HOST buffers (H2D + D2H inside)
-  roofline   dominant kernel: algorithmic bytes per launch / CUDA-event time vs measured HBM peak
+  roofline   dominant kernel: algorithmic bytes per launch / CUDA-event time vs measured HBM peak, plus the step-level and
+             per-kernel figures (DRAM bytes from the committed ncu captures, profiles/traffic.json)
   cpu_baseline  the CPU oracle timed on this box's host cores on a bounded sample (rank 0, N=1)
 `--impl reference` times the reference's CPU implementation of the path: PyTorch3D cannot be installed
 here (no network, not vendored), so this arm runs the oracle port with all host threads.
@@ -39,25 +48,71 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mesh", choices=["mesh", "points"])
-    ap.add_argument("--batch", type=int, default=32, help="objects per GPU")
-    ap.add_argument("--views", type=int, default=12)
-    ap.add_argument("--image-size", type=int, default=224)
-    ap.add_argument("--faces", type=int, default=10000)
-    ap.add_argument("--points", type=int, default=2048)
-    ap.add_argument("--points-per-pixel", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=None, help="objects per GPU (default 32)")
+    ap.add_argument("--views", type=int, default=None)
+    ap.add_argument("--image-size", type=int, default=None)
+    ap.add_argument("--faces", type=int, default=None)
+    ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--points-per-pixel", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="replay the device-resident step from two captured CUDA graphs (mvtn_b200.graphs)")
-    ap.add_argument("--cpu-sample-objects", type=int, default=0, help="0 = size the sample for ~10-20 s")
+    ap.add_argument("--cpu-sample-objects", type=int, default=0, help="0 = size the sample for ~8 s")
+    ap.add_argument("--extras", default="auto", choices=["auto", "all", "none", "tiny"],
+                    help="auto: the BASELINE sub-records when the main workload is the default one; tiny: shrunken (tests)")
+    ap.add_argument("--only", default=None, help="comma list of extra record names to run (default: all of them)")
     return ap.parse_args()
 
 
-def workload_name(a):
+# ---------------------------------------------------------------------------------------------------
+# workload specifications (BASELINE.json configs)
+def main_spec(a):
+    custom = any(x is not None for x in (a.batch, a.views, a.image_size, a.faces, a.points, a.points_per_pixel)) or a.workload != "mesh"
     if a.workload == "mesh":
-        return (f"mesh fwd+bwd: {a.batch} objects/GPU x {a.views} views, ~{a.faces}-face synthetic meshes, "
-                f"{a.image_size}x{a.image_size}, Phong, faces_per_pixel=1 (BASELINE configs[1])")
-    return (f"points fwd+bwd: {a.batch} clouds/GPU x {a.views} learned_spherical views, {a.points} pts, "
-            f"{a.image_size}x{a.image_size}, alpha compositing K={a.points_per_pixel} (BASELINE configs[2])")
+        s = dict(name="c2_mesh", kind="mesh", batch=a.batch or 32, views=a.views or 12, S=a.image_size or 224,
+                 faces=a.faces or 10000, view_kind="circular", baseline="configs[1]")
+    else:
+        s = dict(name="c3_points", kind="points", batch=a.batch or 32, views=a.views or 12, S=a.image_size or 224,
+                 points=a.points or 2048, K=a.points_per_pixel or 4, compositor="alpha", view_kind="learned_spherical",
+                 baseline="configs[2]")
+    return finalize(s), custom
+
+
+def finalize(s):
+    """Workloads whose per-step tensors fit the 126 MB L2 are timed with the L2 flushed between steps (timing rules)."""
+    s.setdefault("flush_l2", s["batch"] * s["views"] * s["S"] * s["S"] * (12 + 12 + 4) < (126 << 20))
+    return s
+
+
+def extra_specs(mode):
+    t = mode == "tiny"
+    return [finalize(x) for x in [
+        dict(name="c1_points", kind="points", batch=1, views=12 if not t else 3, S=224 if not t else 64, points=2048 if not t else 256,
+             K=1, compositor="norm", view_kind="circular", baseline="configs[0]"),
+        dict(name="c3_points", kind="points", batch=32 if not t else 2, views=12 if not t else 3, S=224 if not t else 64,
+             points=2048 if not t else 256, K=4, compositor="alpha", view_kind="learned_spherical", baseline="configs[2]"),
+        dict(name="c5_mesh", kind="mesh", batch=8 if not t else 1, views=20 if not t else 2, S=400 if not t else 80,
+             faces=100000 if not t else 1500, view_kind="spherical", baseline="configs[4]"),
+        dict(name="c5_points", kind="points", batch=8 if not t else 1, views=20 if not t else 2, S=400 if not t else 80,
+             points=16384 if not t else 512, K=4, compositor="alpha", view_kind="spherical", baseline="configs[4]"),
+    ]]
+
+
+def describe(s):
+    if s["kind"] == "mesh":
+        return (f"mesh fwd+bwd: {s['batch']} objects/GPU x {s['views']} {s['view_kind']} views, ~{s['faces']}-face synthetic meshes, "
+                f"{s['S']}x{s['S']}, Phong, faces_per_pixel=1 (BASELINE {s['baseline']})")
+    return (f"points fwd+bwd: {s['batch']} clouds/GPU x {s['views']} {s['view_kind']} views, {s['points']} pts, "
+            f"{s['S']}x{s['S']}, {s['compositor']} compositing K={s['K']} (BASELINE {s['baseline']})")
+
+
+def config_of(s, a):
+    """`config` of the JSON line: the same object in both arms (ours / --impl reference)."""
+    N, S = s["batch"] * s["views"], s["S"]
+    l2 = ("L2 flushed (256 MB memset) between steps, region time = sum of per-step CUDA-event times" if s.get("flush_l2")
+          else f"inputs_exceed_l2 (images + cotangent + index planes = {N * S * S * (12 + 12 + 4) / 1e6:.0f} MB per step > 126 MB)")
+    return {"workload": describe(s), "objects_per_gpu": s["batch"], "views": s["views"], "image_size": S,
+            "cuda_graph": bool(a.cuda_graph), "l2": l2}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -121,32 +176,381 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_table():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
 # ---------------------------------------------------------------------------------------------------
-def make_inputs(a, rank):
+def make_inputs(s, rank):
+    """Seeded synthetic inputs of one workload (SURVEY 8d "Synthetic inputs"); different objects on every rank."""
     from mvtn_b200 import synth
-    seed = 1236 + 1000 * rank
-    if a.workload == "mesh":
-        meshes = synth.make_meshes(a.batch, a.faces, seed)
-        azim, elev, dist = synth.circular_views(a.batch, a.views)   # config.yaml:23-24 canonical 30 deg / 2.2
-        return {"meshes": meshes, "views": (azim, elev, dist)}
-    pts = synth.make_clouds(a.batch, a.points, seed + 1)
-    return {"points": pts, "views": synth.learned_spherical_views(a.batch, a.views, seed + 2)}
+    seed = 1236 + 1000 * rank + (sum(map(ord, s["name"])) % 97)
+    B, M = s["batch"], s["views"]
+    if s["view_kind"] == "circular":
+        views = synth.circular_views(B, M)            # config.yaml:23-24 canonical 30 deg / 2.2
+    elif s["view_kind"] == "spherical":
+        views = synth.spherical_views(B, M)
+    else:
+        views = synth.learned_spherical_views(B, M, seed + 2)
+    if s["kind"] == "mesh":
+        return {"meshes": synth.make_meshes(B, s["faces"], seed), "views": views}
+    return {"points": synth.make_clouds(B, s["points"], seed + 1), "views": views}
 
 
-def algorithmic_bytes_per_view(a, inp, which):
-    """compulsory traffic, each tensor once, geometry counted once per view."""
-    hw = a.image_size * a.image_size
-    if a.workload == "mesh":
+def algorithmic_bytes(s, inp, covered_frac=None):
+    """compulsory traffic per view, each tensor once, geometry counted once per view.  Returns
+    (forward bytes, backward bytes).  Points: without fragments the kernels run under MVR_IDX_SPARSE -- idx is only stored
+    (and read back) for covered pixels, the rest is described by the 1-bit hit mask -- so the bytes that still HAVE to
+    move are 12 N + HW (12 + 1/8) + covered (4 K); `covered_frac` is measured on the rendered batch."""
+    hw = s["S"] * s["S"]
+    if s["kind"] == "mesh":
         V = sum(v.shape[0] for v, _ in inp["meshes"]) / len(inp["meshes"])
         F = sum(f.shape[0] for _, f in inp["meshes"]) / len(inp["meshes"])
-        geo = 12 * V + 12 * F
-        return geo + hw * (12 + 4)            # fwd: RGB + pix_to_face ; bwd: grad RGB + pix_to_face
-    K = a.points_per_pixel
-    return 12 * a.points + hw * (12 + 4 * K)
+        b = 12 * V + 12 * F + hw * (12 + 4)           # fwd: RGB + pix_to_face ; bwd: grad RGB + pix_to_face
+        return b, b
+    K = s["K"]
+    cov = 1.0 if covered_frac is None else covered_frac
+    b = 12 * s["points"] + hw * (12 + 0.125) + cov * hw * 4 * K
+    return b, b
+
+
+class Workload:
+    """One BASELINE configuration on this rank's GPU: the three step flavours bench.py times."""
+
+    def __init__(self, s, a, rank, dev):
+        from mvtn_b200 import MVRenderer, Meshes, collate_meshes
+        self.s, self.a, self.dev = s, a, dev
+        self.inp = inp = make_inputs(s, rank)
+        B, M, S = s["batch"], s["views"], s["S"]
+        self.B, self.M, self.S, self.N = B, M, S, B * M
+        self.views_h = tuple(t.contiguous().pin_memory() for t in inp["views"])
+        self.views_d = tuple(t.to(dev) for t in self.views_h)
+        self.cot = torch.randn(self.N, 3, S, S, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank)) / (3 * S * S)
+        self.bg = torch.tensor([0.99999] * 3, device=dev)
+        self.bg_black = torch.zeros(3, device=dev)
+        self.obj = torch.tensor([0.99999] * 3, device=dev)
+        self.light = torch.tensor([[0.0, 1.0, 0.0]], device=dev)
+        self.graphed = None
+        if s["kind"] == "mesh":
+            self.nv = [v.shape[0] for v, _ in inp["meshes"]]
+            self.nf = [f.shape[0] for _, f in inp["meshes"]]
+            self.verts_d = torch.cat([v for v, _ in inp["meshes"]]).to(dev)
+            self.faces_d = torch.cat([f for _, f in inp["meshes"]]).to(dev)
+            self.mesh_list = [Meshes([v], [f]) for v, f in inp["meshes"]]      # what run_mvtn.py's loader hands over (CPU)
+            self.mesh_host = collate_meshes(self.mesh_list)     # the loader's collate_fn: one packed, pinned host batch (8f N1)
+            self.renderer = MVRenderer(M, image_size=S, pc_rendering=False, light_direction="fixed").to(dev).train()
+            self.renderer_pipe = MVRenderer(M, image_size=S, pc_rendering=False, light_direction="fixed", copy_stream=True).to(dev).train()
+            self.kernels = ["mesh_scatter_kernel", "mesh_shade_kernel", "mesh_backward_kernel", "mesh_tile_kernel"]
+            self.h2d = sum(v.numel() * 4 + f.numel() * 4 for v, f in inp["meshes"]) + 3 * B * M * 4
+        else:
+            self.pts_d = inp["points"].to(dev)
+            self.pts_h = inp["points"].pin_memory()
+            self.renderer = MVRenderer(M, image_size=S, pc_rendering=True, points_per_pixel=s["K"], background_color="black",
+                                       compositor=s["compositor"], cuda_graph=a.cuda_graph).to(dev).train()
+            tiled = s["K"] in (1, 2, 4, 8) and os.environ.get("MVR_POINTS_TILED", "1") != "0"
+            self.kernels = (["points_bin_kernel", "points_tile_kernel", "points_backward_kernel"] if tiled
+                            else ["points_scatter_kernel", "points_resolve_kernel", "points_backward_kernel"])
+            self.h2d = self.pts_h.numel() * 4 + 3 * B * M * 4
+        self.d2h = 3 * B * M * 4 + 4      # gradients + the rotation-validity flag
+        self.g_host = torch.empty(3, B, M, pin_memory=True)
+        self.g_ring = [torch.empty(3, B, M, pin_memory=True) for _ in range(2)]
+        self.ev_ring = [torch.cuda.Event() for _ in range(2)]
+        self.ring_i = 0
+        if a.cuda_graph:
+            from mvtn_b200 import graphs, ops
+            if s["kind"] == "mesh":
+                geom_static = ops.PackedMeshes.from_packed(self.verts_d, self.faces_d, self.nv, self.nf)
+                self.graphed = graphs.graphed_mesh_render(geom_static, M, self.light, self.obj, self.bg, S, self.views_d)
+            else:
+                self.graphed = graphs.graphed_points_render(self.pts_d, self.obj, M, self.renderer.points_radius, self.bg * 0, S,
+                                                            self.views_d, points_per_pixel=s["K"], compositor=s["compositor"])
+
+    # -- the step flavours --------------------------------------------------------------------------
+    def step_resident(self):
+        """Hot path with inputs already in HBM: prepare + look_at + forward + backward + look_at backward."""
+        from mvtn_b200 import ops
+        s, M, S = self.s, self.M, self.S
+        az, el, di = (t.detach().requires_grad_() for t in self.views_d)
+        if self.graphed is not None:
+            img = self.graphed(az, el, di)
+        elif s["kind"] == "mesh":
+            R, T, C, _bad = ops._LookAt.apply(az.reshape(-1), el.reshape(-1), di.reshape(-1))
+            geom = ops.PackedMeshes.from_packed(self.verts_d, self.faces_d, self.nv, self.nf)
+            img, _ = ops.render_meshes(geom, M, R, T, C, self.light, self.obj, self.bg, S)
+        else:
+            img, _cams, self.last_frag = ops.render_points_from_angles(self.pts_d, self.obj, M, az, el, di, self.renderer.points_radius,
+                                                                       self.bg_black, S, points_per_pixel=s["K"], compositor=s["compositor"])
+        img.backward(self.cot)
+        return az.grad, el.grad, di.grad
+
+    def step_forward_only(self):
+        """Forward pass alone (inference: render_and_save, evaluation loops), inputs resident, no autograd graph."""
+        from mvtn_b200 import ops
+        s, M, S = self.s, self.M, self.S
+        with torch.no_grad():
+            R, T, C, _bad = ops._LookAt.apply(*self.views_d)
+            if s["kind"] == "mesh":
+                geom = ops.PackedMeshes.from_packed(self.verts_d, self.faces_d, self.nv, self.nf)
+                img, _ = ops.render_meshes(geom, M, R, T, C, self.light, self.obj, self.bg, S)
+            else:
+                img, _ = ops.render_points(self.pts_d, self.obj, M, R, T, None, self.renderer.points_radius, self.bg_black, S,
+                                           points_per_pixel=s["K"], compositor=s["compositor"], dist=self.views_d[2])
+        return img
+
+    def _views_from_host(self):
+        return tuple(t.to(self.dev, non_blocking=True).requires_grad_() for t in self.views_h)
+
+    def step_e2e(self, list_api=False):
+        """Through the public API from HOST buffers: H2D of the step's inputs (pinned host memory: the collated mesh batch /
+        the point tensor + the view tensors), render, backward, D2H of the result (gradients w.r.t. azim / elev / dist).
+        list_api=True hands MVRenderer the reference's python list of per-object CPU meshes instead, so the multi-threaded
+        gather into pinned memory is inside the timed region too."""
+        az, el, di = self._views_from_host()
+        if self.s["kind"] == "mesh":
+            img, _ = self.renderer(self.mesh_list if list_api else self.mesh_host, None, az, el, di)
+        else:
+            img, _ = self.renderer(None, self.pts_h, az, el, di)
+        img.backward(self.cot.view_as(img))
+        g = self.g_host
+        g[0].copy_(az.grad, non_blocking=True); g[1].copy_(el.grad, non_blocking=True); g[2].copy_(di.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return g
+
+    def step_e2e_pipelined(self):
+        """step_e2e without the per-step device sync: the gradients of step i travel to a pinned ring buffer behind an event
+        and are read on the host while step i+1 is in flight (what a training loop that logs with one step of lag does).
+        Every step still pays its own H2D and D2H inside the timed region; only the wait moves."""
+        i = self.ring_i; self.ring_i = i + 1
+        az, el, di = self._views_from_host()
+        if self.s["kind"] == "mesh":
+            img, _ = self.renderer_pipe(self.mesh_host, None, az, el, di)
+        else:
+            img, _ = self.renderer(None, self.pts_h, az, el, di)
+        img.backward(self.cot.view_as(img))
+        g = self.g_ring[i & 1]
+        g[0].copy_(az.grad, non_blocking=True); g[1].copy_(el.grad, non_blocking=True); g[2].copy_(di.grad, non_blocking=True)
+        self.ev_ring[i & 1].record()
+        if i > 0:
+            self.ev_ring[(i - 1) & 1].synchronize()
+        return self.g_ring[(i - 1) & 1]
+
+    def covered_fraction(self):
+        """Fraction of pixels covered by at least one point (hit mask popcount of the last resident step)."""
+        fr = getattr(self, "last_frag", None)
+        if fr is None or getattr(fr, "_raw", None) is None:
+            return None
+        _idx, mask, H, W = fr._raw
+        mw = (W + 31) // 32
+        words = mask[: self.N * H * mw].to(torch.int64) & 0xFFFFFFFF
+        bits = sum(((words >> k) & 1).sum() for k in range(32))
+        return float(bits) / (self.N * H * W)
+
+
+class Timer:
+    def __init__(self, lib, parallel, dev, flush_l2=False):
+        self.lib, self.parallel, self.dev = lib, parallel, dev
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush_l2 else None
+
+    def bracket(self, fn, steps, profile=None):
+        """EXACTLY `steps` calls between barrier + synchronize on both sides (the contract's timed region) -> total ms, plus
+        one CUDA-event pair per step for the median.  With flush_l2 the L2 is overwritten between steps and the region's time
+        is the SUM of the per-step event times (the flush kernels are not the workload)."""
+        import ctypes
+        from mvtn_b200 import _lib as L
+        lib = self.lib
+        self.parallel.barrier(); torch.cuda.synchronize()
+        if profile:
+            lib.mvr_profile_enable(profile.encode())
+        l0 = lib.mvr_launch_count()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        for i in range(steps):
+            if self.flush is not None:
+                self.flush.zero_()
+            evs[i][0].record()
+            fn()
+            evs[i][1].record()
+        e1.record()
+        torch.cuda.synchronize()
+        w1 = time.time()
+        self.parallel.barrier()
+        per = [a.elapsed_time(b) for a, b in evs]
+        ms = sum(per) if self.flush is not None else e0.elapsed_time(e1)
+        prof = None
+        if profile:
+            tot, n = ctypes.c_double(0), ctypes.c_int(0)
+            L.check(lib.mvr_profile_collect(ctypes.byref(tot), ctypes.byref(n)), "mvr_profile_collect")
+            prof = (tot.value, n.value)
+        return {"ms": ms, "per_step": per, "launches": lib.mvr_launch_count() - l0, "prof": prof, "wall": (w0, w1)}
+
+
+def measure(s, a, rank, world, dev, lib, parallel, with_cpu, clock_sampler=None):
+    """All numbers of one workload -> (record dict, wall-clock window)."""
+    w = Workload(s, a, rank, dev)
+    B, M, S, N = w.B, w.M, w.S, w.N
+    tm = Timer(lib, parallel, dev, flush_l2=bool(s.get("flush_l2")))
+    mesh = s["kind"] == "mesh"
+    for _ in range(max(a.warmup, 3)):      # warm-up (also sizes workspaces / staging buffers)
+        w.step_resident()
+        w.step_forward_only()
+    for _ in range(max(a.warmup, 3)):
+        w.step_e2e()
+        w.step_e2e_pipelined()
+        if mesh:
+            w.step_e2e(list_api=True)
+    torch.cuda.synchronize()
+    # which kernel dominates?  profiled steps per candidate (the profile hook brackets every launch whose name starts with it)
+    shares = {}
+    for k in w.kernels:
+        r = tm.bracket(w.step_resident, 2, profile=k)
+        if r["prof"][1] > 0:
+            shares[k] = r["prof"][0] / 2      # ms per STEP spent in kernels of this name
+    top = max(shares, key=shares.get)
+    res = tm.bracket(w.step_resident, a.steps, profile=top)
+    fwd = tm.bracket(w.step_forward_only, a.steps)
+    e2e = tm.bracket(w.step_e2e, a.steps)
+    pipe = tm.bracket(w.step_e2e_pipelined, a.steps)
+    lst = tm.bracket(lambda: w.step_e2e(list_api=True), a.steps) if mesh else None
+    wall = (res["wall"][0], (lst or pipe)["wall"][1])
+
+    mx = lambda v: parallel.max_over_ranks(v, dev)
+    ms, ms_fwd, ms_e2e, ms_pipe = mx(res["ms"]), mx(fwd["ms"]), mx(e2e["ms"]), mx(pipe["ms"])
+    total_views = parallel.sum_over_ranks(N * a.steps, dev)
+    value = total_views / (ms / 1e3)
+
+    peak, peak_src = measured_peaks()
+    cov = None if mesh else w.covered_fraction()
+    bf, bb = algorithmic_bytes(s, w.inp, cov)
+    k_ms = res["prof"][0] / max(res["prof"][1], 1)              # per LAUNCH of the dominant kernel
+    launches_per_step = max(res["prof"][1], 1) / a.steps
+    fwd_kernel = not top.startswith(("mesh_backward", "points_backward"))
+    per_launch = (bf if fwd_kernel else bb) * N / launches_per_step
+    achieved = per_launch / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
+    step_ms = ms / a.steps
+    tr = traffic_table().get(s["name"], {})
+    kernels = {}
+    for k, v in shares.items():
+        ent = {"ms_per_step": round(v, 4)}
+        t = tr.get(k)
+        if t:      # DRAM bytes of one launch from the committed ncu --set full capture of this very workload
+            ent["dram_bytes"] = t["bytes"]
+            ent["dram_gbs"] = round(t["bytes"] * t.get("launches_per_step", 1) / (v / 1e3) / 1e9, 1) if v > 0 else None
+            ent["dram_frac_of_peak"] = round(ent["dram_gbs"] / peak, 4) if ent["dram_gbs"] else None
+        kernels[k] = ent
+    roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": (tr.get(top) or {}).get("bytes"), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(per_launch), "kernel_ms": round(k_ms, 4),
+                "note": ("`achieved` credits the dominant kernel with the algorithmic bytes of its whole pass (contract); `step` and "
+                         "`forward` are the honest attribution: all bytes of the pass over all kernels of the pass"),
+                "step": {"algorithmic_bytes": int((bf + bb) * N), "ms": round(step_ms, 4),
+                         "achieved": round((bf + bb) * N / (step_ms / 1e3) / 1e9, 1),
+                         "frac": round((bf + bb) * N / (step_ms / 1e3) / 1e9 / peak, 4)},
+                "forward": {"algorithmic_bytes": int(bf * N), "ms": round(ms_fwd / a.steps, 4),
+                            "achieved": round(bf * N / (ms_fwd / a.steps / 1e3) / 1e9, 1),
+                            "frac": round(bf * N / (ms_fwd / a.steps / 1e3) / 1e9 / peak, 4)},
+                "kernels": kernels}
+    if cov is not None:
+        roofline["covered_pixel_fraction"] = round(cov, 4)
+    rec = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+           "warmup": max(a.warmup, 3), "ms_per_step": round(step_ms, 4),
+           "ms_per_step_median": round(statistics.median(res["per_step"]), 4), "ms_per_step_min": round(min(res["per_step"]), 4),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": config_of(s, a),
+           "e2e": {"value": round(total_views / (ms_e2e / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(w.h2d),
+                   "d2h_bytes_per_step": int(w.d2h), "ms_per_step": round(ms_e2e / a.steps, 4),
+                   "input": ("collated pinned host batch (mvtn_b200.collate_meshes) + pinned view tensors" if mesh
+                             else "pinned host point tensor + pinned view tensors"),
+                   "pipelined": {"value": round(total_views / (ms_pipe / 1e3), 1), "ms_per_step": round(ms_pipe / a.steps, 4),
+                                 "note": "same per-step H2D / D2H, but the result of step i is awaited on the host during step i+1 "
+                                         "(no per-step device sync); mesh batches go through MVRenderer(copy_stream=True)"}},
+           "forward_only": {"value": round(total_views / (ms_fwd / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms_fwd / a.steps, 4)},
+           "gpu_launches": int(res["launches"]), "roofline": roofline}
+    if lst is not None:
+        ms_l = mx(lst["ms"])
+        rec["e2e"]["list_api"] = {"value": round(total_views / (ms_l / 1e3), 1), "ms_per_step": round(ms_l / a.steps, 4),
+                                  "input": "python list of per-object CPU meshes (the reference's loader output = what the unmodified "
+                                           "run_mvtn.py:184 passes); gather into pinned memory inside the timed region"}
+    if with_cpu:
+        rec["cpu_baseline"], rec["parity"] = cpu_baseline(s, a, w.inp)
+    del w
+    torch.cuda.empty_cache()
+    return rec, wall
+
+
+def measure_strong(a, rank, world, dev, lib, parallel):
+    """SURVEY 8e strong-scaling row: configs[1] with 32 objects IN TOTAL, split by object over the ranks (48 views per GPU at
+    N = 8: launch-bound)."""
+    lo, hi = parallel.shard_range(32, rank, world)
+    s = finalize(dict(name="c2_strong", kind="mesh", batch=hi - lo, views=12, S=224, faces=10000, view_kind="circular", baseline="configs[1]"))
+    w = Workload(s, a, rank, dev)
+    tm = Timer(lib, parallel, dev, flush_l2=s["flush_l2"])
+    for _ in range(max(a.warmup, 3)):
+        w.step_resident(); w.step_e2e()
+    res = tm.bracket(w.step_resident, a.steps)
+    e2e = tm.bracket(w.step_e2e, a.steps)
+    ms, ms_e2e = parallel.max_over_ranks(res["ms"], dev), parallel.max_over_ranks(e2e["ms"], dev)
+    total = parallel.sum_over_ranks(w.N * a.steps, dev)
+    return {"value": round(total / (ms / 1e3), 1), "unit": UNIT, "scaling": "strong", "n_gpus": world, "ms_per_step": round(ms / a.steps, 4),
+            "e2e": {"value": round(total / (ms_e2e / 1e3), 1), "ms_per_step": round(ms_e2e / a.steps, 4)},
+            "config": {"workload": f"configs[1] mesh fwd+bwd, 32 objects in total over {world} GPU(s) ({hi - lo} on rank {rank}) x 12 views, 224x224",
+                       "l2": "L2 flushed between steps" if s["flush_l2"] else "inputs_exceed_l2"}}
+
+
+def measure_train(a, rank, world, dev, parallel, render_ms):
+    """BASELINE configs[3]: MVTN view selector + MVCNN (ResNet-18) training step, 32 objects x 12 views per GPU, objects sharded
+    by rank, gradients of both networks all-reduced over NCCL (run_mvtn.py:168-224).  Reports ms/step for the overlapped
+    all-reduce, the un-overlapped one and none, so that the exposed share of the collective can be read off."""
+    try:
+        import torchvision  # noqa: F401
+        sys.path.insert(0, os.path.join(ROOT, "examples"))
+        import train_step as T
+    except Exception as e:      # pragma: no cover
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    steps = max(3, min(a.steps, 10))
+    out = {"unit": "ms/step", "n_gpus": world, "steps": steps,
+           "config": {"workload": "MVTN selector + MVCNN ResNet-18 training step, 32 objects/GPU x 12 views, 224x224, ~10k-face meshes, "
+                                  "fp32 (torch defaults), AdamW x 2 (BASELINE configs[3])"}}
+    modes = ["overlap", "after", "none"] if world > 1 else ["none"]
+    for mode in modes:
+        ts = T.TrainStep(dev, rank, 32, 12, 224, 10000, amp=False, sync=mode)
+        for _ in range(3):
+            ts.step()
+        torch.cuda.synchronize(); parallel.barrier()
+        ts.render_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ts.step()
+        e1.record()
+        torch.cuda.synchronize(); parallel.barrier()
+        ms = parallel.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+        out[f"ms_per_step_{mode}"] = round(ms, 3)
+        if mode == modes[0]:
+            out["render_forward_ms"] = round(ts.render_events[0].elapsed_time(ts.render_events[1]), 3)
+            out["grad_bytes"] = ts.grad_bytes()
+            if ts.overlap is not None:
+                out["allreduce"] = dict(ts.overlap.stats, bucket_bytes=8 << 20)
+        ts.close()
+        del ts
+        torch.cuda.empty_cache()
+    main = out[f"ms_per_step_{modes[0]}"]
+    out["value"] = round(32 * 12 * world / (main / 1e3), 1)
+    out["value_unit"] = "views/s through render + CNN fwd/bwd + all-reduce + optimizer"
+    out["render_fwd_bwd_ms_standalone"] = round(render_ms, 4)
+    out["render_share"] = round(render_ms / main, 4)
+    if world > 1:
+        out["allreduce_exposed_ms"] = round(out["ms_per_step_overlap"] - out["ms_per_step_none"], 3)
+        out["allreduce_exposed_ms_unoverlapped"] = round(out["ms_per_step_after"] - out["ms_per_step_none"], 3)
+    return out
 
 
 def run_ours(a):
-    from mvtn_b200 import MVRenderer, Meshes, ops, parallel
+    from mvtn_b200 import parallel
     from mvtn_b200 import _lib as L
     rank, local_rank, world = parallel.init_distributed()
     if world != a.gpus and world > 1:
@@ -155,230 +559,35 @@ def run_ours(a):
     dev = torch.device("cuda", local_rank)
     lib = L.load()
     lib.mvr_host_set_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))     # ranks share the host cores
-    inp = make_inputs(a, rank)
-    B, M, S = a.batch, a.views, a.image_size
-    N = B * M
-    azim_h, elev_h, dist_h = (t.contiguous().pin_memory() for t in inp["views"])
-    cot = torch.randn(N, 3, S, S, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank)) / (3 * S * S)
-    bg = torch.tensor([0.99999] * 3, device=dev)
-    bg_black = torch.zeros(3, device=dev)
-    obj = torch.tensor([0.99999] * 3, device=dev)
-    light = torch.tensor([[0.0, 1.0, 0.0]], device=dev)
-
-    if a.workload == "mesh":
-        nv = [v.shape[0] for v, _ in inp["meshes"]]
-        nf = [f.shape[0] for _, f in inp["meshes"]]
-        verts_d = torch.cat([v for v, _ in inp["meshes"]]).to(dev)
-        faces_d = torch.cat([f for _, f in inp["meshes"]]).to(dev)
-        mesh_list = [Meshes([v], [f]) for v, f in inp["meshes"]]          # what run_mvtn.py's loader hands over (CPU)
-        from mvtn_b200 import collate_meshes
-        mesh_host = collate_meshes(mesh_list)     # the loader's collate_fn: one packed, pinned host batch
-        renderer = MVRenderer(M, image_size=S, pc_rendering=False, light_direction="fixed").to(dev)
-        renderer_pipe = MVRenderer(M, image_size=S, pc_rendering=False, light_direction="fixed", copy_stream=True).to(dev).train()
-        kernels = ["mesh_scatter_kernel", "mesh_shade_kernel", "mesh_backward_kernel"]
-    else:
-        pts_d = inp["points"].to(dev)
-        pts_h = inp["points"].pin_memory()
-        renderer = MVRenderer(M, image_size=S, pc_rendering=True, points_per_pixel=a.points_per_pixel,
-                              background_color="black", compositor="alpha", cuda_graph=a.cuda_graph).to(dev)
-        tiled = a.points_per_pixel in (1, 2, 4, 8) and os.environ.get("MVR_POINTS_TILED", "1") != "0"
-        kernels = (["points_bin_kernel", "points_tile_kernel", "points_backward_kernel"] if tiled
-                   else ["points_scatter_kernel", "points_resolve_kernel", "points_backward_kernel"])
-    renderer.train()
-    azim_d, elev_d, dist_d = (t.to(dev) for t in (azim_h, elev_h, dist_h))
-
-    graphed = None
-    if a.cuda_graph:
-        from mvtn_b200 import graphs
-        sample = (azim_d, elev_d, dist_d)
-        if a.workload == "mesh":
-            geom_static = ops.PackedMeshes.from_packed(verts_d, faces_d, nv, nf)
-            graphed = graphs.graphed_mesh_render(geom_static, M, light, obj, bg, S, sample)      # prepare is in the graph
-        else:
-            graphed = graphs.graphed_points_render(pts_d, obj, M, renderer.points_radius, bg * 0, S, sample,
-                                                   points_per_pixel=a.points_per_pixel, compositor="alpha")
-
-    def step_resident():
-        """Hot path with inputs already in HBM: prepare + look_at + forward + backward + look_at backward."""
-        az = azim_d.detach().requires_grad_(); el = elev_d.detach().requires_grad_(); di = dist_d.detach().requires_grad_()
-        if graphed is not None:
-            img = graphed(az, el, di)
-            img.backward(cot)
-            return az.grad, el.grad, di.grad
-        if a.workload == "mesh":
-            R, T, C, _bad = ops._LookAt.apply(az.reshape(-1), el.reshape(-1), di.reshape(-1))
-            geom = ops.PackedMeshes.from_packed(verts_d, faces_d, nv, nf)
-            img, _ = ops.render_meshes(geom, M, R, T, C, light, obj, bg, S)
-        else:
-            img, _cams, _ = ops.render_points_from_angles(pts_d, obj, M, az, el, di, renderer.points_radius, bg_black, S,
-                                                          points_per_pixel=a.points_per_pixel, compositor="alpha")
-        img.backward(cot)
-        return az.grad, el.grad, di.grad
-
-    def step_forward_only():
-        """Forward pass alone (inference: render_and_save, evaluation loops), inputs resident, no autograd graph."""
-        with torch.no_grad():
-            R, T, C, _bad = ops._LookAt.apply(azim_d, elev_d, dist_d)
-            if a.workload == "mesh":
-                geom = ops.PackedMeshes.from_packed(verts_d, faces_d, nv, nf)
-                img, _ = ops.render_meshes(geom, M, R, T, C, light, obj, bg, S)
-            else:
-                img, _ = ops.render_points(pts_d, obj, M, R, T, None, renderer.points_radius, bg_black, S,
-                                           points_per_pixel=a.points_per_pixel, compositor="alpha", dist=dist_d)
-        return img
-
-    g_host = torch.empty(3, B, M, pin_memory=True)
-
-    def step_e2e(list_api=False):
-        """Through the public API from HOST buffers: H2D of the step's inputs (pinned host memory: the collated mesh
-        batch / the point tensor + the view tensors), render, backward, D2H of the result (gradients w.r.t.
-        azim/elev/dist).  list_api=True hands MVRenderer the reference's python list of per-object CPU meshes instead,
-        so the multi-threaded gather into pinned memory is inside the timed region too."""
-        az = azim_h.to(dev, non_blocking=True).requires_grad_()
-        el = elev_h.to(dev, non_blocking=True).requires_grad_()
-        di = dist_h.to(dev, non_blocking=True).requires_grad_()
-        if a.workload == "mesh":
-            img, _ = renderer(mesh_list if list_api else mesh_host, None, az, el, di)
-        else:
-            img, _ = renderer(None, pts_h, az, el, di)
-        img.backward(cot.view_as(img))
-        g_host[0].copy_(az.grad, non_blocking=True)
-        g_host[1].copy_(el.grad, non_blocking=True)
-        g_host[2].copy_(di.grad, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return g_host
-
-    g_ring = [torch.empty(3, B, M, pin_memory=True) for _ in range(2)]
-    ev_ring = [torch.cuda.Event() for _ in range(2)]
-    ring = {"i": 0}
-
-    def step_e2e_pipelined():
-        """step_e2e without the per-step device sync: the gradients of step i travel to a pinned ring buffer behind an
-        event and are read on the host while step i+1 is in flight (what a training loop that logs with one step of lag
-        does).  Every step still pays its own H2D and D2H inside the timed region; only the wait moves."""
-        i = ring["i"]; ring["i"] = i + 1
-        az = azim_h.to(dev, non_blocking=True).requires_grad_()
-        el = elev_h.to(dev, non_blocking=True).requires_grad_()
-        di = dist_h.to(dev, non_blocking=True).requires_grad_()
-        if a.workload == "mesh":
-            img, _ = renderer_pipe(mesh_host, None, az, el, di)
-        else:
-            img, _ = renderer(None, pts_h, az, el, di)
-        img.backward(cot.view_as(img))
-        g = g_ring[i & 1]
-        g[0].copy_(az.grad, non_blocking=True)
-        g[1].copy_(el.grad, non_blocking=True)
-        g[2].copy_(di.grad, non_blocking=True)
-        ev_ring[i & 1].record()
-        if i > 0:
-            ev_ring[(i - 1) & 1].synchronize()
-        return g_ring[(i - 1) & 1]
-
-    if a.workload == "mesh":
-        # verts fp32 + faces narrowed to int32 by the multi-threaded host gather + the three (B, M) view tensors
-        h2d = sum(v.numel() * 4 + f.numel() * 4 for v, f in inp["meshes"]) + 3 * B * M * 4
-    else:
-        h2d = pts_h.numel() * 4 + 3 * B * M * 4
-    d2h = 3 * B * M * 4 + 4    # gradients + the rotation-validity flag
-
-    def timed(fn, steps, profile=None):
-        parallel.barrier(); torch.cuda.synchronize()
-        if profile:
-            lib.mvr_profile_enable(profile.encode())
-        l0 = lib.mvr_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0 = time.time()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        w1 = time.time()
-        parallel.barrier()
-        ms = e0.elapsed_time(e1)
-        prof = None
-        if profile:
-            import ctypes
-            tot, n = ctypes.c_double(0), ctypes.c_int(0)
-            L.check(lib.mvr_profile_collect(ctypes.byref(tot), ctypes.byref(n)), "mvr_profile_collect")
-            prof = (tot.value, n.value)
-        return ms, lib.mvr_launch_count() - l0, prof, (w0, w1)
-
-    # warm-up (also sizes workspaces / staging buffers)
-    for _ in range(max(a.warmup, 3)):
-        step_resident()
-        step_forward_only()
-    for _ in range(max(a.warmup, 3)):
-        step_e2e()
-        step_e2e_pipelined()
-        if a.workload == "mesh":
-            step_e2e(list_api=True)
-    torch.cuda.synchronize()
-    # which kernel dominates?  one profiled step per candidate
-    shares = {}
-    for k in kernels:
-        _, _, prof, _ = timed(step_resident, 2, profile=k)
-        shares[k] = prof[0] / max(prof[1], 1)
-    top = max(shares, key=shares.get)
+    spec, custom = main_spec(a)
+    with_cpu = rank == 0 and world == 1 and not a.no_cpu_baseline
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
-    ms, launches, prof, (w0, w1) = timed(step_resident, a.steps, profile=top)
-    ms_fwd, _, _, _ = timed(step_forward_only, a.steps)
-    ms_e2e, _, _, (w2, w3) = timed(step_e2e, a.steps)
-    ms_e2e_pipe, _, _, (_, w3) = timed(step_e2e_pipelined, a.steps)
-    ms_e2e_list = None
-    if a.workload == "mesh":
-        ms_e2e_list, _, _, (_, w3) = timed(lambda: step_e2e(list_api=True), a.steps)
-    clocks = sampler.stop(w0, w3)
+    out, wall = measure(spec, a, rank, world, dev, lib, parallel, with_cpu)
+    out["clocks"] = sampler.stop(*wall)
 
-    ms_max = parallel.max_over_ranks(ms, dev)
-    ms_fwd_max = parallel.max_over_ranks(ms_fwd, dev)
-    ms_e2e_max = parallel.max_over_ranks(ms_e2e, dev)
-    ms_e2e_pipe_max = parallel.max_over_ranks(ms_e2e_pipe, dev)
-    ms_e2e_list_max = parallel.max_over_ranks(ms_e2e_list, dev) if ms_e2e_list is not None else None
-    total_views = parallel.sum_over_ranks(N * a.steps, dev)
-    value = total_views / (ms_max / 1e3)
-    e2e_value = total_views / (ms_e2e_max / 1e3)
-
-    peak, peak_src = measured_peaks()
-    per_view = algorithmic_bytes_per_view(a, inp, top)
-    k_ms = prof[0] / max(prof[1], 1)
-    achieved = (per_view * N) / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
-    traffic = None
-    try:   # DRAM bytes per launch of this kernel from the committed ncu capture (only valid for the default workload)
-        default_mesh = a.workload == "mesh" and (B, M, S, a.faces) == (32, 12, 224, 10000)
-        default_points = a.workload == "points" and (B, M, S, a.points, a.points_per_pixel) == (32, 12, 224, 2048, 4)
-        if default_mesh or default_points:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[top]["bytes"]
-    except Exception:
-        traffic = None
-    roofline = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(per_view * N), "kernel_ms": round(k_ms, 4),
-                "kernel_ms_all": {k: round(v, 4) for k, v in shares.items()}}
-
-    out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": a.steps,
-           "warmup": max(a.warmup, 3), "ms_per_step": round(ms_max / a.steps, 4), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": workload_name(a), "objects_per_gpu": B, "views": M, "image_size": S,
-                      "cuda_graph": bool(a.cuda_graph),
-                      "l2": "inputs_exceed_l2 (images + cotangent + pix_to_face > 126 MB per step)"},
-           "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": round(ms_e2e_max / a.steps, 4),
-                   "input": ("collated pinned host batch (mvtn_b200.collate_meshes) + pinned view tensors" if a.workload == "mesh"
-                             else "pinned host point tensor + pinned view tensors")},
-           "forward_only": {"value": round(total_views / (ms_fwd_max / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms_fwd_max / a.steps, 4)},
-           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
-
-    out["e2e"]["pipelined"] = {"value": round(total_views / (ms_e2e_pipe_max / 1e3), 1), "ms_per_step": round(ms_e2e_pipe_max / a.steps, 4),
-                               "note": "same per-step H2D / D2H, but the result of step i is awaited on the host during step i+1 (no per-step device sync); mesh batches go through MVRenderer(copy_stream=True)"}
-    if ms_e2e_list_max is not None:
-        out["e2e"]["list_api"] = {"value": round(total_views / (ms_e2e_list_max / 1e3), 1), "ms_per_step": round(ms_e2e_list_max / a.steps, 4),
-                                  "input": "python list of per-object CPU meshes (the reference's loader output); gather into pinned memory inside the timed region"}
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        out["cpu_baseline"], out["parity"] = cpu_baseline(a, inp)
+    mode = a.extras
+    if mode == "auto":
+        mode = "none" if (custom or a.cuda_graph) else "all"
+    if mode != "none":
+        only = set(a.only.split(",")) if a.only else None
+        extra = {}
+        for s in extra_specs(mode):
+            if only is not None and s["name"] not in only:
+                continue
+            smp = ClockSampler(local_rank); smp.start()
+            rec, w2 = measure(s, a, rank, world, dev, lib, parallel, with_cpu)
+            rec["clocks"] = smp.stop(*w2)
+            for k in ("metric", "unit", "higher_is_better", "vs_baseline", "dtype", "data", "steps", "warmup"):
+                rec.pop(k, None)
+            extra[s["name"]] = rec
+        if mode == "all" and (only is None or "c2_strong" in only) and world > 1:
+            extra["c2_strong"] = measure_strong(a, rank, world, dev, lib, parallel)
+        if mode == "all" and (only is None or "c4_train" in only):
+            extra["c4_train"] = measure_train(a, rank, world, dev, parallel, out["ms_per_step"])
+        out["extra"] = extra
     if rank == 0:
         emit(out)
     if world > 1:
@@ -386,17 +595,18 @@ def run_ours(a):
 
 
 # ---------------------------------------------------------------------------------------------------
-def oracle_step(a, inp, n_obj, keep=None):
-    """One forward+backward of the CPU oracle on the first n_obj objects of the workload.  Returns seconds; `keep` (a dict)
-    receives the cameras, fragment indices, images and gradients for the parity report."""
+def oracle_step(s, inp, n_obj, n_views=None, keep=None):
+    """One forward+backward of the CPU oracle on the first n_obj objects (first n_views views of each) of the workload.
+    Returns seconds; `keep` (a dict) receives the cameras, fragment indices, images and gradients for the parity report."""
     import numpy as np
     from oracle import oracle as orc
     from mvtn_b200 import ops
-    M, S = a.views, a.image_size
-    az, el, di = (t[:n_obj].reshape(-1).numpy() for t in inp["views"])
+    S = s["S"]
+    M = n_views or s["views"]
+    az, el, di = (t[:n_obj, :M].reshape(-1).numpy() for t in inp["views"])
     t0 = time.time()
     R, T, C = orc.look_at(az, el, di)
-    if a.workload == "mesh":
+    if s["kind"] == "mesh":
         ms = inp["meshes"][:n_obj]
         vp = np.concatenate([v.numpy() for v, _ in ms]); fp = np.concatenate([f.numpy() for _, f in ms]).astype(np.int32)
         voff = np.cumsum([0] + [v.shape[0] for v, _ in ms]).astype(np.int32)
@@ -416,35 +626,43 @@ def oracle_step(a, inp, n_obj, keep=None):
         pts = inp["points"][:n_obj].numpy()
         rgb = np.full(3, 0.99999, np.float32)
         inv = (1.0 / di).astype(np.float32)
-        K = a.points_per_pixel
-        o = orc.points_forward(pts, rgb, M, R, T, inv, 0.006, np.zeros(3, np.float32), S, S, K, orc.COMPOSITE_ALPHA,
-                               fragments=False)
+        K = s["K"]
+        flags = orc.COMPOSITE_ALPHA if s["compositor"] == "alpha" else 0
+        o = orc.points_forward(pts, rgb, M, R, T, inv, 0.006, np.zeros(3, np.float32), S, S, K, flags, fragments=False)
         g = np.full((n_obj * M, 3, S, S), 1.0 / (3 * S * S), np.float32)
-        b = orc.points_backward(pts, rgb, M, R, T, inv, 0.006, S, S, K, orc.COMPOSITE_ALPHA, o["idx"], g)
+        b = orc.points_backward(pts, rgb, M, R, T, inv, 0.006, S, S, K, flags, o["idx"], g)
         gv = orc.look_at_backward(az, el, di, b["gR"], b["gT"], np.zeros_like(b["gT"]))      # the orthographic path does not use C
         if keep is not None:
             keep.update(R=R, T=T, C=C, index=o["idx"], images=o["images"], gR=b["gR"], gT=b["gT"], g_scale=b.get("g_inv_dist"), g_views=gv)
     return time.time() - t0
 
 
-def cpu_baseline(a, inp):
+def cpu_baseline(s, a, inp, budget_s=8.0):
+    """The oracle on this box's host cores on a BOUNDED sample of the workload: n objects x m views sized from a one-view
+    probe for ~budget_s seconds of CPU work (the naive CPU rasterizer is O(H W F) per view: 1.6e10 tests at configs[4])."""
     from oracle import oracle as orc
     cores = os.cpu_count() or 1
     orc.set_num_threads(cores)
+    M = s["views"]
     n = a.cpu_sample_objects
+    m = M
     if n <= 0:
-        t1 = oracle_step(a, inp, 1)                     # probe: one object
-        n = max(1, min(a.batch, int(12.0 / max(t1, 1e-3))))
+        t1 = oracle_step(s, inp, 1, 1)                     # probe: one object, one view
+        views = max(1, int(budget_s / max(t1, 1e-4)))
+        if views >= M:
+            n, m = max(1, min(s["batch"], views // M)), M
+        else:
+            n, m = 1, views
     keep = {}
-    t = oracle_step(a, inp, n, keep)
-    base = {"value": round(n * a.views / t, 2), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-            "sample": f"{n} object(s) x {a.views} views of the same workload, fwd+bwd, {t:.2f} s of CPU work "
+    t = oracle_step(s, inp, n, m, keep)
+    base = {"value": round(n * m / t, 3), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+            "sample": f"{n} object(s) x {m} of {M} views of the same workload, fwd+bwd, {t:.2f} s of CPU work "
                       f"(oracle/mvr_oracle.c, OpenMP over image rows)"}
-    return base, parity_report(a, inp, n, keep)
+    return base, parity_report(s, inp, n, m, keep)
 
 
-def parity_report(a, inp, n_obj, ref):
-    """the parity gates that go with every throughput number.  The CUDA path renders the objects the CPU
+def parity_report(s, inp, n_obj, m_views, ref):
+    """the parity gates that go with every throughput number.  The CUDA path renders the objects / views the CPU
     baseline has just rendered (same constant cotangent) and is compared with the oracle's outputs in the two stages of
     the test protocol: (A) rasterizer / shader / compositor and their backward from the SAME cameras -- fragment indices
     bit-exact, images and camera gradients within tolerance; (B) the camera kernels on their own -- look_at forward
@@ -452,22 +670,25 @@ def parity_report(a, inp, n_obj, ref):
     through DIFFERENT cameras would measure how many edge pixels a 1e-7 change of R flips, not the kernels.)
     Exact depth ties are counted from the K-list (meshes: a K = 2 render)."""
     import numpy as np
-    import torch
     from mvtn_b200 import ops
     dev = torch.device("cuda", torch.cuda.current_device())
-    M, S = a.views, a.image_size
+    M, S = m_views, s["S"]
     N = n_obj * M
     cot = torch.full((N, 3, S, S), 1.0 / (3 * S * S), device=dev)
     col = torch.tensor([0.99999] * 3, device=dev)
     Rd, Td, Cd = (torch.from_numpy(ref[k]).to(dev).requires_grad_() for k in ("R", "T", "C"))
-    views = [t[:n_obj].reshape(-1).to(dev).requires_grad_() for t in inp["views"]]
+    views = [t[:n_obj, :M].reshape(-1).to(dev).requires_grad_() for t in inp["views"]]
 
     def rel(x, y):
         x = x.detach().cpu().numpy().reshape(-1); y = np.asarray(y).reshape(-1)
         return float(np.abs(x - y).max() / max(np.abs(y).max(), 1e-30))
 
+    def rel_elem(x, y):      # element-wise, with a floor of 1e-3 of the tensor's largest entry under the small ones
+        x = x.detach().cpu().numpy().reshape(-1).astype(np.float64); y = np.asarray(y).reshape(-1).astype(np.float64)
+        return float((np.abs(x - y) / np.maximum(np.abs(y), 1e-3 * max(np.abs(y).max(), 1e-30))).max())
+
     out = {"sample": f"the cpu_baseline sample ({n_obj} object(s) x {M} views)", "pixels": int(N * S * S)}
-    if a.workload == "mesh":
+    if s["kind"] == "mesh":
         ms = inp["meshes"][:n_obj]
         geom = ops.PackedMeshes([v for v, _ in ms], [f for _, f in ms], dev)
         light = torch.tensor([[0.0, 1.0, 0.0]], device=dev)
@@ -477,23 +698,27 @@ def parity_report(a, inp, n_obj, ref):
         _, fr2 = ops.render_meshes(geom, M, Rd.detach(), Td.detach(), Cd.detach(), light, col, col, S, faces_per_pixel=2, fragments=True)
         zb = fr2["zbuf"]
         ties = int(((zb[..., 0] == zb[..., 1]) & (fr2["pix_to_face"][..., 1] >= 0)).sum())
-        g_cam = max(rel(Rd.grad, ref["gR"]), rel(Td.grad, ref["gT"]), rel(Cd.grad, ref["gC"]))
-        tol = {"index": "bit-exact", "images_abs": 1e-5, "gradients_rel": 1e-4, "look_at_abs": 2e-6}
+        pairs = ((Rd.grad, ref["gR"]), (Td.grad, ref["gT"]), (Cd.grad, ref["gC"]))
+        tol = {"index": "bit-exact", "images_abs": 1e-5, "gradients_rel": 1e-4, "look_at_abs": 2e-6,
+               "gradients_note": "north_star asks 1e-5; two legitimate fp32 evaluations of this chain differ by 1e-5..2e-4 "
+                                 "(profiles/r3_fp32_gradient_floor.txt), so the bar is 1e-4 and the measured error is reported"}
     else:
         pts = inp["points"][:n_obj].to(dev)
         inv = (1.0 / views[2].detach()).requires_grad_()
-        img, fr = ops.render_points(pts, col, M, Rd, Td, inv, 0.006, col * 0, S, points_per_pixel=a.points_per_pixel,
-                                    compositor="alpha", fragments=True)
+        img, fr = ops.render_points(pts, col, M, Rd, Td, inv, 0.006, col * 0, S, points_per_pixel=s["K"],
+                                    compositor=s["compositor"], fragments=True)
         img.backward(cot)
         index = fr["idx"]
         zb = fr["zbuf"]
         ties = int(((zb[..., 1:] == zb[..., :-1]) & (index[..., 1:] >= 0)).sum()) if zb.shape[-1] > 1 else 0
-        g_cam = max(rel(Rd.grad, ref["gR"]), rel(Td.grad, ref["gT"]), rel(inv.grad, ref["g_scale"]))
+        pairs = ((Rd.grad, ref["gR"]), (Td.grad, ref["gT"]), (inv.grad, ref["g_scale"]))
         tol = {"index": "bit-exact", "images_abs": 1e-5, "gradients_rel": 1e-5, "look_at_abs": 2e-6}
     out["index_mismatches"] = int((index.cpu().numpy() != ref["index"]).sum())
     out["exact_depth_ties"] = ties
+    out["covered_pixels"] = int((ref["index"][..., 0] >= 0).sum())
     out["image_max_abs_err"] = round(float(np.abs(img.detach().cpu().numpy() - ref["images"]).max()), 9)
-    out["grad_camera_max_rel_err"] = round(g_cam, 9)
+    out["grad_camera_max_rel_err"] = round(max(rel(x, y) for x, y in pairs), 9)
+    out["grad_camera_max_elementwise_rel_err"] = round(max(rel_elem(x, y) for x, y in pairs), 9)
     # stage B: the camera kernels
     R2, T2, C2, _ = ops._LookAt.apply(*views)
     out["look_at_max_abs_err"] = round(max(float((R2.detach().cpu() - torch.from_numpy(ref["R"])).abs().max()),
@@ -507,6 +732,8 @@ def parity_report(a, inp, n_obj, ref):
     # one scale for the three view gradients: with orthographic cameras d/d dist through the cameras is identically ~0
     out["look_at_backward_max_rel_err"] = round(rel(torch.cat([v.grad for v in views]), np.concatenate([np.asarray(g) for g in ref["g_views"]])), 9)
     out["tolerance"] = tol
+    out["pass"] = bool(out["index_mismatches"] == 0 and out["image_max_abs_err"] <= tol["images_abs"]
+                       and out["grad_camera_max_rel_err"] <= tol["gradients_rel"] and out["look_at_max_abs_err"] <= tol["look_at_abs"])
     return out
 
 
@@ -519,23 +746,24 @@ def run_reference(a):
     from oracle import oracle as orc
     cores = os.cpu_count() or 1
     orc.set_num_threads(cores)
-    inp = make_inputs(a, 0)
-    t1 = oracle_step(a, inp, 1)
-    n = max(1, min(a.batch, int(3.0 / max(t1, 1e-3))))      # ~3 s of CPU work per step
+    s, _ = main_spec(a)
+    inp = make_inputs(dict(s, batch=min(s["batch"], 8)), 0)      # the sample never needs more than a few objects
+    t1 = oracle_step(s, inp, 1)
+    n = max(1, min(len(inp["views"][0]), int(3.0 / max(t1, 1e-3))))      # ~3 s of CPU work per step
     for _ in range(min(a.warmup, 1)):
-        oracle_step(a, inp, n)
+        oracle_step(s, inp, n)
     steps = max(1, min(a.steps, 5))
     t0 = time.time()
     for _ in range(steps):
-        oracle_step(a, inp, n)
+        oracle_step(s, inp, n)
     dt = time.time() - t0
-    v = round(n * a.views * steps / dt, 2)
+    v = round(n * s["views"] * steps / dt, 2)
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
            "warmup": min(a.warmup, 1), "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": workload_name(a), "objects_per_gpu": a.batch, "views": a.views, "image_size": a.image_size},
+           "config": config_of(s, a),      # the workload both arms are quoted on (this arm: a bounded sample of it per step)
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-                            "sample": f"{n} object(s) x {a.views} views per step, fwd+bwd (PyTorch3D is not installable "
+                            "sample": f"{n} object(s) x {s['views']} views per step, fwd+bwd (PyTorch3D is not installable "
                                       f"offline: oracle port of its CPU path)"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}

@@ -7,7 +7,8 @@
       -> CrossEntropy, backward (through the renderer into the selector), AdamW x 2
 
 Objects shard by rank (32 per GPU by default); rendering needs no collective, the network gradients are
-all-reduced in buckets over NCCL (mvtn_b200.parallel.allreduce_gradients).
+all-reduced in buckets over NCCL DURING backward (mvtn_b200.parallel.OverlappedGradientAllReduce: hook-driven, the buckets
+of the backbone are in flight while the renderer's backward kernels run).
 
     python examples/train_step.py --steps 5
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/train_step.py --steps 5
@@ -58,6 +59,54 @@ class MVCNN(nn.Module):
         return self.fc(f.max(dim=1).values)
 
 
+class TrainStep:
+    """One rank's share of the step: `batch` objects x `views` views.  step() returns the loss tensor (no host sync).
+    sync: "overlap" (hook-driven buckets during backward), "after" (parallel.allreduce_gradients once backward is done:
+    the un-overlapped baseline) or "none"."""
+
+    def __init__(self, dev, rank, batch=32, views=12, image_size=224, faces=10000, amp=False, sync="overlap", collate=True):
+        from mvtn_b200 import collate_meshes
+        torch.manual_seed(1234)                         # same initial weights on every rank
+        self.dev, self.amp, self.sync_mode = dev, amp, sync
+        self.selector, self.cnn = ViewSelector(views).to(dev), MVCNN().to(dev)
+        self.renderer = MVRenderer(views, image_size=image_size, pc_rendering=False, light_direction="random").to(dev)
+        self.opt = torch.optim.AdamW(self.cnn.parameters(), lr=1e-3, weight_decay=0.01)
+        self.opt_mvtn = torch.optim.AdamW(self.selector.parameters(), lr=1e-4, weight_decay=0.01)
+        meshes = [Meshes([v], [f]) for v, f in synth.make_meshes(batch, faces, 4000 + 97 * rank)]   # this rank's objects
+        self.points = torch.stack([m.verts_list()[0][torch.randperm(m.verts_list()[0].shape[0])[:2048]] for m in meshes]).to(dev)
+        self.meshes = collate_meshes(meshes) if collate else meshes      # what the loader's collate_fn hands over
+        self.targets = torch.randint(0, 40, (batch,), generator=torch.Generator().manual_seed(rank)).to(dev)
+        self.params = list(self.cnn.parameters()) + list(self.selector.parameters())
+        self.crit = nn.CrossEntropyLoss()
+        self.overlap = parallel.OverlappedGradientAllReduce(self.params) if sync == "overlap" else None
+        self.render_events = None
+
+    def grad_bytes(self):
+        return sum(p.numel() * p.element_size() for p in self.params)
+
+    def step(self):
+        azim, elev, dist = self.selector(self.points)
+        if self.render_events is not None:
+            self.render_events[0].record()
+        images, _ = self.renderer(self.meshes, None, azim, elev, dist)
+        if self.render_events is not None:
+            self.render_events[1].record()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+            loss = self.crit(self.cnn(images), self.targets)
+        self.opt.zero_grad(set_to_none=True); self.opt_mvtn.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.overlap is not None:
+            self.overlap.finish()
+        elif self.sync_mode == "after":
+            parallel.allreduce_gradients(self.params)
+        self.opt.step(); self.opt_mvtn.step()
+        return loss
+
+    def close(self):
+        if self.overlap is not None:
+            self.overlap.remove()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32, help="objects per GPU")
@@ -66,38 +115,23 @@ def main():
     ap.add_argument("--faces", type=int, default=10000)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--amp", action="store_true", help="bf16 autocast for the CNN (the renderer stays fp32)")
+    ap.add_argument("--sync", default="overlap", choices=["overlap", "after", "none"])
     a = ap.parse_args()
     rank, local_rank, world = parallel.init_distributed()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    torch.manual_seed(1234)                         # same initial weights on every rank
-    selector, cnn = ViewSelector(a.views).to(dev), MVCNN().to(dev)
-    renderer = MVRenderer(a.views, image_size=a.image_size, pc_rendering=False, light_direction="random").to(dev)
-    opt = torch.optim.AdamW(cnn.parameters(), lr=1e-3, weight_decay=0.01)
-    opt_mvtn = torch.optim.AdamW(selector.parameters(), lr=1e-4, weight_decay=0.01)
-    meshes = [Meshes([v], [f]) for v, f in synth.make_meshes(a.batch, a.faces, 4000 + 97 * rank)]   # this rank's objects
-    points = torch.stack([m.verts_list()[0][torch.randperm(m.verts_list()[0].shape[0])[:2048]] for m in meshes])
-    targets = torch.randint(0, 40, (a.batch,), generator=torch.Generator().manual_seed(rank))
-    params = list(cnn.parameters()) + list(selector.parameters())
-    crit = nn.CrossEntropyLoss()
+    ts = TrainStep(dev, rank, a.batch, a.views, a.image_size, a.faces, a.amp, a.sync)
     t0 = None
     for step in range(a.steps + 2):
         if step == 2:
             torch.cuda.synchronize(); parallel.barrier(); t0 = time.time()
-        azim, elev, dist = selector(points.to(dev))
-        images, _ = renderer(meshes, None, azim, elev, dist)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=a.amp):
-            loss = crit(cnn(images), targets.to(dev))
-        opt.zero_grad(set_to_none=True); opt_mvtn.zero_grad(set_to_none=True)
-        loss.backward()
-        parallel.allreduce_gradients(params)
-        opt.step(); opt_mvtn.step()
+        loss = ts.step()
     torch.cuda.synchronize(); parallel.barrier()
     dt = (time.time() - t0) / a.steps
-    g = sum(p.grad.abs().sum().item() for p in selector.parameters() if p.grad is not None)
+    g = sum(p.grad.abs().sum().item() for p in ts.selector.parameters() if p.grad is not None)
     if rank == 0:
         print(f"world {world}: {a.batch * world} objects x {a.views} views / step, {dt * 1e3:.1f} ms/step, "
-              f"{a.batch * world * a.views / dt:.0f} views/s end to end (render + ResNet-18 fwd/bwd + all-reduce); "
+              f"{a.batch * world * a.views / dt:.0f} views/s end to end (render + ResNet-18 fwd/bwd + all-reduce [{a.sync}]); "
               f"loss {loss.item():.3f}, |grad| into the view selector {g:.3e}")
     if world > 1:
         torch.distributed.destroy_process_group()

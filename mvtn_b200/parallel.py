@@ -104,3 +104,107 @@ def allreduce_gradients(params, bucket_bytes: int = 32 << 20, average: bool = Tr
             off += g.numel()
         n_buckets += 1
     return n_buckets
+
+
+class OverlappedGradientAllReduce:
+    """Hook-driven bucketed gradient all-reduce that runs DURING backward (BASELINE configs[3]: run_mvtn.py:168-224 sharded
+    by object, NCCL all-reduce of the MVTN regressor + backbone gradients; SURVEY 8e "bucketed and overlapped with backward").
+
+    Parameters are assigned to flat buckets in REVERSE registration order (the order autograd finishes them in, to first
+    order).  A post-accumulate-grad hook copies each finished gradient into its bucket slot; the moment a bucket is complete
+    its all-reduce is launched asynchronously (NCCL runs it on its own stream, under the rest of the backward pass: the
+    renderer's backward and the view selector's come LAST in the graph, so every backbone bucket is in flight before the
+    rasterizer's backward kernels start).  `finish()` -- call it after loss.backward() -- launches whatever is left, waits,
+    averages and scatters the buckets back into the .grad tensors.
+
+        sync = OverlappedGradientAllReduce(params)         # once
+        loss.backward(); sync.finish(); optimizer.step()   # every step
+
+    Single process / no process group: every call is a no-op."""
+
+    def __init__(self, params, bucket_bytes: int = 8 << 20, average: bool = True):
+        self.enabled = dist.is_initialized() and dist.get_world_size() > 1
+        self.average = average
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets = []          # dicts: params, offsets, flat (lazily), pending, handle
+        self._slot = {}
+        cur, size = [], 0
+        for p in reversed(self.params):
+            nbytes = p.numel() * p.element_size()
+            if cur and (size + nbytes > bucket_bytes or cur[0].dtype != p.dtype or cur[0].device != p.device):
+                self._close(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += nbytes
+        if cur:
+            self._close(cur)
+        self._hooks = []
+        if self.enabled:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self.launched_in_backward = 0      # buckets whose all-reduce was launched from a hook (statistics of the last step)
+
+    def _close(self, plist):
+        offs, o = [], 0
+        for p in plist:
+            offs.append(o)
+            o += p.numel()
+        b = {"params": list(plist), "offsets": offs, "numel": o, "flat": None, "pending": len(plist), "handle": None,
+             "filled": set()}
+        for i, p in enumerate(plist):
+            self._slot[id(p)] = (len(self.buckets), i)
+        self.buckets.append(b)
+
+    def _flat(self, b):
+        if b["flat"] is None:
+            p0 = b["params"][0]
+            b["flat"] = torch.zeros(b["numel"], dtype=p0.dtype, device=p0.device)
+        return b["flat"]
+
+    def _on_grad(self, p):
+        bi, i = self._slot[id(p)]
+        b = self.buckets[bi]
+        if i in b["filled"]:          # a parameter used twice in the graph: its hook fires once, after accumulation; be safe
+            return
+        flat = self._flat(b)
+        flat[b["offsets"][i]: b["offsets"][i] + p.numel()].copy_(p.grad.reshape(-1))
+        b["filled"].add(i)
+        if len(b["filled"]) == len(b["params"]):
+            b["handle"] = dist.all_reduce(flat, async_op=True)
+            self.launched_in_backward += 1
+
+    def finish(self):
+        """Launch the buckets that did not complete during backward (parameters without a gradient this step), wait for
+        all of them, average, and copy the reduced values back into the .grad tensors.  Returns the number of buckets."""
+        if not self.enabled:
+            return 0
+        world = dist.get_world_size()
+        for b in self.buckets:
+            if b["handle"] is None:
+                flat = self._flat(b)
+                for i, p in enumerate(b["params"]):       # unfilled slots: the parameter had no gradient on this rank
+                    if i not in b["filled"]:
+                        flat[b["offsets"][i]: b["offsets"][i] + p.numel()].zero_()
+                b["handle"] = dist.all_reduce(flat, async_op=True)
+        for b in self.buckets:
+            b["handle"].wait()
+            flat = b["flat"]
+            if self.average:
+                flat.div_(world)
+            for i, p in enumerate(b["params"]):
+                src = flat[b["offsets"][i]: b["offsets"][i] + p.numel()].view_as(p)
+                if p.grad is None:
+                    p.grad = src.clone()
+                else:
+                    p.grad.copy_(src)
+            b["handle"] = None
+            b["filled"] = set()
+        n = len(self.buckets)
+        self.stats = {"buckets": n, "launched_in_backward": self.launched_in_backward}
+        self.launched_in_backward = 0
+        return n
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

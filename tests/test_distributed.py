@@ -42,6 +42,23 @@ def _worker(rank, world, port, q):
     assert nb >= 2
     for i, p in enumerate(params[:-1]):
         assert torch.allclose(p.grad, torch.full_like(p, (i + 1) * (1 + world) / 2.0))
+    # (4) hook-driven all-reduce launched during backward (configs[3]): same result as averaging the full gradients
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 2))
+    unused = torch.nn.Parameter(torch.ones(3))                      # never reaches the loss: finish() must still reduce it
+    sync = parallel.OverlappedGradientAllReduce(list(net.parameters()) + [unused], bucket_bytes=128)
+    assert sync.enabled and len(sync.buckets) >= 3
+    for step in range(2):
+        x = torch.full((3, 6), float(rank + 1 + step))
+        net.zero_grad(set_to_none=(step == 0))
+        net(x).square().sum().backward()
+        local = [p.grad.clone() for p in net.parameters()]
+        assert sync.finish() == len(sync.buckets) and sync.stats["launched_in_backward"] >= len(sync.buckets) - 1
+        for p, g in zip(net.parameters(), local):
+            want = g.clone(); dist.all_reduce(want); want /= world
+            assert torch.allclose(p.grad, want, atol=1e-6)
+        assert unused.grad is not None and float(unused.grad.abs().sum()) == 0.0
+    sync.remove()
     parallel.barrier()
     dist.destroy_process_group()
     q.put((rank, lo, hi))

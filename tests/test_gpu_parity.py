@@ -127,13 +127,15 @@ def mesh_case(name):
         return dict(meshes=synth.make_meshes(1, 10000, 12), M=2, H=224, K=1, views=synth.circular_views(1, 2))
     if name == "odd_width_k1":      # W % 4 != 0: the tile-per-CTA backward instead of the cp.async strip kernel; 97 px: partial tiles
         return dict(meshes=synth.make_meshes(2, 900, 14), M=3, H=97, K=1, views=synth.learned_spherical_views(2, 3, 11))
+    if name == "c5_mesh_100k_400":  # BASELINE configs[4] shape: ~100k faces at 400x400 (two of the 20 spherical views; 3e10 oracle tests)
+        return dict(meshes=synth.make_meshes(1, 100000, 15), M=2, H=400, K=1, views=tuple(t[:, 4:6].contiguous() for t in synth.spherical_views(1, 20)))
     if name == "dense_subpixel":
         return dict(meshes=synth.make_meshes(1, 20000, 13), M=2, H=64, K=1, views=synth.learned_spherical_views(1, 2, 8))
     raise KeyError(name)
 
 
 MESH_CASES = ["small", "spherical", "ragged_k3", "cube_big_faces", "cull_noperspective", "vertex_rgb", "relative_light",
-              "close_camera_400", "c2_slice", "dense_subpixel", "odd_width_k1"]
+              "close_camera_400", "c2_slice", "dense_subpixel", "odd_width_k1", "c5_mesh_100k_400"]
 
 
 def run_mesh(oracle, dev, cfg, backward=True, extra_flags=0):
@@ -471,6 +473,7 @@ POINT_CASES = {
     "k3_norm_rgb": dict(B=2, Np=300, M=2, H=50, K=3, radius=0.04, mode="norm", views=synth.learned_spherical_views(2, 2, 3), per_point=True),
     "k1_alpha": dict(B=1, Np=1000, M=2, H=100, K=1, radius=0.02, mode="alpha", views=synth.circular_views(1, 2)),
     "k8_big_radius": dict(B=1, Np=400, M=2, H=40, K=8, radius=0.15, mode="alpha", views=synth.learned_spherical_views(1, 2, 5), per_point=True),
+    "c5_16k_400_k4_alpha": dict(B=1, Np=16384, M=2, H=400, K=4, radius=0.006, mode="alpha", views=tuple(t[:, 7:9].contiguous() for t in synth.spherical_views(1, 20))),
     "c5_16k_400": dict(B=1, Np=16384, M=2, H=400, K=1, radius=0.006, mode="norm", views=tuple(t[:, 4:6].contiguous() for t in synth.spherical_views(1, 20))),
 }
 
@@ -984,7 +987,30 @@ def test_bench_line_carries_the_contract_keys_and_parity(cuda_device, workload):
     assert par["image_max_abs_err"] <= par["tolerance"]["images_abs"]
     assert par["grad_camera_max_rel_err"] <= par["tolerance"]["gradients_rel"]
     assert par["look_at_max_abs_err"] <= par["tolerance"]["look_at_abs"]
-    assert par["look_at_backward_max_rel_err"] <= 1e-4
+    assert par["look_at_backward_max_rel_err"] <= 1e-4 and par["pass"]
+
+
+def test_bench_extra_records_carry_parity_baseline_and_roofline(cuda_device):
+    """`bench.py --extras tiny`: the sub-records of BASELINE configs[0], [2] and both configs[4] shapes ride in the ONE JSON line,
+    each with its own parity gates, CPU baseline (stated sub-sample) and roofline."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--batch", "2", "--views", "3", "--image-size", "64", "--faces", "600",
+           "--steps", "2", "--warmup", "1", "--cpu-sample-objects", "1", "--extras", "tiny"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert set(d["extra"]) == {"c1_points", "c3_points", "c5_mesh", "c5_points"}
+    for name, rec in d["extra"].items():
+        assert rec["value"] > 0 and rec["e2e"]["value"] > 0 and rec["gpu_launches"] > 0, name
+        assert rec["parity"]["index_mismatches"] == 0 and rec["parity"]["pass"], (name, rec["parity"])
+        assert rec["cpu_baseline"]["value"] > 0 and "sample" in rec["cpu_baseline"], name
+        assert rec["roofline"]["bound"] == "hbm" and rec["roofline"]["step"]["frac"] > 0, name
+        assert "workload" in rec["config"] and "l2" in rec["config"], name
 
 
 def test_mvrenderer_points_cuda_graph_mode_matches_eager(cuda_device):
