@@ -46,6 +46,10 @@ extern "C" {
 #define MVR_IDX_SPARSE 1024        /* mvr_points_forward (K in {1,2,4,8}, hit_mask given, no zbuf / dists2 wanted): idx is written
                                       only where the pixel's hit_mask bit is set -- 4 K bytes per background pixel (~90 % of a
                                       point image) are not stored; mvr_points_backward never reads them */
+#define MVR_FORWARD_TILED 2048     /* mvr_mesh_forward, K == 1: the tile-binned rasterizer + shader (coarse binning pass, per-tile face
+                                      lists staged by TMA bulk copies, depth keys in shared memory, shading in the same CTA) instead of
+                                      the default bin-free scatter + shade pair.  Same fragments bit for bit; slower on B200 at the
+                                      BASELINE sizes, kept selectable for A/B measurements */
 #define MVR_TEST_TINY_QUEUES 0x40000000 /* tests only: shrink the scatter kernel's work queues to force their fallbacks */
 
 /* Phong constants of DirectionalLights() / Materials() as constructed at renderer.py:190-191 */
@@ -134,8 +138,9 @@ int mvr_mesh_normals_backward(const void* geometry, const int* vert_off, const i
                               float* grad_verts, void* stream);
 
 /* scratch for one forward or backward call: projected vertices of every view (16 B * M * total_verts), the
- * pixel-centre table, and the 64-bit key plane(s) / backward partial sums */
-size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K, int64_t total_verts);
+ * pixel-centre table, the 64-bit key plane(s) / backward partial sums and, for K == 1, the per-(view, tile) face lists of the
+ * binned rasterizer (<= 24 B * M * total_faces) */
+size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K, int64_t total_verts, int64_t total_faces);
 /* MeshRenderer(MeshRasterizer, HardPhongShader)(meshes.extend(M), cameras, lights)
  * (renderer.py:89-113; [upstream] _C.rasterize_meshes + interp_face_attrs + phong_shading +
  * hard_rgb_blend).  blur_radius = 0.

@@ -17,6 +17,7 @@ WS_KEYS_ARMED = 128    # workspace reuse hints of the mesh path (include/mvr_b20
 WS_REARM_KEYS = 256
 WS_PROJECTED = 512
 IDX_SPARSE = 1024
+FORWARD_TILED = 2048     # mesh forward, K == 1: tile-binned rasterizer + shader (opt-in A/B alternative)
 TEST_TINY_QUEUES = 0x40000000   # tests only: shrink the scatter kernel's work queues to force their fallbacks
 CNT_STRADDLE, CNT_BIG_FACES, NUM_COUNTERS = 0, 1, 4
 
@@ -42,7 +43,7 @@ SIGNATURES = {
     "mvr_mesh_prepare": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _i, _vp, _sz, _vp]),
     "mvr_mesh_get_normals": (_i, [_vp, _i64, _i64, _vp, _vp]),
     "mvr_mesh_normals_backward": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp]),
-    "mvr_mesh_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i64]),
+    "mvr_mesh_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i64, _i64]),
     "mvr_mesh_forward": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _f, _f,
                               _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mvr_mesh_backward": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _f, _f, _f, _i, _i, _i, _i,

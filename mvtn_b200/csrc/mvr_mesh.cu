@@ -22,7 +22,7 @@
 //   backward: mesh_backward_kernel -- per pixel recompute (no fragment traffic), chain
 //             d image -> Phong -> barycentrics -> NDC verts -> view verts -> (dR, dT, dC), block-reduced to
 //             one partial per CTA and summed in fixed order (deterministic, no float atomics).
-#include "mvr_mesh.cuh"
+#include "mvr_mesh_fwd.cuh"
 
 namespace mvr {
 
@@ -141,108 +141,15 @@ __global__ void geom_get_normals_kernel(const float4* __restrict__ normals4, int
   out[3 * v] = n.x; out[3 * v + 1] = n.y; out[3 * v + 2] = n.z;
 }
 
-// ------------------------------------------------------------------------------------------------
-// shared device code: projection, face setup and the per-(face, pixel) test
-// ------------------------------------------------------------------------------------------------
-// Face-level rejection ([upstream] clip.py near cull, CheckPointOutsideBoundingBox z_invalid,
-// RasterizeMeshesNaiveCpu zero-area / back-face tests) and the exact pixel bbox (inclusive ranges).
-__device__ __forceinline__ bool face_pixel_bbox(const Face& f, const MeshParams& p, const float* s_xf, const float* s_yf,
-                                                int& xi_lo, int& xi_hi, int& yi_lo, int& yi_hi) {
-  if (p.z_clip >= 0.f && f.z0 < p.z_clip && f.z1 < p.z_clip && f.z2 < p.z_clip) return false;
-  const float zmin = fminf(fminf(f.z0, f.z1), f.z2);
-  if (zmin < MVR_K_EPS) return false;
-  const float face_area = (f.x0 - f.x1) * (f.y2 - f.y1) - (f.y0 - f.y1) * (f.x2 - f.x1);
-  if ((p.flags & MVR_CULL_BACKFACES) && face_area < 0.f) return false;
-  if (face_area <= MVR_K_EPS && face_area >= -1.0f * MVR_K_EPS) return false;
-  const float xmin = fminf(fminf(f.x0, f.x1), f.x2), xmax = fmaxf(fmaxf(f.x0, f.x1), f.x2);
-  const float ymin = fminf(fminf(f.y0, f.y1), f.y2), ymax = fmaxf(fmaxf(f.y0, f.y1), f.y2);
-  pixel_range(xmin, xmax, p.W, p.H, 0, p.W - 1, s_xf, xi_lo, xi_hi);
-  if (xi_lo > xi_hi) return false;
-  pixel_range(ymin, ymax, p.H, p.W, 0, p.H - 1, s_yf, yi_lo, yi_hi);
-  return yi_lo <= yi_hi;
-}
-
-// ------------------------------------------------------------------------------------------------
-// scatter pass
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int smem_addr_pinned(const void* ptr) {
-  unsigned int a;
-  asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(ptr));
-  return a;
-}
-__device__ __forceinline__ unsigned int lanemask_lt() {
-  unsigned int m;
-  asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-  return m;
-}
-__device__ __forceinline__ float lds_f32(unsigned int a) {
-  float v;
-  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts_u32(unsigned int a, unsigned int v) {
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-
-// exact test of one (face, pixel) candidate and the keyed min on the global key plane
-__device__ __forceinline__ void resolve_pixel_with(const Face& fc, const FaceEdges& fe, int fid, unsigned int zmin_bits,
-                                                   bool persp, float xf, float yf, unsigned long long* key_ptr,
-                                                   const unsigned long long* prev_ptr, const unsigned long long cur);
-__device__ __forceinline__ void resolve_pixel(const Face& fc, const FaceEdges& fe, int fid, unsigned int zmin_bits,
-                                              bool persp, float xf, float yf, unsigned long long* key_ptr,
-                                              const unsigned long long* prev_ptr) {
-  resolve_pixel_with(fc, fe, fid, zmin_bits, persp, xf, yf, key_ptr, prev_ptr, __ldcg(key_ptr));
-}
-// cur: a snapshot of *key_ptr taken earlier (keys only decrease, so a stale snapshot is merely less effective)
-__device__ __forceinline__ void resolve_pixel_with(const Face& fc, const FaceEdges& fe, int fid, unsigned int zmin_bits,
-                                                   bool persp, float xf, float yf, unsigned long long* key_ptr,
-                                                   const unsigned long long* prev_ptr, const unsigned long long cur) {
-  // early depth reject: pz is a convex combination of the vertex depths up to a few ulp (perspective-corrected
-  // barycentrics sum to 1 unless their 1e-8 denominator clamp acts, which needs z ~ 1e-4; plain barycentrics sum
-  // to area/(area+1e-8), so zmin_bits is 0 for them), hence a face whose nearest vertex is clearly behind the
-  // pixel's current winner cannot produce a smaller key.  A stale `cur` only makes the test less effective.
-  if (zmin_bits > (unsigned int)(cur >> 32)) return;
-  float w[3], b[3], pz;
-  if (!raster_test(fc, fe, persp, xf, yf, w, b, pz)) return;
-  const unsigned long long key = make_key(pz, fid);
-  if (key >= cur) return;
-  if (prev_ptr && key <= __ldcg(prev_ptr)) return;
-  atomicMin(key_ptr, key);      // result unused: RED.MIN.64 resolved in L2
-}
-
-// Phase B's pixel filter in FMA form.  Edge function i of the oracle, e_i = (px - xa) A - (py - ya) B (five IEEE
-// operations), is evaluated as fma(px, A, fma(-py, B, C)) with C = ya B - xa A: two instructions.  The two differ by
-// rounding only: with u = 2^-24, |px|, |py| <= pmax (1, or the aspect ratio of a non-square image) and
-// S = (pmax + |xa|) |A| + (pmax + |ya|) |B|, the IEEE sequence is within
-// 3 u S of the real value and the FMA form within 4 u S, so adding 16 u S to C makes "fma form > 0" a NECESSARY condition
-// for "IEEE form > 0": the filter never drops a pixel the exact test of phase C would accept, it only lets a few pixels
-// within 2^-20 S of an edge through to be rejected there.  The sign of the area is folded into (A, B, C) first (negation
-// is exact).  Record words 12..20 of the face: (A0, B0, C0', A1, B1, C1', A2, B2, C2').
-__device__ __forceinline__ void store_filter_edges(const Face& f, float pmax, float* rec) {
-  float A[3] = {f.y2 - f.y1, f.y0 - f.y2, f.y1 - f.y0};
-  float B[3] = {f.x2 - f.x1, f.x0 - f.x2, f.x1 - f.x0};
-  const float xa[3] = {f.x1, f.x2, f.x0}, ya[3] = {f.y1, f.y2, f.y0};
-  const float area_p = ((f.x2 - f.x0) * A[2] - (f.y2 - f.y0) * B[2]) + MVR_K_EPS;
-  const bool flip = !(area_p > 0.f);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    if (flip) { A[i] = -A[i]; B[i] = -B[i]; }
-    const float C = ya[i] * B[i] - xa[i] * A[i];
-    const float S = (pmax + fabsf(xa[i])) * fabsf(A[i]) + (pmax + fabsf(ya[i])) * fabsf(B[i]);
-    rec[(3 * i + 0) * MVR_THREADS] = A[i];
-    rec[(3 * i + 1) * MVR_THREADS] = B[i];
-    rec[(3 * i + 2) * MVR_THREADS] = C + 9.5367431640625e-07f * S;      // 2^-20
-  }
-}
+constexpr int SC_REC_WORDS = 13;      // x0 y0 z0 x1 y1 z1 x2 y2 z2 fid zmin_bits | rect_xy rect_wh (big faces only)
+constexpr int SC_QCAP = 3072;         // candidates per round (256 faces x ~4.6 inside pixels at C2)
 
 template <int MINB>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const MeshParams p) {
-  __shared__ float s_rec[REC_WORDS][MVR_THREADS];     // SoA face records of the current round
-  __shared__ int s_items[ITEM_CAP];                    // slot | start << 8 | count << 18
-  __shared__ int s_cand[NWARPS][WCAP];                 // slot | x << 8 | y << 20
+  __shared__ float s_rec[SC_REC_WORDS][MVR_THREADS];  // SoA face records of the current round
+  __shared__ int s_q[SC_QCAP];                         // candidates of the round: slot | x << 8 | y << 20
   __shared__ int s_big[MVR_THREADS];
-  __shared__ int s_cnt[2];                             // [0] items, [1] big faces
-  __shared__ int s_wcnt[NWARPS];
+  __shared__ int s_cnt2[2][2];                         // per round parity: [0] candidates, [1] big faces
   extern __shared__ float s_tab[];                     // pixel centres: xf[W], yf[H]
   const float* s_xf = s_tab;
   const float* s_yf = s_tab + p.W;
@@ -258,156 +165,113 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
   const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
   unsigned long long* keys = p.keys + (size_t)n * p.H * p.W;
   const unsigned long long* prev = p.layer > 0 ? p.prev + (size_t)n * p.H * p.W : nullptr;
+  const int qcap = p.wcap;      // SC_QCAP, or a handful under MVR_TEST_TINY_QUEUES
 
   for (int i = tid; i < p.W + p.H; i += MVR_THREADS) s_tab[i] = __ldg(p.tab + i);
-  if (tid < 2) s_cnt[tid] = 0;
+  if (tid < 4) (&s_cnt2[0][0])[tid] = 0;
   __syncthreads();
-  // shared-memory byte addresses and the lane mask, pinned in registers (volatile asm is never rematerialised: the
-  // compiler otherwise rebuilds them from SR_TID / SR_CgaCtaId inside the phase-B inner loop)
-  const unsigned int tab_a = smem_addr_pinned(s_tab);
-  const unsigned int my_cand_a = smem_addr_pinned(&s_cand[warp][0]);
-  const unsigned int lt_mask = lanemask_lt();
+  const unsigned int q_a = smem_addr_pinned(&s_q[0]);
 
   int n_straddle = 0, n_big = 0;
-  for (int rbeg = fbeg; rbeg < fend; rbeg += MVR_THREADS) {
-    // ---------------- phase A: setup, one thread per face ----------------
+  for (int rbeg = fbeg, rpar = 0; rbeg < fend; rbeg += MVR_THREADS, rpar ^= 1) {
+    int* s_cnt = s_cnt2[rpar];
+    // ---------------- phase A: setup + scanline spans, one thread per face ----------------
+    // gather, cull, exact bbox, then ROW BY ROW the interval of pixels that can pass the edge filter (row_span_regs): its
+    // pixels go straight to the round's candidate queue.  The filter coefficients never leave the registers.
     const int fid = rbeg + tid;
+    int xl = 0, yl = 0, bw = 0, bh = 0;
+    SpanEdges se;
     if (fid < fend) {
       const Face fc = gather_face(pvn, __ldg(p.faces4 + f0 + fid));
-      int xl, xh, yl, yh;
-      if (face_straddles(fc, p.z_clip)) {
-        // crosses the near clip plane ([upstream] clip.py): counted, visible or not (as the oracle does), and handed to
-        // the whole CTA below, which rasterizes its one or two clipped sub-triangles
-        n_straddle += p.layer == 0;
+      int xh, yh;
+      const bool straddles = face_straddles(fc, p.z_clip);
+      if (straddles || face_pixel_bbox_conservative(fc, p, xl, xh, yl, yh)) {
         s_rec[0][tid] = fc.x0; s_rec[1][tid] = fc.y0; s_rec[2][tid] = fc.z0;
         s_rec[3][tid] = fc.x1; s_rec[4][tid] = fc.y1; s_rec[5][tid] = fc.z1;
         s_rec[6][tid] = fc.x2; s_rec[7][tid] = fc.y2; s_rec[8][tid] = fc.z2;
         s_rec[9][tid] = __int_as_float(fid);
-        s_big[atomicAdd(&s_cnt[1], 1)] = tid | 0x100;
-      } else if (face_pixel_bbox(fc, p, s_xf, s_yf, xl, xh, yl, yh)) {
-        const int bw = xh - xl + 1, bh = yh - yl + 1, npx = bw * bh;
-        s_rec[0][tid] = fc.x0; s_rec[1][tid] = fc.y0; s_rec[2][tid] = fc.z0;
-        s_rec[3][tid] = fc.x1; s_rec[4][tid] = fc.y1; s_rec[5][tid] = fc.z1;
-        s_rec[6][tid] = fc.x2; s_rec[7][tid] = fc.y2; s_rec[8][tid] = fc.z2;
-        s_rec[9][tid] = __int_as_float(fid);
-        s_rec[10][tid] = __int_as_float(xl | (yl << 16));
-        s_rec[11][tid] = __int_as_float(bw | (bh << 16));
-        store_filter_edges(fc, p.ndc_max, &s_rec[12][tid]);
-        bool queued = false;
-        if (npx <= BIG_FACE_PIX) {
-          // runs of G pixels: 8 for ordinary faces, up to 32 for large ones (<= 32 runs per face)
-          int G = 8, nsub = (npx + 7) >> 3;
-          if (npx > 256) { G = (npx + 31) >> 5; nsub = (npx + G - 1) / G; }      // the division only for the rare large face
-          const int at = atomicAdd(&s_cnt[0], nsub);
-          if (at + nsub <= p.item_cap) {
-            for (int q = 0; q < nsub; ++q) s_items[at + q] = tid | ((q * G) << 8) | (min(G, npx - q * G) << 18);
-            queued = true;
+        const float zmin = fminf(fminf(fc.z0, fc.z1), fc.z2);
+        s_rec[10][tid] = __uint_as_float((persp && zmin > 1e-3f) ? __float_as_uint(zmin * 0.999999f) : 0u);
+        if (straddles) {
+          // crosses the near clip plane ([upstream] clip.py): counted, visible or not (as the oracle does), and handed to
+          // the whole CTA below, which rasterizes its one or two clipped sub-triangles
+          n_straddle += p.layer == 0;
+          s_big[atomicAdd(&s_cnt[1], 1)] = tid | 0x100;
+        } else {
+          bw = xh - xl + 1; bh = yh - yl + 1;
+          if (bw * bh > BIG_FACE_PIX) {      // walked by the whole CTA below
+            s_rec[11][tid] = __int_as_float(xl | (yl << 16));
+            s_rec[12][tid] = __int_as_float(bw | (bh << 16));
+            s_big[atomicAdd(&s_cnt[1], 1)] = tid;
+            bh = 0;
           } else {
-            for (int q = at; q < p.item_cap; ++q) s_items[q] = 0;      // a straddling reservation leaves no garbage
+            se = span_edges(fc, p.ndc_max);
           }
         }
-        if (!queued) s_big[atomicAdd(&s_cnt[1], 1)] = tid;               // walked by the whole CTA below
       }
     }
-    __syncthreads();
-    // ---------------- phase B: sign filter over bbox pixels, per-warp candidate queues ----------------
-    const int n_items = min(s_cnt[0], p.item_cap);
-    const int n_bigf = s_cnt[1];
-    int wcnt = 0;                                // warp-uniform: candidates queued by this warp
-    for (int j0 = warp * 32; j0 < n_items; j0 += MVR_THREADS) {      // warp-uniform trip count
-      const int j = j0 + lane;
-      int slot = 0, count = 0;
-      unsigned int xl_a = tab_a, xend_a = tab_a + 4u, xa = tab_a, ya = tab_a;     // shared-memory BYTE addresses
-      float A0 = 0.f, B0 = 0.f, C0 = 0.f, A1 = 0.f, B1 = 0.f, C1 = 0.f, A2 = 0.f, B2 = 0.f, C2 = 0.f;
-      if (j < n_items) {
-        const int it = s_items[j];
-        slot = it & 255; count = it >> 18;
-        const int start = (it >> 8) & 1023;
-        A0 = s_rec[12][slot]; B0 = s_rec[13][slot]; C0 = s_rec[14][slot];
-        A1 = s_rec[15][slot]; B1 = s_rec[16][slot]; C1 = s_rec[17][slot];
-        A2 = s_rec[18][slot]; B2 = s_rec[19][slot]; C2 = s_rec[20][slot];
-        const int rxy = __float_as_int(s_rec[10][slot]);
-        const int xl = rxy & 0xffff;
-        const int bw = __float_as_int(s_rec[11][slot]) & 0xffff;
-        const int row = (int)__fdividef((float)start + 0.5f, (float)bw);     // small integers: exact
-        xl_a = tab_a + 4u * (unsigned)xl;
-        xend_a = xl_a + 4u * (unsigned)bw;
-        xa = xl_a + 4u * (unsigned)(start - row * bw);                       // address of xf of the run's first pixel
-        ya = tab_a + 4u * (unsigned)(p.W + (rxy >> 16) + row);               // address of its yf
-      }
-      // candidate word = slot | x << 8 | y << 20 with x = (xa - tab_a) / 4, y = (ya - tab_a) / 4 - W: constants folded
-      const unsigned int cand_m = (unsigned)slot - (tab_a << 6) - ((tab_a + 4u * (unsigned)p.W) << 18);
-      const int maxc = __reduce_max_sync(0xffffffffu, count);
-      for (int c = 0; c < maxc; ++c) {
-        const unsigned int cxa = xa, cya = ya;
-        bool pass = false;
-        if (c < count) {
-          const float xf = lds_f32(xa), yf = lds_f32(ya);
-          // conservative FMA form of the three edge functions (store_filter_edges): necessary for the exact test
-          const float e0 = fmaf(xf, A0, fmaf(-yf, B0, C0));
-          const float e1 = fmaf(xf, A1, fmaf(-yf, B1, C1));
-          const float e2 = fmaf(xf, A2, fmaf(-yf, B2, C2));
-          pass = e0 > 0.f && e1 > 0.f && e2 > 0.f;
-          xa += 4u;
-          if (xa == xend_a) { xa = xl_a; ya += 4u; }
-        }
-        const unsigned int mk = __ballot_sync(0xffffffffu, pass);
-        if (mk == 0u) continue;
-        if (pass) {
-          const int at = wcnt + __popc(mk & lt_mask);
-          if (at < p.wcap) {
-            sts_u32(my_cand_a + 4u * (unsigned)at, cand_m + (cxa << 6) + (cya << 18));
-          } else {                                                  // queue full: resolve in place
-            const int xx = (int)((cxa - tab_a) >> 2), yy = (int)((cya - tab_a) >> 2) - p.W;
-            Face fc;
-            fc.x0 = s_rec[0][slot]; fc.y0 = s_rec[1][slot]; fc.z0 = s_rec[2][slot];
-            fc.x1 = s_rec[3][slot]; fc.y1 = s_rec[4][slot]; fc.z1 = s_rec[5][slot];
-            fc.x2 = s_rec[6][slot]; fc.y2 = s_rec[7][slot]; fc.z2 = s_rec[8][slot];
-            resolve_pixel(fc, face_edges(fc), __float_as_int(s_rec[9][slot]), 0u, persp, s_xf[xx], s_yf[yy],
-                          keys + (size_t)yy * p.W + xx, prev ? prev + (size_t)yy * p.W + xx : nullptr);
-          }
-        }
-        wcnt += __popc(mk);
-      }
-    }
-    if (lane == 0) s_wcnt[warp] = min(wcnt, p.wcap);
-    __syncthreads();
-    // ---------------- phase C: exact resolve, candidates of all warps spread over all threads ----------------
-    if (tid < 2) s_cnt[tid] = 0;          // every thread read both counts before the barrier above
     {
-      int pre[NWARPS + 1];
-      pre[0] = 0;
+      const int maxr = __reduce_max_sync(0xffffffffu, bh);
+      for (int row = 0; row < maxr; ++row) {      // warp-uniform trip count
+        int cnt = 0, xs = 0;
+        const int yy = yl + row;
+        if (row < bh) cnt = row_span_regs(se, s_yf[yy], xl, bw, p.W, p.jx_scale, p.jx_off, xs);
+        int incl = cnt;
 #pragma unroll
-      for (int wi = 0; wi < NWARPS; ++wi) pre[wi + 1] = pre[wi] + s_wcnt[wi];
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&s_cnt[0], total);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+        const unsigned int word0 = (unsigned)tid | ((unsigned)xs << 8) | ((unsigned)yy << 20);
+        const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+        for (int c = 0; c < maxc; ++c) {
+          if (c < cnt) {
+            const int at = base + c;
+            if (at < qcap) {
+              sts_u32(q_a + 4u * (unsigned)at, word0 + ((unsigned)c << 8));
+            } else {                                                  // queue full: resolve in place
+              const int xx = xs + c;
+              Face fc;
+              fc.x0 = s_rec[0][tid]; fc.y0 = s_rec[1][tid]; fc.z0 = s_rec[2][tid];
+              fc.x1 = s_rec[3][tid]; fc.y1 = s_rec[4][tid]; fc.z1 = s_rec[5][tid];
+              fc.x2 = s_rec[6][tid]; fc.y2 = s_rec[7][tid]; fc.z2 = s_rec[8][tid];
+              resolve_pixel(fc, face_edges(fc), fid, 0u, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
+                            prev ? prev + (size_t)yy * p.W + xx : nullptr);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- phase C: exact resolve, the round's candidates spread over all threads ----------------
+    const int total_c = min(s_cnt[0], qcap);
+    const int n_bigf = s_cnt[1];
+    if (tid < 2) s_cnt2[rpar ^ 1][tid] = 0;      // the next round's counters (last read before the barrier that ended the previous round)
+    {
       // the key of the NEXT candidate is fetched before the current one is resolved: its trip to L2 overlaps the
-      // divisions instead of stalling the early depth test (a thread resolves ~3-4 candidates per round)
-      const int total_c = pre[NWARPS];
-      auto fetch = [&](int j) -> int {
-        int wi = 0;
-#pragma unroll
-        for (int q = 1; q < NWARPS; ++q) wi += (j >= pre[q]);
-        return s_cand[wi][j - pre[wi]];
-      };
+      // divisions instead of stalling the early depth test (a thread resolves ~4-5 candidates per round)
       int cd_next = 0;
       unsigned long long cur_next = 0ull;
       if (tid < total_c) {
-        cd_next = fetch(tid);
+        cd_next = s_q[tid];
         cur_next = __ldcg(keys + (size_t)((cd_next >> 20) & 4095) * p.W + ((cd_next >> 8) & 4095));
       }
       for (int j = tid; j < total_c; j += MVR_THREADS) {
         const int cd = cd_next;
         const unsigned long long cur = cur_next;
         if (j + MVR_THREADS < total_c) {
-          cd_next = fetch(j + MVR_THREADS);
+          cd_next = s_q[j + MVR_THREADS];
           cur_next = __ldcg(keys + (size_t)((cd_next >> 20) & 4095) * p.W + ((cd_next >> 8) & 4095));
         }
         const int slot = cd & 255, xx = (cd >> 8) & 4095, yy = (cd >> 20) & 4095;
+        const unsigned int zmin_bits = __float_as_uint(s_rec[10][slot]);
+        if (zmin_bits > (unsigned int)(cur >> 32)) continue;      // hidden: before the face record is even read
         Face fc;
         fc.x0 = s_rec[0][slot]; fc.y0 = s_rec[1][slot]; fc.z0 = s_rec[2][slot];
         fc.x1 = s_rec[3][slot]; fc.y1 = s_rec[4][slot]; fc.z1 = s_rec[5][slot];
         fc.x2 = s_rec[6][slot]; fc.y2 = s_rec[7][slot]; fc.z2 = s_rec[8][slot];
-        const float zmin = fminf(fminf(fc.z0, fc.z1), fc.z2);
-        const unsigned int zmin_bits = (persp && zmin > 1e-3f) ? __float_as_uint(zmin * 0.999999f) : 0u;
         resolve_pixel_with(fc, face_edges(fc), __float_as_int(s_rec[9][slot]), zmin_bits, persp, s_xf[xx], s_yf[yy],
                            keys + (size_t)yy * p.W + xx, prev ? prev + (size_t)yy * p.W + xx : nullptr, cur);
       }
@@ -438,13 +302,12 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
         continue;
       }
       const FaceEdges fe = face_edges(fc);
-      const int rxy = __float_as_int(s_rec[10][slot]), rwh = __float_as_int(s_rec[11][slot]);
-      const int xl = rxy & 0xffff, yl = rxy >> 16, bw = rwh & 0xffff, bh = rwh >> 16;
-      const float zmin = fminf(fminf(fc.z0, fc.z1), fc.z2);
-      const unsigned int zmin_bits = (persp && zmin > 1e-3f) ? __float_as_uint(zmin * 0.999999f) : 0u;
-      for (int y = warp; y < bh; y += NWARPS)
-        for (int x = lane; x < bw; x += 32) {
-          const int xx = xl + x, yy = yl + y;
+      const int rxy = __float_as_int(s_rec[11][slot]), rwh = __float_as_int(s_rec[12][slot]);
+      const int bxl = rxy & 0xffff, byl = rxy >> 16, bbw = rwh & 0xffff, bbh = rwh >> 16;
+      const unsigned int zmin_bits = __float_as_uint(s_rec[10][slot]);
+      for (int y = warp; y < bbh; y += NWARPS)
+        for (int x = lane; x < bbw; x += 32) {
+          const int xx = bxl + x, yy = byl + y;
           resolve_pixel(fc, fe, bfid, zmin_bits, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
                         prev ? prev + (size_t)yy * p.W + xx : nullptr);
         }
@@ -464,24 +327,6 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
 // ------------------------------------------------------------------------------------------------
 // shade pass: one thread per pixel
 // ------------------------------------------------------------------------------------------------
-// Barycentrics of a pixel KNOWN to be inside its face, for shading only (images are compared at 1e-5): the edge
-// functions come from the same projected vertices as the scatter pass, so they are bit-identical to the rasterizer's;
-// only the six IEEE divisions are replaced by two SFU reciprocals (a few ulp on b, ~1e-7 on the colour).  The exact
-// sequence (raster_test) is used whenever the caller asks for the barycentrics themselves.
-__device__ __forceinline__ void shading_barycentrics(const Face& f, const FaceEdges& e, bool persp, float xf, float yf,
-                                                     float b[3]) {
-  const float e0 = (xf - f.x1) * e.A0 - (yf - f.y1) * e.B0;
-  const float e1 = (xf - f.x2) * e.A1 - (yf - f.y2) * e.B1;
-  const float e2 = (xf - f.x0) * e.A2 - (yf - f.y0) * e.B2;
-  const float ia = rcp_fast(e.area_p);
-  b[0] = e0 * ia; b[1] = e1 * ia; b[2] = e2 * ia;
-  if (persp) {
-    const float t0 = b[0] * f.z1 * f.z2, t1 = b[1] * f.z0 * f.z2, t2 = b[2] * f.z0 * f.z1;
-    const float id = rcp_fast(fmaxf(t0 + t1 + t2, MVR_K_EPS));
-    b[0] = t0 * id; b[1] = t1 * id; b[2] = t2 * id;
-  }
-}
-
 // grid: x = 32 x (8 PPT)-pixel tiles of the image, y = view m, z = object b.  EXACT: the caller wants zbuf / bary / dists.
 // PPT pixels per thread (rows yi0 + 8 j): the keys -- the one operand that comes from DRAM -- of all of them are
 // loaded before the first is shaded, so a thread pays the DRAM trip once instead of once per pixel; the dependent L2
@@ -633,9 +478,9 @@ extern "C" int mvr_mesh_normals_backward(const void* geometry, const int* vert_o
   return check_launch("mvr_mesh_normals_backward");
 }
 
-extern "C" size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K, int64_t total_verts) {
-  if (B < 0 || M < 0 || H <= 0 || W <= 0 || K < 1 || total_verts < 0) return 0;
-  return ws_layout(B, M, H, W, K, total_verts).total;
+extern "C" size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K, int64_t total_verts, int64_t total_faces) {
+  if (B < 0 || M < 0 || H <= 0 || W <= 0 || K < 1 || total_verts < 0 || total_faces < 0) return 0;
+  return ws_layout(B, M, H, W, K, total_verts, total_faces).total;
 }
 
 // tuning knob (profiling only): MVR_SCATTER_MINB=3 trades occupancy (3 CTAs/SM, 85 registers) for fewer
@@ -690,7 +535,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   }
   if (!(flags & MVR_RGB_PER_ELEMENT) && !obj_rgb) { set_error("mvr_mesh_forward: obj_rgb is NULL and the geometry has no per-vertex colours"); return -6; }
   if (!out_norm_valid(out_mean_std)) { set_error("mvr_mesh_forward: out_mean_std needs std > 0"); return -9; }
-  const WsLayout w = ws_layout(B, M, H, W, K, total_verts);
+  const WsLayout w = ws_layout(B, M, H, W, K, total_verts, total_faces);
   if (workspace_bytes < w.total) { set_error("mvr_mesh_forward: workspace too small (%zu < %zu)", workspace_bytes, w.total); return -7; }
   const int fpc = scatter_fpc();
   const int chunks_per_view = max_faces > 0 ? (max_faces + fpc - 1) / fpc : 0;
@@ -709,8 +554,14 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.B = B; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags;
   p.chunks_per_view = chunks_per_view; p.layer = 0; p.faces_per_cta = fpc;
   p.ndc_max = W > H ? (float)((W + H - 1) / H) : (float)((H + W - 1) / W);      // bound on |pixel-centre NDC| (>= aspect ratio)
+  {
+    const float rx = W > H ? 2.0f * (float)(W / H) : 2.0f;
+    const float ry = H > W ? 2.0f * (float)(H / W) : 2.0f;
+    p.jx_scale = (float)W / rx; p.jx_off = (0.5f * rx * (float)W - 0.5f * rx) / rx;
+    p.jy_scale = (float)H / ry; p.jy_off = (0.5f * ry * (float)H - 0.5f * ry) / ry;
+  }
   p.item_cap = (flags & MVR_TEST_TINY_QUEUES) ? 24 : ITEM_CAP;
-  p.wcap = (flags & MVR_TEST_TINY_QUEUES) ? 5 : WCAP;
+  p.wcap = (flags & MVR_TEST_TINY_QUEUES) ? 40 : SC_QCAP;      // candidate queue of a round (scatter kernel)
   p.pv = (float4*)(wb + w.pv); p.tab = (float*)(wb + w.tab);
   p.keys = (unsigned long long*)(wb + w.keys); p.prev = (unsigned long long*)(wb + w.prev);
   p.images = images; p.pix_to_face = pix_to_face; p.zbuf = zbuf; p.bary = bary; p.dists = dists;
@@ -718,6 +569,18 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.onorm = make_out_norm(out_mean_std);
   p.wsflags = (int*)(wb + w.flags);
   const size_t HW = (size_t)H * W;
+  if (K == 1 && ((flags & MVR_FORWARD_TILED) || mesh_tiled_enabled())) {
+    // tile-binned path (mvr_mesh_tile.cu): keys live in shared memory -- no key plane, no memset of it, no separate shade pass
+    p.flags &= ~(MVR_WS_KEYS_ARMED | MVR_WS_REARM_KEYS);
+    cudaError_t e = cudaMemsetAsync(wb + w.flags, 0xFF, 4 * sizeof(int), st);      // arms WSF_CLIP
+    if (e != cudaSuccess) { set_error("mvr_mesh_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+    rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, z_clip, false, workspace, st);
+    if (rc) return rc;
+    rc = launch_mesh_forward_tiled(p, w, workspace, B, M, max_faces, zbuf || bary || dists, st);
+    if (rc) return rc;
+    if (z_clip >= 0.f) rc = launch_mesh_shade_clipped(p, (int)N, st);
+    return rc;
+  }
   // every key = EMPTY, and the workspace flags right in front of the plane armed (WSF_CLIP)
   const size_t plane_bytes = (flags & MVR_WS_KEYS_ARMED) ? 0 : (size_t)N * HW * 8;
   cudaError_t e = cudaMemsetAsync(wb + w.flags, 0xFF, (w.keys - w.flags) + plane_bytes, st);

@@ -345,7 +345,7 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   }
   if (!(flags & MVR_RGB_PER_ELEMENT) && !obj_rgb) { set_error("mvr_mesh_backward: obj_rgb is NULL"); return -6; }
   if (!out_norm_valid(out_mean_std)) { set_error("mvr_mesh_backward: out_mean_std needs std > 0"); return -9; }
-  const WsLayout w = ws_layout(B, M, H, W, K, total_verts);
+  const WsLayout w = ws_layout(B, M, H, W, K, total_verts, total_faces);
   if (workspace_bytes < w.total) { set_error("mvr_mesh_backward: workspace too small (%zu < %zu)", workspace_bytes, w.total); return -7; }
   const GeomLayout g = geom_layout(total_verts, total_faces);
   const char* gb = (const char*)geometry;

@@ -43,6 +43,7 @@ void prof_begin(const char* name, cudaStream_t st) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (!g_prof_name[0]) return;
   if (name[0] == '(') ++name;      // MVR_LAUNCH((kernel<a, b>), ...)
+  if (strncmp(name, "mvr::", 5) == 0) name += 5;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (strncmp(name, g_prof_name, strlen(g_prof_name)) != 0 || g_prof_used + 2 > kMaxProfEvents) return;   // prefix: template arguments ignored
   while ((int)g_prof_events.size() < g_prof_used + 2) {
@@ -55,6 +56,7 @@ void prof_begin(const char* name, cudaStream_t st) {
 void prof_end(const char* name, cudaStream_t st) {
   if (!g_prof_name[0]) return;
   if (name[0] == '(') ++name;
+  if (strncmp(name, "mvr::", 5) == 0) name += 5;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (strncmp(name, g_prof_name, strlen(g_prof_name)) != 0 || g_prof_used + 2 > (int)g_prof_events.size()) return;
   cudaEventRecord(g_prof_events[g_prof_used + 1], st);

@@ -668,7 +668,7 @@ def _mesh_forward_launch(geom: "PackedMeshes", M, R, T, Cc, light, obj_rgb, bg_r
         bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
         dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
     counters = torch.empty(L.NUM_COUNTERS, dtype=torch.int64, device=dev)      # zeroed by mvr_mesh_forward
-    ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts)
+    ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts, geom.total_faces)
     ws = workspace(dev, ws_bytes, _mesh_owner=True)
     ws_flags, ws_commit = _ws_mesh_flags_forward(dev, ws, (geom.B, M, H, W, K, geom.total_verts))
     with _on(dev):
@@ -695,7 +695,7 @@ def _mesh_backward_launch(geom: "PackedMeshes", M, cfg, saved, g_images, want_ve
     g_images = _grad_like_images(g_images, flags)
     g = torch.empty(15 * N, dtype=torch.float32, device=dev)
     gR, gT, gC = g[: 9 * N].view(N, 3, 3), g[9 * N: 12 * N].view(N, 3), g[12 * N:].view(N, 3)
-    ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts)
+    ws_bytes = lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts, geom.total_faces)
     ws = workspace(dev, ws_bytes, _mesh_owner=True)
     flags = flags | _ws_mesh_flags_backward(dev, ws, ws_token)
     gV = gN = None

@@ -8,11 +8,13 @@ from mvtn_b200 import ops, synth
 from mvtn_b200 import _lib as L
 
 dev = torch.device("cuda:0")
-B, M, S = 32, 12, 224
-meshes = synth.make_meshes(B, 10000, 1236)
+B, M, S, NF = 32, 12, 224, 10000
+if len(sys.argv) > 1 and sys.argv[1] == "c5":
+    B, M, S, NF = 8, 20, 400, 100000
+meshes = synth.make_meshes(B, NF, 1236)
 nv = [v.shape[0] for v, _ in meshes]; nf = [f.shape[0] for _, f in meshes]
 verts = torch.cat([v for v, _ in meshes]).to(dev); faces = torch.cat([f for _, f in meshes]).to(dev)
-az, el, di = (t.to(dev) for t in synth.circular_views(B, M))
+az, el, di = (t.to(dev) for t in (synth.circular_views(B, M) if S == 224 else synth.spherical_views(B, M)))
 cot = torch.randn(B * M, 3, S, S, device=dev) / (3 * S * S)
 col = torch.tensor([0.99999] * 3, device=dev); light = torch.tensor([[0.0, 1.0, 0.0]], device=dev)
 lib = L.load()
@@ -28,7 +30,7 @@ for _ in range(5):
     step()
 torch.cuda.synchronize()
 names = ["look_at_forward_kernel", "geom_pack_verts_kernel", "geom_pack_faces_kernel", "geom_finish_normals_kernel", "mesh_project_kernel",
-         "mesh_scatter_kernel", "mesh_shade_kernel", "mesh_shade_clipped_kernel", "mesh_backward_kernel", "mesh_backward_finish_kernel", "look_at_backward_kernel"]
+         "mesh_bin_kernel", "mesh_bin_scan_kernel", "mesh_tile_kernel", "mesh_scatter_kernel", "mesh_shade_kernel", "mesh_shade_clipped_kernel", "mesh_backward_kernel", "mesh_backward_finish_kernel", "look_at_backward_kernel"]
 tot_all = 0.0
 for nm in names:
     lib.mvr_profile_enable(nm.encode())

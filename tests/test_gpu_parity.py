@@ -194,6 +194,26 @@ def test_mesh_queue_overflow_fallbacks_are_exact(oracle, cuda_device):
         run_mesh(oracle, cuda_device, mesh_case(name), backward=False, extra_flags=L.TEST_TINY_QUEUES)
 
 
+@pytest.mark.parametrize("name", [n for n in MESH_CASES if mesh_case(n)["K"] == 1] if False else
+                         ["small", "spherical", "cull_noperspective", "vertex_rgb", "relative_light", "c2_slice", "dense_subpixel", "odd_width_k1"])
+def test_mesh_tile_binned_forward_is_exact(oracle, cuda_device, name):
+    """MVR_FORWARD_TILED (K = 1): coarse tile binning + one fine kernel with the depth keys in shared memory and the face lists
+    staged by TMA bulk copies -- the opt-in alternative of the scatter + shade pair.  Same bars: fragments bit-exact."""
+    res = run_mesh(oracle, cuda_device, mesh_case(name), extra_flags=L.FORWARD_TILED)
+    assert (res["p2f"][..., 0] >= 0).mean() > 0.05
+
+
+def test_mesh_tile_binned_forward_edge_paths(oracle, cuda_device):
+    """Tile path: tiny queues (in-place fallbacks), a cube of faces spanning many tiles (per-view big list), near-plane clipping."""
+    run_mesh(oracle, cuda_device, mesh_case("spherical"), backward=False, extra_flags=L.FORWARD_TILED | L.TEST_TINY_QUEUES)
+    cube = dict(mesh_case("cube_big_faces"), K=1)
+    res = run_mesh(oracle, cuda_device, cube, backward=False, extra_flags=L.FORWARD_TILED)
+    assert int(res["frag"]["counters"][L.CNT_BIG_FACES]) > 0
+    close = dict(mesh_case("close_camera_400"), K=1)
+    res = run_mesh(oracle, cuda_device, close, extra_flags=L.FORWARD_TILED)
+    assert res["o"]["straddle"] > 0
+
+
 def test_mesh_big_faces_take_the_cooperative_path(oracle, cuda_device):
     res = run_mesh(oracle, cuda_device, mesh_case("cube_big_faces"), backward=False)
     assert int(res["frag"]["counters"][L.CNT_BIG_FACES]) > 0

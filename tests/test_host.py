@@ -35,10 +35,10 @@ def test_library_loads_and_answers_host_queries():
     assert lib.mvr_abi_version() == _lib.ABI_VERSION
     assert lib.mvr_launch_count() >= 0
     # size queries are pure host arithmetic
-    ws = lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 1, 160000)
+    ws = lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 1, 160000, 320000)
     assert 8 * 384 * 224 * 224 <= ws < 1 << 30          # one 64-bit (z, face) key per pixel and view
     assert ws >= 8 * 384 * 224 * 224 + 16 * 12 * 160000    # + the projected vertices of every view
-    assert lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 2, 160000) >= 2 * 8 * 384 * 224 * 224   # + previous layer when peeling
+    assert lib.mvr_mesh_workspace_bytes(32, 12, 224, 224, 2, 160000, 320000) >= 2 * 8 * 384 * 224 * 224   # + previous layer when peeling
     assert lib.mvr_mesh_geometry_bytes(5000, 10000) >= 5000 * 48 + 10000 * 16
     assert lib.mvr_mesh_geometry_bytes(-1, 0) == 0
     assert lib.mvr_points_workspace_bytes(32, 2048, 12, 224, 224, 3, 0.006) >= 3 * 8 * 384 * 224 * 224   # generic K: key plane
@@ -328,7 +328,7 @@ def test_flag_constants_match_the_header():
     assert defs["ABI_VERSION"] == _lib.ABI_VERSION
     mirrored = [n for n in defs if hasattr(_lib, n) and n != "ABI_VERSION"]
     assert {"PERSPECTIVE_CORRECT", "CULL_BACKFACES", "COMPOSITE_ALPHA", "RGB_PER_ELEMENT", "FACES_I64", "IMAGES_BF16", "SCALE_IS_DIST",
-            "WS_KEYS_ARMED", "WS_REARM_KEYS", "WS_PROJECTED", "IDX_SPARSE", "TEST_TINY_QUEUES", "NUM_COUNTERS"} <= set(mirrored)
+            "WS_KEYS_ARMED", "WS_REARM_KEYS", "WS_PROJECTED", "IDX_SPARSE", "FORWARD_TILED", "TEST_TINY_QUEUES", "NUM_COUNTERS"} <= set(mirrored)
     for n in mirrored:
         assert getattr(_lib, n) == defs[n], n
     flags = [defs[n] for n in mirrored if n not in ("NUM_COUNTERS", "CNT_STRADDLE", "CNT_BIG_FACES")]
