@@ -15,10 +15,13 @@ namespace mvr {
 
 // One covered pixel: forward recompute from the projected vertices, then the chain
 // d image -> Phong -> barycentrics -> NDC vertices -> view-space vertices -> acc = (dR 9, dT 3, dC 3).
-template <bool VRGB>
-__device__ __forceinline__ void mesh_backward_pixel(const MeshBwdParams& p, int n, int f0, int voff, const float4* __restrict__ pvn,
+// GV (vertex gradients wanted): the contributions to d/d verts and d/d normals of the pixel's three vertices are returned
+// in gvn[18] (vertex i: gvn[6 i .. 6 i + 2] = d/d position, gvn[6 i + 3 .. 6 i + 5] = d/d unit normal) and vids, and the
+// caller scatters them with warp-aggregated atomics (scatter_vertex_grads); returns false when nothing was produced.
+template <bool VRGB, bool GV>
+__device__ __forceinline__ bool mesh_backward_pixel(const MeshBwdParams& p, int n, int f0, int voff, const float4* __restrict__ pvn,
                                                     bool persp, const ShadeCtx& sc, const float4 ucol, int fid, float g0, float g1,
-                                                    float g2, float xf, int yi, float acc[16]) {
+                                                    float g2, float xf, int yi, float acc[16], float* gvn = nullptr, int* vids = nullptr) {
   const int4 fi = __ldg(p.faces4 + f0 + fid);
   // ---- forward recompute from the projected vertices (exact IEEE projection, done once per view by
   // mesh_project_kernel: for small faces the barycentrics amplify a 1-ulp change of a vertex by |xy| / area);
@@ -33,7 +36,7 @@ __device__ __forceinline__ void mesh_backward_pixel(const MeshBwdParams& p, int 
   // (after every load of the pixel has been issued) a face crossing the near plane: mesh_backward_clipped_kernel owns the pixel
   // (the flag -- some vertex lies behind the plane, never in MVTN's default setups -- is re-read per pixel: an L1 hit
   // is cheaper than a register kept live across this loop)
-  if (may_clip(p.wsflags) && face_straddles(fc, p.z_clip)) return;
+  if (may_clip(p.wsflags) && face_straddles(fc, p.z_clip)) return false;
   const FaceEdges fe = face_edges(fc);
   const float yf = __ldg(p.tab + p.W + yi);
   const float e0 = (xf - fc.x1) * fe.A0 - (yf - fc.y1) * fe.B0;
@@ -134,23 +137,69 @@ __device__ __forceinline__ void mesh_backward_pixel(const MeshBwdParams& p, int 
     acc[3] = fmaf(Xs[i].y, gpx, acc[3]); acc[4] = fmaf(Xs[i].y, gpy, acc[4]); acc[5] = fmaf(Xs[i].y, gpz, acc[5]);
     acc[6] = fmaf(Xs[i].z, gpx, acc[6]); acc[7] = fmaf(Xs[i].z, gpy, acc[7]); acc[8] = fmaf(Xs[i].z, gpz, acc[8]);
     acc[9] += gpx; acc[10] += gpy; acc[11] += gpz;
-    if (p.grad_verts) {
+    if (GV) {
       const float* r = p.R + 9 * (size_t)n;
-      float* o = p.grad_verts + 3 * (size_t)(voff + vid[i]);
-      atomicAdd(o + 0, fmaf(__ldg(r + 0), gpx, fmaf(__ldg(r + 1), gpy, __ldg(r + 2) * gpz)) - bb[i] * gvx);
-      atomicAdd(o + 1, fmaf(__ldg(r + 3), gpx, fmaf(__ldg(r + 4), gpy, __ldg(r + 5) * gpz)) - bb[i] * gvy);
-      atomicAdd(o + 2, fmaf(__ldg(r + 6), gpx, fmaf(__ldg(r + 7), gpy, __ldg(r + 8) * gpz)) - bb[i] * gvz);
+      gvn[6 * i + 0] = fmaf(__ldg(r + 0), gpx, fmaf(__ldg(r + 1), gpy, __ldg(r + 2) * gpz)) - bb[i] * gvx;
+      gvn[6 * i + 1] = fmaf(__ldg(r + 3), gpx, fmaf(__ldg(r + 4), gpy, __ldg(r + 5) * gpz)) - bb[i] * gvy;
+      gvn[6 * i + 2] = fmaf(__ldg(r + 6), gpx, fmaf(__ldg(r + 7), gpy, __ldg(r + 8) * gpz)) - bb[i] * gvz;
+      gvn[6 * i + 3] = bb[i] * gNx; gvn[6 * i + 4] = bb[i] * gNy; gvn[6 * i + 5] = bb[i] * gNz;
+      vids[i] = vid[i];
     }
-    if (p.grad_normals) {
-      float* o = p.grad_normals + 3 * (size_t)(voff + vid[i]);
-      atomicAdd(o + 0, bb[i] * gNx); atomicAdd(o + 1, bb[i] * gNy); atomicAdd(o + 2, bb[i] * gNz);
+  }
+  return true;
+}
+
+// Warp-aggregated gradient scatter (north_star (4)): neighbouring pixels share faces -- an 8x4-pixel block of the strip
+// kernel touches ~5 of them at C2, a large triangle fills whole warps -- so the lanes of a warp that hold the SAME face sum
+// their 18 per-vertex values first (__match_any_sync on the face id, then one pass over the group's members by shuffles)
+// and ONE lane per face issues the 18 atomicAdds: 6x fewer L2 atomics at C2, 32x fewer on large faces.  Must be called by
+// all 32 lanes (fid < 0: nothing to add).
+__device__ __forceinline__ void scatter_vertex_grads(const MeshBwdParams& p, int voff, int fid, const float gvn[18], const int vids[3]) {
+  const unsigned int full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  if (p.gv_plain) {      // A/B baseline: every lane scatters its own 18 values
+    if (fid >= 0) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (p.grad_verts) { float* o = p.grad_verts + 3 * (size_t)(voff + vids[i]); atomicAdd(o, gvn[6 * i]); atomicAdd(o + 1, gvn[6 * i + 1]); atomicAdd(o + 2, gvn[6 * i + 2]); }
+        if (p.grad_normals) { float* o = p.grad_normals + 3 * (size_t)(voff + vids[i]); atomicAdd(o, gvn[6 * i + 3]); atomicAdd(o + 1, gvn[6 * i + 4]); atomicAdd(o + 2, gvn[6 * i + 5]); }
+      }
+    }
+    return;
+  }
+  const unsigned int grp = __match_any_sync(full, fid);
+  unsigned int peers = fid >= 0 ? grp : 0u;
+  const bool leader = fid >= 0 && (int)(__ffs(grp) - 1) == lane;
+  float sum[18];
+#pragma unroll
+  for (int i = 0; i < 18; ++i) sum[i] = 0.f;
+  while (__any_sync(full, peers != 0u)) {      // warp-uniform: max group size iterations
+    const int src = peers ? __ffs(peers) - 1 : lane;
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      const float t = __shfl_sync(full, gvn[i], src);
+      if (peers) sum[i] += t;
+    }
+    peers &= peers - 1u;
+  }
+  if (leader) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (p.grad_verts) {
+        float* o = p.grad_verts + 3 * (size_t)(voff + vids[i]);
+        atomicAdd(o + 0, sum[6 * i + 0]); atomicAdd(o + 1, sum[6 * i + 1]); atomicAdd(o + 2, sum[6 * i + 2]);
+      }
+      if (p.grad_normals) {
+        float* o = p.grad_normals + 3 * (size_t)(voff + vids[i]);
+        atomicAdd(o + 0, sum[6 * i + 3]); atomicAdd(o + 1, sum[6 * i + 4]); atomicAdd(o + 2, sum[6 * i + 5]);
+      }
     }
   }
 }
 
 // VRGB: per-vertex colours (object_color == "custom"); otherwise ONE object colour: the texel is c * sum(b) and its
 // cotangent one dot product -- six registers and ~13 floating-point instructions less per covered pixel.
-template <int MINB, bool VRGB>
+template <int MINB, bool VRGB, bool GV>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const MeshBwdParams p) {
   const int tid = threadIdx.x;
   // grid: x = 32x32-pixel tiles, y = view m, z = object b; thread (lane, warp) owns pixels (x0+lane, y0+warp+8j)
@@ -191,10 +240,19 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const 
   for (int j = 0; j < BWD_PIX_PER_THREAD; ++j) {
     const int fid = fids[j];
     const float g0 = gin[j][0], g1 = gin[j][1], g2 = gin[j][2];
-    if (fid < 0 || (g0 == 0.f && g1 == 0.f && g2 == 0.f)) continue;
-    any = true;
+    const bool live = !(fid < 0 || (g0 == 0.f && g1 == 0.f && g2 == 0.f));
     const int yi = yi0 + 8 * j;
-    mesh_backward_pixel<VRGB>(p, n, f0, voff, pvn, persp, sc, ucol, fid, g0, g1, g2, xf, yi, acc);
+    if (GV) {      // all lanes stay together for the warp-aggregated scatter
+      float gvn[18];
+      int vids[3] = {0, 0, 0};
+      bool done = false;
+      if (live) { any = true; done = mesh_backward_pixel<VRGB, true>(p, n, f0, voff, pvn, persp, sc, ucol, fid, g0, g1, g2, xf, yi, acc, gvn, vids); }
+      scatter_vertex_grads(p, voff, done ? fid : -1, gvn, vids);
+      continue;
+    }
+    if (!live) continue;
+    any = true;
+    mesh_backward_pixel<VRGB, false>(p, n, f0, voff, pvn, persp, sc, ucol, fid, g0, g1, g2, xf, yi, acc);
   }
   // one partial per WARP, no block barrier: a warp retires as soon as its own pixels are done
   float* out = p.partials + ((size_t)n * p.parts_per_view + (size_t)cta * NWARPS + (tid >> 5)) * 16;
@@ -221,7 +279,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int MINB, bool VRGB>
+template <int MINB, bool VRGB, bool GV>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(const MeshBwdParams p) {
   // rows of 32 words whose eight 16-byte chunks are XOR-swizzled by 2 (row & 3): the 8x4-pixel warp blocks below read
   // 32 distinct banks (chunk pair 2 bx, 2 bx + 1 of row r lands on pair bx ^ r), with no padding
@@ -288,18 +346,31 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(
     __syncwarp();
 #pragma unroll 1
     for (int base = 0; base < cnt; base += 32) {
-      if (base + lane >= cnt) continue;
-      const int e = s_list[warp][base + lane];
+      const bool has = base + lane < cnt;
+      if (!GV && !has) continue;
+      const int e = has ? s_list[warp][base + lane] : 0;
       const int q = warp + 8 * (e >> 5);
       const int x = ((q & 3) << 3) + (e & 7), y = ((q >> 2) << 2) + ((e >> 3) & 3);
       const int o = y * 32 + ((((x >> 2) ^ ((y & 3) << 1)) << 2) | (x & 3));
       const int fid = s_fid[buf][o];
       float g0 = s_g[buf][0][o], g1 = s_g[buf][1][o], g2 = s_g[buf][2][o];
-      if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
+      const bool live = has && !(g0 == 0.f && g1 == 0.f && g2 == 0.f);
+      if (!GV && !live) continue;
       if (p.onorm.on) { g0 *= p.onorm.s0; g1 *= p.onorm.s1; g2 *= p.onorm.s2; }
+      if (GV) {      // all lanes stay together for the warp-aggregated scatter
+        float gvn[18];
+        int vids[3] = {0, 0, 0};
+        bool done = false;
+        if (live) {
+          any = true;
+          done = mesh_backward_pixel<VRGB, true>(p, n, f0, voff, pvn, persp, sc, ucol, fid, g0, g1, g2, __ldg(p.tab + t * 32 + x), tyb * 32 + y, acc, gvn, vids);
+        }
+        scatter_vertex_grads(p, voff, done ? fid : -1, gvn, vids);
+        continue;
+      }
       any = true;
       const float xf = __ldg(p.tab + t * 32 + x);      // covered => inside the image
-      mesh_backward_pixel<VRGB>(p, n, f0, voff, pvn, persp, sc, ucol, fid, g0, g1, g2, xf, tyb * 32 + y, acc);
+      mesh_backward_pixel<VRGB, false>(p, n, f0, voff, pvn, persp, sc, ucol, fid, g0, g1, g2, xf, tyb * 32 + y, acc);
     }
     __syncwarp();                                      // the list is rebuilt for the next tile
     __syncthreads();                                   // everyone is done with `buf` before tile t + 2 overwrites it
@@ -367,20 +438,27 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   p.partials = (float*)(wb + w.partials); p.grad_verts = grad_verts; p.grad_normals = grad_normals;
   p.onorm = make_out_norm(out_mean_std);
   p.z_clip = z_clip; p.wsflags = (int*)(wb + w.flags); p.parts_per_view = w.bwd_parts_per_view;
+  { static const int plain = [] { const char* e = getenv("MVR_BWD_GV_AGG"); return (e && atoi(e) == 0) ? 1 : 0; }(); p.gv_plain = plain; }
   const dim3 bgrid((unsigned)w.bwd_ctas_per_view, (unsigned)M, (unsigned)B);
   const bool vrgb = flags & MVR_RGB_PER_ELEMENT;
   const bool strip = backward_strip() && K == 1 && !(flags & MVR_IMAGES_BF16) && W % 4 == 0 &&
                      ((uintptr_t)pix_to_face % 16 == 0) && ((uintptr_t)grad_images % 16 == 0);
+  const bool gv = grad_verts || grad_normals;
   if (strip) {
     p.parts_per_view = ((H + 31) / 32) * NWARPS;      // one partial per warp of every tile ROW
     const dim3 sgrid((unsigned)((H + 31) / 32), (unsigned)M, (unsigned)B);
-    if (vrgb) MVR_LAUNCH((mesh_backward_kernel_strip<3, true>), sgrid, MVR_THREADS, 0, st, p);
-    else MVR_LAUNCH((mesh_backward_kernel_strip<3, false>), sgrid, MVR_THREADS, 0, st, p);
+    if (gv) {      // vertex gradients: the variant with the warp-aggregated atomic scatter (its 18 extra live values cost occupancy)
+      if (vrgb) MVR_LAUNCH((mesh_backward_kernel_strip<2, true, true>), sgrid, MVR_THREADS, 0, st, p);
+      else MVR_LAUNCH((mesh_backward_kernel_strip<2, false, true>), sgrid, MVR_THREADS, 0, st, p);
+    }
+    else if (vrgb) MVR_LAUNCH((mesh_backward_kernel_strip<3, true, false>), sgrid, MVR_THREADS, 0, st, p);
+    else MVR_LAUNCH((mesh_backward_kernel_strip<3, false, false>), sgrid, MVR_THREADS, 0, st, p);
   }
-  else if (backward_minb() == 2) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<2, true>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<2, false>), bgrid, MVR_THREADS, 0, st, p); }
-  else if (backward_minb() == 4) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<4, true>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<4, false>), bgrid, MVR_THREADS, 0, st, p); }
-  else if (vrgb) MVR_LAUNCH((mesh_backward_kernel<3, true>), bgrid, MVR_THREADS, 0, st, p);
-  else MVR_LAUNCH((mesh_backward_kernel<3, false>), bgrid, MVR_THREADS, 0, st, p);
+  else if (gv) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<2, true, true>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<2, false, true>), bgrid, MVR_THREADS, 0, st, p); }
+  else if (backward_minb() == 2) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<2, true, false>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<2, false, false>), bgrid, MVR_THREADS, 0, st, p); }
+  else if (backward_minb() == 4) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<4, true, false>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<4, false, false>), bgrid, MVR_THREADS, 0, st, p); }
+  else if (vrgb) MVR_LAUNCH((mesh_backward_kernel<3, true, false>), bgrid, MVR_THREADS, 0, st, p);
+  else MVR_LAUNCH((mesh_backward_kernel<3, false, false>), bgrid, MVR_THREADS, 0, st, p);
   rc = check_launch("mesh_backward_kernel");
   if (rc) return rc;
   // clipped-face pixels (if any) + the fixed-order sum of the per-warp partials -> gR, gT, gC

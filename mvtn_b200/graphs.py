@@ -36,19 +36,21 @@ def graphed_points_render(points: torch.Tensor, rgb: torch.Tensor, M: int, radiu
                           normalize=None, out_dtype=None, return_cameras: bool = False):
     """Capture look_at + point rasterization + compositing (and their backward) for a FIXED (B, N, 3) device tensor
     `points` (update it -- and `rgb` / `bg` -- in place between replays).
-    Returns step(azim, elev, dist) -> images (B*M, 3, H, W); with return_cameras=True -> (images, cams, invalid) where
-    cams is the flat R | T | C buffer (9n + 3n + 3n floats, n = B*M) and invalid the rotation-validity flag of look_at
-    (both live in captured buffers: copy what must outlive the next replay)."""
+    Returns step(azim, elev, dist) -> images (B*M, 3, H, W); with return_cameras=True -> (images, cams, invalid, idx, mask)
+    where cams is the flat R | T | C buffer (9n + 3n + 3n floats, n = B*M), invalid the rotation-validity flag of look_at,
+    idx / mask the sparse fragment indices and the 1-bit hit mask (all live in captured buffers: copy what must outlive the
+    next replay)."""
     ops._require_cuda(points, "points")
     rgb = rgb.to(points.device)
     bg = bg.to(points.device)
 
     def fn(az, el, di):
-        img, (R, T, C, bad), _ = ops.render_points_from_angles(points, rgb, M, az, el, di, radius, bg, image_size,
-                                                               points_per_pixel=points_per_pixel, compositor=compositor,
-                                                               normalize=normalize, out_dtype=out_dtype)
+        img, (R, T, C, bad), frag = ops.render_points_from_angles(points, rgb, M, az, el, di, radius, bg, image_size,
+                                                                  points_per_pixel=points_per_pixel, compositor=compositor,
+                                                                  normalize=normalize, out_dtype=out_dtype)
         if return_cameras:
-            return img, torch.cat([R.reshape(-1), T.reshape(-1), C.reshape(-1)]), bad
+            idx, mask = frag._raw[0], frag._raw[1]      # sparse idx + 1-bit hit mask (ops._PointFragments completes them lazily)
+            return img, torch.cat([R.reshape(-1), T.reshape(-1), C.reshape(-1)]), bad, idx, mask
         return img
 
     return torch.cuda.make_graphed_callables(fn, _views_like(sample_views))

@@ -84,6 +84,7 @@ def _flag_reader(flag_dev):
     return read
 
 
+GRAPH_AUTO_MAX_VIEWS = 48     # cuda_graph=None: point steps up to this many views (B * M) are replayed from CUDA graphs
 ORTHOGONAL_THRESHOLD = 1e-6   # renderer.py:29
 EXAHSTION_LIMIT = 20          # renderer.py:30 (sic)
 
@@ -98,12 +99,15 @@ class MVRenderer(nn.Module):
             FoV perspective cameras).
         copy_stream: H2D of a collated host batch on a side stream (overlaps with the previous step's kernels when the
             loop does not synchronise every step; see ops.PackedMeshes.from_host_packed)
-        cuda_graph: point path only -- the device part of a step (look_at, binning, tile rasterizer + compositor, and their
+        cuda_graph: None (default) = automatic -- point steps of at most GRAPH_AUTO_MAX_VIEWS views (BASELINE configs[0]: one
+            cloud x 12 views, a step that is pure launch latency) are replayed from CUDA graphs, larger ones run eagerly;
+            True / False force it.  Point path only -- the device part of a step (look_at, binning, tile rasterizer + compositor, and their
             backward) is captured once per (B, N, views-require-grad) and replayed with ONE launch per direction: the
             point path at small batches is launch-bound (BASELINE configs[0], one cloud x 12 views: 0.470 -> 0.356 ms per
             end-to-end step, r2m); at 32 clouds the eager step is already GPU-bound and the copies into the captured buffers
             make this mode slower (0.516 -> 0.590 ms): leave it off there.  Needs one object colour and fixed shapes; anything else (per-point colours, invalid rotations, torch.no_grad()) takes the eager
-            path.  In this mode `cameras` holds detached copies, `last_fragments` is None and the images are a copy of the
+            path.  In this mode `cameras` holds detached copies, `last_fragments` views the captured buffers (valid until the next
+            replay) and the images are a copy of the
             captured buffer; the tensors the captured backward reads are static, so at most ONE forward may be outstanding
             per backward (two forwards of the same shapes before a backward would overwrite the first one's saved state).
         cache_geometry: keep the packed device geometry of the last mesh batch and reuse it when the
@@ -117,10 +121,10 @@ class MVRenderer(nn.Module):
     def __init__(self, nb_views, image_size=224, pc_rendering=True, object_color="white", background_color="white",
                  faces_per_pixel=1, points_radius=0.006, points_per_pixel=1, light_direction="random",
                  cull_backfaces=False, *, compositor="norm", perspective_correct=True, cache_geometry=False,
-                 normalize=None, out_dtype=None, copy_stream=False, cuda_graph=False):
+                 normalize=None, out_dtype=None, copy_stream=False, cuda_graph=None):
         super().__init__()
         self.copy_stream = copy_stream
-        self.cuda_graph = cuda_graph
+        self.cuda_graph = cuda_graph      # None = auto: replay small (launch-bound) point steps from CUDA graphs
         self._point_graphs = {}
         self.nb_views = nb_views
         self.image_size = image_size
@@ -247,7 +251,10 @@ class MVRenderer(nn.Module):
             raise ValueError(f"{points.shape[0]} clouds but azim has batch {azim.shape[0]}")
         bg = _device_vec(background_color, device)
         rgb = torch.as_tensor(color, dtype=torch.float32)
-        if self.cuda_graph and rgb.numel() == 3 and torch.is_grad_enabled():      # under no_grad the eager path runs
+        use_graph = self.cuda_graph
+        if use_graph is None:      # auto: only where the step is launch-bound
+            use_graph = (points.shape[0] * self.nb_views <= GRAPH_AUTO_MAX_VIEWS and not torch.cuda.is_current_stream_capturing())
+        if use_graph and rgb.numel() == 3 and torch.is_grad_enabled():      # under no_grad the eager path runs
             az, el, di = self._views(azim, elev, dist, device)
             out = self._render_points_graphed(points, _device_vec(rgb, device), az, el, di, bg, device)
             if out is not None:
@@ -285,6 +292,10 @@ class MVRenderer(nn.Module):
         grads = (az.requires_grad, el.requires_grad, di.requires_grad)
         key = (tuple(points.shape), device.index, grads, torch.is_grad_enabled())
         st = self._point_graphs.get(key)
+        if st is not None and st["busy"]:
+            # the previous replay's result is still alive and has not been back-propagated: its saved tensors live in the
+            # captured buffers, which a second replay would overwrite -- this call takes the eager path instead
+            return None
         if st is None:
             static_pts = points.to(device=device, dtype=torch.float32).clone()
             static_rgb, static_bg = rgb.clone(), bg.clone()
@@ -294,25 +305,38 @@ class MVRenderer(nn.Module):
                                                 compositor=self.compositor, normalize=self.normalize,
                                                 out_dtype=self.out_dtype, return_cameras=True)
             st = self._point_graphs[key] = {"pts": static_pts, "rgb": static_rgb, "bg": static_bg, "step": step,
-                                            "rgb_src": rgb, "bg_src": bg}
+                                            "rgb_src": rgb, "bg_src": bg, "busy": False}
         else:
             st["pts"].copy_(points, non_blocking=True)
             if st["rgb_src"] is not rgb:          # named colours are cached constants: nothing to copy in the steady state
                 st["rgb"].copy_(rgb); st["rgb_src"] = rgb
             if st["bg_src"] is not bg:
                 st["bg"].copy_(bg); st["bg_src"] = bg
-        images, cams, bad = st["step"](az, el, di)
+        images, cams, bad, idx, mask = st["step"](az, el, di)
         invalid = _flag_reader(bad)
         n = az.numel()
         cams = cams.detach().clone()              # the captured buffer is overwritten by the next replay
         if invalid() != 0:
             return None
-        self.last_fragments = None
+        # (views of the captured buffers: valid until the next replay of this shape; completed lazily on first access)
+        self.last_fragments = ops._PointFragments(idx, mask, *ops._hw(self.image_size))
         R, T, C = cams[: 9 * n].view(n, 3, 3), cams[9 * n: 12 * n].view(n, 3), cams[12 * n:].view(n, 3)
         # a copy, not a view of the captured output buffer: images kept by the caller (logging, two renders per loss)
-        # survive the next replay.  What the captured BACKWARD reads (idx, hit mask, cameras) stays static: one
-        # outstanding forward per backward -- call backward() before the next forward() of the same shapes.
-        rendered_images = images.clone().view(points.shape[0], self.nb_views, 3, self.image_size, self.image_size)
+        # survive the next replay.  What the captured BACKWARD reads (idx, hit mask, cameras) stays static, hence the
+        # `busy` guard below: a forward issued while the previous result is alive and un-backpropagated runs eagerly.
+        out = images.clone()
+        if out.requires_grad:
+            # one outstanding forward per captured backward: released when the gradient reaches the images (backward has
+            # started; python is single-threaded, so it is enqueued before the next forward) or when the result dies
+            import weakref
+            st["busy"] = True
+
+            def release(*_a, _st=st):
+                _st["busy"] = False
+
+            out.register_hook(lambda g, _r=release: (_r(), g)[1])
+            weakref.finalize(out, release)
+        rendered_images = out.view(points.shape[0], self.nb_views, 3, self.image_size, self.image_size)
         return rendered_images, FoVOrthographicCameras(R, T, C, znear=0.01)
 
     def _packed(self, meshes, color, device):

@@ -1040,7 +1040,7 @@ def test_mvrenderer_points_cuda_graph_mode_matches_eager(cuda_device):
     dev = cuda_device
     M, S = 4, 64
     kw = dict(image_size=S, pc_rendering=True, points_per_pixel=4, points_radius=0.03, background_color="black", compositor="alpha")
-    eager = MVRenderer(M, **kw).to(dev).train()
+    eager = MVRenderer(M, cuda_graph=False, **kw).to(dev).train()
     graph = MVRenderer(M, cuda_graph=True, **kw).to(dev).train()
     eager.object_color = graph.object_color = "white"
 
@@ -1064,6 +1064,23 @@ def test_mvrenderer_points_cuda_graph_mode_matches_eager(cuda_device):
             got, want = run(graph, pts, views, grad=False), run(eager, pts, views, grad=False)
         assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
     assert len(graph._point_graphs) >= 2
+    # one outstanding forward per captured backward: a second forward before the first result is back-propagated runs eagerly
+    # and leaves the first one's gradients intact
+    auto = MVRenderer(M, **kw).to(dev).train()                      # cuda_graph=None: automatic for <= 48 views
+    auto.object_color = "white"
+    pts = synth.make_clouds(2, 700, 3); v1 = synth.learned_spherical_views(2, M, 31); v2 = synth.learned_spherical_views(2, M, 32)
+    a1, e1, d1 = (t.to(dev).clone().requires_grad_() for t in v1)
+    a2, e2, d2 = (t.to(dev).clone().requires_grad_() for t in v2)
+    auto(None, pts, a1, e1, d1)[0].sum().backward()                 # captures, replays, releases
+    a1.grad = None
+    img1, _ = auto(None, pts, a1, e1, d1)                           # replay: busy until img1 is back-propagated
+    assert len(auto._point_graphs) == 1 and next(iter(auto._point_graphs.values()))["busy"]
+    img2, _ = auto(None, pts, a2, e2, d2)                           # must not touch the buffers img1's backward reads
+    cot = torch.linspace(-1, 1, img1.numel(), device=dev).view_as(img1)
+    img1.backward(cot)
+    assert not next(iter(auto._point_graphs.values()))["busy"]
+    want = run(eager, pts, v1)
+    assert torch.equal(a1.grad, want[3]) and torch.equal(img1.detach(), want[0]) and torch.equal(img2.detach(), run(eager, pts, v2)[0])
     # a degenerate elevation (rotation guard): the graphed step steps aside, the eager redraw loop answers
     views = [t.clone() for t in synth.learned_spherical_views(2, M, 9)]
     views[1][0, 0] = 90.0
