@@ -296,14 +296,26 @@ class MVRenderer(nn.Module):
             # the previous replay's result is still alive and has not been back-propagated: its saved tensors live in the
             # captured buffers, which a second replay would overwrite -- this call takes the eager path instead
             return None
+        if st is not None and st.get("failed"):
+            return None
         if st is None:
+            import gc
+            gc.collect()                      # pending frees of other threads (autograd workers) must not land inside the capture
+            torch.cuda.synchronize(device)
             static_pts = points.to(device=device, dtype=torch.float32).clone()
             static_rgb, static_bg = rgb.clone(), bg.clone()
             sample = tuple(t.detach().clone().requires_grad_(g) for t, g in zip((az, el, di), grads))
-            step = graphs.graphed_points_render(static_pts, static_rgb, self.nb_views, self.points_radius, static_bg,
-                                                self.image_size, sample, points_per_pixel=self.points_per_pixel,
-                                                compositor=self.compositor, normalize=self.normalize,
-                                                out_dtype=self.out_dtype, return_cameras=True)
+            try:
+                step = graphs.graphed_points_render(static_pts, static_rgb, self.nb_views, self.points_radius, static_bg,
+                                                    self.image_size, sample, points_per_pixel=self.points_per_pixel,
+                                                    compositor=self.compositor, normalize=self.normalize,
+                                                    out_dtype=self.out_dtype, return_cameras=True)
+            except RuntimeError as e:         # a capture invalidated from outside (another thread's CUDA call): stay eager
+                if self.cuda_graph:           # explicitly requested: say so
+                    import warnings
+                    warnings.warn(f"MVRenderer: CUDA-graph capture failed ({e}); this shape runs eagerly")
+                self._point_graphs[key] = {"failed": True, "busy": False}
+                return None
             st = self._point_graphs[key] = {"pts": static_pts, "rgb": static_rgb, "bg": static_bg, "step": step,
                                             "rgb_src": rgb, "bg_src": bg, "busy": False}
         else:
