@@ -93,7 +93,10 @@ class TrainStep:
             self.render_events[1].record()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
             loss = self.crit(self.cnn(images), self.targets)
-        self.opt.zero_grad(set_to_none=True); self.opt_mvtn.zero_grad(set_to_none=True)
+        if self.overlap is not None:
+            self.overlap.zero_grad()              # gradients stay views of the communication buckets
+        else:
+            self.opt.zero_grad(set_to_none=True); self.opt_mvtn.zero_grad(set_to_none=True)
         loss.backward()
         if self.overlap is not None:
             self.overlap.finish()

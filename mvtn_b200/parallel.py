@@ -111,23 +111,32 @@ class OverlappedGradientAllReduce:
     by object, NCCL all-reduce of the MVTN regressor + backbone gradients; SURVEY 8e "bucketed and overlapped with backward").
 
     Parameters are assigned to flat buckets in REVERSE registration order (the order autograd finishes them in, to first
-    order).  A post-accumulate-grad hook copies each finished gradient into its bucket slot; the moment a bucket is complete
-    its all-reduce is launched asynchronously (NCCL runs it on its own stream, under the rest of the backward pass: the
-    renderer's backward and the view selector's come LAST in the graph, so every backbone bucket is in flight before the
-    rasterizer's backward kernels start).  `finish()` -- call it after loss.backward() -- launches whatever is left, waits,
-    averages and scatters the buckets back into the .grad tensors.
+    order) and their .grad tensors are VIEWS of those buckets, so autograd accumulates straight into the communication buffer:
+    no copy in, no copy out.  A post-accumulate-grad hook counts finished gradients; the moment a bucket is complete its
+    all-reduce (NCCL: ReduceOp.AVG) is launched asynchronously -- NCCL runs it on its own stream, under the rest of the backward
+    pass: the renderer's backward and the view selector's come LAST in the graph, so every backbone bucket is in flight before
+    the rasterizer's backward kernels start.  `finish()` -- call it after loss.backward() -- launches whatever is left and
+    waits.
 
-        sync = OverlappedGradientAllReduce(params)         # once
-        loss.backward(); sync.finish(); optimizer.step()   # every step
+        sync = OverlappedGradientAllReduce(params)                           # once
+        sync.zero_grad(); loss.backward(); sync.finish(); optimizer.step()   # every step
 
-    Single process / no process group: every call is a no-op."""
+    Use sync.zero_grad() instead of optimizer.zero_grad(set_to_none=True): it zeroes the buckets (one memset each) and keeps
+    the views; a gradient that was detached from its bucket anyway is copied back in and re-bound (slower, still correct).
+    Single process / no process group: every call is a no-op (zero_grad falls back to setting grads to None)."""
 
     def __init__(self, params, bucket_bytes: int = 8 << 20, average: bool = True):
         self.enabled = dist.is_initialized() and dist.get_world_size() > 1
         self.average = average
         self.params = [p for p in params if p.requires_grad]
-        self.buckets = []          # dicts: params, offsets, flat (lazily), pending, handle
+        self.buckets = []          # dicts: params, offsets, flat, views, filled, handle
         self._slot = {}
+        self._hooks = []
+        self.launched_in_backward = 0      # buckets whose all-reduce was launched from a hook (statistics of the last step)
+        self.stats = {}
+        if not self.enabled:
+            return
+        self._avg_native = average and dist.get_backend() == "nccl"      # gloo has no ReduceOp.AVG: sum, then divide
         cur, size = [], 0
         for p in reversed(self.params):
             nbytes = p.numel() * p.element_size()
@@ -138,69 +147,75 @@ class OverlappedGradientAllReduce:
             size += nbytes
         if cur:
             self._close(cur)
-        self._hooks = []
-        if self.enabled:
-            for p in self.params:
-                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
-        self.launched_in_backward = 0      # buckets whose all-reduce was launched from a hook (statistics of the last step)
+        for p in self.params:
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
     def _close(self, plist):
         offs, o = [], 0
         for p in plist:
             offs.append(o)
             o += p.numel()
-        b = {"params": list(plist), "offsets": offs, "numel": o, "flat": None, "pending": len(plist), "handle": None,
-             "filled": set()}
+        flat = torch.zeros(o, dtype=plist[0].dtype, device=plist[0].device)
+        views = [flat[offs[i]: offs[i] + p.numel()].view_as(p) for i, p in enumerate(plist)]
+        b = {"params": list(plist), "offsets": offs, "numel": o, "flat": flat, "views": views, "handle": None, "filled": set()}
         for i, p in enumerate(plist):
             self._slot[id(p)] = (len(self.buckets), i)
+            p.grad = views[i]
         self.buckets.append(b)
 
-    def _flat(self, b):
-        if b["flat"] is None:
-            p0 = b["params"][0]
-            b["flat"] = torch.zeros(b["numel"], dtype=p0.dtype, device=p0.device)
-        return b["flat"]
+    def zero_grad(self):
+        """Zero every gradient in place (one memset per bucket) and keep them bound to the buckets."""
+        if not self.enabled:
+            for p in self.params:
+                p.grad = None
+            return
+        for b in self.buckets:
+            b["flat"].zero_()
+            for i, p in enumerate(b["params"]):
+                if p.grad is not b["views"][i]:
+                    p.grad = b["views"][i]
+
+    def _launch(self, b):
+        op = dist.ReduceOp.AVG if self._avg_native else dist.ReduceOp.SUM
+        b["handle"] = dist.all_reduce(b["flat"], op=op, async_op=True)
 
     def _on_grad(self, p):
         bi, i = self._slot[id(p)]
         b = self.buckets[bi]
-        if i in b["filled"]:          # a parameter used twice in the graph: its hook fires once, after accumulation; be safe
+        if i in b["filled"]:
             return
-        flat = self._flat(b)
-        flat[b["offsets"][i]: b["offsets"][i] + p.numel()].copy_(p.grad.reshape(-1))
+        v = b["views"][i]
+        if p.grad is not v and p.grad.data_ptr() != v.data_ptr():      # detached from the bucket (zero_grad(set_to_none=True)): copy in
+            v.copy_(p.grad)
+            p.grad = v
         b["filled"].add(i)
         if len(b["filled"]) == len(b["params"]):
-            b["handle"] = dist.all_reduce(flat, async_op=True)
+            self._launch(b)
             self.launched_in_backward += 1
 
     def finish(self):
-        """Launch the buckets that did not complete during backward (parameters without a gradient this step), wait for
-        all of them, average, and copy the reduced values back into the .grad tensors.  Returns the number of buckets."""
+        """Launch the buckets that did not complete during backward (parameters without a gradient this step: their slots
+        hold whatever zero_grad left there), wait for all of them and, without a native average, divide.  Returns the number
+        of buckets."""
         if not self.enabled:
             return 0
         world = dist.get_world_size()
         for b in self.buckets:
             if b["handle"] is None:
-                flat = self._flat(b)
                 for i, p in enumerate(b["params"]):       # unfilled slots: the parameter had no gradient on this rank
-                    if i not in b["filled"]:
-                        flat[b["offsets"][i]: b["offsets"][i] + p.numel()].zero_()
-                b["handle"] = dist.all_reduce(flat, async_op=True)
+                    if i not in b["filled"] and p.grad is not b["views"][i]:
+                        b["views"][i].zero_()
+                        p.grad = b["views"][i]
+                self._launch(b)
         for b in self.buckets:
             b["handle"].wait()
-            flat = b["flat"]
-            if self.average:
-                flat.div_(world)
-            for i, p in enumerate(b["params"]):
-                src = flat[b["offsets"][i]: b["offsets"][i] + p.numel()].view_as(p)
-                if p.grad is None:
-                    p.grad = src.clone()
-                else:
-                    p.grad.copy_(src)
+            if self.average and not self._avg_native:
+                b["flat"].div_(world)
             b["handle"] = None
             b["filled"] = set()
         n = len(self.buckets)
-        self.stats = {"buckets": n, "launched_in_backward": self.launched_in_backward}
+        self.stats = {"buckets": n, "launched_in_backward": self.launched_in_backward,
+                      "reduce_op": "avg (nccl)" if self._avg_native else "sum + divide"}
         self.launched_in_backward = 0
         return n
 

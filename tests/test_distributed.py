@@ -48,15 +48,23 @@ def _worker(rank, world, port, q):
     unused = torch.nn.Parameter(torch.ones(3))                      # never reaches the loss: finish() must still reduce it
     sync = parallel.OverlappedGradientAllReduce(list(net.parameters()) + [unused], bucket_bytes=128)
     assert sync.enabled and len(sync.buckets) >= 3
-    for step in range(2):
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 2))
+    ref.load_state_dict(net.state_dict())
+    for step in range(3):
         x = torch.full((3, 6), float(rank + 1 + step))
-        net.zero_grad(set_to_none=(step == 0))
+        if step == 1:
+            net.zero_grad(set_to_none=True)                    # a caller that detaches the gradients from the buckets anyway
+        else:
+            sync.zero_grad()
         net(x).square().sum().backward()
-        local = [p.grad.clone() for p in net.parameters()]
+        ref.zero_grad(set_to_none=True)
+        ref(x).square().sum().backward()
         assert sync.finish() == len(sync.buckets) and sync.stats["launched_in_backward"] >= len(sync.buckets) - 1
-        for p, g in zip(net.parameters(), local):
-            want = g.clone(); dist.all_reduce(want); want /= world
+        for p, pr in zip(net.parameters(), ref.parameters()):
+            want = pr.grad.clone(); dist.all_reduce(want); want /= world
             assert torch.allclose(p.grad, want, atol=1e-6)
+            bi, i = sync._slot[id(p)]
+            assert p.grad.data_ptr() == sync.buckets[bi]["views"][i].data_ptr()      # still (or again) a view of its bucket
         assert unused.grad is not None and float(unused.grad.abs().sum()) == 0.0
     sync.remove()
     parallel.barrier()
