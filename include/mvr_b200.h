@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MVR_ABI_VERSION 5
+#define MVR_ABI_VERSION 6
 
 /* flags */
 #define MVR_PERSPECTIVE_CORRECT 1  /* [upstream] RasterizationSettings.perspective_correct (FoV persp.: True) */
@@ -50,6 +50,8 @@ extern "C" {
                                       lists staged by TMA bulk copies, depth keys in shared memory, shading in the same CTA) instead of
                                       the default bin-free scatter + shade pair.  Same fragments bit for bit; slower on B200 at the
                                       BASELINE sizes, kept selectable for A/B measurements */
+#define MVR_CLIP_BARYCENTRIC 4096  /* [upstream] RasterizationSettings.clip_barycentric_coords (default: True iff blur_radius > 0): the
+                                      fragment's barycentrics are clamped below at 0 and renormalised (BarycentricClipForward) */
 #define MVR_TEST_TINY_QUEUES 0x40000000 /* tests only: shrink the scatter kernel's work queues to force their fallbacks */
 
 /* Phong constants of DirectionalLights() / Materials() as constructed at renderer.py:190-191 */
@@ -143,7 +145,11 @@ int mvr_mesh_normals_backward(const void* geometry, const int* vert_off, const i
 size_t mvr_mesh_workspace_bytes(int B, int M, int H, int W, int K, int64_t total_verts, int64_t total_faces);
 /* MeshRenderer(MeshRasterizer, HardPhongShader)(meshes.extend(M), cameras, lights)
  * (renderer.py:89-113; [upstream] _C.rasterize_meshes + interp_face_attrs + phong_shading +
- * hard_rgb_blend).  blur_radius = 0.
+ * hard_rgb_blend).
+ *   blur_radius >= 0 ([upstream] RasterizationSettings.blur_radius, squared NDC units; renderer.py:91 passes 0): with a positive
+ *   radius a face is also a fragment of the pixels closer than it to one of its edges, `dists` carries the SIGNED squared edge
+ *   distance (negative inside) and, with MVR_CLIP_BARYCENTRIC, `bary` the clipped barycentrics -- the fragments the soft
+ *   shaders blend (mvr_mesh_soft_blend_forward); the image written here stays the hard-shaded nearest fragment.
  *   Cc (n,3) camera centres; light (1,3) if light_stride == 0 else (n,3) with stride 3;
  *   obj_rgb (3) uniform colour (ignored when the geometry holds per-vertex colours); bg_rgb (3);
  *   k00,k11: FoV projection scale (1/tan(fov/2)); z_clip: near clip plane in view space ([upstream] MeshRasterizer:
@@ -160,7 +166,7 @@ int mvr_mesh_forward(const void* geometry, const int* vert_off, const int* face_
                      int64_t total_verts, int64_t total_faces, int max_verts, int max_faces,
                      const float* R, const float* T, const float* Cc, const float* light,
                      int light_stride, const float* obj_rgb, const float* bg_rgb, float k00, float k11,
-                     float z_clip, int H, int W, int K, int flags, const float* out_mean_std, void* images,
+                     float z_clip, float blur_radius, int H, int W, int K, int flags, const float* out_mean_std, void* images,
                      int* pix_to_face, float* zbuf, float* bary, float* dists, int64_t* counters,
                      void* workspace, size_t workspace_bytes, void* stream);
 /* backward of the above w.r.t. the cameras ([upstream] _C.rasterize_meshes_backward + autograd
@@ -177,6 +183,25 @@ int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face
                       float* gT, float* gC,
                       float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,
                       void* stream);
+
+/* -- soft shading of K fragments per pixel (renderer.py:4-6 SoftPhongShader / SoftSilhouetteShader) -------- */
+/* mode 0: [upstream] blending.softmax_rgb_blend over per-fragment Phong colours (SoftPhongShader; sigma, gamma = BlendParams,
+ * znear / zfar = the camera's 1 / 100); mode 1: blending.sigmoid_alpha_blend (SoftSilhouetteShader: RGB = 1, alpha = 1 -
+ * prod(1 - sigmoid(-dists / sigma))).  Input: the fragments mvr_mesh_forward wrote with K = faces_per_pixel and
+ * blur_radius > 0 (pix_to_face, zbuf, bary, dists: (n,H,W,K[,3])); output rgba (n,4,H,W) fp32. */
+int mvr_mesh_soft_blend_forward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
+                                int64_t total_verts, int64_t total_faces, const float* Cc, const float* light,
+                                int light_stride, const float* obj_rgb, const float* bg_rgb, int H, int W, int K, int flags,
+                                int mode, float sigma, float gamma, float znear, float zfar, const int* pix_to_face,
+                                const float* zbuf, const float* bary, const float* dists, float* rgba, void* stream);
+/* backward of rasterizer (incl. grad_zbuf, grad_dists, clipped barycentrics: [upstream] RasterizeMeshesBackward) + blend +
+ * Phong + projection w.r.t. the cameras: grad_rgba (n,4,H,W) -> gR, gT, gC.  Fragments are recomputed from pix_to_face. */
+int mvr_mesh_soft_backward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
+                           int64_t total_verts, int64_t total_faces, int max_verts, const float* R, const float* T,
+                           const float* Cc, const float* light, int light_stride, const float* obj_rgb,
+                           const float* bg_rgb, float k00, float k11, int H, int W, int K, int flags, int mode, float sigma,
+                           float gamma, float znear, float zfar, const int* pix_to_face, const float* grad_rgba, float* gR,
+                           float* gT, float* gC, void* workspace, size_t workspace_bytes, void* stream);
 
 /* -- point clouds --------------------------------------------------------------------------- */
 /* scratch for one forward or backward call (forward: pixel table + per-view projected points, tile lists, or for K not

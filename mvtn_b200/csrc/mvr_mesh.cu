@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
   unsigned long long* keys = p.keys + (size_t)n * p.H * p.W;
   const unsigned long long* prev = p.layer > 0 ? p.prev + (size_t)n * p.H * p.W : nullptr;
   const int qcap = p.wcap;      // SC_QCAP, or a handful under MVR_TEST_TINY_QUEUES
+  const SoftMode sm = soft_mode(p);
+  const bool soft = sm.on();    // blur_radius > 0 / clipped barycentrics: every pixel of the (grown) bbox is a candidate
 
   for (int i = tid; i < p.W + p.H; i += MVR_THREADS) s_tab[i] = __ldg(p.tab + i);
   if (tid < 4) (&s_cnt2[0][0])[tid] = 0;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
         s_rec[6][tid] = fc.x2; s_rec[7][tid] = fc.y2; s_rec[8][tid] = fc.z2;
         s_rec[9][tid] = __int_as_float(fid);
         const float zmin = fminf(fminf(fc.z0, fc.z1), fc.z2);
-        s_rec[10][tid] = __uint_as_float((persp && zmin > 1e-3f) ? __float_as_uint(zmin * 0.999999f) : 0u);
+        s_rec[10][tid] = __uint_as_float((persp && zmin > 1e-3f && !soft) ? __float_as_uint(zmin * 0.999999f) : 0u);
         if (straddles) {
           // crosses the near clip plane ([upstream] clip.py): counted, visible or not (as the oracle does), and handed to
           // the whole CTA below, which rasterizes its one or two clipped sub-triangles
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
             s_rec[12][tid] = __int_as_float(bw | (bh << 16));
             s_big[atomicAdd(&s_cnt[1], 1)] = tid;
             bh = 0;
-          } else {
+          } else if (!soft) {
             se = span_edges(fc, p.ndc_max);
           }
         }
@@ -215,7 +217,10 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
       for (int row = 0; row < maxr; ++row) {      // warp-uniform trip count
         int cnt = 0, xs = 0;
         const int yy = yl + row;
-        if (row < bh) cnt = row_span_regs(se, s_yf[yy], xl, bw, p.W, p.jx_scale, p.jx_off, xs);
+        if (row < bh) {
+          if (soft) { cnt = bw; xs = xl; }
+          else cnt = row_span_regs(se, s_yf[yy], xl, bw, p.W, p.jx_scale, p.jx_off, xs);
+        }
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
               fc.x1 = s_rec[3][tid]; fc.y1 = s_rec[4][tid]; fc.z1 = s_rec[5][tid];
               fc.x2 = s_rec[6][tid]; fc.y2 = s_rec[7][tid]; fc.z2 = s_rec[8][tid];
               resolve_pixel(fc, face_edges(fc), fid, 0u, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
-                            prev ? prev + (size_t)yy * p.W + xx : nullptr);
+                            prev ? prev + (size_t)yy * p.W + xx : nullptr, sm);
             }
           }
         }
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
         fc.x1 = s_rec[3][slot]; fc.y1 = s_rec[4][slot]; fc.z1 = s_rec[5][slot];
         fc.x2 = s_rec[6][slot]; fc.y2 = s_rec[7][slot]; fc.z2 = s_rec[8][slot];
         resolve_pixel_with(fc, face_edges(fc), __float_as_int(s_rec[9][slot]), zmin_bits, persp, s_xf[xx], s_yf[yy],
-                           keys + (size_t)yy * p.W + xx, prev ? prev + (size_t)yy * p.W + xx : nullptr, cur);
+                           keys + (size_t)yy * p.W + xx, prev ? prev + (size_t)yy * p.W + xx : nullptr, cur, sm);
       }
     }
     // ---------------- large faces: the whole CTA walks the bbox ----------------
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
           for (int yy = cyl + warp; yy <= cyh; yy += NWARPS)
             for (int xx = cxl + lane; xx <= cxh; xx += 32)
               resolve_pixel(sf, sfe, bfid, 0u, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
-                            prev ? prev + (size_t)yy * p.W + xx : nullptr);
+                            prev ? prev + (size_t)yy * p.W + xx : nullptr, sm);
         }
         continue;
       }
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
         for (int x = lane; x < bbw; x += 32) {
           const int xx = bxl + x, yy = byl + y;
           resolve_pixel(fc, fe, bfid, zmin_bits, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
-                        prev ? prev + (size_t)yy * p.W + xx : nullptr);
+                        prev ? prev + (size_t)yy * p.W + xx : nullptr, sm);
         }
     }
     n_big += (tid == 0) ? n_bigf - n_clipf : 0;
@@ -381,7 +386,11 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_shade_kernel(const Mes
       }
       const float yf = __ldg(p.tab + p.W + yi);
       const FaceEdges fe = face_edges(fc);
-      if (EXACT) {
+      if (EXACT && soft_mode(p).on()) {      // blurred rasterizer: (clipped) barycentrics and the SIGNED edge distance
+        float bu[3];
+        bool inside;
+        raster_soft(fc, fe, persp, p.flags & MVR_CLIP_BARYCENTRIC, xf, yf, bu, bb, pz, dd, inside);
+      } else if (EXACT) {
         // The barycentrics are recomputed with the SAME exact operation sequence as the scatter (from the same
         // projected vertices), so the fragments returned to the caller are the rasterizer's, bit for bit.
         raster_test(fc, fe, persp, xf, yf, w, bb, pz);
@@ -519,7 +528,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
                                 int64_t total_verts, int64_t total_faces, int max_verts, int max_faces,
                                 const float* R, const float* T, const float* Cc, const float* light,
                                 int light_stride, const float* obj_rgb, const float* bg_rgb, float k00, float k11,
-                                float z_clip, int H, int W, int K, int flags, const float* out_mean_std, void* images,
+                                float z_clip, float blur_radius, int H, int W, int K, int flags, const float* out_mean_std, void* images,
                                 int* pix_to_face, float* zbuf, float* bary, float* dists, int64_t* counters,
                                 void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_mesh_common("mvr_mesh_forward", B, M, H, W, K, total_verts, total_faces, max_verts);
@@ -535,6 +544,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   }
   if (!(flags & MVR_RGB_PER_ELEMENT) && !obj_rgb) { set_error("mvr_mesh_forward: obj_rgb is NULL and the geometry has no per-vertex colours"); return -6; }
   if (!out_norm_valid(out_mean_std)) { set_error("mvr_mesh_forward: out_mean_std needs std > 0"); return -9; }
+  if (!(blur_radius >= 0.f)) { set_error("mvr_mesh_forward: blur_radius must be >= 0"); return -10; }
   const WsLayout w = ws_layout(B, M, H, W, K, total_verts, total_faces);
   if (workspace_bytes < w.total) { set_error("mvr_mesh_forward: workspace too small (%zu < %zu)", workspace_bytes, w.total); return -7; }
   const int fpc = scatter_fpc();
@@ -551,6 +561,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.R = R; p.T = T; p.Cc = Cc; p.light = light; p.light_stride = light_stride;
   p.obj_rgb = obj_rgb; p.bg_rgb = bg_rgb;
   p.k00 = k00; p.k11 = k11; p.z_clip = z_clip;
+  p.blur_radius = blur_radius > 0.f ? blur_radius : 0.f; p.blur_r = sqrtf(p.blur_radius);
   p.B = B; p.M = M; p.H = H; p.W = W; p.K = K; p.flags = flags;
   p.chunks_per_view = chunks_per_view; p.layer = 0; p.faces_per_cta = fpc;
   p.ndc_max = W > H ? (float)((W + H - 1) / H) : (float)((H + W - 1) / W);      // bound on |pixel-centre NDC| (>= aspect ratio)
@@ -569,7 +580,8 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   p.onorm = make_out_norm(out_mean_std);
   p.wsflags = (int*)(wb + w.flags);
   const size_t HW = (size_t)H * W;
-  if (K == 1 && ((flags & MVR_FORWARD_TILED) || mesh_tiled_enabled())) {
+  const bool soft_raster = p.blur_radius > 0.f || (flags & MVR_CLIP_BARYCENTRIC);
+  if (K == 1 && !soft_raster && ((flags & MVR_FORWARD_TILED) || mesh_tiled_enabled())) {
     // tile-binned path (mvr_mesh_tile.cu): keys live in shared memory -- no key plane, no memset of it, no separate shade pass
     p.flags &= ~(MVR_WS_KEYS_ARMED | MVR_WS_REARM_KEYS);
     cudaError_t e = cudaMemsetAsync(wb + w.flags, 0xFF, 4 * sizeof(int), st);      // arms WSF_CLIP

@@ -103,83 +103,6 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_shade_clipped_kernel(const M
 // clipped triangle -> original (x_ndc, y_ndc, z_view) (autograd of [upstream] clip.py), then the projection as usual.
 // Same derivation as oracle/mvr_oracle.c clip_face_bwd / raster_bwd_one / phong_pixel_bwd, in fp32.
 // ------------------------------------------------------------------------------------------------
-// d colour / d (barycentrics, camera centre, interpolated normal) of phong_pixel
-__device__ __forceinline__ void phong_backward(const float bb[3], const float4 X0, const float4 X1, const float4 X2,
-                                               const float4 N0, const float4 N1, const float4 N2, const float4 c0,
-                                               const float4 c1, const float4 c2, const ShadeCtx& sc, float g0, float g1,
-                                               float g2, float gb[3], float gv[3], float gN[3]) {
-  const float3 P = interp(bb, X0, X1, X2);
-  const float3 Nn = interp(bb, N0, N1, N2);
-  const float3 tex = interp(bb, c0, c1, c2);
-  const float in = inv_norm_clamped(Nn.x, Nn.y, Nn.z, 1e-6f);
-  const float nx = Nn.x * in, ny = Nn.y * in, nz = Nn.z * in;
-  const float cosang = fmaf(nx, sc.lx, fmaf(ny, sc.ly, nz * sc.lz));
-  const float diff = fmaxf(cosang, 0.f);
-  const float vx = sc.cx - P.x, vy = sc.cy - P.y, vz = sc.cz - P.z;
-  const float iv = inv_norm_clamped(vx, vy, vz, 1e-6f);
-  const float vhx = vx * iv, vhy = vy * iv, vhz = vz * iv;
-  const float rx = fmaf(2.f * cosang, nx, -sc.lx), ry = fmaf(2.f * cosang, ny, -sc.ly), rz = fmaf(2.f * cosang, nz, -sc.lz);
-  const float dt = fmaf(vhx, rx, fmaf(vhy, ry, vhz * rz));
-  const bool lit = cosang > 0.f;
-  const float alpha = (dt > 0.f && lit) ? dt : 0.f;
-  const float kd = fmaf(MVR_DIFFUSE, diff, MVR_AMBIENT);
-  const float gtx = g0 * kd, gty = g1 * kd, gtz = g2 * kd;
-  const float gdiff = MVR_DIFFUSE * fmaf(g0, tex.x, fmaf(g1, tex.y, g2 * tex.z));
-  const float gs = MVR_SPECULAR * (g0 + g1 + g2);
-  const float a2 = alpha * alpha, a4 = a2 * a2, a8 = a4 * a4, a16 = a8 * a8, a32 = a16 * a16;
-  const float a63 = a32 * a16 * a8 * a4 * a2 * alpha;
-  const float gdt = (dt > 0.f && lit) ? gs * 64.f * a63 : 0.f;
-  const float gvhx = gdt * rx, gvhy = gdt * ry, gvhz = gdt * rz;
-  const float grx = gdt * vhx, gry = gdt * vhy, grz = gdt * vhz;
-  const float gcos = (lit ? gdiff : 0.f) + 2.f * fmaf(grx, nx, fmaf(gry, ny, grz * nz));
-  const float gnx = fmaf(2.f * cosang, grx, gcos * sc.lx), gny = fmaf(2.f * cosang, gry, gcos * sc.ly), gnz = fmaf(2.f * cosang, grz, gcos * sc.lz);
-  normalize_bwd3(Nn.x, Nn.y, Nn.z, 1e-6f, gnx, gny, gnz, gN[0], gN[1], gN[2]);
-  normalize_bwd3(vx, vy, vz, 1e-6f, gvhx, gvhy, gvhz, gv[0], gv[1], gv[2]);
-  // d bary_i = gtex.col_i + gN.n_i + gP.X_i  with gP = -gv
-  gb[0] = fmaf(gtx, c0.x, fmaf(gty, c0.y, gtz * c0.z)) + fmaf(gN[0], N0.x, fmaf(gN[1], N0.y, gN[2] * N0.z)) - fmaf(gv[0], X0.x, fmaf(gv[1], X0.y, gv[2] * X0.z));
-  gb[1] = fmaf(gtx, c1.x, fmaf(gty, c1.y, gtz * c1.z)) + fmaf(gN[0], N1.x, fmaf(gN[1], N1.y, gN[2] * N1.z)) - fmaf(gv[0], X1.x, fmaf(gv[1], X1.y, gv[2] * X1.z));
-  gb[2] = fmaf(gtx, c2.x, fmaf(gty, c2.y, gtz * c2.z)) + fmaf(gN[0], N2.x, fmaf(gN[1], N2.y, gN[2] * N2.z)) - fmaf(gv[0], X2.x, fmaf(gv[1], X2.y, gv[2] * X2.z));
-}
-
-// [upstream] BarycentricPerspectiveCorrectionBackward + BarycentricCoordsBackward + EdgeFunctionBackward for one pixel:
-// gb (3) w.r.t. the triangle's (corrected) barycentrics -> gq (3,3) w.r.t. its (x, y, z)
-__device__ __forceinline__ void raster_backward(const Face& fc, bool persp, float xf, float yf, const float gb_in[3], float gq[9]) {
-  const FaceEdges fe = face_edges(fc);
-  const float e0 = (xf - fc.x1) * fe.A0 - (yf - fc.y1) * fe.B0;
-  const float e1 = (xf - fc.x2) * fe.A1 - (yf - fc.y2) * fe.B1;
-  const float e2 = (xf - fc.x0) * fe.A2 - (yf - fc.y0) * fe.B2;
-  const float inv_area = 1.0f / fe.area_p;
-  const float w0 = e0 * inv_area, w1 = e1 * inv_area, w2 = e2 * inv_area;
-  float gb0 = gb_in[0], gb1 = gb_in[1], gb2 = gb_in[2];
-  float dz0 = 0.f, dz1 = 0.f, dz2 = 0.f;
-  if (persp) {
-    const float t0 = w0 * fc.z1 * fc.z2, t1 = w1 * fc.z0 * fc.z2, t2 = w2 * fc.z0 * fc.z1;
-    const float st = t0 + t1 + t2;
-    const bool clamped = st < MVR_K_EPS;
-    const float id = 1.0f / fmaxf(st, MVR_K_EPS);
-    if (!clamped) {      // b = t / sum(t) annihilates a common shift of d/db: remove it before it has to cancel in fp32
-      const float kk = (t0 * gb0 + t1 * gb1 + t2 * gb2) * id;
-      gb0 -= kk; gb1 -= kk; gb2 -= kk;
-    }
-    const float gden = clamped ? -(gb0 * t0 + gb1 * t1 + gb2 * t2) * id * id : 0.f;
-    const float gt0 = gb0 * id + gden, gt1 = gb1 * id + gden, gt2 = gb2 * id + gden;
-    gb0 = gt0 * fc.z1 * fc.z2; gb1 = gt1 * fc.z0 * fc.z2; gb2 = gt2 * fc.z0 * fc.z1;
-    dz0 = gt1 * w1 * fc.z2 + gt2 * w2 * fc.z1;
-    dz1 = gt0 * w0 * fc.z2 + gt2 * w2 * fc.z0;
-    dz2 = gt0 * w0 * fc.z1 + gt1 * w1 * fc.z0;
-  }
-  const float ge0 = gb0 * inv_area, ge1 = gb1 * inv_area, ge2 = gb2 * inv_area;
-  const float garea = -(gb0 * e0 + gb1 * e1 + gb2 * e2) * inv_area * inv_area;
-  float gx0, gy0, gx1, gy1, gx2, gy2;
-  gx1 = ge0 * (yf - fc.y2); gy1 = ge0 * (fc.x2 - xf); gx2 = ge0 * (fc.y1 - yf); gy2 = ge0 * (xf - fc.x1);          // e0 = E(p,v1,v2)
-  gx2 += ge1 * (yf - fc.y0); gy2 += ge1 * (fc.x0 - xf); gx0 = ge1 * (fc.y2 - yf); gy0 = ge1 * (xf - fc.x2);        // e1 = E(p,v2,v0)
-  gx0 += ge2 * (yf - fc.y1); gy0 += ge2 * (fc.x1 - xf); gx1 += ge2 * (fc.y0 - yf); gy1 += ge2 * (xf - fc.x0);      // e2 = E(p,v0,v1)
-  gx0 += garea * (fc.y2 - fc.y1); gy0 += garea * (fc.x1 - fc.x2);                                                  // area = E(v2,v0,v1)
-  gx1 += garea * (fc.y0 - fc.y2); gy1 += garea * (fc.x2 - fc.x0);
-  gx2 += garea * (fc.y1 - fc.y0); gy2 += garea * (fc.x0 - fc.x1);
-  gq[0] = gx0; gq[1] = gy0; gq[2] = dz0; gq[3] = gx1; gq[4] = gy1; gq[5] = dz1; gq[6] = gx2; gq[7] = gy2; gq[8] = dz2;
-}
-
 // backward of clip_face + conv_bary for one pixel of sub-triangle s: gq (3,3) w.r.t. the clipped triangle, gb (3)
 // w.r.t. the UNCLIPPED barycentrics, bcl the clipped barycentrics -> gfv (3,3) w.r.t. the original (x_ndc, y_ndc, z_view)
 static __device__ __noinline__ void clip_face_backward(const Face& f, float c, bool persp, int info, int s, const float gq[9],

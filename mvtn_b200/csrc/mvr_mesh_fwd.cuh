@@ -20,8 +20,8 @@ __device__ __forceinline__ bool face_pixel_bbox(const Face& f, const MeshParams&
   const float face_area = (f.x0 - f.x1) * (f.y2 - f.y1) - (f.y0 - f.y1) * (f.x2 - f.x1);
   if ((p.flags & MVR_CULL_BACKFACES) && face_area < 0.f) return false;
   if (face_area <= MVR_K_EPS && face_area >= -1.0f * MVR_K_EPS) return false;
-  const float xmin = fminf(fminf(f.x0, f.x1), f.x2), xmax = fmaxf(fmaxf(f.x0, f.x1), f.x2);
-  const float ymin = fminf(fminf(f.y0, f.y1), f.y2), ymax = fmaxf(fmaxf(f.y0, f.y1), f.y2);
+  const float xmin = fminf(fminf(f.x0, f.x1), f.x2) - p.blur_r, xmax = fmaxf(fmaxf(f.x0, f.x1), f.x2) + p.blur_r;
+  const float ymin = fminf(fminf(f.y0, f.y1), f.y2) - p.blur_r, ymax = fmaxf(fmaxf(f.y0, f.y1), f.y2) + p.blur_r;
   pixel_range(xmin, xmax, p.W, p.H, 0, p.W - 1, s_xf, xi_lo, xi_hi);
   if (xi_lo > xi_hi) return false;
   pixel_range(ymin, ymax, p.H, p.W, 0, p.H - 1, s_yf, yi_lo, yi_hi);
@@ -49,8 +49,9 @@ __device__ __forceinline__ bool face_pixel_bbox_conservative(const Face& f, cons
   const float face_area = (f.x0 - f.x1) * (f.y2 - f.y1) - (f.y0 - f.y1) * (f.x2 - f.x1);
   if ((p.flags & MVR_CULL_BACKFACES) && face_area < 0.f) return false;
   if (face_area <= MVR_K_EPS && face_area >= -1.0f * MVR_K_EPS) return false;
-  if (!pixel_range_conservative(fminf(fminf(f.x0, f.x1), f.x2), fmaxf(fmaxf(f.x0, f.x1), f.x2), p.W, p.jx_scale, p.jx_off, xi_lo, xi_hi)) return false;
-  return pixel_range_conservative(fminf(fminf(f.y0, f.y1), f.y2), fmaxf(fmaxf(f.y0, f.y1), f.y2), p.H, p.jy_scale, p.jy_off, yi_lo, yi_hi);
+  const float r = p.blur_r;      // [upstream] CheckPointOutsideBoundingBox grows the bbox by sqrt(blur_radius)
+  if (!pixel_range_conservative(fminf(fminf(f.x0, f.x1), f.x2) - r, fmaxf(fmaxf(f.x0, f.x1), f.x2) + r, p.W, p.jx_scale, p.jx_off, xi_lo, xi_hi)) return false;
+  return pixel_range_conservative(fminf(fminf(f.y0, f.y1), f.y2) - r, fmaxf(fmaxf(f.y0, f.y1), f.y2) + r, p.H, p.jy_scale, p.jy_off, yi_lo, yi_hi);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -76,28 +77,46 @@ __device__ __forceinline__ void sts_u32(unsigned int a, unsigned int v) {
 }
 
 // exact test of one (face, pixel) candidate and the keyed min on the global key plane
+// soft: blur_radius (squared), its root, and whether the fragment carries clipped barycentrics (all 0 / false: the hard rasterizer)
+struct SoftMode {
+  float blur, blur_r;
+  bool clipb;
+  __device__ __forceinline__ bool on() const { return blur > 0.f || clipb; }
+};
+__device__ __forceinline__ SoftMode soft_mode(const MeshParams& p) {
+  SoftMode m;
+  m.blur = p.blur_radius; m.blur_r = p.blur_r; m.clipb = p.flags & MVR_CLIP_BARYCENTRIC;
+  return m;
+}
 __device__ __forceinline__ void resolve_pixel_with(const Face& fc, const FaceEdges& fe, int fid, unsigned int zmin_bits,
                                                    bool persp, float xf, float yf, unsigned long long* key_ptr,
-                                                   const unsigned long long* prev_ptr, const unsigned long long cur);
+                                                   const unsigned long long* prev_ptr, const unsigned long long cur,
+                                                   const SoftMode sm = SoftMode{0.f, 0.f, false});
 __device__ __forceinline__ void resolve_pixel(const Face& fc, const FaceEdges& fe, int fid, unsigned int zmin_bits,
                                               bool persp, float xf, float yf, unsigned long long* key_ptr,
-                                              const unsigned long long* prev_ptr) {
-  resolve_pixel_with(fc, fe, fid, zmin_bits, persp, xf, yf, key_ptr, prev_ptr, __ldcg(key_ptr));
+                                              const unsigned long long* prev_ptr, const SoftMode sm = SoftMode{0.f, 0.f, false}) {
+  resolve_pixel_with(fc, fe, fid, zmin_bits, persp, xf, yf, key_ptr, prev_ptr, __ldcg(key_ptr), sm);
 }
 // cur: a snapshot of *key_ptr taken earlier (keys only decrease, so a stale snapshot is merely less effective)
 __device__ __forceinline__ void resolve_pixel_with(const Face& fc, const FaceEdges& fe, int fid, unsigned int zmin_bits,
                                                    bool persp, float xf, float yf, unsigned long long* key_ptr,
-                                                   const unsigned long long* prev_ptr, const unsigned long long cur) {
+                                                   const unsigned long long* prev_ptr, const unsigned long long cur, const SoftMode sm) {
   // early depth reject: pz is a convex combination of the vertex depths up to a few ulp (perspective-corrected
   // barycentrics sum to 1 unless their 1e-8 denominator clamp acts, which needs z ~ 1e-4; plain barycentrics sum
   // to area/(area+1e-8), so zmin_bits is 0 for them), hence a face whose nearest vertex is clearly behind the
   // pixel's current winner cannot produce a smaller key.  A stale `cur` only makes the test less effective.
   if (zmin_bits > (unsigned int)(cur >> 32)) return;
   // [upstream] CheckPointOutsideBoundingBox (blur 0): the candidate generators only guarantee a superset of the bbox pixels
-  if (xf > fmaxf(fmaxf(fc.x0, fc.x1), fc.x2) || xf < fminf(fminf(fc.x0, fc.x1), fc.x2) || yf > fmaxf(fmaxf(fc.y0, fc.y1), fc.y2) ||
-      yf < fminf(fminf(fc.y0, fc.y1), fc.y2)) return;
+  if (xf > fmaxf(fmaxf(fc.x0, fc.x1), fc.x2) + sm.blur_r || xf < fminf(fminf(fc.x0, fc.x1), fc.x2) - sm.blur_r ||
+      yf > fmaxf(fmaxf(fc.y0, fc.y1), fc.y2) + sm.blur_r || yf < fminf(fminf(fc.y0, fc.y1), fc.y2) - sm.blur_r) return;
   float w[3], b[3], pz;
-  if (!raster_test(fc, fe, persp, xf, yf, w, b, pz)) return;
+  if (sm.on()) {      // [upstream] blur_radius > 0: inside, or closer than blur_radius (squared) to an edge
+    float bc[3], sd;
+    bool inside;
+    raster_soft(fc, fe, persp, sm.clipb, xf, yf, b, bc, pz, sd, inside);
+    if (pz < 0.f) return;
+    if (!inside && !(sd < sm.blur)) return;
+  } else if (!raster_test(fc, fe, persp, xf, yf, w, b, pz)) return;
   const unsigned long long key = make_key(pz, fid);
   if (key >= cur) return;
   if (prev_ptr && key <= __ldcg(prev_ptr)) return;

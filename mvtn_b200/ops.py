@@ -641,7 +641,7 @@ class PackedMeshes:
 # mesh rendering
 # --------------------------------------------------------------------------------------------------
 def _mesh_forward_launch(geom: "PackedMeshes", M, R, T, Cc, light, obj_rgb, bg_rgb, k00, k11, z_clip, H, W, K, flags,
-                         want_fragments, out_norm, out_dtype):
+                         want_fragments, out_norm, out_dtype, blur_radius=0.0):
     """Argument normalisation, output allocation and ONE mvr_mesh_forward call.  Returns (saved, images, extras): `saved` is
     what the matching backward launch needs."""
     lib = L.load()
@@ -674,7 +674,7 @@ def _mesh_forward_launch(geom: "PackedMeshes", M, R, T, Cc, light, obj_rgb, bg_r
     with _on(dev):
         L.check(lib.mvr_mesh_forward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
                                      geom.total_verts, geom.total_faces, geom.max_verts, geom.max_faces, _ptr(R), _ptr(T), _ptr(Cc),
-                                     _ptr(light), light_stride, _ptr(obj_rgb), _ptr(bg_rgb), k00, k11, z_clip, H, W,
+                                     _ptr(light), light_stride, _ptr(obj_rgb), _ptr(bg_rgb), k00, k11, z_clip, float(blur_radius), H, W,
                                      K, flags | ws_flags, out_norm, _ptr(images), _ptr(p2f), _ptr(zbuf), _ptr(bary), _ptr(dists),
                                      _ptr(counters), _ptr(ws), ws.numel(), _stream(dev)), "mvr_mesh_forward")
     cfg = (k00, k11, H, W, K, flags, out_norm, light_stride, z_clip, ws_commit())
@@ -783,6 +783,64 @@ class _MeshRenderFromAngles(torch.autograd.Function):
         return (ga.reshape(sa), ge.reshape(se), gd.reshape(sd)) + (None,) * 15
 
 
+SOFT_SHADERS = {"soft_phong": 0, "soft_silhouette": 1}
+
+
+class _MeshRenderSoft(torch.autograd.Function):
+    """Blurred rasterizer (K fragments per pixel, signed edge distances, clipped barycentrics) + soft blend as one autograd
+    node: (R, T, C) -> RGBA (n,4,H,W).  [upstream] MeshRasterizer(blur_radius, faces_per_pixel) + SoftPhongShader
+    (softmax_rgb_blend) / SoftSilhouetteShader (sigmoid_alpha_blend); renderer.py:4-6, :91-92."""
+
+    @staticmethod
+    def forward(ctx, R, T, Cc, geom: PackedMeshes, M, light, obj_rgb, bg_rgb, k00, k11, z_clip, H, W, K, flags, blur_radius,
+                mode, sigma, gamma, znear, zfar):
+        lib = L.load()
+        cfg, saved, _hard, extras = _mesh_forward_launch(geom, M, R, T, Cc, light, obj_rgb, bg_rgb, k00, k11, z_clip, H, W, K, flags,
+                                                         True, None, None, blur_radius=blur_radius)
+        p2f, counters, zbuf, bary, dists = extras
+        Rs, Ts, Cs, lt, col, _ = saved
+        dev = geom.device
+        N = geom.B * M
+        rgba = torch.empty((N, 4, H, W), dtype=torch.float32, device=dev)
+        light_stride = cfg[7]
+        fl = cfg[5]
+        bg = _f32c(bg_rgb)
+        with _on(dev):
+            L.check(lib.mvr_mesh_soft_blend_forward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
+                                                    geom.total_verts, geom.total_faces, _ptr(Cs), _ptr(lt), light_stride,
+                                                    _ptr(col), _ptr(bg), H, W, K, fl, mode, sigma, gamma, znear, zfar, _ptr(p2f),
+                                                    _ptr(zbuf), _ptr(bary), _ptr(dists), _ptr(rgba), _stream(dev)),
+                    "mvr_mesh_soft_blend_forward")
+        ctx.set_materialize_grads(False)
+        ctx.geom, ctx.M = geom, M
+        ctx.cfg = (k00, k11, H, W, K, fl, light_stride, mode, sigma, gamma, znear, zfar)
+        ctx.save_for_backward(Rs, Ts, Cs, lt, col, bg, p2f)
+        ctx.mark_non_differentiable(p2f, counters, zbuf, bary, dists)
+        return rgba, p2f, counters, zbuf, bary, dists
+
+    @staticmethod
+    def backward(ctx, g_rgba, *_unused):
+        if g_rgba is None:
+            return (None,) * 21
+        lib = L.load()
+        geom, M = ctx.geom, ctx.M
+        R, T, Cc, light, col, bg, p2f = ctx.saved_tensors
+        k00, k11, H, W, K, fl, light_stride, mode, sigma, gamma, znear, zfar = ctx.cfg
+        dev = geom.device
+        N = geom.B * M
+        g_rgba = _f32c(g_rgba)
+        g = torch.empty(15 * N, dtype=torch.float32, device=dev)
+        gR, gT, gC = g[: 9 * N].view(N, 3, 3), g[9 * N: 12 * N].view(N, 3), g[12 * N:].view(N, 3)
+        ws = workspace(dev, lib.mvr_mesh_workspace_bytes(geom.B, M, H, W, K, geom.total_verts, geom.total_faces))
+        with _on(dev):
+            L.check(lib.mvr_mesh_soft_backward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B, M,
+                                               geom.total_verts, geom.total_faces, geom.max_verts, _ptr(R), _ptr(T), _ptr(Cc),
+                                               _ptr(light), light_stride, _ptr(col), _ptr(bg), k00, k11, H, W, K, fl, mode, sigma,
+                                               gamma, znear, zfar, _ptr(p2f), _ptr(g_rgba), _ptr(gR), _ptr(gT), _ptr(gC), _ptr(ws),
+                                               ws.numel(), _stream(dev)), "mvr_mesh_soft_backward")
+        return (gR, gT, gC) + (None,) * 18
+
+
 def render_meshes_from_angles(geom: PackedMeshes, M: int, azim, elev, dist, light, obj_rgb, bg_rgb, image_size,
                               faces_per_pixel=1, cull_backfaces=False, perspective_correct=True, fov=60.0, znear=1.0,
                               z_clip: Optional[float] = None, normalize=None, out_dtype=None, after_cameras=None):
@@ -801,8 +859,13 @@ def render_meshes_from_angles(geom: PackedMeshes, M: int, azim, elev, dist, ligh
 
 def render_meshes(geom: PackedMeshes, M: int, R, T, Cc, light, obj_rgb, bg_rgb, image_size: int, faces_per_pixel=1,
                   cull_backfaces=False, perspective_correct=True, fov=60.0, znear=1.0, z_clip: Optional[float] = None,
-                  fragments=False, verts: Optional[torch.Tensor] = None, _extra_flags=0, normalize=None, out_dtype=None):
-    """images (B*M,3,H,W) [+ dict of fragments].  HardPhong + hard blend, blur_radius 0.
+                  fragments=False, verts: Optional[torch.Tensor] = None, _extra_flags=0, normalize=None, out_dtype=None,
+                  shader="hard_phong", blur_radius=0.0, clip_barycentric_coords=None, sigma=1e-4, gamma=1e-4, zfar=100.0):
+    """images (B*M,3,H,W) [+ dict of fragments].  HardPhong + hard blend, blur_radius 0 (MVTN's configuration), or --
+    shader="soft_phong" / "soft_silhouette"  -- RGBA (B*M,4,H,W) from the K = faces_per_pixel fragments of the
+    BLURRED rasterizer ([upstream] blur_radius in squared NDC units, clip_barycentric_coords default True iff blur_radius > 0)
+    blended by softmax_rgb_blend over per-fragment Phong colours / sigmoid_alpha_blend (sigma, gamma = BlendParams);
+    differentiable w.r.t. R, T, C through colours, depths and the signed edge distances (grad_dists).
     `verts`: pass the packed (Vtot,3) vertex tensor the geometry was built from to get gradients w.r.t. it.
     `normalize=(mean, std)` / `out_dtype=torch.bfloat16`: consumer-side fusion -- the kernel writes
     (x - mean) / std (Trainer_mvt.py:41-49) in the dtype the CNN consumes; gradients flow through both."""
@@ -812,6 +875,19 @@ def render_meshes(geom: PackedMeshes, M: int, R, T, Cc, light, obj_rgb, bg_rgb, 
         z_clip = znear / 2 if perspective_correct else -1.0   # [upstream] MeshRasterizer.forward
     flags = (L.PERSPECTIVE_CORRECT if perspective_correct else 0) | (L.CULL_BACKFACES if cull_backfaces else 0) | _extra_flags
     H, W = _hw(image_size)
+    if clip_barycentric_coords is None:
+        clip_barycentric_coords = blur_radius > 0
+    if shader != "hard_phong":
+        if shader not in SOFT_SHADERS:
+            raise ValueError("shader must be 'hard_phong', 'soft_phong' or 'soft_silhouette'")
+        if verts is not None or normalize is not None or out_dtype not in (None, torch.float32):
+            raise ValueError("the soft shaders return fp32 RGBA and gradients w.r.t. the cameras only")
+        flags |= L.CLIP_BARYCENTRIC if clip_barycentric_coords else 0
+        out = _MeshRenderSoft.apply(R, T, Cc, geom, M, light, obj_rgb, bg_rgb, k00, k11, float(z_clip), H, W, int(faces_per_pixel),
+                                    flags, float(blur_radius), SOFT_SHADERS[shader], float(sigma), float(gamma), float(znear), float(zfar))
+        return out[0], {"pix_to_face": out[1], "counters": out[2], "zbuf": out[3], "bary_coords": out[4], "dists": out[5]}
+    if blur_radius > 0 or clip_barycentric_coords:
+        raise ValueError("blur_radius > 0 / clipped barycentrics need shader='soft_phong' or 'soft_silhouette'")
     out = _MeshRender.apply(R, T, Cc, verts, geom, M, light, obj_rgb, bg_rgb, k00, k11, float(z_clip), H, W,
                             int(faces_per_pixel), flags, bool(fragments), _out_norm(normalize), out_dtype)
     images, p2f, counters = out[0], out[1], out[2]

@@ -112,6 +112,9 @@ class MVRenderer(nn.Module):
             per backward (two forwards of the same shapes before a backward would overwrite the first one's saved state).
         cache_geometry: keep the packed device geometry of the last mesh batch and reuse it when the
             same list object is rendered again.
+        shader / blur_radius / blend_sigma / blend_gamma / keep_alpha: mesh path -- "soft_phong" (SoftPhongShader) or
+            "soft_silhouette" (SoftSilhouetteShader) blend the faces_per_pixel fragments of the blurred rasterizer (the
+            shaders renderer.py:4-6 imports); images keep 3 channels as renderer.py:112 unless keep_alpha.
         normalize: None or (mean, std) (3-vectors or scalars): the kernels write (image - mean) / std, the
             normalisation viewGCN/tools/Trainer_mvt.py:41-49 applies before the CNN.
         out_dtype: torch.float32 (default) or torch.bfloat16 -- the dtype the images are written in (a bf16 backbone
@@ -121,8 +124,10 @@ class MVRenderer(nn.Module):
     def __init__(self, nb_views, image_size=224, pc_rendering=True, object_color="white", background_color="white",
                  faces_per_pixel=1, points_radius=0.006, points_per_pixel=1, light_direction="random",
                  cull_backfaces=False, *, compositor="norm", perspective_correct=True, cache_geometry=False,
-                 normalize=None, out_dtype=None, copy_stream=False, cuda_graph=None):
+                 normalize=None, out_dtype=None, copy_stream=False, cuda_graph=None, shader="hard_phong", blur_radius=0.0,
+                 blend_sigma=1e-4, blend_gamma=1e-4, keep_alpha=False):
         super().__init__()
+        self.shader, self.blur_radius, self.blend_sigma, self.blend_gamma, self.keep_alpha = shader, blur_radius, blend_sigma, blend_gamma, keep_alpha
         self.copy_stream = copy_stream
         self.cuda_graph = cuda_graph      # None = auto: replay small (launch-bound) point steps from CUDA graphs
         self._point_graphs = {}
@@ -211,9 +216,16 @@ class MVRenderer(nn.Module):
         obj = None if geom.per_vertex_rgb else _device_vec(color, device)
         fixed_light = None if lights is None else _device_vec(lights, device)
 
+        soft = self.shader != "hard_phong"
+
         def render(R, T, C, dist_, C_light):
             geom.finish()
             light = C_light if fixed_light is None else fixed_light
+            if soft:
+                return ops.render_meshes(geom, self.nb_views, R, T, C, light, obj, bg, self.image_size,
+                                         faces_per_pixel=self.faces_per_pixel, cull_backfaces=self.cull_backfaces,
+                                         perspective_correct=self.perspective_correct, shader=self.shader,
+                                         blur_radius=self.blur_radius, sigma=self.blend_sigma, gamma=self.blend_gamma)
             return ops.render_meshes(geom, self.nb_views, R, T, C, light, obj, bg, self.image_size,
                                      faces_per_pixel=self.faces_per_pixel, cull_backfaces=self.cull_backfaces,
                                      perspective_correct=self.perspective_correct, verts=getattr(geom, "grad_verts", None),
@@ -222,7 +234,7 @@ class MVRenderer(nn.Module):
         try:
             out = None
             reader = []
-            if getattr(geom, "grad_verts", None) is None:
+            if getattr(geom, "grad_verts", None) is None and not soft:
                 # fast path: cameras + rasterizer as ONE autograd node (ops.render_meshes_from_angles); the validity flag
                 # is still awaited through an event recorded between the camera kernel and the rasterizer
                 az, el, di = self._views(azim, elev, dist, device)
@@ -242,7 +254,12 @@ class MVRenderer(nn.Module):
         self.last_fragments = frag
         B = geom.B
         H, W = ops._hw(self.image_size)
-        rendered_images = images.view(B, self.nb_views, 3, H, W)
+        if soft:      # RGBA from the soft shaders; renderer.py:112 keeps [..., 0:3]
+            rendered_images = images.view(B, self.nb_views, 4, H, W)
+            if not self.keep_alpha:
+                rendered_images = rendered_images[:, :, :3]
+        else:
+            rendered_images = images.view(B, self.nb_views, 3, H, W)
         return rendered_images, FoVPerspectiveCameras(R, T, C)
 
     def render_points(self, points, color, azim, elev, dist, background_color=(0.0, 0.0, 0.0)):

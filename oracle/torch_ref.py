@@ -262,3 +262,149 @@ def render_points_view(pts_world, feats, R, T, inv_dist, radius, bg, H, W, K, al
     img = composite(idx.permute(2, 0, 1), w.permute(2, 0, 1), feats, alpha_mode)
     fg = (idx[..., 0] >= 0)[None]
     return torch.where(fg, img, bg[:, None, None].expand_as(img)), idx
+
+
+# --------------------------------------------------------------------------------------------------
+# Soft rasterization (SURVEY 8f N3; renderer.py:4-6 imports SoftPhongShader / SoftSilhouetteShader, :91-92 blur_radius /
+# faces_per_pixel).  [upstream] rasterize_meshes_cpu.cpp with blur_radius > 0 and clip_barycentric_coords, geometry_utils.h
+# PointTriangleDistanceForward / BarycentricClipForward, renderer/blending.py softmax_rgb_blend / sigmoid_alpha_blend.
+# --------------------------------------------------------------------------------------------------
+def point_segment_dist2(px, py, ax, ay, bx, by):
+    """[upstream] PointLineDistanceForward: squared distance to the SEGMENT a-b (degenerate: distance to b)."""
+    dx, dy = bx - ax, by - ay
+    l2 = dx * dx + dy * dy
+    t = (dx * (px - ax) + dy * (py - ay)) / torch.where(l2 <= K_EPS, torch.ones_like(l2), l2)
+    tt = t.clamp(0.0, 1.0)
+    qx, qy = ax + tt * dx, ay + tt * dy
+    d = (px - qx) * (px - qx) + (py - qy) * (py - qy)
+    return torch.where(l2 <= K_EPS, (px - bx) * (px - bx) + (py - by) * (py - by), d)
+
+
+def point_triangle_dist2(px, py, fv):
+    """[upstream] PointTriangleDistanceForward: min over the edges (v0,v1), (v0,v2), (v1,v2)."""
+    x0, y0, x1, y1, x2, y2 = fv[..., 0, 0], fv[..., 0, 1], fv[..., 1, 0], fv[..., 1, 1], fv[..., 2, 0], fv[..., 2, 1]
+    e01 = point_segment_dist2(px, py, x0, y0, x1, y1)
+    e02 = point_segment_dist2(px, py, x0, y0, x2, y2)
+    e12 = point_segment_dist2(px, py, x1, y1, x2, y2)
+    return torch.minimum(torch.minimum(e01, e02), e12)
+
+
+def bary_clip(b):
+    """[upstream] BarycentricClipForward: clamp below at 0, renormalise (sum floored at 1e-5)."""
+    w = b.clamp_min(0.0)
+    return w / w.sum(-1, keepdim=True).clamp_min(1e-5)
+
+
+def soft_fragments(px, py, fv, perspective_correct, clip_bary):
+    """Per (pixel, face) quantities of the blurred rasterizer: unclipped barycentrics (inside test), the barycentrics the
+    fragment carries, depth and the SIGNED squared edge distance (negative inside)."""
+    b = bary_coords(px, py, fv, perspective_correct)
+    bc = bary_clip(b) if clip_bary else b
+    pz = (bc * fv[..., 2]).sum(-1)
+    d = point_triangle_dist2(px, py, fv)
+    inside = (b > 0).all(-1)
+    return b, bc, pz, torch.where(inside, -d, d), inside
+
+
+def rasterize_meshes_soft(face_verts, H, W, K, blur_radius, perspective_correct=True, clip_bary=None, cull_backfaces=False):
+    """One view, blur_radius >= 0 (squared NDC units, as upstream).  -> p2f (H,W,K) long, zbuf, bary (H,W,K,3), dists (signed),
+    all -1 padded.  A face is a fragment of a pixel when the pixel lies in its bbox grown by sqrt(blur_radius) and is inside it
+    or closer than blur_radius (squared) to an edge; the K lexicographically smallest (z, face) win."""
+    if clip_bary is None:
+        clip_bary = blur_radius > 0
+    dt = face_verts.dtype
+    yf = pix_centers(H, dt)[:, None, None]
+    xf = pix_centers(W, dt)[None, :, None]
+    fv = face_verts[None, None]
+    b, bc, pz, sd, inside = soft_fragments(xf, yf, fv, perspective_correct, clip_bary)
+    x, y, z = face_verts[..., 0], face_verts[..., 1], face_verts[..., 2]
+    area = _edge(x[:, 0], y[:, 0], x[:, 1], y[:, 1], x[:, 2], y[:, 2])
+    ok = ~((area <= K_EPS) & (area >= -K_EPS))
+    if cull_backfaces:
+        ok &= ~(area < 0)
+    ok &= ~(z.min(dim=1).values < K_EPS)
+    r = math.sqrt(blur_radius)
+    inbox = (xf <= x.max(1).values + r) & (xf >= x.min(1).values - r) & (yf <= y.max(1).values + r) & (yf >= y.min(1).values - r)
+    hit = ok[None, None] & inbox & ~(pz < 0) & (inside | (sd < blur_radius))
+    key = torch.where(hit, pz, torch.full_like(pz, float("inf")))
+    order = torch.sort(key, dim=-1, stable=True)
+    Fn = face_verts.shape[0]
+    idx, zs = order.indices[..., :K], order.values[..., :K]
+    if Fn < K:
+        idx = torch.cat([idx, idx.new_zeros(H, W, K - Fn)], -1)
+        zs = torch.cat([zs, zs.new_full((H, W, K - Fn), float("inf"))], -1)
+    valid = torch.isfinite(zs)
+    g = idx.clamp(0, max(Fn - 1, 0))
+    p2f = torch.where(valid, idx, torch.full_like(idx, -1))
+    zbuf = torch.where(valid, zs, torch.full_like(zs, -1.0))
+    bary = torch.where(valid[..., None], torch.gather(bc, 2, g[..., None].expand(H, W, K, 3)), torch.full((H, W, K, 3), -1.0, dtype=dt))
+    dists = torch.where(valid, torch.gather(sd, 2, g), torch.full_like(zs, -1.0))
+    return p2f, zbuf, bary, dists
+
+
+def phong_colors(bary, p2f, verts, faces, normals, vert_rgb, light_dir, cam_center, ambient=0.5, diffuse=0.3, specular=0.2, shininess=64):
+    """[upstream] phong_shading for EVERY fragment: bary (H,W,K,3), p2f (H,W,K) -> colours (H,W,K,3); empty fragments
+    interpolate zeros (interpolate_face_attributes masks them), which shades to 0."""
+    fg = (p2f >= 0)[..., None]
+    f = p2f.clamp_min(0)
+    z3 = torch.zeros((), dtype=bary.dtype)
+    P = torch.where(fg, (bary[..., None] * verts[faces][f]).sum(-2), z3)
+    Nn = torch.where(fg, (bary[..., None] * normals[faces][f]).sum(-2), z3)
+    tex = torch.where(fg, (bary[..., None] * vert_rgb[faces][f]).sum(-2), z3)
+    n = F.normalize(Nn, p=2, dim=-1, eps=1e-6)
+    l = F.normalize(light_dir.expand_as(n), p=2, dim=-1, eps=1e-6)
+    cosang = (n * l).sum(-1)
+    mask = (cosang > 0).to(bary.dtype)
+    v = F.normalize(cam_center - P, p=2, dim=-1, eps=1e-6)
+    r = -l + 2 * (cosang[..., None] * n)
+    alpha = F.relu((v * r).sum(-1)) * mask
+    return (ambient + diffuse * F.relu(cosang))[..., None] * tex + (specular * torch.pow(alpha, shininess))[..., None]
+
+
+def softmax_rgb_blend(colors, p2f, zbuf, dists, bg, sigma=1e-4, gamma=1e-4, znear=1.0, zfar=100.0):
+    """[upstream] blending.softmax_rgb_blend -> (H,W,4) RGBA."""
+    eps = 1e-10
+    mask = (p2f >= 0).to(colors.dtype)
+    prob = torch.sigmoid(-dists / sigma) * mask
+    alpha = torch.prod(1.0 - prob, dim=-1)
+    z_inv = (zfar - zbuf) / (zfar - znear) * mask
+    z_inv_max = torch.max(z_inv, dim=-1).values[..., None].clamp(min=eps)
+    wnum = prob * torch.exp((z_inv - z_inv_max) / gamma)
+    delta = torch.exp((eps - z_inv_max) / gamma).clamp(min=eps)
+    denom = wnum.sum(-1)[..., None] + delta
+    rgb = ((wnum[..., None] * colors).sum(-2) + delta * bg) / denom
+    return torch.cat([rgb, (1.0 - alpha)[..., None]], -1)
+
+
+def sigmoid_alpha_blend(colors, p2f, dists, sigma=1e-4):
+    """[upstream] blending.sigmoid_alpha_blend -> (H,W,4): RGB of the nearest fragment, alpha = 1 - prod(1 - sigmoid(-d / sigma))."""
+    mask = (p2f >= 0).to(colors.dtype)
+    prob = torch.sigmoid(-dists / sigma) * mask
+    alpha = torch.prod(1.0 - prob, dim=-1)
+    return torch.cat([colors[..., 0, :], (1.0 - alpha)[..., None]], -1)
+
+
+def render_mesh_view_soft(verts, faces, normals, vert_rgb, R, T, Cc, light_dir, bg, k00, k11, H, W, K, blur_radius, shader,
+                          sigma=1e-4, gamma=1e-4, perspective_correct=True, clip_bary=None, p2f=None):
+    """Differentiable single-view soft render -> (4,H,W) RGBA + fragments.  shader: "soft_phong" | "soft_silhouette".
+    The raster step (which face is fragment k of a pixel) is not differentiated; barycentrics, depth and signed distances are
+    recomputed differentiably from the face ids (what autograd does through _RasterizeFaceVerts)."""
+    if clip_bary is None:
+        clip_bary = blur_radius > 0
+    ndc = project_perspective(verts, R, T, k00, k11)
+    fv = ndc[faces]
+    if p2f is None:
+        with torch.no_grad():
+            p2f, _, _, _ = rasterize_meshes_soft(fv, H, W, K, blur_radius, perspective_correct, clip_bary)
+    yf = pix_centers(H, verts.dtype)[:, None, None].expand(H, W, K)
+    xf = pix_centers(W, verts.dtype)[None, :, None].expand(H, W, K)
+    valid = p2f >= 0
+    _, bc, pz, sd, _ = soft_fragments(xf, yf, fv[p2f.clamp_min(0)], perspective_correct, clip_bary)
+    m1 = torch.full((), -1.0, dtype=verts.dtype)
+    bary = torch.where(valid[..., None], bc, m1); zbuf = torch.where(valid, pz, m1); dists = torch.where(valid, sd, m1)
+    if shader == "soft_silhouette":
+        img = sigmoid_alpha_blend(torch.ones_like(bary), p2f, dists, sigma)
+    else:
+        col = phong_colors(bary, p2f, verts, faces, normals, vert_rgb, light_dir, Cc)
+        img = softmax_rgb_blend(col, p2f, zbuf, dists, bg, sigma, gamma)
+    return img.permute(2, 0, 1), dict(pix_to_face=p2f, zbuf=zbuf, bary=bary, dists=dists)

@@ -53,8 +53,11 @@ def test_argument_validation_returns_status_not_crash():
     assert rc < 0 and b"points_per_pixel" in lib.mvr_last_error_string()
     rc = lib.mvr_points_forward(None, None, 1, 16, 1, None, None, None, -1.0, None, 64, 64, 1, 0, None, None, None, None, None, None, None, 0, None)
     assert rc < 0 and b"radius" in lib.mvr_last_error_string()
-    rc = lib.mvr_mesh_forward(None, None, None, 1, 1, 3, 1, 3, 1, None, None, None, None, 0, None, None, 1.7, 1.7, 0.5, 64, 64, 1, 0,
+    rc = lib.mvr_mesh_forward(None, None, None, 1, 1, 3, 1, 3, 1, None, None, None, None, 0, None, None, 1.7, 1.7, 0.5, 0.0, 64, 64, 1, 0,
                               None, None, None, None, None, None, None, None, 0, None)
+    assert rc < 0 and b"null pointer" in lib.mvr_last_error_string()
+    rc = lib.mvr_mesh_soft_blend_forward(None, None, None, 1, 1, 3, 1, None, None, 0, None, None, 64, 64, 4, 0, 7, 1e-4, 1e-4, 1.0, 100.0,
+                                         None, None, None, None, None, None)
     assert rc < 0 and b"null pointer" in lib.mvr_last_error_string()
     rc = lib.mvr_mesh_prepare(None, None, None, None, 1, 10, 10, 10, None, 0, None, 16, None)
     assert rc < 0 and b"too small" in lib.mvr_last_error_string()
@@ -328,7 +331,7 @@ def test_flag_constants_match_the_header():
     assert defs["ABI_VERSION"] == _lib.ABI_VERSION
     mirrored = [n for n in defs if hasattr(_lib, n) and n != "ABI_VERSION"]
     assert {"PERSPECTIVE_CORRECT", "CULL_BACKFACES", "COMPOSITE_ALPHA", "RGB_PER_ELEMENT", "FACES_I64", "IMAGES_BF16", "SCALE_IS_DIST",
-            "WS_KEYS_ARMED", "WS_REARM_KEYS", "WS_PROJECTED", "IDX_SPARSE", "FORWARD_TILED", "TEST_TINY_QUEUES", "NUM_COUNTERS"} <= set(mirrored)
+            "WS_KEYS_ARMED", "WS_REARM_KEYS", "WS_PROJECTED", "IDX_SPARSE", "FORWARD_TILED", "CLIP_BARYCENTRIC", "TEST_TINY_QUEUES", "NUM_COUNTERS"} <= set(mirrored)
     for n in mirrored:
         assert getattr(_lib, n) == defs[n], n
     flags = [defs[n] for n in mirrored if n not in ("NUM_COUNTERS", "CNT_STRADDLE", "CNT_BIG_FACES")]

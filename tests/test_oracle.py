@@ -643,3 +643,92 @@ def test_mesh_backward_with_clipping_matches_autograd(oracle):
         assert rel(bw["gC"], Cd.grad.numpy()) < 5e-5
         assert rel(bw["grad_verts"], vd.grad.numpy()) < 1e-4
         assert rel(bw["grad_normals"], nd.grad.numpy()) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ soft rasterization (8f N3)
+def _soft_setup(seed=3, faces=260, M=2):
+    v, f = synth.make_mesh(faces, seed)
+    az, el, di = synth.learned_spherical_views(1, M, seed + 2)
+    return v, f, az.numpy().ravel(), el.numpy().ravel(), di.numpy().ravel()
+
+
+def test_soft_rasterizer_reduces_to_the_hard_one_at_zero_blur(oracle):
+    """blur_radius = 0, no barycentric clipping: the torch restatement of the blurred rasterizer is the C oracle's rasterizer
+    (indices, depths, barycentrics and -- now signed -- distances, all inside => negative)."""
+    v, f, az, el, di = _soft_setup()
+    R, T, C = oracle.look_at(az, el, di)
+    fv = torch.from_numpy(oracle.project_perspective(v.numpy(), R[0], T[0], K00, K11))[f]
+    p2f, zb, ba, ds = tr.rasterize_meshes_soft(fv, 40, 40, 3, 0.0)
+    o = oracle.rasterize_meshes(fv.numpy(), [0], [f.shape[0]], 40, 40, 3, oracle.PERSPECTIVE_CORRECT)
+    assert (p2f.numpy() == o[0][0]).all() and (zb.numpy() == o[1][0]).all()
+    assert np.abs(ba.numpy() - o[2][0]).max() < 1e-6 and np.abs(ds.numpy() - o[3][0]).max() < 1e-7
+    assert (ds[p2f >= 0] <= 0).all()
+
+
+def test_soft_silhouette_closed_form_kat():
+    """One right triangle on a 16 x 16 image, blur radius 0.3 NDC: alpha of a pixel = sigmoid(-signed squared edge distance /
+    sigma) ([upstream] sigmoid_alpha_blend with one fragment); pixels farther than the radius from the triangle have no fragment."""
+    fv = torch.tensor([[[-0.5, -0.5, 2.0], [0.5, -0.5, 2.0], [-0.5, 0.5, 2.0]]])
+    S, blur, sigma = 16, 0.09, 0.02
+    p2f, zb, ba, ds = tr.rasterize_meshes_soft(fv, S, S, 2, blur, perspective_correct=False)
+    img = tr.sigmoid_alpha_blend(torch.ones_like(ba), p2f, ds, sigma)
+    xs = tr.pix_centers(S)
+    import math as _m
+    for yi in range(S):
+        for xi in range(S):
+            x, y = float(xs[xi]), float(xs[yi])
+            inside = x > -0.5 and y > -0.5 and x + y < 0.0
+            # distance to the three segments
+            def seg(ax, ay, bx, by):
+                dx, dy = bx - ax, by - ay
+                t = min(max(((x - ax) * dx + (y - ay) * dy) / (dx * dx + dy * dy), 0.0), 1.0)
+                return (x - ax - t * dx) ** 2 + (y - ay - t * dy) ** 2
+            d2 = min(seg(-0.5, -0.5, 0.5, -0.5), seg(-0.5, -0.5, -0.5, 0.5), seg(0.5, -0.5, -0.5, 0.5))
+            in_box = (-0.5 - 0.3 <= x <= 0.5 + 0.3) and (-0.5 - 0.3 <= y <= 0.5 + 0.3)
+            frag = in_box and (inside or d2 < blur)
+            if abs(d2 - blur) < 1e-4 or min(abs(x + 0.5), abs(y + 0.5), abs(x + y)) < 1e-4:
+                continue      # on a boundary: either answer is a rounding matter
+            assert (int(p2f[yi, xi, 0]) == 0) == frag, (yi, xi)
+            want = 1.0 / (1.0 + _m.exp((-d2 if inside else d2) / sigma)) if frag else 0.0
+            assert abs(float(img[yi, xi, 3]) - want) < 1e-5
+            assert int(p2f[yi, xi, 1]) == -1
+
+
+def test_softmax_blend_closed_form_and_clipped_barycentrics():
+    """softmax_rgb_blend with one fragment: rgb = (w c + delta bg) / (w + delta), w = sigmoid(-d / sigma) (its z_inv IS the max),
+    delta = exp((eps - z_inv) / gamma) clamped at eps; BarycentricClipForward clamps and renormalises."""
+    b = torch.tensor([[-0.2, 0.6, 0.6], [0.3, 0.3, 0.4], [-1.0, -1.0, 3.0]])
+    bc = tr.bary_clip(b)
+    assert torch.allclose(bc, torch.tensor([[0.0, 0.5, 0.5], [0.3, 0.3, 0.4], [0.0, 0.0, 1.0]]))
+    col = torch.tensor([[[[0.2, 0.4, 0.6], [0.0, 0.0, 0.0]]]]); p2f = torch.tensor([[[5, -1]]]); z = torch.tensor([[[3.0, -1.0]]])
+    d = torch.tensor([[[-0.01, -1.0]]]); bg = torch.tensor([1.0, 0.0, 0.5])
+    out = tr.softmax_rgb_blend(col, p2f, z, d, bg, sigma=0.01, gamma=0.5)
+    w = 1 / (1 + math.exp(-1.0)); zi = (100 - 3.0) / 99; delta = max(math.exp((1e-10 - zi) / 0.5), 1e-10)
+    want = [(w * c + delta * g) / (w + delta) for c, g in zip((0.2, 0.4, 0.6), (1.0, 0.0, 0.5))]
+    assert torch.allclose(out[0, 0, :3], torch.tensor(want), atol=1e-6) and abs(float(out[0, 0, 3]) - w) < 1e-6
+
+
+def test_soft_render_is_differentiable_and_matches_finite_differences(oracle):
+    """render_mesh_view_soft (fp64): autograd of the silhouette w.r.t. the camera translation against central differences (the
+    fragment assignment is frozen, as in PyTorch3D: the index is not differentiated)."""
+    v, f, az, el, di = _soft_setup(seed=5, faces=120, M=1)
+    R, T, C = oracle.look_at(az, el, di)
+    D = torch.float64
+    nrm = torch.from_numpy(oracle.vertex_normals(v.numpy(), f.numpy())).to(D)
+    Rd, Cd = torch.from_numpy(R[0]).to(D), torch.from_numpy(C[0]).to(D)
+    Td = torch.from_numpy(T[0]).to(D).requires_grad_()
+    g = torch.randn(4, 24, 24, generator=torch.Generator().manual_seed(2), dtype=D)
+    args = (v.to(D), f, nrm, torch.ones_like(v, dtype=D), Rd)
+
+    def loss(Tt, shader, p2f=None):
+        img, fr = tr.render_mesh_view_soft(*args, Tt, Cd, torch.tensor([0.3, 1.0, -0.5], dtype=D), torch.ones(3, dtype=D), K00, K11, 24, 24, 6,
+                                           4e-3, shader, sigma=2e-3, gamma=5e-2, p2f=p2f)
+        return (img * g).sum(), fr["pix_to_face"]
+    for shader in ("soft_silhouette", "soft_phong"):
+        val, p2f = loss(Td, shader)
+        (gT,) = torch.autograd.grad(val, Td)
+        for i in range(3):
+            h = 1e-6
+            e = torch.zeros(3, dtype=D); e[i] = h
+            fd = (loss(Td.detach() + e, shader, p2f)[0] - loss(Td.detach() - e, shader, p2f)[0]) / (2 * h)
+            assert abs(float(gT[i]) - float(fd)) <= 1e-5 * max(1.0, abs(float(fd))), (shader, i, float(gT[i]), float(fd))
