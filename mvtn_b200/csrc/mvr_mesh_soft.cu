@@ -117,6 +117,7 @@ __device__ __forceinline__ void soft_fragment_backward(const MeshParams& p, int 
   float gq[9];
   gbc[0] += gz * fc.z0; gbc[1] += gz * fc.z1; gbc[2] += gz * fc.z2;
   float gb[3] = {gbc[0], gbc[1], gbc[2]};
+  bool orth = false;
   if (clipb) {      // [upstream] BarycentricClipBackward: bc = w / s, w = max(b, 0), s = max(sum w, 1e-5)
     const float w0 = fmaxf(bu[0], 0.f), w1 = fmaxf(bu[1], 0.f), w2 = fmaxf(bu[2], 0.f);
     const float ssum = (w0 + w1) + w2;
@@ -125,8 +126,9 @@ __device__ __forceinline__ void soft_fragment_backward(const MeshParams& p, int 
     gb[0] = bu[0] > 0.f ? (gbc[0] - dot) * is : 0.f;
     gb[1] = bu[1] > 0.f ? (gbc[1] - dot) * is : 0.f;
     gb[2] = bu[2] > 0.f ? (gbc[2] - dot) * is : 0.f;
+    orth = ssum > 1e-5f;      // sum_i bu_i gb_i = dot - dot sum(bc) = 0
   }
-  raster_backward(fc, persp, xf, yf, gb, gq);
+  raster_backward(fc, persp, xf, yf, gb, gq, orth);
   gq[2] += gz * bc[0]; gq[5] += gz * bc[1]; gq[8] += gz * bc[2];
   // signed distance: sd = inside ? -d : d over the nearest edge ([upstream] PointTriangleDistanceBackward)
   if (gsd != 0.f) {

@@ -68,7 +68,11 @@ def bary_coords(px, py, fv, perspective_correct):
     w2 = _edge(px, py, x0, y0, x1, y1) / area
     if perspective_correct:
         t0, t1, t2 = w0 * z1 * z2, w1 * z0 * z2, w2 * z0 * z1
-        den = (t0 + t1 + t2).clamp_min(K_EPS)
+        # forward: max(sum, kEpsilon).  [upstream] BarycentricPerspectiveCorrectionBackward differentiates the denominator as
+        # the plain sum whether or not the clamp acted (it only acts OUTSIDE a face, i.e. for blurred fragments), so the clamp
+        # is straight-through here: value kEpsilon exactly, gradient 1.
+        ssum = t0 + t1 + t2
+        den = torch.where(ssum < K_EPS, K_EPS + (ssum - ssum.detach()), ssum)
         w0, w1, w2 = t0 / den, t1 / den, t2 / den
     return torch.stack([w0, w1, w2], dim=-1)
 

@@ -228,7 +228,7 @@ def test_mesh_soft_shaders_match_the_torch_restatement(oracle, cuda_device, name
     """blur_radius > 0, faces_per_pixel = K, SoftPhong / SoftSilhouette blending and their backward (grad_dists, grad_zbuf,
     clipped barycentrics) against oracle/torch_ref.py (the restatement of rasterize_meshes_cpu.cpp + blending.py; its forward is
     pinned to the C oracle at blur 0, its backward is autograd in fp64): fragment indices bit-exact, zbuf / bary / dists 1e-6,
-    RGBA 1e-5, camera gradients 1e-4 of the tensor's largest entry."""
+    RGBA 1e-5 (5e-9 / gamma for sharper blends), camera gradients 1e-4 of the tensor's largest entry."""
     from oracle import torch_ref as tr
     c = SOFT_CASES[name]
     dev = cuda_device
@@ -253,7 +253,7 @@ def test_mesh_soft_shaders_match_the_torch_restatement(oracle, cuda_device, name
     n_out = 0
     for n in range(M):
         # forward reference in fp32 (fragments), backward reference in fp64 from the CUDA path's own fragment indices
-        fv32 = tr.project_perspective(v, torch.from_numpy(R[n]), torch.from_numpy(T[n]), K00, K11)[f]
+        fv32 = torch.from_numpy(oracle.project_perspective(v.numpy(), R[n], T[n], K00, K11))[f]      # the oracle's IEEE projection
         rp2f, rz, rb, rd = tr.rasterize_meshes_soft(fv32, H, H, K, c["blur"], clip_bary=clip)
         assert (p2f[n].long() == rp2f).all(), f"view {n}: {int((p2f[n].long() != rp2f).sum())} fragment index mismatches"
         ok = rp2f >= 0
@@ -263,7 +263,10 @@ def test_mesh_soft_shaders_match_the_torch_restatement(oracle, cuda_device, name
         ref, _ = tr.render_mesh_view_soft(v.to(D), f, torch.from_numpy(nrm).to(D), obj.to(D).expand(v.shape[0], 3), Rr[n], Tr[n], Cr[n],
                                           light[0].to(D), bg.to(D), K00, K11, H, H, K, c["blur"], c["shader"], sigma=c["sigma"],
                                           gamma=c["gamma"], clip_bary=clip, p2f=rp2f)
-        assert (img[n].detach().cpu().to(D) - ref.detach()).abs().max() <= IMG_ATOL, (n, float((img[n].detach().cpu().to(D) - ref.detach()).abs().max()))
+        # the blend weights are exp((z_inv - z_inv_max) / gamma): an fp32 ulp of z_inv (6e-8) is amplified by 1 / gamma, so against
+        # the fp64 evaluation the fp32 image (PyTorch3D's included) is only good to ~5e-9 / gamma at BlendParams' default 1e-4
+        img_tol = max(IMG_ATOL, 5e-9 / c["gamma"])
+        assert (img[n].detach().cpu().to(D) - ref.detach()).abs().max() <= img_tol, (n, float((img[n].detach().cpu().to(D) - ref.detach()).abs().max()))
         loss = loss + (ref * g[n].to(D)).sum()
     assert n_out > 50                                   # fragments OUTSIDE their face (the blur) are really present
     loss.backward()
