@@ -452,6 +452,8 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
       else MVR_LAUNCH((mesh_backward_kernel_strip<2, false, true>), sgrid, MVR_THREADS, 0, st, p);
     }
     else if (vrgb) MVR_LAUNCH((mesh_backward_kernel_strip<3, true, false>), sgrid, MVR_THREADS, 0, st, p);
+    else if (backward_minb() == 4) MVR_LAUNCH((mesh_backward_kernel_strip<4, false, false>), sgrid, MVR_THREADS, 0, st, p);      // profiling knobs
+    else if (backward_minb() == 2) MVR_LAUNCH((mesh_backward_kernel_strip<2, false, false>), sgrid, MVR_THREADS, 0, st, p);
     else MVR_LAUNCH((mesh_backward_kernel_strip<3, false, false>), sgrid, MVR_THREADS, 0, st, p);
   }
   else if (gv) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<2, true, true>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<2, false, true>), bgrid, MVR_THREADS, 0, st, p); }
