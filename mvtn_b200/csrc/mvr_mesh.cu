@@ -144,7 +144,7 @@ __global__ void geom_get_normals_kernel(const float4* __restrict__ normals4, int
 constexpr int SC_REC_WORDS = 13;      // x0 y0 z0 x1 y1 z1 x2 y2 z2 fid zmin_bits | rect_xy rect_wh (big faces only)
 constexpr int SC_QCAP = 3072;         // candidates per round (256 faces x ~4.6 inside pixels at C2)
 
-template <int MINB>
+template <int MINB, bool SOFT>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const MeshParams p) {
   __shared__ float s_rec[SC_REC_WORDS][MVR_THREADS];  // SoA face records of the current round
   __shared__ int s_q[SC_QCAP];                         // candidates of the round: slot | x << 8 | y << 20
@@ -166,8 +166,8 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
   unsigned long long* keys = p.keys + (size_t)n * p.H * p.W;
   const unsigned long long* prev = p.layer > 0 ? p.prev + (size_t)n * p.H * p.W : nullptr;
   const int qcap = p.wcap;      // SC_QCAP, or a handful under MVR_TEST_TINY_QUEUES
-  const SoftMode sm = soft_mode(p);
-  const bool soft = sm.on();    // blur_radius > 0 / clipped barycentrics: every pixel of the (grown) bbox is a candidate
+  const SoftMode sm = SOFT ? soft_mode(p) : SoftMode{0.f, 0.f, false};
+  constexpr bool soft = SOFT;   // blur_radius > 0 / clipped barycentrics: every pixel of the (grown) bbox is a candidate
 
   for (int i = tid; i < p.W + p.H; i += MVR_THREADS) s_tab[i] = __ldg(p.tab + i);
   if (tid < 4) (&s_cnt2[0][0])[tid] = 0;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
               fc.x0 = s_rec[0][tid]; fc.y0 = s_rec[1][tid]; fc.z0 = s_rec[2][tid];
               fc.x1 = s_rec[3][tid]; fc.y1 = s_rec[4][tid]; fc.z1 = s_rec[5][tid];
               fc.x2 = s_rec[6][tid]; fc.y2 = s_rec[7][tid]; fc.z2 = s_rec[8][tid];
-              resolve_pixel(fc, face_edges(fc), fid, 0u, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
+              resolve_pixel<SOFT>(fc, face_edges(fc), fid, 0u, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
                             prev ? prev + (size_t)yy * p.W + xx : nullptr, sm);
             }
           }
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
         fc.x0 = s_rec[0][slot]; fc.y0 = s_rec[1][slot]; fc.z0 = s_rec[2][slot];
         fc.x1 = s_rec[3][slot]; fc.y1 = s_rec[4][slot]; fc.z1 = s_rec[5][slot];
         fc.x2 = s_rec[6][slot]; fc.y2 = s_rec[7][slot]; fc.z2 = s_rec[8][slot];
-        resolve_pixel_with(fc, face_edges(fc), __float_as_int(s_rec[9][slot]), zmin_bits, persp, s_xf[xx], s_yf[yy],
+        resolve_pixel_with<SOFT>(fc, face_edges(fc), __float_as_int(s_rec[9][slot]), zmin_bits, persp, s_xf[xx], s_yf[yy],
                            keys + (size_t)yy * p.W + xx, prev ? prev + (size_t)yy * p.W + xx : nullptr, cur, sm);
       }
     }
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
           const FaceEdges sfe = face_edges(sf);
           for (int yy = cyl + warp; yy <= cyh; yy += NWARPS)
             for (int xx = cxl + lane; xx <= cxh; xx += 32)
-              resolve_pixel(sf, sfe, bfid, 0u, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
+              resolve_pixel<SOFT>(sf, sfe, bfid, 0u, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
                             prev ? prev + (size_t)yy * p.W + xx : nullptr, sm);
         }
         continue;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
       for (int y = warp; y < bbh; y += NWARPS)
         for (int x = lane; x < bbw; x += 32) {
           const int xx = bxl + x, yy = byl + y;
-          resolve_pixel(fc, fe, bfid, zmin_bits, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
+          resolve_pixel<SOFT>(fc, fe, bfid, zmin_bits, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
                         prev ? prev + (size_t)yy * p.W + xx : nullptr, sm);
         }
     }
@@ -606,8 +606,9 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
     p.layer = k;
     if (chunks_per_view > 0) {
       const dim3 scatter_grid((unsigned)chunks_per_view, (unsigned)M, (unsigned)B);
-      if (scatter_minb() == 3) MVR_LAUNCH(mesh_scatter_kernel<3>, scatter_grid, MVR_THREADS, tab_smem, st, p);
-      else MVR_LAUNCH(mesh_scatter_kernel<4>, scatter_grid, MVR_THREADS, tab_smem, st, p);
+      if (soft_raster) MVR_LAUNCH((mesh_scatter_kernel<3, true>), scatter_grid, MVR_THREADS, tab_smem, st, p);
+      else if (scatter_minb() == 3) MVR_LAUNCH((mesh_scatter_kernel<3, false>), scatter_grid, MVR_THREADS, tab_smem, st, p);
+      else MVR_LAUNCH((mesh_scatter_kernel<4, false>), scatter_grid, MVR_THREADS, tab_smem, st, p);
       rc = check_launch("mesh_scatter_kernel");
       if (rc) return rc;
     }

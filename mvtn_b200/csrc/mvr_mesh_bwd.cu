@@ -281,10 +281,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <int MINB, bool VRGB, bool GV>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(const MeshBwdParams p) {
-  // rows of 32 words whose eight 16-byte chunks are XOR-swizzled by 2 (row & 3): the 8x4-pixel warp blocks below read
-  // 32 distinct banks (chunk pair 2 bx, 2 bx + 1 of row r lands on pair bx ^ r), with no padding
-  __shared__ __align__(16) int s_fid[2][32 * 32];
-  __shared__ __align__(16) float s_g[2][3][32 * 32];
+  // Every WARP stages its own pixels: the four 8x4-pixel blocks it owns in a 32x32 tile (128 pixels x 4 planes = 2 KB per
+  // stage, two stages), one 16-byte cp.async per lane and plane -- so the pipeline needs __syncwarp only.  The kernel has
+  // no CTA barrier at all: a warp whose blocks are background runs ahead through the strip instead of waiting for the
+  // warp that holds the silhouette (22 % of the stall samples of the CTA-staged version were barrier waits).
+  // Layout of a warp's stage: pixel (block j, row r, column c) of plane q at [q][(4 j + r) * 8 + c]: the lanes of a block
+  // read consecutive words.
+  __shared__ __align__(16) int s_fid[NWARPS][2][128];
+  __shared__ __align__(16) float s_g[NWARPS][2][3][128];
   __shared__ unsigned char s_list[NWARPS][128];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // grid: x = tile row, y = view m, z = object b
@@ -295,21 +299,22 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(
   const bool persp = p.flags & MVR_PERSPECTIVE_CORRECT;
   const int* fid_base = p.pix_to_face + (size_t)n * HW;
   const float* g_base = reinterpret_cast<const float*>(p.grad_images) + (size_t)n * 3 * HW;
-  // this thread's 16-byte chunk of every plane of a tile: row cr, pixels cc .. cc + 3
-  const int cr = tid >> 3, cc = (tid & 7) * 4;
-  const int cy = tyb * 32 + cr;
+  // block q = warp + 8 j of the tile (4 across, 8 down): column (warp & 3), rows (warp >> 2) + 2 j
+  const int bx0 = (warp & 3) << 3, by0 = (warp >> 2) << 2;
+  // this lane's 16-byte chunk of every plane: block cj, row cr of the block, half ch (pixels 4 ch .. 4 ch + 3)
+  const int cj = lane >> 3, cr = (lane >> 1) & 3, ch = lane & 1;
+  const int cy = tyb * 32 + by0 + 8 * cj + cr;                 // image row of the chunk
+  const int so = (cj * 4 + cr) * 8 + ch * 4;                    // word offset in the warp's stage
   auto issue = [&](int txb, int buf) {
-    const int x0 = txb * 32 + cc;
-    const int so = cr * 32 + (((cc >> 2) ^ ((cr & 3) << 1)) << 2);      // swizzled word offset of the chunk
-    int* df = &s_fid[buf][so];
+    const int x0 = txb * 32 + bx0 + ch * 4;
     if (cy < p.H && x0 < p.W) {
       const size_t pix = (size_t)cy * p.W + x0;
-      cp_async16(df, fid_base + pix);
-      cp_async16(&s_g[buf][0][so], g_base + pix);
-      cp_async16(&s_g[buf][1][so], g_base + (size_t)HW + pix);
-      cp_async16(&s_g[buf][2][so], g_base + 2 * (size_t)HW + pix);
+      cp_async16(&s_fid[warp][buf][so], fid_base + pix);
+      cp_async16(&s_g[warp][buf][0][so], g_base + pix);
+      cp_async16(&s_g[warp][buf][1][so], g_base + (size_t)HW + pix);
+      cp_async16(&s_g[warp][buf][2][so], g_base + 2 * (size_t)HW + pix);
     } else {
-      *reinterpret_cast<int4*>(df) = make_int4(-1, -1, -1, -1);      // outside the image: background
+      *reinterpret_cast<int4*>(&s_fid[warp][buf][so]) = make_int4(-1, -1, -1, -1);      // outside the image: background
     }
     cp_async_commit();
   };
@@ -321,24 +326,21 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(
   const ShadeCtx sc = load_shade_ctx(p.light, p.light_stride, p.Cc, n);
   float4 ucol = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!VRGB) ucol = make_float4(__ldg(p.obj_rgb), __ldg(p.obj_rgb + 1), __ldg(p.obj_rgb + 2), 0.f);
-  // Pixels -> lanes: shared memory has no coalescing rules, so a warp takes 8x4-pixel BLOCKS (lane = 8 r + c) instead of
-  // 32x1 rows.  A face covers ~2.5 x 2.5 pixels at C2: a block touches ~5 faces where a row touches ~13, and every
-  // gather instruction of the warp (face record, 3 + 6 vertex records) splits into that many fewer L1 wavefronts.
-  const int lc = lane & 7, lr = lane >> 3;
+  // Pixels -> lanes: a warp takes 8x4-pixel BLOCKS (lane = 8 r + c) instead of 32x1 rows.  A face covers ~2.5 x 2.5 pixels
+  // at C2: a block touches ~5 faces where a row touches ~13, and every gather instruction of the warp (face record, 3 + 6
+  // vertex records) splits into that many fewer L1 wavefronts.
 #pragma unroll 1
   for (int t = 0; t < p.tiles_x; ++t) {
     const int buf = t & 1;
     if (t + 1 < p.tiles_x) { issue(t + 1, buf ^ 1); cp_async_wait<1>(); }
     else cp_async_wait<0>();
-    __syncthreads();                                   // tile t has landed for every thread
+    __syncwarp();                                      // tile t has landed for every lane of this warp
     // the warp's covered pixels (of its four blocks) compacted into a list: the chain below then runs in
     // ceil(covered / 32) rounds with every lane busy instead of four rounds with the background lanes idle
     int cnt = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int q = warp + 8 * j;                      // block q of the tile: 4 across, 8 down
-      const int x = ((q & 3) << 3) + lc, y = ((q >> 2) << 2) + lr;
-      const bool cov = s_fid[buf][y * 32 + ((((x >> 2) ^ ((y & 3) << 1)) << 2) | (x & 3))] >= 0;
+      const bool cov = s_fid[warp][buf][j * 32 + lane] >= 0;      // block j, pixel (lane >> 3, lane & 7)
       const unsigned int mk = __ballot_sync(0xffffffffu, cov);
       if (cov) s_list[warp][cnt + __popc(mk & ((1u << lane) - 1u))] = (unsigned char)((j << 5) | lane);
       cnt += __popc(mk);
@@ -348,12 +350,10 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(
     for (int base = 0; base < cnt; base += 32) {
       const bool has = base + lane < cnt;
       if (!GV && !has) continue;
-      const int e = has ? s_list[warp][base + lane] : 0;
-      const int q = warp + 8 * (e >> 5);
-      const int x = ((q & 3) << 3) + (e & 7), y = ((q >> 2) << 2) + ((e >> 3) & 3);
-      const int o = y * 32 + ((((x >> 2) ^ ((y & 3) << 1)) << 2) | (x & 3));
-      const int fid = s_fid[buf][o];
-      float g0 = s_g[buf][0][o], g1 = s_g[buf][1][o], g2 = s_g[buf][2][o];
+      const int o = has ? s_list[warp][base + lane] : 0;          // = 32 j + 8 r + c: the pixel's offset in the stage
+      const int x = bx0 + (o & 7), y = by0 + ((o >> 5) << 3) + ((o >> 3) & 3);
+      const int fid = s_fid[warp][buf][o];
+      float g0 = s_g[warp][buf][0][o], g1 = s_g[warp][buf][1][o], g2 = s_g[warp][buf][2][o];
       const bool live = has && !(g0 == 0.f && g1 == 0.f && g2 == 0.f);
       if (!GV && !live) continue;
       if (p.onorm.on) { g0 *= p.onorm.s0; g1 *= p.onorm.s1; g2 *= p.onorm.s2; }
@@ -372,8 +372,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(
       const float xf = __ldg(p.tab + t * 32 + x);      // covered => inside the image
       mesh_backward_pixel<VRGB, false>(p, n, f0, voff, pvn, persp, sc, ucol, fid, g0, g1, g2, xf, tyb * 32 + y, acc);
     }
-    __syncwarp();                                      // the list is rebuilt for the next tile
-    __syncthreads();                                   // everyone is done with `buf` before tile t + 2 overwrites it
+    __syncwarp();                                      // the list and stage `buf` are free again (tile t + 2 overwrites it)
   }
   float* out = p.partials + ((size_t)n * p.parts_per_view + (size_t)tyb * NWARPS + warp) * 16;
   if (!__any_sync(0xffffffffu, any)) {

@@ -88,16 +88,20 @@ __device__ __forceinline__ SoftMode soft_mode(const MeshParams& p) {
   m.blur = p.blur_radius; m.blur_r = p.blur_r; m.clipb = p.flags & MVR_CLIP_BARYCENTRIC;
   return m;
 }
+// SOFT is a template parameter: the hard rasterizer's instantiation (MVTN's configuration) carries none of the blur code
+template <bool SOFT = false>
 __device__ __forceinline__ void resolve_pixel_with(const Face& fc, const FaceEdges& fe, int fid, unsigned int zmin_bits,
                                                    bool persp, float xf, float yf, unsigned long long* key_ptr,
                                                    const unsigned long long* prev_ptr, const unsigned long long cur,
                                                    const SoftMode sm = SoftMode{0.f, 0.f, false});
+template <bool SOFT = false>
 __device__ __forceinline__ void resolve_pixel(const Face& fc, const FaceEdges& fe, int fid, unsigned int zmin_bits,
                                               bool persp, float xf, float yf, unsigned long long* key_ptr,
                                               const unsigned long long* prev_ptr, const SoftMode sm = SoftMode{0.f, 0.f, false}) {
-  resolve_pixel_with(fc, fe, fid, zmin_bits, persp, xf, yf, key_ptr, prev_ptr, __ldcg(key_ptr), sm);
+  resolve_pixel_with<SOFT>(fc, fe, fid, zmin_bits, persp, xf, yf, key_ptr, prev_ptr, __ldcg(key_ptr), sm);
 }
 // cur: a snapshot of *key_ptr taken earlier (keys only decrease, so a stale snapshot is merely less effective)
+template <bool SOFT>
 __device__ __forceinline__ void resolve_pixel_with(const Face& fc, const FaceEdges& fe, int fid, unsigned int zmin_bits,
                                                    bool persp, float xf, float yf, unsigned long long* key_ptr,
                                                    const unsigned long long* prev_ptr, const unsigned long long cur, const SoftMode sm) {
@@ -107,10 +111,14 @@ __device__ __forceinline__ void resolve_pixel_with(const Face& fc, const FaceEdg
   // pixel's current winner cannot produce a smaller key.  A stale `cur` only makes the test less effective.
   if (zmin_bits > (unsigned int)(cur >> 32)) return;
   // [upstream] CheckPointOutsideBoundingBox (blur 0): the candidate generators only guarantee a superset of the bbox pixels
-  if (xf > fmaxf(fmaxf(fc.x0, fc.x1), fc.x2) + sm.blur_r || xf < fminf(fminf(fc.x0, fc.x1), fc.x2) - sm.blur_r ||
-      yf > fmaxf(fmaxf(fc.y0, fc.y1), fc.y2) + sm.blur_r || yf < fminf(fminf(fc.y0, fc.y1), fc.y2) - sm.blur_r) return;
+  const float grow = SOFT ? sm.blur_r : 0.f;
+  if (SOFT) {
+    if (xf > fmaxf(fmaxf(fc.x0, fc.x1), fc.x2) + grow || xf < fminf(fminf(fc.x0, fc.x1), fc.x2) - grow ||
+        yf > fmaxf(fmaxf(fc.y0, fc.y1), fc.y2) + grow || yf < fminf(fminf(fc.y0, fc.y1), fc.y2) - grow) return;
+  } else if (xf > fmaxf(fmaxf(fc.x0, fc.x1), fc.x2) || xf < fminf(fminf(fc.x0, fc.x1), fc.x2) || yf > fmaxf(fmaxf(fc.y0, fc.y1), fc.y2) ||
+             yf < fminf(fminf(fc.y0, fc.y1), fc.y2)) return;
   float w[3], b[3], pz;
-  if (sm.on()) {      // [upstream] blur_radius > 0: inside, or closer than blur_radius (squared) to an edge
+  if (SOFT) {      // [upstream] blur_radius > 0: inside, or closer than blur_radius (squared) to an edge
     float bc[3], sd;
     bool inside;
     raster_soft(fc, fe, persp, sm.clipb, xf, yf, b, bc, pz, sd, inside);
