@@ -1,5 +1,6 @@
-"""Tiny forward + backward of both paths (mesh: strip and tile backward, K = 1 and 2, a clipped view; points: tiled and generic K)
-for compute-sanitizer:   compute-sanitizer --tool memcheck|racecheck python scripts/sanitize_small.py"""
+"""Tiny forward + backward of both paths (mesh: scatter + shade, strip and tile backward, K = 1 and 2, a clipped view, the
+tile-binned forward with its TMA bulk copies, vertex gradients with the warp-aggregated scatter, the soft shaders; points: tiled
+and generic K) for compute-sanitizer:   compute-sanitizer --tool memcheck|racecheck python scripts/sanitize_small.py"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -19,6 +20,28 @@ for H, K, vs in ((64, 1, views), (50, 1, views), (40, 2, views), (64, 1, near), 
     img.backward(torch.ones_like(img))
     torch.cuda.synchronize()
     print("mesh", H, K, float(img.sum()), float(a.grad.abs().sum()))
+from mvtn_b200 import _lib as L
+for H, vs, flags in ((64, views, L.FORWARD_TILED), (50, near, L.FORWARD_TILED)):      # tile-binned forward (+ clipped faces)
+    a, e, d = (t.to(dev).reshape(-1).requires_grad_() for t in vs)
+    R, T, C, _ = ops._LookAt.apply(a, e, d)
+    img, fr = ops.render_meshes(geom, 3, R, T, C, light, col, bg, H, _extra_flags=flags)
+    img.backward(torch.ones_like(img))
+    torch.cuda.synchronize()
+    print("mesh tiled", H, float(img.detach().sum()), float(a.grad.abs().sum()))
+v = geom.verts.detach().clone().requires_grad_()                      # vertex gradients: warp-aggregated atomic scatter + normals backward
+a, e, d = (t.to(dev).reshape(-1) for t in views)
+R, T, C, _ = ops._LookAt.apply(a, e, d)
+img, fr = ops.render_meshes(geom, 3, R, T, C, light, col, bg, 64, verts=v)
+img.backward(torch.ones_like(img))
+torch.cuda.synchronize()
+print("mesh vertex grads", float(v.grad.abs().sum()))
+for shader, K in (("soft_phong", 4), ("soft_silhouette", 6)):          # blurred rasterizer + soft blend + backward
+    a, e, d = (t.to(dev).reshape(-1).requires_grad_() for t in views)
+    R, T, C, _ = ops._LookAt.apply(a, e, d)
+    img, fr = ops.render_meshes(geom, 3, R, T, C, light, col, bg, 48, faces_per_pixel=K, shader=shader, blur_radius=2e-3, sigma=1e-3, gamma=1e-2)
+    img.backward(torch.ones_like(img))
+    torch.cuda.synchronize()
+    print("mesh", shader, float(img.detach().sum()), float(a.grad.abs().sum()))
 pts = synth.make_clouds(2, 600, 3).to(dev)
 for K in (1, 4, 3):
     a, e, d = (t.to(dev).requires_grad_() for t in views)
