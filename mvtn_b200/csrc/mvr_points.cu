@@ -585,8 +585,9 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
   __shared__ unsigned short s_list[8][1024];      // row << 5 | x of every covered pixel of the warp's tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.z, n = b * p.M + blockIdx.y;
+  const int wpc = blockDim.x >> 5;                   // warps (= tiles) per CTA (8; MVR_PBWD_WPC for profiling)
   const int tgy = blockIdx.x / p.tiles_x, txb = blockIdx.x - tgy * p.tiles_x;
-  const int tyb = tgy * 8 + warp;                    // this warp's tile row
+  const int tyb = tgy * wpc + warp;                  // this warp's tile row
   const int cta = tyb * p.tiles_x + txb;             // tile index within the view (partials slot)
   if (tyb >= p.tiles_y) return;                      // warp-uniform; there is no block barrier in this kernel
   const bool per_point_rgb = p.flags & MVR_RGB_PER_ELEMENT;
@@ -942,7 +943,8 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
   p.grad_points = grad_points; p.grad_rgb = grad_rgb;
   p.onorm = make_out_norm(out_mean_std);
   cudaStream_t st = (cudaStream_t)stream;
-  MVR_LAUNCH(points_backward_kernel, dim3((unsigned)(w.tiles_x * ((p.tiles_y + 7) / 8)), (unsigned)M, (unsigned)B), MVR_THREADS, 0, st, p);
+  static const int wpc = [] { const char* e = getenv("MVR_PBWD_WPC"); const int x = e ? atoi(e) : 8; return (x == 1 || x == 2 || x == 4 || x == 8) ? x : 8; }();      // profiling knob: 8 is fastest at C3, 4 at C5 (-4 %)
+  MVR_LAUNCH(points_backward_kernel, dim3((unsigned)(w.tiles_x * ((p.tiles_y + wpc - 1) / wpc)), (unsigned)M, (unsigned)B), 32 * wpc, 0, st, p);
   rc = check_launch("points_backward_kernel");
   if (rc) return rc;
   const int wpb = 8;
