@@ -150,6 +150,8 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
   __shared__ int s_q[SC_QCAP];                         // candidates of the round: slot | x << 8 | y << 20
   __shared__ int s_big[MVR_THREADS];
   __shared__ int s_cnt2[2][2];                         // per round parity: [0] candidates, [1] big faces
+  __shared__ __align__(16) int4 s_faces[2][MVR_THREADS];      // face records of two rounds: TMA bulk-copy destinations
+  __shared__ __align__(8) unsigned long long s_mbar[2];
   extern __shared__ float s_tab[];                     // pixel centres: xf[W], yf[H]
   const float* s_xf = s_tab;
   const float* s_yf = s_tab + p.W;
@@ -169,14 +171,43 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
   const SoftMode sm = SOFT ? soft_mode(p) : SoftMode{0.f, 0.f, false};
   constexpr bool soft = SOFT;   // blur_radius > 0 / clipped barycentrics: every pixel of the (grown) bbox is a candidate
 
+  // The chunk's face records (int4 vertex ids) are CONTIGUOUS: each round's 256 records (4 KB) are staged by a 1-D TMA bulk
+  // copy (cp.async.bulk + mbarrier), round r + 1 in flight while round r is rasterized -- the first of the two dependent trips of
+  // the setup (face record -> projected vertices) leaves the critical path of every round but the first.
+  const unsigned int mbar_a = smem_addr_pinned(&s_mbar[0]);
+  const unsigned int fstage_a = smem_addr_pinned(&s_faces[0][0]);
+  auto issue_faces = [&](int r) {      // one thread; 16-byte records: source aligned, size a multiple of 16
+    const int start = fbeg + r * MVR_THREADS;
+    const unsigned int bytes = (unsigned int)(min(MVR_THREADS, fend - start) * 16);
+    const unsigned int mb = mbar_a + 8u * (r & 1);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     fstage_a + 16u * MVR_THREADS * (r & 1)),
+                 "l"(p.faces4 + f0 + start), "r"(bytes), "r"(mb)
+                 : "memory");
+  };
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a + 8u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    issue_faces(0);
+  }
   for (int i = tid; i < p.W + p.H; i += MVR_THREADS) s_tab[i] = __ldg(p.tab + i);
   if (tid < 4) (&s_cnt2[0][0])[tid] = 0;
   __syncthreads();
   const unsigned int q_a = smem_addr_pinned(&s_q[0]);
 
   int n_straddle = 0, n_big = 0;
-  for (int rbeg = fbeg, rpar = 0; rbeg < fend; rbeg += MVR_THREADS, rpar ^= 1) {
+  for (int rbeg = fbeg, rpar = 0, round = 0; rbeg < fend; rbeg += MVR_THREADS, rpar ^= 1, ++round) {
     int* s_cnt = s_cnt2[rpar];
+    if (tid == 0 && rbeg + MVR_THREADS < fend) issue_faces(round + 1);      // its stage was released by the barrier that ended round - 1
+    {
+      const unsigned int mb = mbar_a + 8u * (round & 1), parity = (unsigned int)((round >> 1) & 1);
+      asm volatile(
+          "{\n.reg .pred p;\nWAITF_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONEF_%=;\nbra WAITF_%=;\nDONEF_%=:\n}\n" ::"r"(mb),
+          "r"(parity)
+          : "memory");
+    }
     // ---------------- phase A: setup + scanline spans, one thread per face ----------------
     // gather, cull, exact bbox, then ROW BY ROW the interval of pixels that can pass the edge filter (row_span_regs): its
     // pixels go straight to the round's candidate queue.  The filter coefficients never leave the registers.
@@ -184,7 +215,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
     int xl = 0, yl = 0, bw = 0, bh = 0;
     SpanEdges se;
     if (fid < fend) {
-      const Face fc = gather_face(pvn, __ldg(p.faces4 + f0 + fid));
+      const Face fc = gather_face(pvn, s_faces[round & 1][tid]);
       int xh, yh;
       const bool straddles = face_straddles(fc, p.z_clip);
       if (straddles || face_pixel_bbox_conservative(fc, p, xl, xh, yl, yh)) {

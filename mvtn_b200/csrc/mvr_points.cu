@@ -437,6 +437,8 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) points_tile_kernel(const Po
   extern __shared__ unsigned long long s_keys[];              // [KT][1024]
   __shared__ unsigned int s_cand[PT_QCAP];                    // local point << 10 | local pixel
   __shared__ unsigned long long s_key[MVR_THREADS];
+  __shared__ __align__(16) int s_ids[2][MVR_THREADS + 8];     // the tile's point list, a round per stage: TMA bulk-copy destinations
+  __shared__ __align__(8) unsigned long long s_mbar[2];
   __shared__ int s_n;
   const int b = blockIdx.z, n = b * p.M + blockIdx.y, t = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -446,17 +448,50 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) points_tile_kernel(const Po
   const int beg = p.Np > 0 ? p.tile_off[(size_t)n * p.ntiles + t] : 0;
   const int end = p.Np > 0 ? min(p.tile_cur[(size_t)n * p.ntiles + t], p.list_cap) : 0;
   if (beg < end) {                                            // block-uniform
+    // The tile's point list is CONTIGUOUS in global memory: it is staged by 1-D TMA bulk copies (cp.async.bulk + mbarrier),
+    // round r + 1 in flight while round r is rasterized, and round 0 issued before the CTA initialises its key planes -- the
+    // first of the three dependent trips a tile starts with (tile range -> list -> projected point) overlaps the set-up.
+    const unsigned int mbar_a = (unsigned int)__cvta_generic_to_shared(&s_mbar[0]);
+    const unsigned int ids_a = (unsigned int)__cvta_generic_to_shared(&s_ids[0][0]);
+    const int* lst = p.list + (size_t)n * p.list_cap;
+    auto issue_ids = [&](int r) {      // one thread: 16-byte aligned source (the list buffer is), size a multiple of 16
+      const int start = beg + r * MVR_THREADS, cnt = min(MVR_THREADS, end - start);
+      const size_t g = (size_t)n * p.list_cap + start, a0 = g & ~(size_t)3;
+      const unsigned int bytes = (unsigned int)((((int)(g - a0) + cnt + 3) & ~3) * 4);
+      const unsigned int mb = mbar_a + 8u * (r & 1);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       ids_a + 4u * (MVR_THREADS + 8) * (r & 1)),
+                   "l"(p.list + a0), "r"(bytes), "r"(mb)
+                   : "memory");
+    };
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a + 8u) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      issue_ids(0);
+      s_n = 0;
+    }
+    (void)lst;
     for (int i = tid; i < KT * 1024; i += MVR_THREADS) s_keys[i] = MVR_EMPTY_KEY;
-    if (tid == 0) s_n = 0;
     __syncthreads();
     const float* tabx = p.tab;
     const float* taby = p.tab + p.W;
-    for (int base = beg; base < end; base += MVR_THREADS) {
+    int round = 0;
+    for (int base = beg; base < end; base += MVR_THREADS, ++round) {
       // phase 1: thread per point -- pixel centres of the window (clipped to this tile) inside the radius go to the
       // queue (one shared atomic per hit: measured faster here than count + block scan + second pass)
+      if (tid == 0 && base + MVR_THREADS < end) issue_ids(round + 1);      // (its stage was released by the barrier that ended round - 1)
+      {
+        const unsigned int mb = mbar_a + 8u * (round & 1), parity = (unsigned int)((round >> 1) & 1);
+        asm volatile(
+            "{\n.reg .pred p;\nWAITP_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONEP_%=;\nbra WAITP_%=;\nDONEP_%=:\n}\n" ::"r"(mb),
+            "r"(parity)
+            : "memory");
+      }
       const int i = base + tid;
       if (i < end) {
-        const int pi = p.list[(size_t)n * p.list_cap + i];
+        const int pi = s_ids[round & 1][(int)(((size_t)n * p.list_cap + base) & 3) + tid];
         const size_t o = (size_t)n * p.Np + pi;
         const float4 P = p.pp[o];
         const int2 w = p.pw[o];
@@ -785,7 +820,7 @@ static PointsWs points_ws(int B, int Np, int M, int H, int W, int K, double radi
     w.tile_cnt = o; o = al(o + N * w.ntiles * sizeof(int));
     w.tile_off = o; o = al(o + N * w.ntiles * sizeof(int));
     w.tile_cur = o; o = al(o + N * w.ntiles * sizeof(int));
-    w.list = o; o = al(o + N * (size_t)w.list_cap * sizeof(int));
+    w.list = o; o = al(o + N * (size_t)w.list_cap * sizeof(int) + 16);      // + 16: the tile kernel's bulk copies round a list's end up to 16 bytes
   } else {
     w.keys = o; o = al(o + N * H * W * K * 8);
   }
