@@ -91,7 +91,7 @@ def extra_specs(mode):
         dict(name="c1_points", kind="points", batch=1, views=12 if not t else 3, S=224 if not t else 64, points=2048 if not t else 256,
              K=1, compositor="norm", view_kind="circular", baseline="configs[0]", graph=True),
         dict(name="c3_points", kind="points", batch=32 if not t else 2, views=12 if not t else 3, S=224 if not t else 64,
-             points=2048 if not t else 256, K=4, compositor="alpha", view_kind="learned_spherical", baseline="configs[2]"),
+             points=2048 if not t else 256, K=4, compositor="alpha", view_kind="learned_spherical", baseline="configs[2]"),      # eager: GPU-bound at N = 1
         dict(name="c5_mesh", kind="mesh", batch=8 if not t else 1, views=20 if not t else 2, S=400 if not t else 80,
              faces=100000 if not t else 1500, view_kind="spherical", baseline="configs[4]"),
         dict(name="c5_points", kind="points", batch=8 if not t else 1, views=20 if not t else 2, S=400 if not t else 80,

@@ -42,7 +42,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    base = [_nvcc()] + NVCC_FLAGS
+    base = [_nvcc()] + NVCC_FLAGS + os.environ.get("MVR_NVCC_DEFINES", "").split()      # e.g. -DMVR_SHADE_HOIST_FACES for an A/B build
     if os.path.exists("/usr/bin/g++"):
         base += ["-ccbin", "/usr/bin/g++"]
     if verbose:
