@@ -645,6 +645,80 @@ def test_points_golden(cuda_device):
     assert np.allclose(img4.double().sum(dim=(1, 2, 3)).cpu().numpy(), g["image4_sum"], rtol=1e-5)
 
 
+def test_mesh_full_size_c5_properties(oracle, cuda_device):
+    """BASELINE configs[4] at full size (8 meshes x 20 views, ~100k faces, 400^2): properties that need no O(H W F) oracle pass --
+    run-to-run determinism, object independence (an object rendered alone gives the slice of the batch: no cross-object term),
+    invariance of the image under a permutation of the faces (ids map through the permutation), agreement of the two forward
+    rasterizers (scatter + shade vs the tile-binned one), determinism of the backward.  The oracle itself is run at this shape
+    by test_mesh_parity[c5_mesh_100k_400] (two views) and by bench.py's parity gate."""
+    dev = cuda_device
+    B, M, H = 8, 20, 400
+    meshes = synth.make_meshes(B, 100000, 1290)
+    views = synth.spherical_views(B, M)
+    geom = ops.PackedMeshes([v for v, _ in meshes], [f for _, f in meshes], dev)
+    R, T, C, (Rd, Td, Cd) = cams(oracle, views, dev)
+    col = torch.full((3,), 0.99999, device=dev); light = torch.tensor([[0, 1.0, 0]], device=dev)
+    img1, f1 = ops.render_meshes(geom, M, Rd, Td, Cd, light, col, col, H)
+    img2, f2 = ops.render_meshes(geom, M, Rd, Td, Cd, light, col, col, H)
+    assert torch.equal(f1["pix_to_face"], f2["pix_to_face"]) and torch.equal(img1, img2)
+    cov = float((f1["pix_to_face"] >= 0).float().mean())
+    assert 0.2 < cov < 0.8
+    img3, f3 = ops.render_meshes(geom, M, Rd, Td, Cd, light, col, col, H, _extra_flags=L.FORWARD_TILED)
+    assert torch.equal(f3["pix_to_face"], f1["pix_to_face"]) and torch.equal(img3, img1)
+    b = 5
+    s = slice(b * M, (b + 1) * M)
+    gb = ops.PackedMeshes([meshes[b][0]], [meshes[b][1]], dev)
+    imgb, fb = ops.render_meshes(gb, M, Rd[s], Td[s], Cd[s], light, col, col, H)
+    assert torch.equal(fb["pix_to_face"], f1["pix_to_face"][s]) and torch.equal(imgb, img1[s])
+    perm = torch.randperm(meshes[b][1].shape[0], generator=torch.Generator().manual_seed(3))
+    gp = ops.PackedMeshes([meshes[b][0]], [meshes[b][1][perm]], dev)
+    imgp, fpm = ops.render_meshes(gp, M, Rd[s], Td[s], Cd[s], light, col, col, H)
+    ids = fpm["pix_to_face"][..., 0].long()
+    mapped = torch.where(ids >= 0, perm.to(dev)[ids.clamp_min(0)], ids)
+    same = mapped == fb["pix_to_face"][..., 0].long()
+    # exact depth ties between two faces are resolved by the smaller index, which a permutation may change: count them
+    assert float((~same).float().mean()) < 1e-4
+    assert float(((imgp - imgb).abs() > 1e-5).float().mean()) < 1e-4
+    g = torch.randn(B * M, 3, H, H, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    grads = []
+    for _ in range(2):
+        Rg, Tg, Cg = (t.clone().requires_grad_() for t in (Rd, Td, Cd))
+        im, _ = ops.render_meshes(geom, M, Rg, Tg, Cg, light, col, col, H)
+        im.backward(g)
+        grads.append((Rg.grad, Tg.grad, Cg.grad))
+    assert all(torch.equal(a_, b_) for a_, b_ in zip(*grads))
+
+
+def test_points_full_size_c5_properties(oracle, cuda_device):
+    """BASELINE configs[4] at full size (8 clouds x 20 views, 16384 points, 400^2, alpha K = 4): determinism, object independence,
+    invariance under a permutation of the points (indices map through it), sorted layers; two views of one object against the
+    oracle."""
+    dev = cuda_device
+    B, M, H, K = 8, 20, 400, 4
+    pts = synth.make_clouds(B, 16384, 1291)
+    views = synth.spherical_views(B, M)
+    R, T, C, (Rd, Td, Cd) = cams(oracle, views, dev)
+    inv = (1.0 / views[2].reshape(-1)).to(dev)
+    col = torch.full((3,), 0.99999, device=dev); bg = torch.zeros(3, device=dev)
+    a = ops.render_points(pts.to(dev), col, M, Rd, Td, inv, 0.006, bg, H, points_per_pixel=K, compositor="alpha")
+    b = ops.render_points(pts.to(dev), col, M, Rd, Td, inv, 0.006, bg, H, points_per_pixel=K, compositor="alpha")
+    assert torch.equal(a[1]["idx"], b[1]["idx"]) and torch.equal(a[0], b[0])
+    ob_ = 6
+    s = slice(ob_ * M, (ob_ + 1) * M)
+    im, fr = ops.render_points(pts[ob_:ob_ + 1].to(dev), col, M, Rd[s], Td[s], inv[s], 0.006, bg, H, points_per_pixel=K, compositor="alpha")
+    assert torch.equal(fr["idx"], a[1]["idx"][s]) and torch.equal(im, a[0][s])
+    perm = torch.randperm(16384, generator=torch.Generator().manual_seed(4))
+    imp, frp = ops.render_points(pts[ob_:ob_ + 1][:, perm].to(dev), col, M, Rd[s], Td[s], inv[s], 0.006, bg, H, points_per_pixel=K, compositor="alpha")
+    ids = frp["idx"].long()
+    mapped = torch.where(ids >= 0, perm.to(dev)[ids.clamp_min(0)], ids)
+    assert float((mapped != fr["idx"].long()).float().mean()) < 1e-4                  # (exact depth ties may swap)
+    o = oracle.points_forward(pts[ob_:ob_ + 1].numpy(), np.full(3, 0.99999, np.float32), 2, R[s][:2], T[s][:2], inv[s][:2].cpu().numpy(), 0.006,
+                              np.zeros(3, np.float32), H, H, K, oracle.COMPOSITE_ALPHA, fragments=False)
+    assert (fr["idx"][:2].cpu().numpy() == o["idx"]).all() and np.abs(im[:2].cpu().numpy() - o["images"]).max() <= IMG_ATOL
+    idx = a[1]["idx"]
+    assert ((idx[..., 1:] != idx[..., :-1]) | (idx[..., 1:] < 0)).all()
+
+
 def test_points_full_size_c3_properties(oracle, cuda_device):
     """BASELINE configs[2] at full size: 32 clouds x 12 learned_spherical views, alpha compositing, K=4."""
     dev = cuda_device
