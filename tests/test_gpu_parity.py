@@ -212,6 +212,30 @@ def test_mesh_tile_binned_forward_edge_paths(oracle, cuda_device):
     close = dict(mesh_case("close_camera_400"), K=1)
     res = run_mesh(oracle, cuda_device, close, extra_flags=L.FORWARD_TILED)
     assert res["o"]["straddle"] > 0
+    # a single triangle, an object behind the camera (every list empty), a ragged batch with per-vertex colours
+    tri_v = torch.tensor([[-0.5, -0.5, 0.0], [0.5, -0.5, 0.0], [0.0, 0.6, 0.0]]); tri_f = torch.tensor([[0, 1, 2]])
+    run_mesh(oracle, cuda_device, dict(meshes=[(tri_v, tri_f)], M=2, H=33, K=1, views=(torch.tensor([[0.0, 40.0]]), torch.tensor([[10.0, 30.0]]),
+                                       torch.tensor([[2.2, 2.0]])), light_dir=[0.3, 0.5, 0.8]), backward=False, extra_flags=L.FORWARD_TILED)
+    far = tri_v + torch.tensor([0.0, 0.0, 50.0])
+    res = run_mesh(oracle, cuda_device, dict(meshes=[(far, tri_f)], M=1, H=16, K=1, views=(torch.tensor([[0.0]]), torch.tensor([[0.0]]), torch.tensor([[2.0]]))),
+                   backward=False, extra_flags=L.FORWARD_TILED)
+    assert (res["p2f"] == -1).all()
+    run_mesh(oracle, cuda_device, dict(mesh_case("ragged_k3"), K=1), extra_flags=L.FORWARD_TILED)
+    # non-square image (both rasterizers, K = 1)
+    dev = cuda_device
+    H, W, M = 40, 104, 2
+    meshes = synth.make_meshes(1, 700, 79)
+    R, T, C, (Rd, Td, Cd) = cams(oracle, synth.learned_spherical_views(1, M, 6), dev)
+    geom = ops.PackedMeshes([meshes[0][0]], [meshes[0][1]], dev)
+    col = torch.full((3,), 0.99999, device=dev); light = torch.tensor([[0.2, 1.0, 0.3]], device=dev)
+    vp, fp, voff, foff = pack_np(meshes)
+    o = oracle.mesh_forward(vp, fp, voff, foff, oracle.vertex_normals(vp, fp), np.full(3, 0.99999, np.float32), M, R, T, C,
+                            np.array([[0.2, 1.0, 0.3]], np.float32), np.full(3, 0.499995, np.float32), K00, K11, 0.5, H, W, 1,
+                            oracle.PERSPECTIVE_CORRECT)
+    for fl in (0, L.FORWARD_TILED):
+        img, frag = ops.render_meshes(geom, M, Rd, Td, Cd, light, col, col * 0.5, (H, W), fragments=True, _extra_flags=fl)
+        assert (frag["pix_to_face"].cpu().numpy() == o["pix_to_face"]).all() and (frag["zbuf"].cpu().numpy() == o["zbuf"]).all()
+        assert np.abs(img.cpu().numpy() - o["images"]).max() <= IMG_ATOL
 
 
 # ------------------------------------------------------------------------------------------------ soft shaders (8f N3)
