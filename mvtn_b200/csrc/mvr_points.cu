@@ -11,10 +11,10 @@
 //               points_resolve_kernel -- one thread per pixel: the pixel's K keys (one 32-byte sector for K = 4)
 //                 -> idx / zbuf / dists2 of every layer, norm-weighted or alpha compositing, background, planar
 //                 (n,3,H,W) rows, and one bit per pixel in a hit mask (the images are ~90 % background).
-//   backward: points_backward_kernel -- one warp per 32x32-pixel tile: the hit-mask words of the tile are compacted
-//             into a dense list of covered pixels (warp scan + shared memory, no block barrier) and only those touch
-//             idx / grad_images, with all lanes busy: compositor backward -> d dist2 -> d ndc.xy ->
-//             (dR, dT, d(1/dist)) warp-reduced to one partial per (view, tile), summed in fixed order; optional
+//   backward: points_backward_kernel -- one CTA per column of 8 32x32-pixel tiles: the hit-mask words of the tiles are
+//             compacted into one dense list of covered pixels (warp scans + shared memory) and only those touch
+//             idx / grad_images, with all threads busy: compositor backward -> d dist2 -> d ndc.xy ->
+//             (dR, dT, d(1/dist)) reduced to one partial per CTA, summed in fixed order; optional
 //             per-point / colour gradients via atomics.
 #include <cooperative_groups.h>
 #include <cstdlib>
@@ -652,27 +652,76 @@ struct PointsBwdParams {
   OutNorm onorm;
 };
 
-// grid: x = groups of 8 vertically adjacent 32x32-pixel tiles (one per warp), y = view m, z = object b.
-// The images are sparse (~10 % of the pixels are covered), so each warp first COMPACTS the covered pixels of its tile
-// -- lane r owns row r: one hit-mask word, its set bits go to a per-warp list in shared memory at the exclusive
-// prefix of the per-row counts -- and then walks the list with all 32 lanes busy.
+// raw bits of a pixel's three cotangent channels: loaded one iteration ahead, converted only when they are used, so that the
+// loads of item i + 1 are in flight while item i is computed
+struct GradRaw { unsigned int c0, c1, c2; };
+__device__ __forceinline__ GradRaw load_grad_raw(const void* grad, bool bf16, size_t io, size_t plane) {
+  GradRaw r;
+  if (bf16) {
+    const unsigned short* g = reinterpret_cast<const unsigned short*>(grad);
+    r.c0 = __ldg(g + io); r.c1 = __ldg(g + io + plane); r.c2 = __ldg(g + io + 2 * plane);
+  } else {
+    const unsigned int* g = reinterpret_cast<const unsigned int*>(grad);
+    r.c0 = __ldg(g + io); r.c1 = __ldg(g + io + plane); r.c2 = __ldg(g + io + 2 * plane);
+  }
+  return r;
+}
+__device__ __forceinline__ void grad_from_raw(const GradRaw& r, bool bf16, const OutNorm& q, float& g0, float& g1, float& g2) {
+  const int sh = bf16 ? 16 : 0;
+  g0 = __uint_as_float(r.c0 << sh); g1 = __uint_as_float(r.c1 << sh); g2 = __uint_as_float(r.c2 << sh);
+  if (q.on) { g0 *= q.s0; g1 *= q.s1; g2 *= q.s2; }
+}
+
+// (dR, dT, d scale) contributions of one fragment layer whose d out / d alpha is `ga`
+__device__ __forceinline__ void points_backward_layer(const PointsBwdParams& p, const Camera& cam, float s, float inv_r2, int b, int pid,
+                                                      bool per_point_rgb, float X0, float X1, float X2, float dx, float dy, float ga, float gf,
+                                                      float g0, float g1, float g2, float (&acc)[16]) {
+  const float gd2 = -ga * inv_r2;
+  const float gpx = 2.f * gd2 * dx, gpy = 2.f * gd2 * dy;
+  const float Xs0 = X0 * s, Xs1 = X1 * s, Xs2 = X2 * s;
+  acc[0] = fmaf(Xs0, gpx, acc[0]); acc[1] = fmaf(Xs0, gpy, acc[1]);
+  acc[3] = fmaf(Xs1, gpx, acc[3]); acc[4] = fmaf(Xs1, gpy, acc[4]);
+  acc[6] = fmaf(Xs2, gpx, acc[6]); acc[7] = fmaf(Xs2, gpy, acc[7]);
+  acc[9] += gpx; acc[10] += gpy;
+  const float gx0 = cam.r[0] * gpx + cam.r[1] * gpy, gx1 = cam.r[3] * gpx + cam.r[4] * gpy, gx2 = cam.r[6] * gpx + cam.r[7] * gpy;
+  acc[12] += gx0 * X0 + gx1 * X1 + gx2 * X2;
+  if (p.grad_points) {
+    float* o = p.grad_points + 3 * ((size_t)b * p.Np + pid);
+    atomicAdd(o, gx0 * s); atomicAdd(o + 1, gx1 * s); atomicAdd(o + 2, gx2 * s);
+  }
+  if (p.grad_rgb) {
+    float* o = p.grad_rgb + (per_point_rgb ? 3 * ((size_t)b * p.Np + pid) : 0);
+    atomicAdd(o, g0 * gf); atomicAdd(o + 1, g1 * gf); atomicAdd(o + 2, g2 * gf);
+  }
+}
+
+// grid: x = groups of `nw` (= 8) vertically adjacent 32x32-pixel tiles, y = view m, z = object b.
+// The images are sparse (~10 % of the pixels are covered) and unevenly so: a tile holds anything from 0 to 1024 covered
+// pixels.  Each warp COMPACTS the covered pixels of one tile -- lane r owns row r: one hit-mask word, its set bits go to a
+// list in shared memory at the exclusive prefix of the per-row counts -- and the CTA then walks the JOINT list of its tiles
+// with every thread busy, whichever tile the pixels came from (one warp per tile left the warps of the dense tiles running
+// alone at 16 % occupancy).  Per covered pixel the chain idx -> point -> weights is a string of dependent loads, so (i) the
+// pixel's K point ids arrive as ONE vector load and its cotangent as raw bits, both fetched one iteration ahead, and (ii) for
+// KT in {1, 2, 4} the K layers (point, offset, alpha) stay in registers between the compositor-total pass and the gradient
+// pass instead of being re-read and re-projected.  KT = 0 serves any other K with the layers re-read.
+template <int KT, bool VRGB>
 __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const PointsBwdParams p) {
-  __shared__ unsigned short s_list[8][1024];      // row << 5 | x of every covered pixel of the warp's tile
+  __shared__ unsigned short s_list[8 * 1024];     // warp << 10 | row << 5 | x of every covered pixel of the CTA's tiles
+  __shared__ int s_wtot[8];
+  __shared__ float s_part[8][16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.z, n = b * p.M + blockIdx.y;
-  const int wpc = blockDim.x >> 5;                   // warps (= tiles) per CTA (8; MVR_PBWD_WPC for profiling)
+  const int nw = blockDim.x >> 5;                    // warps (= tiles) per CTA (8; MVR_PBWD_WPC for profiling)
   const int tgy = blockIdx.x / p.tiles_x, txb = blockIdx.x - tgy * p.tiles_x;
-  const int tyb = tgy * wpc + warp;                  // this warp's tile row
-  const int cta = tyb * p.tiles_x + txb;             // tile index within the view (partials slot)
-  if (tyb >= p.tiles_y) return;                      // warp-uniform; there is no block barrier in this kernel
-  const bool per_point_rgb = p.flags & MVR_RGB_PER_ELEMENT;
+  const int tyb = tgy * nw + warp;                   // the tile row this warp compacts
   const bool alpha_mode = p.flags & MVR_COMPOSITE_ALPHA;
+  const bool bf16 = p.flags & MVR_IMAGES_BF16;
   const float* pts = p.points + 3 * (size_t)b * p.Np;
-  const float* feat = per_point_rgb ? p.rgb + 3 * (size_t)b * p.Np : p.rgb;
+  const float* feat = VRGB ? p.rgb + 3 * (size_t)b * p.Np : p.rgb;
   const size_t plane = (size_t)p.H * p.W;
   // ---- covered pixels of row (tile row * 32 + lane) ----
   unsigned int word = 0u;
-  {
+  if (tyb < p.tiles_y) {                             // warp-uniform
     const int yi = tyb * 32 + lane;
     if (p.hit_mask) {
       if (yi < p.H) word = __ldg(p.hit_mask + ((size_t)n * p.H + yi) * p.mask_words + txb);
@@ -686,107 +735,172 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
       }
     }
   }
-  int cnt = __popc(word), pre = cnt;                 // inclusive warp scan of the per-row counts
+  const int cnt = __popc(word);
+  int pre = cnt;                                     // inclusive warp scan of the per-row counts
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int v = __shfl_up_sync(0xffffffffu, pre, o);
     if (lane >= o) pre += v;
   }
-  const int total = __shfl_sync(0xffffffffu, pre, 31);
-  float* out = p.partials + ((size_t)n * p.ctas_per_view + cta) * 16;
-  if (total == 0) {                                  // background-only tile
-    if (lane < 16) out[lane] = 0.f;
+  if (lane == 31) s_wtot[warp] = pre;
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int w = 0; w < nw; ++w) { const int c = s_wtot[w]; if (w < warp) base += c; total += c; }
+  float* out = p.partials + ((size_t)n * p.ctas_per_view + blockIdx.x) * 16;      // one partial per CTA
+  if (total == 0) {                                  // background only (block-uniform)
+    if (tid < 16) out[tid] = 0.f;
     return;
   }
   {
-    int at = pre - cnt;
+    int at = base + pre - cnt;
     unsigned int wv = word;
     while (wv) {
       const int x = __ffs(wv) - 1;
       wv &= wv - 1u;
-      s_list[warp][at++] = (unsigned short)((lane << 5) | x);
+      s_list[at++] = (unsigned short)((warp << 10) | (lane << 5) | x);
     }
   }
-  __syncwarp();
+  __syncthreads();
   float acc[16];                                      // PB_VALS used, the rest stay 0
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   const Camera cam = load_camera(p.R, p.T, n);
   const float s = view_scale(p.inv_dist, p.flags, n);
   const float inv_r2 = 1.f / p.r2_weight;
-  for (int it = lane; it < total; it += 32) {
-    const int code = s_list[warp][it];
-    const int yi = tyb * 32 + (code >> 5), xi = txb * 32 + (code & 31);
-    const int* ip = p.idx + (((size_t)n * p.H + yi) * p.W + xi) * p.K;
-    const size_t io = ((size_t)n * 3 * p.H + yi) * p.W + xi;
+  float uf0 = 0.f, uf1 = 0.f, uf2 = 0.f;             // the one colour of all points (!VRGB)
+  if (!VRGB) { uf0 = __ldg(feat); uf1 = __ldg(feat + 1); uf2 = __ldg(feat + 2); }
+  constexpr int KR = KT > 0 ? KT : 1;
+  const int step = blockDim.x;
+  auto pixel_of = [&](int i, int& xi, int& yi) {
+    const int code = s_list[i];
+    yi = (tgy * nw + (code >> 10)) * 32 + ((code >> 5) & 31); xi = txb * 32 + (code & 31);
+  };
+  auto fetch = [&](int i, int (&pid)[KR], GradRaw& gr) {
+    int xi, yi; pixel_of(i, xi, yi);
+    const size_t pix = ((size_t)n * p.H + yi) * p.W + xi;
+    if (KT == 4) { const int4 v = __ldg(reinterpret_cast<const int4*>(p.idx) + pix); pid[0] = v.x; pid[1 % KR] = v.y; pid[2 % KR] = v.z; pid[3 % KR] = v.w; }
+    else if (KT == 2) { const int2 v = __ldg(reinterpret_cast<const int2*>(p.idx) + pix); pid[0] = v.x; pid[1 % KR] = v.y; }
+    else if (KT == 1) pid[0] = __ldg(p.idx + pix);
+    gr = load_grad_raw(p.grad_images, bf16, ((size_t)n * 3 * p.H + yi) * p.W + xi, plane);
+  };
+  int pid_n[KR] = {}; GradRaw gr_n = {0u, 0u, 0u};
+  if (tid < total) fetch(tid, pid_n, gr_n);
+  for (int it = tid; it < total; it += step) {
+    int pid[KR];
+#pragma unroll
+    for (int k = 0; k < KR; ++k) pid[k] = pid_n[k];
+    const GradRaw gr = gr_n;
+    int xi, yi; pixel_of(it, xi, yi);
+    if (it + step < total) fetch(it + step, pid_n, gr_n);
     float g0, g1, g2;
-    load_grad_rgb(p.grad_images, p.flags & MVR_IMAGES_BF16, io, plane, p.onorm, g0, g1, g2);
+    grad_from_raw(gr, bf16, p.onorm, g0, g1, g2);
     if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
     const float xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H), yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
-    // pass 1: compositor totals
-    float t_alpha = 0.f, tf0 = 0.f, tf1 = 0.f, tf2 = 0.f;   // norm: sum a, sum a f ; alpha: out_c
-    {
-      float cum = 1.f;
+    if (KT > 0) {
+      // ---- the K layers in registers: all point loads issued together, one projection per layer ----
+      int nk = 0;
+#pragma unroll
+      for (int k = 0; k < KR; ++k) if (nk == k && pid[k] >= 0) nk = k + 1;      // the filled slots are a prefix
+      float X[KR][3], f[KR][3], a[KR], dx[KR], dy[KR];
+#pragma unroll
+      for (int k = 0; k < KR; ++k) {
+        const size_t q = k < nk ? (size_t)pid[k] : 0;      // (slot 0 is filled: the pixel is covered)
+        X[k][0] = __ldg(pts + 3 * q); X[k][1] = __ldg(pts + 3 * q + 1); X[k][2] = __ldg(pts + 3 * q + 2);
+        if (VRGB) { f[k][0] = __ldg(feat + 3 * q); f[k][1] = __ldg(feat + 3 * q + 1); f[k][2] = __ldg(feat + 3 * q + 2); }
+        else { f[k][0] = uf0; f[k][1] = uf1; f[k][2] = uf2; }
+      }
+      float t_alpha = 0.f, tf0 = 0.f, tf1 = 0.f, tf2 = 0.f;   // norm: sum a, sum a f ; alpha: out_c
+      {
+        float cum = 1.f;
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+          float px, py, pz; world_to_view(cam, X[k][0] * s, X[k][1] * s, X[k][2] * s, px, py, pz);
+          dx[k] = px - xf; dy[k] = py - yf;
+          a[k] = 1.f - (dx[k] * dx[k] + dy[k] * dy[k]) / p.r2_weight;   // exactly the forward's alpha: it is clamped at 1e-4 below
+          if (k < nk) {
+            const float wgt = alpha_mode ? cum * a[k] : a[k];
+            tf0 = fmaf(wgt, f[k][0], tf0); tf1 = fmaf(wgt, f[k][1], tf1); tf2 = fmaf(wgt, f[k][2], tf2);
+            t_alpha += a[k]; cum *= (1.f - a[k]);
+          }
+        }
+      }
+      const float t = fmaxf(t_alpha, 1e-4f);
+      float cum = 1.f, pre0 = 0.f, pre1 = 0.f, pre2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < KR; ++k) {
+        if (k < nk) {
+          float ga, gf;   // d/d alpha_k ; d/d f_k (per unit grad_out, same for all channels)
+          if (alpha_mode) {
+            // out_c = sum_j f_jc cum_j a_j ;  d/da_k = f_kc cum_k - (sum_{j>k} f_jc cum_j a_j) / (1 - a_k + 1e-9)
+            const float w = cum * a[k];
+            pre0 = fmaf(w, f[k][0], pre0); pre1 = fmaf(w, f[k][1], pre1); pre2 = fmaf(w, f[k][2], pre2);
+            const float inv1m = 1.f / (1.f - a[k] + 1e-9f);
+            ga = g0 * (f[k][0] * cum - (tf0 - pre0) * inv1m) + g1 * (f[k][1] * cum - (tf1 - pre1) * inv1m) + g2 * (f[k][2] * cum - (tf2 - pre2) * inv1m);
+            gf = w;
+            cum *= (1.f - a[k]);
+          } else {
+            const float it2 = 1.f / (t * t);
+            ga = (g0 * (t * f[k][0] - tf0) + g1 * (t * f[k][1] - tf1) + g2 * (t * f[k][2] - tf2)) * it2;
+            gf = a[k] / t;
+          }
+          points_backward_layer(p, cam, s, inv_r2, b, pid[k], VRGB, X[k][0], X[k][1], X[k][2], dx[k], dy[k], ga, gf, g0, g1, g2, acc);
+        }
+      }
+    } else {
+      // ---- any K: the layers are re-read (L1) and re-projected by the second pass ----
+      const int* ip = p.idx + (((size_t)n * p.H + yi) * p.W + xi) * p.K;
+      float t_alpha = 0.f, tf0 = 0.f, tf1 = 0.f, tf2 = 0.f;
+      {
+        float cum = 1.f;
+        for (int k = 0; k < p.K; ++k) {
+          const int q = __ldg(ip + k);
+          if (q < 0) break;
+          float px, py, pz; project_point(pts, q, s, cam, px, py, pz);
+          const float ddx = px - xf, ddy = py - yf;
+          const float al = 1.f - (ddx * ddx + ddy * ddy) / p.r2_weight;
+          const float* ff = feat + (VRGB ? 3 * (size_t)q : 0);
+          const float wgt = alpha_mode ? cum * al : al;
+          tf0 = fmaf(wgt, __ldg(ff), tf0); tf1 = fmaf(wgt, __ldg(ff + 1), tf1); tf2 = fmaf(wgt, __ldg(ff + 2), tf2);
+          t_alpha += al; cum *= (1.f - al);
+        }
+      }
+      const float t = fmaxf(t_alpha, 1e-4f);
+      float cum = 1.f, pre0 = 0.f, pre1 = 0.f, pre2 = 0.f;
       for (int k = 0; k < p.K; ++k) {
-        const int pid = __ldg(ip + k);
-        if (pid < 0) break;
-        float px, py, pz; project_point(pts, pid, s, cam, px, py, pz);
-        const float dx = px - xf, dy = py - yf;
-        const float a = 1.f - (dx * dx + dy * dy) / p.r2_weight;   // exactly the forward's alpha: it is clamped at 1e-4 below
-        const float* f = feat + (per_point_rgb ? 3 * (size_t)pid : 0);
-        const float wgt = alpha_mode ? cum * a : a;
-        tf0 = fmaf(wgt, __ldg(f), tf0); tf1 = fmaf(wgt, __ldg(f + 1), tf1); tf2 = fmaf(wgt, __ldg(f + 2), tf2);
-        t_alpha += a; cum *= (1.f - a);
-      }
-    }
-    const float t = fmaxf(t_alpha, 1e-4f);
-    // pass 2: per-layer gradients
-    float cum = 1.f, pre0 = 0.f, pre1 = 0.f, pre2 = 0.f;
-    for (int k = 0; k < p.K; ++k) {
-      const int pid = __ldg(ip + k);
-      if (pid < 0) break;
-      const float X0 = __ldg(pts + 3 * (size_t)pid), X1 = __ldg(pts + 3 * (size_t)pid + 1), X2 = __ldg(pts + 3 * (size_t)pid + 2);
-      float px, py, pz; world_to_view(cam, X0 * s, X1 * s, X2 * s, px, py, pz);
-      const float dx = px - xf, dy = py - yf;
-      const float a = 1.f - (dx * dx + dy * dy) / p.r2_weight;   // exactly the forward's alpha: it is clamped at 1e-4 below
-      const float* f = feat + (per_point_rgb ? 3 * (size_t)pid : 0);
-      const float f0 = __ldg(f), f1 = __ldg(f + 1), f2 = __ldg(f + 2);
-      float ga, gf;   // d/d alpha_k ; d/d f_k (per unit grad_out, same for all channels)
-      if (alpha_mode) {
-        // out_c = sum_j f_jc cum_j a_j ;  d/da_k = f_kc cum_k - (sum_{j>k} f_jc cum_j a_j) / (1 - a_k + 1e-9)
-        const float w = cum * a;
-        pre0 = fmaf(w, f0, pre0); pre1 = fmaf(w, f1, pre1); pre2 = fmaf(w, f2, pre2);
-        const float inv1m = 1.f / (1.f - a + 1e-9f);
-        ga = g0 * (f0 * cum - (tf0 - pre0) * inv1m) + g1 * (f1 * cum - (tf1 - pre1) * inv1m) + g2 * (f2 * cum - (tf2 - pre2) * inv1m);
-        gf = w;
-        cum *= (1.f - a);
-      } else {
-        const float it2 = 1.f / (t * t);
-        ga = (g0 * (t * f0 - tf0) + g1 * (t * f1 - tf1) + g2 * (t * f2 - tf2)) * it2;
-        gf = a / t;
-      }
-      const float gd2 = -ga * inv_r2;
-      const float gpx = 2.f * gd2 * dx, gpy = 2.f * gd2 * dy;
-      const float Xs0 = X0 * s, Xs1 = X1 * s, Xs2 = X2 * s;
-      acc[0] = fmaf(Xs0, gpx, acc[0]); acc[1] = fmaf(Xs0, gpy, acc[1]);
-      acc[3] = fmaf(Xs1, gpx, acc[3]); acc[4] = fmaf(Xs1, gpy, acc[4]);
-      acc[6] = fmaf(Xs2, gpx, acc[6]); acc[7] = fmaf(Xs2, gpy, acc[7]);
-      acc[9] += gpx; acc[10] += gpy;
-      const float gx0 = cam.r[0] * gpx + cam.r[1] * gpy, gx1 = cam.r[3] * gpx + cam.r[4] * gpy, gx2 = cam.r[6] * gpx + cam.r[7] * gpy;
-      acc[12] += gx0 * X0 + gx1 * X1 + gx2 * X2;
-      if (p.grad_points) {
-        float* o = p.grad_points + 3 * ((size_t)b * p.Np + pid);
-        atomicAdd(o, gx0 * s); atomicAdd(o + 1, gx1 * s); atomicAdd(o + 2, gx2 * s);
-      }
-      if (p.grad_rgb) {
-        float* o = p.grad_rgb + (per_point_rgb ? 3 * ((size_t)b * p.Np + pid) : 0);
-        atomicAdd(o, g0 * gf); atomicAdd(o + 1, g1 * gf); atomicAdd(o + 2, g2 * gf);
+        const int q = __ldg(ip + k);
+        if (q < 0) break;
+        const float X0 = __ldg(pts + 3 * (size_t)q), X1 = __ldg(pts + 3 * (size_t)q + 1), X2 = __ldg(pts + 3 * (size_t)q + 2);
+        float px, py, pz; world_to_view(cam, X0 * s, X1 * s, X2 * s, px, py, pz);
+        const float ddx = px - xf, ddy = py - yf;
+        const float al = 1.f - (ddx * ddx + ddy * ddy) / p.r2_weight;
+        const float* ff = feat + (VRGB ? 3 * (size_t)q : 0);
+        const float f0 = __ldg(ff), f1 = __ldg(ff + 1), f2 = __ldg(ff + 2);
+        float ga, gf;
+        if (alpha_mode) {
+          const float w = cum * al;
+          pre0 = fmaf(w, f0, pre0); pre1 = fmaf(w, f1, pre1); pre2 = fmaf(w, f2, pre2);
+          const float inv1m = 1.f / (1.f - al + 1e-9f);
+          ga = g0 * (f0 * cum - (tf0 - pre0) * inv1m) + g1 * (f1 * cum - (tf1 - pre1) * inv1m) + g2 * (f2 * cum - (tf2 - pre2) * inv1m);
+          gf = w;
+          cum *= (1.f - al);
+        } else {
+          const float it2 = 1.f / (t * t);
+          ga = (g0 * (t * f0 - tf0) + g1 * (t * f1 - tf1) + g2 * (t * f2 - tf2)) * it2;
+          gf = al / t;
+        }
+        points_backward_layer(p, cam, s, inv_r2, b, q, VRGB, X0, X1, X2, ddx, ddy, ga, gf, g0, g1, g2, acc);
       }
     }
   }
-  // one partial per tile (= per warp), summed in fixed order by the reduce kernel
+  // one partial per CTA: warp totals, then the warps in fixed order; the reduce kernel sums the CTAs in fixed order
   const float mine = warp_sum16_transposed(acc);      // lanes 2i, 2i+1: total of value i
-  if (!(lane & 1)) out[lane >> 1] = mine;
+  if (!(lane & 1)) s_part[warp][lane >> 1] = mine;
+  __syncthreads();
+  if (tid < 16) {
+    float v = 0.f;
+    for (int w = 0; w < nw; ++w) v += s_part[w][tid];
+    out[tid] = v;
+  }
 }
 
 __global__ void points_backward_reduce_kernel(const float* __restrict__ partials, int N, int n_parts,
@@ -1034,11 +1148,25 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
   p.grad_points = grad_points; p.grad_rgb = grad_rgb;
   p.onorm = make_out_norm(out_mean_std);
   cudaStream_t st = (cudaStream_t)stream;
-  static const int wpc = [] { const char* e = getenv("MVR_PBWD_WPC"); const int x = e ? atoi(e) : 8; return (x == 1 || x == 2 || x == 4 || x == 8) ? x : 8; }();      // profiling knob: 8 is fastest at C3, 4 at C5 (-4 %)
-  MVR_LAUNCH(points_backward_kernel, dim3((unsigned)(w.tiles_x * ((p.tiles_y + wpc - 1) / wpc)), (unsigned)M, (unsigned)B), 32 * wpc, 0, st, p);
+  static const int wpc = [] { const char* e = getenv("MVR_PBWD_WPC"); const int x = e ? atoi(e) : 8; return (x == 1 || x == 2 || x == 4 || x == 8) ? x : 8; }();      // profiling knob
+  const int groups_y = (p.tiles_y + wpc - 1) / wpc;
+  p.ctas_per_view = w.tiles_x * groups_y;             // one partial per CTA (<= one per tile: the workspace is sized for that)
+  const dim3 grid((unsigned)p.ctas_per_view, (unsigned)M, (unsigned)B);
+  const bool vrgb = flags & MVR_RGB_PER_ELEMENT;
+  // the register-resident variants read a pixel's K ids as one vector: they need the fragment tensor aligned to K ints
+  const int kt = ((K == 1 || K == 2 || K == 4) && ((uintptr_t)idx & (size_t)(4 * K - 1)) == 0) ? K : 0;
+#define MVR_PBWD(KT_) do { if (vrgb) MVR_LAUNCH((points_backward_kernel<KT_, true>), grid, 32 * wpc, 0, st, p); \
+                           else MVR_LAUNCH((points_backward_kernel<KT_, false>), grid, 32 * wpc, 0, st, p); } while (0)
+  switch (kt) {
+    case 1: MVR_PBWD(1); break;
+    case 2: MVR_PBWD(2); break;
+    case 4: MVR_PBWD(4); break;
+    default: MVR_PBWD(0); break;
+  }
+#undef MVR_PBWD
   rc = check_launch("points_backward_kernel");
   if (rc) return rc;
   const int wpb = 8;
-  MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, w.ctas_per_view, gR, gT, g_inv_dist, inv_dist, flags);
+  MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, p.ctas_per_view, gR, gT, g_inv_dist, inv_dist, flags);
   return check_launch("points_backward_reduce_kernel");
 }
