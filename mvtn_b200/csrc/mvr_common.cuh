@@ -159,6 +159,26 @@ __device__ __forceinline__ void load_grad_rgb(const void* grad, bool bf16, size_
   if (q.on) { g0 *= q.s0; g1 *= q.s1; g2 *= q.s2; }
 }
 
+// raw bits of a pixel's three cotangent channels: loaded one iteration ahead, converted only when they are used, so that the
+// loads of item i + 1 are in flight while item i is computed
+struct GradRaw { unsigned int c0, c1, c2; };
+__device__ __forceinline__ GradRaw load_grad_raw(const void* grad, bool bf16, size_t io, size_t plane) {
+  GradRaw r;
+  if (bf16) {
+    const unsigned short* g = reinterpret_cast<const unsigned short*>(grad);
+    r.c0 = __ldg(g + io); r.c1 = __ldg(g + io + plane); r.c2 = __ldg(g + io + 2 * plane);
+  } else {
+    const unsigned int* g = reinterpret_cast<const unsigned int*>(grad);
+    r.c0 = __ldg(g + io); r.c1 = __ldg(g + io + plane); r.c2 = __ldg(g + io + 2 * plane);
+  }
+  return r;
+}
+__device__ __forceinline__ void grad_from_raw(const GradRaw& r, bool bf16, const OutNorm& q, float& g0, float& g1, float& g2) {
+  const int sh = bf16 ? 16 : 0;
+  g0 = __uint_as_float(r.c0 << sh); g1 = __uint_as_float(r.c1 << sh); g2 = __uint_as_float(r.c2 << sh);
+  if (q.on) { g0 *= q.s0; g1 *= q.s1; g2 *= q.s2; }
+}
+
 __device__ __forceinline__ unsigned long long make_key(float z, int idx) {
   // z >= 0 here, so the IEEE bit pattern is monotone; +0.0f canonicalises -0.0f.
   return ((unsigned long long)__float_as_uint(z + 0.0f) << 32) | (unsigned int)idx;

@@ -652,26 +652,6 @@ struct PointsBwdParams {
   OutNorm onorm;
 };
 
-// raw bits of a pixel's three cotangent channels: loaded one iteration ahead, converted only when they are used, so that the
-// loads of item i + 1 are in flight while item i is computed
-struct GradRaw { unsigned int c0, c1, c2; };
-__device__ __forceinline__ GradRaw load_grad_raw(const void* grad, bool bf16, size_t io, size_t plane) {
-  GradRaw r;
-  if (bf16) {
-    const unsigned short* g = reinterpret_cast<const unsigned short*>(grad);
-    r.c0 = __ldg(g + io); r.c1 = __ldg(g + io + plane); r.c2 = __ldg(g + io + 2 * plane);
-  } else {
-    const unsigned int* g = reinterpret_cast<const unsigned int*>(grad);
-    r.c0 = __ldg(g + io); r.c1 = __ldg(g + io + plane); r.c2 = __ldg(g + io + 2 * plane);
-  }
-  return r;
-}
-__device__ __forceinline__ void grad_from_raw(const GradRaw& r, bool bf16, const OutNorm& q, float& g0, float& g1, float& g2) {
-  const int sh = bf16 ? 16 : 0;
-  g0 = __uint_as_float(r.c0 << sh); g1 = __uint_as_float(r.c1 << sh); g2 = __uint_as_float(r.c2 << sh);
-  if (q.on) { g0 *= q.s0; g1 *= q.s1; g2 *= q.s2; }
-}
-
 // (dR, dT, d scale) contributions of one fragment layer whose d out / d alpha is `ga`
 __device__ __forceinline__ void points_backward_layer(const PointsBwdParams& p, const Camera& cam, float s, float inv_r2, int b, int pid,
                                                       bool per_point_rgb, float X0, float X1, float X2, float dx, float dy, float ga, float gf,
