@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MVR_ABI_VERSION 6
+#define MVR_ABI_VERSION 7
 
 /* flags */
 #define MVR_PERSPECTIVE_CORRECT 1  /* [upstream] RasterizationSettings.perspective_correct (FoV persp.: True) */
@@ -127,6 +127,16 @@ int mvr_mesh_prepare(const float* verts, const void* faces, const int* vert_off,
                      int B, int64_t total_verts, int64_t total_faces, int max_faces,
                      const float* vert_rgb, int flags, void* geometry, size_t geometry_bytes,
                      void* stream);
+/* The same for objects [obj_begin, obj_end) only, whose vertices are the packed rows [vert_begin, vert_end) (all other
+ * arguments describe the WHOLE batch, as above).  Every kernel of the mesh path indexes the packed arrays absolutely, so a
+ * batch can be prepared -- and then rendered: mvr_mesh_forward / mvr_mesh_backward with vert_off + obj_begin,
+ * face_off + obj_begin, B = obj_end - obj_begin and the per-view arrays offset by obj_begin * M views -- piece by piece
+ * while the rest of it is still on its way to the device (MVRenderer(h2d_chunks=...): the H2D copy of chunk c + 1 overlaps
+ * the kernels of chunk c inside ONE step; SURVEY 8f N1, renderer.py:67-77). */
+int mvr_mesh_prepare_range(const float* verts, const void* faces, const int* vert_off, const int* face_off,
+                           int B, int64_t total_verts, int64_t total_faces, int max_faces,
+                           const float* vert_rgb, int flags, void* geometry, size_t geometry_bytes,
+                           int obj_begin, int obj_end, int64_t vert_begin, int64_t vert_end, void* stream);
 /* copy of the per-vertex unit normals (Vtot,3) out of a prepared geometry (tests / callers) */
 int mvr_mesh_get_normals(const void* geometry, int64_t total_verts, int64_t total_faces,
                          float* normals, void* stream);

@@ -99,6 +99,12 @@ class MVRenderer(nn.Module):
             FoV perspective cameras).
         copy_stream: H2D of a collated host batch on a side stream (overlaps with the previous step's kernels when the
             loop does not synchronise every step; see ops.PackedMeshes.from_host_packed)
+        h2d_chunks: how many groups of objects a collated host batch (collate_meshes) travels in (default 1).  With k > 1 group c
+            is prepared and rendered as soon as its own copy has landed, while group c + 1 is still on the bus (one forward and
+            one backward launch per group, same images / fragments / gradients bit for bit).  Measured on B200 it does NOT pay at
+            MVTN's sizes: the step's first 0.3 ms are bound by the host reaching the rasterizer launch, not by the 0.18 ms copy,
+            and every group adds launches (1.09 -> 1.27 ms per end-to-end step at 32 x 12 views with k = 2;
+            profiles/r3y_h2d_chunks.txt) -- kept for batches whose copy does dominate (large meshes, slow links).
         cuda_graph: None (default) = automatic -- point steps of at most GRAPH_AUTO_MAX_VIEWS views (BASELINE configs[0]: one
             cloud x 12 views, a step that is pure launch latency) are replayed from CUDA graphs, larger ones run eagerly;
             True / False force it.  Point path only -- the device part of a step (look_at, binning, tile rasterizer + compositor, and their
@@ -125,8 +131,9 @@ class MVRenderer(nn.Module):
                  faces_per_pixel=1, points_radius=0.006, points_per_pixel=1, light_direction="random",
                  cull_backfaces=False, *, compositor="norm", perspective_correct=True, cache_geometry=False,
                  normalize=None, out_dtype=None, copy_stream=False, cuda_graph=None, shader="hard_phong", blur_radius=0.0,
-                 blend_sigma=1e-4, blend_gamma=1e-4, keep_alpha=False):
+                 blend_sigma=1e-4, blend_gamma=1e-4, keep_alpha=False, h2d_chunks=1):
         super().__init__()
+        self.h2d_chunks = h2d_chunks
         self.shader, self.blur_radius, self.blend_sigma, self.blend_gamma, self.keep_alpha = shader, blur_radius, blend_sigma, blend_gamma, keep_alpha
         self.copy_stream = copy_stream
         self.cuda_graph = cuda_graph      # None = auto: replay small (launch-bound) point steps from CUDA graphs
@@ -219,7 +226,7 @@ class MVRenderer(nn.Module):
         soft = self.shader != "hard_phong"
 
         def render(R, T, C, dist_, C_light):
-            geom.finish()
+            geom.finish(lazy_chunks=not soft)      # (the groups of a chunked batch are finished by the render launches)
             light = C_light if fixed_light is None else fixed_light
             if soft:
                 return ops.render_meshes(geom, self.nb_views, R, T, C, light, obj, bg, self.image_size,
@@ -238,7 +245,7 @@ class MVRenderer(nn.Module):
                 # fast path: cameras + rasterizer as ONE autograd node (ops.render_meshes_from_angles); the validity flag
                 # is still awaited through an event recorded between the camera kernel and the rasterizer
                 az, el, di = self._views(azim, elev, dist, device)
-                geom.finish()
+                geom.finish(lazy_chunks=True)
                 images, (R, T, C, _bad), frag = ops.render_meshes_from_angles(
                     geom, self.nb_views, az, el, di, fixed_light, obj, bg, self.image_size,
                     faces_per_pixel=self.faces_per_pixel, cull_backfaces=self.cull_backfaces,
@@ -377,7 +384,8 @@ class MVRenderer(nn.Module):
             if color_t.numel() != 3:
                 color_t = color_t.reshape(len(meshes), -1, 3)
                 vert_rgb = torch.cat([color_t[b, :n] for b, n in enumerate(meshes.num_verts)], 0)
-            return ops.PackedMeshes.from_host_packed(meshes, device, vert_rgb=vert_rgb, copy_stream=self.copy_stream)
+            chunks = self.h2d_chunks if self.shader == "hard_phong" else 1
+            return ops.PackedMeshes.from_host_packed(meshes, device, vert_rgb=vert_rgb, copy_stream=self.copy_stream, chunks=chunks)
         if meshes is None:
             raise ValueError("mesh rendering (pc_rendering=False) needs `meshes`")
         if self.cache_geometry and self._geom_cache[0] is meshes:

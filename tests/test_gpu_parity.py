@@ -901,6 +901,35 @@ def test_mvrenderer_accepts_collated_host_batch(cuda_device):
     assert a2.grad is not None and torch.isfinite(a2.grad).all()
 
 
+@pytest.mark.parametrize("chunks,K", [(2, 1), (3, 1), (4, 2), (64, 1)])
+def test_mvrenderer_h2d_chunks_match_single_copy(cuda_device, chunks, K):
+    """h2d_chunks: a collated batch copied / prepared / rendered in groups of objects (mvr_mesh_prepare_range + offset
+    vert_off / per-view pointers, one forward and one backward launch per group) gives the images, fragments and gradients
+    of the single-copy path bit for bit -- uneven groups, more groups than objects, K > 1, pinned or pageable source."""
+    from mvtn_b200 import collate_meshes
+    dev = cuda_device
+    meshes = [synth.make_mesh(nf, 70 + i) for i, nf in enumerate((700, 90, 2500, 300, 1200, 40))]
+    ml = [Meshes([v], [f]) for v, f in meshes]
+    B, M = len(ml), 3
+    views = [t.to(dev) for t in synth.learned_spherical_views(B, M, 23)]
+    cot = torch.randn(B, M, 3, 56, 56, device=dev)
+
+    def run(nch, pin):
+        r = MVRenderer(M, image_size=56, pc_rendering=False, light_direction="relative", faces_per_pixel=K, h2d_chunks=nch).to(dev).eval()
+        a, e, d = (t.detach().clone().requires_grad_() for t in views)
+        img, cams = r(collate_meshes(ml, pin_memory=pin), None, a, e, d)
+        p2f = r.last_fragments["pix_to_face"].clone()
+        img.backward(cot)
+        return img.detach().clone(), p2f, a.grad.clone(), e.grad.clone(), d.grad.clone()
+
+    ref = run(1, True)
+    for pin in (True, False):
+        out = run(chunks, pin)
+        for x, y in zip(ref, out):
+            assert torch.equal(x, y)
+    assert int((ref[1] >= 0).sum()) > 0
+
+
 def test_cuda_graph_replay_matches_eager(cuda_device):
     """mvtn_b200.graphs: the captured forward / backward graphs reproduce the eager path bit for bit, and pick up
     in-place updates of the captured buffers (new points, moved vertices, new views)."""
