@@ -653,6 +653,7 @@ struct PointsBwdParams {
 };
 
 // (dR, dT, d scale) contributions of one fragment layer whose d out / d alpha is `ga`
+template <bool GU>      // GU: the gradient of the single point colour is wanted (it rides in acc[13..15])
 __device__ __forceinline__ void points_backward_layer(const PointsBwdParams& p, const Camera& cam, float s, float inv_r2, int b, int pid,
                                                       bool per_point_rgb, float X0, float X1, float X2, float dx, float dy, float ga, float gf,
                                                       float g0, float g1, float g2, float (&acc)[16]) {
@@ -670,8 +671,15 @@ __device__ __forceinline__ void points_backward_layer(const PointsBwdParams& p, 
     atomicAdd(o, gx0 * s); atomicAdd(o + 1, gx1 * s); atomicAdd(o + 2, gx2 * s);
   }
   if (p.grad_rgb) {
-    float* o = p.grad_rgb + (per_point_rgb ? 3 * ((size_t)b * p.Np + pid) : 0);
-    atomicAdd(o, g0 * gf); atomicAdd(o + 1, g1 * gf); atomicAdd(o + 2, g2 * gf);
+    if (per_point_rgb) {
+      float* o = p.grad_rgb + 3 * ((size_t)b * p.Np + pid);
+      atomicAdd(o, g0 * gf); atomicAdd(o + 1, g1 * gf); atomicAdd(o + 2, g2 * gf);
+    } else if (GU) {
+      // ONE colour for every point: its gradient is a sum over every fragment of the batch.  It rides in the three spare slots
+      // of the per-thread partials (-> one partial per CTA -> one atomicAdd per view in the reduce kernel) instead of three
+      // atomics per fragment on the same three words (serialised in L2, and an fp32 sum of ~10^5 terms in arrival order)
+      acc[13] = fmaf(g0, gf, acc[13]); acc[14] = fmaf(g1, gf, acc[14]); acc[15] = fmaf(g2, gf, acc[15]);
+    }
   }
 }
 
@@ -684,7 +692,7 @@ __device__ __forceinline__ void points_backward_layer(const PointsBwdParams& p, 
 // pixel's K point ids arrive as ONE vector load and its cotangent as raw bits, both fetched one iteration ahead, and (ii) for
 // KT in {1, 2, 4} the K layers (point, offset, alpha) stay in registers between the compositor-total pass and the gradient
 // pass instead of being re-read and re-projected.  KT = 0 serves any other K with the layers re-read.
-template <int KT, bool VRGB>
+template <int KT, bool VRGB, bool GU>
 __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const PointsBwdParams p) {
   __shared__ unsigned short s_list[8 * 1024];     // warp << 10 | row << 5 | x of every covered pixel of the CTA's tiles
   __shared__ int s_wtot[8];
@@ -741,7 +749,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
     }
   }
   __syncthreads();
-  float acc[16];                                      // PB_VALS used, the rest stay 0
+  float acc[16];                                      // PB_VALS camera values + [13..15]: gradient of the single point colour
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   const Camera cam = load_camera(p.R, p.T, n);
@@ -823,7 +831,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
             ga = (g0 * (t * f[k][0] - tf0) + g1 * (t * f[k][1] - tf1) + g2 * (t * f[k][2] - tf2)) * it2;
             gf = a[k] / t;
           }
-          points_backward_layer(p, cam, s, inv_r2, b, pid[k], VRGB, X[k][0], X[k][1], X[k][2], dx[k], dy[k], ga, gf, g0, g1, g2, acc);
+          points_backward_layer<GU>(p, cam, s, inv_r2, b, pid[k], VRGB, X[k][0], X[k][1], X[k][2], dx[k], dy[k], ga, gf, g0, g1, g2, acc);
         }
       }
     } else {
@@ -868,7 +876,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
           ga = (g0 * (t * f0 - tf0) + g1 * (t * f1 - tf1) + g2 * (t * f2 - tf2)) * it2;
           gf = al / t;
         }
-        points_backward_layer(p, cam, s, inv_r2, b, q, VRGB, X0, X1, X2, ddx, ddy, ga, gf, g0, g1, g2, acc);
+        points_backward_layer<GU>(p, cam, s, inv_r2, b, q, VRGB, X0, X1, X2, ddx, ddy, ga, gf, g0, g1, g2, acc);
       }
     }
   }
@@ -883,9 +891,10 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
   }
 }
 
+// grad_rgb_uniform: the (3,) gradient of the single point colour, or NULL (per-point colours / not wanted)
 __global__ void points_backward_reduce_kernel(const float* __restrict__ partials, int N, int n_parts,
                                               float* __restrict__ gR, float* __restrict__ gT, float* __restrict__ gs,
-                                              const float* __restrict__ scale, int flags) {
+                                              const float* __restrict__ scale, int flags, float* __restrict__ grad_rgb_uniform) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -902,6 +911,7 @@ __global__ void points_backward_reduce_kernel(const float* __restrict__ partials
     }
     gs[n] = s;
   }
+  else if (lane < 16 && grad_rgb_uniform) atomicAdd(grad_rgb_uniform + (lane - 13), s);      // N terms per channel
 }
 
 }  // namespace mvr
@@ -1133,10 +1143,12 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
   p.ctas_per_view = w.tiles_x * groups_y;             // one partial per CTA (<= one per tile: the workspace is sized for that)
   const dim3 grid((unsigned)p.ctas_per_view, (unsigned)M, (unsigned)B);
   const bool vrgb = flags & MVR_RGB_PER_ELEMENT;
+  const bool gu = grad_rgb && !vrgb;      // gradient of the single point colour: through the partials (acc[13..15])
   // the register-resident variants read a pixel's K ids as one vector: they need the fragment tensor aligned to K ints
   const int kt = ((K == 1 || K == 2 || K == 4) && ((uintptr_t)idx & (size_t)(4 * K - 1)) == 0) ? K : 0;
-#define MVR_PBWD(KT_) do { if (vrgb) MVR_LAUNCH((points_backward_kernel<KT_, true>), grid, 32 * wpc, 0, st, p); \
-                           else MVR_LAUNCH((points_backward_kernel<KT_, false>), grid, 32 * wpc, 0, st, p); } while (0)
+#define MVR_PBWD(KT_) do { if (vrgb) MVR_LAUNCH((points_backward_kernel<KT_, true, false>), grid, 32 * wpc, 0, st, p); \
+                           else if (gu) MVR_LAUNCH((points_backward_kernel<KT_, false, true>), grid, 32 * wpc, 0, st, p); \
+                           else MVR_LAUNCH((points_backward_kernel<KT_, false, false>), grid, 32 * wpc, 0, st, p); } while (0)
   switch (kt) {
     case 1: MVR_PBWD(1); break;
     case 2: MVR_PBWD(2); break;
@@ -1147,6 +1159,7 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
   rc = check_launch("points_backward_kernel");
   if (rc) return rc;
   const int wpb = 8;
-  MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, p.ctas_per_view, gR, gT, g_inv_dist, inv_dist, flags);
+  MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, p.ctas_per_view, gR, gT, g_inv_dist, inv_dist, flags,
+             gu ? grad_rgb : (float*)nullptr);
   return check_launch("points_backward_reduce_kernel");
 }

@@ -755,16 +755,21 @@ def _mesh_forward_launch(geom: "PackedMeshes", M, R, T, Cc, light, obj_rgb, bg_r
         ws_bytes = lib.mvr_mesh_workspace_bytes(Bc, M, H, W, K, geom.total_verts, geom.total_faces)
         ws = workspace(dev, ws_bytes, _mesh_owner=True)
         ws_flags, ws_commit = _ws_mesh_flags_forward(dev, ws, (Bc, M, H, W, K, geom.total_verts))
-        sl = lambda t: None if t is None else t[n0:n1]
+        if len(ranges) == 1:      # (no views of views on the one-launch path: host microseconds in front of this call are step time)
+            sl = lambda t: t
+            voff, foff, lt, cnt = geom.vert_off, geom.face_off, light, counters
+        else:
+            sl = lambda t: None if t is None else t[n0:n1]
+            voff, foff, lt, cnt = geom.vert_off[b0:], geom.face_off[b0:], (light if light_stride == 0 else light[n0:n1]), counters[ci]
         with _on(dev):
-            L.check(lib.mvr_mesh_forward(_ptr(geom.geometry), _ptr(geom.vert_off[b0:]), _ptr(geom.face_off[b0:]), Bc, M,
-                                         geom.total_verts, geom.total_faces, geom.max_verts, geom.max_faces, _ptr(R[n0:n1]), _ptr(T[n0:n1]),
-                                         _ptr(Cc[n0:n1]), _ptr(light if light_stride == 0 else light[n0:n1]), light_stride, _ptr(obj_rgb),
+            L.check(lib.mvr_mesh_forward(_ptr(geom.geometry), _ptr(voff), _ptr(foff), Bc, M,
+                                         geom.total_verts, geom.total_faces, geom.max_verts, geom.max_faces, _ptr(sl(R)), _ptr(sl(T)),
+                                         _ptr(sl(Cc)), _ptr(lt), light_stride, _ptr(obj_rgb),
                                          _ptr(bg_rgb), k00, k11, z_clip, float(blur_radius), H, W,
-                                         K, flags | ws_flags, out_norm, _ptr(images[n0:n1]), _ptr(p2f[n0:n1]), _ptr(sl(zbuf)), _ptr(sl(bary)),
-                                         _ptr(sl(dists)), _ptr(counters[ci]), _ptr(ws), ws.numel(), _stream(dev)), "mvr_mesh_forward")
+                                         K, flags | ws_flags, out_norm, _ptr(sl(images)), _ptr(sl(p2f)), _ptr(sl(zbuf)), _ptr(sl(bary)),
+                                         _ptr(sl(dists)), _ptr(cnt), _ptr(ws), ws.numel(), _stream(dev)), "mvr_mesh_forward")
         tokens.append(ws_commit())
-    counters = counters[0] if len(ranges) == 1 else counters.sum(0)
+    counters = counters.view(-1) if len(ranges) == 1 else counters.sum(0)
     cfg = (k00, k11, H, W, K, flags, out_norm, light_stride, z_clip, (ranges, tokens))
     saved = (R, T, Cc, light, obj_rgb if obj_rgb is not None else bg_rgb, p2f)
     extras = [p2f, counters]
@@ -795,12 +800,17 @@ def _mesh_backward_launch(geom: "PackedMeshes", M, cfg, saved, g_images, want_ve
         ws_bytes = lib.mvr_mesh_workspace_bytes(Bc, M, H, W, K, geom.total_verts, geom.total_faces)
         ws = workspace(dev, ws_bytes, _mesh_owner=True)
         fl = flags | _ws_mesh_flags_backward(dev, ws, tokens[ci])
+        if len(ranges) == 1:
+            sl = lambda t: t
+            voff, foff, lt = geom.vert_off, geom.face_off, light
+        else:
+            sl = lambda t: t[n0:n1]
+            voff, foff, lt = geom.vert_off[b0:], geom.face_off[b0:], (light if light_stride == 0 else light[n0:n1])
         with _on(dev):
-            L.check(lib.mvr_mesh_backward(_ptr(geom.geometry), _ptr(geom.vert_off[b0:]), _ptr(geom.face_off[b0:]), Bc, M,
-                                          geom.total_verts, geom.total_faces, geom.max_verts, _ptr(R[n0:n1]), _ptr(T[n0:n1]), _ptr(Cc[n0:n1]),
-                                          _ptr(light if light_stride == 0 else light[n0:n1]),
-                                          light_stride, _ptr(obj_rgb), k00, k11, z_clip, H, W, K, fl, out_norm, _ptr(p2f[n0:n1]),
-                                          _ptr(g_images[n0:n1]), _ptr(gR[n0:n1]), _ptr(gT[n0:n1]), _ptr(gC[n0:n1]), _ptr(gV), _ptr(gN), _ptr(ws),
+            L.check(lib.mvr_mesh_backward(_ptr(geom.geometry), _ptr(voff), _ptr(foff), Bc, M,
+                                          geom.total_verts, geom.total_faces, geom.max_verts, _ptr(sl(R)), _ptr(sl(T)), _ptr(sl(Cc)), _ptr(lt),
+                                          light_stride, _ptr(obj_rgb), k00, k11, z_clip, H, W, K, fl, out_norm, _ptr(sl(p2f)),
+                                          _ptr(sl(g_images)), _ptr(sl(gR)), _ptr(sl(gT)), _ptr(sl(gC)), _ptr(gV), _ptr(gN), _ptr(ws),
                                           ws.numel(), _stream(dev)), "mvr_mesh_backward")
     if gV is not None:
         # the kernel returned d/d verts through projection + interpolated position, and d/d unit normals; the

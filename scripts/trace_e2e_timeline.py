@@ -1,3 +1,5 @@
+"""GPU (CUDA events) and host (perf_counter) timeline of the C-ABI calls of one end-to-end mesh step, for h2d_chunks = 1 and 2
+(profiles/r3y_h2d_chunks.txt).  usage: python scripts/trace_e2e_timeline.py"""
 import os, sys, statistics, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
