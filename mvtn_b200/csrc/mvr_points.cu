@@ -35,6 +35,7 @@ struct PointsParams {
   // tiled path (K in {1,2,4,8}): per-(view, point) projection + pixel window, per-(view, tile) point lists
   float4* pp; int2* pw; int* tile_cnt; int* tile_off; int* tile_cur; int* list;
   int tiles_x, tiles_y, ntiles, list_cap;
+  int vec_bg;                    // W % 4 == 0 and 16-byte aligned images: the tile kernel paints the background 4 pixels per store
   void* images; int* idx; float* zbuf; float* dists2; unsigned int* hit_mask;
   OutNorm onorm;
 };
@@ -186,7 +187,9 @@ __device__ __forceinline__ void store_background_pixel(const PointsParams& p, in
 // A covered pixel, its K ascending keys known (kreg: in registers, KT > 0; kp: their address, KT == 0): idx / zbuf /
 // dists2 of every layer, norm-weighted or alpha compositing ([upstream] norm_weighted_sum / alpha_composite), planar
 // image stores.
-template <int KT>
+// PP: the view's projected points are in the workspace (tiled path: p.pp, written by the binning kernel with the very
+// project_point below, so the values are the same bits) -- one 16-byte load instead of three loads and the transform.
+template <int KT, bool PP = false>
 __device__ __forceinline__ void composite_hit_pixel(const PointsParams& p, const unsigned long long* kreg,
                                                     const unsigned long long* kp, const Camera& cam, float s, int b, int n,
                                                     int xi, int yi) {
@@ -212,7 +215,8 @@ __device__ __forceinline__ void composite_hit_pixel(const PointsParams& p, const
     if (open) {
       q = (int)(unsigned int)(key & 0xffffffffull);
       float px, py, pz;
-      project_point(pts, q, s, cam, px, py, pz);
+      if (PP) { const float4 P = __ldg(p.pp + (size_t)n * p.Np + q); px = P.x; py = P.y; }
+      else project_point(pts, q, s, cam, px, py, pz);
       const float dx = px - xf, dy = py - yf;
       d2 = dx * dx + dy * dy;
       z = __uint_as_float((unsigned int)(key >> 32));
@@ -587,6 +591,24 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) points_tile_kernel(const Po
     if (p.onorm.on) { g0 = (g0 - p.onorm.m0) * p.onorm.s0; g1 = (g1 - p.onorm.m1) * p.onorm.s1; g2 = (g2 - p.onorm.m2) * p.onorm.s2; }
     const __nv_bfloat16 h0 = __float2bfloat16_rn(g0), h1 = __float2bfloat16_rn(g1), h2 = __float2bfloat16_rn(g2);
     const int hw = (int)HW, xi = x0 + lane;
+    if (p.vec_bg) {
+      // the background colour of the WHOLE tile first, four pixels per store (thread = row tid / 8, pixels 4 (tid % 8) ..+3):
+      // 3 stores per thread instead of 12; the covered pixels are overwritten by pass 2, behind the barrier below
+      const int yv = y0 + (tid >> 3), xv = x0 + ((tid & 7) << 2);
+      if (yv < p.H && xv < p.W) {
+        const int pv = yv * p.W + xv;
+        if (bf16) {
+          const unsigned int u0 = __bfloat16_as_ushort(h0), u1 = __bfloat16_as_ushort(h1), u2 = __bfloat16_as_ushort(h2);
+          *reinterpret_cast<uint2*>(img_h + pv) = make_uint2(u0 | (u0 << 16), u0 | (u0 << 16));
+          *reinterpret_cast<uint2*>(img_h + pv + hw) = make_uint2(u1 | (u1 << 16), u1 | (u1 << 16));
+          *reinterpret_cast<uint2*>(img_h + pv + 2 * hw) = make_uint2(u2 | (u2 << 16), u2 | (u2 << 16));
+        } else {
+          *reinterpret_cast<float4*>(img_f + pv) = make_float4(g0, g0, g0, g0);
+          *reinterpret_cast<float4*>(img_f + pv + hw) = make_float4(g1, g1, g1, g1);
+          *reinterpret_cast<float4*>(img_f + pv + 2 * hw) = make_float4(g2, g2, g2, g2);
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int row = warp + 8 * j, yi = y0 + row;
@@ -620,8 +642,10 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) points_tile_kernel(const Po
 #pragma unroll
           for (int l = 0; l < KT; ++l) p.dists2[frag_o + KT * pix + l] = -1.f;
         }
-        if (bf16) { img_h[pix] = h0; img_h[pix + hw] = h1; img_h[pix + 2 * hw] = h2; }
-        else { img_f[pix] = g0; img_f[pix + hw] = g1; img_f[pix + 2 * hw] = g2; }
+        if (!p.vec_bg) {
+          if (bf16) { img_h[pix] = h0; img_h[pix + hw] = h1; img_h[pix + 2 * hw] = h2; }
+          else { img_f[pix] = g0; img_f[pix + hw] = g1; img_f[pix + 2 * hw] = g2; }
+        }
       }
     }
   }
@@ -635,7 +659,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) points_tile_kernel(const Po
       unsigned long long kreg[KT];
 #pragma unroll
       for (int k = 0; k < KT; ++k) kreg[k] = s_keys[k * 1024 + q];
-      composite_hit_pixel<KT>(p, kreg, nullptr, cam, s, b, n, x0 + (q & 31), y0 + (q >> 5));
+      composite_hit_pixel<KT, true>(p, kreg, nullptr, cam, s, b, n, x0 + (q & 31), y0 + (q >> 5));
     }
   }
 }
@@ -1028,6 +1052,7 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
   p.tile_cnt = (int*)(wb + w.tile_cnt); p.tile_off = (int*)(wb + w.tile_off); p.tile_cur = (int*)(wb + w.tile_cur);
   p.list = (int*)(wb + w.list);
   p.tiles_x = w.tiles_x; p.tiles_y = w.tiles_y; p.ntiles = w.ntiles; p.list_cap = w.list_cap;
+  p.vec_bg = (W % 4 == 0) && ((uintptr_t)images % 16 == 0);
   p.images = images; p.idx = idx; p.zbuf = zbuf; p.dists2 = dists2; p.hit_mask = hit_mask;
   p.onorm = make_out_norm(out_mean_std);
   cudaStream_t st = (cudaStream_t)stream;
