@@ -1,6 +1,7 @@
 """Tiny forward + backward of both paths (mesh: scatter + shade, strip and tile backward, K = 1 and 2, a clipped view, the
-tile-binned forward with its TMA bulk copies, vertex gradients with the warp-aggregated scatter, the soft shaders; points: tiled
-and generic K) for compute-sanitizer:   compute-sanitizer --tool memcheck|racecheck python scripts/sanitize_small.py"""
+tile-binned forward with its TMA bulk copies, vertex gradients with the warp-aggregated scatter, the soft shaders, a collated batch
+rendered in h2d_chunks groups; points: tiled and generic K, the clustered binning (> 4096 points: DSMEM counters), point / colour
+gradients) for compute-sanitizer:   compute-sanitizer --tool memcheck|racecheck python scripts/sanitize_small.py"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -49,3 +50,19 @@ for K in (1, 4, 3):
     img.backward(torch.ones_like(img))
     torch.cuda.synchronize()
     print("points", K, float(img.sum()), float(d.grad.abs().sum()), int((fr["idx"] >= 0).sum()))
+big = synth.make_clouds(1, 5000, 9).to(dev)                              # > 4096 points: 4-CTA cluster binning, DSMEM counters
+for K, mode in ((4, "alpha"), (1, "norm")):
+    a, e, d = (t[:1].to(dev).requires_grad_() for t in views)
+    pg = big.clone().requires_grad_(); cg = col.clone().requires_grad_()      # per-point atomics + the single colour's gradient (partials)
+    img, _, fr = ops.render_points_from_angles(pg, cg, 3, a, e, d, 0.02, bg, 96, points_per_pixel=K, compositor=mode)
+    img.backward(torch.ones_like(img))
+    torch.cuda.synchronize()
+    print("points clustered", K, float(img.sum()), float(pg.grad.abs().sum()), float(cg.grad.abs().sum()))
+from mvtn_b200 import MVRenderer, Meshes, collate_meshes
+ml = [Meshes([v], [f]) for v, f in synth.make_meshes(4, 500, 21)]
+r = MVRenderer(3, image_size=48, pc_rendering=False, light_direction="fixed", h2d_chunks=2).to(dev)
+a, e, d = (t.to(dev).requires_grad_() for t in synth.learned_spherical_views(4, 3, 8))
+img, _ = r(collate_meshes(ml), None, a, e, d)
+img.backward(torch.ones_like(img))
+torch.cuda.synchronize()
+print("mesh h2d_chunks=2", float(img.detach().sum()), float(a.grad.abs().sum()))
