@@ -117,6 +117,19 @@ int mvr_look_at_backward(const float* azim, const float* elev, const float* dist
                          const float* gR, const float* gT, const float* gC, float* g_azim,
                          float* g_elev, float* g_dist, void* stream);
 
+/* -- consumer side: the regulariser applied to the rendered views ------------------------------ */
+/* ops.py:138-178 regualarize_rendered_views (called right behind the renderer: run_mvtn.py:186,244, Trainer_mvt.py:104) as ONE
+ * gather: view dropout (dropout2d on the 5-D (B,M,3,H,W) tensor = a per-view factor 0 or 1/(1-p): view_scale (N) or NULL),
+ * batchwise horizontal flip, and ReplicationPad2d(pad) + RandomCrop(H) = a shift by (shift_y, shift_x) = crop offset - pad with
+ * edge replication:  out[n,c,y,x] = view_scale[n] * in[n,c,clamp(y+shift_y), fx(clamp(x+shift_x))], fx(u) = flip ? W-1-u : u.
+ * images / out: (N,C,H,W) contiguous, fp32 or bfloat16 [MVR_IMAGES_BF16], out != images.  The caller draws the random decisions
+ * (mvtn_b200/augment.py draws them with the reference's own torch calls). */
+int mvr_images_regularize_forward(const void* images, int N, int C, int H, int W, const float* view_scale, int flip,
+                                  int shift_y, int shift_x, int flags, void* out, void* stream);
+/* its adjoint: grad_out (N,C,H,W) -> grad_in (N,C,H,W), fully written */
+int mvr_images_regularize_backward(const void* grad_out, int N, int C, int H, int W, const float* view_scale, int flip,
+                                   int shift_y, int shift_x, int flags, void* grad_in, void* stream);
+
 /* -- meshes ------------------------------------------------------------------------------- */
 /* Device-resident packed geometry built once per batch of objects (replaces Meshes(...),
  * Textures(verts_rgb) and verts_normals_packed(): renderer.py:67-77 + [upstream] meshes.py). */

@@ -6,6 +6,7 @@ The arithmetic lives in libmvr_b200.so (csrc/*.cu, C ABI in include/mvr_b200.h);
 Python host side that mirrors the reference's interface.  There is no CPU fallback.
 """
 from .renderer import MVRenderer  # noqa: F401
+from .augment import regularize_rendered_views, regualarize_rendered_views  # noqa: F401
 from .structures import Meshes  # noqa: F401
 from .ops import (HostPackedMeshes, PackedMeshes, camera_position_from_spherical_angles, collate_meshes,  # noqa: F401
                   look_at_view_transform, render_meshes, render_points)

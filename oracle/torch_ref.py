@@ -412,3 +412,45 @@ def render_mesh_view_soft(verts, faces, normals, vert_rgb, R, T, Cc, light_dir, 
         col = phong_colors(bary, p2f, verts, faces, normals, vert_rgb, light_dir, Cc)
         img = softmax_rgb_blend(col, p2f, zbuf, dists, bg, sigma, gamma)
     return img.permute(2, 0, 1), dict(pix_to_face=p2f, zbuf=zbuf, bary=bary, dists=dists)
+
+
+# ---------------------------------------------------------------------------------------------------
+# The regulariser behind the renderer: ops.py:138-178 restated with the same torch / torchvision calls in the same order (this
+# one CAN be pinned: the reference's implementation is nothing but torch + torchvision library calls; the reference module itself
+# does not import here only because of `torch._six`, ops.py:9).
+def applied_transforms(images_batch, crop_ratio=0.3):
+    """ops.py:138-146."""
+    from torchvision.transforms import RandomCrop, RandomHorizontalFlip
+    N, C, H, W = images_batch.shape
+    padd = torch.nn.ReplicationPad2d(int((1 + crop_ratio) * H) - H)
+    images_batch = RandomHorizontalFlip()(images_batch)
+    images_batch = RandomCrop(H)(padd(images_batch))
+    return images_batch
+
+
+def regularize_rendered_views(rendered_images, dropout_p=0, augment_training=False, crop_ratio=0.3):
+    """ops.py:168-176 regualarize_rendered_views: dropout2d on the 5-D (B, M, C, H, W) tensor, then the batchwise transforms on
+    the views flattened to (B*M, C, H, W) (super_batched_op(1, ...), ops.py:149-153 with util.batch_tensor / unbatch_tensor)."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")      # torch >= 1.12 warns that a 5-D input makes dropout2d a feature dropout over dim 1
+        rendered_images = F.dropout2d(rendered_images, p=dropout_p, training=True)
+    if augment_training:
+        B, M = rendered_images.shape[:2]
+        flat = rendered_images.reshape(B * M, *rendered_images.shape[2:])
+        rendered_images = applied_transforms(flat, crop_ratio=crop_ratio).reshape(B, M, *rendered_images.shape[2:])
+    return rendered_images
+
+
+def regularize_gather(x, scale, flip, sy, sx):
+    """The composed form the CUDA kernel evaluates (mvtn_b200/csrc/mvr_augment.cu):
+    out[n,c,y,x] = scale[n] * in[n,c,clamp(y+sy), fx(clamp(x+sx))], fx(u) = W-1-u under a flip."""
+    B, M, C, H, W = x.shape
+    yi = (torch.arange(H, device=x.device) + sy).clamp(0, H - 1)
+    xi = (torch.arange(W, device=x.device) + sx).clamp(0, W - 1)
+    if flip:
+        xi = W - 1 - xi
+    out = x[..., yi, :][..., xi]
+    if scale is not None:
+        out = out * scale.to(x.dtype).reshape(B, M, 1, 1, 1)
+    return out

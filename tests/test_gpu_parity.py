@@ -930,6 +930,48 @@ def test_mvrenderer_h2d_chunks_match_single_copy(cuda_device, chunks, K):
     assert int((ref[1] >= 0).sum()) > 0
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_regularize_rendered_views_matches_reference(cuda_device, dtype):
+    """mvtn_b200.regularize_rendered_views (one gather kernel + its adjoint) against ops.py:138-178 restated with the reference's
+    own torch / torchvision calls on the GPU: same seeds -> the same views bit for bit; gradients against torch.autograd through
+    dropout2d / flip / ReplicationPad2d / crop."""
+    import mvtn_b200
+    from oracle import torch_ref as tr
+    dev = cuda_device
+    B, M = 3, 4
+    kinds = set()
+    for seed in range(24):
+        S = 40 if seed % 2 == 0 else 30      # (rows moved as 16-byte quads / element by element)
+        p = [0, 0.3, 0.6][seed % 3]; aug = seed % 4 != 3; cr = [0.3, 0.5, 0.1][seed % 3]
+        x0 = torch.rand(B, M, 3, S, S, generator=torch.Generator().manual_seed(seed)).to(dev).to(dtype)
+        xr, xm = x0.clone().requires_grad_(), x0.clone().requires_grad_()
+        torch.manual_seed(seed); ref = tr.regularize_rendered_views(xr, p, aug, cr)
+        torch.manual_seed(seed); out = mvtn_b200.regualarize_rendered_views(xm, p, aug, cr)
+        assert out.shape == ref.shape and out.dtype == ref.dtype
+        assert torch.equal(out, ref), (seed, p, aug, cr)
+        g = torch.randn(B, M, 3, S, S, generator=torch.Generator().manual_seed(100 + seed)).to(dev).to(dtype)
+        if out.requires_grad:
+            out.backward(g)
+            if dtype is torch.float32:
+                ref.backward(g)
+                want = xr.grad
+            else:
+                # torch sums the folded edge gradients (up to (2 pad + 1)^2 terms per corner pixel) IN bf16; the kernel sums in
+                # fp32 and rounds once: the bf16 check is against the fp32 adjoint of the same gather, to bf16 rounding
+                from mvtn_b200.augment import draw_regularizer
+                torch.manual_seed(seed); sc, fl, sy, sx = draw_regularizer(x0, p, aug, cr)
+                x32 = x0.float().requires_grad_()
+                tr.regularize_gather(x32, sc, fl, sy, sx).backward(g.float())
+                want = x32.grad
+            err = (xm.grad.float() - want.float()).abs().max() / want.float().abs().max().clamp_min(1e-6)
+            # fp32: the folded sums differ from autograd's in order only
+            assert float(err) < (1e-5 if dtype is torch.float32 else 5e-3), (seed, float(err))
+        kinds.add((p > 0, aug))
+    assert len(kinds) == 4
+    with pytest.raises(ValueError):
+        mvtn_b200.regularize_rendered_views(torch.zeros(1, 2, 3, 8, 12, device=dev), 0, True)
+
+
 def test_cuda_graph_replay_matches_eager(cuda_device):
     """mvtn_b200.graphs: the captured forward / backward graphs reproduce the eager path bit for bit, and pick up
     in-place updates of the captured buffers (new points, moved vertices, new views)."""

@@ -734,3 +734,26 @@ def test_soft_render_is_differentiable_and_matches_finite_differences(oracle):
             # (2e-4, not 1e-6: where the perspective-correction denominator is clamped -- some blurred fragments outside their
             # face -- upstream's backward differentiates the unclamped sum, and the restatement follows upstream, not calculus)
             assert abs(float(gT[i]) - float(fd)) <= 2e-4 * max(1.0, abs(float(fd))), (shader, i, float(gT[i]), float(fd))
+
+
+def test_regularizer_composed_gather_matches_reference_composition():
+    """ops.py:138-178 (dropout2d on the 5-D tensor, batchwise flip, ReplicationPad2d, RandomCrop) restated with the reference's own
+    torch / torchvision calls, against the ONE-gather form the CUDA kernel evaluates with the decisions drawn by
+    mvtn_b200.augment.draw_regularizer: same seeds -> same tensor, bit for bit (so the draw order and the index algebra are right)."""
+    import torch
+    from oracle import torch_ref as tr
+    from mvtn_b200.augment import draw_regularizer
+    seen = set()
+    for seed in range(48):
+        x = torch.randn(2, 3, 3, 10, 10)
+        p = [0, 0.3, 0.5][seed % 3]; aug = seed % 2 == 0; cr = [0.3, 0.0, 0.5, 0.15][seed % 4]
+        torch.manual_seed(seed); ref = tr.regularize_rendered_views(x, p, aug, cr)
+        torch.manual_seed(seed); sc, fl, sy, sx = draw_regularizer(x, p, aug, cr)
+        assert torch.equal(ref, tr.regularize_gather(x, sc, fl, sy, sx)), (seed, p, aug, cr, fl, sy, sx)
+        seen.add((fl, sy < 0, sy > 0, sx < 0, sx > 0, sc is not None))
+    assert len(seen) >= 12      # flips, both shift signs on both axes, with and without dropped views all occurred
+    x = torch.randn(1, 2, 3, 6, 6)
+    sc, fl, sy, sx = draw_regularizer(x, 0, False)
+    assert sc is None and not fl and sy == 0 and sx == 0
+    torch.manual_seed(1); sc, _, _, _ = draw_regularizer(x, 1.0, False)
+    assert torch.equal(sc, torch.zeros(2))
