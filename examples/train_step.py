@@ -22,7 +22,7 @@ import torch
 from torch import nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from mvtn_b200 import MVRenderer, Meshes, parallel, synth  # noqa: E402
+from mvtn_b200 import MVRenderer, Meshes, parallel, regualarize_rendered_views, synth  # noqa: E402
 
 
 class ViewSelector(nn.Module):
@@ -64,10 +64,12 @@ class TrainStep:
     sync: "overlap" (hook-driven buckets during backward), "after" (parallel.allreduce_gradients once backward is done:
     the un-overlapped baseline) or "none"."""
 
-    def __init__(self, dev, rank, batch=32, views=12, image_size=224, faces=10000, amp=False, sync="overlap", collate=True):
+    def __init__(self, dev, rank, batch=32, views=12, image_size=224, faces=10000, amp=False, sync="overlap", collate=True,
+                 view_reg=0.0, augment_training=False, crop_ratio=0.3):
         from mvtn_b200 import collate_meshes
         torch.manual_seed(1234)                         # same initial weights on every rank
         self.dev, self.amp, self.sync_mode = dev, amp, sync
+        self.view_reg, self.augment_training, self.crop_ratio = view_reg, augment_training, crop_ratio      # config.yaml:42-44
         self.selector, self.cnn = ViewSelector(views).to(dev), MVCNN().to(dev)
         self.renderer = MVRenderer(views, image_size=image_size, pc_rendering=False, light_direction="random").to(dev)
         self.opt = torch.optim.AdamW(self.cnn.parameters(), lr=1e-3, weight_decay=0.01)
@@ -91,6 +93,8 @@ class TrainStep:
         images, _ = self.renderer(self.meshes, None, azim, elev, dist)
         if self.render_events is not None:
             self.render_events[1].record()
+        # run_mvtn.py:186-187 (a no-op at the reference's defaults: view_reg 0, augment_training false)
+        images = regualarize_rendered_views(images, self.view_reg, self.augment_training, self.crop_ratio)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
             loss = self.crit(self.cnn(images), self.targets)
         if self.overlap is not None:
