@@ -54,6 +54,7 @@ def build(force=False, verbose=False):
     def compile_one(item):
         src, fmad = item
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        fmad = fmad and not os.environ.get("MVR_NO_FMAD")      # A/B builds: every file without contraction
         cmd = base + ["-fmad=true" if fmad else "-fmad=false", "-c", os.path.join(CSRC, src), "-o", obj]
         return obj, subprocess.run(cmd, capture_output=True, text=True)
 

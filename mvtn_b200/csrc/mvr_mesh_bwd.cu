@@ -87,22 +87,40 @@ __device__ __forceinline__ bool mesh_backward_pixel(const MeshBwdParams& p, int 
   normalize_bwd3(vx, vy, vz, 1e-6f, gvhx, gvhy, gvhz, gvx, gvy, gvz);
   acc[12] += gvx; acc[13] += gvy; acc[14] += gvz;   // dC
   // d bary_i = gtex.col_i + gN.n_i + gP.X_i  with gP = -gv
-  const float gc0 = fmaf(gtx, c0.x, fmaf(gty, c0.y, gtz * c0.z));
-  const float gc1 = VRGB ? fmaf(gtx, c1.x, fmaf(gty, c1.y, gtz * c1.z)) : gc0;
-  const float gc2 = VRGB ? fmaf(gtx, c2.x, fmaf(gty, c2.y, gtz * c2.z)) : gc0;
-  float gb0 = gc0 + fmaf(gNx, N0.x, fmaf(gNy, N0.y, gNz * N0.z)) - fmaf(gvx, X0.x, fmaf(gvy, X0.y, gvz * X0.z));
-  float gb1 = gc1 + fmaf(gNx, N1.x, fmaf(gNy, N1.y, gNz * N1.z)) - fmaf(gvx, X1.x, fmaf(gvy, X1.y, gvz * X1.z));
-  float gb2 = gc2 + fmaf(gNx, N2.x, fmaf(gNy, N2.y, gNz * N2.z)) - fmaf(gvx, X2.x, fmaf(gvy, X2.y, gvz * X2.z));
+  float gb0, gb1, gb2;
   // ---- [upstream] BarycentricPerspectiveCorrectionBackward ----
   float dz0 = 0.f, dz1 = 0.f, dz2 = 0.f;
-  if (persp) {
-    // b = t / sum(t) is invariant to a common shift of d/db (its Jacobian annihilates constants), so
-    // remove k = sum(b_i gb_i) first: the d/d denom term then vanishes identically instead of cancelling
-    // O(1/area) terms in fp32.  Same gradient in exact arithmetic; not valid when denom was clamped.
-    if (!clamped) {
-      const float kk = fmaf(bb[0], gb0, fmaf(bb[1], gb1, bb[2] * gb2));
-      gb0 -= kk; gb1 -= kk; gb2 -= kk;
+  if (persp && !clamped) {
+    // b = t / sum(t) is invariant to a common shift of d/db (its Jacobian annihilates constants): the gradient only depends on
+    // gb_i - k, k = sum_j b_j gb_j, i.e. on sum_j b_j (gb_i - gb_j) (sum b = 1) -- and the differences gb_i - gb_j are formed from
+    // ATTRIBUTE differences, gN.(N_i - N_j) - gv.(X_i - X_j) (+ gtex.(c_i - c_j)), never from the gb themselves.  The three gb are
+    // nearly equal (one object colour: the common part is gtex.colour ~ 0.5, the differences ~ 1e-5), the Jacobian behind them is
+    // ~ 1/area, and a sliver's vertex gradients are a small residual of its terms: forming gb_i first rounds them at 6e-8, which a
+    // sliver of NDC area 3e-6 amplifies to a 3..26 % error of the pixel's camera gradient, jumping with single ulps anywhere
+    // upstream (scripts/fuzz_parity.py, soup case 5421; PyTorch3D's own fp32 chain rounds d/db the same way).  From attribute
+    // differences the error stays relative to the differences.  (Without perspective correction sum w = area / (area + eps) is
+    // only nearly constant and the plain chain below is kept, with upstream's conditioning.)
+    const float n01x = N0.x - N1.x, n01y = N0.y - N1.y, n01z = N0.z - N1.z, n02x = N0.x - N2.x, n02y = N0.y - N2.y, n02z = N0.z - N2.z;
+    const float x01x = X0.x - X1.x, x01y = X0.y - X1.y, x01z = X0.z - X1.z, x02x = X0.x - X2.x, x02y = X0.y - X2.y, x02z = X0.z - X2.z;
+    float d01 = fmaf(gNx, n01x, fmaf(gNy, n01y, gNz * n01z)) - fmaf(gvx, x01x, fmaf(gvy, x01y, gvz * x01z));
+    float d02 = fmaf(gNx, n02x, fmaf(gNy, n02y, gNz * n02z)) - fmaf(gvx, x02x, fmaf(gvy, x02y, gvz * x02z));
+    if (VRGB) {
+      d01 += fmaf(gtx, c0.x - c1.x, fmaf(gty, c0.y - c1.y, gtz * (c0.z - c1.z)));
+      d02 += fmaf(gtx, c0.x - c2.x, fmaf(gty, c0.y - c2.y, gtz * (c0.z - c2.z)));
     }
+    const float d12 = d02 - d01;
+    gb0 = fmaf(bb[1], d01, bb[2] * d02);
+    gb1 = fmaf(bb[2], d12, -bb[0] * d01);
+    gb2 = -fmaf(bb[0], d02, bb[1] * d12);
+  } else {
+    const float gc0 = fmaf(gtx, c0.x, fmaf(gty, c0.y, gtz * c0.z));
+    const float gc1 = VRGB ? fmaf(gtx, c1.x, fmaf(gty, c1.y, gtz * c1.z)) : gc0;
+    const float gc2 = VRGB ? fmaf(gtx, c2.x, fmaf(gty, c2.y, gtz * c2.z)) : gc0;
+    gb0 = gc0 + fmaf(gNx, N0.x, fmaf(gNy, N0.y, gNz * N0.z)) - fmaf(gvx, X0.x, fmaf(gvy, X0.y, gvz * X0.z));
+    gb1 = gc1 + fmaf(gNx, N1.x, fmaf(gNy, N1.y, gNz * N1.z)) - fmaf(gvx, X1.x, fmaf(gvy, X1.y, gvz * X1.z));
+    gb2 = gc2 + fmaf(gNx, N2.x, fmaf(gNy, N2.y, gNz * N2.z)) - fmaf(gvx, X2.x, fmaf(gvy, X2.y, gvz * X2.z));
+  }
+  if (persp) {
     const float gden = clamped ? -(gb0 * t0 + gb1 * t1 + gb2 * t2) * id * id : 0.f;
     const float gt0 = fmaf(gb0, id, gden), gt1 = fmaf(gb1, id, gden), gt2 = fmaf(gb2, id, gden);
     gb0 = gt0 * fc.z1 * fc.z2; gb1 = gt1 * fc.z0 * fc.z2; gb2 = gt2 * fc.z0 * fc.z1;
@@ -112,7 +130,9 @@ __device__ __forceinline__ bool mesh_backward_pixel(const MeshBwdParams& p, int 
   }
   // ---- [upstream] BarycentricCoordsBackward / EdgeFunctionBackward ----
   const float ge0 = gb0 * inv_area, ge1 = gb1 * inv_area, ge2 = gb2 * inv_area;
-  const float garea = -(gb0 * e0 + gb1 * e1 + gb2 * e2) * inv_area * inv_area;
+  // (perspective-corrected barycentrics do not depend on a common factor of the w_i: d/d area vanishes identically there --
+  // computed, it is rounding noise times 1/area^2)
+  const float garea = (persp && !clamped) ? 0.f : -(gb0 * e0 + gb1 * e1 + gb2 * e2) * inv_area * inv_area;
   float gx0, gy0, gx1, gy1, gx2, gy2;
   // E(p,a,b): dE/da = (py-by, bx-px), dE/db = (ay-py, px-ax)
   gx1 = ge0 * (yf - fc.y2); gy1 = ge0 * (fc.x2 - xf); gx2 = ge0 * (fc.y1 - yf); gy2 = ge0 * (xf - fc.x1);          // e0 = E(p,v1,v2)
