@@ -33,7 +33,12 @@ import sys
 import threading
 import time
 
-import torch
+# Idle OpenMP workers (torch's intra-op pool, the CPU oracle of the cpu_baseline leg) park instead of spinning: the point steps are
+# bound by the launching host thread (0.26 ms of python per 384-view step), and spinning workers on its cores cost it up to 20 %
+# (c3_points 0.262 vs 0.320 ms per step, same box, same kernels).  Set before torch / libgomp load; an explicit setting wins.
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
