@@ -7,7 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "mvtn_b200", "libmvr_b200.so")
 KERNELS = ("mesh_shade_kernelILb0ELi4ELi4ELb0", "mesh_scatter_kernelILi4ELb0", "mesh_tile_kernelILb0ELi4ELb0", "mesh_bin_kernelILb0",
            "mesh_backward_kernel_stripILi3ELb0ELb0", "mesh_backward_kernel_stripILi2ELb0ELb1", "points_tile_kernelILi4E",
-           "points_bin_kernel_fused", "points_backward_kernelILi4E", "mesh_soft_blend_kernel", "mesh_soft_backward_kernel")
+           "points_bin_kernel_fused", "points_backward_kernelILi4ELb0ELb0", "images_regularize_kernelILb1", "images_regularize_backward_rows_kernelILb1",
+           "mesh_soft_blend_kernel", "mesh_soft_backward_kernel")
 COLS = (("UBLKCP", r"^UBLKCP"), ("SYNCS", r"^SYNCS"), ("LDGSTS", r"^LDGSTS"), ("UCGABAR", r"^UCGABAR"), ("MATCH", r"^MATCH"),
         ("RED/ATOMG", r"^(RED|ATOMG)"), ("ATOMS", r"^ATOMS"), ("MUFU.RCP", r"^MUFU\.RCP"), ("LDG.256", r"^LDG\.E\.(\w+\.)*256"), ("FCHK", r"^FCHK"))
 
