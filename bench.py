@@ -250,7 +250,8 @@ class Workload:
             self.renderer = MVRenderer(M, image_size=S, pc_rendering=False, light_direction="fixed").to(dev).train()
             self.renderer_pipe = MVRenderer(M, image_size=S, pc_rendering=False, light_direction="fixed", copy_stream=True).to(dev).train()
             self.kernels = ["mesh_scatter_kernel", "mesh_shade_kernel", "mesh_backward_kernel", "mesh_tile_kernel"]
-            self.h2d = sum(v.numel() * 4 + f.numel() * 4 for v, f in inp["meshes"]) + 3 * B * M * 4
+            hp = self.mesh_host      # bytes that actually travel: fp32 vertices, faces as collated (uint16 when every mesh has <= 65536 vertices), offsets, views
+            self.h2d = sum(t.numel() * t.element_size() for t in (hp.verts, hp.faces, hp.offs)) + 3 * B * M * 4
         else:
             self.pts_d = inp["points"].to(dev)
             self.pts_h = inp["points"].pin_memory()
@@ -478,7 +479,7 @@ def measure(s, a, rank, world, dev, lib, parallel, with_cpu, clock_sampler=None)
            "config": config_of(s, a),
            "e2e": {"value": round(total_views / (ms_e2e / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(w.h2d),
                    "d2h_bytes_per_step": int(w.d2h), "ms_per_step": round(ms_e2e / a.steps, 4),
-                   "input": ("collated pinned host batch (mvtn_b200.collate_meshes) + pinned view tensors" if mesh
+                   "input": ("collated pinned host batch (mvtn_b200.collate_meshes: fp32 vertices, uint16 faces) + pinned view tensors" if mesh
                              else "pinned host point tensor + pinned view tensors"),
                    "pipelined": {"value": round(total_views / (ms_pipe / 1e3), 1), "ms_per_step": round(ms_pipe / a.steps, 4),
                                  "note": "same per-step H2D / D2H, but the result of step i is awaited on the host during step i+1 "

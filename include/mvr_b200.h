@@ -46,6 +46,8 @@ extern "C" {
 #define MVR_IDX_SPARSE 1024        /* mvr_points_forward (K in {1,2,4,8}, hit_mask given, no zbuf / dists2 wanted): idx is written
                                       only where the pixel's hit_mask bit is set -- 4 K bytes per background pixel (~90 % of a
                                       point image) are not stored; mvr_points_backward never reads them */
+#define MVR_FACES_U16 8192         /* mvr_mesh_prepare: faces given as uint16 (F,3) -- every mesh of the batch has at most 65536 vertices; half
+                                      the bytes of int32 on the host-to-device copy (mvtn_b200.collate_meshes narrows when it can) */
 #define MVR_FORWARD_TILED 2048     /* mvr_mesh_forward, K == 1: the tile-binned rasterizer + shader (coarse binning pass, per-tile face
                                       lists staged by TMA bulk copies, depth keys in shared memory, shading in the same CTA) instead of
                                       the default bin-free scatter + shade pair.  Same fragments bit for bit; slower on B200 at the
@@ -134,7 +136,7 @@ int mvr_images_regularize_backward(const void* grad_out, int N, int C, int H, in
 /* Device-resident packed geometry built once per batch of objects (replaces Meshes(...),
  * Textures(verts_rgb) and verts_normals_packed(): renderer.py:67-77 + [upstream] meshes.py). */
 size_t mvr_mesh_geometry_bytes(int64_t total_verts, int64_t total_faces);
-/* verts (Vtot,3); faces (Ftot,3) int32 or int64 [MVR_FACES_I64], mesh-local vertex ids;
+/* verts (Vtot,3); faces (Ftot,3) int32, int64 [MVR_FACES_I64] or uint16 [MVR_FACES_U16], mesh-local vertex ids;
  * vert_off / face_off (B+1) int32 prefix sums (device); vert_rgb (Vtot,3) or NULL. */
 int mvr_mesh_prepare(const float* verts, const void* faces, const int* vert_off, const int* face_off,
                      int B, int64_t total_verts, int64_t total_faces, int max_faces,

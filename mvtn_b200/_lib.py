@@ -18,6 +18,7 @@ WS_REARM_KEYS = 256
 WS_PROJECTED = 512
 IDX_SPARSE = 1024
 CLIP_BARYCENTRIC = 4096   # [upstream] clip_barycentric_coords
+FACES_U16 = 8192         # faces as uint16 (meshes of at most 65536 vertices): collate_meshes narrows when it can
 FORWARD_TILED = 2048     # mesh forward, K == 1: tile-binned rasterizer + shader (opt-in A/B alternative)
 TEST_TINY_QUEUES = 0x40000000   # tests only: shrink the scatter kernel's work queues to force their fallbacks
 CNT_STRADDLE, CNT_BIG_FACES, NUM_COUNTERS = 0, 1, 4

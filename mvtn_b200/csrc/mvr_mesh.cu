@@ -480,6 +480,7 @@ extern "C" int mvr_mesh_prepare_range(const float* verts, const void* faces, con
   if (obj_begin == obj_end || vert_begin == vert_end) return 0;
   if (!verts || !vert_off || !face_off || !geometry || (total_faces > 0 && !faces)) { set_error("mvr_mesh_prepare: null pointer"); return -4; }
   if ((flags & MVR_RGB_PER_ELEMENT) && !vert_rgb) { set_error("mvr_mesh_prepare: MVR_RGB_PER_ELEMENT without vert_rgb"); return -5; }
+  if ((flags & MVR_FACES_I64) && (flags & MVR_FACES_U16)) { set_error("mvr_mesh_prepare: MVR_FACES_I64 and MVR_FACES_U16 are exclusive"); return -7; }
   char* base = (char*)geometry;
   cudaStream_t st = (cudaStream_t)stream;
   float4* verts4 = (float4*)(base + g.verts4);
@@ -494,6 +495,7 @@ extern "C" int mvr_mesh_prepare_range(const float* verts, const void* faces, con
   if (total_faces > 0 && max_faces > 0) {
     dim3 grid((max_faces + tb - 1) / tb, obj_end - obj_begin);
     if (flags & MVR_FACES_I64) MVR_LAUNCH(geom_pack_faces_kernel<long long>, grid, tb, 0, st, (const long long*)faces, vert_off + obj_begin, face_off + obj_begin, verts4, faces4, nacc);
+    else if (flags & MVR_FACES_U16) MVR_LAUNCH(geom_pack_faces_kernel<unsigned short>, grid, tb, 0, st, (const unsigned short*)faces, vert_off + obj_begin, face_off + obj_begin, verts4, faces4, nacc);
     else MVR_LAUNCH(geom_pack_faces_kernel<int>, grid, tb, 0, st, (const int*)faces, vert_off + obj_begin, face_off + obj_begin, verts4, faces4, nacc);
   }
   MVR_LAUNCH(geom_finish_normals_kernel, (unsigned)((nv + tb - 1) / tb), tb, 0, st, nacc + 3 * vert_begin, nv, verts4 + vert_begin, normals4 + vert_begin,

@@ -323,7 +323,8 @@ def camera_position_from_spherical_angles(distance, elevation, azimuth, degrees:
 # --------------------------------------------------------------------------------------------------
 class HostPackedMeshes:
     """A batch of meshes packed on the HOST into pinned memory: verts (Vtot,3) f32, faces (Ftot,3) int32 (mesh-local
-    ids), per-mesh counts.  This is what a DataLoader collate_fn should hand to MVRenderer (the
+    ids) -- or int16 holding UNSIGNED 16-bit ids (torch has no uint16 arithmetic; collate_meshes narrows to it when every mesh
+    has at most 65536 vertices: half the faces' bytes on the host-to-device copy, MVR_FACES_U16) --, per-mesh counts.  This is what a DataLoader collate_fn should hand to MVRenderer (the
     reference's collate keeps python lists, custom_dataset.py:149-188, and re-packs them on every forward,
     renderer.py:67-77): the packing then runs in the loader's workers, off the training step, and the step itself only
     pays two H2D copies.  Build with collate_meshes()."""
@@ -334,8 +335,10 @@ class HostPackedMeshes:
             raise ValueError("verts must be (Vtot,3) and faces (Ftot,3)")
         if verts.is_cuda or faces.is_cuda:
             raise ValueError("HostPackedMeshes holds host tensors; use PackedMeshes.from_packed for device arrays")
-        if verts.dtype != torch.float32 or faces.dtype != torch.int32:
-            raise ValueError("verts must be float32 and faces int32")
+        if verts.dtype != torch.float32 or faces.dtype not in (torch.int32, torch.int16):
+            raise ValueError("verts must be float32 and faces int32 (or int16 holding uint16 ids)")
+        if faces.dtype == torch.int16 and max(num_verts, default=0) > 65536:
+            raise ValueError("16-bit faces need meshes of at most 65536 vertices")
         if sum(num_verts) != verts.shape[0] or sum(num_faces) != faces.shape[0]:
             raise ValueError("packed arrays do not match the per-mesh counts")
         self.verts, self.faces = verts.contiguous(), faces.contiguous()
@@ -372,7 +375,8 @@ class HostPackedMeshes:
         return list(torch.split(self.verts, self.num_verts))
 
     def faces_list(self):
-        return list(torch.split(self.faces, self.num_faces))
+        f = self.faces if self.faces.dtype == torch.int32 else self.faces.to(torch.int32) & 0xFFFF
+        return list(torch.split(f, self.num_faces))
 
 
 def _in_loader_worker() -> bool:
@@ -383,14 +387,17 @@ def _in_loader_worker() -> bool:
         return False
 
 
-def collate_meshes(meshes, pin_memory: Optional[bool] = None, vert_rgb: Optional[torch.Tensor] = None) -> HostPackedMeshes:
+def collate_meshes(meshes, pin_memory: Optional[bool] = None, vert_rgb: Optional[torch.Tensor] = None,
+                   narrow_faces: Optional[bool] = None) -> HostPackedMeshes:
     """Pack a list of meshes (objects with verts_list()/faces_list(), or (verts, faces) pairs) into one
     HostPackedMeshes with the library's multi-threaded gather (int64 faces are narrowed to int32).  Host only: usable
     as a DataLoader collate_fn.
     pin_memory=None (default): pinned when called in the main process with CUDA available, pageable inside a DataLoader
     worker -- a forked worker must not initialise CUDA (run_mvtn.py:110 uses num_workers=6), and its batch travels back
     through shared memory anyway; DataLoader(pin_memory=True) then pins it via HostPackedMeshes.pin_memory() in the main
-    process, and PackedMeshes.from_host_packed stages whatever is still pageable through a reusable pinned buffer."""
+    process, and PackedMeshes.from_host_packed stages whatever is still pageable through a reusable pinned buffer.
+    narrow_faces=None (default): the faces travel as uint16 when every mesh has at most 65536 vertices (3.8 -> 1.9 MB for 32
+    ModelNet-sized meshes), as int32 otherwise; True insists (ValueError when a mesh is too large), False keeps int32."""
     from .structures import unpack_mesh_list
     verts, faces = unpack_mesh_list(meshes)
     if len(verts) != len(faces):
@@ -403,8 +410,12 @@ def collate_meshes(meshes, pin_memory: Optional[bool] = None, vert_rgb: Optional
     if pin_memory is None:
         pin_memory = not _in_loader_worker()
     pin = bool(pin_memory) and not _in_loader_worker() and torch.cuda.is_available()
+    small = max(nv, default=0) <= 65536
+    if narrow_faces and not small:
+        raise ValueError("narrow_faces=True needs meshes of at most 65536 vertices")
+    narrow = small if narrow_faces is None else bool(narrow_faces)
     v_host = torch.empty((sum(nv), 3), dtype=torch.float32, pin_memory=pin)
-    f_host = torch.empty((sum(nf), 3), dtype=torch.int32, pin_memory=pin)
+    f_host = torch.empty((sum(nf), 3), dtype=torch.int32, pin_memory=pin and not narrow)
     if len(verts):
         import ctypes as C
         fdt = torch.int32 if all(f.dtype == torch.int32 for f in faces) else torch.int64
@@ -415,6 +426,10 @@ def collate_meshes(meshes, pin_memory: Optional[bool] = None, vert_rgb: Optional
         fp = (C.c_void_p * n)(*[t.data_ptr() for t in f_src]); fc = (C.c_int64 * n)(*[t.numel() for t in f_src])
         L.check(L.load().mvr_host_stage_meshes(vp, vc, fp, fc, n, 8 if fdt == torch.int64 else 4, v_host.data_ptr(),
                                                f_host.data_ptr(), None, None, None), "mvr_host_stage_meshes")
+    if narrow:      # (loader side, off the step) the low 16 bits of every id: out-of-range ids are clamped by mvr_mesh_prepare either way
+        f16 = torch.empty((sum(nf), 3), dtype=torch.int16, pin_memory=pin)
+        f16.copy_(f_host.clamp(0, 65535))      # int32 -> int16 keeps the low 16 bits (two's complement)
+        f_host = f16
     return HostPackedMeshes(v_host, f_host, nv, nf, vert_rgb=vert_rgb)
 
 
@@ -537,7 +552,7 @@ class PackedMeshes:
             hp = HostPackedMeshes.__new__(HostPackedMeshes)
             hp.__dict__.update(src.__dict__)
             v_st = _staging("hp_verts", device, src.verts.numel(), torch.float32).view(-1, 3)
-            f_st = _staging("hp_faces", device, src.faces.numel(), torch.int32).view(-1, 3)
+            f_st = _staging("hp_faces16" if src.faces.dtype == torch.int16 else "hp_faces", device, src.faces.numel(), src.faces.dtype).view(-1, 3)
             o_st = _staging("hp_offs", device, src.offs.numel(), torch.int32)
             v_st.copy_(src.verts); f_st.copy_(src.faces); o_st.copy_(src.offs)
             hp.verts, hp.faces, hp.offs = v_st, f_st, o_st
@@ -559,7 +574,7 @@ class PackedMeshes:
             with torch.cuda.stream(cs):
                 offs = hp.offs.to(device, non_blocking=True)
                 v_dev = torch.empty((hp.verts.shape[0], 3), dtype=torch.float32, device=device)
-                f_dev = torch.empty((hp.faces.shape[0], 3), dtype=torch.int32, device=device)
+                f_dev = torch.empty((hp.faces.shape[0], 3), dtype=hp.faces.dtype, device=device)
                 for c in range(chunks):
                     b0, b1 = bounds[c], bounds[c + 1]
                     v0, v1 = hp.vert_off_host[b0], hp.vert_off_host[b1]
@@ -659,11 +674,13 @@ class PackedMeshes:
         self.device = device
         self.per_vertex_rgb = vert_rgb is not None
         self.verts = _f32c(v_dev)
-        if f_dev.dtype not in (torch.int32, torch.int64):
+        if f_dev.dtype not in (torch.int32, torch.int64, torch.int16):      # (int16: uint16 ids of a narrowed host batch)
             f_dev = f_dev.to(torch.int64)
+        if f_dev.dtype == torch.int16 and self.max_verts > 65536:
+            raise ValueError("16-bit faces need meshes of at most 65536 vertices")
         self.faces = f_dev if f_dev.is_contiguous() else f_dev.contiguous()
         self.vert_off, self.face_off = offs[: self.B + 1], offs[self.B + 1:]
-        flags = L.FACES_I64 if self.faces.dtype == torch.int64 else 0
+        flags = L.FACES_I64 if self.faces.dtype == torch.int64 else (L.FACES_U16 if self.faces.dtype == torch.int16 else 0)
         rgb = None
         if vert_rgb is not None:
             rgb = _f32c(vert_rgb.to(device)).reshape(-1, 3)
@@ -698,7 +715,10 @@ class PackedMeshes:
         if getattr(self, "_faces_global", None) is None:
             counts = torch.tensor(self.num_faces, device=self.device)
             off = torch.repeat_interleave(self.vert_off[:-1].to(torch.int64), counts)
-            self._faces_global = self.faces.to(torch.int64) + off[:, None]
+            f = self.faces.to(torch.int64)
+            if self.faces.dtype == torch.int16:
+                f = f & 0xFFFF
+            self._faces_global = f + off[:, None]
         return self._faces_global
 
     def vertex_normals(self) -> torch.Tensor:

@@ -893,8 +893,12 @@ def test_mvrenderer_accepts_collated_host_batch(cuda_device):
     r = MVRenderer(3, image_size=48, pc_rendering=False, light_direction="fixed").to(dev).eval()
     az, el, di = (t.to(dev) for t in synth.learned_spherical_views(3, 3, 14))
     img_a, _ = r(ml, None, az, el, di)
-    img_b, _ = r(collate_meshes(ml), None, az, el, di)
+    hp = collate_meshes(ml)
+    assert hp.faces.dtype == torch.int16          # narrowed: every mesh has <= 65536 vertices (MVR_FACES_U16)
+    img_b, _ = r(hp, None, az, el, di)
     assert torch.equal(img_a, img_b)
+    img_b32, _ = r(collate_meshes(ml, narrow_faces=False), None, az, el, di)
+    assert torch.equal(img_a, img_b32)
     a2 = az.clone().requires_grad_()
     img_c, _ = r(collate_meshes(ml), None, a2, el, di)
     img_c.square().mean().backward()

@@ -224,8 +224,10 @@ def test_collate_meshes_packs_like_torch_cat():
     hp = collate_meshes([Meshes([v], [f]) for v, f in meshes], pin_memory=False)
     assert isinstance(hp, HostPackedMeshes) and len(hp) == 3
     assert hp.num_verts == [v.shape[0] for v, _ in meshes] and hp.num_faces == [f.shape[0] for _, f in meshes]
-    assert torch.equal(hp.verts, torch.cat([v for v, _ in meshes])) and hp.faces.dtype == torch.int32
-    assert torch.equal(hp.faces, torch.cat([f for _, f in meshes]).to(torch.int32))
+    assert torch.equal(hp.verts, torch.cat([v for v, _ in meshes])) and hp.faces.dtype == torch.int16      # (<= 65536 vertices: uint16 ids)
+    assert torch.equal(torch.cat(hp.faces_list()), torch.cat([f for _, f in meshes]).to(torch.int32))
+    hp32 = collate_meshes([Meshes([v], [f]) for v, f in meshes], pin_memory=False, narrow_faces=False)
+    assert hp32.faces.dtype == torch.int32 and torch.equal(hp32.faces, torch.cat([f for _, f in meshes]).to(torch.int32))
     assert all(torch.equal(a, b) for a, (b, _) in zip(hp.verts_list(), meshes))
     with pytest.raises(ValueError):
         HostPackedMeshes(hp.verts, hp.faces, [1, 2, 3], hp.num_faces)
@@ -331,9 +333,36 @@ def test_flag_constants_match_the_header():
     assert defs["ABI_VERSION"] == _lib.ABI_VERSION
     mirrored = [n for n in defs if hasattr(_lib, n) and n != "ABI_VERSION"]
     assert {"PERSPECTIVE_CORRECT", "CULL_BACKFACES", "COMPOSITE_ALPHA", "RGB_PER_ELEMENT", "FACES_I64", "IMAGES_BF16", "SCALE_IS_DIST",
-            "WS_KEYS_ARMED", "WS_REARM_KEYS", "WS_PROJECTED", "IDX_SPARSE", "FORWARD_TILED", "CLIP_BARYCENTRIC", "TEST_TINY_QUEUES", "NUM_COUNTERS"} <= set(mirrored)
+            "WS_KEYS_ARMED", "WS_REARM_KEYS", "WS_PROJECTED", "IDX_SPARSE", "FORWARD_TILED", "FACES_U16", "CLIP_BARYCENTRIC", "TEST_TINY_QUEUES", "NUM_COUNTERS"} <= set(mirrored)
     for n in mirrored:
         assert getattr(_lib, n) == defs[n], n
     flags = [defs[n] for n in mirrored if n not in ("NUM_COUNTERS", "CNT_STRADDLE", "CNT_BIG_FACES")]
     assert all(f & (f - 1) == 0 for f in flags)                   # single bits
     assert len(set(flags)) == len(flags)                          # no two flags share a bit
+
+
+def test_collate_meshes_narrows_faces_to_uint16_when_it_can():
+    """collate_meshes sends the faces as uint16 (in an int16 tensor) when every mesh has at most 65536 vertices -- ids above 32767
+    included -- and as int32 otherwise; faces_list() gives the ids back either way."""
+    import torch
+    from mvtn_b200 import Meshes, collate_meshes
+    g = torch.Generator().manual_seed(3)
+    big = torch.rand(40000, 3, generator=g)
+    fbig = torch.randint(0, 40000, (500, 3), generator=g)
+    fbig[0] = torch.tensor([39999, 32768, 32767])
+    small = torch.rand(50, 3, generator=g)
+    fsmall = torch.randint(0, 50, (80, 3), generator=g)
+    ml = [Meshes([big], [fbig]), Meshes([small], [fsmall])]
+    hp = collate_meshes(ml, pin_memory=False)
+    assert hp.faces.dtype == torch.int16 and hp.faces.shape == (580, 3)
+    got = hp.faces_list()
+    assert torch.equal(got[0].long(), fbig) and torch.equal(got[1].long(), fsmall)
+    hp32 = collate_meshes(ml, pin_memory=False, narrow_faces=False)
+    assert hp32.faces.dtype == torch.int32 and torch.equal(hp32.faces_list()[0].long(), fbig)
+    huge = torch.rand(70000, 3, generator=g)
+    fhuge = torch.randint(0, 70000, (10, 3), generator=g)
+    hp2 = collate_meshes([Meshes([huge], [fhuge])], pin_memory=False)
+    assert hp2.faces.dtype == torch.int32 and torch.equal(hp2.faces_list()[0].long(), fhuge)
+    import pytest
+    with pytest.raises(ValueError):
+        collate_meshes([Meshes([huge], [fhuge])], pin_memory=False, narrow_faces=True)
