@@ -1,7 +1,7 @@
 """Tiny forward + backward of both paths (mesh: scatter + shade, strip and tile backward, K = 1 and 2, a clipped view, the
 tile-binned forward with its TMA bulk copies, vertex gradients with the warp-aggregated scatter, the soft shaders, a collated batch
 rendered in h2d_chunks groups; points: tiled and generic K, the clustered binning (> 4096 points: DSMEM counters), point / colour
-gradients) for compute-sanitizer:   compute-sanitizer --tool memcheck|racecheck python scripts/sanitize_small.py"""
+gradients; the view regulariser) for compute-sanitizer:   compute-sanitizer --tool memcheck|racecheck python scripts/sanitize_small.py"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -65,4 +65,12 @@ a, e, d = (t.to(dev).requires_grad_() for t in synth.learned_spherical_views(4, 
 img, _ = r(collate_meshes(ml), None, a, e, d)
 img.backward(torch.ones_like(img))
 torch.cuda.synchronize()
-print("mesh h2d_chunks=2", float(img.detach().sum()), float(a.grad.abs().sum()))
+print("mesh h2d_chunks=2 (uint16 faces)", float(img.detach().sum()), float(a.grad.abs().sum()), collate_meshes(ml).faces.dtype)
+from mvtn_b200 import regularize_rendered_views
+for dt, S in ((torch.float32, 48), (torch.bfloat16, 48), (torch.float32, 30)):      # the view regulariser: gather + adjoint (quads / scalar rows)
+    x = torch.rand(2, 3, 3, S, S, device=dev).to(dt).requires_grad_()
+    torch.manual_seed(4)
+    y = regularize_rendered_views(x, 0.4, True, 0.3)
+    y.backward(torch.ones_like(y))
+    torch.cuda.synchronize()
+    print("regularize", dt, S, float(y.float().sum()), float(x.grad.float().abs().sum()))
