@@ -9,7 +9,7 @@ Operator surface (mirrors what renderer.py reaches in PyTorch3D):
 """
 import functools
 import math
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 

@@ -4,7 +4,7 @@ import os, sys, time, statistics, collections
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from mvtn_b200 import MVRenderer, Meshes, ops, synth, collate_meshes
+from mvtn_b200 import MVRenderer, Meshes, synth, collate_meshes
 from mvtn_b200 import _lib as L
 
 dev = torch.device("cuda:0")

@@ -1,7 +1,7 @@
 """Regenerates profiles/r3_sass_summary.txt: per-kernel counts of the SASS mnemonics that show which hardware path a kernel
 uses (TMA bulk copies, mbarriers, cp.async, cluster barriers, match, atomics, IEEE-division fast paths), from the shipped
 libmvr_b200.so.   python scripts/sass_summary.py [> profiles/r3_sass_summary.txt]"""
-import os, re, subprocess, sys
+import os, re, subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "mvtn_b200", "libmvr_b200.so")

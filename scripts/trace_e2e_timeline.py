@@ -1,10 +1,10 @@
 """GPU (CUDA events) and host (perf_counter) timeline of the C-ABI calls of one end-to-end mesh step, for h2d_chunks = 1 and 2
 (profiles/r3y_h2d_chunks.txt).  usage: python scripts/trace_e2e_timeline.py"""
-import os, sys, statistics, time
+import os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from mvtn_b200 import MVRenderer, Meshes, synth, collate_meshes, ops
+from mvtn_b200 import MVRenderer, Meshes, synth, collate_meshes
 from mvtn_b200 import _lib as L
 dev = torch.device("cuda:0")
 B, M, S, NF = 32, 12, 224, 10000
