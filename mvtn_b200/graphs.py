@@ -57,19 +57,24 @@ def graphed_points_render(points: torch.Tensor, rgb: torch.Tensor, M: int, radiu
 
 
 def graphed_mesh_render(geom: "ops.PackedMeshes", M: int, light: torch.Tensor, obj_rgb, bg: torch.Tensor, image_size,
-                        sample_views: Sequence[torch.Tensor], refresh_geometry: bool = True, **render_kwargs):
+                        sample_views: Sequence[torch.Tensor], refresh_geometry: bool = True, return_cameras: bool = False,
+                        **render_kwargs):
     """Capture [mvr_mesh_prepare] + look_at + mesh rasterization + Phong shading (and their backward) for a packed
     batch whose topology (counts, faces) is fixed.  With refresh_geometry=True the vertex positions may be updated in
     place (geom.verts.copy_(...)) between replays: packing and vertex normals are part of the graph.
-    Returns step(azim, elev, dist) -> images (B*M, 3, H, W).  `light` (1,3) or None for the camera-relative light."""
+    Returns step(azim, elev, dist) -> images (B*M, 3, H, W).  `light` (1,3) or None for the camera-relative light.
+    return_cameras=True -> (images, cams, invalid, pix_to_face) as graphed_points_render does (cams: the flat R | T | C buffer;
+    everything lives in captured buffers)."""
     geom.finish()
 
     def fn(az, el, di):
         if refresh_geometry:
             geom.refresh()
-        R, T, C, _bad = ops._LookAt.apply(az.reshape(-1), el.reshape(-1), di.reshape(-1))
+        R, T, C, bad = ops._LookAt.apply(az.reshape(-1), el.reshape(-1), di.reshape(-1))
         lt = C.detach() if light is None else light
-        img, _ = ops.render_meshes(geom, M, R, T, C, lt, obj_rgb, bg, image_size, **render_kwargs)
+        img, frag = ops.render_meshes(geom, M, R, T, C, lt, obj_rgb, bg, image_size, **render_kwargs)
+        if return_cameras:
+            return img, torch.cat([R.reshape(-1), T.reshape(-1), C.reshape(-1)]), bad, frag["pix_to_face"]
         return img
 
     return torch.cuda.make_graphed_callables(fn, _views_like(sample_views))

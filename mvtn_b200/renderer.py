@@ -150,6 +150,14 @@ class MVRenderer(nn.Module):
             MVTN's sizes: the step's first 0.3 ms are bound by the host reaching the rasterizer launch, not by the 0.18 ms copy,
             and every group adds launches (1.09 -> 1.27 ms per end-to-end step at 32 x 12 views with k = 2;
             profiles/r3y_h2d_chunks.txt) -- kept for batches whose copy does dominate (large meshes, slow links).
+        cuda_graph (mesh path): only when True, and only for collated host batches (collate_meshes) rendered with the hard Phong
+            shader: the device part of the forward and of the backward -- mvr_mesh_prepare, look_at, rasterizer, shader -- is captured
+            once per batch SHAPE (the per-mesh vertex / face counts, views-require-grad) and replayed; a batch of another shape is
+            captured too (the four most recent shapes are kept), so this is for loops over equal-sized batches -- small per-GPU
+            batches of a strong-scaling run, evaluation over a fixed set -- where the step is launch- and host-bound (end to end from a
+            collated batch: 0.57 -> 0.43 ms at 1 mesh x 12 views, 0.53 -> 0.46 at 4, even at 8, SLOWER from 16 on -- the copy of the
+            images out of the captured buffer costs more than the launches saved; profiles/r3z_mesh_graph_mode.txt); ragged
+            training batches should leave it off.  Same static-buffer rules as the point path below.
         cuda_graph: None (default) = automatic -- point steps of at most GRAPH_AUTO_MAX_VIEWS views (BASELINE configs[0]: one
             cloud x 12 views, a step that is pure launch latency) are replayed from CUDA graphs, larger ones run eagerly;
             True / False force it.  Point path only -- the device part of a step (look_at, binning, tile rasterizer + compositor, and their
@@ -183,6 +191,7 @@ class MVRenderer(nn.Module):
         self.copy_stream = copy_stream
         self.cuda_graph = cuda_graph      # None = auto: replay small (launch-bound) point steps from CUDA graphs
         self._point_graphs = {}
+        self._mesh_graphs = {}
         self.nb_views = nb_views
         self.image_size = image_size
         self.pc_rendering = pc_rendering
@@ -261,6 +270,12 @@ class MVRenderer(nn.Module):
         # deferred: the meshes are staged (gather + H2D + mvr_mesh_prepare) inside render(), AFTER the camera kernel and
         # the constants below have been enqueued, so that the rasterizer launch follows the geometry with as little host
         # work in between as possible (the GPU would idle through it)
+        if (self.cuda_graph is True and isinstance(meshes, ops.HostPackedMeshes) and self.shader == "hard_phong" and torch.is_grad_enabled()
+                and meshes.vert_rgb is None and torch.as_tensor(color).numel() == 3 and len(meshes) == azim.shape[0] and len(meshes) > 0
+                and not torch.cuda.is_current_stream_capturing()):
+            out = self._render_meshes_graphed(meshes, color, azim, elev, dist, lights, background_color, device)
+            if out is not None:
+                return out
         geom = self._packed(meshes, color, device)
         if geom.B != azim.shape[0]:
             raise ValueError(f"{geom.B} meshes but azim has batch {azim.shape[0]}")
@@ -356,6 +371,73 @@ class MVRenderer(nn.Module):
         self.last_fragments = frag
         rendered_images = images.view(pts.shape[0], self.nb_views, 3, self.image_size, self.image_size)
         return rendered_images, FoVOrthographicCameras(R, T, C, znear=0.01)
+
+    def _render_meshes_graphed(self, hp, color, azim, elev, dist, lights, background_color, device):
+        """CUDA-graph replay of the mesh step for a collated host batch whose shape has been seen before (see `cuda_graph` in the
+        class docstring): vertices and faces are copied straight into the captured geometry buffers.  Returns None when the
+        eager path must take over (invalid rotations, a replay still outstanding, a capture that failed)."""
+        from . import graphs
+        az, el, di = self._views(azim, elev, dist, device)
+        grads = (az.requires_grad, el.requires_grad, di.requires_grad)
+        key = (tuple(hp.num_verts), tuple(hp.num_faces), hp.faces.dtype, device.index, grads, lights is None)
+        st = self._mesh_graphs.get(key)
+        if st is not None and (st["busy"] or st.get("failed")):
+            return None
+        bg = _device_vec(background_color, device)
+        obj = _device_vec(color, device)
+        light = None if lights is None else _device_vec(lights, device)
+        if st is None:
+            import gc
+            gc.collect()
+            torch.cuda.synchronize(device)
+            geom = ops.PackedMeshes.from_host_packed(hp, device)
+            static_obj, static_bg = obj.clone(), bg.clone()
+            static_light = None if light is None else light.clone().reshape(1, 3)
+            sample = tuple(t.detach().clone().requires_grad_(g) for t, g in zip((az, el, di), grads))
+            try:
+                step = graphs.graphed_mesh_render(geom, self.nb_views, static_light, static_obj, static_bg, self.image_size, sample,
+                                                  refresh_geometry=True, return_cameras=True, faces_per_pixel=self.faces_per_pixel,
+                                                  cull_backfaces=self.cull_backfaces, perspective_correct=self.perspective_correct,
+                                                  normalize=self.normalize, out_dtype=self.out_dtype)
+            except RuntimeError as e:         # a capture invalidated from outside (another thread's CUDA call): stay eager
+                import warnings
+                warnings.warn(f"MVRenderer: CUDA-graph capture of the mesh step failed ({e}); this shape runs eagerly")
+                self._mesh_graphs[key] = {"failed": True, "busy": False}
+                return None
+            if len(self._mesh_graphs) >= 4:   # a loop over ragged batches must not hoard captured buffers
+                self._mesh_graphs.pop(next(iter(self._mesh_graphs)))
+            st = self._mesh_graphs[key] = {"geom": geom, "obj": static_obj, "bg": static_bg, "light": static_light, "step": step,
+                                           "obj_src": obj, "bg_src": bg, "light_src": light, "busy": False}
+        else:
+            geom = st["geom"]
+            geom.verts.copy_(hp.verts, non_blocking=True)
+            geom.faces.copy_(hp.faces, non_blocking=True)
+            if st["obj_src"] is not obj:
+                st["obj"].copy_(obj); st["obj_src"] = obj
+            if st["bg_src"] is not bg:
+                st["bg"].copy_(bg); st["bg_src"] = bg
+            if light is not None and st["light_src"] is not light:      # (a fresh random light every training step lands here)
+                st["light"].copy_(light.reshape(1, 3)); st["light_src"] = light
+        images, cams, bad, p2f = st["step"](az, el, di)
+        invalid = _flag_reader(bad)
+        n = az.numel()
+        cams = cams.detach().clone()
+        if invalid() != 0:
+            return None
+        self.last_fragments = {"pix_to_face": p2f}      # (a view of the captured buffer: valid until the next replay of this shape)
+        R, T, C = cams[: 9 * n].view(n, 3, 3), cams[9 * n: 12 * n].view(n, 3), cams[12 * n:].view(n, 3)
+        out = images.clone()                             # the caller's images survive the next replay (see _render_points_graphed)
+        if out.requires_grad:
+            import weakref
+            st["busy"] = True
+
+            def release(*_a, _st=st):
+                _st["busy"] = False
+
+            out.register_hook(lambda g, _r=release: (_r(), g)[1])
+            weakref.finalize(out, release)
+        H, W = ops._hw(self.image_size)
+        return out.view(len(hp), self.nb_views, 3, H, W), FoVPerspectiveCameras(R, T, C)
 
     def _render_points_graphed(self, points, rgb, az, el, di, bg, device):
         """CUDA-graph replay of the point step (see `cuda_graph` in the class docstring): `points` (host or device) is

@@ -1340,3 +1340,59 @@ def test_mvrenderer_points_cuda_graph_mode_matches_eager(cuda_device):
     torch.manual_seed(0)
     img, cams = graph(None, synth.make_clouds(2, 700, 1), *[t.to(dev) for t in views])
     assert img.shape == (2, M, 3, S, S) and torch.isfinite(img).all()
+
+
+def test_mvrenderer_mesh_cuda_graph_mode_matches_eager(cuda_device):
+    """MVRenderer(cuda_graph=True) on the mesh path: collated host batches of a repeated SHAPE (per-mesh counts) are rendered by
+    replaying the captured prepare + look_at + rasterizer + shader graphs, new vertices / faces / views / light copied into the
+    captured buffers -- images, cameras, fragments and view gradients equal the eager renderer's bit for bit; a second shape gets
+    its own capture; an outstanding forward and a python list of meshes take the eager path."""
+    from mvtn_b200 import collate_meshes
+    dev = cuda_device
+    M, S = 3, 56
+    kw = dict(image_size=S, pc_rendering=False, light_direction="relative")
+    eager = MVRenderer(M, cuda_graph=False, **kw).to(dev).train()
+    graph = MVRenderer(M, cuda_graph=True, **kw).to(dev).train()
+
+    def batch(counts, seed):
+        out = []
+        for i, nf in enumerate(counts):
+            v, f = synth.make_mesh(nf, 300 + i)                        # same topology / counts for every seed ...
+            g = torch.Generator().manual_seed(seed * 10 + i)
+            v = v * (1.0 + 0.05 * torch.randn(v.shape, generator=g))    # ... new vertex positions
+            out.append(Meshes([v], [f.flip(1) if seed % 2 else f]))     # ... and (every other batch) re-wound faces
+        return out
+
+    def run(r, ml, views, collate=True):
+        a, e, d = (t.to(dev).clone().requires_grad_() for t in views)
+        img, cams = r(collate_meshes(ml) if collate else ml, None, a, e, d)
+        p2f = r.last_fragments["pix_to_face"].clone()
+        cot = torch.linspace(-1, 1, img.numel(), device=dev).view_as(img)
+        img.backward(cot)
+        return img.detach().clone(), cams.R.detach().clone(), cams.T.detach().clone(), p2f, a.grad.clone(), e.grad.clone(), d.grad.clone()
+
+    for counts, seeds in (((300, 90, 700), (1, 2, 3)), ((120, 500), (4, 5))):
+        for sd in seeds:
+            ml = batch(counts, sd)
+            views = synth.learned_spherical_views(len(counts), M, 40 + sd)
+            got, want = run(graph, ml, views), run(eager, ml, views)
+            for k, (x, y) in enumerate(zip(got, want)):
+                assert torch.equal(x, y), (counts, sd, k)
+    assert len(graph._mesh_graphs) == 2 and not any(s.get("failed") for s in graph._mesh_graphs.values())
+    # python lists (no fixed host layout to copy from) stay eager
+    ml = batch((300, 90, 700), 7)
+    views = synth.learned_spherical_views(3, M, 50)
+    got, want = run(graph, ml, views, collate=False), run(eager, ml, views, collate=False)
+    assert all(torch.equal(x, y) for x, y in zip(got, want)) and len(graph._mesh_graphs) == 2
+    # one outstanding forward per captured backward
+    a1, e1, d1 = (t.to(dev).clone().requires_grad_() for t in views)
+    img1, _ = graph(collate_meshes(ml), None, a1, e1, d1)
+    st = graph._mesh_graphs[next(k for k in graph._mesh_graphs if len(k[0]) == 3)]
+    assert st["busy"]
+    v2 = synth.learned_spherical_views(3, M, 51)
+    img2, _ = graph(collate_meshes(ml), None, *[t.to(dev) for t in v2])      # eager: must not touch what img1's backward reads
+    img1.backward(torch.linspace(-1, 1, img1.numel(), device=dev).view_as(img1))
+    assert not st["busy"]
+    want = run(eager, ml, views)
+    assert torch.equal(a1.grad, want[4]) and torch.equal(img1.detach(), want[0])
+    assert torch.equal(img2.detach(), run(eager, ml, v2)[0])
