@@ -144,13 +144,13 @@ __global__ void geom_get_normals_kernel(const float4* __restrict__ normals4, int
 constexpr int SC_REC_WORDS = 13;      // x0 y0 z0 x1 y1 z1 x2 y2 z2 fid zmin_bits | rect_xy rect_wh (big faces only)
 constexpr int SC_QCAP = 3072;         // candidates per round (256 faces x ~4.6 inside pixels at C2)
 
-template <int MINB, bool SOFT>
-__global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const MeshParams p) {
-  __shared__ float s_rec[SC_REC_WORDS][MVR_THREADS];  // SoA face records of the current round
-  __shared__ int s_q[SC_QCAP];                         // candidates of the round: slot | x << 8 | y << 20
-  __shared__ int s_big[MVR_THREADS];
+template <int MINB, bool SOFT, int NT = MVR_THREADS>      // NT: threads (= faces per round) of a CTA
+__global__ void __launch_bounds__(NT, MINB) mesh_scatter_kernel(const MeshParams p) {
+  __shared__ float s_rec[SC_REC_WORDS][NT];  // SoA face records of the current round
+  __shared__ int s_q[SC_QCAP * NT / 256];                         // candidates of the round: slot | x << 8 | y << 20
+  __shared__ int s_big[NT];
   __shared__ int s_cnt2[2][2];                         // per round parity: [0] candidates, [1] big faces
-  __shared__ __align__(16) int4 s_faces[2][MVR_THREADS];      // face records of two rounds: TMA bulk-copy destinations
+  __shared__ __align__(16) int4 s_faces[2][NT];      // face records of two rounds: TMA bulk-copy destinations
   __shared__ __align__(8) unsigned long long s_mbar[2];
   extern __shared__ float s_tab[];                     // pixel centres: xf[W], yf[H]
   const float* s_xf = s_tab;
@@ -177,12 +177,12 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
   const unsigned int mbar_a = smem_addr_pinned(&s_mbar[0]);
   const unsigned int fstage_a = smem_addr_pinned(&s_faces[0][0]);
   auto issue_faces = [&](int r) {      // one thread; 16-byte records: source aligned, size a multiple of 16
-    const int start = fbeg + r * MVR_THREADS;
-    const unsigned int bytes = (unsigned int)(min(MVR_THREADS, fend - start) * 16);
+    const int start = fbeg + r * NT;
+    const unsigned int bytes = (unsigned int)(min(NT, fend - start) * 16);
     const unsigned int mb = mbar_a + 8u * (r & 1);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     fstage_a + 16u * MVR_THREADS * (r & 1)),
+                     fstage_a + 16u * NT * (r & 1)),
                  "l"(p.faces4 + f0 + start), "r"(bytes), "r"(mb)
                  : "memory");
   };
@@ -192,15 +192,15 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     issue_faces(0);
   }
-  for (int i = tid; i < p.W + p.H; i += MVR_THREADS) s_tab[i] = __ldg(p.tab + i);
+  for (int i = tid; i < p.W + p.H; i += NT) s_tab[i] = __ldg(p.tab + i);
   if (tid < 4) (&s_cnt2[0][0])[tid] = 0;
   __syncthreads();
   const unsigned int q_a = smem_addr_pinned(&s_q[0]);
 
   int n_straddle = 0, n_big = 0;
-  for (int rbeg = fbeg, rpar = 0, round = 0; rbeg < fend; rbeg += MVR_THREADS, rpar ^= 1, ++round) {
+  for (int rbeg = fbeg, rpar = 0, round = 0; rbeg < fend; rbeg += NT, rpar ^= 1, ++round) {
     int* s_cnt = s_cnt2[rpar];
-    if (tid == 0 && rbeg + MVR_THREADS < fend) issue_faces(round + 1);      // its stage was released by the barrier that ended round - 1
+    if (tid == 0 && rbeg + NT < fend) issue_faces(round + 1);      // its stage was released by the barrier that ended round - 1
     {
       const unsigned int mb = mbar_a + 8u * (round & 1), parity = (unsigned int)((round >> 1) & 1);
       asm volatile(
@@ -294,11 +294,11 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
         cd_next = s_q[tid];
         cur_next = __ldcg(keys + (size_t)((cd_next >> 20) & 4095) * p.W + ((cd_next >> 8) & 4095));
       }
-      for (int j = tid; j < total_c; j += MVR_THREADS) {
+      for (int j = tid; j < total_c; j += NT) {
         const int cd = cd_next;
         const unsigned long long cur = cur_next;
-        if (j + MVR_THREADS < total_c) {
-          cd_next = s_q[j + MVR_THREADS];
+        if (j + NT < total_c) {
+          cd_next = s_q[j + NT];
           cur_next = __ldcg(keys + (size_t)((cd_next >> 20) & 4095) * p.W + ((cd_next >> 8) & 4095));
         }
         const int slot = cd & 255, xx = (cd >> 8) & 4095, yy = (cd >> 20) & 4095;
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
           int cxl, cxh, cyl, cyh;
           if (!face_pixel_bbox(sf, p, s_xf, s_yf, cxl, cxh, cyl, cyh)) continue;
           const FaceEdges sfe = face_edges(sf);
-          for (int yy = cyl + warp; yy <= cyh; yy += NWARPS)
+          for (int yy = cyl + warp; yy <= cyh; yy += (NT / 32))
             for (int xx = cxl + lane; xx <= cxh; xx += 32)
               resolve_pixel<SOFT>(sf, sfe, bfid, 0u, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
                             prev ? prev + (size_t)yy * p.W + xx : nullptr, sm);
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_scatter_kernel(const M
       const int rxy = __float_as_int(s_rec[11][slot]), rwh = __float_as_int(s_rec[12][slot]);
       const int bxl = rxy & 0xffff, byl = rxy >> 16, bbw = rwh & 0xffff, bbh = rwh >> 16;
       const unsigned int zmin_bits = __float_as_uint(s_rec[10][slot]);
-      for (int y = warp; y < bbh; y += NWARPS)
+      for (int y = warp; y < bbh; y += (NT / 32))
         for (int x = lane; x < bbw; x += 32) {
           const int xx = bxl + x, yy = byl + y;
           resolve_pixel<SOFT>(fc, fe, bfid, zmin_bits, persp, s_xf[xx], s_yf[yy], keys + (size_t)yy * p.W + xx,
@@ -549,6 +549,14 @@ static int scatter_minb() {
   return v;
 }
 
+// Threads (= faces per round) of a scatter CTA: 256 (4 CTAs per SM), or 128 (8 per SM) for large meshes -- twice as many
+// independent CTAs to cover each other's two barriers per round: 706 -> 663 us at 100 k faces x 160 views (r3z), but 340 -> 358 us at
+// 10 k faces x 384 views, where the rounds are too few to fill.  MVR_SCATTER_NT=128|256 overrides (profiling).
+static int scatter_nt(int max_faces) {
+  static const int v = [] { const char* e = getenv("MVR_SCATTER_NT"); const int x = e ? atoi(e) : 0; return (x == 128 || x == 256) ? x : 0; }();
+  return v ? v : (max_faces > 32768 ? 128 : 256);
+}
+
 static int shade_minb() {
   static const int v = [] { const char* e = getenv("MVR_SHADE_MINB"); const int x = e ? atoi(e) : 4; return x == 3 ? 3 : 4; }();
   return v;
@@ -657,6 +665,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
     if (chunks_per_view > 0) {
       const dim3 scatter_grid((unsigned)chunks_per_view, (unsigned)M, (unsigned)B);
       if (soft_raster) MVR_LAUNCH((mesh_scatter_kernel<3, true>), scatter_grid, MVR_THREADS, tab_smem, st, p);
+      else if (scatter_nt(max_faces) == 128) { MeshParams q = p; q.wcap = p.wcap < SC_QCAP ? p.wcap : SC_QCAP / 2; MVR_LAUNCH((mesh_scatter_kernel<8, false, 128>), scatter_grid, 128, tab_smem, st, q); }
       else if (scatter_minb() == 3) MVR_LAUNCH((mesh_scatter_kernel<3, false>), scatter_grid, MVR_THREADS, tab_smem, st, p);
       else MVR_LAUNCH((mesh_scatter_kernel<4, false>), scatter_grid, MVR_THREADS, tab_smem, st, p);
       rc = check_launch("mesh_scatter_kernel");
