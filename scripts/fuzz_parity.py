@@ -23,10 +23,21 @@ dev = torch.device("cuda:0")
 # soup of slivers is far worse conditioned than anything the renderer is fed, and the sweep should say by how much
 _rel, _seen = T.rel, []
 def _rec(a, b, floor=1e-6):
-    # An analytically vanishing gradient -- every visible face unlit under one object colour, one point colour under the norm
-    # compositor: the image is a constant -- leaves rounding noise on both sides (~1e-7 of per-pixel terms of size 1..100): a tensor
-    # whose reference is smaller than 0.5 everywhere is checked against 0.5 instead of against itself.
-    r = _rel(a, b, max(floor, 0.5)); _seen.append(r); return r
+    # Recorded as (largest error, largest reference entry) per tensor and judged per CASE (_worst below): a tensor is compared with its
+    # own largest entry, but never with less than 0.5, nor with less than 1e-3 of the largest gradient entry of the case.  Two kinds of
+    # tensors would otherwise compare rounding noise with rounding noise: an analytically vanishing gradient (every visible face unlit
+    # under one object colour, one point colour under the norm compositor: the image is a constant), and a sum that happens to cancel
+    # (d loss / d scale = 0.56 next to d loss / d T = 1970 in the same view: 3e-4 of absolute error is 1.6e-7 of its terms).
+    a64 = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, np.float64); b64 = np.asarray(b, np.float64)
+    _seen.append((float(np.abs(a64 - b64).max()), float(np.abs(b64).max())))
+    return 0.0
+
+
+def _worst():
+    scale = max((m for _, m in _seen), default=0.0)
+    return max((e / max(m, 0.5, 1e-3 * scale) for e, m in _seen), default=0.0)
+
+
 T.rel = _rec
 T.GRAD_RTOL = T.POINT_GRAD_RTOL = float("inf")
 T.IMG_ATOL = float("inf")      # (checked below, so that a failure says by how much and where)
@@ -127,8 +138,8 @@ for case in (range(seed0, seed0 + n_cases) if __name__ == "__main__" else ()):
             res = T.run_mesh(orc, dev, cfg, backward=True, extra_flags=flags)
             d = np.abs(res["img"].detach().cpu().numpy() - res["o"]["images"])
             hl = ""
-            if 1e-5 < d.max() <= 1.5e-5 and int((d > 1e-5).sum()) <= 3 and res["o"]["images"][d > 1e-5].min() > 0.9:
-                # one saturated highlight pixel: alpha^64 multiplies the rounding differences of two fp32 evaluation orders by 64 --
+            if 1e-5 < d.max() <= 1.5e-5 and int((d > 1e-5).sum()) <= 6 and res["o"]["images"][d > 1e-5].min() > 0.9:
+                # one or two saturated highlight pixels: alpha^64 multiplies the rounding differences of two fp32 evaluation orders by 64 --
                 # the oracle itself is 6e-6 away from an fp64 evaluation there; counted, not failed
                 hl = f" [highlight pixel {d.max():.3e}]"; n_highlight += 1
             elif d.max() > 1e-5:
@@ -153,7 +164,7 @@ for case in (range(seed0, seed0 + n_cases) if __name__ == "__main__" else ()):
             if d.max() > 1e-5:
                 raise AssertionError(f"image error {d.max():.3e}, {int((d > 1e-5).sum())} values over 1e-5")
             what = f"points B={B} M={M} Np={Np} H={H} K={K} r={radius} {cfg['mode']} per_point={cfg['per_point']}"
-        worst = max(_seen) if _seen else 0.0
+        worst = _worst()
         _seen.clear()
         note = ""
         if worst > GRAD_BAR:
@@ -173,4 +184,4 @@ for case in (range(seed0, seed0 + n_cases) if __name__ == "__main__" else ()):
               + ", ".join(f"{k}={v}" for k, v in cfg.items() if k not in ("meshes", "views")) + f" views={[t.tolist() for t in cfg['views']]}", flush=True)
         fails.append(case); _seen.clear()
 if __name__ == "__main__":
-    print(f"{n_cases - len(fails)} / {n_cases} cases passed ({n_highlight} with one highlight pixel between 1e-5 and 1.5e-5); failing seeds: {fails}")
+    print(f"{n_cases - len(fails)} / {n_cases} cases passed ({n_highlight} with one or two highlight pixels between 1e-5 and 1.5e-5); failing seeds: {fails}")
