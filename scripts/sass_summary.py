@@ -5,7 +5,7 @@ import os, re, subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "mvtn_b200", "libmvr_b200.so")
-KERNELS = ("mesh_shade_kernelILb0ELi4ELi4ELb0", "mesh_scatter_kernelILi4ELb0", "mesh_tile_kernelILb0ELi4ELb0", "mesh_bin_kernelILb0",
+KERNELS = ("mesh_shade_kernelILb0ELi4ELi4ELb0", "mesh_scatter_kernelILi4ELb0ELi256", "mesh_scatter_kernelILi8ELb0ELi128", "mesh_tile_kernelILb0ELi4ELb0", "mesh_bin_kernelILb0",
            "mesh_backward_kernel_stripILi3ELb0ELb0", "mesh_backward_kernel_stripILi2ELb0ELb1", "points_tile_kernelILi4E",
            "points_bin_kernel_fused", "points_backward_kernelILi4ELb0ELb0", "images_regularize_kernelILb1", "images_regularize_backward_rows_kernelILb1",
            "mesh_soft_blend_kernel", "mesh_soft_backward_kernel")
