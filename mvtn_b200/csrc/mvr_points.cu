@@ -1062,7 +1062,9 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
   if (w.tiled) {
     if (bin_fused) {
       static const int cs_knob = [] { const char* e = getenv("MVR_BIN_CLUSTER"); return e ? atoi(e) : 0; }();      // profiling knob: 1 / 2 / 4 / 8
-      const int cs = (cs_knob == 1 || cs_knob == 2 || cs_knob == 4 || cs_knob == 8) ? cs_knob : (Np > 4096 ? 4 : 1);
+      // a cluster of 4 CTAs per view for large clouds, and whenever there are fewer views than SMs (configs[0]: 12 views -- one CTA per
+      // view leaves 136 SMs idle while 12 CTAs walk 2048 points each: 24 -> 16 us, a fifth of that graph-replayed step)
+      const int cs = (cs_knob == 1 || cs_knob == 2 || cs_knob == 4 || cs_knob == 8) ? cs_knob : ((Np > 4096 || (N < 148 && Np >= 512)) ? 4 : 1);
       if (cs == 1) {
         MVR_LAUNCH(points_bin_kernel_fused, dim3((unsigned)M, (unsigned)B), MVR_THREADS, ((size_t)W + H) * sizeof(float), st, p, (float*)(wb + w.tab), 1);
       } else {      // thread-block cluster of cs CTAs per view (distributed shared memory)

@@ -1,4 +1,4 @@
-"""Per-kernel device times of the resident point step.  usage: python scripts/points_times.py [c3|c5]"""
+"""Per-kernel device times of the resident point step.  usage: python scripts/points_times.py [c1|c3|c5]"""
 import ctypes, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -7,7 +7,7 @@ from mvtn_b200 import ops, synth
 from mvtn_b200 import _lib as L
 dev = torch.device("cuda:0")
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
-B, M, S, NP, K = (8, 20, 400, 16384, 4) if cfg == "c5" else (32, 12, 224, 2048, 4)
+B, M, S, NP, K = (8, 20, 400, 16384, 4) if cfg == "c5" else ((1, 12, 224, 2048, 1) if cfg == "c1" else (32, 12, 224, 2048, 4))
 pts = synth.make_clouds(B, NP, 77).to(dev)
 az, el, di = (t.to(dev) for t in (synth.spherical_views(B, M) if cfg == "c5" else synth.learned_spherical_views(B, M, 5)))
 cot = torch.randn(B * M, 3, S, S, device=dev) / (3 * S * S)
