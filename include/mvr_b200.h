@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MVR_ABI_VERSION 7
+#define MVR_ABI_VERSION 8
 
 /* flags */
 #define MVR_PERSPECTIVE_CORRECT 1  /* [upstream] RasterizationSettings.perspective_correct (FoV persp.: True) */
@@ -257,6 +257,16 @@ int mvr_points_backward(const float* points, const float* rgb, int B, int Np, in
                         int flags, const float* out_mean_std, const int* idx, const uint32_t* hit_mask,
                         const void* grad_images, float* gR, float* gT, float* g_inv_dist, float* grad_points, float* grad_rgb,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* The same for a caller whose cameras came from mvr_look_at_forward(azim, elev, dist) and whose clouds are scaled by 1 / dist
+ * (MVR_SCALE_IS_DIST, the scale array = dist: renderer.py:122-123,142): the last kernel also applies the camera backward
+ * (mvr_look_at_backward) and the scale term, so the chain ends in g_azim, g_elev, g_dist (n) with one launch and one call less
+ * (SURVEY 8f N4).  gR / gT: optional copies of the camera gradients (NULL: not stored). */
+int mvr_points_backward_angles(const float* points, const float* rgb, int B, int Np, int M, const float* R,
+                               const float* T, const float* azim, const float* elev, const float* dist, double radius,
+                               int H, int W, int K, int flags, const float* out_mean_std, const int* idx,
+                               const uint32_t* hit_mask, const void* grad_images, float* g_azim, float* g_elev,
+                               float* g_dist, float* gR, float* gT, float* grad_points, float* grad_rgb, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

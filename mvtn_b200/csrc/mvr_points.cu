@@ -19,7 +19,7 @@
 #include <cooperative_groups.h>
 #include <cstdlib>
 
-#include "mvr_common.cuh"
+#include "mvr_camera.cuh"
 
 namespace mvr {
 
@@ -938,6 +938,36 @@ __global__ void points_backward_reduce_kernel(const float* __restrict__ partials
   else if (lane < 16 && grad_rgb_uniform) atomicAdd(grad_rgb_uniform + (lane - 13), s);      // N terms per channel
 }
 
+// The same reduction with the camera backward of the view behind it: (dR, dT) -> (d azim, d elev, d dist) by look_at_backward_view,
+// plus the cloud-scale term of d dist -- the path MVRenderer takes (angles in, images out) then ends its backward with ONE launch
+// instead of a reduction and a camera kernel, and the host with one call instead of two (the point step is bound by the host).
+// gR / gT: optional copies of the camera gradients (NULL: not stored).  `dist` is the scale array (MVR_SCALE_IS_DIST).
+__global__ void points_backward_reduce_angles_kernel(const float* __restrict__ partials, int N, int n_parts, const float* __restrict__ azim,
+                                                     const float* __restrict__ elev, const float* __restrict__ dist, float* __restrict__ gR,
+                                                     float* __restrict__ gT, float* __restrict__ g_azim, float* __restrict__ g_elev,
+                                                     float* __restrict__ g_dist, float* __restrict__ grad_rgb_uniform) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const int v = lane & 15, par = lane >> 4;
+  float s = 0.f;
+  for (int t = par; t < n_parts; t += 2) s += partials[((size_t)n * n_parts + t) * 16 + v];
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  if (gR && lane < 9) gR[9 * (size_t)n + lane] = s;
+  else if (gT && lane >= 9 && lane < 12) gT[3 * (size_t)n + lane - 9] = s;
+  else if (lane >= 13 && lane < 16 && grad_rgb_uniform) atomicAdd(grad_rgb_uniform + (lane - 13), s);
+  float g[13];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) g[i] = __shfl_sync(0xffffffffu, s, i);
+  if (lane == 0) {
+    const float d = __ldg(dist + n);
+    float ga, ge, gd;
+    look_at_backward_view(__ldg(azim + n), __ldg(elev + n), d, g, g + 9, nullptr, ga, ge, gd);
+    const float inv = __fdiv_rn(1.0f, d);      // d(1/dist)/d dist = -(1/dist)^2, as points_backward_reduce_kernel
+    g_azim[n] = ga; g_elev[n] = ge; g_dist[n] = gd + (-g[12] * (inv * inv));
+  }
+}
+
 }  // namespace mvr
 
 using namespace mvr;
@@ -1138,19 +1168,23 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
   return check_launch("points_resolve_kernel");
 }
 
-extern "C" int mvr_points_backward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
-                                   const float* T, const float* inv_dist, double radius, int H, int W, int K,
-                                   int flags, const float* out_mean_std, const int* idx, const uint32_t* hit_mask,
-                                   const void* grad_images,
-                                   float* gR, float* gT, float* g_inv_dist, float* grad_points, float* grad_rgb,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
+static int points_backward_impl(const float* points, const float* rgb, int B, int Np, int M, const float* R,
+                                const float* T, const float* inv_dist, double radius, int H, int W, int K,
+                                int flags, const float* out_mean_std, const int* idx, const uint32_t* hit_mask,
+                                const void* grad_images,
+                                float* gR, float* gT, float* g_inv_dist, float* grad_points, float* grad_rgb,
+                                void* workspace, size_t workspace_bytes, void* stream,
+                                const float* azim, const float* elev, float* g_azim, float* g_elev, float* g_dist) {
+  const bool angles = azim != nullptr;
   int rc = check_points_common("mvr_points_backward", B, Np, M, H, W, K, radius);
   if (rc) return rc;
   const int64_t N = (int64_t)B * M;
   if (N == 0) return 0;
-  if ((Np > 0 && !points) || !rgb || !R || !T || !inv_dist || !idx || !grad_images || !gR || !gT || !g_inv_dist || !workspace) {
+  if ((Np > 0 && !points) || !rgb || !R || !T || !inv_dist || !idx || !grad_images || !workspace ||
+      (!angles && (!gR || !gT || !g_inv_dist)) || (angles && (!elev || !g_azim || !g_elev || !g_dist))) {
     set_error("mvr_points_backward: null pointer"); return -6;
   }
+  if (angles && !(flags & MVR_SCALE_IS_DIST)) { set_error("mvr_points_backward_angles: needs MVR_SCALE_IS_DIST (the scale array is dist)"); return -10; }
   if (!out_norm_valid(out_mean_std)) { set_error("mvr_points_backward: out_mean_std needs std > 0"); return -9; }
   const PointsWs w = points_ws(B, Np, M, H, W, K, radius);
   const size_t need = (size_t)N * w.ctas_per_view * 16 * sizeof(float);
@@ -1186,7 +1220,33 @@ extern "C" int mvr_points_backward(const float* points, const float* rgb, int B,
   rc = check_launch("points_backward_kernel");
   if (rc) return rc;
   const int wpb = 8;
+  if (angles) {
+    MVR_LAUNCH(points_backward_reduce_angles_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, p.ctas_per_view,
+               azim, elev, inv_dist, gR, gT, g_azim, g_elev, g_dist, gu ? grad_rgb : (float*)nullptr);
+    return check_launch("points_backward_reduce_angles_kernel");
+  }
   MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, p.ctas_per_view, gR, gT, g_inv_dist, inv_dist, flags,
              gu ? grad_rgb : (float*)nullptr);
   return check_launch("points_backward_reduce_kernel");
+}
+
+extern "C" int mvr_points_backward(const float* points, const float* rgb, int B, int Np, int M, const float* R,
+                                   const float* T, const float* inv_dist, double radius, int H, int W, int K,
+                                   int flags, const float* out_mean_std, const int* idx, const uint32_t* hit_mask,
+                                   const void* grad_images,
+                                   float* gR, float* gT, float* g_inv_dist, float* grad_points, float* grad_rgb,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  return points_backward_impl(points, rgb, B, Np, M, R, T, inv_dist, radius, H, W, K, flags, out_mean_std, idx, hit_mask, grad_images, gR, gT,
+                              g_inv_dist, grad_points, grad_rgb, workspace, workspace_bytes, stream, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int mvr_points_backward_angles(const float* points, const float* rgb, int B, int Np, int M, const float* R,
+                                          const float* T, const float* azim, const float* elev, const float* dist, double radius,
+                                          int H, int W, int K, int flags, const float* out_mean_std, const int* idx,
+                                          const uint32_t* hit_mask, const void* grad_images, float* g_azim, float* g_elev,
+                                          float* g_dist, float* gR, float* gT, float* grad_points, float* grad_rgb, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  if (!azim) { set_error("mvr_points_backward_angles: null pointer"); return -6; }
+  return points_backward_impl(points, rgb, B, Np, M, R, T, dist, radius, H, W, K, flags, out_mean_std, idx, hit_mask, grad_images, gR, gT,
+                              nullptr, grad_points, grad_rgb, workspace, workspace_bytes, stream, azim, elev, g_azim, g_elev, g_dist);
 }

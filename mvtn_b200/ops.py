@@ -1092,6 +1092,31 @@ def _points_backward_launch(cfg, saved, g_images, want_points, want_rgb):
     return gR, gT, gs, gP, gF
 
 
+def _points_backward_angles_launch(cfg, saved, azim, elev, g_images, want_points, want_rgb):
+    """ONE mvr_points_backward_angles call -> (g_azim, g_elev, g_dist (flat), g_points | None, g_rgb | None)."""
+    lib = L.load()
+    R, T, dist, pts, rgb, idx, mask = saved
+    B, Np, M, radius, H, W, K, flags, out_norm, rgb_shape, points_shape = cfg
+    dev = pts.device
+    N = B * M
+    g_images = _grad_like_images(g_images, flags)
+    g = torch.empty(3 * N, dtype=torch.float32, device=dev)      # one allocation: g_azim | g_elev | g_dist
+    ga, ge, gd = g[:N], g[N: 2 * N], g[2 * N:]
+    gP = torch.zeros_like(pts) if want_points else None
+    gF = torch.zeros_like(rgb) if want_rgb else None
+    ws = workspace(dev, lib.mvr_points_workspace_bytes(B, Np, M, H, W, K, float(radius)))
+    with _on(dev):
+        L.check(lib.mvr_points_backward_angles(_ptr(pts), _ptr(rgb), B, Np, M, _ptr(R), _ptr(T), _ptr(azim), _ptr(elev), _ptr(dist), radius,
+                                               H, W, K, flags, out_norm, _ptr(idx), _ptr(mask), _ptr(g_images), _ptr(ga), _ptr(ge), _ptr(gd),
+                                               None, None, _ptr(gP), _ptr(gF), _ptr(ws), ws.numel(), _stream(dev)),
+                "mvr_points_backward_angles")
+    if gP is not None:
+        gP = gP.reshape(points_shape)
+    if gF is not None:
+        gF = gF.reshape(rgb_shape)
+    return ga, ge, gd, gP, gF
+
+
 class _PointsRender(torch.autograd.Function):
     @staticmethod
     def forward(ctx, R, T, inv_dist, points, rgb, M, radius, bg_rgb, H, W, K, flags, want_fragments, out_norm=None,
@@ -1142,6 +1167,12 @@ class _PointsRenderFromAngles(torch.autograd.Function):
         a, e = ctx.saved_tensors[:2]
         saved = ctx.saved_tensors[2:]
         d = saved[2]
+        if g_images is not None and gR_ext is None and gT_ext is None and gC_ext is None:
+            # nothing arrives through the cameras object (the usual case): rasterizer backward, reduction, camera backward and the
+            # scale term in ONE call ending in (d azim, d elev, d dist) -- mvr_points_backward_angles
+            ga, ge, gd, gP, gF = _points_backward_angles_launch(ctx.cfg, saved, a, e, g_images, ctx.needs_input_grad[3], ctx.needs_input_grad[4])
+            sa, se, sd = ctx.shapes
+            return (ga.reshape(sa), ge.reshape(se), gd.reshape(sd), gP, gF) + (None,) * 10
         gR = gT = gs = gP = gF = None
         if g_images is not None:
             gR, gT, gs, gP, gF = _points_backward_launch(ctx.cfg, saved, g_images, ctx.needs_input_grad[3], ctx.needs_input_grad[4])

@@ -1396,3 +1396,36 @@ def test_mvrenderer_mesh_cuda_graph_mode_matches_eager(cuda_device):
     want = run(eager, ml, views)
     assert torch.equal(a1.grad, want[4]) and torch.equal(img1.detach(), want[0])
     assert torch.equal(img2.detach(), run(eager, ml, v2)[0])
+
+
+def test_points_from_angles_fused_backward_equals_the_two_node_chain(cuda_device):
+    """ops.render_points_from_angles ends its backward in mvr_points_backward_angles (rasterizer backward + reduction + camera backward
+    + scale term in one call); ops.look_at_view_transform + ops.render_points(dist=...) runs the same chain as separate autograd nodes
+    (mvr_points_backward, mvr_look_at_backward, torch adds): same gradients bit for bit; gradients sent through the cameras still
+    take the unfused path and add up."""
+    dev = cuda_device
+    B, M, S = 3, 4, 64
+    pts = synth.make_clouds(B, 900, 5).to(dev)
+    col = torch.full((3,), 0.9, device=dev); bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    views = [t.to(dev) for t in synth.learned_spherical_views(B, M, 12)]
+    cot = torch.randn(B * M, 3, S, S, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    for K, mode in ((4, "alpha"), (1, "norm"), (3, "alpha")):
+        a1, e1, d1 = (t.clone().requires_grad_() for t in views)
+        img1, cams1, _ = ops.render_points_from_angles(pts, col, M, a1, e1, d1, 0.03, bg, S, points_per_pixel=K, compositor=mode)
+        img1.backward(cot)
+        a2, e2, d2 = (t.clone().requires_grad_() for t in views)
+        R, T, C, _bad = ops._LookAt.apply(a2, e2, d2)
+        img2, _ = ops.render_points(pts, col, M, R, T, None, 0.03, bg, S, points_per_pixel=K, compositor=mode, dist=d2.reshape(-1))
+        img2.backward(cot)
+        assert torch.equal(img1, img2)
+        for x, y in ((a1.grad, a2.grad), (e1.grad, e2.grad), (d1.grad, d2.grad)):
+            assert torch.equal(x, y), (K, mode)
+        # a loss that also reads the cameras: unfused path, contributions summed
+        a3, e3, d3 = (t.clone().requires_grad_() for t in views)
+        img3, (R3, T3, C3, _b), _ = ops.render_points_from_angles(pts, col, M, a3, e3, d3, 0.03, bg, S, points_per_pixel=K, compositor=mode)
+        ((img3 * cot).sum() + T3.sum()).backward()
+        a4, e4, d4 = (t.clone().requires_grad_() for t in views)
+        R4, T4, C4, _b = ops._LookAt.apply(a4, e4, d4)
+        img4, _ = ops.render_points(pts, col, M, R4, T4, None, 0.03, bg, S, points_per_pixel=K, compositor=mode, dist=d4.reshape(-1))
+        ((img4 * cot).sum() + T4.sum()).backward()
+        assert torch.allclose(a3.grad, a4.grad, rtol=1e-5, atol=1e-6) and torch.allclose(d3.grad, d4.grad, rtol=1e-5, atol=1e-6)
