@@ -114,6 +114,10 @@ int mvr_host_stage_meshes_end(int job);
  * azim/elev in degrees, n = B*M.  C (n,3) = camera centres (may be NULL). */
 int mvr_look_at_forward(const float* azim, const float* elev, const float* dist, int n, float* R,
                         float* T, float* C, int* invalid_count, void* stream);
+/* The same with the flag sent to the host behind the kernel: host_flag (pinned int) receives *invalid_count by an asynchronous
+ * copy, and `event` (cudaEvent_t) is recorded behind the copy -- the rotation guard (ops.py:156-165) waits for that event only. */
+int mvr_look_at_forward_flagged(const float* azim, const float* elev, const float* dist, int n, float* R, float* T, float* C,
+                                int* invalid_count, int* host_flag, void* event, void* stream);
 /* autograd backward of the above: (gR, gT, gC) -> (g_azim, g_elev, g_dist); any g* input may be NULL */
 int mvr_look_at_backward(const float* azim, const float* elev, const float* dist, int n,
                          const float* gR, const float* gT, const float* gC, float* g_azim,

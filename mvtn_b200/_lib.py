@@ -40,6 +40,7 @@ SIGNATURES = {
                                          _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "mvr_host_stage_meshes_end": (_i, [_i]),
     "mvr_look_at_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "mvr_look_at_forward_flagged": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvr_look_at_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvr_mesh_geometry_bytes": (_sz, [_i64, _i64]),
     "mvr_images_regularize_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),

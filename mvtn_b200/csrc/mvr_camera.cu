@@ -83,6 +83,21 @@ extern "C" int mvr_look_at_forward(const float* azim, const float* elev, const f
   return mvr::check_launch("look_at_forward_kernel");
 }
 
+// The same, and the validity flag on its way to the host behind the kernel: `host_flag` (pinned) receives invalid_count by an
+// asynchronous copy and `event` (a cudaEvent_t) is recorded behind that copy -- a caller that checks the flag before it trusts the
+// cameras (MVRenderer's rotation guard, util.py:403-420) then waits for this event only, and pays neither a copy call nor an event
+// call of its own in front of the rasterizer launch (host time there is step time).
+extern "C" int mvr_look_at_forward_flagged(const float* azim, const float* elev, const float* dist, int n, float* R, float* T,
+                                           float* C, int* invalid_count, int* host_flag, void* event, void* stream) {
+  if (!invalid_count || !host_flag || !event) { mvr::set_error("mvr_look_at_forward_flagged: null pointer"); return -2; }
+  int rc = mvr_look_at_forward(azim, elev, dist, n, R, T, C, invalid_count, stream);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(host_flag, invalid_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream);
+  if (e != cudaSuccess) { mvr::set_error("mvr_look_at_forward_flagged: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
 extern "C" int mvr_look_at_backward(const float* azim, const float* elev, const float* dist, int n,
                                     const float* gR, const float* gT, const float* gC, float* g_azim,
                                     float* g_elev, float* g_dist, void* stream) {

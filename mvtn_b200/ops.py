@@ -244,8 +244,36 @@ def fov_projection_scale(fov_deg: float = 60.0, znear: float = 1.0, aspect: floa
 # --------------------------------------------------------------------------------------------------
 # cameras
 # --------------------------------------------------------------------------------------------------
-def _look_at_launch(azim, elev, dist):
-    """Flat fp32 copies of the angles + one mvr_look_at_forward launch -> (a, e, d, R, T, C, invalid flag)."""
+class FlagSink:
+    """Where the rotation-validity flag of a look_at launch lands on the host: a pinned word + an event the LIBRARY records behind
+    its copy (mvr_look_at_forward_flagged), so the caller neither issues a copy nor records an event in front of the rasterizer
+    launch.  read() waits for that event only -- i.e. for the camera kernel, not for the rasterizer behind it.  Pooled per device."""
+    _pool = {}
+
+    def __init__(self, device):
+        self.device = device
+        self.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.event = torch.cuda.Event()
+        self.event.record(torch.cuda.current_stream(device))      # (torch creates the cudaEvent_t on first record)
+        self.armed = False
+
+    @classmethod
+    def get(cls, device):
+        pool = cls._pool.setdefault(device.index, [])
+        return pool.pop() if pool else cls(device)
+
+    def read(self) -> int:
+        """The flag (number of invalid rotations); returns the sink to the pool."""
+        self.event.synchronize()
+        v = int(self.host[0])
+        self.armed = False
+        FlagSink._pool.setdefault(self.device.index, []).append(self)
+        return v
+
+
+def _look_at_launch(azim, elev, dist, sink: "Optional[FlagSink]" = None):
+    """Flat fp32 copies of the angles + one mvr_look_at_forward launch -> (a, e, d, R, T, C, invalid flag).
+    sink: a FlagSink that receives the flag on the host (copy + event issued by the library call itself)."""
     _require_cuda(azim, "azim")
     a, e, d = _f32c(azim).reshape(-1), _f32c(elev).reshape(-1), _f32c(dist).reshape(-1)
     n = a.numel()
@@ -256,8 +284,14 @@ def _look_at_launch(azim, elev, dist):
     R, T, Cc = buf[: 9 * n].view(n, 3, 3), buf[9 * n: 12 * n].view(n, 3), buf[12 * n:].view(n, 3)
     bad = torch.empty(1, dtype=torch.int32, device=dev)      # zeroed by mvr_look_at_forward
     with _on(dev):
-        L.check(L.load().mvr_look_at_forward(_ptr(a), _ptr(e), _ptr(d), n, _ptr(R), _ptr(T), _ptr(Cc), _ptr(bad),
-                                             _stream(dev)), "mvr_look_at_forward")
+        if sink is not None:
+            L.check(L.load().mvr_look_at_forward_flagged(_ptr(a), _ptr(e), _ptr(d), n, _ptr(R), _ptr(T), _ptr(Cc), _ptr(bad),
+                                                         sink.host.data_ptr(), sink.event.cuda_event, _stream(dev)),
+                    "mvr_look_at_forward_flagged")
+            sink.armed = True
+        else:
+            L.check(L.load().mvr_look_at_forward(_ptr(a), _ptr(e), _ptr(d), n, _ptr(R), _ptr(T), _ptr(Cc), _ptr(bad),
+                                                 _stream(dev)), "mvr_look_at_forward")
     return a, e, d, R, T, Cc, bad
 
 
@@ -869,14 +903,16 @@ class _MeshRenderFromAngles(torch.autograd.Function):
     plumbing between them -- on the end-to-end step the GPU has the geometry before the host has reached
     mvr_mesh_forward, so host microseconds in front of that call are step time.
     light=None: the "relative" light, i.e. the (detached) camera centres (renderer.py:168).
-    after_cameras: called with the invalid-rotation flag tensor right after the camera kernel has been enqueued (the
+    after_cameras: a FlagSink (the flag travels to its pinned word behind the camera kernel, copy and event issued by the library
+    call), or a callable invoked with the invalid-rotation flag tensor right after the camera kernel has been enqueued (the
     renderer records its event there, in front of the rasterizer)."""
 
     @staticmethod
     def forward(ctx, azim, elev, dist, geom: PackedMeshes, M, light, obj_rgb, bg_rgb, k00, k11, z_clip, H, W, K, flags,
                 out_norm, out_dtype, after_cameras):
-        a, e, d, R, T, Cc, bad = _look_at_launch(azim, elev, dist)
-        if after_cameras is not None:
+        sink = after_cameras if isinstance(after_cameras, FlagSink) else None
+        a, e, d, R, T, Cc, bad = _look_at_launch(azim, elev, dist, sink)
+        if after_cameras is not None and sink is None:
             after_cameras(bad)
         cfg, saved, images, extras = _mesh_forward_launch(geom, M, R, T, Cc, Cc if light is None else light, obj_rgb, bg_rgb,
                                                           k00, k11, z_clip, H, W, K, flags, False, out_norm, out_dtype)
@@ -1148,8 +1184,9 @@ class _PointsRenderFromAngles(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, azim, elev, dist, points, rgb, M, radius, bg_rgb, H, W, K, flags, out_norm, out_dtype, after_cameras):
-        a, e, d, R, T, Cc, bad = _look_at_launch(azim, elev, dist)
-        if after_cameras is not None:
+        sink = after_cameras if isinstance(after_cameras, FlagSink) else None
+        a, e, d, R, T, Cc, bad = _look_at_launch(azim, elev, dist, sink)
+        if after_cameras is not None and sink is None:
             after_cameras(bad)
         cfg, saved, images, extras = _points_forward_launch(R, T, d, points, rgb, M, radius, bg_rgb, H, W, K,
                                                             flags | L.SCALE_IS_DIST, False, out_norm, out_dtype)

@@ -84,51 +84,6 @@ def _flag_reader(flag_dev):
     return read
 
 
-_flag_streams = {}
-_flag_events = {}
-
-
-class _DeferredFlag:
-    """The invalid-rotation flag read OFF the critical path.  arm(bad) -- called between the camera kernel and the rasterizer
-    launch -- only records an event; read() -- called after the rasterizer has been launched -- makes a side stream wait for
-    that event, copy the word into pinned memory and record a second event, waits for that one and returns the flag.  Host
-    work in front of the rasterizer launch is step time (the GPU has the geometry and waits for the launch: DESIGN.md
-    section 5); the same work behind it is hidden by the kernels.  The wait covers the camera kernel only, as before."""
-
-    def __init__(self):
-        self.bad = None
-        self._v = None
-
-    def _event(self, idx):
-        pool = _flag_events.setdefault(idx, [])
-        return pool.pop() if pool else torch.cuda.Event()
-
-    def arm(self, bad):
-        self.bad = bad
-        self._ev = self._event(bad.device.index)
-        self._ev.record(torch.cuda.current_stream(bad.device))
-
-    def read(self):
-        if self._v is None:
-            dev = self.bad.device
-            side = _flag_streams.get(dev.index)
-            if side is None:
-                side = _flag_streams[dev.index] = torch.cuda.Stream(dev)
-            pool = _flag_bufs.setdefault(dev.index, [])
-            host = pool.pop() if pool else torch.empty(1, dtype=torch.int32, pin_memory=True)
-            side.wait_event(self._ev)
-            with torch.cuda.stream(side):
-                host.copy_(self.bad, non_blocking=True)
-            self.bad.record_stream(side)
-            ev2 = self._event(dev.index)
-            ev2.record(side)
-            ev2.synchronize()
-            self._v = int(host[0])
-            pool.append(host)
-            _flag_events[dev.index] += [self._ev, ev2]
-        return self._v
-
-
 GRAPH_AUTO_MAX_VIEWS = 48     # cuda_graph=None: point steps up to this many views (B * M) are replayed from CUDA graphs
 ORTHOGONAL_THRESHOLD = 1e-6   # renderer.py:29
 EXAHSTION_LIMIT = 20          # renderer.py:30 (sic)
@@ -300,21 +255,24 @@ class MVRenderer(nn.Module):
 
         try:
             out = None
-            flag = _DeferredFlag()
+            flag = None
             if getattr(geom, "grad_verts", None) is None and not soft:
                 # fast path: cameras + rasterizer as ONE autograd node (ops.render_meshes_from_angles); the validity flag
                 # is still awaited through an event recorded between the camera kernel and the rasterizer
                 az, el, di = self._views(azim, elev, dist, device)
                 geom.finish(lazy_chunks=True)
+                # the rotation flag travels to a pinned word behind the camera kernel: copy and event are issued by the library
+                # call itself (ops.FlagSink), so nothing of it stands between the camera launch and the rasterizer launch
+                flag = ops.FlagSink.get(device)
                 images, (R, T, C, _bad), frag = ops.render_meshes_from_angles(
                     geom, self.nb_views, az, el, di, fixed_light, obj, bg, self.image_size,
                     faces_per_pixel=self.faces_per_pixel, cull_backfaces=self.cull_backfaces,
                     perspective_correct=self.perspective_correct, normalize=self.normalize, out_dtype=self.out_dtype,
-                    after_cameras=flag.arm)
+                    after_cameras=flag)
                 if flag.read() == 0:
                     out = (images, frag)
             if out is None:      # vertex gradients wanted, or invalid rotations: the general path with the redraw loop
-                out, R, T, C = self._render_with_guard(azim, elev, dist, device, render, known_invalid=flag.bad is not None)
+                out, R, T, C = self._render_with_guard(azim, elev, dist, device, render, known_invalid=flag is not None)
             images, frag = out
         finally:
             geom.finish()      # never leave a deferred / in-flight staging behind (e.g. when the cameras were rejected)
@@ -358,15 +316,14 @@ class MVRenderer(nn.Module):
         az, el, di = self._views(azim, elev, dist, device)
         # fast path: cameras + rasterizer + compositor as ONE autograd node (ops.render_points_from_angles); the validity
         # flag is awaited through an event recorded between the camera kernel and the rasterizer
-        # (the point step is bound by the HOST from end to end -- ~0.3 ms of python per step against ~0.23 ms of kernels at 32 x 12
-        # views -- so the flag is read the cheap way here: _DeferredFlag's side stream moves host work behind the rasterizer launch at
-        # the price of more of it, which pays on the mesh path only: 0.265 -> 0.313 ms per point step when it was tried here)
-        reader = []
+        # the rotation flag travels to a pinned word behind the camera kernel, copy and event issued by the library call (ops.FlagSink):
+        # the point step is bound by the HOST from end to end (~0.25 ms of python against ~0.23 ms of kernels at 32 x 12 views)
+        flag = ops.FlagSink.get(device)
         images, (R, T, C, _bad), frag = ops.render_points_from_angles(
             pts, rgb, self.nb_views, az, el, di, self.points_radius, bg, self.image_size,
             points_per_pixel=self.points_per_pixel, compositor=self.compositor, normalize=self.normalize,
-            out_dtype=self.out_dtype, after_cameras=lambda bad: reader.append(_flag_reader(bad)))
-        if reader[0]() != 0:      # invalid rotations: the general path with the redraw loop
+            out_dtype=self.out_dtype, after_cameras=flag)
+        if flag.read() != 0:      # invalid rotations: the general path with the redraw loop
             (images, frag), R, T, C = self._render_with_guard(azim, elev, dist, device, render, known_invalid=True)
         self.last_fragments = frag
         rendered_images = images.view(pts.shape[0], self.nb_views, 3, self.image_size, self.image_size)
