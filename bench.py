@@ -277,7 +277,7 @@ class Workload:
 
     # -- the step flavours --------------------------------------------------------------------------
     def step_resident(self, eager=False):
-        """Hot path with inputs already in HBM: prepare + look_at + forward + backward + look_at backward.
+        """Hot path with inputs already in HBM: prepare + look_at + forward + backward (its last kernel applies the look_at backward).
         eager=True: issue the launches even when the workload is replayed from CUDA graphs (per-kernel profiling)."""
         from mvtn_b200 import ops
         s, M, S = self.s, self.M, self.S
@@ -285,9 +285,8 @@ class Workload:
         if self.graphed is not None and not eager:
             img = self.graphed(az, el, di)
         elif s["kind"] == "mesh":
-            R, T, C, _bad = ops._LookAt.apply(az.reshape(-1), el.reshape(-1), di.reshape(-1))
             geom = ops.PackedMeshes.from_packed(self.verts_d, self.faces_d, self.nv, self.nf)
-            img, _ = ops.render_meshes(geom, M, R, T, C, self.light, self.obj, self.bg, S)
+            img, _cams, _frag = ops.render_meshes_from_angles(geom, M, az, el, di, self.light, self.obj, self.bg, S)
         else:
             img, _cams, self.last_frag = ops.render_points_from_angles(self.pts_d, self.obj, M, az, el, di, self.renderer.points_radius,
                                                                        self.bg_black, S, points_per_pixel=s["K"], compositor=s["compositor"])

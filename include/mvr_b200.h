@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MVR_ABI_VERSION 8
+#define MVR_ABI_VERSION 9
 
 /* flags */
 #define MVR_PERSPECTIVE_CORRECT 1  /* [upstream] RasterizationSettings.perspective_correct (FoV persp.: True) */
@@ -212,6 +212,17 @@ int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face
                       float* gT, float* gC,
                       float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,
                       void* stream);
+/* The same for cameras that came from mvr_look_at_forward(azim, elev, dist) (renderer.py:161-166): the kernel that sums a view's
+ * partial camera gradients also applies mvr_look_at_backward to them, so the chain ends in g_azim, g_elev, g_dist (n) with one
+ * launch and one call less.  gR / gT / gC: optional copies of the camera gradients (NULL: not stored). */
+int mvr_mesh_backward_angles(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
+                             int64_t total_verts, int64_t total_faces, int max_verts, const float* R, const float* T,
+                             const float* C, const float* light, int light_stride, const float* obj_rgb, float k00,
+                             float k11, float z_clip, int H, int W, int K, int flags, const float* out_mean_std,
+                             const int* pix_to_face, const void* grad_images, const float* azim, const float* elev,
+                             const float* dist, float* g_azim, float* g_elev, float* g_dist, float* gR, float* gT,
+                             float* gC, float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,
+                             void* stream);
 
 /* -- soft shading of K fragments per pixel (renderer.py:4-6 SoftPhongShader / SoftSilhouetteShader) -------- */
 /* mode 0: [upstream] blending.softmax_rgb_blend over per-fragment Phong colours (SoftPhongShader; sigma, gamma = BlendParams,

@@ -419,18 +419,20 @@ static bool backward_strip() {
   return v;
 }
 
-extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
-                                 int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
-                                 const float* T, const float* Cc, const float* light, int light_stride,
-                                 const float* obj_rgb, float k00, float k11, float z_clip, int H, int W, int K, int flags,
-                                 const float* out_mean_std, const int* pix_to_face, const void* grad_images, float* gR, float* gT, float* gC,
-                                 float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,
-                                 void* stream) {
+static int mesh_backward_impl(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
+                              int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
+                              const float* T, const float* Cc, const float* light, int light_stride,
+                              const float* obj_rgb, float k00, float k11, float z_clip, int H, int W, int K, int flags,
+                              const float* out_mean_std, const int* pix_to_face, const void* grad_images, float* gR, float* gT, float* gC,
+                              float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,
+                              void* stream, const float* azim, const float* elev, const float* dist, float* g_azim, float* g_elev,
+                              float* g_dist) {
   int rc = check_mesh_common("mvr_mesh_backward", B, M, H, W, K, total_verts, total_faces, max_verts);
   if (rc) return rc;
   const int64_t N = (int64_t)B * M;
   if (N == 0) return 0;
-  if (!geometry || !vert_off || !face_off || !R || !T || !Cc || !light || !pix_to_face || !grad_images || !gR || !gT || !gC || !workspace) {
+  if (!geometry || !vert_off || !face_off || !R || !T || !Cc || !light || !pix_to_face || !grad_images || !workspace ||
+      (!azim && (!gR || !gT || !gC)) || (azim && (!elev || !dist || !g_azim || !g_elev || !g_dist))) {
     set_error("mvr_mesh_backward: null pointer"); return -5;
   }
   if (!(flags & MVR_RGB_PER_ELEMENT) && !obj_rgb) { set_error("mvr_mesh_backward: obj_rgb is NULL"); return -6; }
@@ -457,6 +459,7 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   p.partials = (float*)(wb + w.partials); p.grad_verts = grad_verts; p.grad_normals = grad_normals;
   p.onorm = make_out_norm(out_mean_std);
   p.z_clip = z_clip; p.wsflags = (int*)(wb + w.flags); p.parts_per_view = w.bwd_parts_per_view;
+  p.azim = azim; p.elev = elev; p.dist = dist; p.g_azim = g_azim; p.g_elev = g_elev; p.g_dist = g_dist;
   { static const int plain = [] { const char* e = getenv("MVR_BWD_GV_AGG"); return (e && atoi(e) == 0) ? 1 : 0; }(); p.gv_plain = plain; }
   const dim3 bgrid((unsigned)w.bwd_ctas_per_view, (unsigned)M, (unsigned)B);
   const bool vrgb = flags & MVR_RGB_PER_ELEMENT;
@@ -484,4 +487,32 @@ extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, cons
   if (rc) return rc;
   // clipped-face pixels (if any) + the fixed-order sum of the per-warp partials -> gR, gT, gC
   return launch_mesh_backward_finish(p, (int)N, gR, gT, gC, st);
+}
+
+extern "C" int mvr_mesh_backward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
+                                 int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
+                                 const float* T, const float* Cc, const float* light, int light_stride,
+                                 const float* obj_rgb, float k00, float k11, float z_clip, int H, int W, int K, int flags,
+                                 const float* out_mean_std, const int* pix_to_face, const void* grad_images, float* gR, float* gT, float* gC,
+                                 float* grad_verts, float* grad_normals, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  return mesh_backward_impl(geometry, vert_off, face_off, B, M, total_verts, total_faces, max_verts, R, T, Cc, light, light_stride, obj_rgb,
+                            k00, k11, z_clip, H, W, K, flags, out_mean_std, pix_to_face, grad_images, gR, gT, gC, grad_verts, grad_normals,
+                            workspace, workspace_bytes, stream, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// mvr_mesh_backward for cameras that came from mvr_look_at_forward(azim, elev, dist): the kernel that sums the per-warp partials of a
+// view also applies its camera backward (look_at_backward_view), so the chain ends in (d azim, d elev, d dist) with one launch less.
+extern "C" int mvr_mesh_backward_angles(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
+                                        int64_t total_verts, int64_t total_faces, int max_verts, const float* R,
+                                        const float* T, const float* Cc, const float* light, int light_stride,
+                                        const float* obj_rgb, float k00, float k11, float z_clip, int H, int W, int K, int flags,
+                                        const float* out_mean_std, const int* pix_to_face, const void* grad_images,
+                                        const float* azim, const float* elev, const float* dist, float* g_azim, float* g_elev,
+                                        float* g_dist, float* gR, float* gT, float* gC, float* grad_verts, float* grad_normals,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!azim) { set_error("mvr_mesh_backward_angles: null pointer"); return -5; }
+  return mesh_backward_impl(geometry, vert_off, face_off, B, M, total_verts, total_faces, max_verts, R, T, Cc, light, light_stride, obj_rgb,
+                            k00, k11, z_clip, H, W, K, flags, out_mean_std, pix_to_face, grad_images, gR, gT, gC, grad_verts, grad_normals,
+                            workspace, workspace_bytes, stream, azim, elev, dist, g_azim, g_elev, g_dist);
 }

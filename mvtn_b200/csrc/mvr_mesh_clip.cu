@@ -9,6 +9,7 @@
 // -- redo exactly those pixels with the clipped geometry.
 // Compiled with -fmad=false like the forward unit: which sub-triangle owns a pixel is a fragment decision.
 #include "mvr_mesh.cuh"
+#include "mvr_camera.cuh"
 
 namespace mvr {
 
@@ -252,9 +253,18 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_backward_finish_kernel(const
 #pragma unroll
     for (int g = 0; g < MVR_THREADS / 16; ++g) tot += s_sum[g * 16 + tid];
     const float out = (float)tot;
-    if (tid < 9) gR[9 * (size_t)n + tid] = out;
-    else if (tid < 12) gT[3 * (size_t)n + tid - 9] = out;
-    else if (tid < 15) gC[3 * (size_t)n + tid - 12] = out;
+    if (tid < 9) { if (gR) gR[9 * (size_t)n + tid] = out; }
+    else if (tid < 12) { if (gT) gT[3 * (size_t)n + tid - 9] = out; }
+    else if (tid < 15) { if (gC) gC[3 * (size_t)n + tid - 12] = out; }
+    s_red[tid] = out;
+  }
+  if (p.azim) {      // mvr_mesh_backward_angles: (dR, dT, dC) -> (d azim, d elev, d dist) of this view, same launch (block-uniform)
+    __syncthreads();
+    if (tid == 0) {
+      float ga, ge, gd;
+      look_at_backward_view(__ldg(p.azim + n), __ldg(p.elev + n), __ldg(p.dist + n), s_red, s_red + 9, s_red + 12, ga, ge, gd);
+      p.g_azim[n] = ga; p.g_elev[n] = ge; p.g_dist[n] = gd;
+    }
   }
 }
 

@@ -346,6 +346,7 @@ extern "C" int mvr_mesh_soft_backward(const void* geometry, const int* vert_off,
   rc = check_launch("mesh_soft_backward_kernel");
   if (rc) return rc;
   MeshBwdParams q;
+  q.azim = q.elev = q.dist = nullptr; q.g_azim = q.g_elev = q.g_dist = nullptr;
   q.partials = (float*)(wb + w.partials); q.parts_per_view = w.bwd_parts_per_view; q.wsflags = (int*)(wb + w.flags);
   q.B = B; q.M = M; q.H = H; q.W = W; q.K = K; q.flags = flags; q.z_clip = -1.f; q.grad_verts = nullptr; q.grad_normals = nullptr;
   return launch_mesh_backward_finish(q, (int)N, gR, gT, gC, st);

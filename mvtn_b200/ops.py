@@ -832,9 +832,10 @@ def _mesh_forward_launch(geom: "PackedMeshes", M, R, T, Cc, light, obj_rgb, bg_r
     return cfg, saved, images, extras
 
 
-def _mesh_backward_launch(geom: "PackedMeshes", M, cfg, saved, g_images, want_verts):
+def _mesh_backward_launch(geom: "PackedMeshes", M, cfg, saved, g_images, want_verts, angles=None):
     """mvr_mesh_backward (one call per staging group of the forward) -> (gR, gT, gC, gV | None) (gV includes the chain through
-    the vertex normals)."""
+    the vertex normals).  angles = (azim, elev, dist) flat fp32: mvr_mesh_backward_angles instead, whose last kernel also applies
+    the camera backward -> (g_azim, g_elev, g_dist, gV | None)."""
     lib = L.load()
     R, T, Cc, light, obj_rgb, p2f = saved
     k00, k11, H, W, K, flags, out_norm, light_stride, z_clip, (ranges, tokens) = cfg
@@ -842,8 +843,12 @@ def _mesh_backward_launch(geom: "PackedMeshes", M, cfg, saved, g_images, want_ve
     N = geom.B * M
     g_images = _grad_like_images(g_images, flags)
     # three separate (N, .) blocks, so that a group's views are a contiguous slice of each
-    g = torch.empty(15 * N, dtype=torch.float32, device=dev)
-    gR, gT, gC = g[: 9 * N].view(N, 3, 3), g[9 * N: 12 * N].view(N, 3), g[12 * N:].view(N, 3)
+    if angles is None:
+        g = torch.empty(15 * N, dtype=torch.float32, device=dev)
+        gR, gT, gC = g[: 9 * N].view(N, 3, 3), g[9 * N: 12 * N].view(N, 3), g[12 * N:].view(N, 3)
+    else:
+        g = torch.empty(3 * N, dtype=torch.float32, device=dev)
+        ga, ge, gd = g[:N], g[N: 2 * N], g[2 * N:]
     gV = gN = None
     if want_verts:
         gV = torch.zeros((geom.total_verts, 3), dtype=torch.float32, device=dev)
@@ -860,6 +865,16 @@ def _mesh_backward_launch(geom: "PackedMeshes", M, cfg, saved, g_images, want_ve
         else:
             sl = lambda t: t[n0:n1]
             voff, foff, lt = geom.vert_off[b0:], geom.face_off[b0:], (light if light_stride == 0 else light[n0:n1])
+        if angles is not None:
+            az, el, di = angles
+            with _on(dev):
+                L.check(lib.mvr_mesh_backward_angles(_ptr(geom.geometry), _ptr(voff), _ptr(foff), Bc, M, geom.total_verts, geom.total_faces,
+                                                     geom.max_verts, _ptr(sl(R)), _ptr(sl(T)), _ptr(sl(Cc)), _ptr(lt), light_stride,
+                                                     _ptr(obj_rgb), k00, k11, z_clip, H, W, K, fl, out_norm, _ptr(sl(p2f)),
+                                                     _ptr(sl(g_images)), _ptr(sl(az)), _ptr(sl(el)), _ptr(sl(di)), _ptr(sl(ga)), _ptr(sl(ge)),
+                                                     _ptr(sl(gd)), None, None, None, _ptr(gV), _ptr(gN), _ptr(ws), ws.numel(),
+                                                     _stream(dev)), "mvr_mesh_backward_angles")
+            continue
         with _on(dev):
             L.check(lib.mvr_mesh_backward(_ptr(geom.geometry), _ptr(voff), _ptr(foff), Bc, M,
                                           geom.total_verts, geom.total_faces, geom.max_verts, _ptr(sl(R)), _ptr(sl(T)), _ptr(sl(Cc)), _ptr(lt),
@@ -873,6 +888,8 @@ def _mesh_backward_launch(geom: "PackedMeshes", M, cfg, saved, g_images, want_ve
             L.check(lib.mvr_mesh_normals_backward(_ptr(geom.geometry), _ptr(geom.vert_off), _ptr(geom.face_off), geom.B,
                                                   geom.total_verts, geom.total_faces, geom.max_faces, _ptr(gN), _ptr(gV),
                                                   _stream(dev)), "mvr_mesh_normals_backward")
+    if angles is not None:
+        return ga, ge, gd, gV
     return gR, gT, gC, gV
 
 
@@ -928,6 +945,12 @@ class _MeshRenderFromAngles(torch.autograd.Function):
         if g_images is None and gR_ext is None and gT_ext is None and gC_ext is None:
             return (None,) * 18
         a, e, d = ctx.saved_tensors[:3]
+        if g_images is not None and gR_ext is None and gT_ext is None and gC_ext is None:
+            # nothing arrives through the cameras object (the usual case): rasterizer backward, reduction and camera backward in
+            # ONE call ending in (d azim, d elev, d dist) -- mvr_mesh_backward_angles
+            ga, ge, gd, _ = _mesh_backward_launch(ctx.geom, ctx.M, ctx.cfg, ctx.saved_tensors[3:], g_images, False, (a, e, d))
+            sa, se, sd = ctx.shapes
+            return (ga.reshape(sa), ge.reshape(se), gd.reshape(sd)) + (None,) * 15
         gR = gT = gC = None
         if g_images is not None:
             gR, gT, gC, _ = _mesh_backward_launch(ctx.geom, ctx.M, ctx.cfg, ctx.saved_tensors[3:], g_images, False)

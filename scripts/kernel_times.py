@@ -21,9 +21,8 @@ lib = L.load()
 
 def step():
     a = az.detach().requires_grad_(); e = el.detach().requires_grad_(); d = di.detach().requires_grad_()
-    R, T, C, _ = ops._LookAt.apply(a, e, d)
     geom = ops.PackedMeshes.from_packed(verts, faces, nv, nf)
-    img, _ = ops.render_meshes(geom, M, R, T, C, light, col, col, S)
+    img, _cams, _frag = ops.render_meshes_from_angles(geom, M, a, e, d, light, col, col, S)
     img.backward(cot)
 
 for _ in range(5):

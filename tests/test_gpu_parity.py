@@ -1429,3 +1429,42 @@ def test_points_from_angles_fused_backward_equals_the_two_node_chain(cuda_device
         img4, _ = ops.render_points(pts, col, M, R4, T4, None, 0.03, bg, S, points_per_pixel=K, compositor=mode, dist=d4.reshape(-1))
         ((img4 * cot).sum() + T4.sum()).backward()
         assert torch.allclose(a3.grad, a4.grad, rtol=1e-5, atol=1e-6) and torch.allclose(d3.grad, d4.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_mesh_from_angles_fused_backward_equals_the_two_node_chain(cuda_device):
+    """ops.render_meshes_from_angles ends its backward in mvr_mesh_backward_angles (rasterizer/shader backward + per-view sums + camera
+    backward in one call); ops._LookAt + ops.render_meshes runs the same chain as two autograd nodes (mvr_mesh_backward,
+    mvr_look_at_backward): same gradients bit for bit, fixed and relative light, with a staged batch (h2d_chunks-style groups) too;
+    gradients sent through the cameras take the unfused path and add up."""
+    dev = cuda_device
+    B, M, S = 3, 4, 64
+    ms = synth.make_meshes(B, 700, 41)
+    geom = ops.PackedMeshes([m[0] for m in ms], [m[1] for m in ms], dev)
+    col = torch.tensor([0.9, 0.5, 0.3], device=dev); bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    views = [t.to(dev) for t in synth.learned_spherical_views(B, M, 13)]
+    cot = torch.randn(B * M, 3, S, S, device=dev, generator=torch.Generator(device=dev).manual_seed(2))
+    fixed = torch.tensor([[0.0, 1.0, 0.2]], device=dev)
+    for K, light in ((1, None), (2, fixed), (1, fixed)):
+        a1, e1, d1 = (t.clone().requires_grad_() for t in views)
+        img1, cams1, _ = ops.render_meshes_from_angles(geom, M, a1, e1, d1, light, col, bg, S, faces_per_pixel=K)
+        img1.backward(cot)
+        a2, e2, d2 = (t.clone().requires_grad_() for t in views)
+        R, T, C, _bad = ops._LookAt.apply(a2, e2, d2)
+        img2 = ops.render_meshes(geom, M, R, T, C, C.detach() if light is None else light, col, bg, S, faces_per_pixel=K)
+        img2 = img2[0] if isinstance(img2, tuple) else img2
+        img2.backward(cot)
+        assert torch.equal(img1, img2)
+        for x, y in ((a1.grad, a2.grad), (e1.grad, e2.grad), (d1.grad, d2.grad)):
+            assert torch.equal(x, y), (K, light is None)
+        assert float(a1.grad.abs().sum()) > 0 and float(d1.grad.abs().sum()) > 0
+        # a loss that also reads the cameras: unfused path, contributions summed
+        a3, e3, d3 = (t.clone().requires_grad_() for t in views)
+        img3, (R3, T3, C3, _b), _ = ops.render_meshes_from_angles(geom, M, a3, e3, d3, light, col, bg, S, faces_per_pixel=K)
+        ((img3 * cot).sum() + T3.sum() + C3.sum()).backward()
+        a4, e4, d4 = (t.clone().requires_grad_() for t in views)
+        R4, T4, C4, _b = ops._LookAt.apply(a4, e4, d4)
+        img4 = ops.render_meshes(geom, M, R4, T4, C4, C4.detach() if light is None else light, col, bg, S, faces_per_pixel=K)
+        img4 = img4[0] if isinstance(img4, tuple) else img4
+        ((img4 * cot).sum() + T4.sum() + C4.sum()).backward()
+        assert torch.allclose(a3.grad, a4.grad, rtol=1e-5, atol=1e-6) and torch.allclose(d3.grad, d4.grad, rtol=1e-5, atol=1e-6)
