@@ -97,6 +97,15 @@ int mvr_host_stage_meshes(const void* const* vert_srcs, const int64_t* vert_coun
                           int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
                           float* dev_verts, int32_t* dev_faces, void* stream);
 
+/* The same, plus: the faces optionally narrowed (saturating) to uint16 ids (face_out_bytes 2: pinned_faces / dev_faces hold 2-byte
+ * elements; for batches whose meshes all have at most 65536 vertices, then prepare with MVR_FACES_U16 -- a third fewer H2D bytes than
+ * the int32 form), and the batch's offset table written to pinned_offs and copied to dev_offs (either may be NULL): 2n + 2 int32,
+ * vertex offsets (n + 1) | face offsets (n + 1), the vert_off / face_off arguments of mvr_mesh_prepare. */
+int mvr_host_stage_meshes_packed(const void* const* vert_srcs, const int64_t* vert_counts,
+                                 const void* const* face_srcs, const int64_t* face_counts, int n,
+                                 int face_elem_bytes, int face_out_bytes, float* pinned_verts, void* pinned_faces,
+                                 int32_t* pinned_offs, float* dev_verts, void* dev_faces, int32_t* dev_offs, void* stream);
+
 /* Asynchronous variant: _begin hands the same work to a persistent native worker thread (which selects CUDA device
  * `device` before enqueueing the copies) and returns a job id > 0 at once, so the caller can build the rest of the step
  * while the meshes are staged; _end(job) waits for it and returns its status.  Every array passed to _begin must stay

@@ -36,6 +36,8 @@ SIGNATURES = {
     "mvr_host_gather": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _i, _vp, _i, _i]),
     "mvr_host_stage_meshes": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _i,
                                    _i, _vp, _vp, _vp, _vp, _vp]),
+    "mvr_host_stage_meshes_packed": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _i,
+                                          _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvr_host_stage_meshes_begin": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                          _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "mvr_host_stage_meshes_end": (_i, [_i]),

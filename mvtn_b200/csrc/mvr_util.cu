@@ -143,8 +143,11 @@ extern "C" int mvr_host_gather(const void* const* srcs, const int64_t* counts, i
 // face gather: the step's time-to-first-kernel is bounded by this call.
 static int stage_meshes_impl(const void* const* vert_srcs, const int64_t* vert_counts,
                              const void* const* face_srcs, const int64_t* face_counts, int n,
-                             int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
-                             float* dev_verts, int32_t* dev_faces, void* stream) {
+                             int face_elem_bytes, float* pinned_verts, void* pinned_faces_any,
+                             float* dev_verts, void* dev_faces, void* stream, int face_out_bytes = 4,
+                             int32_t* pinned_offs = nullptr, int32_t* dev_offs = nullptr) {
+  int32_t* pinned_faces = (int32_t*)pinned_faces_any;
+  uint16_t* pinned_faces16 = (uint16_t*)pinned_faces_any;
   if (n < 0 || (n > 0 && (!vert_srcs || !vert_counts || !face_srcs || !face_counts || !pinned_verts || !pinned_faces))) {
     mvr::set_error("mvr_host_stage_meshes: null pointer"); return -1;
   }
@@ -155,6 +158,14 @@ static int stage_meshes_impl(const void* const* vert_srcs, const int64_t* vert_c
     voff[i + 1] = voff[i] + vert_counts[i];      // counts are in ELEMENTS (floats / indices)
     foff[i + 1] = foff[i] + face_counts[i];
   }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pinned_offs) {      // vertex | face offsets of the packed batch (n + 1 each, in vertices / faces), first on the wire: 2n + 2 words
+    for (int i = 0; i <= n; ++i) { pinned_offs[i] = (int32_t)(voff[i] / 3); pinned_offs[n + 1 + i] = (int32_t)(foff[i] / 3); }
+    if (dev_offs) {
+      const cudaError_t e = cudaMemcpyAsync(dev_offs, pinned_offs, (size_t)(2 * n + 2) * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) { mvr::set_error("mvr_host_stage_meshes: cudaMemcpyAsync(offsets): %s", cudaGetErrorString(e)); return (int)e; }
+    }
+  }
   const int64_t kChunk = 1 << 14;
   std::vector<int64_t> vwork, fwork;              // (array, start) pairs
   for (int i = 0; i < n; ++i) for (int64_t s = 0; s < vert_counts[i]; s += kChunk) { vwork.push_back(i); vwork.push_back(s); }
@@ -162,7 +173,6 @@ static int stage_meshes_impl(const void* const* vert_srcs, const int64_t* vert_c
   const int64_t nv = (int64_t)vwork.size() / 2, nf = (int64_t)fwork.size() / 2;
   int nthreads = g_host_threads > 0 ? g_host_threads : omp_get_max_threads();
   if (nthreads > 8) nthreads = 8;                 // memory-bound: more threads only add wake-up latency
-  cudaStream_t st = (cudaStream_t)stream;
   cudaError_t err_v = cudaSuccess;
 #pragma omp parallel num_threads(nthreads)
   {
@@ -180,6 +190,17 @@ static int stage_meshes_impl(const void* const* vert_srcs, const int64_t* vert_c
     for (int64_t w = 0; w < nf; ++w) {
       const int i = (int)fwork[2 * w];
       const int64_t s = fwork[2 * w + 1], cnt = std::min<int64_t>(kChunk, face_counts[i] - s);
+      if (face_out_bytes == 2) {      // saturate to [0, 65535]: mvr_mesh_prepare then clamps to the mesh's vertex count, as it does for int32
+        uint16_t* d16 = pinned_faces16 + foff[i] + s;
+        if (face_elem_bytes == 8) {
+          const int64_t* src = (const int64_t*)face_srcs[i] + s;
+          for (int64_t e = 0; e < cnt; ++e) { const int64_t x = src[e]; d16[e] = (uint16_t)(x < 0 ? 0 : (x > 65535 ? 65535 : x)); }
+        } else {
+          const int32_t* src = (const int32_t*)face_srcs[i] + s;
+          for (int64_t e = 0; e < cnt; ++e) { const int32_t x = src[e]; d16[e] = (uint16_t)(x < 0 ? 0 : (x > 65535 ? 65535 : x)); }
+        }
+        continue;
+      }
       int32_t* d = pinned_faces + foff[i] + s;
       if (face_elem_bytes == 8) {
         const int64_t* src = (const int64_t*)face_srcs[i] + s;
@@ -191,7 +212,7 @@ static int stage_meshes_impl(const void* const* vert_srcs, const int64_t* vert_c
   }
   if (err_v != cudaSuccess) { mvr::set_error("mvr_host_stage_meshes: cudaMemcpyAsync(verts): %s", cudaGetErrorString(err_v)); return (int)err_v; }
   if (dev_faces && foff[n] > 0) {
-    const cudaError_t e = cudaMemcpyAsync(dev_faces, pinned_faces, (size_t)foff[n] * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+    const cudaError_t e = cudaMemcpyAsync(dev_faces, pinned_faces_any, (size_t)foff[n] * (size_t)face_out_bytes, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { mvr::set_error("mvr_host_stage_meshes: cudaMemcpyAsync(faces): %s", cudaGetErrorString(e)); return (int)e; }
   }
   return 0;
@@ -203,6 +224,20 @@ extern "C" int mvr_host_stage_meshes(const void* const* vert_srcs, const int64_t
                                      float* dev_verts, int32_t* dev_faces, void* stream) {
   return stage_meshes_impl(vert_srcs, vert_counts, face_srcs, face_counts, n, face_elem_bytes, pinned_verts, pinned_faces,
                            dev_verts, dev_faces, stream);
+}
+
+// The same for a caller that also wants the batch's offset table written and copied, and the faces optionally narrowed to uint16 ids
+// (face_out_bytes 2, saturating; for batches whose meshes all have at most 65536 vertices: MVR_FACES_U16 in mvr_mesh_prepare -- a third
+// of the H2D bytes less than int32).  pinned_offs / dev_offs: 2n + 2 int32 = vertex offsets (n + 1) | face offsets (n + 1).
+extern "C" int mvr_host_stage_meshes_packed(const void* const* vert_srcs, const int64_t* vert_counts,
+                                            const void* const* face_srcs, const int64_t* face_counts, int n,
+                                            int face_elem_bytes, int face_out_bytes, float* pinned_verts, void* pinned_faces,
+                                            int32_t* pinned_offs, float* dev_verts, void* dev_faces, int32_t* dev_offs, void* stream) {
+  if (face_out_bytes != 2 && face_out_bytes != 4) { mvr::set_error("mvr_host_stage_meshes_packed: face_out_bytes must be 2 or 4"); return -2; }
+  for (int i = 0; i < n; ++i)
+    if (vert_counts && face_counts && (vert_counts[i] % 3 || face_counts[i] % 3)) { mvr::set_error("mvr_host_stage_meshes_packed: counts must be multiples of 3"); return -3; }
+  return stage_meshes_impl(vert_srcs, vert_counts, face_srcs, face_counts, n, face_elem_bytes, pinned_verts, pinned_faces,
+                           dev_verts, dev_faces, stream, face_out_bytes, pinned_offs, dev_offs);
 }
 
 // ---- asynchronous variant: the staging runs on a persistent native worker thread while the caller (Python) prepares

@@ -203,7 +203,7 @@ def _host_gather(srcs, dst: torch.Tensor, elem_bytes: int, narrow: bool):
     L.check(L.load().mvr_host_gather(ptrs, counts, n, dst.data_ptr(), elem_bytes, 1 if narrow else 0), "mvr_host_gather")
 
 
-def _stage_meshes(v_src, f_src, face_elem_bytes, v_host, f_host, v_dev, f_dev, device, overlap):
+def _stage_meshes(v_src, f_src, face_elem_bytes, v_host, f_host, v_dev, f_dev, device, overlap, offs_host=None, offs_dev=None):
     """Parallel gather of every mesh into the pinned buffers with the vertices' H2D copy already in flight while the
     faces are gathered (mvr_host_stage_meshes).  overlap=True runs it on the library's worker thread and returns
     (job, keep-alive); the caller joins with mvr_host_stage_meshes_end."""
@@ -215,6 +215,12 @@ def _stage_meshes(v_src, f_src, face_elem_bytes, v_host, f_host, v_dev, f_dev, d
     fp = (C.c_void_p * n)(*[t.data_ptr() for t in f_src])
     fc = (C.c_int64 * n)(*[t.numel() for t in f_src])
     keep = (vp, vc, fp, fc, v_src, f_src, v_host, f_host)
+    if not overlap:      # on the calling thread: offsets written + copied by the same call, ids as wide as f_host (int16 tensor = uint16 ids)
+        with _on(torch.device(device)):
+            L.check(lib.mvr_host_stage_meshes_packed(vp, vc, fp, fc, n, face_elem_bytes, f_host.element_size(), v_host.data_ptr(),
+                                                     f_host.data_ptr(), _ptr(offs_host), v_dev.data_ptr(), f_dev.data_ptr(),
+                                                     _ptr(offs_dev), _stream(device)), "mvr_host_stage_meshes_packed")
+        return None, keep
     if overlap:
         job = lib.mvr_host_stage_meshes_begin(vp, vc, fp, fc, n, face_elem_bytes, v_host.data_ptr(), f_host.data_ptr(),
                                               v_dev.data_ptr(), f_dev.data_ptr(), torch.device(device).index or 0,
@@ -449,7 +455,7 @@ def collate_meshes(meshes, pin_memory: Optional[bool] = None, vert_rgb: Optional
         raise ValueError("narrow_faces=True needs meshes of at most 65536 vertices")
     narrow = small if narrow_faces is None else bool(narrow_faces)
     v_host = torch.empty((sum(nv), 3), dtype=torch.float32, pin_memory=pin)
-    f_host = torch.empty((sum(nf), 3), dtype=torch.int32, pin_memory=pin and not narrow)
+    f_host = torch.empty((sum(nf), 3), dtype=torch.int16 if narrow else torch.int32, pin_memory=pin)
     if len(verts):
         import ctypes as C
         fdt = torch.int32 if all(f.dtype == torch.int32 for f in faces) else torch.int64
@@ -458,12 +464,9 @@ def collate_meshes(meshes, pin_memory: Optional[bool] = None, vert_rgb: Optional
         n = len(v_src)
         vp = (C.c_void_p * n)(*[t.data_ptr() for t in v_src]); vc = (C.c_int64 * n)(*[t.numel() for t in v_src])
         fp = (C.c_void_p * n)(*[t.data_ptr() for t in f_src]); fc = (C.c_int64 * n)(*[t.numel() for t in f_src])
-        L.check(L.load().mvr_host_stage_meshes(vp, vc, fp, fc, n, 8 if fdt == torch.int64 else 4, v_host.data_ptr(),
-                                               f_host.data_ptr(), None, None, None), "mvr_host_stage_meshes")
-    if narrow:      # (loader side, off the step) the low 16 bits of every id: out-of-range ids are clamped by mvr_mesh_prepare either way
-        f16 = torch.empty((sum(nf), 3), dtype=torch.int16, pin_memory=pin)
-        f16.copy_(f_host.clamp(0, 65535))      # int32 -> int16 keeps the low 16 bits (two's complement)
-        f_host = f16
+        lib = L.load()      # narrow: ids saturated to [0, 65535] on the way (out-of-range ids are clamped by mvr_mesh_prepare either way)
+        L.check(lib.mvr_host_stage_meshes_packed(vp, vc, fp, fc, n, 8 if fdt == torch.int64 else 4, 2 if narrow else 4, v_host.data_ptr(),
+                                                 f_host.data_ptr(), None, None, None, None, None), "mvr_host_stage_meshes_packed")
     return HostPackedMeshes(v_host, f_host, nv, nf, vert_rgb=vert_rgb)
 
 
@@ -521,6 +524,7 @@ class PackedMeshes:
         tv, tf = sum(nv), sum(nf)
         job = None
         keep = None
+        offs = None
         if len(verts) == 0:
             v_dev = torch.zeros((0, 3), dtype=torch.float32, device=device)
             f_dev = torch.zeros((0, 3), dtype=torch.int64, device=device)
@@ -534,13 +538,20 @@ class PackedMeshes:
                 # vertices' H2D copy in flight while the faces are gathered: one native call
                 v_src = [_host_array(v, torch.float32) for v in verts]
                 f_src = [_host_array(f, fdt) for f in faces]
+                # ... and to uint16 when every mesh has at most 65536 vertices (MVR_FACES_U16): 5.8 -> 3.8 MB at BASELINE configs[1]
+                narrow = max(nv) <= 65536 and not overlap
+                fdev_t = torch.int16 if narrow else torch.int32
                 v_host = _staging("verts", device, tv * 3, torch.float32)
-                f_host = _staging("faces", device, tf * 3, torch.int32)
+                f_host = _staging("faces16" if narrow else "faces", device, tf * 3, fdev_t)
                 v_dev = torch.empty((tv, 3), dtype=torch.float32, device=device)
-                f_dev = torch.empty((tf, 3), dtype=torch.int32, device=device)
+                f_dev = torch.empty((tf, 3), dtype=fdev_t, device=device)
+                offs_h = None
+                if not overlap:      # the offset table travels with the same call (2B + 2 words, first on the wire)
+                    offs_h = _staging("offs", device, 2 * len(nv) + 2, torch.int32)
+                    offs = torch.empty(2 * len(nv) + 2, dtype=torch.int32, device=device)
                 job, keep = _stage_meshes(v_src, f_src, 8 if fdt == torch.int64 else 4, v_host, f_host, v_dev, f_dev, device,
-                                          overlap)
-        return (v_dev, f_dev, nv, nf, device, vert_rgb, job, keep)
+                                          overlap, offs_h, offs)
+        return (v_dev, f_dev, nv, nf, device, vert_rgb, job, keep, offs)
 
     def finish(self, lazy_chunks: bool = False):
         """Stage (if deferred) or join the staging job (if overlapped), then build the packed device geometry
@@ -555,13 +566,17 @@ class PackedMeshes:
         if pending[0] == "deferred":
             _, verts, faces, device, vert_rgb = pending
             pending = self._stage(verts, faces, device, vert_rgb, overlap=False)
-        v_dev, f_dev, nv, nf, device, vert_rgb, job, keep = pending
+        v_dev, f_dev, nv, nf, device, vert_rgb, job, keep, offs = pending
         if job is not None:
             L.check(L.load().mvr_host_stage_meshes_end(job), "mvr_host_stage_meshes_end")
         if keep is not None:
             _staging_done(device)
         del keep
-        self._init_packed(v_dev, f_dev, nv, nf, device, vert_rgb)
+        offsets = None
+        if offs is not None:
+            from itertools import accumulate
+            offsets = (list(accumulate(nv, initial=0)), list(accumulate(nf, initial=0)), offs)
+        self._init_packed(v_dev, f_dev, nv, nf, device, vert_rgb, offsets)
         return self
 
     @classmethod

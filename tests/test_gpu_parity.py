@@ -903,6 +903,27 @@ def test_mvrenderer_accepts_collated_host_batch(cuda_device):
     img_c, _ = r(collate_meshes(ml), None, a2, el, di)
     img_c.square().mean().backward()
     assert a2.grad is not None and torch.isfinite(a2.grad).all()
+    # the list path stages through mvr_host_stage_meshes_packed: uint16 ids + the offset table in the same call; a mesh with more
+    # than 65536 vertices keeps int32 ids; both give the geometry of the already-packed device arrays
+    g = ops.PackedMeshes([v for v, _ in meshes], [f for _, f in meshes], dev)
+    assert g.faces.dtype == torch.int16
+    assert g.vert_off.tolist() == [0] + list(np.cumsum([v.shape[0] for v, _ in meshes]))
+    assert g.face_off.tolist() == [0] + list(np.cumsum([f.shape[0] for _, f in meshes]))
+    g_dev = ops.PackedMeshes.from_packed(torch.cat([v for v, _ in meshes]).to(dev), torch.cat([f for _, f in meshes]).to(dev),
+                                         [v.shape[0] for v, _ in meshes], [f.shape[0] for _, f in meshes])
+    col = torch.tensor([0.8, 0.7, 0.6], device=dev); lt = torch.tensor([[0.0, 1.0, 0.3]], device=dev)
+
+    def shot(gm):
+        v = [t.to(dev) for t in synth.learned_spherical_views(gm.B, 3, 14)]
+        with torch.no_grad():
+            return ops.render_meshes_from_angles(gm, 3, v[0], v[1], v[2], lt, col, col * 0.5, 48)[0]
+    assert torch.equal(shot(g), shot(g_dev)) and float(shot(g).std()) > 0
+    big = synth.make_mesh(140000, 3)
+    assert big[0].shape[0] > 65536
+    g_big = ops.PackedMeshes([big[0], meshes[0][0]], [big[1], meshes[0][1]], dev)
+    g_big_dev = ops.PackedMeshes.from_packed(torch.cat([big[0], meshes[0][0]]).to(dev), torch.cat([big[1], meshes[0][1]]).to(dev),
+                                             [big[0].shape[0], meshes[0][0].shape[0]], [big[1].shape[0], meshes[0][1].shape[0]])
+    assert g_big.faces.dtype == torch.int32 and torch.equal(shot(g_big), shot(g_big_dev))
 
 
 @pytest.mark.parametrize("chunks,K", [(2, 1), (3, 1), (4, 2), (64, 1)])

@@ -216,6 +216,21 @@ def test_async_mesh_staging_worker_matches_torch_cat():
     assert lib.mvr_host_stage_meshes(vp, vc, fp32, fc, n, 4, vd.data_ptr(), fd.data_ptr(), None, None, None) == 0
     assert torch.equal(torch.cat(f32).reshape(-1), fd)
     assert lib.mvr_host_stage_meshes(vp, vc, fp32, fc, n, 2, vd.data_ptr(), fd.data_ptr(), None, None, None) == -2
+    # uint16 ids, from int64 and from int32 sources; out-of-range ids saturate (mvr_mesh_prepare clamps them to the mesh afterwards)
+    fs_bad = [f.clone() for f in fs]
+    fs_bad[1][0, 0] = -7; fs_bad[1][1, 2] = 70000; fs_bad[3][5, 1] = 65535
+    want = torch.cat(fs_bad).reshape(-1).clamp(0, 65535)
+    for srcs, eb in ((fs_bad, 8), ([f.to(torch.int32) for f in fs_bad], 4)):
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in srcs])
+        f16 = torch.zeros(tf * 3, dtype=torch.int16)
+        offs = torch.zeros(2 * n + 2, dtype=torch.int32)
+        assert lib.mvr_host_stage_meshes_packed(vp, vc, ptrs, fc, n, eb, 2, vd.data_ptr(), f16.data_ptr(), offs.data_ptr(), None, None, None, None) == 0
+        assert torch.equal(f16.to(torch.int64) & 0xFFFF, want) and torch.equal(torch.cat(vs).reshape(-1), vd)
+        assert offs.tolist() == [0] + list(np.cumsum([v.shape[0] for v in vs])) + [0] + list(np.cumsum([f.shape[0] for f in fs]))
+    f32o = torch.zeros(tf * 3, dtype=torch.int32)
+    assert lib.mvr_host_stage_meshes_packed(vp, vc, fp32, fc, n, 4, 4, vd.data_ptr(), f32o.data_ptr(), None, None, None, None, None) == 0
+    assert torch.equal(torch.cat(f32).reshape(-1), f32o)
+    assert lib.mvr_host_stage_meshes_packed(vp, vc, fp32, fc, n, 4, 3, vd.data_ptr(), f32o.data_ptr(), None, None, None, None, None) == -2
 
 
 def test_collate_meshes_packs_like_torch_cat():
