@@ -114,6 +114,11 @@ int mvr_host_stage_meshes_begin(const void* const* vert_srcs, const int64_t* ver
                                 const void* const* face_srcs, const int64_t* face_counts, int n,
                                 int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
                                 float* dev_verts, int32_t* dev_faces, int device, void* stream);
+int mvr_host_stage_meshes_packed_begin(const void* const* vert_srcs, const int64_t* vert_counts,
+                                       const void* const* face_srcs, const int64_t* face_counts, int n,
+                                       int face_elem_bytes, int face_out_bytes, float* pinned_verts, void* pinned_faces,
+                                       int32_t* pinned_offs, float* dev_verts, void* dev_faces, int32_t* dev_offs,
+                                       int device, void* stream);      /* mvr_host_stage_meshes_packed on the worker */
 int mvr_host_stage_meshes_end(int job);
 
 /* -- cameras ------------------------------------------------------------------------------ */

@@ -40,6 +40,8 @@ SIGNATURES = {
                                           _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvr_host_stage_meshes_begin": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                          _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "mvr_host_stage_meshes_packed_begin": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                                _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "mvr_host_stage_meshes_end": (_i, [_i]),
     "mvr_look_at_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mvr_look_at_forward_flagged": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

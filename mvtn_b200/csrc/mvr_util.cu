@@ -136,23 +136,97 @@ extern "C" int mvr_host_gather(const void* const* srcs, const int64_t* counts, i
   return 0;
 }
 
+namespace {
+// One staging job cut into (array, start) work items of kChunk elements; the items are independent, so any set of threads may run them.
+struct StagePlan {
+  const void* const* vert_srcs; const int64_t* vert_counts; const void* const* face_srcs; const int64_t* face_counts;
+  int n, face_elem_bytes, face_out_bytes; float* pinned_verts; void* pinned_faces;
+  std::vector<int64_t> voff, foff, vwork, fwork;
+  int64_t nv = 0, nf = 0;
+  static constexpr int64_t kChunk = 1 << 14;
+  void vert_item(int64_t w) const {
+    const int i = (int)vwork[2 * w];
+    const int64_t s = vwork[2 * w + 1], cnt = std::min<int64_t>(kChunk, vert_counts[i] - s);
+    memcpy(pinned_verts + voff[i] + s, (const float*)vert_srcs[i] + s, (size_t)cnt * sizeof(float));
+  }
+  void face_item(int64_t w) const {
+    const int i = (int)fwork[2 * w];
+    const int64_t s = fwork[2 * w + 1], cnt = std::min<int64_t>(kChunk, face_counts[i] - s);
+    if (face_out_bytes == 2) {      // saturate to [0, 65535]: mvr_mesh_prepare then clamps to the mesh's vertex count, as it does for int32
+      uint16_t* d16 = (uint16_t*)pinned_faces + foff[i] + s;
+      if (face_elem_bytes == 8) {
+        const int64_t* src = (const int64_t*)face_srcs[i] + s;
+        for (int64_t e = 0; e < cnt; ++e) { const int64_t x = src[e]; d16[e] = (uint16_t)(x < 0 ? 0 : (x > 65535 ? 65535 : x)); }
+      } else {
+        const int32_t* src = (const int32_t*)face_srcs[i] + s;
+        for (int64_t e = 0; e < cnt; ++e) { const int32_t x = src[e]; d16[e] = (uint16_t)(x < 0 ? 0 : (x > 65535 ? 65535 : x)); }
+      }
+      return;
+    }
+    int32_t* d = (int32_t*)pinned_faces + foff[i] + s;
+    if (face_elem_bytes == 8) {
+      const int64_t* src = (const int64_t*)face_srcs[i] + s;
+      for (int64_t e = 0; e < cnt; ++e) d[e] = (int32_t)src[e];
+    } else {
+      memcpy(d, (const int32_t*)face_srcs[i] + s, (size_t)cnt * sizeof(int32_t));
+    }
+  }
+};
+
+// Helper threads of the asynchronous staging (mvr_host_stage_meshes*_begin): a private pool, independent of OpenMP -- an OpenMP team
+// started from the staging thread would fight the caller's own (spinning) team for the cores.  The coordinator (the staging thread)
+// publishes a plan and works on it too; helpers sleep on a condition variable between jobs.
+struct GatherPool {
+  std::mutex mu; std::condition_variable cv_work, cv_idle;
+  const StagePlan* plan = nullptr; uint64_t epoch = 0; int busy = 0, nthreads = 0;
+  std::atomic<int64_t> next_v{0}, next_f{0}, done_v{0}, done_f{0};
+  void drain(const StagePlan& p) {
+    for (int64_t w; (w = next_v.fetch_add(1, std::memory_order_relaxed)) < p.nv;) { p.vert_item(w); done_v.fetch_add(1, std::memory_order_release); }
+    for (int64_t w; (w = next_f.fetch_add(1, std::memory_order_relaxed)) < p.nf;) { p.face_item(w); done_f.fetch_add(1, std::memory_order_release); }
+  }
+  void helper(uint64_t seen) {      // seen: the epoch at creation -- a new helper waits for the NEXT job, it never checks out of one it did not join
+    for (;;) {
+      const StagePlan* p;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_work.wait(lk, [&] { return epoch != seen; });
+        seen = epoch; p = plan;
+      }
+      if (p) drain(*p);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (--busy == 0) cv_idle.notify_all();
+      }
+    }
+  }
+  void ensure(int want) {      // (coordinator only)
+    std::lock_guard<std::mutex> lk(mu);
+    while (nthreads < want) { std::thread(&GatherPool::helper, this, epoch).detach(); ++nthreads; }
+  }
+};
+GatherPool* gather_pool() { static GatherPool* g = new GatherPool(); return g; }   // leaked on purpose, like the staging thread
+}  // namespace
+
 // Stage a batch of meshes for the device in ONE parallel region (renderer.py:67-68 + Meshes(...) packing): gather the
 // per-mesh vertex arrays into pinned_verts, enqueue their H2D copy from one thread while the others already gather /
 // narrow the faces into pinned_faces, then enqueue the faces' copy.  HOST pointers except dev_*; faces are int64
-// (face_elem_bytes == 8, narrowed to int32 on the way) or int32.  One fork/join and the vertex copy overlapped with the
-// face gather: the step's time-to-first-kernel is bounded by this call.
+// (face_elem_bytes == 8, narrowed on the way) or int32.  One fork/join and the vertex copy overlapped with the
+// face gather: the step's time-to-first-kernel is bounded by this call.  pooled: run the items on the private helper pool (the
+// caller is the staging thread) instead of an OpenMP team.
 static int stage_meshes_impl(const void* const* vert_srcs, const int64_t* vert_counts,
                              const void* const* face_srcs, const int64_t* face_counts, int n,
                              int face_elem_bytes, float* pinned_verts, void* pinned_faces_any,
                              float* dev_verts, void* dev_faces, void* stream, int face_out_bytes = 4,
-                             int32_t* pinned_offs = nullptr, int32_t* dev_offs = nullptr) {
-  int32_t* pinned_faces = (int32_t*)pinned_faces_any;
-  uint16_t* pinned_faces16 = (uint16_t*)pinned_faces_any;
-  if (n < 0 || (n > 0 && (!vert_srcs || !vert_counts || !face_srcs || !face_counts || !pinned_verts || !pinned_faces))) {
+                             int32_t* pinned_offs = nullptr, int32_t* dev_offs = nullptr, bool pooled = false) {
+  if (n < 0 || (n > 0 && (!vert_srcs || !vert_counts || !face_srcs || !face_counts || !pinned_verts || !pinned_faces_any))) {
     mvr::set_error("mvr_host_stage_meshes: null pointer"); return -1;
   }
   if (face_elem_bytes != 4 && face_elem_bytes != 8) { mvr::set_error("mvr_host_stage_meshes: faces must be int32 or int64"); return -2; }
-  std::vector<int64_t> voff((size_t)n + 1, 0), foff((size_t)n + 1, 0);
+  StagePlan pl;
+  pl.vert_srcs = vert_srcs; pl.vert_counts = vert_counts; pl.face_srcs = face_srcs; pl.face_counts = face_counts;
+  pl.n = n; pl.face_elem_bytes = face_elem_bytes; pl.face_out_bytes = face_out_bytes; pl.pinned_verts = pinned_verts; pl.pinned_faces = pinned_faces_any;
+  std::vector<int64_t>& voff = pl.voff; std::vector<int64_t>& foff = pl.foff;
+  voff.assign((size_t)n + 1, 0); foff.assign((size_t)n + 1, 0);
   for (int i = 0; i < n; ++i) {
     if (vert_counts[i] < 0 || face_counts[i] < 0) { mvr::set_error("mvr_host_stage_meshes: negative count"); return -3; }
     voff[i + 1] = voff[i] + vert_counts[i];      // counts are in ELEMENTS (floats / indices)
@@ -166,48 +240,45 @@ static int stage_meshes_impl(const void* const* vert_srcs, const int64_t* vert_c
       if (e != cudaSuccess) { mvr::set_error("mvr_host_stage_meshes: cudaMemcpyAsync(offsets): %s", cudaGetErrorString(e)); return (int)e; }
     }
   }
-  const int64_t kChunk = 1 << 14;
-  std::vector<int64_t> vwork, fwork;              // (array, start) pairs
-  for (int i = 0; i < n; ++i) for (int64_t s = 0; s < vert_counts[i]; s += kChunk) { vwork.push_back(i); vwork.push_back(s); }
-  for (int i = 0; i < n; ++i) for (int64_t s = 0; s < face_counts[i]; s += kChunk) { fwork.push_back(i); fwork.push_back(s); }
-  const int64_t nv = (int64_t)vwork.size() / 2, nf = (int64_t)fwork.size() / 2;
-  int nthreads = g_host_threads > 0 ? g_host_threads : omp_get_max_threads();
+  const int64_t kChunk = StagePlan::kChunk;
+  for (int i = 0; i < n; ++i) for (int64_t s = 0; s < vert_counts[i]; s += kChunk) { pl.vwork.push_back(i); pl.vwork.push_back(s); }
+  for (int i = 0; i < n; ++i) for (int64_t s = 0; s < face_counts[i]; s += kChunk) { pl.fwork.push_back(i); pl.fwork.push_back(s); }
+  const int64_t nv = pl.nv = (int64_t)pl.vwork.size() / 2, nf = pl.nf = (int64_t)pl.fwork.size() / 2;
+  int nthreads = g_host_threads > 0 ? g_host_threads : (pooled ? (int)std::thread::hardware_concurrency() : omp_get_max_threads());
   if (nthreads > 8) nthreads = 8;                 // memory-bound: more threads only add wake-up latency
+  if (nthreads < 1) nthreads = 1;
   cudaError_t err_v = cudaSuccess;
-#pragma omp parallel num_threads(nthreads)
-  {
-#pragma omp for schedule(dynamic, 1)
-    for (int64_t w = 0; w < nv; ++w) {
-      const int i = (int)vwork[2 * w];
-      const int64_t s = vwork[2 * w + 1], cnt = std::min<int64_t>(kChunk, vert_counts[i] - s);
-      memcpy(pinned_verts + voff[i] + s, (const float*)vert_srcs[i] + s, (size_t)cnt * sizeof(float));
-    }   // implicit barrier: every vertex is staged
-#pragma omp single nowait
+  if (pooled) {
+    GatherPool* g = gather_pool();
+    const int helpers = (int)std::min<int64_t>(nthreads - 1, std::max<int64_t>(nv + nf - 1, 0));
+    g->ensure(helpers);
     {
-      if (dev_verts && voff[n] > 0) err_v = cudaMemcpyAsync(dev_verts, pinned_verts, (size_t)voff[n] * sizeof(float), cudaMemcpyHostToDevice, st);
+      std::lock_guard<std::mutex> lk(g->mu);
+      g->next_v = 0; g->next_f = 0; g->done_v = 0; g->done_f = 0;
+      g->plan = &pl; g->busy = g->nthreads; ++g->epoch;      // every helper checks in (and out) once per job, late ones find no items
     }
+    if (g->nthreads > 0) g->cv_work.notify_all();
+    for (int64_t w; (w = g->next_v.fetch_add(1, std::memory_order_relaxed)) < nv;) { pl.vert_item(w); g->done_v.fetch_add(1, std::memory_order_release); }
+    while (g->done_v.load(std::memory_order_acquire) < nv) std::this_thread::yield();      // every vertex is staged
+    if (dev_verts && voff[n] > 0) err_v = cudaMemcpyAsync(dev_verts, pinned_verts, (size_t)voff[n] * sizeof(float), cudaMemcpyHostToDevice, st);
+    for (int64_t w; (w = g->next_f.fetch_add(1, std::memory_order_relaxed)) < nf;) { pl.face_item(w); g->done_f.fetch_add(1, std::memory_order_release); }
+    while (g->done_f.load(std::memory_order_acquire) < nf) std::this_thread::yield();
+    {      // the plan lives on this stack frame: wait until every helper has let go of it
+      std::unique_lock<std::mutex> lk(g->mu);
+      g->cv_idle.wait(lk, [g] { return g->busy == 0; });
+      g->plan = nullptr;
+    }
+  } else {
+#pragma omp parallel num_threads(nthreads)
+    {
 #pragma omp for schedule(dynamic, 1)
-    for (int64_t w = 0; w < nf; ++w) {
-      const int i = (int)fwork[2 * w];
-      const int64_t s = fwork[2 * w + 1], cnt = std::min<int64_t>(kChunk, face_counts[i] - s);
-      if (face_out_bytes == 2) {      // saturate to [0, 65535]: mvr_mesh_prepare then clamps to the mesh's vertex count, as it does for int32
-        uint16_t* d16 = pinned_faces16 + foff[i] + s;
-        if (face_elem_bytes == 8) {
-          const int64_t* src = (const int64_t*)face_srcs[i] + s;
-          for (int64_t e = 0; e < cnt; ++e) { const int64_t x = src[e]; d16[e] = (uint16_t)(x < 0 ? 0 : (x > 65535 ? 65535 : x)); }
-        } else {
-          const int32_t* src = (const int32_t*)face_srcs[i] + s;
-          for (int64_t e = 0; e < cnt; ++e) { const int32_t x = src[e]; d16[e] = (uint16_t)(x < 0 ? 0 : (x > 65535 ? 65535 : x)); }
-        }
-        continue;
+      for (int64_t w = 0; w < nv; ++w) pl.vert_item(w);      // implicit barrier: every vertex is staged
+#pragma omp single nowait
+      {
+        if (dev_verts && voff[n] > 0) err_v = cudaMemcpyAsync(dev_verts, pinned_verts, (size_t)voff[n] * sizeof(float), cudaMemcpyHostToDevice, st);
       }
-      int32_t* d = pinned_faces + foff[i] + s;
-      if (face_elem_bytes == 8) {
-        const int64_t* src = (const int64_t*)face_srcs[i] + s;
-        for (int64_t e = 0; e < cnt; ++e) d[e] = (int32_t)src[e];
-      } else {
-        memcpy(d, (const int32_t*)face_srcs[i] + s, (size_t)cnt * sizeof(int32_t));
-      }
+#pragma omp for schedule(dynamic, 1)
+      for (int64_t w = 0; w < nf; ++w) pl.face_item(w);
     }
   }
   if (err_v != cudaSuccess) { mvr::set_error("mvr_host_stage_meshes: cudaMemcpyAsync(verts): %s", cudaGetErrorString(err_v)); return (int)err_v; }
@@ -245,8 +316,9 @@ extern "C" int mvr_host_stage_meshes_packed(const void* const* vert_srcs, const 
 namespace {
 struct StageJob {
   const void* const* vert_srcs; const int64_t* vert_counts; const void* const* face_srcs; const int64_t* face_counts;
-  int n, face_elem_bytes; float* pinned_verts; int32_t* pinned_faces; float* dev_verts; int32_t* dev_faces; void* stream;
+  int n, face_elem_bytes; float* pinned_verts; void* pinned_faces; float* dev_verts; void* dev_faces; void* stream;
   int device, status; bool pending, done; char err[512];
+  int face_out_bytes; int32_t* pinned_offs; int32_t* dev_offs;
 };
 struct StageWorker {
   std::mutex mu; std::condition_variable cv_job, cv_done; StageJob job; bool started = false; int next_id = 1, cur_id = 0;
@@ -267,7 +339,7 @@ void stage_worker_loop() {
     }
     if (rc == 0)
       rc = stage_meshes_impl(j.vert_srcs, j.vert_counts, j.face_srcs, j.face_counts, j.n, j.face_elem_bytes, j.pinned_verts,
-                             j.pinned_faces, j.dev_verts, j.dev_faces, j.stream);
+                             j.pinned_faces, j.dev_verts, j.dev_faces, j.stream, j.face_out_bytes, j.pinned_offs, j.dev_offs, true);
     lk.lock();
     w->job.status = rc;
     strncpy(w->job.err, mvr::g_err, sizeof(w->job.err) - 1);
@@ -278,20 +350,39 @@ void stage_worker_loop() {
 }
 }  // namespace
 
-extern "C" int mvr_host_stage_meshes_begin(const void* const* vert_srcs, const int64_t* vert_counts,
-                                           const void* const* face_srcs, const int64_t* face_counts, int n,
-                                           int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
-                                           float* dev_verts, int32_t* dev_faces, int device, void* stream) {
+static int stage_begin_impl(const void* const* vert_srcs, const int64_t* vert_counts, const void* const* face_srcs,
+                            const int64_t* face_counts, int n, int face_elem_bytes, int face_out_bytes, float* pinned_verts,
+                            void* pinned_faces, int32_t* pinned_offs, float* dev_verts, void* dev_faces, int32_t* dev_offs,
+                            int device, void* stream) {
   StageWorker* w = worker();
   std::unique_lock<std::mutex> lk(w->mu);
   if (w->job.pending || (w->cur_id != 0)) { mvr::set_error("mvr_host_stage_meshes_begin: a staging job is already in flight"); return -10; }
   if (!w->started) { std::thread(stage_worker_loop).detach(); w->started = true; }
   w->job = StageJob{vert_srcs, vert_counts, face_srcs, face_counts, n, face_elem_bytes, pinned_verts, pinned_faces, dev_verts,
-                    dev_faces, stream, device, 0, true, false, {0}};
+                    dev_faces, stream, device, 0, true, false, {0}, face_out_bytes, pinned_offs, dev_offs};
   w->cur_id = w->next_id++;
   if (w->next_id <= 0) w->next_id = 1;
   w->cv_job.notify_one();
   return w->cur_id;
+}
+
+extern "C" int mvr_host_stage_meshes_begin(const void* const* vert_srcs, const int64_t* vert_counts,
+                                           const void* const* face_srcs, const int64_t* face_counts, int n,
+                                           int face_elem_bytes, float* pinned_verts, int32_t* pinned_faces,
+                                           float* dev_verts, int32_t* dev_faces, int device, void* stream) {
+  return stage_begin_impl(vert_srcs, vert_counts, face_srcs, face_counts, n, face_elem_bytes, 4, pinned_verts, pinned_faces, nullptr,
+                          dev_verts, dev_faces, nullptr, device, stream);
+}
+
+// mvr_host_stage_meshes_packed on the worker thread (join with mvr_host_stage_meshes_end)
+extern "C" int mvr_host_stage_meshes_packed_begin(const void* const* vert_srcs, const int64_t* vert_counts,
+                                                  const void* const* face_srcs, const int64_t* face_counts, int n,
+                                                  int face_elem_bytes, int face_out_bytes, float* pinned_verts, void* pinned_faces,
+                                                  int32_t* pinned_offs, float* dev_verts, void* dev_faces, int32_t* dev_offs,
+                                                  int device, void* stream) {
+  if (face_out_bytes != 2 && face_out_bytes != 4) { mvr::set_error("mvr_host_stage_meshes_packed_begin: face_out_bytes must be 2 or 4"); return -2; }
+  return stage_begin_impl(vert_srcs, vert_counts, face_srcs, face_counts, n, face_elem_bytes, face_out_bytes, pinned_verts, pinned_faces,
+                          pinned_offs, dev_verts, dev_faces, dev_offs, device, stream);
 }
 
 extern "C" int mvr_host_stage_meshes_end(int job) {

@@ -205,8 +205,9 @@ def _host_gather(srcs, dst: torch.Tensor, elem_bytes: int, narrow: bool):
 
 def _stage_meshes(v_src, f_src, face_elem_bytes, v_host, f_host, v_dev, f_dev, device, overlap, offs_host=None, offs_dev=None):
     """Parallel gather of every mesh into the pinned buffers with the vertices' H2D copy already in flight while the
-    faces are gathered (mvr_host_stage_meshes).  overlap=True runs it on the library's worker thread and returns
-    (job, keep-alive); the caller joins with mvr_host_stage_meshes_end."""
+    faces are gathered (mvr_host_stage_meshes_packed: offsets written + copied by the same call, ids as wide as f_host -- an int16
+    tensor = uint16 ids).  overlap=True runs it on the library's worker thread and returns (job, keep-alive); the caller joins
+    with mvr_host_stage_meshes_end."""
     import ctypes as C
     lib = L.load()
     n = len(v_src)
@@ -215,23 +216,18 @@ def _stage_meshes(v_src, f_src, face_elem_bytes, v_host, f_host, v_dev, f_dev, d
     fp = (C.c_void_p * n)(*[t.data_ptr() for t in f_src])
     fc = (C.c_int64 * n)(*[t.numel() for t in f_src])
     keep = (vp, vc, fp, fc, v_src, f_src, v_host, f_host)
-    if not overlap:      # on the calling thread: offsets written + copied by the same call, ids as wide as f_host (int16 tensor = uint16 ids)
-        with _on(torch.device(device)):
-            L.check(lib.mvr_host_stage_meshes_packed(vp, vc, fp, fc, n, face_elem_bytes, f_host.element_size(), v_host.data_ptr(),
-                                                     f_host.data_ptr(), _ptr(offs_host), v_dev.data_ptr(), f_dev.data_ptr(),
-                                                     _ptr(offs_dev), _stream(device)), "mvr_host_stage_meshes_packed")
-        return None, keep
     if overlap:
-        job = lib.mvr_host_stage_meshes_begin(vp, vc, fp, fc, n, face_elem_bytes, v_host.data_ptr(), f_host.data_ptr(),
-                                              v_dev.data_ptr(), f_dev.data_ptr(), torch.device(device).index or 0,
-                                              _stream(device))
+        job = lib.mvr_host_stage_meshes_packed_begin(vp, vc, fp, fc, n, face_elem_bytes, f_host.element_size(), v_host.data_ptr(),
+                                                     f_host.data_ptr(), _ptr(offs_host), v_dev.data_ptr(), f_dev.data_ptr(),
+                                                     _ptr(offs_dev), torch.device(device).index or 0, _stream(device))
         if job > 0:
             return job, keep
         if job != -10:          # -10: the worker is busy with another batch -> stage synchronously
-            L.check(job, "mvr_host_stage_meshes_begin")
+            L.check(job, "mvr_host_stage_meshes_packed_begin")
     with _on(torch.device(device)):
-        L.check(lib.mvr_host_stage_meshes(vp, vc, fp, fc, n, face_elem_bytes, v_host.data_ptr(), f_host.data_ptr(),
-                                          v_dev.data_ptr(), f_dev.data_ptr(), _stream(device)), "mvr_host_stage_meshes")
+        L.check(lib.mvr_host_stage_meshes_packed(vp, vc, fp, fc, n, face_elem_bytes, f_host.element_size(), v_host.data_ptr(),
+                                                 f_host.data_ptr(), _ptr(offs_host), v_dev.data_ptr(), f_dev.data_ptr(),
+                                                 _ptr(offs_dev), _stream(device)), "mvr_host_stage_meshes_packed")
     return None, keep
 
 
@@ -492,9 +488,9 @@ class PackedMeshes:
         """Deferred construction: validate now, stage + build the device geometry in .finish().  MVRenderer uses it to
         enqueue the camera kernel and build its constants BEFORE the meshes are staged, so that the rasterizer launch
         follows mvr_mesh_prepare with as little host work in between as possible.
-        overlap=True additionally starts the gather + H2D at once on the library's worker thread
-        (mvr_host_stage_meshes_begin); on the B200 boxes measured so far the thread hand-off costs more than it hides
-        (e2e 2.07 vs 1.85 ms at BASELINE configs[1]), so it is off by default."""
+        overlap=True additionally starts the gather + H2D at once on the library's staging thread and its private helper pool
+        (mvr_host_stage_meshes_packed_begin); finish() joins it.  MVRenderer's default since the pool no longer runs an OpenMP team
+        (two teams, the caller's spinning, cost 1.92 vs 1.30 ms per end-to-end step at BASELINE configs[1]; the pool: 1.26)."""
         self = cls.__new__(cls)
         self._pending = None
         self._begin(verts, faces, device, vert_rgb, overlap=overlap, defer=not overlap)
@@ -539,16 +535,15 @@ class PackedMeshes:
                 v_src = [_host_array(v, torch.float32) for v in verts]
                 f_src = [_host_array(f, fdt) for f in faces]
                 # ... and to uint16 when every mesh has at most 65536 vertices (MVR_FACES_U16): 5.8 -> 3.8 MB at BASELINE configs[1]
-                narrow = max(nv) <= 65536 and not overlap
+                narrow = max(nv) <= 65536
                 fdev_t = torch.int16 if narrow else torch.int32
                 v_host = _staging("verts", device, tv * 3, torch.float32)
                 f_host = _staging("faces16" if narrow else "faces", device, tf * 3, fdev_t)
                 v_dev = torch.empty((tv, 3), dtype=torch.float32, device=device)
                 f_dev = torch.empty((tf, 3), dtype=fdev_t, device=device)
-                offs_h = None
-                if not overlap:      # the offset table travels with the same call (2B + 2 words, first on the wire)
-                    offs_h = _staging("offs", device, 2 * len(nv) + 2, torch.int32)
-                    offs = torch.empty(2 * len(nv) + 2, dtype=torch.int32, device=device)
+                # the offset table travels with the same call (2B + 2 words, first on the wire)
+                offs_h = _staging("offs", device, 2 * len(nv) + 2, torch.int32)
+                offs = torch.empty(2 * len(nv) + 2, dtype=torch.int32, device=device)
                 job, keep = _stage_meshes(v_src, f_src, 8 if fdt == torch.int64 else 4, v_host, f_host, v_dev, f_dev, device,
                                           overlap, offs_h, offs)
         return (v_dev, f_dev, nv, nf, device, vert_rgb, job, keep, offs)
@@ -946,6 +941,7 @@ class _MeshRenderFromAngles(torch.autograd.Function):
         a, e, d, R, T, Cc, bad = _look_at_launch(azim, elev, dist, sink)
         if after_cameras is not None and sink is None:
             after_cameras(bad)
+        geom.finish(lazy_chunks=True)      # a deferred / worker-thread staging (PackedMeshes.begin) ends here, behind the camera launch
         cfg, saved, images, extras = _mesh_forward_launch(geom, M, R, T, Cc, Cc if light is None else light, obj_rgb, bg_rgb,
                                                           k00, k11, z_clip, H, W, K, flags, False, out_norm, out_dtype)
         ctx.set_materialize_grads(False)

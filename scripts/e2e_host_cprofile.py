@@ -5,10 +5,6 @@ here = os.path.dirname(os.path.abspath(__file__))
 src = open(os.path.join(here, "e2e_host_profile.py")).read().split("for _ in range(10):")[0]
 g = {"__file__": os.path.join(here, "e2e_host_profile.py"), "__name__": "prof"}
 exec(compile(src, "e2e_host_profile.py", "exec"), g)
-if len(sys.argv) > 1 and sys.argv[1] == "list":
-    g["host"] = g["ml"]
-    for n in ("mvr_host_stage_meshes",):
-        g["wrap"](n)
 step = g["step"]
 for _ in range(20):
     step(None)

@@ -10,9 +10,9 @@ from mvtn_b200 import _lib as L
 dev = torch.device("cuda:0")
 B, M, S = 32, 12, 224
 ml = [Meshes([v], [f]) for v, f in synth.make_meshes(B, 10000, 1236)]
-host = collate_meshes(ml)
+host = ml if "list" in sys.argv[1:] else collate_meshes(ml)      # list: the reference's python list of per-object CPU meshes
 az, el, di = (t.contiguous().pin_memory() for t in synth.circular_views(B, M))
-r = MVRenderer(M, image_size=S, pc_rendering=False, light_direction="fixed").to(dev)
+r = MVRenderer(M, image_size=S, pc_rendering=False, light_direction="fixed", stage_overlap="overlap" in sys.argv[1:]).to(dev)
 cot = torch.randn(B, M, 3, S, S, device=dev) / (3 * S * S)
 g_host = torch.empty(3, B, M, pin_memory=True)
 st = torch.cuda.current_stream()
@@ -30,7 +30,7 @@ def wrap(name):
         return rc
     setattr(lib, name, w)
 
-for n in ("mvr_look_at_forward", "mvr_look_at_forward_flagged", "mvr_mesh_prepare", "mvr_mesh_prepare_range", "mvr_mesh_forward", "mvr_mesh_backward", "mvr_mesh_backward_angles", "mvr_look_at_backward"):
+for n in ("mvr_host_stage_meshes_packed", "mvr_host_stage_meshes_packed_begin", "mvr_host_stage_meshes_end", "mvr_look_at_forward", "mvr_look_at_forward_flagged", "mvr_mesh_prepare", "mvr_mesh_prepare_range", "mvr_mesh_forward", "mvr_mesh_backward", "mvr_mesh_backward_angles", "mvr_look_at_backward"):
     wrap(n)
 
 def step(rec):

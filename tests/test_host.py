@@ -381,3 +381,36 @@ def test_collate_meshes_narrows_faces_to_uint16_when_it_can():
     import pytest
     with pytest.raises(ValueError):
         collate_meshes([Meshes([huge], [fhuge])], pin_memory=False, narrow_faces=True)
+
+
+def test_async_packed_staging_on_the_helper_pool_matches_the_synchronous_call():
+    """mvr_host_stage_meshes_packed_begin/_end: the gather runs on the staging thread + its private helper pool (no OpenMP team);
+    same bytes as the synchronous call for ragged batches, repeated jobs (pool reuse), a single tiny mesh (fewer items than
+    threads) and an empty batch."""
+    import ctypes as C
+    from mvtn_b200 import synth
+    lib = _lib.load()
+    cases = [[synth.make_mesh(nf, 60 + i) for i, nf in enumerate((300, 50000, 60, 2200, 9000))], [synth.make_mesh(12, 3)],
+             [synth.make_mesh(nf, 80 + i) for i, nf in enumerate((40000, 40000, 40000))]]
+    for rep in range(3):
+        for meshes in cases:
+            vs = [v for v, _ in meshes]; fs = [f for _, f in meshes]
+            n = len(vs); tv = sum(v.shape[0] for v in vs); tf = sum(f.shape[0] for f in fs)
+            vp = (C.c_void_p * n)(*[t.data_ptr() for t in vs]); vc = (C.c_int64 * n)(*[t.numel() for t in vs])
+            fp = (C.c_void_p * n)(*[t.data_ptr() for t in fs]); fc = (C.c_int64 * n)(*[t.numel() for t in fs])
+            for out_bytes, dt in ((2, torch.int16), (4, torch.int32)):
+                got, want = [], []
+                for sync in (False, True):
+                    vd = torch.zeros(tv * 3); fd = torch.zeros(tf * 3, dtype=dt); offs = torch.zeros(2 * n + 2, dtype=torch.int32)
+                    if sync:
+                        assert lib.mvr_host_stage_meshes_packed(vp, vc, fp, fc, n, 8, out_bytes, vd.data_ptr(), fd.data_ptr(), offs.data_ptr(),
+                                                                None, None, None, None) == 0
+                    else:
+                        job = lib.mvr_host_stage_meshes_packed_begin(vp, vc, fp, fc, n, 8, out_bytes, vd.data_ptr(), fd.data_ptr(),
+                                                                     offs.data_ptr(), None, None, None, 0, None)
+                        assert job > 0 and lib.mvr_host_stage_meshes_end(job) == 0
+                    (want if sync else got).extend([vd, fd, offs])
+                assert all(torch.equal(a, b) for a, b in zip(got, want))
+                assert torch.equal(got[0], torch.cat(vs).reshape(-1)) and torch.equal(got[1].to(torch.int64) & (0xFFFF if out_bytes == 2 else -1),
+                                                                                         torch.cat(fs).reshape(-1))
+    assert lib.mvr_host_stage_meshes_packed_begin(None, None, None, None, 0, 8, 3, None, None, None, None, None, None, 0, None) == -2
