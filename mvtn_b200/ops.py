@@ -188,7 +188,7 @@ def _hw(image_size):
 
 def _host_array(t: torch.Tensor, dtype) -> torch.Tensor:
     """Contiguous CPU view of `t` in `dtype`; the common case (already so) costs three attribute reads."""
-    if t.dtype == dtype and t.device.type == "cpu" and t.is_contiguous():
+    if t.dtype == dtype and t.is_cpu and t.is_contiguous():
         return t
     return t.detach().to(device="cpu", dtype=dtype).contiguous()
 
@@ -212,9 +212,9 @@ def _stage_meshes(v_src, f_src, face_elem_bytes, v_host, f_host, v_dev, f_dev, d
     lib = L.load()
     n = len(v_src)
     vp = (C.c_void_p * n)(*[t.data_ptr() for t in v_src])
-    vc = (C.c_int64 * n)(*[t.numel() for t in v_src])
+    vc = (C.c_int64 * n)(*[3 * t.shape[0] for t in v_src])
     fp = (C.c_void_p * n)(*[t.data_ptr() for t in f_src])
-    fc = (C.c_int64 * n)(*[t.numel() for t in f_src])
+    fc = (C.c_int64 * n)(*[3 * t.shape[0] for t in f_src])
     keep = (vp, vc, fp, fc, v_src, f_src, v_host, f_host)
     if overlap:
         job = lib.mvr_host_stage_meshes_packed_begin(vp, vc, fp, fc, n, face_elem_bytes, f_host.element_size(), v_host.data_ptr(),
@@ -525,8 +525,8 @@ class PackedMeshes:
             v_dev = torch.zeros((0, 3), dtype=torch.float32, device=device)
             f_dev = torch.zeros((0, 3), dtype=torch.int64, device=device)
         else:
-            fdt = torch.int32 if all(f.dtype == torch.int32 for f in faces) else torch.int64
-            if all(v.is_cuda for v in verts) and all(f.is_cuda for f in faces):
+            fdt = torch.int32 if faces[0].dtype == torch.int32 and all(f.dtype == torch.int32 for f in faces) else torch.int64
+            if verts[0].is_cuda and all(v.is_cuda for v in verts) and all(f.is_cuda for f in faces):
                 v_dev = torch.cat([v.detach().to(torch.float32) for v in verts], 0)
                 f_dev = torch.cat([f.detach().to(fdt) for f in faces], 0)
             else:
@@ -562,16 +562,19 @@ class PackedMeshes:
             _, verts, faces, device, vert_rgb = pending
             pending = self._stage(verts, faces, device, vert_rgb, overlap=False)
         v_dev, f_dev, nv, nf, device, vert_rgb, job, keep, offs = pending
+        offsets = None
+        if offs is not None:
+            from itertools import accumulate
+            offsets = (list(accumulate(nv, initial=0)), list(accumulate(nf, initial=0)), offs)
+        # everything that does not read the staged bytes happens BEFORE the join: while the staging thread still gathers, this one
+        # is idle anyway
+        self._init_packed(v_dev, f_dev, nv, nf, device, vert_rgb, offsets, prepare=False)
         if job is not None:
             L.check(L.load().mvr_host_stage_meshes_end(job), "mvr_host_stage_meshes_end")
         if keep is not None:
             _staging_done(device)
         del keep
-        offsets = None
-        if offs is not None:
-            from itertools import accumulate
-            offsets = (list(accumulate(nv, initial=0)), list(accumulate(nf, initial=0)), offs)
-        self._init_packed(v_dev, f_dev, nv, nf, device, vert_rgb, offsets)
+        self.refresh()
         return self
 
     @classmethod

@@ -103,7 +103,10 @@ class MVRenderer(nn.Module):
             memory -- faces narrowed to uint16 ids when every mesh has at most 65536 vertices -- and copied by the library's staging
             thread and its private helper pool (mvr_host_stage_meshes_packed_begin) WHILE this thread builds the cameras and launches
             the camera kernel; joined right in front of mvr_mesh_prepare.  False: the same gather on the calling thread (OpenMP team).
-            1.29 -> 1.26 ms per end-to-end step at 32 x 12 views (1.37 -> 1.33 with OMP_WAIT_POLICY=passive).
+            Per end-to-end step at 32 x 12 views: 1.37 -> 1.29 ms with OMP_WAIT_POLICY=passive (what bench.py runs under: the
+            calling thread's OpenMP team would have to be woken for every batch), 1.27 vs 1.28 with the policy unset (the team is still
+            spinning from the previous batch: no gain, no loss); with OMP_WAIT_POLICY=active every core is taken by a spinning OpenMP
+            worker and the staging threads queue behind them (1.26 ... 1.45 ms vs 1.29) -- pass False there.
         h2d_chunks: how many groups of objects a collated host batch (collate_meshes) travels in (default 1).  With k > 1 group c
             is prepared and rendered as soon as its own copy has landed, while group c + 1 is still on the bus (one forward and
             one backward launch per group, same images / fragments / gradients bit for bit).  Measured on B200 it does NOT pay at
