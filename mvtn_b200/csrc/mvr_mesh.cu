@@ -592,7 +592,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   int rc = check_mesh_common("mvr_mesh_forward", B, M, H, W, K, total_verts, total_faces, max_verts);
   if (rc) return rc;
   const int64_t N = (int64_t)B * M;
-  if (counters) {           // the call owns the counters: zeroed here, so that the caller does not pay a fill launch for them
+  if (counters && N == 0) {           // the call owns the counters: zeroed by mesh_project_kernel, in front of the kernels that count
     cudaError_t ce = cudaMemsetAsync(counters, 0, MVR_NUM_COUNTERS * sizeof(int64_t), (cudaStream_t)stream);
     if (ce != cudaSuccess) { set_error("mvr_mesh_forward: cudaMemsetAsync: %s", cudaGetErrorString(ce)); return (int)ce; }
   }
@@ -644,7 +644,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
     p.flags &= ~(MVR_WS_KEYS_ARMED | MVR_WS_REARM_KEYS);
     cudaError_t e = cudaMemsetAsync(wb + w.flags, 0xFF, 4 * sizeof(int), st);      // arms WSF_CLIP
     if (e != cudaSuccess) { set_error("mvr_mesh_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
-    rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, z_clip, false, workspace, st);
+    rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, z_clip, false, workspace, st, (long long*)counters);
     if (rc) return rc;
     rc = launch_mesh_forward_tiled(p, w, workspace, B, M, max_faces, zbuf || bary || dists, st);
     if (rc) return rc;
@@ -655,7 +655,7 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
   const size_t plane_bytes = (flags & MVR_WS_KEYS_ARMED) ? 0 : (size_t)N * HW * 8;
   cudaError_t e = cudaMemsetAsync(wb + w.flags, 0xFF, (w.keys - w.flags) + plane_bytes, st);
   if (e != cudaSuccess) { set_error("mvr_mesh_forward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
-  rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, z_clip, false, workspace, st);
+  rc = launch_project("mesh_project_kernel", g, w, geometry, vert_off, R, T, B, M, H, W, max_verts, k00, k11, z_clip, false, workspace, st, (long long*)counters);
   if (rc) return rc;
   const size_t tab_smem = ((size_t)W + H) * sizeof(float);
   const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;

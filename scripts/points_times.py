@@ -20,7 +20,7 @@ def step():
 for _ in range(5): step()
 torch.cuda.synchronize()
 tot = 0.0
-for nm in ("look_at_forward_kernel", "pixel_table_kernel", "points_bin_kernel", "points_bin_scan_kernel", "points_tile_kernel", "points_backward_kernel", "points_backward_reduce", "look_at_backward_kernel"):
+for nm in ("look_at_forward_one_cta_kernel", "pixel_table_kernel", "points_bin_kernel", "points_bin_scan_kernel", "points_tile_kernel", "points_backward_kernel", "points_backward_reduce", "look_at_backward_kernel"):
     lib.mvr_profile_enable(nm.encode())
     for _ in range(5): step()
     t, n = ctypes.c_double(0), ctypes.c_int(0)

@@ -95,6 +95,33 @@ def test_rotation_guard_flag_matches_oracle(oracle, cuda_device):
     assert int(bad) == oracle.count_invalid_rotations(Ro) == 2
 
 
+@pytest.mark.parametrize("n", [1, 300, 4096, 4097, 20000])
+def test_rotation_flag_device_word_and_pinned_word_agree(cuda_device, n):
+    """Up to 4096 views ONE CTA owns the count: no memset in front of the camera kernel, and with a FlagSink the kernel stores the
+    count straight into the pinned host word (no copy behind it); above, the multi-CTA kernel + memset + copy.  Same cameras, same
+    count, on the device word and on the host word, on both sides of the threshold and on repeated use of a pooled sink."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(n)
+    az = torch.rand(n, generator=g) * 360 - 180; el = torch.rand(n, generator=g) * 160 - 80; di = torch.rand(n, generator=g) + 1.5
+    bad_at = sorted(set(int(i) for i in torch.randint(0, n, (min(n, 5),), generator=g)))
+    for k, i in enumerate(bad_at):
+        if k % 2: di[i] = 0.0
+        else: az[i] = float("nan")
+    az, el, di = az.to(dev), el.to(dev), di.to(dev)
+    a, e, d, R0, T0, C0, bad0 = ops._look_at_launch(az, el, di)
+    assert int(bad0) == len(bad_at)
+    for _ in range(3):
+        sink = ops.FlagSink.get(dev)
+        _, _, _, R1, T1, C1, bad1 = ops._look_at_launch(az, el, di, sink)
+        assert sink.read() == len(bad_at) == int(bad1)
+        assert torch.equal(R0.nan_to_num(7.0), R1.nan_to_num(7.0)) and torch.equal(T0.nan_to_num(7.0), T1.nan_to_num(7.0))
+    # all-valid launch after an invalid one: the word is rewritten, not accumulated
+    sink = ops.FlagSink.get(dev)
+    ok = torch.ones(n, device=dev)
+    ops._look_at_launch(ok * 30, ok * 20, ok * 2.2, sink)
+    assert sink.read() == 0
+
+
 # ------------------------------------------------------------------------------------------------- meshes
 CUBE_V = torch.tensor([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]],
                       dtype=torch.float32) * 0.55
