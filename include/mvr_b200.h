@@ -124,12 +124,13 @@ int mvr_host_stage_meshes_end(int job);
 /* -- cameras ------------------------------------------------------------------------------ */
 /* look_at_view_transform(dist, elev, azim) + camera_position_from_spherical_angles
  * (renderer.py:79-80,122-123,168; ops.py:160) fused with util.py:403-420
- * check_valid_rotation_matrix: *invalid_count = number of matrices failing the check (the call zeroes it first).
- * azim/elev in degrees, n = B*M.  C (n,3) = camera centres (may be NULL). */
+ * check_valid_rotation_matrix: *invalid_count = number of matrices failing the check (the call owns the word: up to 4096 views one
+ * CTA counts and stores it, no memset; above, memset + atomics).  azim/elev in degrees, n = B*M.  C (n,3) = camera centres (may be NULL). */
 int mvr_look_at_forward(const float* azim, const float* elev, const float* dist, int n, float* R,
                         float* T, float* C, int* invalid_count, void* stream);
-/* The same with the flag sent to the host behind the kernel: host_flag (pinned int) receives *invalid_count by an asynchronous
- * copy, and `event` (cudaEvent_t) is recorded behind the copy -- the rotation guard (ops.py:156-165) waits for that event only. */
+/* The same with the flag sent to the host behind the kernel: host_flag (pinned int) receives *invalid_count -- stored by the kernel
+ * itself when n <= 4096 and the word is device-addressable (pinned memory under unified addressing), by an asynchronous copy
+ * otherwise -- and `event` (cudaEvent_t) is recorded behind it: the rotation guard (ops.py:156-165) waits for that event only. */
 int mvr_look_at_forward_flagged(const float* azim, const float* elev, const float* dist, int n, float* R, float* T, float* C,
                                 int* invalid_count, int* host_flag, void* event, void* stream);
 /* autograd backward of the above: (gR, gT, gC) -> (g_azim, g_elev, g_dist); any g* input may be NULL */
