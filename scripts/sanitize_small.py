@@ -1,7 +1,8 @@
 """Tiny forward + backward of both paths (mesh: scatter + shade, strip and tile backward, K = 1 and 2, a clipped view, the
 tile-binned forward with its TMA bulk copies, vertex gradients with the warp-aggregated scatter, the soft shaders, a collated batch
 rendered in h2d_chunks groups; points: tiled and generic K, the clustered binning (> 4096 points: DSMEM counters), point / colour
-gradients; the view regulariser) for compute-sanitizer:   compute-sanitizer --tool memcheck|racecheck python scripts/sanitize_small.py"""
+gradients; the view regulariser; the one-node mesh path from a python list of host meshes -- camera kernel that stores its flag into
+the pinned word, staging threads, backward ending in the angle gradients; the multi-CTA camera kernel) for compute-sanitizer:   compute-sanitizer --tool memcheck|racecheck python scripts/sanitize_small.py"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -74,3 +75,19 @@ for dt, S in ((torch.float32, 48), (torch.bfloat16, 48), (torch.float32, 30)):  
     y.backward(torch.ones_like(y))
     torch.cuda.synchronize()
     print("regularize", dt, S, float(y.float().sum()), float(x.grad.float().abs().sum()))
+# one-node path: camera kernel that owns its flag (stored into the pinned word by the kernel), list of host meshes staged on the
+# library's threads (uint16 ids + offsets in one call), backward ending in the angle gradients (mesh_backward_finish_kernel + look_at)
+from mvtn_b200 import MVRenderer, Meshes
+r = MVRenderer(3, image_size=48, pc_rendering=False, light_direction="fixed").to(dev)
+for near_cam in (False, True):
+    a, e, d = (t.to(dev).clone().requires_grad_() for t in (near if near_cam else views))
+    img, cams = r([Meshes([v_], [f_]) for v_, f_ in meshes], None, a, e, d)
+    img.sum().backward()
+    torch.cuda.synchronize()
+    print("mesh from angles (list staging, fused camera backward)", near_cam, float(img.detach().sum()), float(a.grad.abs().sum()), float(d.grad.abs().sum()))
+n_big = 5000                                                            # multi-CTA camera kernel (> 4096 views) + pooled sink
+g_ = torch.Generator().manual_seed(3)
+az_b = (torch.rand(n_big, generator=g_) * 360 - 180).to(dev); az_b[17] = float("nan")
+sink = ops.FlagSink.get(dev)
+ops._look_at_launch(az_b, az_b * 0 + 20, az_b * 0 + 2.2, sink)
+print("cameras", n_big, "invalid:", sink.read())
