@@ -8,6 +8,7 @@
 #include <mutex>
 #include <thread>
 #include <omp.h>
+#include <pthread.h>
 #include <vector>
 
 #include "mvr_common.cuh"
@@ -204,7 +205,10 @@ struct GatherPool {
     while (nthreads < want) { std::thread(&GatherPool::helper, this, epoch).detach(); ++nthreads; }
   }
 };
-GatherPool* gather_pool() { static GatherPool* g = new GatherPool(); return g; }   // leaked on purpose, like the staging thread
+// Leaked on purpose, like the staging thread.  After fork() the child has none of the threads (and possibly a locked mutex inside the
+// old object): stage_atfork_child() swaps in a fresh pool and a fresh worker, so that the child starts its own threads on first use.
+GatherPool* g_gather_pool = nullptr;
+GatherPool* gather_pool() { return g_gather_pool; }      // created together with the worker (worker())
 }  // namespace
 
 // Stage a batch of meshes for the device in ONE parallel region (renderer.py:67-68 + Meshes(...) packing): gather the
@@ -323,7 +327,13 @@ struct StageJob {
 struct StageWorker {
   std::mutex mu; std::condition_variable cv_job, cv_done; StageJob job; bool started = false; int next_id = 1, cur_id = 0;
 };
-StageWorker* worker() { static StageWorker* w = new StageWorker(); return w; }   // leaked on purpose: outlives exit handlers
+StageWorker* g_stage_worker = nullptr;
+void stage_atfork_child() { g_stage_worker = new StageWorker(); g_gather_pool = new GatherPool(); }
+StageWorker* worker() {      // leaked on purpose: outlives exit handlers
+  static std::once_flag once;
+  std::call_once(once, [] { g_stage_worker = new StageWorker(); g_gather_pool = new GatherPool(); pthread_atfork(nullptr, nullptr, stage_atfork_child); });
+  return g_stage_worker;
+}
 
 void stage_worker_loop() {
   StageWorker* w = worker();

@@ -414,3 +414,37 @@ def test_async_packed_staging_on_the_helper_pool_matches_the_synchronous_call():
                 assert torch.equal(got[0], torch.cat(vs).reshape(-1)) and torch.equal(got[1].to(torch.int64) & (0xFFFF if out_bytes == 2 else -1),
                                                                                          torch.cat(fs).reshape(-1))
     assert lib.mvr_host_stage_meshes_packed_begin(None, None, None, None, 0, 8, 3, None, None, None, None, None, None, 0, None) == -2
+
+
+def test_async_staging_survives_fork():
+    """The staging thread and its helper pool do not exist in a forked child (a DataLoader worker): the library starts fresh ones
+    there instead of waiting for threads that are gone."""
+    import ctypes as C
+    import os
+    from mvtn_b200 import synth
+    lib = _lib.load()
+    meshes = [synth.make_mesh(nf, 90 + i) for i, nf in enumerate((3000, 50000, 700))]
+    vs = [v for v, _ in meshes]; fs = [f for _, f in meshes]
+    n = len(vs); tv = sum(v.shape[0] for v in vs); tf = sum(f.shape[0] for f in fs)
+    vp = (C.c_void_p * n)(*[t.data_ptr() for t in vs]); vc = (C.c_int64 * n)(*[t.numel() for t in vs])
+    fp = (C.c_void_p * n)(*[t.data_ptr() for t in fs]); fc = (C.c_int64 * n)(*[t.numel() for t in fs])
+
+    def job():
+        vd = torch.zeros(tv * 3); fd = torch.zeros(tf * 3, dtype=torch.int16); offs = torch.zeros(2 * n + 2, dtype=torch.int32)
+        j = lib.mvr_host_stage_meshes_packed_begin(vp, vc, fp, fc, n, 8, 2, vd.data_ptr(), fd.data_ptr(), offs.data_ptr(), None, None, None, 0, None)
+        return j > 0 and lib.mvr_host_stage_meshes_end(j) == 0 and torch.equal(vd, torch.cat(vs).reshape(-1)) and torch.equal(fd.to(torch.int64) & 0xFFFF, torch.cat(fs).reshape(-1))
+
+    assert job()                      # threads exist in the parent now
+    pid = os.fork()
+    if pid == 0:
+        ok = False
+        try:
+            import signal
+            signal.alarm(60)          # a hang (waiting for threads that do not exist) must not outlive the test
+            torch.set_num_threads(1)  # (libgomp's own team does not survive fork either: keep torch's checks below serial)
+            ok = job() and job()
+        finally:
+            os._exit(0 if ok else 1)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+    assert job()                      # and the parent's threads are untouched
