@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) look_at_forward_one_cta_kernel(const floa
                                                                       float* __restrict__ T, float* __restrict__ C,
                                                                       int* __restrict__ invalid_count, int* host_flag) {
   __shared__ int s_bad;
+  pdl_enter();
   if (threadIdx.x == 0) s_bad = 0;
   __syncthreads();
   int bad = 0;
@@ -104,7 +105,7 @@ static const int kLookAtOneCtaMax = 4096;
 static int look_at_forward_impl(const float* azim, const float* elev, const float* dist, int n, float* R, float* T, float* C,
                                 int* invalid_count, int* host_flag, void* stream) {
   if (n > 0 && n <= kLookAtOneCtaMax) {
-    MVR_LAUNCH(look_at_forward_one_cta_kernel, 1, 256, 0, (cudaStream_t)stream, azim, elev, dist, n, R, T, C, invalid_count, host_flag);
+    MVR_LAUNCH_PDL(look_at_forward_one_cta_kernel, 1, 256, 0, (cudaStream_t)stream, azim, elev, dist, n, R, T, C, invalid_count, host_flag);
     return mvr::check_launch("look_at_forward_one_cta_kernel");
   }
   if (invalid_count) {      // the call owns the flag: zeroed here, so that the caller does not pay a fill launch for it

@@ -31,6 +31,34 @@ void prof_end(const char* name, cudaStream_t st);
     mvr::prof_end(#kernel, st);                                 \
   } while (0)
 
+// Programmatic dependent launch (on unless MVR_PDL=0): a kernel launched through MVR_LAUNCH_PDL may be scheduled while its predecessor in
+// the stream is still draining; pdl_enter() -- the FIRST statement of such a kernel -- blocks until the predecessor has completed
+// and its writes are visible, then lets the kernel behind this one be scheduled in turn.  Only the launch latency is hidden; no
+// kernel touches memory before its predecessor is done (0.800 -> 0.786 ms per resident mesh step at BASELINE configs[1], six edges).
+// Not used on a capturing stream.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled(cudaStream_t st);
+#define MVR_LAUNCH_PDL(kernel, grid, block, smem, st, ...)                                   \
+  do {                                                                                       \
+    mvr::prof_begin(#kernel, st);                                                            \
+    if (mvr::pdl_enabled(st)) {                                                              \
+      cudaLaunchConfig_t cfg_ = {};                                                          \
+      cfg_.gridDim = dim3(grid); cfg_.blockDim = dim3(block);                                \
+      cfg_.dynamicSmemBytes = smem; cfg_.stream = st;                                        \
+      cudaLaunchAttribute at_[1];                                                            \
+      at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                        \
+      at_[0].val.programmaticStreamSerializationAllowed = 1;                                 \
+      cfg_.attrs = at_; cfg_.numAttrs = 1;                                                   \
+      cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                        \
+    } else {                                                                                 \
+      kernel<<<grid, block, smem, st>>>(__VA_ARGS__);                                        \
+    }                                                                                        \
+    mvr::prof_end(#kernel, st);                                                              \
+  } while (0)
+
 // [upstream] rasterization_utils PixToNonSquareNdc -- NDC coordinate of the centre of pixel i.
 __host__ __device__ __forceinline__ float pix_to_ndc(int i, int S1, int S2) {
   float range = 2.0f;

@@ -42,6 +42,7 @@ template <typename IdxT>
 __global__ void geom_pack_faces_kernel(const IdxT* __restrict__ faces, const int* __restrict__ vert_off,
                                        const int* __restrict__ face_off, const float4* __restrict__ verts4,
                                        int4* __restrict__ faces4, double* __restrict__ nacc) {
+  pdl_enter();
   const int b = blockIdx.y;
   const int f0 = face_off[b], F = face_off[b + 1] - f0;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,6 +125,7 @@ __global__ void geom_normals_bwd_face_kernel(const int4* __restrict__ faces4, co
 
 __global__ void geom_finish_normals_kernel(const double* __restrict__ nacc, int64_t tv, const float4* __restrict__ verts4,
                                            float4* __restrict__ normals4, float4* __restrict__ xn8) {
+  pdl_enter();
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= tv) return;
   const float x = (float)nacc[3 * v], y = (float)nacc[3 * v + 1], z = (float)nacc[3 * v + 2];
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(NT, MINB) mesh_scatter_kernel(const MeshParams
   __shared__ int s_q[SC_QCAP * NT / 256];                         // candidates of the round: slot | x << 8 | y << 20
   __shared__ int s_big[NT];
   __shared__ int s_cnt2[2][2];                         // per round parity: [0] candidates, [1] big faces
+  pdl_enter();
   __shared__ __align__(16) int4 s_faces[2][NT];      // face records of two rounds: TMA bulk-copy destinations
   __shared__ __align__(8) unsigned long long s_mbar[2];
   extern __shared__ float s_tab[];                     // pixel centres: xf[W], yf[H]
@@ -369,6 +372,7 @@ __global__ void __launch_bounds__(NT, MINB) mesh_scatter_kernel(const MeshParams
 // trips (face -> vertex records) of pixel j then overlap with those of the other warps only.
 template <bool EXACT, int MINB, int PPT, bool VRGB>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_shade_kernel(const MeshParams p, int tiles_x) {
+  pdl_enter();
   const int b = blockIdx.z, m = blockIdx.y, n = b * p.M + m;
   int ty, tx;
   tile_rc(blockIdx.x, tiles_x, ty, tx);
@@ -494,11 +498,11 @@ extern "C" int mvr_mesh_prepare_range(const float* verts, const void* faces, con
              (flags & MVR_RGB_PER_ELEMENT) ? vert_rgb + 3 * vert_begin : nullptr, nv, verts4 + vert_begin, rgb4 + vert_begin, nacc + 3 * vert_begin);
   if (total_faces > 0 && max_faces > 0) {
     dim3 grid((max_faces + tb - 1) / tb, obj_end - obj_begin);
-    if (flags & MVR_FACES_I64) MVR_LAUNCH(geom_pack_faces_kernel<long long>, grid, tb, 0, st, (const long long*)faces, vert_off + obj_begin, face_off + obj_begin, verts4, faces4, nacc);
-    else if (flags & MVR_FACES_U16) MVR_LAUNCH(geom_pack_faces_kernel<unsigned short>, grid, tb, 0, st, (const unsigned short*)faces, vert_off + obj_begin, face_off + obj_begin, verts4, faces4, nacc);
-    else MVR_LAUNCH(geom_pack_faces_kernel<int>, grid, tb, 0, st, (const int*)faces, vert_off + obj_begin, face_off + obj_begin, verts4, faces4, nacc);
+    if (flags & MVR_FACES_I64) MVR_LAUNCH_PDL(geom_pack_faces_kernel<long long>, grid, tb, 0, st, (const long long*)faces, vert_off + obj_begin, face_off + obj_begin, verts4, faces4, nacc);
+    else if (flags & MVR_FACES_U16) MVR_LAUNCH_PDL(geom_pack_faces_kernel<unsigned short>, grid, tb, 0, st, (const unsigned short*)faces, vert_off + obj_begin, face_off + obj_begin, verts4, faces4, nacc);
+    else MVR_LAUNCH_PDL(geom_pack_faces_kernel<int>, grid, tb, 0, st, (const int*)faces, vert_off + obj_begin, face_off + obj_begin, verts4, faces4, nacc);
   }
-  MVR_LAUNCH(geom_finish_normals_kernel, (unsigned)((nv + tb - 1) / tb), tb, 0, st, nacc + 3 * vert_begin, nv, verts4 + vert_begin, normals4 + vert_begin,
+  MVR_LAUNCH_PDL(geom_finish_normals_kernel, (unsigned)((nv + tb - 1) / tb), tb, 0, st, nacc + 3 * vert_begin, nv, verts4 + vert_begin, normals4 + vert_begin,
              (float4*)(base + g.xn8) + 2 * vert_begin);
   return check_launch("mvr_mesh_prepare");
 }
@@ -579,8 +583,8 @@ static void launch_shade_fast(const MeshParams& p, int B, int M, int H, int W, c
   const int tiles_x = (W + 31) / 32, tiles_y = (H + 8 * PPT - 1) / (8 * PPT);
   const dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)M, (unsigned)B);
   const int mb = shade_minb();
-  if (mb == 3) MVR_LAUNCH((mesh_shade_kernel<false, 3, PPT, VRGB>), grid, MVR_THREADS, 0, st, p, tiles_x);
-  else MVR_LAUNCH((mesh_shade_kernel<false, 4, PPT, VRGB>), grid, MVR_THREADS, 0, st, p, tiles_x);
+  if (mb == 3) MVR_LAUNCH_PDL((mesh_shade_kernel<false, 3, PPT, VRGB>), grid, MVR_THREADS, 0, st, p, tiles_x);
+  else MVR_LAUNCH_PDL((mesh_shade_kernel<false, 4, PPT, VRGB>), grid, MVR_THREADS, 0, st, p, tiles_x);
 }
 extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const int* face_off, int B, int M,
                                 int64_t total_verts, int64_t total_faces, int max_verts, int max_faces,
@@ -664,17 +668,17 @@ extern "C" int mvr_mesh_forward(const void* geometry, const int* vert_off, const
     p.layer = k;
     if (chunks_per_view > 0) {
       const dim3 scatter_grid((unsigned)chunks_per_view, (unsigned)M, (unsigned)B);
-      if (soft_raster) MVR_LAUNCH((mesh_scatter_kernel<3, true>), scatter_grid, MVR_THREADS, tab_smem, st, p);
-      else if (scatter_nt(max_faces) == 128) { MeshParams q = p; q.wcap = p.wcap < SC_QCAP ? p.wcap : SC_QCAP / 2; MVR_LAUNCH((mesh_scatter_kernel<8, false, 128>), scatter_grid, 128, tab_smem, st, q); }
-      else if (scatter_minb() == 3) MVR_LAUNCH((mesh_scatter_kernel<3, false>), scatter_grid, MVR_THREADS, tab_smem, st, p);
-      else MVR_LAUNCH((mesh_scatter_kernel<4, false>), scatter_grid, MVR_THREADS, tab_smem, st, p);
+      if (soft_raster) MVR_LAUNCH_PDL((mesh_scatter_kernel<3, true>), scatter_grid, MVR_THREADS, tab_smem, st, p);
+      else if (scatter_nt(max_faces) == 128) { MeshParams q = p; q.wcap = p.wcap < SC_QCAP ? p.wcap : SC_QCAP / 2; MVR_LAUNCH_PDL((mesh_scatter_kernel<8, false, 128>), scatter_grid, 128, tab_smem, st, q); }
+      else if (scatter_minb() == 3) MVR_LAUNCH_PDL((mesh_scatter_kernel<3, false>), scatter_grid, MVR_THREADS, tab_smem, st, p);
+      else MVR_LAUNCH_PDL((mesh_scatter_kernel<4, false>), scatter_grid, MVR_THREADS, tab_smem, st, p);
       rc = check_launch("mesh_scatter_kernel");
       if (rc) return rc;
     }
     const bool vrgb = flags & MVR_RGB_PER_ELEMENT;
     if (zbuf || bary || dists) {
-      if (vrgb) MVR_LAUNCH((mesh_shade_kernel<true, 3, 1, true>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
-      else MVR_LAUNCH((mesh_shade_kernel<true, 3, 1, false>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+      if (vrgb) MVR_LAUNCH_PDL((mesh_shade_kernel<true, 3, 1, true>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
+      else MVR_LAUNCH_PDL((mesh_shade_kernel<true, 3, 1, false>), shade_grid, MVR_THREADS, 0, st, p, tiles_x);
     } else if (vrgb) launch_shade_fast<4, true>(p, B, M, H, W, st);
     else if (shade_ppt() == 4) launch_shade_fast<4, false>(p, B, M, H, W, st);
     else if (shade_ppt() == 2) launch_shade_fast<2, false>(p, B, M, H, W, st);

@@ -92,6 +92,7 @@ __device__ __forceinline__ void shade_clipped_pixel(const MeshParams& p, int b, 
 // grid: one CTA per view, striding over its pixels (the common case is "flag down": N tiny CTAs that exit at once).
 // Writes EVERY output of a pixel whose winning face straddles the plane (mesh_shade_kernel left it untouched).
 __global__ void __launch_bounds__(MVR_THREADS) mesh_shade_clipped_kernel(const MeshParams p) {
+  pdl_enter();
   if (!may_clip(p.wsflags)) return;
   const int n = blockIdx.x, b = n / p.M, m = n - b * p.M;
   const int HW = p.H * p.W;
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_backward_finish_kernel(const
                                                                            float* __restrict__ gT, float* __restrict__ gC) {
   __shared__ double s_sum[MVR_THREADS];
   __shared__ float s_red[(MVR_THREADS / 32) * 16];
+  pdl_enter();
   const int n = blockIdx.x, tid = threadIdx.x;
   const bool clip = may_clip(p.wsflags);      // block-uniform
   if (clip) {
@@ -273,11 +275,11 @@ __global__ void __launch_bounds__(MVR_THREADS) mesh_backward_finish_kernel(const
 using namespace mvr;
 
 int launch_mesh_shade_clipped(const MeshParams& p, int N, cudaStream_t st) {
-  MVR_LAUNCH(mesh_shade_clipped_kernel, (unsigned)N, MVR_THREADS, 0, st, p);
+  MVR_LAUNCH_PDL(mesh_shade_clipped_kernel, (unsigned)N, MVR_THREADS, 0, st, p);
   return check_launch("mesh_shade_clipped_kernel");
 }
 
 int launch_mesh_backward_finish(const MeshBwdParams& p, int N, float* gR, float* gT, float* gC, cudaStream_t st) {
-  MVR_LAUNCH(mesh_backward_finish_kernel, (unsigned)N, MVR_THREADS, 0, st, p, gR, gT, gC);
+  MVR_LAUNCH_PDL(mesh_backward_finish_kernel, (unsigned)N, MVR_THREADS, 0, st, p, gR, gT, gC);
   return check_launch("mesh_backward_finish_kernel");
 }

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <condition_variable>
 #include <mutex>
@@ -62,6 +63,14 @@ void prof_end(const char* name, cudaStream_t st) {
   if (strncmp(name, g_prof_name, strlen(g_prof_name)) != 0 || g_prof_used + 2 > (int)g_prof_events.size()) return;
   cudaEventRecord(g_prof_events[g_prof_used + 1], st);
   g_prof_used += 2;
+}
+
+bool pdl_enabled(cudaStream_t st) {
+  static const bool on = [] { const char* e = getenv("MVR_PDL"); return !(e && e[0] == '0'); }();      // on unless MVR_PDL=0
+  if (!on) return false;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs == cudaStreamCaptureStatusNone;
 }
 
 }  // namespace mvr
