@@ -221,6 +221,7 @@ __device__ __forceinline__ void scatter_vertex_grads(const MeshBwdParams& p, int
 // cotangent one dot product -- six registers and ~13 floating-point instructions less per covered pixel.
 template <int MINB, bool VRGB, bool GV>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel(const MeshBwdParams p) {
+  pdl_enter();
   const int tid = threadIdx.x;
   // grid: x = 32x32-pixel tiles, y = view m, z = object b; thread (lane, warp) owns pixels (x0+lane, y0+warp+8j)
   const int b = blockIdx.z, m = blockIdx.y, n = b * p.M + m, cta = blockIdx.x;
@@ -301,6 +302,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <int MINB, bool VRGB, bool GV>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) mesh_backward_kernel_strip(const MeshBwdParams p) {
+  pdl_enter();
   // Every WARP stages its own pixels: the four 8x4-pixel blocks it owns in a 32x32 tile (128 pixels x 4 planes = 2 KB per
   // stage, two stages), one 16-byte cp.async per lane and plane -- so the pipeline needs __syncwarp only.  The kernel has
   // no CTA barrier at all: a warp whose blocks are background runs ahead through the strip instead of waiting for the
@@ -470,19 +472,19 @@ static int mesh_backward_impl(const void* geometry, const int* vert_off, const i
     p.parts_per_view = ((H + 31) / 32) * NWARPS;      // one partial per warp of every tile ROW
     const dim3 sgrid((unsigned)((H + 31) / 32), (unsigned)M, (unsigned)B);
     if (gv) {      // vertex gradients: the variant with the warp-aggregated atomic scatter (its 18 extra live values cost occupancy)
-      if (vrgb) MVR_LAUNCH((mesh_backward_kernel_strip<2, true, true>), sgrid, MVR_THREADS, 0, st, p);
-      else MVR_LAUNCH((mesh_backward_kernel_strip<2, false, true>), sgrid, MVR_THREADS, 0, st, p);
+      if (vrgb) MVR_LAUNCH_PDL((mesh_backward_kernel_strip<2, true, true>), sgrid, MVR_THREADS, 0, st, p);
+      else MVR_LAUNCH_PDL((mesh_backward_kernel_strip<2, false, true>), sgrid, MVR_THREADS, 0, st, p);
     }
-    else if (vrgb) MVR_LAUNCH((mesh_backward_kernel_strip<3, true, false>), sgrid, MVR_THREADS, 0, st, p);
-    else if (backward_minb() == 4) MVR_LAUNCH((mesh_backward_kernel_strip<4, false, false>), sgrid, MVR_THREADS, 0, st, p);      // profiling knobs
-    else if (backward_minb() == 2) MVR_LAUNCH((mesh_backward_kernel_strip<2, false, false>), sgrid, MVR_THREADS, 0, st, p);
-    else MVR_LAUNCH((mesh_backward_kernel_strip<3, false, false>), sgrid, MVR_THREADS, 0, st, p);
+    else if (vrgb) MVR_LAUNCH_PDL((mesh_backward_kernel_strip<3, true, false>), sgrid, MVR_THREADS, 0, st, p);
+    else if (backward_minb() == 4) MVR_LAUNCH_PDL((mesh_backward_kernel_strip<4, false, false>), sgrid, MVR_THREADS, 0, st, p);      // profiling knobs
+    else if (backward_minb() == 2) MVR_LAUNCH_PDL((mesh_backward_kernel_strip<2, false, false>), sgrid, MVR_THREADS, 0, st, p);
+    else MVR_LAUNCH_PDL((mesh_backward_kernel_strip<3, false, false>), sgrid, MVR_THREADS, 0, st, p);
   }
-  else if (gv) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<2, true, true>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<2, false, true>), bgrid, MVR_THREADS, 0, st, p); }
-  else if (backward_minb() == 2) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<2, true, false>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<2, false, false>), bgrid, MVR_THREADS, 0, st, p); }
-  else if (backward_minb() == 4) { if (vrgb) MVR_LAUNCH((mesh_backward_kernel<4, true, false>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH((mesh_backward_kernel<4, false, false>), bgrid, MVR_THREADS, 0, st, p); }
-  else if (vrgb) MVR_LAUNCH((mesh_backward_kernel<3, true, false>), bgrid, MVR_THREADS, 0, st, p);
-  else MVR_LAUNCH((mesh_backward_kernel<3, false, false>), bgrid, MVR_THREADS, 0, st, p);
+  else if (gv) { if (vrgb) MVR_LAUNCH_PDL((mesh_backward_kernel<2, true, true>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH_PDL((mesh_backward_kernel<2, false, true>), bgrid, MVR_THREADS, 0, st, p); }
+  else if (backward_minb() == 2) { if (vrgb) MVR_LAUNCH_PDL((mesh_backward_kernel<2, true, false>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH_PDL((mesh_backward_kernel<2, false, false>), bgrid, MVR_THREADS, 0, st, p); }
+  else if (backward_minb() == 4) { if (vrgb) MVR_LAUNCH_PDL((mesh_backward_kernel<4, true, false>), bgrid, MVR_THREADS, 0, st, p); else MVR_LAUNCH_PDL((mesh_backward_kernel<4, false, false>), bgrid, MVR_THREADS, 0, st, p); }
+  else if (vrgb) MVR_LAUNCH_PDL((mesh_backward_kernel<3, true, false>), bgrid, MVR_THREADS, 0, st, p);
+  else MVR_LAUNCH_PDL((mesh_backward_kernel<3, false, false>), bgrid, MVR_THREADS, 0, st, p);
   rc = check_launch("mesh_backward_kernel");
   if (rc) return rc;
   // clipped-face pixels (if any) + the fixed-order sum of the per-warp partials -> gR, gT, gC

@@ -478,6 +478,7 @@ __device__ __forceinline__ void insert_key_smem(unsigned long long* s_keys, int 
 // MINB: minimum CTAs per SM for the register allocator; 0 = unconstrained
 template <int KT, int MINB>
 __global__ void __launch_bounds__(MVR_THREADS, MINB) points_tile_kernel(const PointsParams p) {
+  pdl_enter();
   extern __shared__ unsigned long long s_keys[];              // [KT][1024]
   __shared__ unsigned int s_cand[PT_QCAP];                    // local point << 10 | local pixel
   __shared__ unsigned long long s_key[MVR_THREADS];
@@ -919,6 +920,7 @@ __global__ void __launch_bounds__(MVR_THREADS) points_backward_kernel(const Poin
 __global__ void points_backward_reduce_kernel(const float* __restrict__ partials, int N, int n_parts,
                                               float* __restrict__ gR, float* __restrict__ gT, float* __restrict__ gs,
                                               const float* __restrict__ scale, int flags, float* __restrict__ grad_rgb_uniform) {
+  pdl_enter();
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -946,6 +948,7 @@ __global__ void points_backward_reduce_angles_kernel(const float* __restrict__ p
                                                      const float* __restrict__ elev, const float* __restrict__ dist, float* __restrict__ gR,
                                                      float* __restrict__ gT, float* __restrict__ g_azim, float* __restrict__ g_elev,
                                                      float* __restrict__ g_dist, float* __restrict__ grad_rgb_uniform) {
+  pdl_enter();
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -1130,19 +1133,19 @@ extern "C" int mvr_points_forward(const float* points, const float* rgb, int B, 
       // left alone (MINB = 0), K = 4 is held to five CTAs per SM (48 registers instead of 56, no spills: 0.131 vs 0.133 ms),
       // K = 8 to three (74 KB of shared memory per CTA).
       case 1:
-        if (points_tile_minb_k1() == 5) MVR_LAUNCH((points_tile_kernel<1, 5>), tile_grid, MVR_THREADS, smem, st, p);
-        else MVR_LAUNCH((points_tile_kernel<1, 0>), tile_grid, MVR_THREADS, smem, st, p);
+        if (points_tile_minb_k1() == 5) MVR_LAUNCH_PDL((points_tile_kernel<1, 5>), tile_grid, MVR_THREADS, smem, st, p);
+        else MVR_LAUNCH_PDL((points_tile_kernel<1, 0>), tile_grid, MVR_THREADS, smem, st, p);
         break;
-      case 2: MVR_LAUNCH((points_tile_kernel<2, 0>), tile_grid, MVR_THREADS, smem, st, p); break;
+      case 2: MVR_LAUNCH_PDL((points_tile_kernel<2, 0>), tile_grid, MVR_THREADS, smem, st, p); break;
       case 4:
-        if (points_tile_minb() == 4) MVR_LAUNCH((points_tile_kernel<4, 0>), tile_grid, MVR_THREADS, smem, st, p);
-        else MVR_LAUNCH((points_tile_kernel<4, 5>), tile_grid, MVR_THREADS, smem, st, p);
+        if (points_tile_minb() == 4) MVR_LAUNCH_PDL((points_tile_kernel<4, 0>), tile_grid, MVR_THREADS, smem, st, p);
+        else MVR_LAUNCH_PDL((points_tile_kernel<4, 5>), tile_grid, MVR_THREADS, smem, st, p);
         break;
       default: {
         // 64 KB of dynamic shared memory needs the opt-in (per device; the call is a few hundred nanoseconds)
         e = cudaFuncSetAttribute(points_tile_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("mvr_points_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        MVR_LAUNCH((points_tile_kernel<8, 3>), tile_grid, MVR_THREADS, smem, st, p);
+        MVR_LAUNCH_PDL((points_tile_kernel<8, 3>), tile_grid, MVR_THREADS, smem, st, p);
       }
     }
     return check_launch("points_tile_kernel");
@@ -1221,11 +1224,11 @@ static int points_backward_impl(const float* points, const float* rgb, int B, in
   if (rc) return rc;
   const int wpb = 8;
   if (angles) {
-    MVR_LAUNCH(points_backward_reduce_angles_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, p.ctas_per_view,
+    MVR_LAUNCH_PDL(points_backward_reduce_angles_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, p.ctas_per_view,
                azim, elev, inv_dist, gR, gT, g_azim, g_elev, g_dist, gu ? grad_rgb : (float*)nullptr);
     return check_launch("points_backward_reduce_angles_kernel");
   }
-  MVR_LAUNCH(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, p.ctas_per_view, gR, gT, g_inv_dist, inv_dist, flags,
+  MVR_LAUNCH_PDL(points_backward_reduce_kernel, (unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st, (const float*)p.partials, (int)N, p.ctas_per_view, gR, gT, g_inv_dist, inv_dist, flags,
              gu ? grad_rgb : (float*)nullptr);
   return check_launch("points_backward_reduce_kernel");
 }
