@@ -472,6 +472,7 @@ class PackedMeshes:
     verts_normals_packed() (renderer.py:67-77); can be cached across iterations."""
 
     _pending = None
+    _inflight = None      # the instance whose staging job is running on the library's thread (at most one)
 
     def __init__(self, verts: Sequence[torch.Tensor], faces: Sequence[torch.Tensor], device,
                  vert_rgb: Optional[torch.Tensor] = None):
@@ -511,7 +512,12 @@ class PackedMeshes:
         if defer:
             self._pending = ("deferred", list(verts), list(faces), device, vert_rgb)
             return
+        if overlap and PackedMeshes._inflight is not None:
+            # one staging thread and one set of pinned buffers: a batch that is still in flight is completed before the next one starts
+            PackedMeshes._inflight.finish()
         self._pending = self._stage(verts, faces, device, vert_rgb, overlap)
+        if self._pending[6] is not None:      # (a job id: the gather runs on the library's thread until finish() joins it)
+            PackedMeshes._inflight = self
 
     @staticmethod
     def _stage(verts, faces, device, vert_rgb, overlap):
@@ -558,6 +564,8 @@ class PackedMeshes:
                     self.finish_chunk(i)
             return self
         pending, self._pending = self._pending, None
+        if PackedMeshes._inflight is self:
+            PackedMeshes._inflight = None
         if pending[0] == "deferred":
             _, verts, faces, device, vert_rgb = pending
             pending = self._stage(verts, faces, device, vert_rgb, overlap=False)

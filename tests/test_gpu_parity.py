@@ -1516,3 +1516,27 @@ def test_mesh_from_angles_fused_backward_equals_the_two_node_chain(cuda_device):
         img4 = img4[0] if isinstance(img4, tuple) else img4
         ((img4 * cot).sum() + T4.sum() + C4.sum()).backward()
         assert torch.allclose(a3.grad, a4.grad, rtol=1e-5, atol=1e-6) and torch.allclose(d3.grad, d4.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_two_overlapped_staging_jobs_do_not_share_buffers(cuda_device):
+    """PackedMeshes.begin(overlap=True) twice before either finish(): one staging thread and one set of pinned buffers, so the second
+    begin completes the first batch before it starts its own; both batches come out like the already-packed device arrays."""
+    dev = cuda_device
+    sets = [[synth.make_mesh(nf, 120 + i) for i, nf in enumerate((900, 4000, 150))], [synth.make_mesh(nf, 130 + i) for i, nf in enumerate((2500, 60))]]
+    col = torch.tensor([0.8, 0.7, 0.6], device=dev); lt = torch.tensor([[0.0, 1.0, 0.3]], device=dev)
+
+    def shot(gm):
+        v = [t.to(dev) for t in synth.learned_spherical_views(gm.B, 2, 5)]
+        with torch.no_grad():
+            return ops.render_meshes_from_angles(gm, 2, v[0], v[1], v[2], lt, col, col * 0.5, 40)[0]
+    for _ in range(3):
+        a = ops.PackedMeshes.begin([v for v, _ in sets[0]], [f for _, f in sets[0]], dev, overlap=True)
+        b = ops.PackedMeshes.begin([v for v, _ in sets[1]], [f for _, f in sets[1]], dev, overlap=True)
+        assert a._pending is None and ops.PackedMeshes._inflight is b      # a was completed by b's begin
+        imgs = [shot(b), shot(a)]                                           # (the node finishes b)
+        assert ops.PackedMeshes._inflight is None
+        for gm, ms, img in ((b, sets[1], imgs[0]), (a, sets[0], imgs[1])):
+            ref = ops.PackedMeshes.from_packed(torch.cat([v for v, _ in ms]).to(dev), torch.cat([f for _, f in ms]).to(dev),
+                                               [v.shape[0] for v, _ in ms], [f.shape[0] for _, f in ms])
+            assert torch.equal(img, shot(ref)) and float(img.std()) > 0
