@@ -30,6 +30,37 @@ def test_library_exports_every_declared_symbol():
     assert set(names) == set(_lib.SIGNATURES), "ctypes signatures and header declarations differ"
 
 
+def test_ctypes_signatures_follow_the_header_argument_by_argument():
+    """Every prototype of include/mvr_b200.h against mvtn_b200/_lib.py SIGNATURES: same number of arguments, and each argument in
+    the same class (pointer / int / int64 / size_t / float / double / uint32) -- a swapped or missing argument in the hand-written
+    ctypes table would otherwise only show up as garbage on the GPU."""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, "include", "mvr_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(mvr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert {p[1] for p in protos} == set(_lib.SIGNATURES)
+    scalar = {"int": "int", "int64_t": "i64", "long long": "i64", "size_t": "size", "float": "f32", "double": "f64", "uint32_t": "u32"}
+
+    def header_class(param):
+        param = param.strip()
+        if param in ("void", ""):
+            return None
+        if "*" in param:
+            return "ptr"
+        ctype = re.sub(r"\b[a-zA-Z_][a-zA-Z0-9_]*$", "", param).replace("const", "").strip()      # drop the parameter name
+        return scalar[ctype]
+
+    def ctypes_class(t):
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents"):
+            return "ptr"
+        return {C.c_int: "int", C.c_int64: "i64", C.c_size_t: "size", C.c_float: "f32", C.c_double: "f64", C.c_uint32: "u32"}[t]
+
+    for _ret, name, args in protos:
+        want = [c for c in (header_class(a) for a in args.split(",")) if c is not None]
+        got = [ctypes_class(t) for t in _lib.SIGNATURES[name][1]]
+        assert want == got, f"{name}: header {want} != ctypes {got}"
+
+
 def test_library_loads_and_answers_host_queries():
     lib = _lib.load()
     assert lib.mvr_abi_version() == _lib.ABI_VERSION
