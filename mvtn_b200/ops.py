@@ -247,9 +247,10 @@ def fov_projection_scale(fov_deg: float = 60.0, znear: float = 1.0, aspect: floa
 # cameras
 # --------------------------------------------------------------------------------------------------
 class FlagSink:
-    """Where the rotation-validity flag of a look_at launch lands on the host: a pinned word + an event the LIBRARY records behind
-    its copy (mvr_look_at_forward_flagged), so the caller neither issues a copy nor records an event in front of the rasterizer
-    launch.  read() waits for that event only -- i.e. for the camera kernel, not for the rasterizer behind it.  Pooled per device."""
+    """Where the rotation-validity flag of a look_at launch lands on the host: a pinned word the camera kernel stores the count
+    into (up to 4096 views; an asynchronous copy above) + an event the LIBRARY records behind it (mvr_look_at_forward_flagged), so
+    the caller neither issues a copy nor records an event in front of the rasterizer launch.  read() waits for that event only --
+    i.e. for the camera kernel, not for the rasterizer behind it.  Pooled per device."""
     _pool = {}
 
     def __init__(self, device):
